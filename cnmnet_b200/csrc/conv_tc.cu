@@ -1,0 +1,459 @@
+// K2: convolution + folded BatchNorm + ReLU as a persistent, warp-specialised implicit GEMM on
+// the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// Reference semantics: nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU and the torch.cat of the
+// inputs (depthnet/depthNet_model.py:19-112, 235-261, 335-365).
+//
+// GEMM view      D[M = N*Ho*Wo pixels, Cout] = sum over K-steps of A_step[M, chunk] * W_step[Cout, chunk]^T
+// K-step         = (source tensor, parity sub-image, tap shift (dx,dy), channel chunk c0); listed by
+//                  the host, so concatenated inputs, taps and stride 2 are all the same loop.
+// A operand      one 4-D TMA box {chunk ch, TW, TH, NB} (TW*TH*NB = 128 pixels) of the NHWC source at
+//                  the shifted tile origin; out-of-image pixels are zero-filled by TMA (= conv padding).
+//                  The box lands in smem as 128 rows x 128 B, 128B-swizzled = a K-major UMMA tile.
+// B operand      2-D TMA box {chunk, BN} of the packed weights [Cout, K] (BN folded), same layout.
+// MMA            tcgen05.mma cta_group::1, M = 128, N = BN, K = 32 bytes per instruction
+//                  (kind::f16: 16 x bf16, kind::tf32: 8 x tf32); fp32 accumulators in TMEM, two
+//                  accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogue       4 warps: tcgen05.ld -> + bias -> ReLU -> cast -> swizzled smem -> TMA store into a
+//                  channel slice of the NHWC output (TMA clips partial tiles).
+// Warp roles     warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM
+//                  allocator, warp 3 idle, warps 4-7 = epilogue (TMEM lane quarter = warp - 4).
+#include <cuda.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cnm {
+
+int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* srcs, const void* steps, const void* wp,
+                    const void* out);
+
+constexpr int TC_MAX_SRCS = 3;
+constexpr int TC_A_BYTES = 128 * 128;  // 128 pixels x 128 B
+constexpr int TC_THREADS = 256;
+
+struct alignas(64) TcParams {
+  CUtensorMap a_maps[TC_MAX_SRCS * 4];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  const cnm_conv_step* steps;
+  const float* bias;
+  int num_steps;
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int TW, TH, NB;
+  int relu;
+  int c_out_offset;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (TF32)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, 128B-swizzled smem tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3ffff) >> 4) | ((uint64_t)1 << 16) /* LBO (unused when swizzled) */ |
+         ((uint64_t)(1024 >> 4) << 32) /* SBO */ | ((uint64_t)1 << 46) /* sm100 descriptor version */ |
+         ((uint64_t)2 << 61) /* SWIZZLE_128B */;
+}
+
+template <int BN, int STAGES, bool TF32>
+struct TcSmem {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = 2 * TC_A_BYTES;  // double-buffered 128 x 128 B staging
+  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BIAS = OFF_OUT + OUT_BYTES;
+  static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + slack for manual 1024 B alignment
+};
+
+template <int BN, int STAGES, bool TF32>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  using L = TcSmem<BN, STAGES, TF32>;
+  constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;  // accumulator columns per 128-byte output row
+  constexpr int CHUNK_CH = TF32 ? 32 : 64;        // channels per K-step
+  constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
+  constexpr uint32_t TMEM_COLS = 2 * BN;          // 128 / 256 / 512: powers of two >= 32
+  constexpr uint32_t IDESC = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + L::OFF_BAR;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TMEM);
+  float* bias_s = reinterpret_cast<float*>(base_ptr + L::OFF_BIAS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.out_map);
+    tma_prefetch_desc(&p.a_maps[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L::OFF_TMEM),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int m = tile / p.tiles_n;
+        const int x0 = (m % p.tiles_x) * p.TW;
+        m /= p.tiles_x;
+        const int y0 = (m % p.tiles_y) * p.TH;
+        const int n0 = (m / p.tiles_y) * p.NB;
+        for (int ks = 0; ks < p.num_steps; ++ks) {
+          const int4 st = __ldg(reinterpret_cast<const int4*>(p.steps + ks));  // src, sub, dx, dy
+          const int c0 = __ldg(&p.steps[ks].c0);
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          const uint32_t sa = base + stage * L::STAGE_BYTES;
+          tma_load_4d(sa, &p.a_maps[st.x * 4 + st.y], full_bar(stage), c0, x0 + st.z, y0 + st.w, n0);
+          tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), ks * CHUNK_CH, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int ks = 0; ks < p.num_steps; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * L::STAGE_BYTES;
+          const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x 32 B along K inside the 128 B swizzle row
+            tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (ks | k) ? 1u : 0u);
+          tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(as));  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;               // TMEM lane quarter
+    const int row = q * 32 + lane;        // pixel row of the tile handled by this thread
+    const int et = threadIdx.x - 128;     // 0..127
+    const bool leader = (et == 0);
+    int it = 0;
+    uint32_t chunk_counter = 0;
+    int bias_tile = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.tiles_n;
+      int m = tile / p.tiles_n;
+      const int x0 = (m % p.tiles_x) * p.TW;
+      m /= p.tiles_x;
+      const int y0 = (m % p.tiles_y) * p.TH;
+      const int n0 = (m / p.tiles_y) * p.NB;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      if (bias_tile != nt) {
+        epi_bar();  // previous tile's bias reads are done
+        for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
+        bias_tile = nt;
+        // visibility is ordered by the epi_bar() inside the chunk loop below
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < NUM_CHUNKS; ++ch, ++chunk_counter) {
+        const uint32_t buf = chunk_counter & 1;
+        uint8_t* stg = base_ptr + L::OFF_OUT + buf * TC_A_BYTES;
+        // the TMA store that last read this staging buffer (two chunks ago) must have finished reading
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        epi_bar();
+        uint32_t v[COLS_PER_CHUNK];
+        tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
+        if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
+        tmem_ld_wait();
+        const float* bs = bias_s + ch * COLS_PER_CHUNK;
+        uint8_t* rowp = stg + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 8 x 16 B per output row, 128B-swizzled like the TMA box
+          uint4 o;
+          if (TF32) {
+            float f[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
+              if (p.relu) t = fmaxf(t, 0.0f);
+              uint32_t r;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t));  // store tf32-rounded activations
+              f[e] = __uint_as_float(r);
+            }
+            o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+          } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
+              float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
+              if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
+              w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            o = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
+        epi_bar();
+        if (leader) {
+          tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + nt * BN + ch * CHUNK_CH, x0, y0, n0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));  // 128 arrivals release the accumulator stage
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CNM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gd[5];
+  cuuint64_t gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(map, dtype == CNM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                   (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CNM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return CNM_OK;
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int BN, int STAGES, bool TF32>
+static int launch_tc(const TcParams& p, int grid, cudaStream_t s) {
+  using L = TcSmem<BN, STAGES, TF32>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::TOTAL);
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_tc_kernel<BN, STAGES, TF32><<<grid, TC_THREADS, L::TOTAL, s>>>(p);
+  return after_launch("cnm_conv2d_tc");
+}
+
+}  // namespace cnm
+
+using namespace cnm;
+
+extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, const cnm_conv_step* steps,
+                             const void* wp, const float* bias, void* out, void* stream) {
+  int rc = check_conv_args("cnm_conv2d_tc", d, srcs, steps, wp, out);
+  if (rc) return rc;
+  const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
+  CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_tc: Cout=%d must be a multiple of 64", d->Cout);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  // pixel tile: TW x TH x NB = 128
+  p.TW = d->Wo >= 16 ? 16 : 8;
+  const int rows = 128 / p.TW;
+  p.TH = next_pow2(d->Ho) < rows ? next_pow2(d->Ho) : rows;
+  p.NB = 128 / (p.TW * p.TH);
+  p.tiles_x = (d->Wo + p.TW - 1) / p.TW;
+  p.tiles_y = (d->Ho + p.TH - 1) / p.TH;
+  p.tiles_b = (d->N + p.NB - 1) / p.NB;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  int BN = 64;
+  if (d->Cout % 256 == 0 && m_tiles * (d->Cout / 256) >= 148) BN = 256;
+  else if (d->Cout % 128 == 0 && m_tiles * (d->Cout / 128) >= 148) BN = 128;
+  else if (d->Cout % 256 == 0 && m_tiles * (d->Cout / 64) > 4 * 148) BN = 256;
+  p.tiles_n = d->Cout / BN;
+  p.steps = steps;
+  p.bias = bias;
+  p.num_steps = d->num_steps;
+  p.relu = d->relu;
+  p.c_out_offset = d->c_out_offset;
+
+  const uint32_t box[4] = {(uint32_t)ch, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.NB};
+  for (int i = 0; i < d->num_srcs; ++i) {
+    const cnm_conv_src& s = srcs[i];
+    const uint64_t pix = (uint64_t)s.C * eb;
+    if (d->stride == 1) {
+      const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)d->N};
+      const uint64_t str[3] = {pix, pix * s.W, pix * s.W * s.H};
+      rc = encode_map(&p.a_maps[i * 4], d->dtype, 4, s.ptr, dims, str, box);
+      if (rc) return rc;
+    } else {
+      for (int sub = 0; sub < 4; ++sub) {
+        const int py = sub >> 1, px = sub & 1;
+        const int ws = (s.W - px + 1) / 2, hs = (s.H - py + 1) / 2;
+        if (ws <= 0 || hs <= 0) continue;
+        const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)ws, (uint64_t)hs, (uint64_t)d->N};
+        const uint64_t str[3] = {2 * pix, 2 * pix * s.W, pix * s.W * s.H};
+        const uint8_t* ptr = (const uint8_t*)s.ptr + ((uint64_t)py * s.W + px) * pix;
+        rc = encode_map(&p.a_maps[i * 4 + sub], d->dtype, 4, ptr, dims, str, box);
+        if (rc) return rc;
+      }
+    }
+  }
+  {
+    const uint64_t K = (uint64_t)d->num_steps * ch;
+    const uint64_t dims[2] = {K, (uint64_t)d->Cout};
+    const uint64_t str[1] = {K * eb};
+    const uint32_t bbox[2] = {(uint32_t)ch, (uint32_t)BN};
+    rc = encode_map(&p.b_map, d->dtype, 2, wp, dims, str, bbox);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t pix = (uint64_t)d->c_out_total * eb;
+    const uint64_t dims[4] = {(uint64_t)d->c_out_total, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    const uint64_t str[3] = {pix, pix * d->Wo, pix * d->Wo * d->Ho};
+    rc = encode_map(&p.out_map, d->dtype, 4, out, dims, str, box);
+    if (rc) return rc;
+  }
+  const int total = m_tiles * p.tiles_n;
+  const int grid = total < 148 ? total : 148;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tf32 = d->dtype == CNM_TF32;
+  if (BN == 256) return tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
+  if (BN == 128) return tf32 ? launch_tc<128, 6, true>(p, grid, s) : launch_tc<128, 6, false>(p, grid, s);
+  return tf32 ? launch_tc<64, 8, true>(p, grid, s) : launch_tc<64, 8, false>(p, grid, s);
+}

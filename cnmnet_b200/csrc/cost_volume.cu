@@ -1,0 +1,245 @@
+// K1: camera pre-processing, source repack and the fused plane-sweep cost volume.
+//
+// Reference semantics: depthnet/depth_util.py:13-56 (process_camera_parameters),
+// depthnet/depthNet_model.py:185-224 (getVolume: 64 x {mul, add, div, grid_sample, abs, sum}).
+// Here: one launch for all (view, batch) pairs and all planes; the warped volume never exists.
+//
+// Data layout in HBM
+//   ref      [B,3,H,W] fp32 (public NCHW), read once per (pair, plane group)
+//   texels   [P][H+3][W+4] float4 = (r,g,b,0): source views repacked pixel-interleaved with a
+//            zero border at row/col -1 and two trailing rows/cols, so that after clamping the
+//            sample position to [-1, W] x [-1, H] every bilinear tap is an unpredicated 16 B
+//            load and grid_sample's zeros padding falls out of the border texels.
+//   out      NCHW fp32 [P,D,H,W] (parity layout) or act [P,H,W,D] bf16/fp32 (conv1.0 operand)
+#include "common.cuh"
+
+namespace cnm {
+
+// ---------------------------------------------------------------------------------------------
+// camera pre-processing: one thread per (view, batch) pair, fp64
+// ---------------------------------------------------------------------------------------------
+__device__ bool invert_n(double* a, double* inv, int n) {
+  // Gauss-Jordan with partial pivoting on an n x n row-major matrix (n <= 4)
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) inv[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    double best = fabs(a[c * n + c]);
+    for (int r = c + 1; r < n; ++r)
+      if (fabs(a[r * n + c]) > best) { best = fabs(a[r * n + c]); piv = r; }
+    if (best == 0.0) return false;
+    if (piv != c)
+      for (int j = 0; j < n; ++j) {
+        double t = a[c * n + j]; a[c * n + j] = a[piv * n + j]; a[piv * n + j] = t;
+        t = inv[c * n + j]; inv[c * n + j] = inv[piv * n + j]; inv[piv * n + j] = t;
+      }
+    double d = 1.0 / a[c * n + c];
+    for (int j = 0; j < n; ++j) { a[c * n + j] *= d; inv[c * n + j] *= d; }
+    for (int r = 0; r < n; ++r) {
+      if (r == c) continue;
+      double f = a[r * n + c];
+      if (f == 0.0) continue;
+      for (int j = 0; j < n; ++j) { a[r * n + j] -= f * a[c * n + j]; inv[r * n + j] -= f * inv[c * n + j]; }
+    }
+  }
+  return true;
+}
+
+__global__ void camera_setup_kernel(const float* __restrict__ ref_cam, const float* __restrict__ src_cam,
+                                    float* __restrict__ hk, int B, int V) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B * V) return;
+  int b = p % B;
+  const float* rc = ref_cam + (size_t)b * 32;
+  const float* sc = src_cam + (size_t)p * 32;
+  double Er[16], Eri[16], Es[16], Kr[9], Kri[9], Ks[9];
+  for (int i = 0; i < 16; ++i) { Er[i] = rc[i]; Es[i] = sc[i]; }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) { Kr[i * 3 + j] = rc[16 + i * 4 + j]; Ks[i * 3 + j] = sc[16 + i * 4 + j]; }
+  bool ok = invert_n(Er, Eri, 4);
+  ok = invert_n(Kr, Kri, 3) && ok;
+  double T[16];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += Es[i * 4 + k] * Eri[k * 4 + j];
+      T[i * 4 + j] = s;
+    }
+  double RK[9];  // R * Kr^-1
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += T[i * 4 + k] * Kri[k * 3 + j];
+      RK[i * 3 + j] = s;
+    }
+  float* o = hk + (size_t)p * 12;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += Ks[i * 3 + k] * RK[k * 3 + j];
+      o[i * 3 + j] = (float)(ok ? s : nan);
+    }
+    double s = 0;
+    for (int k = 0; k < 3; ++k) s += Ks[i * 3 + k] * T[k * 4 + 3];
+    o[9 + i] = (float)(ok ? s : nan);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// source repack: NCHW planar -> zero-bordered pixel-interleaved float4
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_source_kernel(const float* __restrict__ src, float4* __restrict__ tex, int N, int H, int W) {
+  const int pitch = W + 4, rows = H + 3;
+  size_t total = (size_t)N * rows * pitch;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int xx = (int)(i % pitch);
+    size_t t = i / pitch;
+    int yy = (int)(t % rows);
+    int n = (int)(t / rows);
+    int x = xx - 1, y = yy - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+      const float* s = src + (size_t)n * 3 * H * W + (size_t)y * W + x;
+      v.x = __ldg(s);
+      v.y = __ldg(s + (size_t)H * W);
+      v.z = __ldg(s + 2 * (size_t)H * W);
+    }
+    tex[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused plane sweep
+// ---------------------------------------------------------------------------------------------
+constexpr int CV_TX = 32, CV_TY = 8;
+
+template <int DPB, int LAYOUT>  // LAYOUT: 0 = NCHW fp32, 1 = act bf16, 2 = act fp32
+__global__ void __launch_bounds__(CV_TX* CV_TY)
+    cost_volume_kernel(const float* __restrict__ ref, const float4* __restrict__ tex, const float* __restrict__ hk,
+                       void* __restrict__ out, int B, int H, int W, int D, double idmin, double idstep) {
+  __shared__ float zs[DPB];
+  const int groups = D / DPB;
+  const int p = blockIdx.z / groups;
+  const int d0 = (blockIdx.z % groups) * DPB;
+  const int tid = threadIdx.y * CV_TX + threadIdx.x;
+  if (tid < DPB) zs[tid] = (float)(1.0 / (idmin + (double)(d0 + tid) * idstep));  // fp64 like the Python double
+  __syncthreads();
+
+  const int x = blockIdx.x * CV_TX + threadIdx.x;
+  const int y = blockIdx.y * CV_TY + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int b = p % B;
+  const size_t HW = (size_t)H * W;
+
+  const float* h = hk + (size_t)p * 12;
+  const float fx = (float)x, fy = (float)y;
+  // a = Hm . [x, y, 1]^T   (KRKiUV)
+  const float a0 = fmaf(__ldg(h + 0), fx, fmaf(__ldg(h + 1), fy, __ldg(h + 2)));
+  const float a1 = fmaf(__ldg(h + 3), fx, fmaf(__ldg(h + 4), fy, __ldg(h + 5)));
+  const float a2 = fmaf(__ldg(h + 6), fx, fmaf(__ldg(h + 7), fy, __ldg(h + 8)));
+  const float k0 = __ldg(h + 9), k1 = __ldg(h + 10), k2 = __ldg(h + 11) + 1e-6f;
+
+  const float* rp = ref + (size_t)b * 3 * HW + (size_t)y * W + x;
+  const float r0 = __ldg(rp), r1 = __ldg(rp + HW), r2 = __ldg(rp + 2 * HW);
+
+  const int pitch = W + 4;
+  const float4* tp = tex + (size_t)p * (H + 3) * pitch + pitch + 1;  // texel (0,0)
+  const float xmax = (float)W, ymax = (float)H;
+
+  float res[DPB];
+#pragma unroll
+  for (int i = 0; i < DPB; ++i) {
+    const float z = zs[i];
+    const float px = fmaf(a0, z, k0), py = fmaf(a1, z, k1);
+    const float den = fmaf(a2, z, k2);  // p_z + 1e-6
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(den));
+    rcp = fmaf(fmaf(-den, rcp, 1.0f), rcp, rcp);  // one Newton step: ~0.5 ulp
+    // grid_sample un-normalisation with align_corners=False: ix = u - 0.5
+    float ix = fmaf(px, rcp, -0.5f), iy = fmaf(py, rcp, -0.5f);
+    ix = fminf(fmaxf(ix, -1.0f), xmax);  // NaN -> -1 (zero border)
+    iy = fminf(fmaxf(iy, -1.0f), ymax);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx1 = ix - x0f, wy1 = iy - y0f;
+    const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    const float4* t = tp + (int)y0f * pitch + (int)x0f;
+    const float4 t00 = __ldg(t), t10 = __ldg(t + 1), t01 = __ldg(t + pitch), t11 = __ldg(t + pitch + 1);
+    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+    const float c0 = fmaf(t11.x, w11, fmaf(t01.x, w01, fmaf(t10.x, w10, t00.x * w00))) - r0;
+    const float c1 = fmaf(t11.y, w11, fmaf(t01.y, w01, fmaf(t10.y, w10, t00.y * w00))) - r1;
+    const float c2 = fmaf(t11.z, w11, fmaf(t01.z, w01, fmaf(t10.z, w10, t00.z * w00))) - r2;
+    res[i] = fabsf(c0) + fabsf(c1) + fabsf(c2);
+  }
+
+  if (LAYOUT == 0) {
+    float* o = reinterpret_cast<float*>(out) + ((size_t)p * D + d0) * HW + (size_t)y * W + x;
+#pragma unroll
+    for (int i = 0; i < DPB; ++i) __stcs(o + (size_t)i * HW, res[i]);
+  } else if (LAYOUT == 1) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + ((size_t)p * HW + (size_t)y * W + x) * D + d0;
+#pragma unroll
+    for (int i = 0; i < DPB; i += 8) Vec16<__nv_bfloat16>::store(o + i, res + i);
+  } else {
+    float* o = reinterpret_cast<float*>(out) + ((size_t)p * HW + (size_t)y * W + x) * D + d0;
+#pragma unroll
+    for (int i = 0; i < DPB; i += 4) Vec16<float>::store(o + i, res + i);
+  }
+}
+
+}  // namespace cnm
+
+using namespace cnm;
+
+extern "C" int cnm_camera_setup(const float* ref_cam, const float* src_cam, float* hk, int B, int V, void* stream) {
+  CNM_REQUIRE(ref_cam && src_cam && hk, CNM_ERR_INVALID_ARGUMENT, "cnm_camera_setup: null pointer");
+  CNM_REQUIRE(B > 0 && V > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_camera_setup: B=%d V=%d", B, V);
+  int n = B * V;
+  camera_setup_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ref_cam, src_cam, hk, B, V);
+  return after_launch("cnm_camera_setup");
+}
+
+extern "C" int64_t cnm_packed_source_bytes(int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  return (int64_t)N * (H + 3) * (W + 4) * 16;
+}
+
+extern "C" int cnm_pack_source(const float* src, void* packed, int N, int H, int W, void* stream) {
+  CNM_REQUIRE(src && packed, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: null pointer");
+  CNM_REQUIRE(N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: bad shape");
+  CNM_REQUIRE(((uintptr_t)packed & 15) == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: packed must be 16B aligned");
+  size_t total = (size_t)N * (H + 3) * (W + 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_source_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (float4*)packed, N, H, W);
+  return after_launch("cnm_pack_source");
+}
+
+extern "C" int cnm_cost_volume(const float* ref, const void* packed_src, const float* hk, void* out, int B, int V,
+                               int H, int W, int D, double idepth_min, double idepth_max, int layout, int dtype,
+                               void* stream) {
+  CNM_REQUIRE(ref && packed_src && hk && out, CNM_ERR_INVALID_ARGUMENT, "cnm_cost_volume: null pointer");
+  CNM_REQUIRE(B > 0 && V > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_cost_volume: bad shape");
+  CNM_REQUIRE(D >= 16 && D % 16 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_cost_volume: D=%d must be a multiple of 16", D);
+  CNM_REQUIRE(layout == CNM_VOLUME_NCHW_F32 || layout == CNM_VOLUME_ACT, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_cost_volume: layout %d", layout);
+  CNM_REQUIRE(((uintptr_t)packed_src & 15) == 0 && ((uintptr_t)out & 15) == 0, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_cost_volume: pointers must be 16B aligned");
+  const int P = B * V;
+  constexpr int DPB = 16;
+  CNM_REQUIRE((long long)P * (D / DPB) <= 65535, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_cost_volume: too many pairs x planes");
+  const double step = (idepth_max - idepth_min) / (double)(D - 1);
+  dim3 grid((W + CV_TX - 1) / CV_TX, (H + CV_TY - 1) / CV_TY, P * (D / DPB));
+  dim3 block(CV_TX, CV_TY);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float4* tex = (const float4*)packed_src;
+  if (layout == CNM_VOLUME_NCHW_F32)
+    cost_volume_kernel<DPB, 0><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+  else if (dtype == CNM_BF16)
+    cost_volume_kernel<DPB, 1><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+  else if (dtype == CNM_TF32)
+    cost_volume_kernel<DPB, 2><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+  else
+    return fail(CNM_ERR_INVALID_ARGUMENT, "cnm_cost_volume: dtype %d", dtype);
+  return after_launch("cnm_cost_volume");
+}

@@ -1,0 +1,387 @@
+// K4 (refine-input aggregation) and the small bandwidth-bound kernels around the convolutions:
+// layout converters, tap packers, bilinear x2 upsample, 1-channel 3x3 heads.
+//
+// Reference semantics: depthnet/depthNet_model.py:82-84 (depth_layer), :94,105 (nn.Upsample),
+// :233,247-258 (torch.cat / F.upsample of the inputs), :332-333 (refine input), eval.py:659-663,
+// 920-929 (view-group means).
+#include "common.cuh"
+
+namespace cnm {
+
+// ---- NCHW fp32 <-> act (NHWC) ----------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_act_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int H, int W, int ct,
+                                   int co) {
+  // tile transpose through smem: 32 pixels x 32 channels
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const size_t p0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const size_t p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (c < C && p < HW) ? __ldg(src + ((size_t)n * C + c) * HW + p) : 0.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const size_t p = p0 + j;
+    const int c = c0 + threadIdx.x;
+    if (p < HW && c < C) dst[((size_t)n * HW + p) * ct + co + c] = from_f<T>(tile[threadIdx.x][j]);
+  }
+}
+
+template <typename T>
+__global__ void act_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int H, int W, int ct,
+                                   int co) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const size_t p0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const size_t p = p0 + j;
+    const int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && c < C) ? to_f<T>(src[((size_t)n * HW + p) * ct + co + c]) : 0.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const size_t p = p0 + threadIdx.x;
+    if (c < C && p < HW) dst[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+// ---- tap packers -----------------------------------------------------------------------------
+// one thread per pixel writes one 128-byte chunk row (64 bf16 or 32 fp32 channels)
+template <typename T>
+__device__ __forceinline__ void store_chunk(T* dst, const float* v) {
+  constexpr int CH = 128 / sizeof(T);
+#pragma unroll
+  for (int i = 0; i < CH; i += Vec16<T>::N) Vec16<T>::store(dst + i, v + i);
+}
+
+template <typename T>
+__global__ void pack_row_taps_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int Cx, int H,
+                                     int W, int kw) {
+  constexpr int CH = 128 / sizeof(T);
+  const size_t HW = (size_t)H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * HW) return;
+  const int n = (int)(i / HW) % Nsrc;
+  const size_t p = i % HW;
+  const int y = (int)(p / W), xx = (int)(p % W);
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = 0.0f;
+  const int r = kw / 2;
+#pragma unroll 1
+  for (int s = 0; s < kw; ++s) {
+    const int xs = xx + s - r;
+    if (xs < 0 || xs >= W) continue;
+    for (int c = 0; c < Cx; ++c) {
+      const float val = __ldg(x + ((size_t)n * Cx + c) * HW + (size_t)y * W + xs);
+      const int j = s * Cx + c;
+#pragma unroll
+      for (int q = 0; q < CH; ++q)
+        if (q == j) v[q] = val;  // keeps v[] in registers
+    }
+  }
+  store_chunk<T>(dst + i * CH, v);
+}
+
+template <typename T>
+__global__ void pack_disp_taps_kernel(const float* __restrict__ disp, T* __restrict__ dst, int N, int h, int w) {
+  constexpr int CH = 128 / sizeof(T);
+  const int H = 2 * h, W = 2 * w;
+  const size_t HW = (size_t)H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * HW) return;
+  const int n = (int)(i / HW);
+  const size_t p = i % HW;
+  const int y = (int)(p / W), x = (int)(p % W);
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int yy = y + r - 1, xx = x + s - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v[3 * r + s] = __ldg(disp + ((size_t)n * h + (yy >> 1)) * w + (xx >> 1));  // nearest x2
+    }
+  store_chunk<T>(dst + i * CH, v);
+}
+
+// ---- refine-input aggregation ------------------------------------------------------------------
+// taps: channel 9c+3r+s of (id1, id2, |id1-id2|) with group means taken first
+__device__ __forceinline__ float group_mean_at(const float* __restrict__ idepth, int g, int group, size_t BHW,
+                                               size_t off) {
+  float acc = __ldg(idepth + (size_t)g * BHW + off);
+  for (int k = 1; k < group; ++k) acc += __ldg(idepth + (size_t)(g + 2 * k) * BHW + off);
+  return group > 1 ? acc / (float)group : acc;
+}
+
+template <typename T>
+__global__ void refine_taps_kernel(const float* __restrict__ idepth, T* __restrict__ taps, float* __restrict__ id_out,
+                                   int B, int H, int W, int group) {
+  constexpr int CH = 128 / sizeof(T);
+  const size_t HW = (size_t)H * W, BHW = (size_t)B * HW;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BHW) return;
+  const int b = (int)(i / HW);
+  const size_t p = i % HW;
+  const int y = (int)(p / W), x = (int)(p % W);
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int yy = y + r - 1, xx = x + s - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const size_t off = (size_t)b * HW + (size_t)yy * W + xx;
+        const float a = group_mean_at(idepth, 0, group, BHW, off), c = group_mean_at(idepth, 1, group, BHW, off);
+        v[3 * r + s] = a;
+        v[9 + 3 * r + s] = c;
+        v[18 + 3 * r + s] = fabsf(a - c);
+        if (r == 1 && s == 1 && id_out) { id_out[off] = a; id_out[BHW + off] = c; }
+      }
+    }
+  store_chunk<T>(taps + i * CH, v);
+}
+
+// sum_act = mean_0(iconv) + mean_1(iconv) on act tensors [V*B,H,W,64]; one 16-byte vector per thread
+template <typename T>
+__global__ void refine_sum_act_kernel(const T* __restrict__ iconv, T* __restrict__ out, size_t per_view, int group) {
+  constexpr int VN = Vec16<T>::N;
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VN;
+  if (i >= per_view) return;
+  float m[2][VN];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    Vec16<T>::load(iconv + (size_t)g * per_view + i, m[g]);
+    for (int k = 1; k < group; ++k) {
+      float t[VN];
+      Vec16<T>::load(iconv + (size_t)(g + 2 * k) * per_view + i, t);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) m[g][j] += t[j];
+    }
+    if (group > 1)
+#pragma unroll
+      for (int j = 0; j < VN; ++j) m[g][j] /= (float)group;
+  }
+#pragma unroll
+  for (int j = 0; j < VN; ++j) m[0][j] += m[1][j];
+  Vec16<T>::store(out + i, m[0]);
+}
+
+// public-boundary variant: iconv NCHW fp32 [2,B,64,H,W] -> sum act [B,H,W,64]
+template <typename T>
+__global__ void refine_sum_nchw_kernel(const float* __restrict__ iconv, T* __restrict__ out, int B, int H, int W) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const size_t HW = (size_t)H * W;
+  const size_t p0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const size_t view = (size_t)B * 64 * HW;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const size_t p = p0 + threadIdx.x;
+    const size_t off = ((size_t)b * 64 + c0 + j) * HW + p;
+    tile[j][threadIdx.x] = (p < HW) ? __ldg(iconv + off) + __ldg(iconv + view + off) : 0.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const size_t p = p0 + j;
+    if (p < HW) out[((size_t)b * HW + p) * 64 + c0 + threadIdx.x] = from_f<T>(tile[threadIdx.x][j]);
+  }
+}
+
+// ---- bilinear x2 upsample (align_corners=False): weights 0.25/0.75, clamped at the border ------
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int h, int w, int C) {
+  constexpr int VN = Vec16<T>::N;
+  const int cv = C / VN;
+  const int H = 2 * h, W = 2 * w;
+  const size_t total = (size_t)N * H * W * cv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VN;
+    size_t t = i / cv;
+    const int X = (int)(t % W);
+    t /= W;
+    const int Y = (int)(t % H);
+    const int n = (int)(t / H);
+    // src = (dst + 0.5)/2 - 0.5, clamped at 0
+    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f), sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.0f);
+    const int x0 = (int)sx, y0 = (int)sy;
+    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+    const float lx = sx - x0, ly = sy - y0;
+    const T* base = src + (size_t)n * h * w * C + c;
+    float a[VN], b[VN], cc[VN], d[VN], o[VN];
+    Vec16<T>::load(base + ((size_t)y0 * w + x0) * C, a);
+    Vec16<T>::load(base + ((size_t)y0 * w + x1) * C, b);
+    Vec16<T>::load(base + ((size_t)y1 * w + x0) * C, cc);
+    Vec16<T>::load(base + ((size_t)y1 * w + x1) * C, d);
+    const float w00 = (1.f - lx) * (1.f - ly), w10 = lx * (1.f - ly), w01 = (1.f - lx) * ly, w11 = lx * ly;
+#pragma unroll
+    for (int j = 0; j < VN; ++j) o[j] = a[j] * w00 + b[j] * w10 + cc[j] * w01 + d[j] * w11;
+    Vec16<T>::store(dst + (((size_t)n * H + Y) * W + X) * C + c, o);
+  }
+}
+
+// ---- 1-channel 3x3 head: 8 lanes per pixel, fp32 accumulate, sigmoid epilogue -------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+    head3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, float bias, float scale,
+                   float* __restrict__ out, float* __restrict__ logits, int N, int H, int W, int C) {
+  extern __shared__ float ws[];  // [9*C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) ws[i] = __ldg(w + i);
+  __syncthreads();
+  constexpr int VN = Vec16<T>::N;
+  const size_t HW = (size_t)H * W;
+  const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool active = pix < (size_t)N * HW;
+  float acc = 0.0f;
+  if (active) {
+    const int n = (int)(pix / HW);
+    const size_t p = pix % HW;
+    const int y = (int)(p / W), xx = (int)(p % W);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y + r - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int xs = xx + s - 1;
+        if (xs < 0 || xs >= W) continue;
+        const T* px = x + (((size_t)n * H + yy) * W + xs) * C;
+        const float* wp = ws + (r * 3 + s) * C;
+        for (int c = sub * VN; c < C; c += 8 * VN) {
+          float v[VN];
+          Vec16<T>::load(px + c, v);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) acc = fmaf(v[j], wp[c + j], acc);
+        }
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (active && sub == 0) {
+    const float l = acc + bias;
+    if (logits) logits[pix] = l;
+    out[pix] = scale / (1.0f + expf(-l));
+  }
+}
+
+}  // namespace cnm
+
+using namespace cnm;
+
+#define DISPATCH_DTYPE(dtype, ...)                                   \
+  if ((dtype) == CNM_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else if ((dtype) == CNM_TF32) { using T = float; __VA_ARGS__; }    \
+  else return fail(CNM_ERR_INVALID_ARGUMENT, "%s: dtype %d", __func__, (int)(dtype));
+
+extern "C" int cnm_nchw_to_act(const float* src, void* dst, int N, int C, int H, int W, int c_dst_total,
+                               int c_dst_offset, int dtype, void* stream) {
+  CNM_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_nchw_to_act: bad argument");
+  CNM_REQUIRE(c_dst_offset >= 0 && c_dst_offset + C <= c_dst_total, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_nchw_to_act: channel slice out of range");
+  dim3 grid((unsigned)(((size_t)H * W + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  DISPATCH_DTYPE(dtype, (nchw_to_act_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(src, (T*)dst, C, H, W,
+                                                                                         c_dst_total, c_dst_offset)));
+  return after_launch("cnm_nchw_to_act");
+}
+
+extern "C" int cnm_act_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int c_src_total,
+                               int c_src_offset, int dtype, void* stream) {
+  CNM_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_act_to_nchw: bad argument");
+  CNM_REQUIRE(c_src_offset >= 0 && c_src_offset + C <= c_src_total, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_act_to_nchw: channel slice out of range");
+  dim3 grid((unsigned)(((size_t)H * W + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  DISPATCH_DTYPE(dtype, (act_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>((const T*)src, dst, C, H, W,
+                                                                                         c_src_total, c_src_offset)));
+  return after_launch("cnm_act_to_nchw");
+}
+
+extern "C" int cnm_pack_row_taps(const float* x, void* dst, int N, int Nsrc, int Cx, int H, int W, int kw, int dtype,
+                                 void* stream) {
+  CNM_REQUIRE(x && dst && N > 0 && Nsrc > 0 && Cx > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_pack_row_taps: bad argument");
+  CNM_REQUIRE(kw >= 1 && (kw & 1) && kw * Cx <= chunk_channels(dtype), CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_pack_row_taps: kw*Cx=%d exceeds one chunk", kw * Cx);
+  const size_t total = (size_t)N * H * W;
+  DISPATCH_DTYPE(dtype, (pack_row_taps_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+                            x, (T*)dst, N, Nsrc, Cx, H, W, kw)));
+  return after_launch("cnm_pack_row_taps");
+}
+
+extern "C" int cnm_pack_disp_taps(const float* disp, void* dst, int N, int h, int w, int dtype, void* stream) {
+  CNM_REQUIRE(disp && dst && N > 0 && h > 0 && w > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_disp_taps: bad argument");
+  const size_t total = (size_t)N * 4 * h * w;
+  DISPATCH_DTYPE(dtype, (pack_disp_taps_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+                            disp, (T*)dst, N, h, w)));
+  return after_launch("cnm_pack_disp_taps");
+}
+
+extern "C" int cnm_refine_aggregate(const float* idepth, const void* iconv, void* sum_act, void* taps_act,
+                                    float* id_out, int B, int H, int W, int group, int dtype, void* stream) {
+  CNM_REQUIRE(idepth && iconv && sum_act && taps_act, CNM_ERR_INVALID_ARGUMENT, "cnm_refine_aggregate: null pointer");
+  CNM_REQUIRE(B > 0 && H > 0 && W > 0 && group >= 1 && group <= 8, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_refine_aggregate: bad shape");
+  const size_t px = (size_t)B * H * W, per_view = px * 64;
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    refine_taps_kernel<T><<<(unsigned)((px + 127) / 128), 128, 0, s>>>(idepth, (T*)taps_act, id_out, B, H, W, group);
+    int rc = after_launch("cnm_refine_aggregate(taps)");
+    if (rc) return rc;
+    const size_t nv = per_view / Vec16<T>::N;
+    refine_sum_act_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, s>>>((const T*)iconv, (T*)sum_act, per_view, group);
+  });
+  return after_launch("cnm_refine_aggregate(sum)");
+}
+
+extern "C" int cnm_refine_aggregate_nchw(const float* idepth, const float* iconv_nchw, void* sum_act, void* taps_act,
+                                         int B, int H, int W, int dtype, void* stream) {
+  CNM_REQUIRE(idepth && iconv_nchw && sum_act && taps_act, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_refine_aggregate_nchw: null pointer");
+  CNM_REQUIRE(B > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_refine_aggregate_nchw: bad shape");
+  const size_t px = (size_t)B * H * W;
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    refine_taps_kernel<T><<<(unsigned)((px + 127) / 128), 128, 0, s>>>(idepth, (T*)taps_act, nullptr, B, H, W, 1);
+    int rc = after_launch("cnm_refine_aggregate_nchw(taps)");
+    if (rc) return rc;
+    dim3 grid((unsigned)(((size_t)H * W + 31) / 32), 2, B), block(32, 8);
+    refine_sum_nchw_kernel<T><<<grid, block, 0, s>>>(iconv_nchw, (T*)sum_act, B, H, W);
+  });
+  return after_launch("cnm_refine_aggregate_nchw(sum)");
+}
+
+extern "C" int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, int C, int dtype, void* stream) {
+  CNM_REQUIRE(src && dst && N > 0 && h > 0 && w > 0 && C > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_upsample2x: bad argument");
+  CNM_REQUIRE(C % 8 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_upsample2x: C=%d must be a multiple of 8", C);
+  DISPATCH_DTYPE(dtype, {
+    const size_t total = (size_t)N * 4 * h * w * (C / Vec16<T>::N);
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    upsample2x_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, N, h, w, C);
+  });
+  return after_launch("cnm_upsample2x");
+}
+
+extern "C" int cnm_head3x3(const void* x, const float* w, float bias, float scale, float* out, float* logits, int N,
+                           int H, int W, int C, int dtype, void* stream) {
+  CNM_REQUIRE(x && w && out && N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_head3x3: bad argument");
+  CNM_REQUIRE(C % 64 == 0 && C <= 1024, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head3x3: C=%d must be a multiple of 64", C);
+  const size_t threads = (size_t)N * H * W * 8;
+  const size_t smem = (size_t)9 * C * sizeof(float);
+  DISPATCH_DTYPE(dtype, (head3x3_kernel<T><<<(unsigned)((threads + 255) / 256), 256, smem, (cudaStream_t)stream>>>(
+                            (const T*)x, w, bias, scale, out, logits, N, H, W, C)));
+  return after_launch("cnm_head3x3");
+}

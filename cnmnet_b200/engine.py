@@ -1,0 +1,377 @@
+"""Host-side layer programs for the B200 kernels: BN folding, weight packing, K-step lists and
+static execution plans for DepthNet / DepthRefineNet.
+
+A *plan* owns every activation buffer for one (batch, H, W, dtype) shape and a flat list of
+pre-bound C-ABI calls, so running it is a loop of ctypes calls with fixed device pointers:
+no allocation, no host sync, CUDA-graph capturable.  The wiring follows the reference
+(depthnet/depthNet_model.py:226-263 and :331-370); torch.cat never happens -- concatenated
+inputs are extra operand sources of the implicit GEMM (see csrc/conv_tc.cu).
+"""
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from ._lib import CNM_BF16, CNM_TF32
+
+BN_EPS = 1e-5
+TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32}
+
+
+def chunk_channels(dtype):
+    return 64 if dtype == CNM_BF16 else 32
+
+
+def parse_dtype(d):
+    if d in (CNM_BF16, "bf16", torch.bfloat16):
+        return CNM_BF16
+    if d in (CNM_TF32, "tf32", torch.float32):
+        return CNM_TF32
+    raise ValueError("precision must be 'bf16' or 'tf32', got %r" % (d,))
+
+
+def round_tf32(t):
+    """Round-to-nearest (ties away) onto the 10-bit tf32 mantissa, like cvt.rna.tf32.f32."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & -8192).view(torch.float32)
+
+
+def fold_bn(sd, prefix, ci):
+    """conv (no bias) + BatchNorm2d(eval) -> (w', b') with w' = w*g/sqrt(v+eps), b' = beta - mu*g/sqrt(v+eps)."""
+    w = sd["%s.%d.weight" % (prefix, ci)].double()
+    p = "%s.%d." % (prefix, ci + 1)
+    scale = sd[p + "weight"].double() / torch.sqrt(sd[p + "running_var"].double() + BN_EPS)
+    wf = w * scale.view(-1, 1, 1, 1)
+    bf = sd[p + "bias"].double() - sd[p + "running_mean"].double() * scale
+    return wf.float(), bf.float()
+
+
+# An operand source of a convolution.
+#   kind 'act'      full act tensor, channels [coff, coff+C) <-> weight input channels [wch, wch+C)
+#   kind 'rowtaps'  side tensor whose channel s*nreal+c holds tap s of input channel wch+c (one K-step per kernel row)
+#   kind 'taps3x3'  side tensor whose channel 9c+3r+s holds tap (r,s) of input channel wch+c (a single K-step)
+Src = namedtuple("Src", "buf kind wch C coff nreal")
+
+
+def act_src(buf, wch, C=None, coff=0):
+    return Src(buf, "act", wch, buf.shape[3] if C is None else C, coff, 0)
+
+
+def make_steps(srcs, k, stride, ch):
+    """-> (steps [(src, sub, dx, dy, c0)], cols [packing recipe per step]).  See include/cnmnet_b200.h."""
+    pad = (k - 1) // 2
+    steps, cols = [], []
+    for si, s in enumerate(srcs):
+        if s.kind == "act":
+            assert s.C % ch == 0 and s.coff % ch == 0
+            for r in range(k):
+                for t in range(k):
+                    ty, tx = r - pad, t - pad
+                    if stride == 1:
+                        sub, dy, dx = 0, ty, tx
+                    else:  # input row 2*oy + ty = 2*(oy + dy) + py
+                        py, px = ty % 2, tx % 2
+                        dy, dx = (ty - py) // 2, (tx - px) // 2
+                        sub = py * 2 + px
+                    for c0 in range(0, s.C, ch):
+                        steps.append((si, sub, dx, dy, s.coff + c0))
+                        cols.append(("act", s.wch + c0, r, t))
+        elif s.kind == "rowtaps":
+            assert stride == 1 and k * s.nreal <= ch
+            for r in range(k):
+                steps.append((si, 0, 0, r - pad, 0))
+                cols.append(("rowtaps", s.wch, s.nreal, r))
+        elif s.kind == "taps3x3":
+            assert stride == 1 and k == 3 and 9 * s.nreal <= ch
+            steps.append((si, 0, 0, 0, 0))
+            cols.append(("taps3x3", s.wch, s.nreal, 0))
+        else:
+            raise ValueError(s.kind)
+    return steps, cols
+
+
+def pack_weights(wf, cols, ch, dtype):
+    """Folded weights [Cout, Cin, k, k] -> K-major operand [Cout, len(cols)*ch] in the act dtype."""
+    cout, _, k, _ = wf.shape
+    wp = torch.zeros((cout, len(cols) * ch), dtype=torch.float32, device=wf.device)
+    for i, col in enumerate(cols):
+        base = i * ch
+        if col[0] == "act":
+            _, c, r, t = col
+            wp[:, base:base + ch] = wf[:, c:c + ch, r, t]
+        elif col[0] == "rowtaps":
+            _, wch, n, r = col
+            wp[:, base:base + k * n] = wf[:, wch:wch + n, r, :].permute(0, 2, 1).reshape(cout, k * n)
+        else:
+            _, wch, n, _ = col
+            wp[:, base:base + 9 * n] = wf[:, wch:wch + n].reshape(cout, 9 * n)
+    if dtype == CNM_BF16:
+        return wp.to(torch.bfloat16).contiguous()
+    return round_tf32(wp)
+
+
+class ConvOp:
+    """One pre-bound cnm_conv2d_* call."""
+
+    def __init__(self, name, srcs, k, stride, cout, N, Ho, Wo, dtype, device, relu=True, out=None, c_out_offset=0,
+                 backend="tc"):
+        self.name, self.k, self.stride, self.dtype, self.backend = name, k, stride, dtype, backend
+        ch = chunk_channels(dtype)
+        self.steps, self.cols = make_steps(srcs, k, stride, ch)
+        self.srcs = srcs
+        self.out = out if out is not None else torch.empty((N, Ho, Wo, cout), dtype=TORCH_DTYPE[dtype], device=device)
+        self.wp = torch.zeros((cout, len(self.steps) * ch), dtype=TORCH_DTYPE[dtype], device=device)
+        self.bias = torch.zeros((cout,), dtype=torch.float32, device=device)
+        st = torch.zeros((len(self.steps), 8), dtype=torch.int32)
+        st[:, :5] = torch.tensor(self.steps, dtype=torch.int32)
+        self.steps_dev = st.to(device)
+        self.desc = _lib.ConvDesc(N, Ho, Wo, cout, self.out.shape[3], c_out_offset, stride, 1 if relu else 0,
+                                  len(srcs), len(self.steps), dtype, 0)
+        arr = (_lib.ConvSrc * len(srcs))()
+        for i, s in enumerate(srcs):
+            arr[i] = _lib.ConvSrc(_lib.ptr(s.buf), s.buf.shape[1], s.buf.shape[2], s.buf.shape[3], 0)
+        self.srcs_arr = arr
+        self.flops = 2.0 * N * Ho * Wo * cout * len(self.steps) * ch
+
+    def load(self, wf, bf):
+        self.wp.copy_(pack_weights(wf.to(self.wp.device), self.cols, chunk_channels(self.dtype), self.dtype))
+        self.bias.copy_(bf.to(self.bias.device))
+
+    def __call__(self, stream):
+        lib = _lib.load()
+        fn = lib.cnm_conv2d_tc if self.backend == "tc" else lib.cnm_conv2d_simt
+        _lib.check(fn(C.byref(self.desc), self.srcs_arr, self.steps_dev.data_ptr(), self.wp.data_ptr(),
+                      self.bias.data_ptr(), self.out.data_ptr(), stream), self.name)
+
+
+class _Plan:
+    def __init__(self, dtype, device, backend):
+        self.dtype, self.device, self.backend = parse_dtype(dtype), torch.device(device), backend
+        if self.device.type != "cuda":
+            raise RuntimeError("cnmnet_b200 runs on CUDA devices only (no CPU path); got %s" % (self.device,))
+        self.lib = _lib.load()
+        self.ops = []      # (callable(stream))
+        self.convs = {}    # name -> ConvOp
+        self.heads = {}    # name -> dict(w, bias, scale)
+        self.ch = chunk_channels(self.dtype)
+
+    def buf(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=TORCH_DTYPE[self.dtype] if dtype is None else dtype, device=self.device)
+
+    def conv(self, name, srcs, k, stride, cout, N, Ho, Wo, relu=True):
+        op = ConvOp(name, srcs, k, stride, cout, N, Ho, Wo, self.dtype, self.device, relu, backend=self.backend)
+        self.convs[name] = op
+        self.ops.append(op)
+        return op.out
+
+    def upsample(self, x):
+        N, h, w, Cc = x.shape
+        out = self.buf(N, 2 * h, 2 * w, Cc)
+        lib, dt = self.lib, self.dtype
+        self.ops.append(lambda s: _lib.check(lib.cnm_upsample2x(x.data_ptr(), out.data_ptr(), N, h, w, Cc, dt, s),
+                                             "upsample2x"))
+        return out
+
+    def head(self, name, x, scale, want_logits=False):
+        N, H, W, Cc = x.shape
+        out = self.buf(N, 1, H, W, dtype=torch.float32)
+        logits = self.buf(N, 1, H, W, dtype=torch.float32) if want_logits else None
+        hw = {"w": torch.zeros((9 * Cc,), dtype=torch.float32, device=self.device), "bias": 0.0, "scale": float(scale)}
+        self.heads[name] = hw
+        lib, dt = self.lib, self.dtype
+        lp = logits.data_ptr() if logits is not None else None
+        self.ops.append(lambda s: _lib.check(
+            lib.cnm_head3x3(x.data_ptr(), hw["w"].data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, Cc,
+                            dt, s), name))
+        return out, logits
+
+    def disp_taps(self, disp):
+        N, _, h, w = disp.shape
+        out = self.buf(N, 2 * h, 2 * w, self.ch)
+        lib, dt = self.lib, self.dtype
+        self.ops.append(lambda s: _lib.check(lib.cnm_pack_disp_taps(disp.data_ptr(), out.data_ptr(), N, h, w, dt, s),
+                                             "pack_disp_taps"))
+        return out
+
+    def load_head(self, name, sd):
+        hw = self.heads[name]
+        w = sd[name + ".0.weight"].to(self.device, torch.float32)  # [1, C, 3, 3] -> (r, s, c)
+        hw["w"].copy_(w[0].permute(1, 2, 0).reshape(-1))
+        hw["bias"] = float(sd[name + ".0.bias"].reshape(-1)[0])
+
+    def run(self, stream=None):
+        s = _lib.stream_ptr() if stream is None else stream
+        for op in self.ops:
+            op(s)
+
+    @property
+    def conv_flops(self):
+        return sum(op.flops for op in self.convs.values())
+
+
+class DepthNetPlan(_Plan):
+    """camera setup -> cost volume -> DepthNet trunk for N (view, batch) pairs sharing Bref reference frames.
+
+    Inputs are bound at run time: ref [Bref,3,H,W], src [N,3,H,W] (view-major: pair p = v*Bref + b),
+    ref_cam [Bref,2,4,4], src_cam [N,2,4,4].  Outputs live in plan buffers: disp1..4 fp32 [N,1,h,w],
+    iconv1 act [N,H,W,64]."""
+
+    def __init__(self, N, Bref, H, W, idepth_scale=3.0, dtype="bf16", device="cuda", backend="tc", planes=64,
+                 want_logits=False):
+        super().__init__(dtype, device, backend)
+        if H % 32 or W % 32:
+            raise ValueError("DepthNet needs H and W divisible by 32 (five stride-2 stages); got %dx%d" % (H, W))
+        if N % Bref:
+            raise ValueError("N=%d pairs must be a multiple of Bref=%d reference frames" % (N, Bref))
+        if float(idepth_scale) == 2.0:
+            self.idmin, self.idmax = 0.02, 2.0
+        elif float(idepth_scale) == 3.0:
+            self.idmin, self.idmax = 0.1, 3.0
+        else:  # the reference raises UnboundLocalError here (depthNet_model.py:186-191)
+            raise ValueError("idepth_scale must be 2.0 or 3.0 (the reference defines no other plane range)")
+        if planes != 64:
+            raise ValueError("the reference network has 67 input channels = 3 + 64 planes")
+        self.N, self.Bref, self.H, self.W, self.D, self.scale = N, Bref, H, W, planes, float(idepth_scale)
+        lib, dt, ch = self.lib, self.dtype, self.ch
+        self.hk = self.buf(N, 12, dtype=torch.float32)
+        self.tex = torch.empty((lib.cnm_packed_source_bytes(N, H, W),), dtype=torch.uint8, device=self.device)
+        self.cost = self.buf(N, H, W, planes)
+        self.img_taps = self.buf(N, H, W, ch)
+        self.inputs = {}
+
+        def front(s):
+            i = self.inputs
+            _lib.check(lib.cnm_camera_setup(i["ref_cam"], i["src_cam"], self.hk.data_ptr(), Bref, N // Bref, s), "camera")
+            _lib.check(lib.cnm_pack_source(i["src"], self.tex.data_ptr(), N, H, W, s), "pack_source")
+            _lib.check(lib.cnm_cost_volume(i["ref"], self.tex.data_ptr(), self.hk.data_ptr(), self.cost.data_ptr(), Bref,
+                                           N // Bref, H, W, planes, self.idmin, self.idmax, _lib.VOLUME_ACT, dt, s),
+                       "cost_volume")
+            _lib.check(lib.cnm_pack_row_taps(i["ref"], self.img_taps.data_ptr(), N, Bref, 3, H, W, 7, dt, s),
+                       "pack_row_taps")
+
+        self.ops.append(front)
+        self._trunk(want_logits)
+
+    def _trunk(self, want_logits):
+        N, H, W = self.N, self.H, self.W
+        cv = self.conv
+        x = cv("conv1.0", [act_src(self.cost, 3), Src(self.img_taps, "rowtaps", 0, self.ch, 0, 3)], 7, 1, 128, N, H, W)
+        conv1 = cv("conv1.3", [act_src(x, 0)], 7, 2, 128, N, H // 2, W // 2)
+        x = cv("conv2.0", [act_src(conv1, 0)], 5, 1, 256, N, H // 2, W // 2)
+        conv2 = cv("conv2.3", [act_src(x, 0)], 5, 2, 256, N, H // 4, W // 4)
+        x = cv("conv3.0", [act_src(conv2, 0)], 3, 1, 512, N, H // 4, W // 4)
+        conv3 = cv("conv3.3", [act_src(x, 0)], 3, 2, 512, N, H // 8, W // 8)
+        x = cv("conv4.0", [act_src(conv3, 0)], 3, 1, 512, N, H // 8, W // 8)
+        conv4 = cv("conv4.3", [act_src(x, 0)], 3, 2, 512, N, H // 16, W // 16)
+        x = cv("conv5.0", [act_src(conv4, 0)], 3, 1, 512, N, H // 16, W // 16)
+        conv5 = cv("conv5.3", [act_src(x, 0)], 3, 2, 512, N, H // 32, W // 32)
+
+        up5 = cv("upconv5.1", [act_src(self.upsample(conv5), 0)], 3, 1, 512, N, H // 16, W // 16)
+        iconv5 = cv("iconv5.0", [act_src(up5, 0), act_src(conv4, 512)], 3, 1, 512, N, H // 16, W // 16)
+        up4 = cv("upconv4.1", [act_src(self.upsample(iconv5), 0)], 3, 1, 512, N, H // 8, W // 8)
+        iconv4 = cv("iconv4.0", [act_src(up4, 0), act_src(conv3, 512)], 3, 1, 512, N, H // 8, W // 8)
+        self.disp4, l4 = self.head("disp4", iconv4, self.scale, want_logits)
+        t4 = self.disp_taps(self.disp4)
+        up3 = cv("upconv3.1", [act_src(self.upsample(iconv4), 0)], 3, 1, 256, N, H // 4, W // 4)
+        iconv3 = cv("iconv3.0", [act_src(up3, 0), act_src(conv2, 256), Src(t4, "taps3x3", 512, self.ch, 0, 1)], 3, 1,
+                    256, N, H // 4, W // 4)
+        self.disp3, l3 = self.head("disp3", iconv3, self.scale, want_logits)
+        t3 = self.disp_taps(self.disp3)
+        up2 = cv("upconv2.1", [act_src(self.upsample(iconv3), 0)], 3, 1, 128, N, H // 2, W // 2)
+        iconv2 = cv("iconv2.0", [act_src(up2, 0), act_src(conv1, 128), Src(t3, "taps3x3", 256, self.ch, 0, 1)], 3, 1,
+                    128, N, H // 2, W // 2)
+        self.disp2, l2 = self.head("disp2", iconv2, self.scale, want_logits)
+        t2 = self.disp_taps(self.disp2)
+        up1 = cv("upconv1.1", [act_src(self.upsample(iconv2), 0)], 3, 1, 64, N, H, W)
+        self.iconv1 = cv("iconv1.0", [act_src(up1, 0), Src(t2, "taps3x3", 64, self.ch, 0, 1)], 3, 1, 64, N, H, W)
+        self.disp1, l1 = self.head("disp1", self.iconv1, self.scale, want_logits)
+        self.logits = [l1, l2, l3, l4]
+
+    def load_state(self, sd):
+        for name, op in self.convs.items():
+            prefix, ci = name.rsplit(".", 1)
+            op.load(*fold_bn(sd, prefix, int(ci)))
+        for name in self.heads:
+            self.load_head(name, sd)
+
+    def bind(self, ref, src, ref_cam, src_cam):
+        for t, shape in ((ref, (self.Bref, 3, self.H, self.W)), (src, (self.N, 3, self.H, self.W)),
+                         (ref_cam, (self.Bref, 2, 4, 4)), (src_cam, (self.N, 2, 4, 4))):
+            if tuple(t.shape) != shape or t.dtype != torch.float32:
+                raise ValueError("expected fp32 tensor of shape %s, got %s %s" % (shape, tuple(t.shape), t.dtype))
+        self.inputs = {"ref": _lib.ptr(ref), "src": _lib.ptr(src), "ref_cam": _lib.ptr(ref_cam),
+                       "src_cam": _lib.ptr(src_cam)}
+        self._keep = (ref, src, ref_cam, src_cam)
+
+    def iconv1_nchw(self, stream=None):
+        N, H, W, Cc = self.iconv1.shape
+        out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=self.device)
+        s = _lib.stream_ptr() if stream is None else stream
+        _lib.check(self.lib.cnm_act_to_nchw(self.iconv1.data_ptr(), out.data_ptr(), N, Cc, H, W, Cc, 0, self.dtype, s),
+                   "act_to_nchw")
+        return out
+
+
+class RefinePlan(_Plan):
+    """refine-input aggregation -> DepthRefineNet for B frames.
+
+    Inputs: idepth [V,B,H,W] fp32 and iconv1 either as the DepthNet plan's act tensor [V*B,H,W,64] or, at
+    the public boundary, NCHW fp32 [2,B,64,H,W].  V = 2*group source views (eval.py:659-663, 920-929)."""
+
+    def __init__(self, B, H, W, idepth_scale=2.0, dtype="bf16", device="cuda", backend="tc", group=1,
+                 nchw_input=False, want_logits=False):
+        super().__init__(dtype, device, backend)
+        if H % 8 or W % 8:
+            raise ValueError("DepthRefineNet needs H and W divisible by 8; got %dx%d" % (H, W))
+        self.B, self.H, self.W, self.group, self.scale = B, H, W, group, float(idepth_scale)
+        lib, dt, ch = self.lib, self.dtype, self.ch
+        self.sum_act = self.buf(B, H, W, 64)
+        self.taps = self.buf(B, H, W, ch)
+        self.id_mean = self.buf(2, B, H, W, dtype=torch.float32)
+        self.inputs = {}
+
+        def front(s):
+            i = self.inputs
+            if nchw_input:
+                _lib.check(lib.cnm_refine_aggregate_nchw(i["idepth"], i["iconv"], self.sum_act.data_ptr(),
+                                                         self.taps.data_ptr(), B, H, W, dt, s), "refine_aggregate")
+            else:
+                _lib.check(lib.cnm_refine_aggregate(i["idepth"], i["iconv"], self.sum_act.data_ptr(),
+                                                    self.taps.data_ptr(), self.id_mean.data_ptr(), B, H, W, group, dt,
+                                                    s), "refine_aggregate")
+
+        self.ops.append(front)
+        cv = self.conv
+        x = cv("conv1.0", [act_src(self.sum_act, 3), Src(self.taps, "taps3x3", 0, ch, 0, 3)], 3, 1, 128, B, H, W)
+        conv1 = cv("conv1.3", [act_src(x, 0)], 3, 2, 128, B, H // 2, W // 2)
+        x = cv("conv2.0", [act_src(conv1, 0)], 3, 1, 256, B, H // 2, W // 2)
+        conv2 = cv("conv2.3", [act_src(x, 0)], 3, 2, 256, B, H // 4, W // 4)
+        x = cv("conv3.0", [act_src(conv2, 0)], 3, 1, 512, B, H // 4, W // 4)
+        conv3 = cv("conv3.3", [act_src(x, 0)], 3, 2, 512, B, H // 8, W // 8)
+        up_conv3 = self.upsample(conv3)  # shared by both decoders
+        self.out, self.logits, self.iconv1 = {}, {}, {}
+        for br, head, sc in (("depth", "disp_refine", self.scale), ("prob", "prob", 1.0)):
+            u3 = cv("upconv3_%s.1" % br, [act_src(up_conv3, 0)], 3, 1, 256, B, H // 4, W // 4)
+            i3 = cv("iconv3_%s.0" % br, [act_src(u3, 0), act_src(conv2, 256)], 3, 1, 256, B, H // 4, W // 4)
+            u2 = cv("upconv2_%s.1" % br, [act_src(self.upsample(i3), 0)], 3, 1, 128, B, H // 2, W // 2)
+            i2 = cv("iconv2_%s.0" % br, [act_src(u2, 0), act_src(conv1, 128)], 3, 1, 128, B, H // 2, W // 2)
+            u1 = cv("upconv1_%s.1" % br, [act_src(self.upsample(i2), 0)], 3, 1, 64, B, H, W)
+            i1 = cv("iconv1_%s.0" % br, [act_src(u1, 0)], 3, 1, 64, B, H, W)
+            self.iconv1[br] = i1
+            self.out[br], self.logits[br] = self.head(head, i1, sc, want_logits)
+
+    load_state = DepthNetPlan.load_state
+
+    def bind(self, idepth, iconv):
+        self.inputs = {"idepth": _lib.ptr(idepth), "iconv": _lib.ptr(iconv)}
+        self._keep = (idepth, iconv)
+
+    def iconv1_depth_nchw(self, stream=None):
+        x = self.iconv1["depth"]
+        N, H, W, Cc = x.shape
+        out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=self.device)
+        s = _lib.stream_ptr() if stream is None else stream
+        _lib.check(self.lib.cnm_act_to_nchw(x.data_ptr(), out.data_ptr(), N, Cc, H, W, Cc, 0, self.dtype, s),
+                   "act_to_nchw")
+        return out

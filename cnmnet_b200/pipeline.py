@@ -1,0 +1,113 @@
+"""End-to-end inference wrapper mirroring the reference's eval loops (eval.py:440-455 for 3 views,
+eval.py:635-668 / 885-937 for 5 / 7 views):
+
+    (ref_img [B,3,H,W], src_imgs [B,V,3,H,W], ref_cam [B,2,4,4], src_cams [B,V,2,4,4])
+        -> depth [B,H,W], normal [B,3,H,W], prob [B,1,H,W]
+
+All V source views are stacked view-major on the batch axis of one DepthNet plan (the cost volume
+kernel shares each reference tile across them), group means + the refine input come from
+cnm_refine_aggregate, then DepthRefineNet, depth = 1/idepth and depth->normal.  Inputs are copied
+into static buffers and the whole step is replayed as one CUDA graph.
+"""
+import torch
+
+from . import _lib
+from .depthnet.depthNet_model import DepthRefineNet, depthNet
+
+
+class CNMPipeline:
+    def __init__(self, depth_network, depth_refine_network, k_size=9, use_graph=True):
+        if not isinstance(depth_network, depthNet) or not isinstance(depth_refine_network, DepthRefineNet):
+            raise TypeError("CNMPipeline expects cnmnet_b200 depthNet and DepthRefineNet modules")
+        if depth_network.precision != depth_refine_network.precision:
+            raise ValueError("both networks must use the same precision")
+        self.depth_network, self.refine_network = depth_network, depth_refine_network
+        self.k_size, self.use_graph = int(k_size), use_graph
+        self._state = {}
+
+    # -- static state for one shape -----------------------------------------------------------
+    def _prepare(self, B, V, H, W, device):
+        key = (B, V, H, W, str(device))
+        st = self._state.get(key)
+        if st is not None:
+            # weights may have changed since the plan was packed
+            self.depth_network.plan(V * B, B, H, W)
+            self.refine_network.plan(B, H, W, V // 2, False)
+            return st
+        if V < 2 or V % 2:
+            raise ValueError("the refine network takes two view groups: V must be even and >= 2 (got %d)" % V)
+        f32 = dict(dtype=torch.float32, device=device)
+        st = {
+            "ref": torch.empty((B, 3, H, W), **f32), "src": torch.empty((V, B, 3, H, W), **f32),
+            "ref_cam": torch.empty((B, 2, 4, 4), **f32), "src_cam": torch.empty((V, B, 2, 4, 4), **f32),
+            "Kinv": torch.empty((B, 3, 3), **f32), "depth": torch.empty((B, H, W), **f32),
+            "normal": torch.empty((B, 3, H, W), **f32), "graph": None,
+        }
+        dplan = self.depth_network.plan(V * B, B, H, W)
+        rplan = self.refine_network.plan(B, H, W, V // 2, False)
+        dplan.bind(st["ref"], st["src"].view(V * B, 3, H, W), st["ref_cam"], st["src_cam"].view(V * B, 2, 4, 4))
+        rplan.bind(dplan.disp1.view(V, B, H, W), dplan.iconv1)
+        st["dplan"], st["rplan"] = dplan, rplan
+        st["prob"] = rplan.out["prob"]
+        st["idepth"] = rplan.out["depth"]
+        self._state[key] = st
+        return st
+
+    def _launch(self, st, stream):
+        lib = _lib.load()
+        B, _, H, W = st["ref"].shape
+        st["dplan"].run(stream)
+        st["rplan"].run(stream)
+        _lib.check(lib.cnm_reciprocal(st["idepth"].data_ptr(), st["depth"].data_ptr(), B * H * W, stream), "reciprocal")
+        _lib.check(lib.cnm_intrinsics_inverse(st["ref_cam"].data_ptr(), st["Kinv"].data_ptr(), B, stream), "Kinv")
+        _lib.check(lib.cnm_depth2normal(st["depth"].data_ptr(), st["Kinv"].data_ptr(), st["normal"].data_ptr(), None, B,
+                                        H, W, self.k_size, stream), "depth2normal")
+
+    def step(self, st):
+        """Runs one step on the static buffers (graph replay when enabled)."""
+        if not self.use_graph:
+            self._launch(st, _lib.stream_ptr())
+            return
+        if st["graph"] is None:
+            # warm-up outside capture (lazy module / attribute initialisation), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._launch(st, side.cuda_stream)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(g):
+                self._launch(st, _lib.stream_ptr())
+            st["graph"] = g
+            st["launches_per_step"] = _lib.launch_count() - before
+        st["graph"].replay()
+
+    def launches_per_step(self, st):
+        if st.get("launches_per_step") is None:
+            before = _lib.launch_count()
+            self._launch(st, _lib.stream_ptr())
+            st["launches_per_step"] = _lib.launch_count() - before
+        return st["launches_per_step"]
+
+    def load_inputs(self, st, ref_img, src_imgs, ref_cam, src_cams, non_blocking=True):
+        st["ref"].copy_(ref_img, non_blocking=non_blocking)
+        st["src"].copy_(src_imgs.transpose(0, 1), non_blocking=non_blocking)
+        st["ref_cam"].copy_(ref_cam, non_blocking=non_blocking)
+        st["src_cam"].copy_(src_cams.transpose(0, 1), non_blocking=non_blocking)
+
+    def static_state(self, B, V, H, W, device=None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        return self._prepare(B, V, H, W, dev)
+
+    def __call__(self, ref_img, src_imgs, ref_cam, src_cams):
+        if ref_img.dim() != 4 or src_imgs.dim() != 5 or src_imgs.shape[0] != ref_img.shape[0]:
+            raise ValueError("expected ref_img [B,3,H,W] and src_imgs [B,V,3,H,W]")
+        B, V = src_imgs.shape[:2]
+        H, W = ref_img.shape[2:]
+        dev = next(self.depth_network.parameters()).device
+        st = self._prepare(B, V, H, W, dev)
+        self.load_inputs(st, ref_img, src_imgs, ref_cam, src_cams)
+        self.step(st)
+        return st["depth"].clone(), st["normal"].clone(), st["prob"].clone()

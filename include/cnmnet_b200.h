@@ -1,0 +1,191 @@
+/*
+ * cnmnet_b200 -- C ABI of the B200-native CNMNet inference hot path (libcnmnet_b200.so).
+ *
+ * The reference (xxlong0/CNMNet) has no FFI layer: its boundary is the torch.nn.Module API
+ * of depthnet/ (SURVEY.md section 8b).  This header is the layer inserted UNDER that API:
+ * every entry point replaces one chain of PyTorch library ops in the reference, cited
+ * per function as <file>:<lines> relative to the reference tree.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers on the current
+ *     device unless the name says `host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - returns 0 on success, a negative cnm_status otherwise; never throws, never allocates
+ *     device memory, never synchronises (CUDA-graph capturable); cnm_last_error() gives
+ *     a thread-local message for the last failing call;
+ *   - inputs are never modified; outputs are fully overwritten.
+ *
+ * Public-boundary tensors are contiguous NCHW fp32 exactly as in the reference.  Network
+ * activations between kernels use the private "act" layout: NHWC, channel count a multiple
+ * of the K-chunk (64 for CNM_BF16, 32 for CNM_TF32), element type per cnm_dtype.
+ */
+#ifndef CNMNET_B200_H_
+#define CNMNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cnm_status {
+  CNM_OK = 0,
+  CNM_ERR_INVALID_ARGUMENT = -1,
+  CNM_ERR_UNSUPPORTED_SHAPE = -2,
+  CNM_ERR_CUDA = -3,
+  CNM_ERR_NO_DEVICE = -4
+} cnm_status;
+
+/* element type of private activation tensors and packed conv weights */
+typedef enum cnm_dtype {
+  CNM_BF16 = 0, /* bf16 storage, tcgen05 kind::f16, fp32 accumulate; K-chunk = 64 channels */
+  CNM_TF32 = 1  /* fp32 storage, tcgen05 kind::tf32, fp32 accumulate; K-chunk = 32 channels */
+} cnm_dtype;
+
+/* cost-volume output layouts */
+typedef enum cnm_volume_layout {
+  CNM_VOLUME_NCHW_F32 = 0, /* [P, D, H, W] fp32: the reference's getVolume() result */
+  CNM_VOLUME_ACT = 1       /* [P, H, W, D] in cnm_dtype: conv1.0's operand, no torch.cat */
+} cnm_volume_layout;
+
+const char* cnm_last_error(void);
+/* library / build identification, e.g. "cnmnet_b200 0.1 sm_100a" */
+const char* cnm_version(void);
+/* number of kernels launched by this library since load (all threads); used for gpu_launches */
+int64_t cnm_launch_count(void);
+
+/* ---- camera pre-processing -------------------------------------------------------------
+ * replaces process_camera_parameters + get_pixel_coordinates  (depthnet/depth_util.py:13-56)
+ * ref_cam [B,2,4,4], src_cam [V,B,2,4,4]  ->  hk [V*B, 12] = (Hm row-major 3x3, kt 3)
+ * with Hm = K_s R K_r^-1, kt = K_s t, [R|t] = E_s E_r^-1; computed in fp64, stored fp32.  */
+int cnm_camera_setup(const float* ref_cam, const float* src_cam, float* hk, int B, int V, void* stream);
+
+/* ---- plane-sweep cost volume -----------------------------------------------------------
+ * replaces depthNet.getVolume incl. F.grid_sample  (depthnet/depthNet_model.py:185-224)
+ * cnm_pack_source: src [N,3,H,W] fp32 -> packed texels [N, H+3, W+4] x float4 (RGB0) with a
+ *   zero border (row/col -1 and the two trailing ones) so zero padding needs no predicates.
+ * cnm_cost_volume: ref [B,3,H,W]; packed sources for pair p = v*B + b; hk [V*B,12];
+ *   out per `layout`; D planes, z_d = 1/(idmin + d (idmax-idmin)/(D-1)) evaluated in fp64.  */
+int64_t cnm_packed_source_bytes(int N, int H, int W);
+int cnm_pack_source(const float* src, void* packed, int N, int H, int W, void* stream);
+int cnm_cost_volume(const float* ref, const void* packed_src, const float* hk, void* out, int B, int V, int H,
+                    int W, int D, double idepth_min, double idepth_max, int layout, int dtype, void* stream);
+
+/* ---- depth -> normal -------------------------------------------------------------------
+ * replaces pixel2cam (depthnet/inverse_warp.py:27-43) + Depth2normal.forward without planes
+ * (depthnet/depth_util.py:149-203,240).  depth [B,H,W], Kinv [B,3,3] -> normals [B,3,H,W],
+ * points [B,3,H,W] (may be NULL).  k odd, 3..15.  Box sums and the 3x3 solve run in fp64.   */
+int cnm_depth2normal(const float* depth, const float* Kinv, float* normals, float* points, int B, int H, int W,
+                     int k_size, void* stream);
+
+/* replaces Kinv = inverse(ref_cam[1,:3,:3])  (eval.py:270-271, 453-454): cam [B,2,4,4] -> Kinv [B,3,3] */
+int cnm_intrinsics_inverse(const float* cam, float* Kinv, int B, void* stream);
+
+/* ---- Combined Normal Map ---------------------------------------------------------------
+ * replaces the planes branch of Depth2normal.forward (depthnet/depth_util.py:205-238) and
+ * get_normal_by_planes (:243-278).  normals [B,3,H,W] updated IN PLACE (the one exception to
+ * the no-mutation rule: callers pass a private copy); segs [B,P,H,W] uint8; planes_num [B]
+ * int32 on device; loss (device double, may be NULL) receives sum_b sum_i mean_hw(1-cos).  */
+int cnm_plane_regularize(float* normals, const uint8_t* segs, const int32_t* planes_num, double* loss, int B, int P,
+                         int H, int W, void* stream);
+
+/* ---- idepth -> depth -------------------------------------------------------------------
+ * replaces torch.div(1.0, idepth)  (eval.py:269,452,934).  n elements.                      */
+int cnm_reciprocal(const float* idepth, float* depth, int64_t n, void* stream);
+
+/* ---- layout converters between the public NCHW fp32 boundary and private act tensors ---- */
+int cnm_nchw_to_act(const float* src, void* dst, int N, int C, int H, int W, int c_dst_total, int c_dst_offset,
+                    int dtype, void* stream);
+int cnm_act_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int c_src_total, int c_src_offset,
+                    int dtype, void* stream);
+
+/* ---- tap packers (side operands of the implicit GEMM) ------------------------------------
+ * cnm_pack_row_taps: x [Nsrc,Cx,H,W] fp32 -> act [N,H,W,chunk]; image n reads x[n % Nsrc] (one ref image
+ *   serves all its source views); channel s*Cx+c holds x[c][y][x+s-kw/2] (zero outside the image),
+ *   for s < kw; used for the 3 image channels of conv1.0
+ *   (torch.cat((left_image, volume),1), depthNet_model.py:233-235).
+ * cnm_pack_disp_taps: disp [N,1,h,w] fp32 -> act [N,2h,2w,chunk]; channel 3r+s holds
+ *   nearest_up2(disp)[y+r-1][x+s-1] (zero outside): F.upsample + cat (depthNet_model.py:247-258). */
+int cnm_pack_row_taps(const float* x, void* dst, int N, int Nsrc, int Cx, int H, int W, int kw, int dtype,
+                      void* stream);
+int cnm_pack_disp_taps(const float* disp, void* dst, int N, int h, int w, int dtype, void* stream);
+
+/* ---- refine-input aggregation ----------------------------------------------------------
+ * replaces x = cat(id1, id2, |id1-id2|, iconv1+iconv2) (depthnet/depthNet_model.py:332-333) and
+ * the view-group means that precede it (eval.py:659-663, 920-929).
+ * idepth [G*2... see below]: the V = 2*group views are laid out view-major: idepth [V,B,H,W]
+ * fp32, iconv act [V*B,H,W,64]; group g in {0,1} averages views g, g+2, g+4, ... (op order
+ * ((x0+x2)+x4)/group).  Outputs: sum_act [B,H,W,64] = mean_0(iconv) + mean_1(iconv);
+ * taps_act [B,H,W,chunk] channel 9c+3r+s = 3x3 taps of c in (id1,id2,|id1-id2|);
+ * id_out [2,B,H,W] fp32 group-mean idepths (may be NULL).                                   */
+int cnm_refine_aggregate(const float* idepth, const void* iconv, void* sum_act, void* taps_act, float* id_out,
+                         int B, int H, int W, int group, int dtype, void* stream);
+/* same, but iconv given at the public boundary as NCHW fp32 [2,B,64,H,W] (group = 1) */
+int cnm_refine_aggregate_nchw(const float* idepth, const float* iconv_nchw, void* sum_act, void* taps_act, int B,
+                              int H, int W, int dtype, void* stream);
+
+/* ---- bilinear x2 upsample of an act tensor ----------------------------------------------
+ * replaces nn.Upsample(scale_factor=2, mode='bilinear') (depthnet/depthNet_model.py:94,105)
+ * [N,h,w,C] -> [N,2h,2w,C], align_corners=False.                                            */
+int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, int C, int dtype, void* stream);
+
+/* ---- 1-channel 3x3 head ----------------------------------------------------------------
+ * replaces depth_layer = conv3x3(C->1, bias) + sigmoid, times idepth_scale
+ * (depthnet/depthNet_model.py:82-84,245,250,255,261,351,365).  x act [N,H,W,C]; w [9*C] fp32
+ * ordered (r,s,c); out [N,1,H,W] fp32 = scale * sigmoid(conv + bias); logits (may be NULL).  */
+int cnm_head3x3(const void* x, const float* w, float bias, float scale, float* out, float* logits, int N, int H,
+                int W, int C, int dtype, void* stream);
+
+/* ---- convolution as implicit GEMM --------------------------------------------------------
+ * replaces nn.Conv2d + BatchNorm2d(eval) + ReLU and the torch.cat of its inputs
+ * (depthnet/depthNet_model.py:19-112, 235-261, 335-365).
+ *
+ * The K loop is a list of steps; step i multiplies a [128 pixel x chunk] tile of source
+ * tensor `src` shifted by (dx,dy) pixels, channels [c0, c0+chunk), with columns
+ * [i*chunk, (i+1)*chunk) of the packed weight matrix wp [Cout, num_steps*chunk] (K-major,
+ * BN folded).  Several sources = concatenation; taps = spatial kernel; stride-2 layers list
+ * their taps against the four parity sub-images of the source (sub = py*2+px).
+ */
+typedef struct cnm_conv_src {
+  const void* ptr; /* act tensor [N, H, W, C] */
+  int32_t H, W, C;
+  int32_t reserved;
+} cnm_conv_src;
+
+typedef struct cnm_conv_step {
+  int32_t src; /* index into srcs */
+  int32_t sub; /* 0 for stride 1; parity sub-image py*2+px for stride 2 */
+  int32_t dx, dy; /* tile shift in (sub-)image pixels */
+  int32_t c0;  /* first channel */
+  int32_t reserved[3];
+} cnm_conv_step;
+
+typedef struct cnm_conv_desc {
+  int32_t N, Ho, Wo, Cout; /* output act tensor [N, Ho, Wo, c_out_total], written at c_out_offset */
+  int32_t c_out_total, c_out_offset;
+  int32_t stride; /* 1 or 2 */
+  int32_t relu;
+  int32_t num_srcs, num_steps;
+  int32_t dtype; /* cnm_dtype */
+  int32_t reserved;
+} cnm_conv_desc;
+
+/* tcgen05/TMEM/TMA implicit GEMM (the product path).  `steps` is a DEVICE array of
+ * num_steps entries (uploaded once when the layer plan is built); wp/bias/out are device.   */
+int cnm_conv2d_tc(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const cnm_conv_step* steps, const void* wp,
+                  const float* bias, void* out, void* stream);
+/* same contract on CUDA cores with fp32 FMA: validation twin of the tensor-core kernel        */
+int cnm_conv2d_simt(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const cnm_conv_step* steps, const void* wp,
+                    const float* bias, void* out, void* stream);
+
+/* ---- depth-driven inverse warp ("next") ----------------------------
+ * replaces inverse_warp + cam2pixel  (depthnet/inverse_warp.py:46-118).
+ * feat [B,C,H,W], depth [B,H,W], pose [B,3,4], K [B,3,3], Kinv [B,3,3] -> out [B,C,H,W];
+ * padding_mode 0 = zeros, 1 = border.                                                      */
+int cnm_inverse_warp(const float* feat, const float* depth, const float* pose, const float* K, const float* Kinv,
+                     float* out, int B, int C, int H, int W, int padding_mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNMNET_B200_H_ */

@@ -1,0 +1,40 @@
+"""Shared helpers for the -m gpu parity tests (all compute calls go through the C ABI)."""
+import numpy as np
+import torch
+
+from cnmnet_b200 import _lib, engine
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def to_act(x_nchw, dtype):
+    """NCHW fp32 (CPU) -> act tensor on the GPU through cnm_nchw_to_act."""
+    lib = _lib.load()
+    x = x_nchw.float().contiguous().to(dev())
+    N, C, H, W = x.shape
+    out = torch.empty((N, H, W, C), dtype=engine.TORCH_DTYPE[dtype], device=dev())
+    _lib.check(lib.cnm_nchw_to_act(x.data_ptr(), out.data_ptr(), N, C, H, W, C, 0, dtype, _lib.stream_ptr()))
+    return out
+
+
+def from_act(a, dtype):
+    lib = _lib.load()
+    N, H, W, C = a.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=a.device)
+    _lib.check(lib.cnm_act_to_nchw(a.data_ptr(), out.data_ptr(), N, C, H, W, C, 0, dtype, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def quantize(x, dtype):
+    """What storing x in an act tensor does to it."""
+    if dtype == _lib.CNM_BF16:
+        return x.to(torch.bfloat16).float()
+    return engine.round_tf32(x.float())

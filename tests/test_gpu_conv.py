@@ -1,0 +1,93 @@
+"""GPU parity: implicit-GEMM convolution (tcgen05 kernel and its SIMT twin) vs torch CPU conv2d in fp64
+on the same quantised operands, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cnmnet_b200 import _lib, engine
+from gpu_util import dev, from_act, quantize, rel_l2, to_act
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [_lib.CNM_BF16, _lib.CNM_TF32]
+
+
+def run_conv(backend, dtype, xs, wchs, w, b, k, stride, relu=True):
+    N, _, H, W = xs[0].shape
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    acts = [to_act(x, dtype) for x in xs]
+    srcs = [engine.act_src(a, wch) for a, wch in zip(acts, wchs)]
+    op = engine.ConvOp("t", srcs, k, stride, w.shape[0], N, Ho, Wo, dtype, dev(), relu, backend=backend)
+    op.load(w, b)
+    op(_lib.stream_ptr())
+    torch.cuda.synchronize()
+    return from_act(op.out, dtype)
+
+
+def oracle_conv(dtype, xs, w, b, k, stride, relu=True):
+    x = torch.cat([quantize(t, dtype) for t in xs], 1).double()
+    wq = quantize(w, dtype).double()
+    y = F.conv2d(x, wq, b.double(), stride=stride, padding=(k - 1) // 2)
+    return (F.relu(y) if relu else y).float()
+
+
+CASES = [
+    # (N, H, W, [Cin per source], Cout, k, stride)
+    (1, 8, 16, [64], 64, 1, 1),       # plain GEMM, one tile
+    (1, 8, 16, [64], 64, 3, 1),
+    (2, 16, 32, [128], 128, 3, 1),
+    (2, 16, 32, [128], 128, 3, 2),
+    (1, 24, 32, [64], 128, 7, 1),
+    (1, 24, 32, [64], 64, 7, 2),
+    (1, 16, 16, [64], 256, 5, 1),
+    (1, 16, 16, [64], 64, 5, 2),
+    (3, 6, 8, [128], 512, 3, 1),      # tiny layer: batch packed into the pixel tile
+    (5, 12, 16, [64, 64], 256, 3, 1), # concatenated sources, ragged batch tile
+    (1, 20, 40, [64], 64, 3, 1),      # partial tiles (640x480 pyramid sizes)
+    (2, 96, 128, [64], 128, 3, 1),    # enough tiles for BN=128 and several tiles per CTA
+    (1, 48, 64, [128], 512, 3, 1),    # two BN=256 column tiles
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("backend", ["simt", "tc"])
+def test_conv_matches_oracle(backend, dtype, case):
+    N, H, W, cins, cout, k, stride = case
+    g = torch.Generator().manual_seed(N * 1000 + H * 7 + W + cout + k * 13 + stride)
+    xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, generator=g) / np.sqrt(sum(cins) * k * k)
+    b = torch.randn(cout, generator=g)
+    wchs = [sum(cins[:i]) for i in range(len(cins))]
+    got = run_conv(backend, dtype, xs, wchs, w, b, k, stride)
+    want = oracle_conv(dtype, xs, w, b, k, stride)
+    assert got.shape == want.shape
+    # operands are identical; only fp32 accumulation order and the output rounding differ
+    tol = 6e-3 if dtype == _lib.CNM_BF16 else 1e-3
+    err = (got - quantize(want, dtype)).abs().max().item()
+    assert err < tol * max(1.0, want.abs().max().item()), (err, rel_l2(got, want))
+    assert rel_l2(got, want) < (3e-3 if dtype == _lib.CNM_BF16 else 3e-4)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv_no_relu_negative_outputs(dtype):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 64, 16, 16, generator=g)
+    w = torch.randn(64, 64, 3, 3, generator=g) / 24.0
+    b = torch.randn(64, generator=g)
+    got = run_conv("tc", dtype, [x], [0], w, b, 3, 1, relu=False)
+    want = oracle_conv(dtype, [x], w, b, 3, 1, relu=False)
+    assert (want < 0).any() and rel_l2(got, want) < 3e-3
+
+
+def test_conv_rejects_bad_arguments():
+    lib = _lib.load()
+    a = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=dev())  # 48 channels: not chunk aligned
+    desc = _lib.ConvDesc(1, 8, 8, 64, 64, 0, 1, 1, 1, 9, _lib.CNM_BF16, 0)
+    srcs = (_lib.ConvSrc * 1)(_lib.ConvSrc(a.data_ptr(), 8, 8, 48, 0))
+    import ctypes as C
+    rc = lib.cnm_conv2d_tc(C.byref(desc), srcs, a.data_ptr(), a.data_ptr(), None, a.data_ptr(), None)
+    assert rc == -2 and b"channels" in lib.cnm_last_error()
+    rc = lib.cnm_conv2d_tc(None, srcs, a.data_ptr(), a.data_ptr(), None, a.data_ptr(), None)
+    assert rc == -1

@@ -1,0 +1,139 @@
+"""GPU parity of the networks and the end-to-end pipeline against the reference's outputs (tests/golden/)
+and the CPU oracle, through the reference-shaped module API.
+
+Tolerances (north_star): final depth within 1e-3 relative in the TF32 tensor-core mode; the BF16 speed mode
+is reported against a looser bound (pure-bf16 operands give ~1.4e-3 mean / 7e-3 max)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cnmnet_b200
+from cnmnet_b200 import synth
+from gpu_util import dev, rel_l2
+from oracle import nets as onets
+from oracle import normals as onrm
+
+pytestmark = pytest.mark.gpu
+
+# (precision, backend) -> (iconv rel-L2, depth max rel, depth mean rel)
+TOL = {("tf32", "tc"): (1.5e-3, 1e-3, 3e-4), ("tf32", "simt"): (1.5e-3, 1e-3, 3e-4),
+       ("bf16", "tc"): (1.5e-2, 2e-2, 3e-3), ("bf16", "simt"): (1.5e-2, 2e-2, 3e-3)}
+MODES = list(TOL.keys())
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+
+
+def _state(layers, g):
+    return synth.kaiming_state(onets.state_shapes(layers), int(g["weight_seed"]), float(g["head_scale"]))
+
+
+@pytest.mark.parametrize("precision,backend", MODES)
+def test_depthnet_forward_golden(golden_dir, precision, backend):
+    g = _g(golden_dir, "depthnet_fwd.npz")
+    net = cnmnet_b200.depthNet(idepth_scale=3.0, precision=precision, backend=backend)
+    net.load_state_dict(_state(onets.DEPTHNET_LAYERS, g))
+    net = net.to(dev()).eval()
+    disps, iconv1 = net(_cuda(g["left"]), _cuda(g["right"]), _cuda(g["left_cam"]), _cuda(g["right_cam"]))
+    t_ic, t_max, t_mean = TOL[(precision, backend)]
+    assert iconv1.shape == g["iconv1"].shape
+    assert rel_l2(iconv1.cpu().numpy(), g["iconv1"]) < t_ic
+    for i, k in enumerate(["disp1", "disp2", "disp3", "disp4"]):
+        got = disps[i].cpu().numpy()
+        assert got.shape == g[k].shape
+        rel = np.abs(1.0 / got - 1.0 / g[k]) * g[k]          # relative depth error, depth = 1/idepth
+        assert rel.max() < t_max and rel.mean() < t_mean, (k, rel.max(), rel.mean())
+
+
+@pytest.mark.parametrize("precision,backend", MODES)
+def test_refinenet_forward_golden(golden_dir, precision, backend):
+    g = _g(golden_dir, "refinenet_fwd.npz")
+    net = cnmnet_b200.DepthRefineNet(idepth_scale=3.0, precision=precision, backend=backend)
+    net.load_state_dict(_state(onets.REFINENET_LAYERS, g))
+    net = net.to(dev()).eval()
+    dr, pm, vol = net(_cuda(g["idepth01"]), _cuda(g["idepth02"]), _cuda(g["iconv01"]), _cuda(g["iconv02"]),
+                      ReturnVolume=True)
+    t_ic, t_max, t_mean = TOL[(precision, backend)]
+    assert rel_l2(vol.cpu().numpy(), g["iconv1_depth"]) < t_ic
+    rel = np.abs(1.0 / dr.cpu().numpy() - 1.0 / g["disp_refined"]) * g["disp_refined"]
+    assert rel.max() < t_max and rel.mean() < t_mean, (rel.max(), rel.mean())
+    assert np.abs(pm.cpu().numpy() - g["prob_map"]).max() < 10 * t_max
+    dr2, pm2 = net(_cuda(g["idepth01"]), _cuda(g["idepth02"]), _cuda(g["iconv01"]), _cuda(g["iconv02"]))
+    assert torch.equal(dr2, dr) and torch.equal(pm2, pm)     # deterministic, and the 2-tuple return form
+
+
+def _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, scale, k_size):
+    B, V = srcs.shape[:2]
+    ids, ics = [], []
+    with torch.no_grad():
+        for v in range(V):
+            d, ic = onets.depthnet_forward(dsd, ref, srcs[:, v], ref_cam, src_cams[:, v], scale)
+            ids.append(d[0])
+            ics.append(ic)
+        id1, id2 = onets.group_mean(ids[0::2]), onets.group_mean(ids[1::2])
+        ic1, ic2 = onets.group_mean(ics[0::2]), onets.group_mean(ics[1::2])
+        idr, prob = onets.refinenet_forward(rsd, id1, id2, ic1, ic2, scale)
+        depth = onets.idepth_to_depth(idr)
+    Kinv = np.linalg.inv(ref_cam[:, 1, :3, :3].numpy().astype(np.float64))
+    normal, _ = onrm.depth2normal(depth.numpy(), Kinv, k_size)
+    return depth.numpy(), normal, prob.numpy()
+
+
+@pytest.mark.parametrize("precision,V", [("tf32", 2), ("bf16", 2), ("tf32", 4)])
+def test_pipeline_matches_oracle(precision, V):
+    B, H, W = 2, 64, 96
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(4321 + V, B, H, W, V)
+    dsd = synth.kaiming_state(onets.state_shapes(onets.DEPTHNET_LAYERS), 21, 0.02)
+    rsd = synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), 22, 0.02)
+    dnet = cnmnet_b200.depthNet(idepth_scale=3.0, precision=precision)
+    rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0, precision=precision)
+    dnet.load_state_dict(dsd)
+    rnet.load_state_dict(rsd)
+    dnet, rnet = dnet.to(dev()), rnet.to(dev())
+    want_d, want_n, want_p = _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, 9)
+    outs = {}
+    for graph in (False, True):
+        pipe = cnmnet_b200.CNMPipeline(dnet, rnet, k_size=9, use_graph=graph)
+        d, n, p = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))
+        d2, n2, p2 = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))   # replay
+        assert torch.equal(d, d2) and torch.equal(n, n2) and torch.equal(p, p2)
+        outs[graph] = (d.cpu().numpy(), n.cpu().numpy(), p.cpu().numpy())
+    for a, b in zip(outs[False], outs[True]):
+        assert np.array_equal(a, b)                          # the CUDA graph replays the same kernels
+    d, n, p = outs[True]
+    rel = np.abs(d - want_d) / np.abs(want_d)
+    t_max, t_mean = (1e-3, 3e-4) if precision == "tf32" else (2e-2, 3e-3)
+    assert rel.max() < t_max and rel.mean() < t_mean, (rel.max(), rel.mean())
+    assert np.abs(p - want_p).max() < 10 * t_max
+    # normals amplify depth noise (9x9 plane fit on a ~1e-3 perturbed surface): compare by angle
+    cos = np.clip((n * want_n).sum(1), -1, 1)
+    ang = np.degrees(np.arccos(cos))
+    assert np.median(ang) < (1.0 if precision == "tf32" else 8.0), np.median(ang)
+
+
+def test_weight_updates_are_picked_up():
+    B, H, W = 1, 32, 32
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(9, B, H, W, 2)
+    net = cnmnet_b200.depthNet(idepth_scale=3.0).to(dev())
+    a, _ = net(ref.to(dev()), srcs[:, 0].to(dev()), ref_cam.to(dev()), src_cams[:, 0].to(dev()))
+    with torch.no_grad():
+        net.disp1[0].bias.add_(1.0)
+    b, _ = net(ref.to(dev()), srcs[:, 0].to(dev()), ref_cam.to(dev()), src_cams[:, 0].to(dev()))
+    assert not torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_shape_validation():
+    net = cnmnet_b200.depthNet(idepth_scale=3.0).to(dev())
+    z = torch.zeros((1, 3, 40, 64), device=dev())
+    cam = torch.zeros((1, 2, 4, 4), device=dev())
+    with pytest.raises(ValueError):
+        net(z, z, cam, cam)                                   # 40 is not divisible by 32
+    with pytest.raises(ValueError):
+        cnmnet_b200.depthNet(idepth_scale=5.0).to(dev())(z[:, :, :32], z[:, :, :32], cam, cam)

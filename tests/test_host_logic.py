@@ -1,0 +1,180 @@
+"""CPU tests of the host-side logic: K-step programs + weight packing (emulated in torch), BN folding,
+module / state_dict contract, the C-ABI export list, sharding helpers.  No GPU, no kernel calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cnmnet_b200
+from cnmnet_b200 import _lib, engine, synth
+from cnmnet_b200.dist import shard_range
+from oracle import nets
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def emulate_steps(srcs, steps, wp, bias, stride, ch, relu):
+    """Reference semantics of the device K-step loop (include/cnmnet_b200.h), NHWC float tensors."""
+    N, H, W, _ = srcs[0].shape
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    out = torch.zeros((N, Ho, Wo, wp.shape[0]), dtype=torch.float64)
+    for i, (si, sub, dx, dy, c0) in enumerate(steps):
+        x = srcs[si].double()
+        if stride == 2:
+            x = x[:, (sub >> 1)::2, (sub & 1)::2]
+        hs, ws = x.shape[1:3]
+        a = torch.zeros((N, Ho, Wo, ch), dtype=torch.float64)
+        ys, xs = torch.arange(Ho) + dy, torch.arange(Wo) + dx
+        vy, vx = (ys >= 0) & (ys < hs), (xs >= 0) & (xs < ws)
+        a[:, vy.nonzero().flatten()[:, None], vx.nonzero().flatten()[None, :]] = \
+            x[:, ys[vy][:, None], xs[vx][None, :], c0:c0 + ch]
+        out += a @ wp[:, i * ch:(i + 1) * ch].double().T
+    out += bias.double()
+    return F.relu(out) if relu else out
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("k,stride", [(3, 1), (3, 2), (5, 1), (5, 2), (7, 1), (7, 2)])
+def test_act_steps_reproduce_conv(k, stride):
+    torch.manual_seed(k * 10 + stride)
+    ch, cin, cout, N, H, W = 32, 64, 8, 2, 10, 12
+    x = torch.randn(N, cin, H, W)
+    w = torch.randn(cout, cin, k, k)
+    b = torch.randn(cout)
+    src = engine.act_src(nhwc(x), 0)
+    steps, cols = engine.make_steps([src], k, stride, ch)
+    wp = engine.pack_weights(w, cols, ch, _lib.CNM_TF32)
+    got = emulate_steps([nhwc(x)], steps, wp, b, stride, ch, True)
+    want = nhwc(F.relu(F.conv2d(x.double(), engine.round_tf32(w).double(), b.double(), stride=stride,
+                                padding=(k - 1) // 2)))
+    assert torch.allclose(got, want, atol=1e-9)
+
+
+def test_concat_and_side_sources_reproduce_conv():
+    """iconv3-style layer: cat(upconv [64], skip [32], nearest-upsampled 1-channel disparity)."""
+    torch.manual_seed(3)
+    ch, N, h, w = 32, 2, 5, 6
+    up, skip, disp = torch.randn(N, 64, 2 * h, 2 * w), torch.randn(N, 32, 2 * h, 2 * w), torch.randn(N, 1, h, w)
+    wt, b = torch.randn(16, 97, 3, 3), torch.randn(16)
+    udisp = F.interpolate(disp, scale_factor=2, mode="nearest")
+    want = nhwc(F.conv2d(torch.cat((up, skip, udisp), 1).double(), engine.round_tf32(wt).double(), b.double(), padding=1))
+    # side tensor: channel 3r+s = tap (r,s) of the upsampled disparity (what cnm_pack_disp_taps writes)
+    taps = torch.zeros(N, 2 * h, 2 * w, ch)
+    pd = F.pad(udisp, (1, 1, 1, 1))
+    for r in range(3):
+        for s in range(3):
+            taps[..., 3 * r + s] = pd[:, 0, r:r + 2 * h, s:s + 2 * w]
+    srcs = [engine.act_src(nhwc(up), 0), engine.act_src(nhwc(skip), 64), engine.Src(taps, "taps3x3", 96, ch, 0, 1)]
+    steps, cols = engine.make_steps(srcs, 3, 1, ch)
+    wp = engine.pack_weights(wt, cols, ch, _lib.CNM_TF32)
+    got = emulate_steps([s.buf for s in srcs], steps, wp, b, 1, ch, False)
+    assert torch.allclose(got, want, atol=1e-9)
+
+
+def test_rowtaps_source_reproduces_conv1():
+    """conv1.0-style layer: 3 image channels as a 7-tap row-packed side tensor + cost channels."""
+    torch.manual_seed(4)
+    ch, N, H, W, k = 32, 1, 9, 11, 7
+    img, cost = torch.randn(N, 3, H, W), torch.randn(N, 32, H, W)
+    wt, b = torch.randn(8, 35, k, k), torch.randn(8)
+    want = nhwc(F.conv2d(torch.cat((img, cost), 1).double(), engine.round_tf32(wt).double(), b.double(), padding=3))
+    taps = torch.zeros(N, H, W, ch)
+    pi = F.pad(img, (3, 3, 0, 0))
+    for s in range(k):
+        for c in range(3):
+            taps[..., s * 3 + c] = pi[:, c, :, s:s + W]
+    srcs = [engine.act_src(nhwc(cost), 3), engine.Src(taps, "rowtaps", 0, ch, 0, 3)]
+    steps, cols = engine.make_steps(srcs, k, 1, ch)
+    wp = engine.pack_weights(wt, cols, ch, _lib.CNM_TF32)
+    got = emulate_steps([s.buf for s in srcs], steps, wp, b, 1, ch, False)
+    assert torch.allclose(got, want, atol=1e-9)
+
+
+def test_fold_bn_matches_batchnorm():
+    sd = synth.kaiming_state(nets.state_shapes([("c", "conv", 8, 4, 3)]), seed=5)
+    x = torch.randn(2, 8, 6, 6)
+    want = F.batch_norm(F.conv2d(x, sd["c.0.weight"], padding=1), sd["c.1.running_mean"], sd["c.1.running_var"],
+                        sd["c.1.weight"], sd["c.1.bias"], False, 0.0, 1e-5)
+    wf, bf = engine.fold_bn(sd, "c", 0)
+    assert torch.allclose(F.conv2d(x, wf, bf, padding=1), want, atol=1e-5)
+
+
+def test_round_tf32():
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -3.14159, 1e-30, 65504.0])
+    r = engine.round_tf32(x)
+    assert r[0] == 1.0 and r[1] == 1.0 + 2 ** -10 and r[2] == 1.0 + 2 ** -10
+    assert torch.all((r.view(torch.int32) & 0x1FFF) == 0)
+    assert torch.allclose(r, x, rtol=2 ** -11)
+
+
+def test_module_contract_matches_reference_keys():
+    d = cnmnet_b200.depthNet(idepth_scale=3.0)
+    r = cnmnet_b200.DepthRefineNet(idepth_scale=3.0)
+    for mod, layers in ((d, nets.DEPTHNET_LAYERS), (r, nets.REFINENET_LAYERS)):
+        shapes = nets.state_shapes(layers)
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(v) for k, v in shapes.items())
+    assert sum(p.numel() for p in d.parameters()) == 33898500
+    assert sum(p.numel() for p in r.parameters()) == 10776066
+    # same init stream as the reference constructor
+    torch.manual_seed(0)
+    d0 = cnmnet_b200.depthNet(idepth_scale=3.0).state_dict()
+    ref = nets.reference_init_state(nets.DEPTHNET_LAYERS, 0)
+    assert all(torch.equal(d0[k], ref[k]) for k in ref)
+    # DataParallel-prefixed checkpoints load (eval.py:184-198)
+    d.load_reference_checkpoint({"module." + k: v for k, v in ref.items()})
+    assert torch.equal(d.state_dict()["conv1.0.weight"], ref["conv1.0.weight"])
+    # reference defaults (depthNet_model.py:127, 273)
+    assert cnmnet_b200.DepthRefineNet().idepth_scale == 2 and cnmnet_b200.depthNet().idepth_scale == 3
+
+
+def test_errors_without_gpu_are_loud():
+    d = cnmnet_b200.depthNet()
+    with pytest.raises(RuntimeError):
+        d(torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 32, 32), torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 4, 4))
+    with pytest.raises(RuntimeError):
+        cnmnet_b200.Depth2normal(9)(torch.ones(1, 8, 8), torch.eye(3)[None])
+    with pytest.raises(RuntimeError):
+        d.train()
+    with pytest.raises(AssertionError):  # reference check_sizes contract (inverse_warp.py:18-24)
+        cnmnet_b200.inverse_warp(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4), torch.zeros(1, 3, 5), torch.zeros(1, 3, 3),
+                                 torch.zeros(1, 3, 3))
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cnmnet_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(cnm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES.keys()), declared ^ set(_lib.SIGNATURES.keys())
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.cnm_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.cnm_version()
+    assert _lib.load().cnm_packed_source_bytes(2, 192, 256) == 2 * 195 * 260 * 16
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.ConvSrc) == 24 and ctypes.sizeof(_lib.ConvStep) == 32 and ctypes.sizeof(_lib.ConvDesc) == 48
+
+
+def test_shard_range_partitions():
+    for total in (0, 1, 5, 8, 37):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
