@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the CNMNet inference hot path on B200 (one JSON line on stdout, rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[3], the one the metric "depth frames/s @256x192x64 planes" is quoted
+on): full refine model, 1 ref + 2 source views, 256x192, 64 planes, k_size 9, batch 5 frame tuples per
+GPU, random-init weights (reference init under torch.manual_seed(0)), synthetic frames.  A step is one
+pass of the whole pipeline over one batch: 2 cost volumes -> 2 x DepthNet -> aggregation -> DepthRefineNet
+-> 1/idepth -> depth->normal, replayed as one CUDA graph.  Multi-GPU = weak scaling: every rank runs its
+own batch, then one NCCL all-gather of the outputs.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+H, W, D, V, B_PER_GPU, K_SIZE = 192, 256, 64, 2, 5, 9
+METRIC = "depth frames/s @256x192x64 planes"
+WORKLOAD = "C4: full refine model, 1 ref + 2 src views, 256x192, 64 planes, k_size 9, batch 5 per GPU"
+# algorithmic work (SURVEY.md section 8d / BASELINE.md section 3)
+DEPTHNET_GFLOP, REFINE_GFLOP = 161.43, 112.79
+C2_COST_VOLUME_BYTES = 5 * (2 * 4 * D * H * W + 3 * 4 * 3 * H * W)  # 134 676 480
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_weights(seed=0):
+    """Reference random init (kaiming_normal fan_out, BN 1/0) under torch.manual_seed(seed)."""
+    import cnmnet_b200
+    torch.manual_seed(seed)
+    d = cnmnet_b200.depthNet(idepth_scale=3.0)
+    r = cnmnet_b200.DepthRefineNet(idepth_scale=3.0)
+    return d, r
+
+
+def cpu_pipeline_fps(reps, batch=1):
+    """The reference's algorithm (fp32 torch-CPU ports in oracle/nets.py) on the host cores, bounded sample."""
+    from cnmnet_b200 import synth
+    from oracle import nets as onets
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    dsd = onets.reference_init_state(onets.DEPTHNET_LAYERS, 0)
+    rsd = onets.reference_init_state(onets.REFINENET_LAYERS, 0)
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(1234, batch, H, W, V)
+    onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)  # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)
+        ts.append(time.perf_counter() - t0)
+    return batch / statistics.median(ts), ts
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from cnmnet_b200 import synth
+    from oracle import nets as onets
+    torch.set_num_threads(os.cpu_count() or 1)
+    dsd = onets.reference_init_state(onets.DEPTHNET_LAYERS, 0)
+    rsd = onets.reference_init_state(onets.REFINENET_LAYERS, 0)
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(1234, 1, H, W, V)
+    for _ in range(max(1, min(args.warmup, 2))):
+        onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)
+    steps = max(1, min(args.steps, 12))  # bounded: ~1.5 s of CPU work per step
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)
+    dt = time.perf_counter() - t0
+    fps = steps / dt
+    sample = "%d steps of 1 frame tuple (of the batch of %d) at 256x192x64" % (steps, B_PER_GPU)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample, "host": "torch %s CPU" % torch.__version__},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def time_events(fn, reps, flush):
+    """Average device time of fn() over reps, CUDA events on the current stream, L2 flushed between reps."""
+    ts = []
+    for _ in range(reps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.mean(ts), ts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cnmnet_b200", choices=["cnmnet_b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CNM_PRECISION", "bf16"), choices=["bf16", "tf32"])
+    ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="also print a per-layer timing table on stderr")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import cnmnet_b200
+    from cnmnet_b200 import _lib, synth
+    from cnmnet_b200.dist import gather_outputs
+    lib = _lib.load()
+    peaks = load_peaks()
+    B = B_PER_GPU
+    dnet, rnet = make_weights(0)
+    dnet.precision = rnet.precision = cnmnet_b200.engine.parse_dtype(args.precision)
+    dnet, rnet = dnet.to(dev), rnet.to(dev)
+    pipe = cnmnet_b200.CNMPipeline(dnet, rnet, k_size=K_SIZE, use_graph=True)
+    st = pipe.static_state(B, V, H, W, dev)
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(1234 + rank, B, H, W, V)
+    host = [t.pin_memory() for t in (ref, srcs, ref_cam, src_cams)]
+    pipe.load_inputs(st, *host, non_blocking=False)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    gathered = {}
+
+    def step():
+        pipe.step(st)
+        if world > 1:  # the only collective: gather the outputs (depth, normal, prob) of all ranks
+            for k in ("depth", "normal", "prob"):
+                gathered[k] = gather_outputs(st[k], B * world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches_per_step = st.get("launches_per_step") or 0
+
+    # ---- timed region: exactly K steps, device time per step by CUDA events, L2 flushed in between ----
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        wall0 = time.perf_counter()
+        total_ms = 0.0
+        for _ in range(args.steps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b.record()
+            b.synchronize()
+            total_ms += a.elapsed_time(b)
+        barrier()
+        wall = time.perf_counter() - wall0
+        # ---- end to end through the public wrapper: pinned host inputs in, host outputs back, every step ----
+        out_host = {k: torch.empty(st[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")}
+        for _ in range(2):
+            pipe.load_inputs(st, *host)
+            step()
+            for k in out_host:
+                out_host[k].copy_(st[k], non_blocking=True)
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(args.steps):
+            pipe.load_inputs(st, *host)
+            step()
+            for k in out_host:
+                out_host[k].copy_(st[k], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        barrier()
+        e2e_s = time.perf_counter() - e0
+    t = torch.tensor([total_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
+    ms_per_step = total_ms / args.steps
+    fps = B * world / (ms_per_step * 1e-3)
+    e2e_fps = B * world / (e2e_ms * 1e-3 / args.steps)
+    h2d = sum(x.numel() * 4 for x in host)
+    d2h = sum(x.numel() * 4 for x in out_host.values())
+
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "views": V + 1, "planes": D, "k_size": K_SIZE,
+                   "weights": "reference random init, torch.manual_seed(0)", "parallelism": "dp%d" % world,
+                   "l2": "flushed between timed steps (256 MiB memset, outside the event pair)",
+                   "cuda_graph": True, "precision_note": "tensor-core operands %s, fp32 accumulate" % args.precision},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step),
+        "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+    }
+
+    if rank == 0:
+        # ---- per-kernel live timing for the rooflines (rank 0, outside the timed region) ----
+        s = _lib.stream_ptr()
+        dplan, rplan = st["dplan"], st["rplan"]
+        conv_ms, conv_rows = 0.0, []
+        for plan, tag in ((dplan, "depthnet"), (rplan, "refine")):
+            for name, op in plan.convs.items():
+                ms, _ = time_events(lambda: op(s), 5, flush)
+                conv_ms += ms
+                conv_rows.append((tag + "." + name, ms, op.flops))
+        alg_flop = B * (V * DEPTHNET_GFLOP + REFINE_GFLOP) * 1e9  # real channels only (no padding)
+        issued_flop = sum(r[2] for r in conv_rows)
+        tf = alg_flop / (conv_ms * 1e-3) / 1e12
+        tf32 = args.precision == "tf32"
+        peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
+        line["roofline"] = {
+            "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all %d conv launches of one step)" % len(conv_rows),
+            "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+            "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step,
+            "peak_source": "%s bf16 sustained%s" % (peaks["source"], " x 0.5 for tf32" if tf32 else ""),
+            "issued_tflops_incl_padding": issued_flop / (conv_ms * 1e-3) / 1e12,
+        }
+        # cost volume at BASELINE config 2: NCHW fp32, batch 5, 2 views
+        refd, srcd = st["ref"], st["src"].view(V * B, 3, H, W)
+        hk = dplan.hk
+        vol = torch.empty((V * B, D, H, W), dtype=torch.float32, device=dev)
+
+        def cv():
+            _lib.check(lib.cnm_pack_source(srcd.data_ptr(), dplan.tex.data_ptr(), V * B, H, W, s))
+            _lib.check(lib.cnm_cost_volume(refd.data_ptr(), dplan.tex.data_ptr(), hk.data_ptr(), vol.data_ptr(), B, V, H,
+                                           W, D, 0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
+
+        def cv_only():
+            _lib.check(lib.cnm_cost_volume(refd.data_ptr(), dplan.tex.data_ptr(), hk.data_ptr(), vol.data_ptr(), B, V, H,
+                                           W, D, 0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
+
+        cv()
+        ms_cv, _ = time_events(cv, 20, flush)
+        ms_cvk, _ = time_events(cv_only, 20, flush)
+        gbs = C2_COST_VOLUME_BYTES / (ms_cvk * 1e-3) / 1e9
+        line["roofline_cost_volume"] = {
+            "kernel": "cost_volume_kernel (C2: 256x192x64, 2 views, batch 5, fp32 NCHW)", "bound": "hbm",
+            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+            "us_per_launch": ms_cvk * 1e3, "us_with_source_repack": ms_cv * 1e3, "algorithmic_bytes": C2_COST_VOLUME_BYTES,
+            "peak_source": peaks["source"],
+        }
+        # depth -> normal at C3 and the aggregation at C4
+        nrm = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        ms_n, _ = time_events(lambda: _lib.check(lib.cnm_depth2normal(st["depth"].data_ptr(), st["Kinv"].data_ptr(),
+                                                                      nrm.data_ptr(), None, B, H, W, K_SIZE, s)), 20, flush)
+        nb = B * 16 * H * W
+        line["roofline_normals"] = {"kernel": "depth2normal_kernel (C3: 256x192, batch 5, k=9)", "bound": "hbm",
+                                    "achieved": nb / (ms_n * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": nb / (ms_n * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_launch": ms_n * 1e3,
+                                    "algorithmic_bytes": nb}
+        if args.layers:
+            for name, ms, fl in sorted(conv_rows, key=lambda r: -r[1]):
+                sys.stderr.write("%-28s %8.3f ms  %7.1f TFLOP/s issued\n" % (name, ms, fl / ms / 1e9))
+        if not args.no_cpu_baseline and world == 1:
+            fps_cpu, ts = cpu_pipeline_fps(args.cpu_reps)
+            line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "%d timed runs of 1 frame tuple at 256x192x64 (median), fp32 torch-CPU port "
+                                              "of the reference pipeline" % len(ts)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

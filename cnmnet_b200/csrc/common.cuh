@@ -48,8 +48,15 @@ __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return _
 
 template <typename T>
 __device__ __forceinline__ T from_f(float v);
+// fp32 act tensors are tcgen05 kind::tf32 operands: store them tf32-rounded (nearest, ties away) so that the
+// tensor core's truncation of the low 13 mantissa bits is exact and every consumer sees the same value
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
 template <>
-__device__ __forceinline__ float from_f<float>(float v) { return v; }
+__device__ __forceinline__ float from_f<float>(float v) { return round_tf32(v); }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
@@ -64,7 +71,7 @@ struct Vec16<float> {
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
   }
   __device__ static __forceinline__ void store(float* p, const float* f) {
-    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p) = make_float4(round_tf32(f[0]), round_tf32(f[1]), round_tf32(f[2]), round_tf32(f[3]));
   }
 };
 template <>

@@ -232,3 +232,75 @@ def reference_init_state(layers, seed):
     """state_dict equal to what the reference constructor produces under torch.manual_seed(seed)."""
     torch.manual_seed(seed)
     return _RefModules(layers).state_dict()
+
+
+def cost_volume_torch(left_image, right_image, left_cam, right_cam, idepth_scale=3.0, num_planes=64):
+    """fp32 torch-CPU port of the reference's camera pre-processing + getVolume, op for op
+    (depth_util.py:13-56, depthNet_model.py:185-224).  Used for the timed CPU baseline (it runs at the
+    reference's own speed: 64 x {mul, add, div, grid_sample, abs, sum}); parity checks use the fp64
+    numpy restatement in oracle/cost_volume.py."""
+    B, C, H, W = left_image.shape
+    idmin, idmax = _cv.idepth_range(float(idepth_scale))
+    pix = np.indices([W, H]).astype(np.float32)
+    pix = np.concatenate((pix, np.ones([1, W, H], dtype=np.float32)), axis=0).reshape(3, -1)
+    pix = torch.from_numpy(pix)
+    left_E, left_K = left_cam[:, 0], left_cam[:, 1, :3, :3]
+    right_E, right_K = right_cam[:, 0], right_cam[:, 1, :3, :3]
+    r2l = torch.matmul(right_E, left_E.inverse())
+    R, t = r2l[:, :3, :3], r2l[:, :3, 3]
+    KRKiUV = torch.matmul(torch.matmul(right_K, torch.matmul(R, left_K.inverse())), pix)
+    KT = torch.matmul(right_K, t.unsqueeze(-1))
+    step = (idmax - idmin) / (num_planes - 1.0)
+    norm = torch.tensor([W / 2.0, H / 2.0], dtype=torch.float32).view(1, 2, 1)
+    out = torch.empty((B, num_planes, H, W), dtype=torch.float32)
+    for d in range(num_planes):
+        z = 1.0 / (idmin + d * step)
+        tr = KRKiUV * z + KT
+        uv = tr[:, 0:2, :] / (tr[:, 2:3, :] + 1e-6)
+        uv = ((uv - norm) / norm).view(B, 2, W, H).permute(0, 3, 2, 1)
+        warped = F.grid_sample(right_image, uv, mode="bilinear", padding_mode="zeros", align_corners=False)
+        out[:, d] = torch.sum(torch.abs(warped - left_image), dim=1)
+    return out
+
+
+def depth2normal_torch(depth, intrinsic_inv, k_size=9):
+    """fp32 torch-CPU port of Depth2normal.forward without planes (depth_util.py:149-203), op for op:
+    Unfold -> mask -> bmm -> det -> inverse -> matmul -> normalise.  Timed CPU baseline only."""
+    b, h, w = depth.shape
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=depth.dtype), torch.arange(w, dtype=depth.dtype), indexing="ij")
+    pix = torch.stack((xs, ys, torch.ones_like(xs)), 0).reshape(1, 3, -1).expand(b, 3, -1)
+    points = intrinsic_inv.bmm(pix).view(b, 3, h, w) * depth.unsqueeze(1)
+    valid = ((depth > 0) & (depth < 10.0)).to(depth.dtype).unsqueeze(1)
+    kk = k_size * k_size
+    unf = torch.nn.Unfold(kernel_size=(k_size, k_size), padding=k_size // 2, stride=(1, 1))
+    A = unf(points).view(-1, 3, kk, h, w).permute(0, 3, 4, 2, 1)
+    vm = unf(valid).view(-1, 1, kk, h, w).permute(0, 3, 4, 2, 1).repeat(1, 1, 1, 1, 3) > 0.5
+    A = torch.where(vm, A, torch.zeros_like(A))
+    At = torch.transpose(A, 3, 4).reshape(-1, 3, kk)
+    A = A.reshape(-1, kk, 3)
+    M = torch.bmm(At, A)
+    det = M.det()
+    bad = torch.isnan(det) | (det < 1e-5)
+    M = torch.where(bad.view(-1, 1, 1), torch.eye(3, dtype=depth.dtype).expand_as(M), M)
+    n = torch.matmul(torch.matmul(torch.inverse(M), At), torch.ones(At.shape[0], kk, 1, dtype=depth.dtype)).squeeze(-1)
+    n = n / (torch.norm(n, dim=1, keepdim=True) + 1e-5)
+    return n.view(b, h, w, 3).permute(0, 3, 1, 2), points
+
+
+def reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, idepth_scale=3.0, k_size=9):
+    """The reference's eval_refine call sequence (eval.py:440-455) on the fp32 torch-CPU ports above:
+    V x depthNet (with its own cost volume), refine, 1/idepth, Depth2normal.  -> depth, normal, prob."""
+    V = srcs.shape[1]
+    ids, ics = [], []
+    with torch.no_grad():
+        for v in range(V):
+            vol = cost_volume_torch(ref, srcs[:, v], ref_cam, src_cams[:, v], idepth_scale)
+            d, ic = depthnet_trunk(dsd, torch.cat((ref, vol), 1), idepth_scale)
+            ids.append(d[0])
+            ics.append(ic)
+        idr, prob = refinenet_forward(rsd, group_mean(ids[0::2]), group_mean(ids[1::2]), group_mean(ics[0::2]),
+                                      group_mean(ics[1::2]), idepth_scale)
+        depth = idepth_to_depth(idr)
+        Kinv = torch.inverse(ref_cam[:, 1, :3, :3])
+        normal, _ = depth2normal_torch(depth, Kinv, k_size)
+    return depth, normal, prob

@@ -73,7 +73,7 @@ def test_cost_volume_c2_size_vs_oracle():
                                        3.0, _lib.VOLUME_ACT, dtype, st))
         back = from_act(act, dtype)
         want = out.cpu()
-        assert torch.equal(back, want.to(torch.bfloat16).float() if dtype == _lib.CNM_BF16 else want)
+        assert torch.equal(back, quantize(want, dtype))
 
 
 @pytest.mark.parametrize("H,W", [(24, 40), (33, 70), (8, 8)])
@@ -192,7 +192,7 @@ def test_upsample_head_packers(dtype):
     up = torch.empty((2, 12, 20, 64), dtype=engine.TORCH_DTYPE[dtype], device=dev())
     _lib.check(lib.cnm_upsample2x(xa.data_ptr(), up.data_ptr(), 2, 6, 10, 64, dtype, st))
     want = F.interpolate(quantize(x, dtype), scale_factor=2, mode="bilinear", align_corners=False)
-    tol = 1e-2 if dtype == _lib.CNM_BF16 else 1e-6
+    tol = 2e-2 if dtype == _lib.CNM_BF16 else 2e-3   # one output rounding (2^-9 / 2^-11 relative)
     assert (from_act(up, dtype) - want).abs().max() < tol
     # head: conv3x3(C->1)+bias -> scale*sigmoid
     w = torch.randn(1, 64, 3, 3, generator=g) * 0.05

@@ -133,3 +133,15 @@ def test_inverse_warp_matches_reference(golden_dir):
     t = lambda k: torch.from_numpy(g[k])
     out = nets.inverse_warp(t("feat"), t("depth"), t("pose"), t("K"), t("Kinv"))
     assert np.allclose(out.numpy(), g["warped"], rtol=1e-4, atol=1e-4)
+
+
+def test_fast_torch_ports_match_reference(golden_dir):
+    """The fp32 torch ports used for the timed CPU baseline reproduce the reference's outputs."""
+    g = _load(golden_dir, "cost_volume_s3.npz")
+    t = lambda k: torch.from_numpy(g[k])
+    vol = nets.cost_volume_torch(t("left"), t("right"), t("left_cam"), t("right_cam"), 3.0)
+    assert rel_l2(vol.numpy(), g["volume"]) < 1e-6
+    g = _load(golden_dir, "normals_k9.npz")
+    n, p = nets.depth2normal_torch(torch.from_numpy(g["depth"]), torch.from_numpy(g["Kinv"]), 9)
+    fin = np.isfinite(g["normals"]) & np.isfinite(n.numpy())
+    assert fin.mean() > 0.99 and np.abs(n.numpy() - g["normals"])[fin].mean() < 1e-4
