@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int4 st_next = __ldg(reinterpret_cast<const int4*>(p.steps));
+      int c0_next = __ldg(&p.steps[0].c0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.tiles_n;
         int m = tile / p.tiles_n;
@@ -200,8 +202,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int y0 = (m % p.tiles_y) * p.TH;
         const int n0 = (m / p.tiles_y) * p.NB;
         for (int ks = 0; ks < p.num_steps; ++ks) {
-          const int4 st = __ldg(reinterpret_cast<const int4*>(p.steps + ks));  // src, sub, dx, dy
-          const int c0 = __ldg(&p.steps[ks].c0);
+          const int4 st = st_next;  // src, sub, dx, dy
+          const int c0 = c0_next;
+          {  // prefetch the next step descriptor: its L2 latency overlaps the barrier wait below
+            const int kn = (ks + 1 == p.num_steps) ? 0 : ks + 1;
+            st_next = __ldg(reinterpret_cast<const int4*>(p.steps + kn));
+            c0_next = __ldg(&p.steps[kn].c0);
+          }
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
           const uint32_t sa = base + stage * L::STAGE_BYTES;
@@ -401,10 +408,18 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.tiles_y = (d->Ho + p.TH - 1) / p.TH;
   p.tiles_b = (d->N + p.NB - 1) / p.NB;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  // column-tile width: minimise waves x cycles-per-K-step.  Per K-step the MMAs take 2*BN cycles (M=128,
+  // 4 x K=32B) and the smem operand reads (128 + BN) cycles, whichever is larger.
   int BN = 64;
-  if (d->Cout % 256 == 0 && m_tiles * (d->Cout / 256) >= 148) BN = 256;
-  else if (d->Cout % 128 == 0 && m_tiles * (d->Cout / 128) >= 148) BN = 128;
-  else if (d->Cout % 256 == 0 && m_tiles * (d->Cout / 64) > 4 * 148) BN = 256;
+  long best = -1;
+  for (int cand = 256; cand >= 64; cand >>= 1) {
+    if (d->Cout % cand) continue;
+    const long tiles = (long)m_tiles * (d->Cout / cand);
+    const long waves = (tiles + 147) / 148;
+    const long cyc = (2 * cand > 128 + cand) ? 2 * cand : 128 + cand;
+    const long cost = waves * cyc;
+    if (best < 0 || cost < best) { best = cost; BN = cand; }
+  }
   p.tiles_n = d->Cout / BN;
   p.steps = steps;
   p.bias = bias;
