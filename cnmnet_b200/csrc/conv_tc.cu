@@ -408,15 +408,16 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.tiles_y = (d->Ho + p.TH - 1) / p.TH;
   p.tiles_b = (d->N + p.NB - 1) / p.NB;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
-  // column-tile width: minimise waves x cycles-per-K-step.  Per K-step the MMAs take 2*BN cycles (M=128,
-  // 4 x K=32B) and the smem operand reads (128 + BN) cycles, whichever is larger.
+  // column-tile width: minimise waves x measured cycles per K-step.  The main loop is bound by operand delivery
+  // (L2 -> smem bytes in flight / loaded latency), not by MMA issue: measured on B200 (profiles/r01_conv_tc_ncu.md)
+  // a K-step costs ~800 cycles at BN=256 and ~575 at BN=128 and BN=64, so wide tiles win unless they cost a wave.
   int BN = 64;
   long best = -1;
   for (int cand = 256; cand >= 64; cand >>= 1) {
     if (d->Cout % cand) continue;
     const long tiles = (long)m_tiles * (d->Cout / cand);
     const long waves = (tiles + 147) / 148;
-    const long cyc = (2 * cand > 128 + cand) ? 2 * cand : 128 + cand;
+    const long cyc = cand == 256 ? 800 : (cand == 128 ? 575 : 560);
     const long cost = waves * cyc;
     if (best < 0 || cost < best) { best = cost; BN = cand; }
   }

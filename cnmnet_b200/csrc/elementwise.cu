@@ -61,10 +61,10 @@ __device__ __forceinline__ void store_chunk(T* dst, const float* v) {
   for (int i = 0; i < CH; i += Vec16<T>::N) Vec16<T>::store(dst + i, v + i);
 }
 
-template <typename T>
-__global__ void pack_row_taps_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int Cx, int H,
-                                     int W, int kw) {
+template <typename T, int KW, int CX>
+__global__ void pack_row_taps_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int H, int W) {
   constexpr int CH = 128 / sizeof(T);
+  static_assert(KW * CX <= CH, "taps must fit one chunk");
   const size_t HW = (size_t)H * W;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * HW) return;
@@ -74,18 +74,13 @@ __global__ void pack_row_taps_kernel(const float* __restrict__ x, T* __restrict_
   float v[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) v[j] = 0.0f;
-  const int r = kw / 2;
-#pragma unroll 1
-  for (int s = 0; s < kw; ++s) {
-    const int xs = xx + s - r;
-    if (xs < 0 || xs >= W) continue;
-    for (int c = 0; c < Cx; ++c) {
-      const float val = __ldg(x + ((size_t)n * Cx + c) * HW + (size_t)y * W + xs);
-      const int j = s * Cx + c;
+  const float* row = x + (size_t)n * CX * HW + (size_t)y * W;
 #pragma unroll
-      for (int q = 0; q < CH; ++q)
-        if (q == j) v[q] = val;  // keeps v[] in registers
-    }
+  for (int s = 0; s < KW; ++s) {
+    const int xs = xx + s - KW / 2;
+    const bool ok = xs >= 0 && xs < W;
+#pragma unroll
+    for (int c = 0; c < CX; ++c) v[s * CX + c] = ok ? __ldg(row + (size_t)c * HW + xs) : 0.0f;
   }
   store_chunk<T>(dst + i * CH, v);
 }
@@ -200,81 +195,107 @@ __global__ void refine_sum_nchw_kernel(const float* __restrict__ iconv, T* __res
 }
 
 // ---- bilinear x2 upsample (align_corners=False): weights 0.25/0.75, clamped at the border ------
+// one thread per (low-res pixel, 16-byte channel vector): 9 clamped loads in flight -> the 2x2 output quad
 template <typename T>
-__global__ void upsample2x_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int h, int w, int C) {
+__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int h, int w, int C) {
   constexpr int VN = Vec16<T>::N;
   const int cv = C / VN;
-  const int H = 2 * h, W = 2 * w;
-  const size_t total = (size_t)N * H * W * cv;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * VN;
-    size_t t = i / cv;
-    const int X = (int)(t % W);
-    t /= W;
-    const int Y = (int)(t % H);
-    const int n = (int)(t / H);
-    // src = (dst + 0.5)/2 - 0.5, clamped at 0
-    const float sx = fmaxf((X + 0.5f) * 0.5f - 0.5f, 0.0f), sy = fmaxf((Y + 0.5f) * 0.5f - 0.5f, 0.0f);
-    const int x0 = (int)sx, y0 = (int)sy;
-    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
-    const float lx = sx - x0, ly = sy - y0;
-    const T* base = src + (size_t)n * h * w * C + c;
-    float a[VN], b[VN], cc[VN], d[VN], o[VN];
-    Vec16<T>::load(base + ((size_t)y0 * w + x0) * C, a);
-    Vec16<T>::load(base + ((size_t)y0 * w + x1) * C, b);
-    Vec16<T>::load(base + ((size_t)y1 * w + x0) * C, cc);
-    Vec16<T>::load(base + ((size_t)y1 * w + x1) * C, d);
-    const float w00 = (1.f - lx) * (1.f - ly), w10 = lx * (1.f - ly), w01 = (1.f - lx) * ly, w11 = lx * ly;
+  const size_t total = (size_t)N * h * w * cv;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % cv) * VN;
+  size_t t = i / cv;
+  const int x = (int)(t % w);
+  t /= w;
+  const int y = (int)(t % h);
+  const int n = (int)(t / h);
+  const int xm = max(x - 1, 0), xp = min(x + 1, w - 1), ym = max(y - 1, 0), yp = min(y + 1, h - 1);
+  const T* base = src + (size_t)n * h * w * C + c;
+  float v[3][3][VN];
+  const int ys[3] = {ym, y, yp}, xs[3] = {xm, x, xp};
 #pragma unroll
-    for (int j = 0; j < VN; ++j) o[j] = a[j] * w00 + b[j] * w10 + cc[j] * w01 + d[j] * w11;
-    Vec16<T>::store(dst + (((size_t)n * H + Y) * W + X) * C + c, o);
-  }
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) Vec16<T>::load(base + ((size_t)ys[a] * w + xs[b]) * C, v[a][b]);
+  // output (2y+dy, 2x+dx): source coordinate y - 0.25 (dy=0) or y + 0.25 (dy=1): rows (y-1,y) w (.25,.75) or (y,y+1) w (.75,.25)
+  const int W2 = 2 * w;
+  T* out = dst + (((size_t)n * 2 * h + 2 * y) * W2 + 2 * x) * C + c;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float fx = dx ? 0.25f : 0.75f, fy = dy ? 0.25f : 0.75f;  // fraction toward the right / lower tap
+      float o[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        const float a00 = v[dy][dx][j], a01 = v[dy][dx + 1][j], a10 = v[dy + 1][dx][j], a11 = v[dy + 1][dx + 1][j];
+        o[j] = a00 * ((1.f - fx) * (1.f - fy)) + a01 * (fx * (1.f - fy)) + a10 * ((1.f - fx) * fy) + a11 * (fx * fy);
+      }
+      Vec16<T>::store(out + ((size_t)dy * W2 + dx) * C, o);
+    }
 }
 
-// ---- 1-channel 3x3 head: 8 lanes per pixel, fp32 accumulate, sigmoid epilogue -------------------
+// ---- 1-channel 3x3 head: 8 lanes per pixel, 8 pixels per lane group, fp32 accumulate, sigmoid epilogue ------
+constexpr int HEAD_PIX_PER_BLOCK = 256;  // 32 lane groups x 8 pixels: amortises the weight staging
+
 template <typename T>
 __global__ void __launch_bounds__(256)
     head3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, float bias, float scale,
                    float* __restrict__ out, float* __restrict__ logits, int N, int H, int W, int C) {
-  extern __shared__ float ws[];  // [9*C]
+  extern __shared__ float ws[];  // [9*C], order (r, s, c)
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) ws[i] = __ldg(w + i);
   __syncthreads();
   constexpr int VN = Vec16<T>::N;
-  const size_t HW = (size_t)H * W;
-  const size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
-  const bool active = pix < (size_t)N * HW;
-  float acc = 0.0f;
-  if (active) {
-    const int n = (int)(pix / HW);
-    const size_t p = pix % HW;
-    const int y = (int)(p / W), xx = (int)(p % W);
+  const size_t HW = (size_t)H * W, total = (size_t)N * HW;
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+#pragma unroll 1
+  for (int it = 0; it < HEAD_PIX_PER_BLOCK / 32; ++it) {
+    // consecutive lane groups take consecutive pixels: the 8 lanes of a group read one 128-byte run per tap
+    const size_t pix = (size_t)blockIdx.x * HEAD_PIX_PER_BLOCK + it * 32 + grp;
+    const bool active = pix < total;
+    float acc = 0.0f;
+    if (active) {
+      const int n = (int)(pix / HW);
+      const size_t p = pix % HW;
+      const int y = (int)(p / W), xx = (int)(p % W);
+      for (int c = sub * VN; c < C; c += 8 * VN) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int yy = y + r - 1;
-      if (yy < 0 || yy >= H) continue;
+        for (int r = 0; r < 3; ++r) {  // one kernel row at a time: 3 vector loads in flight, then 3*VN FMAs
+          float v[3][VN];
+          const int yy = y + r - 1;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int xs = xx + s - 1;
-        if (xs < 0 || xs >= W) continue;
-        const T* px = x + (((size_t)n * H + yy) * W + xs) * C;
-        const float* wp = ws + (r * 3 + s) * C;
-        for (int c = sub * VN; c < C; c += 8 * VN) {
-          float v[VN];
-          Vec16<T>::load(px + c, v);
+          for (int s = 0; s < 3; ++s) {
+            const int xs = xx + s - 1;
+            if (yy >= 0 && yy < H && xs >= 0 && xs < W) {
+              Vec16<T>::load(x + (((size_t)n * H + yy) * W + xs) * C + c, v[s]);
+            } else {
 #pragma unroll
-          for (int j = 0; j < VN; ++j) acc = fmaf(v[j], wp[c + j], acc);
+              for (int j = 0; j < VN; ++j) v[s][j] = 0.0f;
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const float* wp = ws + (r * 3 + s) * C + c;
+#pragma unroll
+            for (int j = 0; j < VN; j += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wp + j);
+              acc = fmaf(v[s][j], w4.x, acc);
+              acc = fmaf(v[s][j + 1], w4.y, acc);
+              acc = fmaf(v[s][j + 2], w4.z, acc);
+              acc = fmaf(v[s][j + 3], w4.w, acc);
+            }
+          }
         }
       }
     }
-  }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (active && sub == 0) {
-    const float l = acc + bias;
-    if (logits) logits[pix] = l;
-    out[pix] = scale / (1.0f + expf(-l));
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (active && sub == 0) {
+      const float l = acc + bias;
+      if (logits) logits[pix] = l;
+      out[pix] = scale / (1.0f + expf(-l));
+    }
   }
 }
 
@@ -313,11 +334,11 @@ extern "C" int cnm_pack_row_taps(const float* x, void* dst, int N, int Nsrc, int
                                  void* stream) {
   CNM_REQUIRE(x && dst && N > 0 && Nsrc > 0 && Cx > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT,
               "cnm_pack_row_taps: bad argument");
-  CNM_REQUIRE(kw >= 1 && (kw & 1) && kw * Cx <= chunk_channels(dtype), CNM_ERR_UNSUPPORTED_SHAPE,
-              "cnm_pack_row_taps: kw*Cx=%d exceeds one chunk", kw * Cx);
+  CNM_REQUIRE(kw == 7 && Cx == 3, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_pack_row_taps: only kw=7, Cx=3 (conv1.0 of DepthNet) is instantiated, got kw=%d Cx=%d", kw, Cx);
   const size_t total = (size_t)N * H * W;
-  DISPATCH_DTYPE(dtype, (pack_row_taps_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-                            x, (T*)dst, N, Nsrc, Cx, H, W, kw)));
+  DISPATCH_DTYPE(dtype, (pack_row_taps_kernel<T, 7, 3><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+                            x, (T*)dst, N, Nsrc, H, W)));
   return after_launch("cnm_pack_row_taps");
 }
 
@@ -367,10 +388,8 @@ extern "C" int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, i
   CNM_REQUIRE(src && dst && N > 0 && h > 0 && w > 0 && C > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_upsample2x: bad argument");
   CNM_REQUIRE(C % 8 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_upsample2x: C=%d must be a multiple of 8", C);
   DISPATCH_DTYPE(dtype, {
-    const size_t total = (size_t)N * 4 * h * w * (C / Vec16<T>::N);
-    size_t blocks = (total + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    upsample2x_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, N, h, w, C);
+    const size_t total = (size_t)N * h * w * (C / Vec16<T>::N);
+    upsample2x_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, N, h, w, C);
   });
   return after_launch("cnm_upsample2x");
 }
@@ -379,9 +398,9 @@ extern "C" int cnm_head3x3(const void* x, const float* w, float bias, float scal
                            int H, int W, int C, int dtype, void* stream) {
   CNM_REQUIRE(x && w && out && N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_head3x3: bad argument");
   CNM_REQUIRE(C % 64 == 0 && C <= 1024, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head3x3: C=%d must be a multiple of 64", C);
-  const size_t threads = (size_t)N * H * W * 8;
+  const size_t blocks = ((size_t)N * H * W + HEAD_PIX_PER_BLOCK - 1) / HEAD_PIX_PER_BLOCK;
   const size_t smem = (size_t)9 * C * sizeof(float);
-  DISPATCH_DTYPE(dtype, (head3x3_kernel<T><<<(unsigned)((threads + 255) / 256), 256, smem, (cudaStream_t)stream>>>(
+  DISPATCH_DTYPE(dtype, (head3x3_kernel<T><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
                             (const T*)x, w, bias, scale, out, logits, N, H, W, C)));
   return after_launch("cnm_head3x3");
 }

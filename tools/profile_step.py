@@ -1,5 +1,6 @@
 """One un-graphed pipeline step (after one warm-up) for ncu captures:
-    ncu --set full --clock-control none --import-source on -k regex:conv_tc -s <n> -c 3 -o gpurun_out/prof python tools/profile_step.py
+    ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc -c 3 \
+        -o gpurun_out/prof python tools/profile_step.py
 Also runs the C2 cost-volume micro-benchmark (NCHW fp32) and the C3 depth->normal call once."""
 import os
 import sys
@@ -19,14 +20,17 @@ dnet.precision = rnet.precision = cnmnet_b200.engine.parse_dtype(precision)
 pipe = cnmnet_b200.CNMPipeline(dnet.to(dev), rnet.to(dev), k_size=9, use_graph=False)
 st = pipe.static_state(B, V, H, W, dev)
 pipe.load_inputs(st, *synth.frame_tuples(1234, B, H, W, V), non_blocking=False)
-for _ in range(2):
-    pipe.step(st)
+pipe.step(st)  # warm-up (lazy attribute setup)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off: the capture starts here
+pipe.step(st)
 torch.cuda.synchronize()
 lib, s = _lib.load(), _lib.stream_ptr()
 dplan = st["dplan"]
 vol = torch.empty((V * B, 64, H, W), dtype=torch.float32, device=dev)
-for _ in range(2):
+for _ in range(1):
     _lib.check(lib.cnm_cost_volume(st["ref"].data_ptr(), dplan.tex.data_ptr(), dplan.hk.data_ptr(), vol.data_ptr(), B, V, H,
                                    W, 64, 0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done", _lib.launch_count())
