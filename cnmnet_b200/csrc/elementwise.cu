@@ -235,67 +235,53 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ s
     }
 }
 
-// ---- 1-channel 3x3 head: 8 lanes per pixel, 8 pixels per lane group, fp32 accumulate, sigmoid epilogue ------
-constexpr int HEAD_PIX_PER_BLOCK = 256;  // 32 lane groups x 8 pixels: amortises the weight staging
-
-template <typename T>
+// ---- 1-channel 3x3 head: LPP lanes per pixel, branch-free so all 9 tap loads are in flight at once --------
+template <typename T, int LPP>
 __global__ void __launch_bounds__(256)
     head3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, float bias, float scale,
                    float* __restrict__ out, float* __restrict__ logits, int N, int H, int W, int C) {
-  extern __shared__ float ws[];  // [9*C], order (r, s, c)
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) ws[i] = __ldg(w + i);
-  __syncthreads();
   constexpr int VN = Vec16<T>::N;
   const size_t HW = (size_t)H * W, total = (size_t)N * HW;
-  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
-#pragma unroll 1
-  for (int it = 0; it < HEAD_PIX_PER_BLOCK / 32; ++it) {
-    // consecutive lane groups take consecutive pixels: the 8 lanes of a group read one 128-byte run per tap
-    const size_t pix = (size_t)blockIdx.x * HEAD_PIX_PER_BLOCK + it * 32 + grp;
-    const bool active = pix < total;
-    float acc = 0.0f;
-    if (active) {
-      const int n = (int)(pix / HW);
-      const size_t p = pix % HW;
-      const int y = (int)(p / W), xx = (int)(p % W);
-      for (int c = sub * VN; c < C; c += 8 * VN) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t pix = gt / LPP;
+  const int sub = (int)(gt % LPP);
+  const bool active = pix < total;
+  const size_t pc = active ? pix : total - 1;  // clamp: inactive lanes still take part in the shuffles
+  const int n = (int)(pc / HW);
+  const size_t p = pc % HW;
+  const int y = (int)(p / W), xx = (int)(p % W);
+  float acc = 0.0f;
+  for (int c = sub * VN; c < C; c += LPP * VN) {
+    float v[9][VN];
+    float valid[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {  // one kernel row at a time: 3 vector loads in flight, then 3*VN FMAs
-          float v[3][VN];
-          const int yy = y + r - 1;
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xs = xx + t % 3 - 1;
+      valid[t] = (yy >= 0 && yy < H && xs >= 0 && xs < W) ? 1.0f : 0.0f;
+      const int yc = min(max(yy, 0), H - 1), xc = min(max(xs, 0), W - 1);
+      Vec16<T>::load(x + (((size_t)n * H + yc) * W + xc) * C + c, v[t]);
+    }
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int xs = xx + s - 1;
-            if (yy >= 0 && yy < H && xs >= 0 && xs < W) {
-              Vec16<T>::load(x + (((size_t)n * H + yy) * W + xs) * C + c, v[s]);
-            } else {
+    for (int t = 0; t < 9; ++t) {
+      const float* wp = w + t * C + c;  // (r, s, c) order; L1-resident, same address across the pixel's lanes
+      float part = 0.0f;
 #pragma unroll
-              for (int j = 0; j < VN; ++j) v[s][j] = 0.0f;
-            }
-          }
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const float* wp = ws + (r * 3 + s) * C + c;
-#pragma unroll
-            for (int j = 0; j < VN; j += 4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wp + j);
-              acc = fmaf(v[s][j], w4.x, acc);
-              acc = fmaf(v[s][j + 1], w4.y, acc);
-              acc = fmaf(v[s][j + 2], w4.z, acc);
-              acc = fmaf(v[s][j + 3], w4.w, acc);
-            }
-          }
-        }
+      for (int j = 0; j < VN; j += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + j));
+        part = fmaf(v[t][j], w4.x, part);
+        part = fmaf(v[t][j + 1], w4.y, part);
+        part = fmaf(v[t][j + 2], w4.z, part);
+        part = fmaf(v[t][j + 3], w4.w, part);
       }
+      acc = fmaf(part, valid[t], acc);
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (active && sub == 0) {
-      const float l = acc + bias;
-      if (logits) logits[pix] = l;
-      out[pix] = scale / (1.0f + expf(-l));
-    }
+  }
+#pragma unroll
+  for (int o = 1; o < LPP; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (active && sub == 0) {
+    const float l = acc + bias;
+    if (logits) logits[pix] = l;
+    out[pix] = scale / (1.0f + expf(-l));
   }
 }
 
@@ -398,9 +384,18 @@ extern "C" int cnm_head3x3(const void* x, const float* w, float bias, float scal
                            int H, int W, int C, int dtype, void* stream) {
   CNM_REQUIRE(x && w && out && N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_head3x3: bad argument");
   CNM_REQUIRE(C % 64 == 0 && C <= 1024, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head3x3: C=%d must be a multiple of 64", C);
-  const size_t blocks = ((size_t)N * H * W + HEAD_PIX_PER_BLOCK - 1) / HEAD_PIX_PER_BLOCK;
-  const size_t smem = (size_t)9 * C * sizeof(float);
-  DISPATCH_DTYPE(dtype, (head3x3_kernel<T><<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
-                            (const T*)x, w, bias, scale, out, logits, N, H, W, C)));
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_DTYPE(dtype, {
+    const int lanes = C / Vec16<T>::N;  // one 16-byte vector per lane
+    const int lpp = lanes >= 32 ? 32 : (lanes >= 16 ? 16 : 8);
+    const size_t threads = (size_t)N * H * W * lpp;
+    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    if (lpp == 32)
+      head3x3_kernel<T, 32><<<blocks, 256, 0, s>>>((const T*)x, w, bias, scale, out, logits, N, H, W, C);
+    else if (lpp == 16)
+      head3x3_kernel<T, 16><<<blocks, 256, 0, s>>>((const T*)x, w, bias, scale, out, logits, N, H, W, C);
+    else
+      head3x3_kernel<T, 8><<<blocks, 256, 0, s>>>((const T*)x, w, bias, scale, out, logits, N, H, W, C);
+  });
   return after_launch("cnm_head3x3");
 }
