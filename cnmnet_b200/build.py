@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcnmnet_b200.so")
-SOURCES = ["api.cu", "cost_volume.cu", "normals.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu"]
+SOURCES = ["api.cu", "cost_volume.cu", "normals.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -25,7 +25,7 @@ def _stale(obj, deps):
 
 
 def build(force=False, verbose=False):
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "cnmnet_b200.h")]
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "cnmnet_b200.h")]
     objs = []
     procs = []
     for src in SOURCES:

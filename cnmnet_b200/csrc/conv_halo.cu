@@ -1,0 +1,344 @@
+// K2h: stride-1 convolution + folded BatchNorm + ReLU as implicit GEMM on tcgen05 with a ROW-HALO A slab and two
+// pixel tiles per weight tile.  Same math and act/weight layouts as conv_tc.cu; what changes is operand delivery,
+// the measured limiter of that kernel (profiles/r01_conv_tc_ncu.md: every tap re-read its 16 KB pixel tile from L2).
+//
+// Reference semantics: nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU and the torch.cat of the inputs
+// (depthnet/depthNet_model.py:19-112, 235-261, 335-365).
+//
+// Output tile     16 x 16 pixels = two M=128 UMMA tiles (rows 0-7 and 8-15), N = BN output channels.
+// A slab          for a (source, channel chunk, dx): ONE TMA box {chunk, 16, 16+2p, 1} at (c0, x0+dx, y0-p): the k
+//                   vertical taps of both pixel tiles are row windows of this slab, i.e. plain K-major 128B-swizzled
+//                   operands starting at slab + (dy + 8*tile)*2048 B (1024-aligned, SBO = 1024: no descriptor tricks).
+//                   L2->SM bytes per tap drop from 2 x 16 KB to (16+2p)/k x 2 KB  (3x3: 12 KB, 7x7: 6.3 KB).
+// B tile          per tap {chunk, BN} of the packed weights, shared by the two pixel tiles (halves weight traffic).
+// Pipelines       A ring (2-4 slabs) and B ring (3-6 tiles), both TMA -> mbarrier -> tcgen05.mma -> tcgen05.commit.
+// Accumulators    2 x BN TMEM columns per tile pair; double-buffered when 4*BN <= 512.
+// Warp roles      as conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace cnm {
+
+constexpr int HL_MAX_SRCS = 3;
+constexpr int HL_TILE_BYTES = 128 * 128;
+constexpr int HL_MAX_A = 4, HL_MAX_B = 8;
+
+struct alignas(64) HaloParams {
+  CUtensorMap a_maps[HL_MAX_SRCS];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  const cnm_conv_group* groups;
+  const float* bias;
+  int num_groups;
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int a_stages, b_stages, slab_bytes;
+  int src_pad[HL_MAX_SRCS];
+  int relu;
+  int c_out_offset;
+};
+
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;
+  constexpr int CHUNK_CH = TF32 ? 32 : 64;
+  constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
+  constexpr int ACC_STAGES = (4 * BN <= 512) ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = (2 * BN * ACC_STAGES) < 32 ? 32 : 2 * BN * ACC_STAGES;
+  constexpr int B_BYTES = BN * 128;
+  constexpr uint32_t IDESC = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // carve-up: [A ring][B ring][staging 2 x 16 KB][bias][barriers][tmem slot]
+  const uint32_t off_b = (uint32_t)p.a_stages * p.slab_bytes;
+  const uint32_t off_out = off_b + (uint32_t)p.b_stages * B_BYTES;
+  const uint32_t off_bias = off_out + 2 * HL_TILE_BYTES;
+  const uint32_t off_bar = off_bias + BN * 4;
+  const uint32_t bar0 = base + off_bar;
+  auto fullA = [&](int s) { return bar0 + 8u * s; };
+  auto emptyA = [&](int s) { return bar0 + 8u * (HL_MAX_A + s); };
+  auto fullB = [&](int s) { return bar0 + 8u * (2 * HL_MAX_A + s); };
+  auto emptyB = [&](int s) { return bar0 + 8u * (2 * HL_MAX_A + HL_MAX_B + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + 2 + a); };
+  const uint32_t off_tmem = off_bar + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
+  float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.out_map);
+    tma_prefetch_desc(&p.a_maps[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + off_tmem), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int4 g_next = __ldg(reinterpret_cast<const int4*>(p.groups));
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int m = tile / p.tiles_n;
+        const int x0 = (m % p.tiles_x) * 16;
+        m /= p.tiles_x;
+        const int y0 = (m % p.tiles_y) * 16;
+        const int n0 = m / p.tiles_y;
+        int kstep = 0;
+        for (int g = 0; g < p.num_groups; ++g) {
+          const int4 gr = g_next;  // src, c0, dx, ntaps
+          g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == p.num_groups) ? 0 : g + 1)));
+          const int pad = p.src_pad[gr.x];
+          mbar_wait(emptyA(sa), pa ^ 1);
+          mbar_expect_tx(fullA(sa), (uint32_t)(16 + 2 * pad) * 2048u);
+          tma_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          for (int t = 0; t < gr.w; ++t, ++kstep) {
+            mbar_wait(emptyB(sb), pb ^ 1);
+            mbar_expect_tx(fullB(sb), B_BYTES);
+            tma_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN);
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
+        const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(tempty(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 2 * BN);
+        uint32_t first = 1;
+        for (int g = 0; g < p.num_groups; ++g) {
+          const int ntaps = __ldg(&p.groups[g].ntaps);
+          mbar_wait(fullA(sa), pa);
+          tc_fence_after();
+          const uint32_t slab = base + sa * p.slab_bytes;
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(fullB(sb), pb);
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
+            const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+              tc_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+            }
+            first = 0;
+            tc_commit(emptyB(sb));
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+          tc_commit(emptyA(sa));
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        }
+        tc_commit(tfull(as));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const bool leader = (et == 0);
+    int it = 0;
+    uint32_t chunk_counter = 0;
+    int bias_tile = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % p.tiles_n;
+      int m = tile / p.tiles_n;
+      const int x0 = (m % p.tiles_x) * 16;
+      m /= p.tiles_x;
+      const int y0 = (m % p.tiles_y) * 16;
+      const int n0 = m / p.tiles_y;
+      const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
+      const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+      if (bias_tile != nt) {
+        epi_bar();
+        for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
+        bias_tile = nt;
+      }
+      mbar_wait(tfull(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + half * BN);
+#pragma unroll 1
+        for (int ch = 0; ch < NUM_CHUNKS; ++ch, ++chunk_counter) {
+          const uint32_t buf = chunk_counter & 1;
+          uint8_t* stg = base_ptr + off_out + buf * HL_TILE_BYTES;
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar();
+          uint32_t v[COLS_PER_CHUNK];
+          tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
+          if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
+          tmem_ld_wait();
+          const float* bs = bias_s + ch * COLS_PER_CHUNK;
+          uint8_t* rowp = stg + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 o;
+            if (TF32) {
+              float f[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
+                if (p.relu) t = fmaxf(t, 0.0f);
+                f[e] = round_tf32(t);
+              }
+              o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+            } else {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
+                float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
+                if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_bar();
+          if (leader) {
+            tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + nt * BN + ch * CHUNK_CH, x0, y0 + 8 * half, n0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty(as));
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN, bool TF32>
+static int launch_halo(const HaloParams& p, int grid, int smem, cudaStream_t s) {
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_halo: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  conv_halo_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
+  return after_launch("cnm_conv2d_halo");
+}
+
+}  // namespace cnm
+
+using namespace cnm;
+
+extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* src_pad,
+                               const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                               void* stream) {
+  int rc = check_conv_args("cnm_conv2d_halo", d, srcs, groups, wp, out);
+  if (rc) return rc;
+  CNM_REQUIRE(src_pad && num_groups > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo: bad group list");
+  CNM_REQUIRE(d->stride == 1, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: stride 1 only (use cnm_conv2d_tc)");
+  CNM_REQUIRE(d->Ho >= 16 && d->Wo >= 16, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_conv2d_halo: output %dx%d smaller than the 16x16 tile (use cnm_conv2d_tc)", d->Ho, d->Wo);
+  CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: Cout=%d must be a multiple of 64", d->Cout);
+  const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  int pmax = 0;
+  for (int i = 0; i < d->num_srcs; ++i) {
+    CNM_REQUIRE(src_pad[i] >= 0 && src_pad[i] <= 4, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: pad %d", src_pad[i]);
+    p.src_pad[i] = src_pad[i];
+    if (src_pad[i] > pmax) pmax = src_pad[i];
+  }
+  p.slab_bytes = (16 + 2 * pmax) * 2048;
+  p.tiles_x = (d->Wo + 15) / 16;
+  p.tiles_y = (d->Ho + 15) / 16;
+  p.tiles_b = d->N;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  // column tile: widest that keeps >= ~0.8 waves of work; BN=256 is single-buffered in TMEM (2 x 256 columns)
+  int BN = 64;
+  if (d->Cout % 256 == 0 && m_tiles * (d->Cout / 256) >= 120) BN = 256;
+  else if (d->Cout % 128 == 0) BN = 128;
+  p.tiles_n = d->Cout / BN;
+  p.groups = groups;
+  p.bias = bias;
+  p.num_groups = num_groups;
+  p.relu = d->relu;
+  p.c_out_offset = d->c_out_offset;
+  // smem budget: 227 KB - alignment slack - staging - bias - barriers
+  const int fixed = 1024 + 2 * HL_TILE_BYTES + BN * 4 + 8 * (2 * HL_MAX_A + 2 * HL_MAX_B + 4) + 16;
+  const int budget = 232448 - fixed;
+  p.b_stages = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
+  p.a_stages = (budget - p.b_stages * BN * 128) / p.slab_bytes;
+  if (p.a_stages > HL_MAX_A) p.a_stages = HL_MAX_A;
+  if (p.a_stages < 2) { p.b_stages -= 1; p.a_stages = (budget - p.b_stages * BN * 128) / p.slab_bytes; }
+  CNM_REQUIRE(p.a_stages >= 2, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: slab of %d B does not fit twice", p.slab_bytes);
+  const int smem = fixed + p.a_stages * p.slab_bytes + p.b_stages * BN * 128;
+
+  for (int i = 0; i < d->num_srcs; ++i) {
+    const cnm_conv_src& s = srcs[i];
+    const uint64_t pix = (uint64_t)s.C * eb;
+    const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)d->N};
+    const uint64_t str[3] = {pix, pix * s.W, pix * s.W * s.H};
+    const uint32_t box[4] = {(uint32_t)ch, 16u, (uint32_t)(16 + 2 * p.src_pad[i]), 1u};
+    rc = encode_map(&p.a_maps[i], d->dtype, 4, s.ptr, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t K = (uint64_t)d->num_steps * ch;
+    const uint64_t dims[2] = {K, (uint64_t)d->Cout};
+    const uint64_t str[1] = {K * eb};
+    const uint32_t bbox[2] = {(uint32_t)ch, (uint32_t)BN};
+    rc = encode_map(&p.b_map, d->dtype, 2, wp, dims, str, bbox);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t pix = (uint64_t)d->c_out_total * eb;
+    const uint64_t dims[4] = {(uint64_t)d->c_out_total, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    const uint64_t str[3] = {pix, pix * d->Wo, pix * d->Wo * d->Ho};
+    const uint32_t box[4] = {(uint32_t)ch, 16u, 8u, 1u};
+    rc = encode_map(&p.out_map, d->dtype, 4, out, dims, str, box);
+    if (rc) return rc;
+  }
+  const int total = m_tiles * p.tiles_n;
+  const int grid = total < 148 ? total : 148;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tf32 = d->dtype == CNM_TF32;
+  if (BN == 256) return tf32 ? launch_halo<256, true>(p, grid, smem, s) : launch_halo<256, false>(p, grid, smem, s);
+  if (BN == 128) return tf32 ? launch_halo<128, true>(p, grid, smem, s) : launch_halo<128, false>(p, grid, smem, s);
+  return tf32 ? launch_halo<64, true>(p, grid, smem, s) : launch_halo<64, false>(p, grid, smem, s);
+}

@@ -8,6 +8,7 @@ no allocation, no host sync, CUDA-graph capturable.  The wiring follows the refe
 inputs are extra operand sources of the implicit GEMM (see csrc/conv_tc.cu).
 """
 import ctypes as C
+import os
 from collections import namedtuple
 
 import torch
@@ -16,6 +17,9 @@ from . import _lib
 from ._lib import CNM_BF16, CNM_TF32
 
 BN_EPS = 1e-5
+# which stride-1 layers use the row-halo kernel: "auto" (enough tiles for a wave), "force" (every eligible layer,
+# used by tests), "off" (per-tap kernel everywhere)
+HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
 TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32}
 
 
@@ -91,6 +95,33 @@ def make_steps(srcs, k, stride, ch):
     return steps, cols
 
 
+def make_groups(srcs, k, ch):
+    """Row-halo K loop for stride-1 layers (csrc/conv_halo.cu): -> (groups [(src, c0, dx, ntaps)], cols, pads).
+    One group = one slab load serving `ntaps` vertical taps; the weight steps (cols) follow group order."""
+    pad = (k - 1) // 2
+    groups, cols, pads = [], [], []
+    for si, s in enumerate(srcs):
+        if s.kind == "act":
+            pads.append(pad)
+            for c0 in range(0, s.C, ch):
+                for t in range(k):
+                    groups.append((si, s.coff + c0, t - pad, k))
+                    cols += [("act", s.wch + c0, r, t) for r in range(k)]
+        elif s.kind == "rowtaps":
+            assert k * s.nreal <= ch
+            pads.append(pad)
+            groups.append((si, 0, 0, k))
+            cols += [("rowtaps", s.wch, s.nreal, r) for r in range(k)]
+        elif s.kind == "taps3x3":
+            assert k == 3 and 9 * s.nreal <= ch
+            pads.append(0)
+            groups.append((si, 0, 0, 1))
+            cols.append(("taps3x3", s.wch, s.nreal, 0))
+        else:
+            raise ValueError(s.kind)
+    return groups, cols, pads
+
+
 def pack_weights(wf, cols, ch, dtype):
     """Folded weights [Cout, Cin, k, k] -> K-major operand [Cout, len(cols)*ch] in the act dtype."""
     cout, _, k, _ = wf.shape
@@ -116,16 +147,29 @@ class ConvOp:
 
     def __init__(self, name, srcs, k, stride, cout, N, Ho, Wo, dtype, device, relu=True, out=None, c_out_offset=0,
                  backend="tc"):
-        self.name, self.k, self.stride, self.dtype, self.backend = name, k, stride, dtype, backend
+        self.name, self.k, self.stride, self.dtype = name, k, stride, dtype
         ch = chunk_channels(dtype)
-        self.steps, self.cols = make_steps(srcs, k, stride, ch)
+        # the row-halo kernel covers stride-1 layers with at least one 16x16 tile per image and ~a wave of tiles
+        halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
+        if backend == "tc" and stride == 1 and Ho >= 16 and Wo >= 16 and HALO_MODE != "off" and \
+                (halo_tiles >= 120 or HALO_MODE == "force"):
+            backend = "halo"
+        self.backend = backend
+        if backend == "halo":
+            self.groups, self.cols, pads = make_groups(srcs, k, ch)
+            self.steps = self.cols  # one weight step per col
+            self.groups_dev = torch.tensor(self.groups, dtype=torch.int32).to(device)
+            self.pads = (C.c_int32 * len(pads))(*pads)
+        else:
+            self.steps, self.cols = make_steps(srcs, k, stride, ch)
         self.srcs = srcs
         self.out = out if out is not None else torch.empty((N, Ho, Wo, cout), dtype=TORCH_DTYPE[dtype], device=device)
         self.wp = torch.zeros((cout, len(self.steps) * ch), dtype=TORCH_DTYPE[dtype], device=device)
         self.bias = torch.zeros((cout,), dtype=torch.float32, device=device)
-        st = torch.zeros((len(self.steps), 8), dtype=torch.int32)
-        st[:, :5] = torch.tensor(self.steps, dtype=torch.int32)
-        self.steps_dev = st.to(device)
+        if backend != "halo":
+            st = torch.zeros((len(self.steps), 8), dtype=torch.int32)
+            st[:, :5] = torch.tensor(self.steps, dtype=torch.int32)
+            self.steps_dev = st.to(device)
         self.desc = _lib.ConvDesc(N, Ho, Wo, cout, self.out.shape[3], c_out_offset, stride, 1 if relu else 0,
                                   len(srcs), len(self.steps), dtype, 0)
         arr = (_lib.ConvSrc * len(srcs))()
@@ -140,6 +184,11 @@ class ConvOp:
 
     def __call__(self, stream):
         lib = _lib.load()
+        if self.backend == "halo":
+            _lib.check(lib.cnm_conv2d_halo(C.byref(self.desc), self.srcs_arr, self.pads, self.groups_dev.data_ptr(),
+                                           len(self.groups), self.wp.data_ptr(), self.bias.data_ptr(),
+                                           self.out.data_ptr(), stream), self.name)
+            return
         fn = lib.cnm_conv2d_tc if self.backend == "tc" else lib.cnm_conv2d_simt
         _lib.check(fn(C.byref(self.desc), self.srcs_arr, self.steps_dev.data_ptr(), self.wp.data_ptr(),
                       self.bias.data_ptr(), self.out.data_ptr(), stream), self.name)

@@ -178,6 +178,18 @@ int cnm_conv2d_tc(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const cnm
 int cnm_conv2d_simt(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const cnm_conv_step* steps, const void* wp,
                     const float* bias, void* out, void* stream);
 
+/* Row-halo variant for stride-1 layers with Ho, Wo >= 16 (csrc/conv_halo.cu): same act / weight layouts and
+ * descriptor; the K loop is given as GROUPS.  A group loads one slab {chunk, 16, 16+2*pad} of source `src`
+ * (channels [c0, c0+chunk), columns shifted by dx, rows starting pad above the tile) and consumes `ntaps`
+ * consecutive weight steps, tap t reading the slab rows shifted by t (dy = t - pad).  desc->num_steps is the total
+ * number of weight steps (sum of ntaps); src_pad[i] is the vertical halo of source i (host array).             */
+typedef struct cnm_conv_group {
+  int32_t src, c0, dx, ntaps;
+} cnm_conv_group;
+int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* src_pad,
+                    const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                    void* stream);
+
 /* ---- depth-driven inverse warp ("next") ----------------------------
  * replaces inverse_warp + cam2pixel  (depthnet/inverse_warp.py:46-118).
  * feat [B,C,H,W], depth [B,H,W], pose [B,3,4], K [B,3,3], Kinv [B,3,3] -> out [B,C,H,W];

@@ -70,6 +70,35 @@ def test_conv_matches_oracle(backend, dtype, case):
     assert rel_l2(got, want) < (3e-3 if dtype == _lib.CNM_BF16 else 3e-4)
 
 
+HALO_CASES = [
+    (1, 16, 16, [64], 64, 3, 1),
+    (2, 32, 48, [128], 128, 3, 1),
+    (1, 24, 40, [64], 128, 7, 1),      # partial tiles in both directions, deepest halo
+    (1, 32, 32, [64], 256, 5, 1),      # BN = 128 (too few tiles for 256)
+    (2, 16, 32, [64, 64], 256, 3, 1),  # concatenated sources
+    (3, 48, 64, [64], 512, 3, 1),
+    (16, 48, 64, [64], 256, 3, 1),     # >= 120 tiles of BN = 256: single-buffered accumulators, several tiles per CTA
+    (10, 192, 256, [64], 64, 3, 1),    # C4-sized Cout = 64 layer: many tiles per CTA
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_halo_conv_matches_oracle(dtype, case):
+    N, H, W, cins, cout, k, stride = case
+    g = torch.Generator().manual_seed(N * 1000 + H * 7 + W + cout + k * 13)
+    xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, generator=g) / np.sqrt(sum(cins) * k * k)
+    b = torch.randn(cout, generator=g)
+    wchs = [sum(cins[:i]) for i in range(len(cins))]
+    got = run_conv("halo", dtype, xs, wchs, w, b, k, stride)
+    want = oracle_conv(dtype, xs, w, b, k, stride)
+    tol = 6e-3 if dtype == _lib.CNM_BF16 else 1e-3
+    err = (got - quantize(want, dtype)).abs().max().item()
+    assert err < tol * max(1.0, want.abs().max().item()), (err, rel_l2(got, want))
+    assert rel_l2(got, want) < (3e-3 if dtype == _lib.CNM_BF16 else 3e-4)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_conv_no_relu_negative_outputs(dtype):
     g = torch.Generator().manual_seed(7)

@@ -124,6 +124,31 @@ def test_pipeline_matches_oracle(precision, V):
     assert np.median(ang) < (1.0 if precision == "tf32" else 8.0), np.median(ang)
 
 
+def test_pipeline_with_halo_kernel_forced(monkeypatch):
+    """Every eligible stride-1 layer through csrc/conv_halo.cu (incl. the side-tensor sources) vs the per-tap kernel."""
+    from cnmnet_b200 import engine
+    B, H, W, V = 1, 64, 64, 2
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(99, B, H, W, V)
+    dsd = synth.kaiming_state(onets.state_shapes(onets.DEPTHNET_LAYERS), 41, 0.02)
+    rsd = synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), 42, 0.02)
+    outs = {}
+    for mode in ("off", "force"):
+        monkeypatch.setattr(engine, "HALO_MODE", mode)
+        dnet = cnmnet_b200.depthNet(idepth_scale=3.0, precision="tf32")
+        rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0, precision="tf32")
+        dnet.load_state_dict(dsd)
+        rnet.load_state_dict(rsd)
+        pipe = cnmnet_b200.CNMPipeline(dnet.to(dev()), rnet.to(dev()), use_graph=False)
+        st = pipe.static_state(B, V, H, W, dev())
+        kinds = {op.backend for op in list(st["dplan"].convs.values()) + list(st["rplan"].convs.values())}
+        assert ("halo" in kinds) == (mode == "force")
+        d, n, p = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))
+        outs[mode] = (d.cpu().numpy(), p.cpu().numpy())
+    # same operands, same fp32 accumulation on the tensor core, different K order only
+    assert np.abs(outs["force"][0] - outs["off"][0]).max() / np.abs(outs["off"][0]).max() < 2e-4
+    assert np.abs(outs["force"][1] - outs["off"][1]).max() < 2e-4
+
+
 def test_weight_updates_are_picked_up():
     B, H, W = 1, 32, 32
     ref, srcs, ref_cam, src_cams = synth.frame_tuples(9, B, H, W, 2)

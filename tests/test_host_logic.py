@@ -97,6 +97,41 @@ def test_rowtaps_source_reproduces_conv1():
     assert torch.allclose(got, want, atol=1e-9)
 
 
+def test_halo_groups_reproduce_conv():
+    """Row-halo K loop (csrc/conv_halo.cu): groups + group-ordered weights == conv2d, incl. side sources."""
+    torch.manual_seed(8)
+    ch, N, H, W = 32, 1, 9, 11
+    for k in (3, 5, 7):
+        x, extra = torch.randn(N, 64, H, W), torch.randn(N, 3, H, W)
+        wt, b = torch.randn(8, 67, k, k), torch.randn(8)
+        want = nhwc(F.conv2d(torch.cat((extra, x), 1).double(), engine.round_tf32(wt).double(), b.double(), padding=k // 2))
+        taps = torch.zeros(N, H, W, ch)
+        if k == 3:      # 3 extra channels as 27 packed 3x3 taps (refine conv1.0)
+            pe = F.pad(extra, (1, 1, 1, 1))
+            for c in range(3):
+                for r in range(3):
+                    for s_ in range(3):
+                        taps[..., 9 * c + 3 * r + s_] = pe[:, c, r:r + H, s_:s_ + W]
+            side = engine.Src(taps, "taps3x3", 0, ch, 0, 3)
+        elif k == 7:    # 3 extra channels as 7 row taps (DepthNet conv1.0)
+            pe = F.pad(extra, (3, 3, 0, 0))
+            for s_ in range(7):
+                for c in range(3):
+                    taps[..., s_ * 3 + c] = pe[:, c, :, s_:s_ + W]
+            side = engine.Src(taps, "rowtaps", 0, ch, 0, 3)
+        else:
+            side = None
+            wt[:, :3] = 0
+            want = nhwc(F.conv2d(torch.cat((extra, x), 1).double(), engine.round_tf32(wt).double(), b.double(), padding=2))
+        srcs = [engine.act_src(nhwc(x), 3)] + ([side] if side is not None else [])
+        groups, cols, pads = engine.make_groups(srcs, k, ch)
+        steps = [(si, 0, dx, t - pads[si], c0) for (si, c0, dx, nt) in groups for t in range(nt)]
+        assert len(steps) == len(cols)
+        wp = engine.pack_weights(wt, cols, ch, _lib.CNM_TF32)
+        got = emulate_steps([s_.buf for s_ in srcs], steps, wp, b, 1, ch, False)
+        assert torch.allclose(got, want, atol=1e-9), k
+
+
 def test_fold_bn_matches_batchnorm():
     sd = synth.kaiming_state(nets.state_shapes([("c", "conv", 8, 4, 3)]), seed=5)
     x = torch.randn(2, 8, 6, 6)
