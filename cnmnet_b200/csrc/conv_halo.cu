@@ -289,10 +289,16 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   p.tiles_y = (d->Ho + 15) / 16;
   p.tiles_b = d->N;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
-  // column tile: widest that keeps >= ~0.8 waves of work; BN=256 is single-buffered in TMEM (2 x 256 columns)
+  // column tile: minimise waves x relative tile time.  BN=256 holds 2 x 256 accumulator columns = all of TMEM, so its
+  // epilogue is not overlapped with the next tile's main loop (~10 % on top of twice the BN=128 tile time).
   int BN = 64;
-  if (d->Cout % 256 == 0 && m_tiles * (d->Cout / 256) >= 120) BN = 256;
-  else if (d->Cout % 128 == 0) BN = 128;
+  if (d->Cout % 128 == 0) {
+    BN = 128;
+    if (d->Cout % 256 == 0) {
+      const long w256 = ((long)m_tiles * (d->Cout / 256) + 147) / 148, w128 = ((long)m_tiles * (d->Cout / 128) + 147) / 148;
+      if (w256 * 22 < w128 * 10) BN = 256;
+    }
+  }
   p.tiles_n = d->Cout / BN;
   p.groups = groups;
   p.bias = bias;

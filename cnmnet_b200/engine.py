@@ -150,7 +150,7 @@ class ConvOp:
         self.name, self.k, self.stride, self.dtype = name, k, stride, dtype
         ch = chunk_channels(dtype)
         # the row-halo kernel covers stride-1 layers with at least one 16x16 tile per image and ~a wave of tiles
-        halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
+        halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 128)
         if backend == "tc" and stride == 1 and Ho >= 16 and Wo >= 16 and HALO_MODE != "off" and \
                 (halo_tiles >= 120 or HALO_MODE == "force"):
             backend = "halo"
