@@ -294,7 +294,7 @@ def main():
             for name, op in plan.convs.items():
                 ms, _ = time_events(lambda: op(s), 5, flush)
                 conv_ms += ms
-                conv_rows.append((tag + "." + name, ms, op.flops))
+                conv_rows.append(("%s.%s [%s/%d]" % (tag, name, op.backend, op.desc.reserved), ms, op.flops))
         alg_flop = B * (V * DEPTHNET_GFLOP + REFINE_GFLOP) * 1e9  # real channels only (no padding)
         issued_flop = sum(r[2] for r in conv_rows)
         tf = alg_flop / (conv_ms * 1e-3) / 1e12
@@ -354,7 +354,7 @@ def main():
                               "n_gpus": 1}
         if args.layers:
             for name, ms, fl in sorted(conv_rows, key=lambda r: -r[1]):
-                sys.stderr.write("%-28s %8.3f ms  %7.1f TFLOP/s issued\n" % (name, ms, fl / ms / 1e9))
+                sys.stderr.write("%-40s %8.3f ms  %7.1f TFLOP/s issued\n" % (name, ms, fl / ms / 1e9))
         if not args.no_cpu_baseline and world == 1:
             fps_cpu, ts = cpu_pipeline_fps(args.cpu_reps)
             line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",

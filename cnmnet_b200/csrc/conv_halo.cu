@@ -296,8 +296,13 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
     BN = 128;
     if (d->Cout % 256 == 0) {
       const long w256 = ((long)m_tiles * (d->Cout / 256) + 147) / 148, w128 = ((long)m_tiles * (d->Cout / 128) + 147) / 148;
-      if (w256 * 22 < w128 * 10) BN = 256;
+      if (w256 * 20 <= w128 * 10) BN = 256;
     }
+  }
+  if (d->reserved == 64 || d->reserved == 128 || d->reserved == 256) {  // caller-selected tile (host autotuner)
+    CNM_REQUIRE(d->Cout % d->reserved == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo: BN=%d does not divide Cout=%d",
+                d->reserved, d->Cout);
+    BN = d->reserved;
   }
   p.tiles_n = d->Cout / BN;
   p.groups = groups;

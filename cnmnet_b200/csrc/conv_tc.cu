@@ -334,6 +334,11 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
     const long cost = waves * cyc;
     if (best < 0 || cost < best) { best = cost; BN = cand; }
   }
+  if (d->reserved == 64 || d->reserved == 128 || d->reserved == 256) {  // caller-selected tile (host autotuner)
+    CNM_REQUIRE(d->Cout % d->reserved == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_tc: BN=%d does not divide Cout=%d",
+                d->reserved, d->Cout);
+    BN = d->reserved;
+  }
   p.tiles_n = d->Cout / BN;
   p.steps = steps;
   p.bias = bias;

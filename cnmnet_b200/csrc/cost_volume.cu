@@ -6,8 +6,8 @@
 //
 // Data layout in HBM
 //   ref      [B,3,H,W] fp32 (public NCHW), read once per (pair, plane group)
-//   texels   [P][H+4][W+4] float4 = (r,g,b,0): source views repacked pixel-interleaved with a
-//            zero border at row/col -1 and three/two trailing rows/cols, so that after clamping the
+//   texels   [P][H+6][W+4] float4 = (r,g,b,0): source views repacked pixel-interleaved with a
+//            zero border at row/col -1 and five/two trailing rows/cols, so that after clamping the
 //            sample position to [-1, W] x [-1, H] every bilinear tap is an unpredicated 16 B
 //            load and grid_sample's zeros padding falls out of the border texels.
 //   out      NCHW fp32 [P,D,H,W] (parity layout) or act [P,H,W,D] bf16/fp32 (conv1.0 operand)
@@ -90,7 +90,7 @@ __global__ void camera_setup_kernel(const float* __restrict__ ref_cam, const flo
 // source repack: NCHW planar -> zero-bordered pixel-interleaved float4
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_source_kernel(const float* __restrict__ src, float4* __restrict__ tex, int N, int H, int W) {
-  const int pitch = W + 4, rows = H + 4;
+  const int pitch = W + 4, rows = H + 6;
   size_t total = (size_t)N * rows * pitch;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int xx = (int)(i % pitch);
@@ -112,11 +112,12 @@ __global__ void pack_source_kernel(const float* __restrict__ src, float4* __rest
 // ---------------------------------------------------------------------------------------------
 // fused plane sweep
 // ---------------------------------------------------------------------------------------------
-// One thread owns a 2x2 pixel quad.  For a plane the four sample positions are ~1 texel apart, so their 16
-// bilinear taps normally fall inside the 3x3 texel block anchored at the first pixel's (x0, y0): 9 loads instead
-// of 16 (the kernel is bound by L1 data-pipe wavefronts, profiles/r01_cost_volume_ncu.md).  A pixel whose own
-// anchor is not at the expected +1 offset re-loads its 4 taps (rare: it happens once per 1/|scale-1| pixels).
-constexpr int CV_TX = 32, CV_TY = 4;  // threads per CTA: a CTA covers 64 x 8 pixels
+// One thread owns a column of CV_Q = 4 vertically adjacent pixels (lanes = consecutive x, so every load is
+// unit-stride across the warp).  For a plane the four sample positions are ~1 texel apart vertically, so their 16
+// bilinear taps normally fall inside the 5 x 2 texel block anchored at the first pixel's (x0, y0): 10 loads instead
+// of 16 (the kernel is bound by L1 data-pipe wavefronts, profiles/r01_cost_volume_ncu.md).  A pixel whose own anchor
+// is not at the expected (x0, y0+q) re-loads its 4 taps (happens once per ~1/|scale-1| pixels).
+constexpr int CV_TX = 32, CV_TY = 4, CV_Q = 4;  // a CTA covers 32 x 16 pixels
 
 struct Tap4 {
   float4 t00, t10, t01, t11;
@@ -131,7 +132,7 @@ __device__ __forceinline__ float cv_cost(const Tap4& t, float wx1, float wy1, fl
   return fabsf(c0) + fabsf(c1) + fabsf(c2);
 }
 
-// sample position of pixel with homography row products (a0,a1,a2) at plane depth z: returns clamped (ix, iy)
+// sample position of a pixel with homography row products (a0,a1,a2) at plane depth z: clamped (ix, iy)
 __device__ __forceinline__ void cv_project(float a0, float a1, float a2, float z, float k0, float k1, float k2e,
                                            float xmax, float ymax, float& ix, float& iy) {
   const float px = fmaf(a0, z, k0), py = fmaf(a1, z, k1);
@@ -156,111 +157,82 @@ __global__ void __launch_bounds__(CV_TX* CV_TY)
   if (tid < DPB) zs[tid] = (float)(1.0 / (idmin + (double)(d0 + tid) * idstep));  // fp64 like the Python double
   __syncthreads();
 
-  const int x = 2 * (blockIdx.x * CV_TX + threadIdx.x);
-  const int y = 2 * (blockIdx.y * CV_TY + threadIdx.y);
+  const int x = blockIdx.x * CV_TX + threadIdx.x;
+  const int y = CV_Q * (blockIdx.y * CV_TY + threadIdx.y);
   if (x >= W || y >= H) return;
-  const bool hasx = x + 1 < W, hasy = y + 1 < H;
   const int b = p % B;
   const size_t HW = (size_t)H * W;
 
   const float* h = hk + (size_t)p * 12;
-  const float h0 = __ldg(h + 0), h1 = __ldg(h + 1), h3 = __ldg(h + 3), h4 = __ldg(h + 4), h6 = __ldg(h + 6), h7 = __ldg(h + 7);
-  const float fx = (float)x, fy = (float)y;
-  // a = Hm . [x, y, 1]^T for the quad (KRKiUV): pixel order A(x,y) B(x+1,y) C(x,y+1) D(x+1,y+1)
-  float a0[4], a1[4], a2[4];
-  a0[0] = fmaf(h0, fx, fmaf(h1, fy, __ldg(h + 2)));
-  a1[0] = fmaf(h3, fx, fmaf(h4, fy, __ldg(h + 5)));
-  a2[0] = fmaf(h6, fx, fmaf(h7, fy, __ldg(h + 8)));
-  a0[1] = fmaf(h0, fx + 1.0f, fmaf(h1, fy, __ldg(h + 2)));
-  a1[1] = fmaf(h3, fx + 1.0f, fmaf(h4, fy, __ldg(h + 5)));
-  a2[1] = fmaf(h6, fx + 1.0f, fmaf(h7, fy, __ldg(h + 8)));
-  a0[2] = fmaf(h0, fx, fmaf(h1, fy + 1.0f, __ldg(h + 2)));
-  a1[2] = fmaf(h3, fx, fmaf(h4, fy + 1.0f, __ldg(h + 5)));
-  a2[2] = fmaf(h6, fx, fmaf(h7, fy + 1.0f, __ldg(h + 8)));
-  a0[3] = fmaf(h0, fx + 1.0f, fmaf(h1, fy + 1.0f, __ldg(h + 2)));
-  a1[3] = fmaf(h3, fx + 1.0f, fmaf(h4, fy + 1.0f, __ldg(h + 5)));
-  a2[3] = fmaf(h6, fx + 1.0f, fmaf(h7, fy + 1.0f, __ldg(h + 8)));
+  const float h1 = __ldg(h + 1), h4 = __ldg(h + 4), h7 = __ldg(h + 7);
+  const float fx = (float)x;
+  const float b0 = fmaf(__ldg(h + 0), fx, __ldg(h + 2)), b1 = fmaf(__ldg(h + 3), fx, __ldg(h + 5)),
+              b2 = fmaf(__ldg(h + 6), fx, __ldg(h + 8));
+  // a = Hm . [x, y+q, 1]^T (KRKiUV) and the reference pixels of the column (rows past H are computed on a clamped
+  // address and never stored)
+  float a0[CV_Q], a1[CV_Q], a2[CV_Q], r[CV_Q][3];
+  const float* rp = ref + (size_t)b * 3 * HW + x;
+#pragma unroll
+  for (int q = 0; q < CV_Q; ++q) {
+    const float fy = (float)(y + q);
+    a0[q] = fmaf(h1, fy, b0); a1[q] = fmaf(h4, fy, b1); a2[q] = fmaf(h7, fy, b2);
+    const int yr = min(y + q, H - 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[q][c] = __ldg(rp + c * HW + (size_t)yr * W);
+  }
   const float k0 = __ldg(h + 9), k1 = __ldg(h + 10), k2 = __ldg(h + 11) + 1e-6f;
 
-  // reference pixels of the quad (clamped addresses for quads hanging over an odd edge; never stored)
-  float r[4][3];
-  {
-    const float* rp = ref + (size_t)b * 3 * HW;
-    const int xb = hasx ? x + 1 : x, yc = hasy ? y + 1 : y;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      r[0][c] = __ldg(rp + c * HW + (size_t)y * W + x);
-      r[1][c] = __ldg(rp + c * HW + (size_t)y * W + xb);
-      r[2][c] = __ldg(rp + c * HW + (size_t)yc * W + x);
-      r[3][c] = __ldg(rp + c * HW + (size_t)yc * W + xb);
-    }
-  }
-
   const int pitch = W + 4;
-  const float4* tp = tex + (size_t)p * (H + 4) * pitch + pitch + 1;  // texel (0,0)
+  const float4* tp = tex + (size_t)p * (H + 6) * pitch + pitch + 1;  // texel (0,0)
   const float xmax = (float)W, ymax = (float)H;
   constexpr int NBUF = (LAYOUT == 0) ? 1 : DPB;
-  float res[4][NBUF];
+  float res[CV_Q][NBUF];
 
 #pragma unroll
   for (int i = 0; i < DPB; ++i) {
     const float z = zs[i];
-    float ix[4], iy[4];
+    int xi[CV_Q], yi[CV_Q];
+    float wx[CV_Q], wy[CV_Q];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cv_project(a0[q], a1[q], a2[q], z, k0, k1, k2, xmax, ymax, ix[q], iy[q]);
-    int xi[4], yi[4];
-    float wx[4], wy[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float xf = floorf(ix[q]), yf = floorf(iy[q]);
+    for (int q = 0; q < CV_Q; ++q) {
+      float ix, iy;
+      cv_project(a0[q], a1[q], a2[q], z, k0, k1, k2, xmax, ymax, ix, iy);
+      const float xf = floorf(ix), yf = floorf(iy);
       xi[q] = (int)xf; yi[q] = (int)yf;
-      wx[q] = ix[q] - xf; wy[q] = iy[q] - yf;
+      wx[q] = ix - xf; wy[q] = iy - yf;
     }
-    // 3x3 texel block anchored at pixel A
+    // (CV_Q+1) x 2 texel block anchored at the first pixel
     const float4* t0 = tp + yi[0] * pitch + xi[0];
-    const float4* t1 = t0 + pitch;
-    const float4* t2 = t1 + pitch;
-    const float4 T00 = __ldg(t0), T01 = __ldg(t0 + 1), T02 = __ldg(t0 + 2);
-    const float4 T10 = __ldg(t1), T11 = __ldg(t1 + 1), T12 = __ldg(t1 + 2);
-    const float4 T20 = __ldg(t2), T21 = __ldg(t2 + 1), T22 = __ldg(t2 + 2);
-    Tap4 tq[4];
-    tq[0].t00 = T00; tq[0].t10 = T01; tq[0].t01 = T10; tq[0].t11 = T11;
-    tq[1].t00 = T01; tq[1].t10 = T02; tq[1].t01 = T11; tq[1].t11 = T12;
-    tq[2].t00 = T10; tq[2].t10 = T11; tq[2].t01 = T20; tq[2].t11 = T21;
-    tq[3].t00 = T11; tq[3].t10 = T12; tq[3].t01 = T21; tq[3].t11 = T22;
+    float4 T[CV_Q + 1][2];
 #pragma unroll
-    for (int q = 1; q < 4; ++q) {
-      const int ex = xi[0] + (q & 1), ey = yi[0] + (q >> 1);
-      if (xi[q] != ex || yi[q] != ey) {  // irregular neighbour: its own four taps
-        const float4* t = tp + yi[q] * pitch + xi[q];
-        tq[q].t00 = __ldg(t); tq[q].t10 = __ldg(t + 1); tq[q].t01 = __ldg(t + pitch); tq[q].t11 = __ldg(t + pitch + 1);
+    for (int j = 0; j <= CV_Q; ++j) { T[j][0] = __ldg(t0 + j * pitch); T[j][1] = __ldg(t0 + j * pitch + 1); }
+    float c[CV_Q];
+#pragma unroll
+    for (int q = 0; q < CV_Q; ++q) {
+      Tap4 t;
+      t.t00 = T[q][0]; t.t10 = T[q][1]; t.t01 = T[q + 1][0]; t.t11 = T[q + 1][1];
+      if (q > 0 && (xi[q] != xi[0] || yi[q] != yi[0] + q)) {  // irregular neighbour: its own four taps
+        const float4* tt = tp + yi[q] * pitch + xi[q];
+        t.t00 = __ldg(tt); t.t10 = __ldg(tt + 1); t.t01 = __ldg(tt + pitch); t.t11 = __ldg(tt + pitch + 1);
       }
+      c[q] = cv_cost(t, wx[q], wy[q], r[q][0], r[q][1], r[q][2]);
     }
-    float c[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) c[q] = cv_cost(tq[q], wx[q], wy[q], r[q][0], r[q][1], r[q][2]);
-
     if (LAYOUT == 0) {
       float* o = reinterpret_cast<float*>(out) + ((size_t)p * D + d0 + i) * HW + (size_t)y * W + x;
-      if (hasx && (W & 1) == 0) {
-        __stcs(reinterpret_cast<float2*>(o), make_float2(c[0], c[1]));
-        if (hasy) __stcs(reinterpret_cast<float2*>(o + W), make_float2(c[2], c[3]));
-      } else {
-        __stcs(o, c[0]);
-        if (hasx) __stcs(o + 1, c[1]);
-        if (hasy) { __stcs(o + W, c[2]); if (hasx) __stcs(o + W + 1, c[3]); }
-      }
+#pragma unroll
+      for (int q = 0; q < CV_Q; ++q)
+        if (y + q < H) __stcs(o + (size_t)q * W, c[q]);
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) res[q][i % NBUF] = c[q];
+      for (int q = 0; q < CV_Q; ++q) res[q][i % NBUF] = c[q];
     }
   }
 
   if (LAYOUT != 0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (((q & 1) && !hasx) || ((q >> 1) && !hasy)) continue;
-      const size_t pix = (size_t)p * HW + (size_t)(y + (q >> 1)) * W + x + (q & 1);
+    for (int q = 0; q < CV_Q; ++q) {
+      if (y + q >= H) continue;
+      const size_t pix = (size_t)p * HW + (size_t)(y + q) * W + x;
       if (LAYOUT == 1) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + pix * D + d0;
 #pragma unroll
@@ -288,14 +260,14 @@ extern "C" int cnm_camera_setup(const float* ref_cam, const float* src_cam, floa
 
 extern "C" int64_t cnm_packed_source_bytes(int N, int H, int W) {
   if (N <= 0 || H <= 0 || W <= 0) return 0;
-  return (int64_t)N * (H + 4) * (W + 4) * 16;
+  return (int64_t)N * (H + 6) * (W + 4) * 16;
 }
 
 extern "C" int cnm_pack_source(const float* src, void* packed, int N, int H, int W, void* stream) {
   CNM_REQUIRE(src && packed, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: null pointer");
   CNM_REQUIRE(N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: bad shape");
   CNM_REQUIRE(((uintptr_t)packed & 15) == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: packed must be 16B aligned");
-  size_t total = (size_t)N * (H + 4) * (W + 4);
+  size_t total = (size_t)N * (H + 6) * (W + 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_source_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (float4*)packed, N, H, W);
@@ -316,7 +288,7 @@ extern "C" int cnm_cost_volume(const float* ref, const void* packed_src, const f
   CNM_REQUIRE((long long)P * (D / 8) <= 65535, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_cost_volume: too many pairs x planes");
   const double step = (idepth_max - idepth_min) / (double)(D - 1);
   dim3 block(CV_TX, CV_TY);
-  const unsigned gx = (unsigned)((W + 2 * CV_TX - 1) / (2 * CV_TX)), gy = (unsigned)((H + 2 * CV_TY - 1) / (2 * CV_TY));
+  const unsigned gx = (unsigned)((W + CV_TX - 1) / CV_TX), gy = (unsigned)((H + CV_Q * CV_TY - 1) / (CV_Q * CV_TY));
   cudaStream_t s = (cudaStream_t)stream;
   const float4* tex = (const float4*)packed_src;
   if (layout == CNM_VOLUME_NCHW_F32)

@@ -142,55 +142,114 @@ def pack_weights(wf, cols, ch, dtype):
     return round_tf32(wp)
 
 
+_TUNE_CACHE = {}
+AUTOTUNE = os.environ.get("CNM_AUTOTUNE", "1") != "0"
+
+
 class ConvOp:
-    """One pre-bound cnm_conv2d_* call."""
+    """One pre-bound convolution call.  Holds the per-tap program (cnm_conv2d_tc / _simt) and, for stride-1 layers
+    with at least one 16x16 tile, the row-halo program (cnm_conv2d_halo); `tune()` times the candidates
+    (kernel x output-channel tile) on the device once per layer shape and keeps the fastest."""
 
     def __init__(self, name, srcs, k, stride, cout, N, Ho, Wo, dtype, device, relu=True, out=None, c_out_offset=0,
                  backend="tc"):
         self.name, self.k, self.stride, self.dtype = name, k, stride, dtype
         ch = chunk_channels(dtype)
-        # the row-halo kernel covers stride-1 layers with at least one 16x16 tile per image and ~a wave of tiles
-        halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 128)
-        if backend == "tc" and stride == 1 and Ho >= 16 and Wo >= 16 and HALO_MODE != "off" and \
-                (halo_tiles >= 120 or HALO_MODE == "force"):
-            backend = "halo"
-        self.backend = backend
-        if backend == "halo":
-            self.groups, self.cols, pads = make_groups(srcs, k, ch)
-            self.steps = self.cols  # one weight step per col
-            self.groups_dev = torch.tensor(self.groups, dtype=torch.int32).to(device)
-            self.pads = (C.c_int32 * len(pads))(*pads)
-        else:
-            self.steps, self.cols = make_steps(srcs, k, stride, ch)
         self.srcs = srcs
+        self.variants = {}
+        steps, cols = make_steps(srcs, k, stride, ch)
+        st = torch.zeros((len(steps), 8), dtype=torch.int32)
+        st[:, :5] = torch.tensor(steps, dtype=torch.int32)
+        self.variants["tc"] = {"cols": cols, "steps_dev": st.to(device)}
+        self.variants["simt"] = self.variants["tc"]
+        halo_ok = stride == 1 and Ho >= 16 and Wo >= 16 and backend in ("tc", "halo")
+        if halo_ok:
+            groups, gcols, pads = make_groups(srcs, k, ch)
+            assert len(gcols) == len(cols)
+            self.variants["halo"] = {"cols": gcols, "groups_dev": torch.tensor(groups, dtype=torch.int32).to(device),
+                                     "ngroups": len(groups), "pads": (C.c_int32 * len(pads))(*pads)}
+        elif backend == "halo":
+            raise ValueError("%s: the row-halo kernel needs stride 1 and an output of at least 16x16" % name)
+        self.num_steps = len(cols)
         self.out = out if out is not None else torch.empty((N, Ho, Wo, cout), dtype=TORCH_DTYPE[dtype], device=device)
-        self.wp = torch.zeros((cout, len(self.steps) * ch), dtype=TORCH_DTYPE[dtype], device=device)
+        self.wp = torch.zeros((cout, self.num_steps * ch), dtype=TORCH_DTYPE[dtype], device=device)
         self.bias = torch.zeros((cout,), dtype=torch.float32, device=device)
-        if backend != "halo":
-            st = torch.zeros((len(self.steps), 8), dtype=torch.int32)
-            st[:, :5] = torch.tensor(self.steps, dtype=torch.int32)
-            self.steps_dev = st.to(device)
         self.desc = _lib.ConvDesc(N, Ho, Wo, cout, self.out.shape[3], c_out_offset, stride, 1 if relu else 0,
-                                  len(srcs), len(self.steps), dtype, 0)
+                                  len(srcs), self.num_steps, dtype, 0)
         arr = (_lib.ConvSrc * len(srcs))()
         for i, s in enumerate(srcs):
             arr[i] = _lib.ConvSrc(_lib.ptr(s.buf), s.buf.shape[1], s.buf.shape[2], s.buf.shape[3], 0)
         self.srcs_arr = arr
-        self.flops = 2.0 * N * Ho * Wo * cout * len(self.steps) * ch
+        self.flops = 2.0 * N * Ho * Wo * cout * self.num_steps * ch
+        self._weights = None
+        self.tuned = None
+        self.key = (dtype, N, Ho, Wo, cout, k, stride, tuple((s.kind, s.C, s.buf.shape[3]) for s in srcs))
+        # default choice without tuning
+        halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
+        if backend == "tc" and halo_ok and HALO_MODE != "off" and (halo_tiles >= 120 or HALO_MODE == "force"):
+            backend = "halo"
+        self.tunable = backend in ("tc", "halo") and HALO_MODE == "auto" and AUTOTUNE
+        self.select(backend, 0)
+
+    @property
+    def cols(self):
+        return self.variants[self.backend]["cols"]
+
+    def select(self, backend, bn):
+        repack = getattr(self, "backend", backend) != backend and self._weights is not None
+        self.backend = backend
+        self.desc.reserved = int(bn)
+        if repack:
+            self.load(*self._weights)
+
+    def candidates(self):
+        cout = self.desc.Cout
+        out = []
+        for be in ("tc", "halo"):
+            if be in self.variants:
+                out += [(be, bn) for bn in (256, 128, 64) if cout % bn == 0]
+        return out
+
+    def tune(self, stream, reps=3):
+        """Times every (kernel, tile) candidate with CUDA events and keeps the fastest (cached per layer shape)."""
+        if not self.tunable:
+            return
+        best = _TUNE_CACHE.get(self.key)
+        if best is None:
+            results = []
+            for be, bn in self.candidates():
+                self.select(be, bn)
+                for _ in range(2):
+                    self(stream)
+                ts = []
+                for _ in range(reps):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    self(stream)
+                    b.record()
+                    b.synchronize()
+                    ts.append(a.elapsed_time(b))
+                results.append((min(ts), be, bn))
+            results.sort()
+            best = _TUNE_CACHE[self.key] = (results[0][1], results[0][2], results)
+        self.tuned = best
+        self.select(best[0], best[1])
 
     def load(self, wf, bf):
+        self._weights = (wf, bf)
         self.wp.copy_(pack_weights(wf.to(self.wp.device), self.cols, chunk_channels(self.dtype), self.dtype))
         self.bias.copy_(bf.to(self.bias.device))
 
     def __call__(self, stream):
         lib = _lib.load()
+        v = self.variants[self.backend]
         if self.backend == "halo":
-            _lib.check(lib.cnm_conv2d_halo(C.byref(self.desc), self.srcs_arr, self.pads, self.groups_dev.data_ptr(),
-                                           len(self.groups), self.wp.data_ptr(), self.bias.data_ptr(),
+            _lib.check(lib.cnm_conv2d_halo(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(),
+                                           v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),
                                            self.out.data_ptr(), stream), self.name)
             return
         fn = lib.cnm_conv2d_tc if self.backend == "tc" else lib.cnm_conv2d_simt
-        _lib.check(fn(C.byref(self.desc), self.srcs_arr, self.steps_dev.data_ptr(), self.wp.data_ptr(),
+        _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["steps_dev"].data_ptr(), self.wp.data_ptr(),
                       self.bias.data_ptr(), self.out.data_ptr(), stream), self.name)
 
 
@@ -248,6 +307,13 @@ class _Plan:
         w = sd[name + ".0.weight"].to(self.device, torch.float32)  # [1, C, 3, 3] -> (r, s, c)
         hw["w"].copy_(w[0].permute(1, 2, 0).reshape(-1))
         hw["bias"] = float(sd[name + ".0.bias"].reshape(-1)[0])
+
+    def tune(self):
+        """Autotune every convolution of the plan (kernel x tile) on its real buffers; weights are still zero."""
+        s = _lib.stream_ptr()
+        for op in self.convs.values():
+            op.tune(s)
+        torch.cuda.synchronize(self.device)
 
     def run(self, stream=None):
         s = _lib.stream_ptr() if stream is None else stream
@@ -336,6 +402,7 @@ class DepthNetPlan(_Plan):
         self.iconv1 = cv("iconv1.0", [act_src(up1, 0), Src(t2, "taps3x3", 64, self.ch, 0, 1)], 3, 1, 64, N, H, W)
         self.disp1, l1 = self.head("disp1", self.iconv1, self.scale, want_logits)
         self.logits = [l1, l2, l3, l4]
+        self.tune()
 
     def load_state(self, sd):
         for name, op in self.convs.items():
@@ -409,6 +476,7 @@ class RefinePlan(_Plan):
             i1 = cv("iconv1_%s.0" % br, [act_src(u1, 0)], 3, 1, 64, B, H, W)
             self.iconv1[br] = i1
             self.out[br], self.logits[br] = self.head(head, i1, sc, want_logits)
+        self.tune()
 
     load_state = DepthNetPlan.load_state
 
