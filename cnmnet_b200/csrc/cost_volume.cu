@@ -6,11 +6,19 @@
 //
 // Data layout in HBM
 //   ref      [B,3,H,W] fp32 (public NCHW), read once per (pair, plane group)
-//   texels   [P][H+6][W+4] float4 = (r,g,b,0): source views repacked pixel-interleaved with a
-//            zero border at row/col -1 and five/two trailing rows/cols, so that after clamping the
+//   texels   [P][H+3][W+4] float4 = (r,g,b,0): source views repacked pixel-interleaved with a
+//            zero border at row/col -1 and two trailing rows/cols, so that after clamping the
 //            sample position to [-1, W] x [-1, H] every bilinear tap is an unpredicated 16 B
 //            load and grid_sample's zeros padding falls out of the border texels.
 //   out      NCHW fp32 [P,D,H,W] (parity layout) or act [P,H,W,D] bf16/fp32 (conv1.0 operand)
+//
+// Tried and rejected in round 1 (B200 measurements, C2: 256x192x64, 2 views, batch 5, NCHW fp32):
+//   one pixel per thread, 4 x 16 B taps per plane (this file)            105 us   l1tex LSU wavefronts 89 % of peak
+//   2x2 pixel quad per thread sharing a 3x3 texel block (9 loads / 4 px)  141 us   lanes 2 px apart: every load
+//                                                                                  touches twice the 128 B lines
+//   4x1 pixel column per thread sharing a 5x2 block (10 loads / 4 px)     127 us   ~30 % of neighbours off the
+//                                                                                  expected anchor, 80 regs
+// The kernel is bound by L1 data-pipe wavefronts (a 32-lane x 16 B tap request spans 4-6 lines), not by HBM.
 #include "common.cuh"
 
 namespace cnm {
@@ -90,7 +98,7 @@ __global__ void camera_setup_kernel(const float* __restrict__ ref_cam, const flo
 // source repack: NCHW planar -> zero-bordered pixel-interleaved float4
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_source_kernel(const float* __restrict__ src, float4* __restrict__ tex, int N, int H, int W) {
-  const int pitch = W + 4, rows = H + 6;
+  const int pitch = W + 4, rows = H + 3;
   size_t total = (size_t)N * rows * pitch;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int xx = (int)(i % pitch);
@@ -112,38 +120,7 @@ __global__ void pack_source_kernel(const float* __restrict__ src, float4* __rest
 // ---------------------------------------------------------------------------------------------
 // fused plane sweep
 // ---------------------------------------------------------------------------------------------
-// One thread owns a column of CV_Q = 4 vertically adjacent pixels (lanes = consecutive x, so every load is
-// unit-stride across the warp).  For a plane the four sample positions are ~1 texel apart vertically, so their 16
-// bilinear taps normally fall inside the 5 x 2 texel block anchored at the first pixel's (x0, y0): 10 loads instead
-// of 16 (the kernel is bound by L1 data-pipe wavefronts, profiles/r01_cost_volume_ncu.md).  A pixel whose own anchor
-// is not at the expected (x0, y0+q) re-loads its 4 taps (happens once per ~1/|scale-1| pixels).
-constexpr int CV_TX = 32, CV_TY = 4, CV_Q = 4;  // a CTA covers 32 x 16 pixels
-
-struct Tap4 {
-  float4 t00, t10, t01, t11;
-};
-
-__device__ __forceinline__ float cv_cost(const Tap4& t, float wx1, float wy1, float r0, float r1, float r2) {
-  const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-  const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
-  const float c0 = fmaf(t.t11.x, w11, fmaf(t.t01.x, w01, fmaf(t.t10.x, w10, fmaf(t.t00.x, w00, -r0))));
-  const float c1 = fmaf(t.t11.y, w11, fmaf(t.t01.y, w01, fmaf(t.t10.y, w10, fmaf(t.t00.y, w00, -r1))));
-  const float c2 = fmaf(t.t11.z, w11, fmaf(t.t01.z, w01, fmaf(t.t10.z, w10, fmaf(t.t00.z, w00, -r2))));
-  return fabsf(c0) + fabsf(c1) + fabsf(c2);
-}
-
-// sample position of a pixel with homography row products (a0,a1,a2) at plane depth z: clamped (ix, iy)
-__device__ __forceinline__ void cv_project(float a0, float a1, float a2, float z, float k0, float k1, float k2e,
-                                           float xmax, float ymax, float& ix, float& iy) {
-  const float px = fmaf(a0, z, k0), py = fmaf(a1, z, k1);
-  const float den = fmaf(a2, z, k2e);  // p_z + 1e-6
-  float rcp;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(den));
-  rcp = fmaf(fmaf(-den, rcp, 1.0f), rcp, rcp);  // one Newton step: ~0.5 ulp
-  // grid_sample un-normalisation with align_corners=False: ix = u - 0.5; clamp into the zero border (NaN -> -1)
-  ix = fminf(fmaxf(fmaf(px, rcp, -0.5f), -1.0f), xmax);
-  iy = fminf(fmaxf(fmaf(py, rcp, -0.5f), -1.0f), ymax);
-}
+constexpr int CV_TX = 32, CV_TY = 8;
 
 template <int DPB, int LAYOUT>  // LAYOUT: 0 = NCHW fp32, 1 = act bf16, 2 = act fp32
 __global__ void __launch_bounds__(CV_TX* CV_TY)
@@ -158,91 +135,63 @@ __global__ void __launch_bounds__(CV_TX* CV_TY)
   __syncthreads();
 
   const int x = blockIdx.x * CV_TX + threadIdx.x;
-  const int y = CV_Q * (blockIdx.y * CV_TY + threadIdx.y);
+  const int y = blockIdx.y * CV_TY + threadIdx.y;
   if (x >= W || y >= H) return;
   const int b = p % B;
   const size_t HW = (size_t)H * W;
 
   const float* h = hk + (size_t)p * 12;
-  const float h1 = __ldg(h + 1), h4 = __ldg(h + 4), h7 = __ldg(h + 7);
-  const float fx = (float)x;
-  const float b0 = fmaf(__ldg(h + 0), fx, __ldg(h + 2)), b1 = fmaf(__ldg(h + 3), fx, __ldg(h + 5)),
-              b2 = fmaf(__ldg(h + 6), fx, __ldg(h + 8));
-  // a = Hm . [x, y+q, 1]^T (KRKiUV) and the reference pixels of the column (rows past H are computed on a clamped
-  // address and never stored)
-  float a0[CV_Q], a1[CV_Q], a2[CV_Q], r[CV_Q][3];
-  const float* rp = ref + (size_t)b * 3 * HW + x;
-#pragma unroll
-  for (int q = 0; q < CV_Q; ++q) {
-    const float fy = (float)(y + q);
-    a0[q] = fmaf(h1, fy, b0); a1[q] = fmaf(h4, fy, b1); a2[q] = fmaf(h7, fy, b2);
-    const int yr = min(y + q, H - 1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) r[q][c] = __ldg(rp + c * HW + (size_t)yr * W);
-  }
+  const float fx = (float)x, fy = (float)y;
+  // a = Hm . [x, y, 1]^T   (KRKiUV)
+  const float a0 = fmaf(__ldg(h + 0), fx, fmaf(__ldg(h + 1), fy, __ldg(h + 2)));
+  const float a1 = fmaf(__ldg(h + 3), fx, fmaf(__ldg(h + 4), fy, __ldg(h + 5)));
+  const float a2 = fmaf(__ldg(h + 6), fx, fmaf(__ldg(h + 7), fy, __ldg(h + 8)));
   const float k0 = __ldg(h + 9), k1 = __ldg(h + 10), k2 = __ldg(h + 11) + 1e-6f;
 
-  const int pitch = W + 4;
-  const float4* tp = tex + (size_t)p * (H + 6) * pitch + pitch + 1;  // texel (0,0)
-  const float xmax = (float)W, ymax = (float)H;
-  constexpr int NBUF = (LAYOUT == 0) ? 1 : DPB;
-  float res[CV_Q][NBUF];
+  const float* rp = ref + (size_t)b * 3 * HW + (size_t)y * W + x;
+  const float r0 = __ldg(rp), r1 = __ldg(rp + HW), r2 = __ldg(rp + 2 * HW);
 
+  const int pitch = W + 4;
+  const float4* tp = tex + (size_t)p * (H + 3) * pitch + pitch + 1;  // texel (0,0)
+  const float xmax = (float)W, ymax = (float)H;
+
+  float res[DPB];
 #pragma unroll
   for (int i = 0; i < DPB; ++i) {
     const float z = zs[i];
-    int xi[CV_Q], yi[CV_Q];
-    float wx[CV_Q], wy[CV_Q];
-#pragma unroll
-    for (int q = 0; q < CV_Q; ++q) {
-      float ix, iy;
-      cv_project(a0[q], a1[q], a2[q], z, k0, k1, k2, xmax, ymax, ix, iy);
-      const float xf = floorf(ix), yf = floorf(iy);
-      xi[q] = (int)xf; yi[q] = (int)yf;
-      wx[q] = ix - xf; wy[q] = iy - yf;
-    }
-    // (CV_Q+1) x 2 texel block anchored at the first pixel
-    const float4* t0 = tp + yi[0] * pitch + xi[0];
-    float4 T[CV_Q + 1][2];
-#pragma unroll
-    for (int j = 0; j <= CV_Q; ++j) { T[j][0] = __ldg(t0 + j * pitch); T[j][1] = __ldg(t0 + j * pitch + 1); }
-    float c[CV_Q];
-#pragma unroll
-    for (int q = 0; q < CV_Q; ++q) {
-      Tap4 t;
-      t.t00 = T[q][0]; t.t10 = T[q][1]; t.t01 = T[q + 1][0]; t.t11 = T[q + 1][1];
-      if (q > 0 && (xi[q] != xi[0] || yi[q] != yi[0] + q)) {  // irregular neighbour: its own four taps
-        const float4* tt = tp + yi[q] * pitch + xi[q];
-        t.t00 = __ldg(tt); t.t10 = __ldg(tt + 1); t.t01 = __ldg(tt + pitch); t.t11 = __ldg(tt + pitch + 1);
-      }
-      c[q] = cv_cost(t, wx[q], wy[q], r[q][0], r[q][1], r[q][2]);
-    }
-    if (LAYOUT == 0) {
-      float* o = reinterpret_cast<float*>(out) + ((size_t)p * D + d0 + i) * HW + (size_t)y * W + x;
-#pragma unroll
-      for (int q = 0; q < CV_Q; ++q)
-        if (y + q < H) __stcs(o + (size_t)q * W, c[q]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < CV_Q; ++q) res[q][i % NBUF] = c[q];
-    }
+    const float px = fmaf(a0, z, k0), py = fmaf(a1, z, k1);
+    const float den = fmaf(a2, z, k2);  // p_z + 1e-6
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(den));
+    rcp = fmaf(fmaf(-den, rcp, 1.0f), rcp, rcp);  // one Newton step: ~0.5 ulp
+    // grid_sample un-normalisation with align_corners=False: ix = u - 0.5
+    float ix = fmaf(px, rcp, -0.5f), iy = fmaf(py, rcp, -0.5f);
+    ix = fminf(fmaxf(ix, -1.0f), xmax);  // NaN -> -1 (zero border)
+    iy = fminf(fmaxf(iy, -1.0f), ymax);
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float wx1 = ix - x0f, wy1 = iy - y0f;
+    const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    const float4* t = tp + (int)y0f * pitch + (int)x0f;
+    const float4 t00 = __ldg(t), t10 = __ldg(t + 1), t01 = __ldg(t + pitch), t11 = __ldg(t + pitch + 1);
+    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
+    const float c0 = fmaf(t11.x, w11, fmaf(t01.x, w01, fmaf(t10.x, w10, fmaf(t00.x, w00, -r0))));
+    const float c1 = fmaf(t11.y, w11, fmaf(t01.y, w01, fmaf(t10.y, w10, fmaf(t00.y, w00, -r1))));
+    const float c2 = fmaf(t11.z, w11, fmaf(t01.z, w01, fmaf(t10.z, w10, fmaf(t00.z, w00, -r2))));
+    res[i] = fabsf(c0) + fabsf(c1) + fabsf(c2);
   }
 
-  if (LAYOUT != 0) {
+  if (LAYOUT == 0) {
+    float* o = reinterpret_cast<float*>(out) + ((size_t)p * D + d0) * HW + (size_t)y * W + x;
 #pragma unroll
-    for (int q = 0; q < CV_Q; ++q) {
-      if (y + q >= H) continue;
-      const size_t pix = (size_t)p * HW + (size_t)(y + q) * W + x;
-      if (LAYOUT == 1) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + pix * D + d0;
+    for (int i = 0; i < DPB; ++i) __stcs(o + (size_t)i * HW, res[i]);
+  } else if (LAYOUT == 1) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + ((size_t)p * HW + (size_t)y * W + x) * D + d0;
 #pragma unroll
-        for (int i = 0; i < DPB; i += 8) Vec16<__nv_bfloat16>::store(o + i, res[q] + i);
-      } else {
-        float* o = reinterpret_cast<float*>(out) + pix * D + d0;
+    for (int i = 0; i < DPB; i += 8) Vec16<__nv_bfloat16>::store(o + i, res + i);
+  } else {
+    float* o = reinterpret_cast<float*>(out) + ((size_t)p * HW + (size_t)y * W + x) * D + d0;
 #pragma unroll
-        for (int i = 0; i < DPB; i += 4) Vec16<float>::store(o + i, res[q] + i);
-      }
-    }
+    for (int i = 0; i < DPB; i += 4) Vec16<float>::store(o + i, res + i);
   }
 }
 
@@ -260,14 +209,14 @@ extern "C" int cnm_camera_setup(const float* ref_cam, const float* src_cam, floa
 
 extern "C" int64_t cnm_packed_source_bytes(int N, int H, int W) {
   if (N <= 0 || H <= 0 || W <= 0) return 0;
-  return (int64_t)N * (H + 6) * (W + 4) * 16;
+  return (int64_t)N * (H + 3) * (W + 4) * 16;
 }
 
 extern "C" int cnm_pack_source(const float* src, void* packed, int N, int H, int W, void* stream) {
   CNM_REQUIRE(src && packed, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: null pointer");
   CNM_REQUIRE(N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: bad shape");
   CNM_REQUIRE(((uintptr_t)packed & 15) == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_source: packed must be 16B aligned");
-  size_t total = (size_t)N * (H + 6) * (W + 4);
+  size_t total = (size_t)N * (H + 3) * (W + 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_source_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (float4*)packed, N, H, W);
@@ -285,18 +234,19 @@ extern "C" int cnm_cost_volume(const float* ref, const void* packed_src, const f
   CNM_REQUIRE(((uintptr_t)packed_src & 15) == 0 && ((uintptr_t)out & 15) == 0, CNM_ERR_INVALID_ARGUMENT,
               "cnm_cost_volume: pointers must be 16B aligned");
   const int P = B * V;
-  CNM_REQUIRE((long long)P * (D / 8) <= 65535, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_cost_volume: too many pairs x planes");
+  constexpr int DPB = 16;
+  CNM_REQUIRE((long long)P * (D / DPB) <= 65535, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_cost_volume: too many pairs x planes");
   const double step = (idepth_max - idepth_min) / (double)(D - 1);
+  dim3 grid((W + CV_TX - 1) / CV_TX, (H + CV_TY - 1) / CV_TY, P * (D / DPB));
   dim3 block(CV_TX, CV_TY);
-  const unsigned gx = (unsigned)((W + CV_TX - 1) / CV_TX), gy = (unsigned)((H + CV_Q * CV_TY - 1) / (CV_Q * CV_TY));
   cudaStream_t s = (cudaStream_t)stream;
   const float4* tex = (const float4*)packed_src;
   if (layout == CNM_VOLUME_NCHW_F32)
-    cost_volume_kernel<16, 0><<<dim3(gx, gy, P * (D / 16)), block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    cost_volume_kernel<DPB, 0><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else if (dtype == CNM_BF16)
-    cost_volume_kernel<8, 1><<<dim3(gx, gy, P * (D / 8)), block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    cost_volume_kernel<DPB, 1><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else if (dtype == CNM_TF32)
-    cost_volume_kernel<8, 2><<<dim3(gx, gy, P * (D / 8)), block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    cost_volume_kernel<DPB, 2><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else
     return fail(CNM_ERR_INVALID_ARGUMENT, "cnm_cost_volume: dtype %d", dtype);
   return after_launch("cnm_cost_volume");

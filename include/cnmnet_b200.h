@@ -62,7 +62,7 @@ int cnm_camera_setup(const float* ref_cam, const float* src_cam, float* hk, int 
 
 /* ---- plane-sweep cost volume -----------------------------------------------------------
  * replaces depthNet.getVolume incl. F.grid_sample  (depthnet/depthNet_model.py:185-224)
- * cnm_pack_source: src [N,3,H,W] fp32 -> packed texels [N, H+6, W+4] x float4 (RGB0) with a
+ * cnm_pack_source: src [N,3,H,W] fp32 -> packed texels [N, H+3, W+4] x float4 (RGB0) with a
  *   zero border (row/col -1 and the trailing ones) so zero padding needs no predicates.
  * cnm_cost_volume: ref [B,3,H,W]; packed sources for pair p = v*B + b; hk [V*B,12];
  *   out per `layout`; D planes, z_d = 1/(idmin + d (idmax-idmin)/(D-1)) evaluated in fp64.  */
