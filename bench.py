@@ -44,7 +44,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons every 50 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -55,7 +55,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -285,6 +285,8 @@ def main():
         "wall_ms_per_step_incl_flush": wall_ms / args.steps,
     }
 
+    if rank == 0 and os.environ.get("CNM_SAVE_TUNE_CACHE"):
+        cnmnet_b200.engine.save_tune_cache(os.environ["CNM_SAVE_TUNE_CACHE"])
     if rank == 0:
         # ---- per-kernel live timing for the rooflines (rank 0, outside the timed region) ----
         s = _lib.stream_ptr()
@@ -301,7 +303,8 @@ def main():
         tf32 = args.precision == "tf32"
         peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
         line["roofline"] = {
-            "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all %d conv launches of one step)" % len(conv_rows),
+            "kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit GEMM, all %d conv launches of one step)"
+                      % len(conv_rows),
             "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
             "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step,
             "peak_source": "%s bf16 sustained%s" % (peaks["source"], " x 0.5 for tf32" if tf32 else ""),

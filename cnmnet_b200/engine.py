@@ -144,6 +144,26 @@ def pack_weights(wf, cols, ch, dtype):
 
 _TUNE_CACHE = {}
 AUTOTUNE = os.environ.get("CNM_AUTOTUNE", "1") != "0"
+# optional JSON file with earlier decisions ({repr(key): [backend, bn]}): loaded at import, written by save_tune_cache().
+# Needed under profilers, where timing the candidates is meaningless (ncu serialises and replays every launch).
+TUNE_CACHE_FILE = os.environ.get("CNM_TUNE_CACHE", "")
+
+
+def _load_tune_cache():
+    if TUNE_CACHE_FILE and os.path.exists(TUNE_CACHE_FILE):
+        import json
+        with open(TUNE_CACHE_FILE) as f:
+            for k, v in json.load(f).items():
+                _TUNE_CACHE[k] = (v[0], int(v[1]), None)
+
+
+def save_tune_cache(path):
+    import json
+    with open(path, "w") as f:
+        json.dump({k: [v[0], v[1]] for k, v in _TUNE_CACHE.items()}, f, indent=0, sort_keys=True)
+
+
+_load_tune_cache()
 
 
 class ConvOp:
@@ -183,7 +203,7 @@ class ConvOp:
         self.flops = 2.0 * N * Ho * Wo * cout * self.num_steps * ch
         self._weights = None
         self.tuned = None
-        self.key = (dtype, N, Ho, Wo, cout, k, stride, tuple((s.kind, s.C, s.buf.shape[3]) for s in srcs))
+        self.key = repr((dtype, N, Ho, Wo, cout, k, stride, tuple((s.kind, s.C, s.buf.shape[3]) for s in srcs)))
         # default choice without tuning
         halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
         if backend == "tc" and halo_ok and HALO_MODE != "off" and (halo_tiles >= 120 or HALO_MODE == "force"):
