@@ -30,7 +30,7 @@ struct alignas(64) HaloParams {
   CUtensorMap out_map;
   const cnm_conv_group* groups;
   const float* bias;
-  int num_groups;
+  int num_groups, num_steps;
   int tiles_x, tiles_y, tiles_b, tiles_n;
   int a_stages, b_stages, slab_bytes;
   int src_pad[HL_MAX_SRCS];
@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  // carve-up: [A ring][B ring][staging 2 x 16 KB][bias][barriers][tmem slot]
+  // carve-up: [A ring][B ring][staging 16 KB][bias][barriers][tmem slot]
   const uint32_t off_b = (uint32_t)p.a_stages * p.slab_bytes;
   const uint32_t off_out = off_b + (uint32_t)p.b_stages * B_BYTES;
-  const uint32_t off_bias = off_out + 2 * HL_TILE_BYTES;
+  const uint32_t off_bias = off_out + HL_TILE_BYTES;
   const uint32_t off_bar = off_bias + BN * 4;
   const uint32_t bar0 = base + off_bar;
   auto fullA = [&](int s) { return bar0 + 8u * s; };
@@ -93,19 +93,18 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer, A slabs =================
+    // (separate from the B producer so that slab requests run a_stages groups ahead regardless of the B ring depth)
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      int sa = 0;
+      uint32_t pa = 0;
       int4 g_next = __ldg(reinterpret_cast<const int4*>(p.groups));
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
         int m = tile / p.tiles_n;
         const int x0 = (m % p.tiles_x) * 16;
         m /= p.tiles_x;
         const int y0 = (m % p.tiles_y) * 16;
         const int n0 = m / p.tiles_y;
-        int kstep = 0;
         for (int g = 0; g < p.num_groups; ++g) {
           const int4 gr = g_next;  // src, c0, dx, ntaps
           g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == p.num_groups) ? 0 : g + 1)));
@@ -114,12 +113,22 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
           mbar_expect_tx(fullA(sa), (uint32_t)(16 + 2 * pad) * 2048u);
           tma_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-          for (int t = 0; t < gr.w; ++t, ++kstep) {
-            mbar_wait(emptyB(sb), pb ^ 1);
-            mbar_expect_tx(fullB(sb), B_BYTES);
-            tma_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN);
-            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
-          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= TMA producer, B (weight) tiles =================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      const int num_steps = p.num_steps;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        for (int kstep = 0; kstep < num_steps; ++kstep) {
+          mbar_wait(emptyB(sb), pb ^ 1);
+          mbar_expect_tx(fullB(sb), B_BYTES);
+          tma_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN);
+          if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
         }
       }
     }
@@ -168,7 +177,6 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     const int et = threadIdx.x - 128;
     const bool leader = (et == 0);
     int it = 0;
-    uint32_t chunk_counter = 0;
     int bias_tile = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.tiles_n;
@@ -190,10 +198,11 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
       for (int half = 0; half < 2; ++half) {
         const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + half * BN);
 #pragma unroll 1
-        for (int ch = 0; ch < NUM_CHUNKS; ++ch, ++chunk_counter) {
-          const uint32_t buf = chunk_counter & 1;
-          uint8_t* stg = base_ptr + off_out + buf * HL_TILE_BYTES;
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
+          // one staging buffer (smem goes to deeper operand rings): the previous chunk's TMA store must have
+          // finished reading it; the epilogue runs under the next tile's main loop, so this wait is off the critical path
+          uint8_t* stg = base_ptr + off_out;
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           epi_bar();
           uint32_t v[COLS_PER_CHUNK];
           tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
@@ -308,16 +317,31 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   p.groups = groups;
   p.bias = bias;
   p.num_groups = num_groups;
+  p.num_steps = d->num_steps;
   p.relu = d->relu;
   p.c_out_offset = d->c_out_offset;
-  // smem budget: 227 KB - alignment slack - staging - bias - barriers
-  const int fixed = 1024 + 2 * HL_TILE_BYTES + BN * 4 + 8 * (2 * HL_MAX_A + 2 * HL_MAX_B + 4) + 16;
+  // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
+  // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
+  // lasts ntaps B tiles.
+  const int fixed = 1024 + HL_TILE_BYTES + BN * 4 + 8 * (2 * HL_MAX_A + 2 * HL_MAX_B + 4) + 16;
   const int budget = 232448 - fixed;
-  p.b_stages = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
-  p.a_stages = (budget - p.b_stages * BN * 128) / p.slab_bytes;
-  if (p.a_stages > HL_MAX_A) p.a_stages = HL_MAX_A;
-  if (p.a_stages < 2) { p.b_stages -= 1; p.a_stages = (budget - p.b_stages * BN * 128) / p.slab_bytes; }
-  CNM_REQUIRE(p.a_stages >= 2, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: slab of %d B does not fit twice", p.slab_bytes);
+  const int want_b = BN == 256 ? 4 : (BN == 128 ? 7 : 8);
+  p.a_stages = (pmax >= 3 || BN == 256) ? 2 : (BN == 64 ? 4 : 3);
+  p.b_stages = (budget - p.a_stages * p.slab_bytes) / (BN * 128);
+  if (p.b_stages > want_b) p.b_stages = want_b;
+  if (p.b_stages > HL_MAX_B) p.b_stages = HL_MAX_B;
+  while (p.b_stages < 3 && p.a_stages > 2) {
+    p.a_stages -= 1;
+    p.b_stages = (budget - p.a_stages * p.slab_bytes) / (BN * 128);
+  }
+  CNM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_conv2d_halo: slab of %d B does not fit", p.slab_bytes);
+  {  // spend what is left on more slabs
+    const int left = budget - p.a_stages * p.slab_bytes - p.b_stages * BN * 128;
+    const int extra = left / p.slab_bytes;
+    p.a_stages += extra;
+    if (p.a_stages > HL_MAX_A) p.a_stages = HL_MAX_A;
+  }
   const int smem = fixed + p.a_stages * p.slab_bytes + p.b_stages * BN * 128;
 
   for (int i = 0; i < d->num_srcs; ++i) {

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ s
 // (zero outside the image = conv padding), so each input pixel crosses L2 -> SM 1.3-1.6x instead of 3.2x.  LPP lanes
 // per pixel, one 16-byte vector per lane and tap; fp32 accumulate, shuffle reduce, bias + scale * sigmoid epilogue.
 template <typename T, int LPP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     head3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, float bias, float scale,
                    float* __restrict__ out, float* __restrict__ logits, int H, int W, int C, int TR) {
   extern __shared__ __align__(16) uint8_t hsm[];
@@ -261,22 +261,43 @@ __global__ void __launch_bounds__(256)
   __syncthreads();
   const int sub = threadIdx.x % LPP, grp = threadIdx.x / LPP;
   constexpr int GROUPS = 256 / LPP;
+  // When one 16-byte vector per lane covers all channels (C == LPP*VN) a lane needs the same 9*VN weights for every
+  // pixel: keep them in registers.  Otherwise (C = 512) they are read from shared memory per pixel.
+  const bool wreg = (C == LPP * VN);
+  float wr[9][VN];
+  if (wreg) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < VN; ++j) wr[t][j] = ws[t * C + sub * VN + j];
+  }
   for (int pi = grp; pi < TR * 32; pi += GROUPS) {  // uniform trip count: TR*32 is a multiple of GROUPS
     const int ty = pi / 32, tx = pi % 32;
     float acc = 0.0f;
-    for (int c = sub * VN; c < C; c += LPP * VN) {
+    if (wreg) {
+      const T* tp = tile + ((size_t)ty * 34 + tx) * C + sub * VN;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         float v[VN];
-        Vec16<T>::load(tile + ((size_t)(ty + t / 3) * 34 + tx + t % 3) * C + c, v);
-        const float* wp = ws + t * C + c;
+        Vec16<T>::load(tp + ((t / 3) * 34 + t % 3) * C, v);
 #pragma unroll
-        for (int j = 0; j < VN; j += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wp + j);
-          acc = fmaf(v[j], w4.x, acc);
-          acc = fmaf(v[j + 1], w4.y, acc);
-          acc = fmaf(v[j + 2], w4.z, acc);
-          acc = fmaf(v[j + 3], w4.w, acc);
+        for (int j = 0; j < VN; ++j) acc = fmaf(v[j], wr[t][j], acc);
+      }
+    } else {
+      for (int c = sub * VN; c < C; c += LPP * VN) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          float v[VN];
+          Vec16<T>::load(tile + ((size_t)(ty + t / 3) * 34 + tx + t % 3) * C + c, v);
+          const float* wp = ws + t * C + c;
+#pragma unroll
+          for (int j = 0; j < VN; j += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + j);
+            acc = fmaf(v[j], w4.x, acc);
+            acc = fmaf(v[j + 1], w4.y, acc);
+            acc = fmaf(v[j + 2], w4.z, acc);
+            acc = fmaf(v[j + 3], w4.w, acc);
+          }
         }
       }
     }
