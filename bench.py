@@ -34,6 +34,12 @@ DEPTHNET_GFLOP, REFINE_GFLOP = 161.43, 112.79
 C2_COST_VOLUME_BYTES = 5 * (2 * 4 * D * H * W + 3 * 4 * 3 * H * W)  # 134 676 480
 
 
+def load_traffic():
+    """ncu-measured DRAM bytes (read + write) of the profiled kernels, committed under profiles/ (null if absent)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -195,6 +201,7 @@ def main():
     from cnmnet_b200.dist import gather_outputs
     lib = _lib.load()
     peaks = load_peaks()
+    traffic = load_traffic()
     B = B_PER_GPU
     dnet, rnet = make_weights(0)
     dnet.precision = rnet.precision = cnmnet_b200.engine.parse_dtype(args.precision)
@@ -305,7 +312,9 @@ def main():
         line["roofline"] = {
             "kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit GEMM, all %d conv launches of one step)"
                       % len(conv_rows),
-            "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+            "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+            "traffic": traffic.get("conv_bytes_per_step") if not tf32 else None,
+            "traffic_note": "DRAM read+write bytes of all conv launches of one step, ncu (profiles/r01_launches_step.md)",
             "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step,
             "peak_source": "%s bf16 sustained%s" % (peaks["source"], " x 0.5 for tf32" if tf32 else ""),
             "issued_tflops_incl_padding": issued_flop / (conv_ms * 1e-3) / 1e12,
@@ -330,7 +339,8 @@ def main():
         gbs = C2_COST_VOLUME_BYTES / (ms_cvk * 1e-3) / 1e9
         line["roofline_cost_volume"] = {
             "kernel": "cost_volume_kernel (C2: 256x192x64, 2 views, batch 5, fp32 NCHW)", "bound": "hbm",
-            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+            "traffic": traffic.get("cost_volume_c2_bytes"),
             "us_per_launch": ms_cvk * 1e3, "us_with_source_repack": ms_cv * 1e3, "algorithmic_bytes": C2_COST_VOLUME_BYTES,
             "peak_source": peaks["source"],
         }
