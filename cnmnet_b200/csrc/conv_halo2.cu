@@ -1,0 +1,430 @@
+// K2h2: the row-halo convolution (conv_halo.cu) on CTA PAIRS: tcgen05.mma.cta_group::2 with M = 256.
+//
+// Why: with both operands in shared memory a single-SM UMMA at N <= 128 is bound by the 128 B/clk shared-memory port
+// (profiles/r01_conv_halo_ncu.md: 4 KB of A + 4 KB of B per 64-cycle MMA plus the TMA fill).  In cta_group::2 the two
+// SMs of a cluster execute one M = 256 MMA together: each SM supplies the 128 A rows of its own pixel tile but only
+// HALF of the weight tile (BN/2 rows), so B reads and B fill per SM halve.
+//
+// Structure (differences to conv_halo.cu only):
+//   * cluster of 2 CTAs, both walk the same (N-tile, group, tap) sequence on two different 16x16 pixel blocks;
+//   * every CTA TMA-loads its own A slabs and its half of each B tile; the loads signal the LEADER CTA's "full"
+//     barriers (cp.async.bulk.tensor ... .cta_group::2 with the peer bit of the barrier address cleared);
+//   * only the leader's warp 1 issues MMAs (D = 128 rows x BN columns in EACH CTA's TMEM); tcgen05.commit is
+//     multicast to both CTAs' "empty" and "accumulator full" barriers;
+//   * both CTAs run the epilogue on their own TMEM half; "accumulator empty" arrivals go to the leader's barrier.
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace cnm {
+
+constexpr int H2_MAX_SRCS = 3;
+constexpr int H2_TILE_BYTES = 128 * 128;
+constexpr int H2_MAX_A = 4, H2_MAX_B = 8;
+
+struct alignas(64) Halo2Params {
+  CUtensorMap a_maps[H2_MAX_SRCS];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  const cnm_conv_group* groups;
+  const float* bias;
+  int num_groups, num_steps;
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int a_stages, b_stages, slab_bytes;
+  int src_pad[H2_MAX_SRCS];
+  int relu;
+  int c_out_offset;
+};
+
+// ---- 2-CTA PTX wrappers --------------------------------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA's smem, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// tcgen05.commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (TF32)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+// arrive on the barrier at this offset in the leader CTA (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+
+template <int BN, bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_kernel(const __grid_constant__ Halo2Params p) {
+  constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;
+  constexpr int CHUNK_CH = TF32 ? 32 : 64;
+  constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
+  constexpr int ACC_STAGES = (4 * BN <= 512) ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = (2 * BN * ACC_STAGES) < 32 ? 32 : 2 * BN * ACC_STAGES;
+  constexpr int B_BYTES = (BN / 2) * 128;  // this CTA's half of the weight tile
+  constexpr uint32_t IDESC = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M = 256 over the CTA pair
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  // carve-up: [A ring][B ring][staging 16 KB][bias][barriers][tmem slot]
+  const uint32_t off_b = (uint32_t)p.a_stages * p.slab_bytes;
+  const uint32_t off_out = off_b + (uint32_t)p.b_stages * B_BYTES;
+  const uint32_t off_bias = off_out + H2_TILE_BYTES;
+  const uint32_t off_bar = off_bias + BN * 4;
+  const uint32_t bar0 = base + off_bar;
+  auto fullA = [&](int s) { return bar0 + 8u * s; };
+  auto emptyA = [&](int s) { return bar0 + 8u * (H2_MAX_A + s); };
+  auto fullB = [&](int s) { return bar0 + 8u * (2 * H2_MAX_A + s); };
+  auto emptyB = [&](int s) { return bar0 + 8u * (2 * H2_MAX_A + H2_MAX_B + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (2 * H2_MAX_A + 2 * H2_MAX_B + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (2 * H2_MAX_A + 2 * H2_MAX_B + 2 + a); };
+  const uint32_t off_tmem = off_bar + 8u * (2 * H2_MAX_A + 2 * H2_MAX_B + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
+  float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // a super-tile = the same N tile on two neighbouring pixel blocks (m = 2*mm + rank), one per CTA of the pair
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int total_tiles = (p.tiles_x * p.tiles_y * p.tiles_b / 2) * p.tiles_n;
+  const int first_tile = blockIdx.x >> 1, tile_stride = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.out_map);
+    tma_prefetch_desc(&p.a_maps[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + off_tmem), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised and TMEM is allocated before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer, A slabs =================
+    // (separate from the B producer so that slab requests run a_stages groups ahead regardless of the B ring depth)
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pa = 0;
+      int4 g_next = __ldg(reinterpret_cast<const int4*>(p.groups));
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        int m = 2 * (tile / p.tiles_n) + (int)rank;
+        const int x0 = (m % p.tiles_x) * 16;
+        m /= p.tiles_x;
+        const int y0 = (m % p.tiles_y) * 16;
+        const int n0 = m / p.tiles_y;
+        for (int g = 0; g < p.num_groups; ++g) {
+          const int4 gr = g_next;  // src, c0, dx, ntaps
+          g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == p.num_groups) ? 0 : g + 1)));
+          const int pad = p.src_pad[gr.x];
+          mbar_wait(emptyA(sa), pa ^ 1);
+          if (leader) mbar_expect_tx(fullA(sa), 2u * (uint32_t)(16 + 2 * pad) * 2048u);  // both CTAs' slabs
+          tma2_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ================= TMA producer, B (weight) tiles =================
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      const int num_steps = p.num_steps;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        const int nt = tile % p.tiles_n;
+        for (int kstep = 0; kstep < num_steps; ++kstep) {
+          mbar_wait(emptyB(sb), pb ^ 1);
+          if (leader) mbar_expect_tx(fullB(sb), 2u * B_BYTES);  // both halves
+          tma2_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN + (int)rank * (BN / 2));
+          if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only; one M = 256 MMA spans both CTAs) =================
+    if (lane == 0 && leader) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+        const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
+        const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+        mbar_wait(tempty(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 2 * BN);
+        uint32_t first = 1;
+        for (int g = 0; g < p.num_groups; ++g) {
+          const int ntaps = __ldg(&p.groups[g].ntaps);
+          mbar_wait(fullA(sa), pa);
+          tc_fence_after();
+          const uint32_t slab = base + sa * p.slab_bytes;
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(fullB(sb), pb);
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
+            const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc2_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+              tc2_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+            }
+            first = 0;
+            tc2_commit(emptyB(sb));
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+          }
+          tc2_commit(emptyA(sa));
+          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        }
+        tc2_commit(tfull(as));
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    const bool storer = (et == 0);
+    int it = 0;
+    int bias_tile = -1;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+      const int nt = tile % p.tiles_n;
+      int m = 2 * (tile / p.tiles_n) + (int)rank;
+      const int x0 = (m % p.tiles_x) * 16;
+      m /= p.tiles_x;
+      const int y0 = (m % p.tiles_y) * 16;
+      const int n0 = m / p.tiles_y;
+      const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
+      const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+      if (bias_tile != nt) {
+        epi_bar();
+        for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
+        bias_tile = nt;
+      }
+      mbar_wait(tfull(as), aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + half * BN);
+#pragma unroll 1
+        for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
+          // one staging buffer (smem goes to deeper operand rings): the previous chunk's TMA store must have
+          // finished reading it; the epilogue runs under the next tile's main loop, so this wait is off the critical path
+          uint8_t* stg = base_ptr + off_out;
+          if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          epi_bar();
+          uint32_t v[COLS_PER_CHUNK];
+          tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
+          if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
+          tmem_ld_wait();
+          const float* bs = bias_s + ch * COLS_PER_CHUNK;
+          uint8_t* rowp = stg + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 o;
+            if (TF32) {
+              float f[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
+                if (p.relu) t = fmaxf(t, 0.0f);
+                f[e] = round_tf32(t);
+              }
+              o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+            } else {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
+                float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
+                if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_bar();
+          if (storer) {
+            tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + nt * BN + ch * CHUNK_CH, x0, y0 + 8 * half, n0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_leader(tempty(as));  // 2 x 128 arrivals on the leader's barrier release the accumulator stage
+    }
+    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its operands
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN, bool TF32>
+static int launch_halo2(const Halo2Params& p, int grid, int smem, cudaStream_t s) {
+  static int configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_halo2: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  conv_halo2_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
+  return after_launch("cnm_conv2d_halo2");
+}
+
+}  // namespace cnm
+
+using namespace cnm;
+
+extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* src_pad,
+                               const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                               void* stream) {
+  int rc = check_conv_args("cnm_conv2d_halo2", d, srcs, groups, wp, out);
+  if (rc) return rc;
+  CNM_REQUIRE(src_pad && num_groups > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo2: bad group list");
+  CNM_REQUIRE(d->stride == 1, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo2: stride 1 only (use cnm_conv2d_tc)");
+  CNM_REQUIRE(d->Ho >= 16 && d->Wo >= 16, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_conv2d_halo2: output %dx%d smaller than the 16x16 tile (use cnm_conv2d_tc)", d->Ho, d->Wo);
+  CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo2: Cout=%d must be a multiple of 64", d->Cout);
+  CNM_REQUIRE((((d->Wo + 15) / 16) * ((d->Ho + 15) / 16) * d->N) % 2 == 0, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_conv2d_halo2: needs an even number of 16x16 pixel blocks (CTA pairs)");
+  const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
+  Halo2Params p;
+  memset(&p, 0, sizeof(p));
+  int pmax = 0;
+  for (int i = 0; i < d->num_srcs; ++i) {
+    CNM_REQUIRE(src_pad[i] >= 0 && src_pad[i] <= 4, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo2: pad %d", src_pad[i]);
+    p.src_pad[i] = src_pad[i];
+    if (src_pad[i] > pmax) pmax = src_pad[i];
+  }
+  p.slab_bytes = (16 + 2 * pmax) * 2048;
+  p.tiles_x = (d->Wo + 15) / 16;
+  p.tiles_y = (d->Ho + 15) / 16;
+  p.tiles_b = d->N;
+  const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+  // column tile: minimise waves x relative tile time.  BN=256 holds 2 x 256 accumulator columns = all of TMEM, so its
+  // epilogue is not overlapped with the next tile's main loop (~10 % on top of twice the BN=128 tile time).
+  int BN = 64;
+  if (d->Cout % 128 == 0) {
+    BN = 128;
+    if (d->Cout % 256 == 0) {
+      const long w256 = ((long)m_tiles * (d->Cout / 256) + 147) / 148, w128 = ((long)m_tiles * (d->Cout / 128) + 147) / 148;
+      if (w256 * 20 <= w128 * 10) BN = 256;
+    }
+  }
+  if (d->reserved == 64 || d->reserved == 128 || d->reserved == 256) {  // caller-selected tile (host autotuner)
+    CNM_REQUIRE(d->Cout % d->reserved == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo2: BN=%d does not divide Cout=%d",
+                d->reserved, d->Cout);
+    BN = d->reserved;
+  }
+  p.tiles_n = d->Cout / BN;
+  p.groups = groups;
+  p.bias = bias;
+  p.num_groups = num_groups;
+  p.num_steps = d->num_steps;
+  p.relu = d->relu;
+  p.c_out_offset = d->c_out_offset;
+  // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
+  // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
+  // lasts ntaps B tiles.
+  const int fixed = 1024 + H2_TILE_BYTES + BN * 4 + 8 * (2 * H2_MAX_A + 2 * H2_MAX_B + 4) + 16;
+  const int budget = 232448 - fixed;
+  const int want_b = 8;
+  p.a_stages = (pmax >= 3 || BN == 256) ? 2 : (BN == 64 ? 4 : 3);
+  p.b_stages = (budget - p.a_stages * p.slab_bytes) / (BN * 64);
+  if (p.b_stages > want_b) p.b_stages = want_b;
+  if (p.b_stages > H2_MAX_B) p.b_stages = H2_MAX_B;
+  while (p.b_stages < 3 && p.a_stages > 2) {
+    p.a_stages -= 1;
+    p.b_stages = (budget - p.a_stages * p.slab_bytes) / (BN * 64);
+  }
+  CNM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_conv2d_halo2: slab of %d B does not fit", p.slab_bytes);
+  {  // spend what is left on more slabs
+    const int left = budget - p.a_stages * p.slab_bytes - p.b_stages * BN * 64;
+    const int extra = left / p.slab_bytes;
+    p.a_stages += extra;
+    if (p.a_stages > H2_MAX_A) p.a_stages = H2_MAX_A;
+  }
+  const int smem = fixed + p.a_stages * p.slab_bytes + p.b_stages * BN * 64;
+
+  for (int i = 0; i < d->num_srcs; ++i) {
+    const cnm_conv_src& s = srcs[i];
+    const uint64_t pix = (uint64_t)s.C * eb;
+    const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)d->N};
+    const uint64_t str[3] = {pix, pix * s.W, pix * s.W * s.H};
+    const uint32_t box[4] = {(uint32_t)ch, 16u, (uint32_t)(16 + 2 * p.src_pad[i]), 1u};
+    rc = encode_map(&p.a_maps[i], d->dtype, 4, s.ptr, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t K = (uint64_t)d->num_steps * ch;
+    const uint64_t dims[2] = {K, (uint64_t)d->Cout};
+    const uint64_t str[1] = {K * eb};
+    const uint32_t bbox[2] = {(uint32_t)ch, (uint32_t)(BN / 2)};
+    rc = encode_map(&p.b_map, d->dtype, 2, wp, dims, str, bbox);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t pix = (uint64_t)d->c_out_total * eb;
+    const uint64_t dims[4] = {(uint64_t)d->c_out_total, (uint64_t)d->Wo, (uint64_t)d->Ho, (uint64_t)d->N};
+    const uint64_t str[3] = {pix, pix * d->Wo, pix * d->Wo * d->Ho};
+    const uint32_t box[4] = {(uint32_t)ch, 16u, 8u, 1u};
+    rc = encode_map(&p.out_map, d->dtype, 4, out, dims, str, box);
+    if (rc) return rc;
+  }
+  const int total = (m_tiles / 2) * p.tiles_n;  // super-tiles, one per CTA pair
+  const int grid = 2 * (total < 74 ? total : 74);
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tf32 = d->dtype == CNM_TF32;
+  if (BN == 256) return tf32 ? launch_halo2<256, true>(p, grid, smem, s) : launch_halo2<256, false>(p, grid, smem, s);
+  if (BN == 128) return tf32 ? launch_halo2<128, true>(p, grid, smem, s) : launch_halo2<128, false>(p, grid, smem, s);
+  return tf32 ? launch_halo2<64, true>(p, grid, smem, s) : launch_halo2<64, false>(p, grid, smem, s);
+}

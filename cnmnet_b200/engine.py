@@ -20,6 +20,7 @@ BN_EPS = 1e-5
 # which stride-1 layers use the row-halo kernel: "auto" (enough tiles for a wave), "force" (every eligible layer,
 # used by tests), "off" (per-tap kernel everywhere)
 HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
+HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
 TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32}
 
 
@@ -182,13 +183,15 @@ class ConvOp:
         st[:, :5] = torch.tensor(steps, dtype=torch.int32)
         self.variants["tc"] = {"cols": cols, "steps_dev": st.to(device)}
         self.variants["simt"] = self.variants["tc"]
-        halo_ok = stride == 1 and Ho >= 16 and Wo >= 16 and backend in ("tc", "halo")
+        halo_ok = stride == 1 and Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2")
         if halo_ok:
             groups, gcols, pads = make_groups(srcs, k, ch)
             assert len(gcols) == len(cols)
             self.variants["halo"] = {"cols": gcols, "groups_dev": torch.tensor(groups, dtype=torch.int32).to(device),
                                      "ngroups": len(groups), "pads": (C.c_int32 * len(pads))(*pads)}
-        elif backend == "halo":
+            if (N * ((Ho + 15) // 16) * ((Wo + 15) // 16)) % 2 == 0 and HALO2_ENABLED:
+                self.variants["halo2"] = self.variants["halo"]   # same program, CTA-pair kernel
+        elif backend in ("halo", "halo2"):
             raise ValueError("%s: the row-halo kernel needs stride 1 and an output of at least 16x16" % name)
         self.num_steps = len(cols)
         self.out = out if out is not None else torch.empty((N, Ho, Wo, cout), dtype=TORCH_DTYPE[dtype], device=device)
@@ -208,7 +211,7 @@ class ConvOp:
         halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
         if backend == "tc" and halo_ok and HALO_MODE != "off" and (halo_tiles >= 120 or HALO_MODE == "force"):
             backend = "halo"
-        self.tunable = backend in ("tc", "halo") and HALO_MODE == "auto" and AUTOTUNE
+        self.tunable = backend in ("tc", "halo", "halo2") and HALO_MODE == "auto" and AUTOTUNE
         self.select(backend, 0)
 
     @property
@@ -225,7 +228,7 @@ class ConvOp:
     def candidates(self):
         cout = self.desc.Cout
         out = []
-        for be in ("tc", "halo"):
+        for be in ("tc", "halo", "halo2"):
             if be in self.variants:
                 out += [(be, bn) for bn in (256, 128, 64) if cout % bn == 0]
         return out
@@ -263,8 +266,9 @@ class ConvOp:
     def __call__(self, stream):
         lib = _lib.load()
         v = self.variants[self.backend]
-        if self.backend == "halo":
-            _lib.check(lib.cnm_conv2d_halo(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(),
+        if self.backend in ("halo", "halo2"):
+            fn = lib.cnm_conv2d_halo if self.backend == "halo" else lib.cnm_conv2d_halo2
+            _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(),
                                            v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),
                                            self.out.data_ptr(), stream), self.name)
             return

@@ -190,6 +190,12 @@ int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const i
                     const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
                     void* stream);
 
+/* Same contract as cnm_conv2d_halo on CTA pairs (tcgen05.mma.cta_group::2, M = 256: csrc/conv_halo2.cu); additionally
+ * needs an even number of 16x16 pixel blocks.                                                                       */
+int cnm_conv2d_halo2(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* src_pad,
+                     const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                     void* stream);
+
 /* ---- depth-driven inverse warp ("next") ----------------------------
  * replaces inverse_warp + cam2pixel  (depthnet/inverse_warp.py:46-118).
  * feat [B,C,H,W], depth [B,H,W], pose [B,3,4], K [B,3,3], Kinv [B,3,3] -> out [B,C,H,W];
