@@ -13,7 +13,8 @@
 // B tile          per tap {chunk, BN} of the packed weights, shared by the two pixel tiles (halves weight traffic).
 // Pipelines       A ring (2-4 slabs) and B ring (3-6 tiles), both TMA -> mbarrier -> tcgen05.mma -> tcgen05.commit.
 // Accumulators    2 x BN TMEM columns per tile pair; double-buffered when 4*BN <= 512.
-// Warp roles      as conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+// Warp roles      warp 0 A-slab TMA producer, warp 3 B-tile TMA producer, warps 1-2 MMA issuers (one per pixel tile;
+//                   warp 2 also allocates TMEM), warps 4-7 epilogue.
 #include <cstring>
 
 #include "tc_common.cuh"
@@ -68,7 +69,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
   float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -77,9 +79,9 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     tma_prefetch_desc(&p.a_maps[0]);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
-    for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 2); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 2); mbar_init(tempty(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -132,9 +134,17 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // ================= MMA issuers =================
+    // Two issuing lanes, one per pixel tile of the pair (warp 1 -> rows 0-7 / accumulator columns [0,BN), warp 2 -> rows
+    // 8-15 / [BN,2BN)): a single lane needs ~100 instructions per weight step (barrier wait, descriptors, 8 MMAs,
+    // commit), which at BN <= 128 is as long as the MMAs themselves take (profiles/r01_conv_halo_ncu.md).  Each
+    // barrier that the MMAs release therefore expects two commits.
+    // The whole warp walks the loop (all lanes poll the barriers) and one elected lane issues: this keeps the control
+    // flow warp-uniform, so the compiler holds descriptors in uniform registers instead of wrapping every tcgen05
+    // instruction in a per-lane election loop.
+    {
+      const int half = warp - 1;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -143,31 +153,32 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
         const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(tempty(as), aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 2 * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 2 * BN + half * BN);
         uint32_t first = 1;
         for (int g = 0; g < p.num_groups; ++g) {
           const int ntaps = __ldg(&p.groups[g].ntaps);
           mbar_wait(fullA(sa), pa);
-          tc_fence_after();
-          const uint32_t slab = base + sa * p.slab_bytes;
+          const uint64_t adesc0 = umma_desc(base + sa * p.slab_bytes + half * 8 * 2048);
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(fullB(sb), pb);
             tc_fence_after();
-            const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
-            const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
+            if (elect_one()) {
+              const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
+              const uint64_t adesc = adesc0 + (uint64_t)(t * (2048 >> 4));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
-              tc_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k)
+                tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+              tc_commit(emptyB(sb));
+              if (t == ntaps - 1) tc_commit(emptyA(sa));
             }
+            __syncwarp();
             first = 0;
-            tc_commit(emptyB(sb));
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
-          tc_commit(emptyA(sa));
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
-        tc_commit(tfull(as));
+        if (elect_one()) tc_commit(tfull(as));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

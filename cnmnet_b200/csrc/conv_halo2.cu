@@ -113,7 +113,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
   float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   // a super-tile = the same N tile on two neighbouring pixel blocks (m = 2*mm + rank), one per CTA of the pair
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
@@ -183,7 +184,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only; one M = 256 MMA spans both CTAs) =================
-    if (lane == 0 && leader) {
+    // whole warp walks the loop, one elected lane issues (warp-uniform control flow, see conv_halo.cu)
+    if (leader) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -197,26 +199,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
         for (int g = 0; g < p.num_groups; ++g) {
           const int ntaps = __ldg(&p.groups[g].ntaps);
           mbar_wait(fullA(sa), pa);
-          tc_fence_after();
           const uint32_t slab = base + sa * p.slab_bytes;
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(fullB(sb), pb);
             tc_fence_after();
-            const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
-            const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
+            if (elect_one()) {
+              const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
+              const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc2_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
-              tc2_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) {
+                tc2_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+                tc2_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+              }
+              tc2_commit(emptyB(sb));
+              if (t == ntaps - 1) tc2_commit(emptyA(sa));
             }
+            __syncwarp();
             first = 0;
-            tc2_commit(emptyB(sb));
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
-          tc2_commit(emptyA(sa));
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
-        tc2_commit(tfull(as));
+        if (elect_one()) tc2_commit(tfull(as));
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TMEM);
   float* bias_s = reinterpret_cast<float*>(base_ptr + L::OFF_BIAS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
 
   if (warp == 0 && lane == 0) {
@@ -133,7 +134,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // The whole warp walks the loop and one elected lane issues (warp-uniform control flow: descriptors stay in
+    // uniform registers, the tcgen05 instructions are not wrapped in per-lane election loops).
+    {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -146,15 +149,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int ks = 0; ks < p.num_steps; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = base + stage * L::STAGE_BYTES;
-          const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + TC_A_BYTES);
+          if (elect_one()) {
+            const uint32_t sa = base + stage * L::STAGE_BYTES;
+            const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + TC_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32 B along K inside the 128 B swizzle row
-            tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (ks | k) ? 1u : 0u);
-          tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+            for (int k = 0; k < 4; ++k)  // 4 x 32 B along K inside the 128 B swizzle row
+              tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (ks | k) ? 1u : 0u);
+            tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+            if (ks == p.num_steps - 1) tc_commit(tfull_bar(as));  // accumulator complete
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(as));  // accumulator complete
       }
     }
   } else if (warp >= 4) {
