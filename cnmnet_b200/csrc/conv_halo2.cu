@@ -23,7 +23,7 @@ constexpr int H2_TILE_BYTES = 128 * 128;
 constexpr int H2_MAX_A = 4, H2_MAX_B = 8;
 
 struct alignas(64) Halo2Params {
-  CUtensorMap a_maps[H2_MAX_SRCS];
+  CUtensorMap a_maps[H2_MAX_SRCS * 4];  // [source][parity sub-image]
   CUtensorMap b_map;
   CUtensorMap out_map;
   const cnm_conv_group* groups;
@@ -31,7 +31,8 @@ struct alignas(64) Halo2Params {
   int num_groups, num_steps;
   int tiles_x, tiles_y, tiles_b, tiles_n;
   int a_stages, b_stages, slab_bytes;
-  int src_pad[H2_MAX_SRCS];
+  int map_pad[H2_MAX_SRCS * 4];   // rows of the slab above the tile, per map
+  int map_rows[H2_MAX_SRCS * 4];  // slab height (16 + vertical tap span), per map
   int relu;
   int c_out_offset;
 };
@@ -158,9 +159,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
         for (int g = 0; g < p.num_groups; ++g) {
           const int4 gr = g_next;  // src, c0, dx, ntaps
           g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == p.num_groups) ? 0 : g + 1)));
-          const int pad = p.src_pad[gr.x];
+          const int pad = p.map_pad[gr.x];
+          const uint32_t slab_tx = (uint32_t)p.map_rows[gr.x] * 2048u;
           mbar_wait(emptyA(sa), pa ^ 1);
-          if (leader) mbar_expect_tx(fullA(sa), 2u * (uint32_t)(16 + 2 * pad) * 2048u);  // both CTAs' slabs
+          if (leader) mbar_expect_tx(fullA(sa), 2u * slab_tx);  // both CTAs' slabs
           tma2_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
@@ -328,13 +330,12 @@ static int launch_halo2(const Halo2Params& p, int grid, int smem, cudaStream_t s
 
 using namespace cnm;
 
-extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* src_pad,
+extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* map_info,
                                const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
                                void* stream) {
   int rc = check_conv_args("cnm_conv2d_halo2", d, srcs, groups, wp, out);
   if (rc) return rc;
-  CNM_REQUIRE(src_pad && num_groups > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo2: bad group list");
-  CNM_REQUIRE(d->stride == 1, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo2: stride 1 only (use cnm_conv2d_tc)");
+  CNM_REQUIRE(map_info && num_groups > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo2: bad group list");
   CNM_REQUIRE(d->Ho >= 16 && d->Wo >= 16, CNM_ERR_UNSUPPORTED_SHAPE,
               "cnm_conv2d_halo2: output %dx%d smaller than the 16x16 tile (use cnm_conv2d_tc)", d->Ho, d->Wo);
   CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo2: Cout=%d must be a multiple of 64", d->Cout);
@@ -343,13 +344,22 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
   const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
   Halo2Params p;
   memset(&p, 0, sizeof(p));
-  int pmax = 0;
-  for (int i = 0; i < d->num_srcs; ++i) {
-    CNM_REQUIRE(src_pad[i] >= 0 && src_pad[i] <= 4, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo2: pad %d", src_pad[i]);
-    p.src_pad[i] = src_pad[i];
-    if (src_pad[i] > pmax) pmax = src_pad[i];
-  }
-  p.slab_bytes = (16 + 2 * pmax) * 2048;
+  // map_info[src*4 + sub] = {rows above the tile, slab rows}; sub = 0 for stride 1, parity py*2+px for stride 2
+  int rows_max = 0;
+  const int nsub = d->stride == 2 ? 4 : 1;
+  for (int i = 0; i < d->num_srcs; ++i)
+    for (int sub = 0; sub < nsub; ++sub) {
+      const int m = i * 4 + sub, pad = map_info[2 * m], rows = map_info[2 * m + 1];
+      if (rows == 0) continue;  // sub-image not used by any group
+      CNM_REQUIRE(pad >= 0 && pad <= 4 && rows >= 16 && rows <= 24, CNM_ERR_UNSUPPORTED_SHAPE,
+                  "cnm_conv2d_halo2: map %d has pad %d / %d slab rows", m, pad, rows);
+      p.map_pad[m] = pad;
+      p.map_rows[m] = rows;
+      if (rows > rows_max) rows_max = rows;
+    }
+  CNM_REQUIRE(rows_max > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo2: no operand maps");
+  const int pmax = (rows_max - 16 + 1) / 2;
+  p.slab_bytes = rows_max * 2048;
   p.tiles_x = (d->Wo + 15) / 16;
   p.tiles_y = (d->Ho + 15) / 16;
   p.tiles_b = d->N;
@@ -403,11 +413,24 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
   for (int i = 0; i < d->num_srcs; ++i) {
     const cnm_conv_src& s = srcs[i];
     const uint64_t pix = (uint64_t)s.C * eb;
-    const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)d->N};
-    const uint64_t str[3] = {pix, pix * s.W, pix * s.W * s.H};
-    const uint32_t box[4] = {(uint32_t)ch, 16u, (uint32_t)(16 + 2 * p.src_pad[i]), 1u};
-    rc = encode_map(&p.a_maps[i], d->dtype, 4, s.ptr, dims, str, box);
-    if (rc) return rc;
+    for (int sub = 0; sub < nsub; ++sub) {
+      const int m = i * 4 + sub;
+      if (p.map_rows[m] == 0) continue;
+      const uint32_t box[4] = {(uint32_t)ch, 16u, (uint32_t)p.map_rows[m], 1u};
+      if (d->stride == 1) {
+        const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)d->N};
+        const uint64_t str[3] = {pix, pix * s.W, pix * s.W * s.H};
+        rc = encode_map(&p.a_maps[m], d->dtype, 4, s.ptr, dims, str, box);
+      } else {  // parity sub-image (py, px): every other row / column of the source, doubled strides
+        const int py = sub >> 1, px = sub & 1;
+        const int ws = (s.W - px + 1) / 2, hs = (s.H - py + 1) / 2;
+        const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)ws, (uint64_t)hs, (uint64_t)d->N};
+        const uint64_t str[3] = {2 * pix, 2 * pix * s.W, pix * s.W * s.H};
+        const uint8_t* ptr = (const uint8_t*)s.ptr + ((uint64_t)py * s.W + px) * pix;
+        rc = encode_map(&p.a_maps[m], d->dtype, 4, ptr, dims, str, box);
+      }
+      if (rc) return rc;
+    }
   }
   {
     const uint64_t K = (uint64_t)d->num_steps * ch;

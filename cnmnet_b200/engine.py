@@ -96,31 +96,48 @@ def make_steps(srcs, k, stride, ch):
     return steps, cols
 
 
-def make_groups(srcs, k, ch):
-    """Row-halo K loop for stride-1 layers (csrc/conv_halo.cu): -> (groups [(src, c0, dx, ntaps)], cols, pads).
-    One group = one slab load serving `ntaps` vertical taps; the weight steps (cols) follow group order."""
+def make_groups(srcs, k, ch, stride=1):
+    """Row-halo K loop (csrc/conv_halo.cu): -> (groups [(map, c0, dx, ntaps)], cols, map_info [12][2]).
+    One group = one slab load serving `ntaps` vertical taps; the weight steps (cols) follow group order.
+    map = src*4 + sub; map_info[map] = (rows of the slab above the tile, slab rows)."""
     pad = (k - 1) // 2
-    groups, cols, pads = [], [], []
+    groups, cols = [], []
+    info = [[0, 0] for _ in range(12)]
     for si, s in enumerate(srcs):
-        if s.kind == "act":
-            pads.append(pad)
+        if s.kind == "act" and stride == 1:
+            info[si * 4] = [pad, 16 + 2 * pad]
             for c0 in range(0, s.C, ch):
                 for t in range(k):
-                    groups.append((si, s.coff + c0, t - pad, k))
+                    groups.append((si * 4, s.coff + c0, t - pad, k))
                     cols += [("act", s.wch + c0, r, t) for r in range(k)]
+        elif s.kind == "act":  # stride 2: taps grouped by (column tap, row parity) on the parity sub-images
+            for c0 in range(0, s.C, ch):
+                for t in range(k):
+                    tx = t - pad
+                    px, qx = tx % 2, (tx - tx % 2) // 2
+                    for py in (0, 1):
+                        rs = [r for r in range(k) if (r - pad) % 2 == py]
+                        if not rs:
+                            continue
+                        qs = [(r - pad - py) // 2 for r in rs]
+                        assert qs == list(range(qs[0], qs[0] + len(qs)))
+                        m = si * 4 + py * 2 + px
+                        info[m] = [-qs[0], 16 + qs[-1] - qs[0]]
+                        groups.append((m, s.coff + c0, qx, len(rs)))
+                        cols += [("act", s.wch + c0, r, t) for r in rs]
         elif s.kind == "rowtaps":
-            assert k * s.nreal <= ch
-            pads.append(pad)
-            groups.append((si, 0, 0, k))
+            assert stride == 1 and k * s.nreal <= ch
+            info[si * 4] = [pad, 16 + 2 * pad]
+            groups.append((si * 4, 0, 0, k))
             cols += [("rowtaps", s.wch, s.nreal, r) for r in range(k)]
         elif s.kind == "taps3x3":
-            assert k == 3 and 9 * s.nreal <= ch
-            pads.append(0)
-            groups.append((si, 0, 0, 1))
+            assert stride == 1 and k == 3 and 9 * s.nreal <= ch
+            info[si * 4] = [0, 16]
+            groups.append((si * 4, 0, 0, 1))
             cols.append(("taps3x3", s.wch, s.nreal, 0))
         else:
             raise ValueError(s.kind)
-    return groups, cols, pads
+    return groups, cols, info
 
 
 def pack_weights(wf, cols, ch, dtype):
@@ -183,16 +200,18 @@ class ConvOp:
         st[:, :5] = torch.tensor(steps, dtype=torch.int32)
         self.variants["tc"] = {"cols": cols, "steps_dev": st.to(device)}
         self.variants["simt"] = self.variants["tc"]
-        halo_ok = stride == 1 and Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2")
+        halo_ok = Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2") and \
+            (stride == 1 or all(s.kind == "act" for s in srcs))
         if halo_ok:
-            groups, gcols, pads = make_groups(srcs, k, ch)
+            groups, gcols, info = make_groups(srcs, k, ch, stride)
             assert len(gcols) == len(cols)
+            flat = [v for pr in info for v in pr]
             self.variants["halo"] = {"cols": gcols, "groups_dev": torch.tensor(groups, dtype=torch.int32).to(device),
-                                     "ngroups": len(groups), "pads": (C.c_int32 * len(pads))(*pads)}
+                                     "ngroups": len(groups), "pads": (C.c_int32 * len(flat))(*flat)}
             if (N * ((Ho + 15) // 16) * ((Wo + 15) // 16)) % 2 == 0 and HALO2_ENABLED:
                 self.variants["halo2"] = self.variants["halo"]   # same program, CTA-pair kernel
         elif backend in ("halo", "halo2"):
-            raise ValueError("%s: the row-halo kernel needs stride 1 and an output of at least 16x16" % name)
+            raise ValueError("%s: the row-halo kernel needs an output of at least 16x16" % name)
         self.num_steps = len(cols)
         self.out = out if out is not None else torch.empty((N, Ho, Wo, cout), dtype=TORCH_DTYPE[dtype], device=device)
         self.wp = torch.zeros((cout, self.num_steps * ch), dtype=TORCH_DTYPE[dtype], device=device)

@@ -178,21 +178,22 @@ int cnm_conv2d_tc(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const cnm
 int cnm_conv2d_simt(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const cnm_conv_step* steps, const void* wp,
                     const float* bias, void* out, void* stream);
 
-/* Row-halo variant for stride-1 layers with Ho, Wo >= 16 (csrc/conv_halo.cu): same act / weight layouts and
- * descriptor; the K loop is given as GROUPS.  A group loads one slab {chunk, 16, 16+2*pad} of source `src`
- * (channels [c0, c0+chunk), columns shifted by dx, rows starting pad above the tile) and consumes `ntaps`
- * consecutive weight steps, tap t reading the slab rows shifted by t (dy = t - pad).  desc->num_steps is the total
- * number of weight steps (sum of ntaps); src_pad[i] is the vertical halo of source i (host array).             */
+/* Row-halo variant for layers with Ho, Wo >= 16 (csrc/conv_halo.cu): same act / weight layouts and descriptor; the
+ * K loop is given as GROUPS.  A group loads one slab {chunk, 16, rows} of operand map `map` = src*4 + sub (sub = 0
+ * for stride 1, the parity sub-image py*2+px for stride 2): channels [c0, c0+chunk), columns shifted by dx, rows
+ * starting `pad` above the tile; it consumes `ntaps` consecutive weight steps, tap t reading the slab rows shifted
+ * by t.  desc->num_steps is the total number of weight steps (sum of ntaps); map_info[2*map] = pad and
+ * map_info[2*map+1] = rows (16 + vertical tap span; 0 = map unused) is a HOST array of 12 x 2 ints.             */
 typedef struct cnm_conv_group {
-  int32_t src, c0, dx, ntaps;
+  int32_t map, c0, dx, ntaps;
 } cnm_conv_group;
-int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* src_pad,
+int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* map_info,
                     const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
                     void* stream);
 
 /* Same contract as cnm_conv2d_halo on CTA pairs (tcgen05.mma.cta_group::2, M = 256: csrc/conv_halo2.cu); additionally
  * needs an even number of 16x16 pixel blocks.                                                                       */
-int cnm_conv2d_halo2(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* src_pad,
+int cnm_conv2d_halo2(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* map_info,
                      const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
                      void* stream);
 

@@ -79,6 +79,9 @@ HALO_CASES = [
     (3, 48, 64, [64], 512, 3, 1),
     (16, 48, 64, [64], 256, 3, 1),     # >= 120 tiles of BN = 256: single-buffered accumulators, several tiles per CTA
     (10, 192, 256, [64], 64, 3, 1),    # C4-sized Cout = 64 layer: many tiles per CTA
+    (2, 32, 64, [64], 128, 3, 2),      # stride 2: slabs of the four parity sub-images
+    (1, 64, 96, [128], 128, 7, 2),
+    (2, 40, 72, [64], 256, 5, 2),      # partial tiles, odd sub-image extents
 ]
 
 
@@ -87,7 +90,8 @@ HALO_CASES = [
 @pytest.mark.parametrize("backend", ["halo", "halo2"])
 def test_halo_conv_matches_oracle(backend, dtype, case):
     N, H, W, cins, cout, k, stride = case
-    if backend == "halo2" and (N * ((H + 15) // 16) * ((W + 15) // 16)) % 2:
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    if backend == "halo2" and (N * ((Ho + 15) // 16) * ((Wo + 15) // 16)) % 2:
         pytest.skip("the CTA-pair kernel needs an even number of 16x16 pixel blocks")
     g = torch.Generator().manual_seed(N * 1000 + H * 7 + W + cout + k * 13)
     xs = [torch.randn(N, c, H, W, generator=g) for c in cins]

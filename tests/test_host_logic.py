@@ -124,12 +124,28 @@ def test_halo_groups_reproduce_conv():
             wt[:, :3] = 0
             want = nhwc(F.conv2d(torch.cat((extra, x), 1).double(), engine.round_tf32(wt).double(), b.double(), padding=2))
         srcs = [engine.act_src(nhwc(x), 3)] + ([side] if side is not None else [])
-        groups, cols, pads = engine.make_groups(srcs, k, ch)
-        steps = [(si, 0, dx, t - pads[si], c0) for (si, c0, dx, nt) in groups for t in range(nt)]
+        groups, cols, info = engine.make_groups(srcs, k, ch)
+        steps = [(m // 4, 0, dx, t - info[m][0], c0) for (m, c0, dx, nt) in groups for t in range(nt)]
         assert len(steps) == len(cols)
         wp = engine.pack_weights(wt, cols, ch, _lib.CNM_TF32)
         got = emulate_steps([s_.buf for s_ in srcs], steps, wp, b, 1, ch, False)
         assert torch.allclose(got, want, atol=1e-9), k
+
+
+@pytest.mark.parametrize("k", [3, 5, 7])
+def test_halo_groups_stride2_reproduce_conv(k):
+    torch.manual_seed(k)
+    ch, cin, cout, N, H, W = 32, 64, 8, 1, 12, 14
+    x = torch.randn(N, cin, H, W)
+    w, b = torch.randn(cout, cin, k, k), torch.randn(cout)
+    groups, cols, info = engine.make_groups([engine.act_src(nhwc(x), 0)], k, ch, stride=2)
+    steps = [(m // 4, m % 4, dx, t - info[m][0], c0) for (m, c0, dx, nt) in groups for t in range(nt)]
+    assert len(steps) == len(cols) == k * k * (cin // ch)
+    assert all(info[m][1] == 16 + max(nt for (mm, _, _, nt) in groups if mm == m) - 1 for m in {g[0] for g in groups})
+    wp = engine.pack_weights(w, cols, ch, _lib.CNM_TF32)
+    got = emulate_steps([nhwc(x)], steps, wp, b, 2, ch, True)
+    want = nhwc(F.relu(F.conv2d(x.double(), engine.round_tf32(w).double(), b.double(), stride=2, padding=k // 2)))
+    assert torch.allclose(got, want, atol=1e-9)
 
 
 def test_fold_bn_matches_batchnorm():
