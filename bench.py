@@ -310,7 +310,7 @@ def main():
         tf32 = args.precision == "tf32"
         peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
         line["roofline"] = {
-            "kernel": "conv_tc_kernel + conv_halo_kernel (tcgen05 implicit GEMM, all %d conv launches of one step)"
+            "kernel": "conv_tc / conv_halo / conv_halo2 kernels (tcgen05 implicit GEMM, all %d conv launches of one step)"
                       % len(conv_rows),
             "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
             "traffic": traffic.get("conv_bytes_per_step") if not tf32 else None,

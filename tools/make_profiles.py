@@ -1,0 +1,99 @@
+"""Turns the raw ncu outputs in gpurun_out/ into the committed summaries under profiles/ (round tag as argv[1])."""
+import collections
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+# ---- launch list ----
+rows = list(csv.reader(open(os.path.join(G, "launches_step.csv"))))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+hdr, data = rows[hi], rows[hi + 1:]
+ki, vi, mi, idc, gi = (hdr.index(k) for k in ("Kernel Name", "Metric Value", "Metric Name", "ID", "Grid Size"))
+L = collections.OrderedDict()
+for r in data:
+    if len(r) <= vi:
+        continue
+    d = L.setdefault(r[idc], {"name": r[ki].split("(")[0].replace("void ", ""), "grid": r[gi]})
+    d[r[mi]] = float(r[vi].replace(",", ""))
+bench = {}
+bp = os.path.join(G, "bench.json")
+if os.path.exists(bp):
+    bench = json.load(open(bp))
+out = ["# %s launch list of one pipeline step" % tag, "",
+       "Command: `CNM_TUNE_CACHE=gpurun_out/tune_cache.json ncu --profile-from-start off --metrics "
+       "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv python tools/profile_step.py`",
+       "(one un-graphed C4 step, bf16 mode, B=5 x 2 source views, 256x192x64, after one warm-up step; conv kernel / tile choices",
+       "come from the autotuner cache written by the preceding `bench.py` run; the last `cost_volume_kernel<16,0>` launch is the C2",
+       "NCHW fp32 micro-benchmark).  Times are cold-cache and serialised by ncu: compare SHARES, not absolutes (the same step",
+       "replayed as a CUDA graph takes %.2f ms in bench.py)." % bench.get("ms_per_step", float("nan")), "",
+       "| # | kernel | grid | us | DRAM read+write MB |", "|---|---|---|---|---|"]
+tot = collections.OrderedDict()
+n = 0
+for d in L.values():
+    n += 1
+    t, b = d["gpu__time_duration.sum"] / 1e3, (d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]) / 1e6
+    out.append("| %d | `%s` | %s | %.1f | %.1f |" % (n, d["name"], d["grid"], t, b))
+    x = tot.setdefault(d["name"], [0, 0.0, 0.0])
+    x[0] += 1
+    x[1] += t
+    x[2] += b
+s = sum(v[1] for v in tot.values())
+out += ["", "## Shares", "", "| kernel | launches | us | share | DRAM MB |", "|---|---|---|---|---|"]
+for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+    out.append("| `%s` | %d | %.1f | %.1f %% | %.1f |" % (k, v[0], v[1], 100 * v[1] / s, v[2]))
+out.append("| total | %d | %.1f | 100 %% | %.1f |" % (n, s, sum(v[2] for v in tot.values())))
+cu = sum(v[1] for k, v in tot.items() if k.startswith("conv_"))
+cm = sum(v[2] for k, v in tot.items() if k.startswith("conv_"))
+out += ["", "Convolution kernels (`conv_tc_kernel`, `conv_halo_kernel`, `conv_halo2_kernel`): %.1f us = %.1f %% of the step, "
+        "%.1f MB of DRAM traffic per step." % (cu, 100 * cu / s, cm)]
+open(os.path.join(P, "%s_launches_step.md" % tag), "w").write("\n".join(out) + "\n")
+cv = [d for d in L.values() if d["name"].startswith("cost_volume_kernel<16, 0>")]
+json.dump({"source": "profiles/%s_launches_step.md (ncu dram__bytes_read.sum + dram__bytes_write.sum, one C4 step, bf16)" % tag,
+           "conv_bytes_per_step": cm * 1e6, "conv_launches": sum(v[0] for k, v in tot.items() if k.startswith("conv_")),
+           "cost_volume_c2_bytes": (cv[0]["dram__bytes_read.sum"] + cv[0]["dram__bytes_write.sum"]) if cv else None},
+          open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
+
+# ---- full-set captures ----
+PICKS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+         "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum",
+         "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed",
+         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+         "launch__registers_per_thread", "sm__cycles_elapsed.max", "sm__cycles_elapsed.max.per_second"]
+
+
+def dump(rep, outname, title, note):
+    rp = os.path.join(G, rep)
+    if not os.path.exists(rp):
+        return
+    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rws = list(csv.reader(raw.splitlines()))
+    h, u = rws[0], rws[1]
+    lines = ["# " + title, "", note, ""]
+    for r in rws[2:]:
+        lines += ["## `%s`  grid %s" % (r[h.index("Kernel Name")].split("(")[0], r[h.index("launch__grid_size")]), "",
+                  "| metric | value | unit |", "|---|---|---|"]
+        lines += ["| %s | %s | %s |" % (p, r[h.index(p)], u[h.index(p)]) for p in PICKS if p in h]
+        lines.append("")
+    open(os.path.join(P, outname), "w").write("\n".join(lines))
+
+
+dump("prof_halo.ncu-rep", "%s_conv_halo_ncu.md" % tag,
+     "%s ncu --set full: conv_halo_kernel / conv_halo2_kernel (row-halo tcgen05 conv, 1-SM and CTA-pair)" % tag,
+     "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k "
+     "regex:\"conv_halo2_kernel|conv_halo_kernel\" -c 6 python tools/profile_step.py` (bf16, C4 step, first six halo launches of "
+     "the DepthNet pass: conv1.0, conv1.3, conv2.0, conv3.0, ... in launch order; see the launch list for grids).")
+dump("prof_tc.ncu-rep", "%s_conv_tc_final_ncu.md" % tag,
+     "%s ncu --set full: conv_tc_kernel (per-tap tcgen05 conv) after the warp-uniform issue loop" % tag,
+     "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 "
+     "python tools/profile_step.py` (bf16, C4 step; the layers the autotuner leaves on the per-tap kernel: stride-2 and <= 48x64 layers).")
+print("ok", cu, cm, s)
