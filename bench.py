@@ -144,7 +144,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     fps = steps / dt
     sample = "%d steps of 1 frame tuple (of the batch of %d) at 256x192x64" % (steps, B_PER_GPU)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -152,7 +152,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def time_events(fn, reps, flush):
@@ -169,7 +169,29 @@ def time_events(fn, reps, flush):
     return statistics.mean(ts), ts
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Prints the one JSON line on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1: route fd 1 to stderr for the run, keep the real one."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -250,23 +272,30 @@ def main():
             total_ms += a.elapsed_time(b)
         barrier()
         wall = time.perf_counter() - wall0
-        # ---- end to end through the public wrapper: pinned host inputs in, host outputs back, every step ----
-        out_host = {k: torch.empty(st[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")}
-        for _ in range(2):
-            pipe.load_inputs(st, *host)
-            step()
-            for k in out_host:
-                out_host[k].copy_(st[k], non_blocking=True)
+        # ---- end to end through the public streaming API (CNMPipeline.infer_stream): every step uploads its inputs
+        # from pinned host memory and downloads depth / normal / prob to the host; uploads of step i+1 and
+        # downloads of step i-1 overlap the compute of step i on a copy stream ----
+        def gather(_st):
+            if world > 1:
+                for k in ("depth", "normal", "prob"):
+                    gathered[k] = gather_outputs(_st[k], B * world)
+
+        def host_batches(n):
+            for _ in range(n):
+                yield tuple(host)
+
+        for _ in pipe.infer_stream(host_batches(3), after_step=gather):
+            pass
         barrier()
         e0 = time.perf_counter()
-        for _ in range(args.steps):
-            pipe.load_inputs(st, *host)
-            step()
-            for k in out_host:
-                out_host[k].copy_(st[k], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        n_out = 0
+        for outs in pipe.infer_stream(host_batches(args.steps), after_step=gather):
+            n_out += 1
+        torch.cuda.synchronize()
+        assert n_out == args.steps
         barrier()
         e2e_s = time.perf_counter() - e0
+        out_host = {k: st[k] for k in ("depth", "normal", "prob")}
     t = torch.tensor([total_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -373,7 +402,7 @@ def main():
             line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d timed runs of 1 frame tuple at 256x192x64 (median), fp32 torch-CPU port "
                                               "of the reference pipeline" % len(ts)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

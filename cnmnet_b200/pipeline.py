@@ -101,6 +101,75 @@ class CNMPipeline:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         return self._prepare(B, V, H, W, dev)
 
+    def infer_stream(self, batches, after_step=None):
+        """Streams host batches through the pipeline with transfers overlapped with compute.
+
+        `batches` yields (ref_img [B,3,H,W], src_imgs [B,V,3,H,W], ref_cam [B,2,4,4], src_cams [B,V,2,4,4]) CPU tensors
+        (pinned memory gives asynchronous copies); yields (depth, normal, prob) as pinned CPU tensors, one tuple per
+        batch, in order (the tensors of a tuple are reused two batches later).  A copy stream uploads batch i+1 and
+        downloads batch i-1 while batch i computes: double-buffered device staging on both sides, CUDA events
+        between the streams, no host synchronisation except when a result is handed out.  `after_step(st)`, if
+        given, is enqueued on the compute stream after every graph replay (bench.py gathers outputs across ranks
+        there)."""
+        comp = torch.cuda.current_stream()
+        copy = torch.cuda.Stream()
+        st = stage_in = stage_out = host_out = None
+        ev = {}
+        pending = []
+
+        def new_event(name, i):
+            ev[(name, i)] = torch.cuda.Event()
+            return ev[(name, i)]
+
+        for i, (ref_img, src_imgs, ref_cam, src_cams) in enumerate(batches):
+            if st is None:
+                B, V = src_imgs.shape[:2]
+                H, W = ref_img.shape[2:]
+                dev = next(self.depth_network.parameters()).device
+                st = self._prepare(B, V, H, W, dev)
+                stage_in = [[torch.empty_like(st[k]) for k in ("ref", "src", "ref_cam", "src_cam")] for _ in range(2)]
+                stage_out = [[torch.empty_like(st[k]) for k in ("depth", "normal", "prob")] for _ in range(2)]
+                host_out = [[torch.empty(st[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
+                            for _ in range(2)]
+                if self.use_graph and st["graph"] is None:
+                    self.step(st)  # capture outside the pipelined region
+            b = i & 1
+            with torch.cuda.stream(copy):  # upload batch i (after compute consumed this staging slot two batches ago)
+                if ("in_free", i - 2) in ev:
+                    copy.wait_event(ev.pop(("in_free", i - 2)))
+                stage_in[b][0].copy_(ref_img, non_blocking=True)
+                stage_in[b][1].copy_(src_imgs.transpose(0, 1), non_blocking=True)
+                stage_in[b][2].copy_(ref_cam, non_blocking=True)
+                stage_in[b][3].copy_(src_cams.transpose(0, 1), non_blocking=True)
+                new_event("in", i).record(copy)
+            comp.wait_event(ev.pop(("in", i)))
+            for dst, src in zip(("ref", "src", "ref_cam", "src_cam"), stage_in[b]):
+                st[dst].copy_(src, non_blocking=True)
+            new_event("in_free", i).record(comp)
+            self.step(st)
+            if after_step is not None:
+                after_step(st)
+            if ("out_free", i - 2) in ev:
+                comp.wait_event(ev.pop(("out_free", i - 2)))
+            for dst, k in zip(stage_out[b], ("depth", "normal", "prob")):
+                dst.copy_(st[k], non_blocking=True)
+            new_event("out", i).record(comp)
+            with torch.cuda.stream(copy):  # download batch i while batch i+1 computes
+                copy.wait_event(ev.pop(("out", i)))
+                for dst, src in zip(host_out[b], stage_out[b]):
+                    dst.copy_(src, non_blocking=True)
+                new_event("out_free", i).record(copy)
+                done = torch.cuda.Event()
+                done.record(copy)
+            pending.append((done, host_out[b]))
+            if len(pending) > 1:  # hand out batch i-1 (its download overlapped the launch of batch i)
+                d, outs = pending.pop(0)
+                d.synchronize()
+                yield tuple(outs)
+        for d, outs in pending:
+            d.synchronize()
+            yield tuple(outs)
+
     def __call__(self, ref_img, src_imgs, ref_cam, src_cams):
         if ref_img.dim() != 4 or src_imgs.dim() != 5 or src_imgs.shape[0] != ref_img.shape[0]:
             raise ValueError("expected ref_img [B,3,H,W] and src_imgs [B,V,3,H,W]")

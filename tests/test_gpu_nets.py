@@ -153,6 +153,21 @@ def test_pipeline_with_halo_kernel_forced(monkeypatch):
     assert np.abs(outs["force"][1] - outs["off"][1]).mean() < 2e-3
 
 
+def test_infer_stream_matches_single_calls():
+    """The double-buffered streaming API returns, batch by batch, what the blocking call returns."""
+    B, H, W, V = 2, 32, 64, 2
+    dnet = cnmnet_b200.depthNet(idepth_scale=3.0).to(dev())
+    rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0).to(dev())
+    pipe = cnmnet_b200.CNMPipeline(dnet, rnet, use_graph=True)
+    batches = [tuple(t.pin_memory() for t in synth.frame_tuples(100 + i, B, H, W, V)) for i in range(5)]
+    want = [tuple(o.cpu().clone() for o in pipe(*[t.to(dev()) for t in b])) for b in batches]
+    got = [tuple(o.clone() for o in outs) for outs in pipe.infer_stream(iter(batches))]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert torch.equal(a, b)
+
+
 def test_weight_updates_are_picked_up():
     B, H, W = 1, 32, 32
     ref, srcs, ref_cam, src_cams = synth.frame_tuples(9, B, H, W, 2)
