@@ -127,7 +127,11 @@ class CNMPipeline:
                 H, W = ref_img.shape[2:]
                 dev = next(self.depth_network.parameters()).device
                 st = self._prepare(B, V, H, W, dev)
-                stage_in = [[torch.empty_like(st[k]) for k in ("ref", "src", "ref_cam", "src_cam")] for _ in range(2)]
+                # staging keeps the caller's [B,V,...] layout so the uploads are plain contiguous DMA transfers; the
+                # view-major transpose happens in the device-side copy into the static buffers
+                f32 = dict(dtype=torch.float32, device=dev)
+                stage_in = [[torch.empty((B, 3, H, W), **f32), torch.empty((B, V, 3, H, W), **f32),
+                             torch.empty((B, 2, 4, 4), **f32), torch.empty((B, V, 2, 4, 4), **f32)] for _ in range(2)]
                 stage_out = [[torch.empty_like(st[k]) for k in ("depth", "normal", "prob")] for _ in range(2)]
                 host_out = [[torch.empty(st[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
                             for _ in range(2)]
@@ -137,14 +141,14 @@ class CNMPipeline:
             with torch.cuda.stream(copy):  # upload batch i (after compute consumed this staging slot two batches ago)
                 if ("in_free", i - 2) in ev:
                     copy.wait_event(ev.pop(("in_free", i - 2)))
-                stage_in[b][0].copy_(ref_img, non_blocking=True)
-                stage_in[b][1].copy_(src_imgs.transpose(0, 1), non_blocking=True)
-                stage_in[b][2].copy_(ref_cam, non_blocking=True)
-                stage_in[b][3].copy_(src_cams.transpose(0, 1), non_blocking=True)
+                for dst, src in zip(stage_in[b], (ref_img, src_imgs, ref_cam, src_cams)):
+                    dst.copy_(src, non_blocking=True)
                 new_event("in", i).record(copy)
             comp.wait_event(ev.pop(("in", i)))
-            for dst, src in zip(("ref", "src", "ref_cam", "src_cam"), stage_in[b]):
-                st[dst].copy_(src, non_blocking=True)
+            st["ref"].copy_(stage_in[b][0], non_blocking=True)
+            st["src"].copy_(stage_in[b][1].transpose(0, 1), non_blocking=True)
+            st["ref_cam"].copy_(stage_in[b][2], non_blocking=True)
+            st["src_cam"].copy_(stage_in[b][3].transpose(0, 1), non_blocking=True)
             new_event("in_free", i).record(comp)
             self.step(st)
             if after_step is not None:
