@@ -112,7 +112,7 @@ class CNMPipeline:
         given, is enqueued on the compute stream after every graph replay (bench.py gathers outputs across ranks
         there)."""
         comp = torch.cuda.current_stream()
-        copy = torch.cuda.Stream()
+        up, down = torch.cuda.Stream(), torch.cuda.Stream()  # separate streams: an upload never queues behind a download
         st = stage_in = stage_out = host_out = None
         ev = {}
         pending = []
@@ -138,12 +138,12 @@ class CNMPipeline:
                 if self.use_graph and st["graph"] is None:
                     self.step(st)  # capture outside the pipelined region
             b = i & 1
-            with torch.cuda.stream(copy):  # upload batch i (after compute consumed this staging slot two batches ago)
+            with torch.cuda.stream(up):  # upload batch i (after compute consumed this staging slot two batches ago)
                 if ("in_free", i - 2) in ev:
-                    copy.wait_event(ev.pop(("in_free", i - 2)))
+                    up.wait_event(ev.pop(("in_free", i - 2)))
                 for dst, src in zip(stage_in[b], (ref_img, src_imgs, ref_cam, src_cams)):
                     dst.copy_(src, non_blocking=True)
-                new_event("in", i).record(copy)
+                new_event("in", i).record(up)
             comp.wait_event(ev.pop(("in", i)))
             st["ref"].copy_(stage_in[b][0], non_blocking=True)
             st["src"].copy_(stage_in[b][1].transpose(0, 1), non_blocking=True)
@@ -158,13 +158,13 @@ class CNMPipeline:
             for dst, k in zip(stage_out[b], ("depth", "normal", "prob")):
                 dst.copy_(st[k], non_blocking=True)
             new_event("out", i).record(comp)
-            with torch.cuda.stream(copy):  # download batch i while batch i+1 computes
-                copy.wait_event(ev.pop(("out", i)))
+            with torch.cuda.stream(down):  # download batch i while batch i+1 computes
+                down.wait_event(ev.pop(("out", i)))
                 for dst, src in zip(host_out[b], stage_out[b]):
                     dst.copy_(src, non_blocking=True)
-                new_event("out_free", i).record(copy)
+                new_event("out_free", i).record(down)
                 done = torch.cuda.Event()
-                done.record(copy)
+                done.record(down)
             pending.append((done, host_out[b]))
             if len(pending) > 1:  # hand out batch i-1 (its download overlapped the launch of batch i)
                 d, outs = pending.pop(0)
