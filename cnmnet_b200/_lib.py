@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcnmnet_b200.so")
 
-CNM_BF16, CNM_TF32 = 0, 1
+CNM_BF16, CNM_TF32, CNM_BF16X3 = 0, 1, 2
 VOLUME_NCHW_F32, VOLUME_ACT = 0, 1
 
 

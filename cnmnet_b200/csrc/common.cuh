@@ -35,8 +35,11 @@ inline int after_launch(const char* what) {
     if (!(cond)) return ::cnm::fail(code, __VA_ARGS__); \
   } while (0)
 
-inline int chunk_channels(int dtype) { return dtype == CNM_BF16 ? 64 : 32; }
-inline int elem_bytes(int dtype) { return dtype == CNM_BF16 ? 2 : 4; }
+// K-chunk in PHYSICAL channels (one 128-byte operand row) and bytes per physical element
+inline int chunk_channels(int dtype) { return dtype == CNM_TF32 ? 32 : 64; }
+inline int elem_bytes(int dtype) { return dtype == CNM_TF32 ? 4 : 2; }
+// physical channels per logical channel: CNM_BF16X3 stores every value as a (hi, lo) pair of bf16
+inline int phys_factor(int dtype) { return dtype == CNM_BF16X3 ? 2 : 1; }
 
 // ---- act element access (T = __nv_bfloat16 or float) ----
 template <typename T>
@@ -59,6 +62,50 @@ template <>
 __device__ __forceinline__ float from_f<float>(float v) { return round_tf32(v); }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Element of a CNM_BF16X3 ("split bf16") act tensor.  A value v is stored as hi = bf16(v), lo = bf16(v - hi) (16 mantissa
+// bits together).  Layout: logical channel c of a pixel lives at physical channel (c/64)*128 + c%64 (hi) and 64 further
+// (lo), i.e. every 64-channel logical chunk is a 128-byte hi row followed by a 128-byte lo row -- both are ordinary
+// bf16 tcgen05 operand rows, so a convolution runs as three bf16 passes (hi*Whi + lo*Whi + hi*Wlo) of the same kernels.
+struct bf16s {
+  __nv_bfloat16 v;
+};
+
+template <typename T>
+struct ActTraits {
+  static constexpr bool SPLIT = false;
+  static constexpr int CHUNK = 128 / sizeof(T);  // logical channels per K-chunk
+  __host__ __device__ static constexpr size_t phys(size_t c) { return c; }
+  __host__ __device__ static constexpr size_t pstride(size_t C) { return C; }
+};
+template <>
+struct ActTraits<bf16s> {
+  static constexpr bool SPLIT = true;
+  static constexpr int CHUNK = 64;
+  __host__ __device__ static constexpr size_t phys(size_t c) { return ((c >> 6) << 7) + (c & 63); }
+  __host__ __device__ static constexpr size_t pstride(size_t C) { return 2 * C; }
+};
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// scalar access to logical channel c of the pixel starting at `px`
+template <typename T>
+__device__ __forceinline__ float load_scalar(const T* px, size_t c) { return to_f<T>(px[c]); }
+template <>
+__device__ __forceinline__ float load_scalar<bf16s>(const bf16s* px, size_t c) {
+  const size_t q = ActTraits<bf16s>::phys(c);
+  return __bfloat162float(px[q].v) + __bfloat162float(px[q + 64].v);
+}
+template <typename T>
+__device__ __forceinline__ void store_scalar(T* px, size_t c, float v) { px[c] = from_f<T>(v); }
+template <>
+__device__ __forceinline__ void store_scalar<bf16s>(bf16s* px, size_t c, float v) {
+  const size_t q = ActTraits<bf16s>::phys(c);
+  split_bf16(v, px[q].v, px[q + 64].v);
+}
 
 // 16-byte vector of act elements <-> floats
 template <typename T>
@@ -94,6 +141,29 @@ struct Vec16<__nv_bfloat16> {
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// split bf16: p points at the hi vector, the lo vector is 64 physical channels further
+template <>
+struct Vec16<bf16s> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const bf16s* p, float* f) {
+    float lo[8];
+    Vec16<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(p), f);
+    Vec16<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(p) + 64, lo);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += lo[i];
+  }
+  __device__ static __forceinline__ void store(bf16s* p, const float* f) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hi[i] = __bfloat162float(__float2bfloat16_rn(f[i]));
+      lo[i] = f[i] - hi[i];
+    }
+    Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(p), hi);
+    Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(p) + 64, lo);
   }
 };
 

@@ -35,6 +35,7 @@ struct alignas(64) Halo2Params {
   int map_rows[H2_MAX_SRCS * 4];  // slab height (16 + vertical tap span), per map
   int relu;
   int c_out_offset;
+  int split;  // CNM_BF16X3: every 64-column chunk is stored as a hi row and a lo row (2 x 128 B per pixel)
 };
 
 // ---- 2-CTA PTX wrappers --------------------------------------------------------------------------------------
@@ -255,48 +256,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
         const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + half * BN);
 #pragma unroll 1
         for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
-          // one staging buffer (smem goes to deeper operand rings): the previous chunk's TMA store must have
-          // finished reading it; the epilogue runs under the next tile's main loop, so this wait is off the critical path
-          uint8_t* stg = base_ptr + off_out;
-          if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          epi_bar();
           uint32_t v[COLS_PER_CHUNK];
           tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
           if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
           tmem_ld_wait();
-          const float* bs = bias_s + ch * COLS_PER_CHUNK;
-          uint8_t* rowp = stg + row * 128;
+          for (int part = 0; part < (p.split ? 2 : 1); ++part) {
+          // one staging buffer (smem goes to deeper operand rings): the previous TMA store must have finished
+            // reading it; the epilogue runs under the next tile's main loop, so this wait is off the critical path
+            uint8_t* stg = base_ptr + off_out;
+            if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            epi_bar();
+            const float* bs = bias_s + ch * COLS_PER_CHUNK;
+            uint8_t* rowp = stg + row * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 o;
-            if (TF32) {
-              float f[4];
+            for (int j = 0; j < 8; ++j) {
+              uint4 o;
+              if (TF32) {
+                float f[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
-                if (p.relu) t = fmaxf(t, 0.0f);
-                f[e] = round_tf32(t);
-              }
-              o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-            } else {
-              uint32_t w[4];
+                for (int e = 0; e < 4; ++e) {
+                  float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
+                  if (p.relu) t = fmaxf(t, 0.0f);
+                  f[e] = round_tf32(t);
+                }
+                o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+              } else {
+                uint32_t w[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
-                float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
-                if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+                for (int e = 0; e < 4; ++e) {
+                  float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
+                  float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
+                  if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+                  if (part) {  // lo pass of the split-bf16 output: what the hi pass rounded away
+                  t0 -= __bfloat162float(__float2bfloat16_rn(t0));
+                  t1 -= __bfloat162float(__float2bfloat16_rn(t1));
+                }
                 __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
-                w[e] = *reinterpret_cast<uint32_t*>(&h);
+                  w[e] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
               }
-              o = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
             }
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          epi_bar();
-          if (storer) {
-            tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + nt * BN + ch * CHUNK_CH, x0, y0 + 8 * half, n0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            epi_bar();
+            if (storer) {
+              tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.split ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
+                                   x0, y0 + 8 * half, n0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
           }
         }
       }
@@ -386,6 +394,7 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
   p.num_steps = d->num_steps;
   p.relu = d->relu;
   p.c_out_offset = d->c_out_offset;
+  p.split = d->dtype == CNM_BF16X3;
   // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
   // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
   // lasts ntaps B tiles.
@@ -451,7 +460,7 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
   const int total = (m_tiles / 2) * p.tiles_n;  // super-tiles, one per CTA pair
   const int grid = 2 * (total < 74 ? total : 74);
   cudaStream_t s = (cudaStream_t)stream;
-  const bool tf32 = d->dtype == CNM_TF32;
+  const bool tf32 = d->dtype == CNM_TF32;  // CNM_BF16 and CNM_BF16X3 both run the kind::f16 kernels
   if (BN == 256) return tf32 ? launch_halo2<256, true>(p, grid, smem, s) : launch_halo2<256, false>(p, grid, smem, s);
   if (BN == 128) return tf32 ? launch_halo2<128, true>(p, grid, smem, s) : launch_halo2<128, false>(p, grid, smem, s);
   return tf32 ? launch_halo2<64, true>(p, grid, smem, s) : launch_halo2<64, false>(p, grid, smem, s);

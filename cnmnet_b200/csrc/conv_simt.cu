@@ -12,7 +12,7 @@ struct SimtSrc {
 };
 struct SimtParams {
   SimtSrc srcs[4];
-  int N, Ho, Wo, Cout, c_out_total, c_out_offset, stride, relu, num_steps;
+  int N, Ho, Wo, Cout, c_out_total, c_out_offset, stride, relu, num_steps, split;
 };
 
 constexpr int SM_TM = 64, SM_TN = 64;
@@ -74,7 +74,15 @@ __global__ void __launch_bounds__(256)
       if (co >= p.Cout) continue;
       float v = acc[i][j] + (bias ? __ldg(bias + co) : 0.0f);
       if (p.relu) v = fmaxf(v, 0.0f);
-      out[m * p.c_out_total + p.c_out_offset + co] = from_f<T>(v);
+      if (p.split) {  // CNM_BF16X3 output: hi row, lo row 64 physical channels further
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        T* o = out + m * p.c_out_total + p.c_out_offset + ActTraits<bf16s>::phys(co);
+        o[0] = from_f<T>(__bfloat162float(hi));
+        o[64] = from_f<T>(__bfloat162float(lo));
+      } else {
+        out[m * p.c_out_total + p.c_out_offset + co] = from_f<T>(v);
+      }
     }
   }
 }
@@ -82,14 +90,15 @@ __global__ void __launch_bounds__(256)
 int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* srcs, const void* steps, const void* wp,
                     const void* out) {
   CNM_REQUIRE(d && srcs && steps && wp && out, CNM_ERR_INVALID_ARGUMENT, "%s: null pointer", fn);
-  CNM_REQUIRE(d->dtype == CNM_BF16 || d->dtype == CNM_TF32, CNM_ERR_INVALID_ARGUMENT, "%s: dtype %d", fn, d->dtype);
+  CNM_REQUIRE(d->dtype == CNM_BF16 || d->dtype == CNM_TF32 || d->dtype == CNM_BF16X3, CNM_ERR_INVALID_ARGUMENT,
+              "%s: dtype %d", fn, d->dtype);
   CNM_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->Cout > 0, CNM_ERR_INVALID_ARGUMENT, "%s: bad output shape", fn);
   CNM_REQUIRE(d->stride == 1 || d->stride == 2, CNM_ERR_UNSUPPORTED_SHAPE, "%s: stride %d", fn, d->stride);
   CNM_REQUIRE(d->num_srcs >= 1 && d->num_srcs <= 3, CNM_ERR_UNSUPPORTED_SHAPE, "%s: num_srcs %d (max 3)", fn, d->num_srcs);
   CNM_REQUIRE(d->num_steps >= 1, CNM_ERR_INVALID_ARGUMENT, "%s: num_steps %d", fn, d->num_steps);
   const int ch = chunk_channels(d->dtype);
   CNM_REQUIRE(d->Cout % ch == 0 && d->c_out_total % ch == 0 && d->c_out_offset % ch == 0 &&
-                  d->c_out_offset + d->Cout <= d->c_out_total,
+                  d->c_out_offset + phys_factor(d->dtype) * d->Cout <= d->c_out_total,
               CNM_ERR_UNSUPPORTED_SHAPE, "%s: Cout=%d / c_out_total=%d / offset=%d must be chunk (%d) aligned", fn,
               d->Cout, d->c_out_total, d->c_out_offset, ch);
   for (int i = 0; i < d->num_srcs; ++i) {
@@ -121,9 +130,10 @@ extern "C" int cnm_conv2d_simt(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;
   p.c_out_total = d->c_out_total; p.c_out_offset = d->c_out_offset;
   p.stride = d->stride; p.relu = d->relu; p.num_steps = d->num_steps;
+  p.split = d->dtype == CNM_BF16X3;
   const size_t M = (size_t)d->N * d->Ho * d->Wo;
   dim3 grid((unsigned)((M + SM_TM - 1) / SM_TM), (d->Cout + SM_TN - 1) / SM_TN);
-  if (d->dtype == CNM_BF16)
+  if (d->dtype != CNM_TF32)
     conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p, steps, (const __nv_bfloat16*)wp, bias,
                                                                            (__nv_bfloat16*)out);
   else

@@ -40,6 +40,7 @@ struct alignas(64) TcParams {
   int TW, TH, NB;
   int relu;
   int c_out_offset;
+  int split;  // CNM_BF16X3: every 64-column chunk is stored as a hi row and a lo row (2 x 128 B per pixel)
 };
 
 template <int BN, int STAGES, bool TF32>
@@ -191,51 +192,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int ch = 0; ch < NUM_CHUNKS; ++ch, ++chunk_counter) {
-        const uint32_t buf = chunk_counter & 1;
-        uint8_t* stg = base_ptr + L::OFF_OUT + buf * TC_A_BYTES;
-        // the TMA store that last read this staging buffer (two chunks ago) must have finished reading
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        epi_bar();
+      for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
         uint32_t v[COLS_PER_CHUNK];
         tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
         if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
         tmem_ld_wait();
-        const float* bs = bias_s + ch * COLS_PER_CHUNK;
-        uint8_t* rowp = stg + row * 128;
+        for (int part = 0; part < (p.split ? 2 : 1); ++part) {
+          const uint32_t buf = chunk_counter & 1;
+          uint8_t* stg = base_ptr + L::OFF_OUT + buf * TC_A_BYTES;
+          // the TMA store that last read this staging buffer (two stores ago) must have finished reading
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar();
+          const float* bs = bias_s + ch * COLS_PER_CHUNK;
+          uint8_t* rowp = stg + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // 8 x 16 B per output row, 128B-swizzled like the TMA box
-          uint4 o;
-          if (TF32) {
-            float f[4];
+          for (int j = 0; j < 8; ++j) {  // 8 x 16 B per output row, 128B-swizzled like the TMA box
+            uint4 o;
+            if (TF32) {
+              float f[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
-              if (p.relu) t = fmaxf(t, 0.0f);
-              uint32_t r;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t));  // store tf32-rounded activations
-              f[e] = __uint_as_float(r);
+              for (int e = 0; e < 4; ++e) {
+                float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
+                if (p.relu) t = fmaxf(t, 0.0f);
+                uint32_t r;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t));  // store tf32-rounded activations
+                f[e] = __uint_as_float(r);
+              }
+              o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+            } else {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
+                float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
+                if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
+                if (part) {  // lo pass of the split-bf16 output: what the hi pass rounded away
+                  t0 -= __bfloat162float(__float2bfloat16_rn(t0));
+                  t1 -= __bfloat162float(__float2bfloat16_rn(t1));
+                }
+                __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              o = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-          } else {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
-              float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
-              if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
-              __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
-              w[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            o = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
           }
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
-        epi_bar();
-        if (leader) {
-          tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + nt * BN + ch * CHUNK_CH, x0, y0, n0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
+          epi_bar();
+          if (leader) {
+            tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.split ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
+                                 x0, y0, n0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++chunk_counter;
         }
       }
       tc_fence_before();
@@ -279,7 +288,7 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const uin
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = enc(map, dtype == CNM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+  CUresult r = enc(map, dtype == CNM_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                    (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CNM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -351,6 +360,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.num_steps = d->num_steps;
   p.relu = d->relu;
   p.c_out_offset = d->c_out_offset;
+  p.split = d->dtype == CNM_BF16X3;
 
   const uint32_t box[4] = {(uint32_t)ch, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.NB};
   for (int i = 0; i < d->num_srcs; ++i) {
@@ -392,7 +402,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   const int total = m_tiles * p.tiles_n;
   const int grid = total < 148 ? total : 148;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool tf32 = d->dtype == CNM_TF32;
+  const bool tf32 = d->dtype == CNM_TF32;  // CNM_BF16 and CNM_BF16X3 both run the kind::f16 kernels
   if (BN == 256) return tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
   if (BN == 128) return tf32 ? launch_tc<128, 6, true>(p, grid, s) : launch_tc<128, 6, false>(p, grid, s);
   return tf32 ? launch_tc<64, 8, true>(p, grid, s) : launch_tc<64, 8, false>(p, grid, s);

@@ -27,7 +27,7 @@ __global__ void nchw_to_act_kernel(const float* __restrict__ src, T* __restrict_
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const size_t p = p0 + j;
     const int c = c0 + threadIdx.x;
-    if (p < HW && c < C) dst[((size_t)n * HW + p) * ct + co + c] = from_f<T>(tile[threadIdx.x][j]);
+    if (p < HW && c < C) store_scalar<T>(dst + ((size_t)n * HW + p) * ActTraits<T>::pstride(ct), co + c, tile[threadIdx.x][j]);
   }
 }
 
@@ -42,7 +42,7 @@ __global__ void act_to_nchw_kernel(const T* __restrict__ src, float* __restrict_
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const size_t p = p0 + j;
     const int c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (p < HW && c < C) ? to_f<T>(src[((size_t)n * HW + p) * ct + co + c]) : 0.0f;
+    tile[j][threadIdx.x] = (p < HW && c < C) ? load_scalar<T>(src + ((size_t)n * HW + p) * ActTraits<T>::pstride(ct), co + c) : 0.0f;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -56,14 +56,14 @@ __global__ void act_to_nchw_kernel(const T* __restrict__ src, float* __restrict_
 // one thread per pixel writes one 128-byte chunk row (64 bf16 or 32 fp32 channels)
 template <typename T>
 __device__ __forceinline__ void store_chunk(T* dst, const float* v) {
-  constexpr int CH = 128 / sizeof(T);
+  constexpr int CH = ActTraits<T>::CHUNK;
 #pragma unroll
-  for (int i = 0; i < CH; i += Vec16<T>::N) Vec16<T>::store(dst + i, v + i);
+  for (int i = 0; i < CH; i += Vec16<T>::N) Vec16<T>::store(dst + i, v + i);  // split bf16: + the lo row 64 further
 }
 
 template <typename T, int KW, int CX>
 __global__ void pack_row_taps_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int H, int W) {
-  constexpr int CH = 128 / sizeof(T);
+  constexpr int CH = ActTraits<T>::CHUNK;
   static_assert(KW * CX <= CH, "taps must fit one chunk");
   const size_t HW = (size_t)H * W;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,12 +82,12 @@ __global__ void pack_row_taps_kernel(const float* __restrict__ x, T* __restrict_
 #pragma unroll
     for (int c = 0; c < CX; ++c) v[s * CX + c] = ok ? __ldg(row + (size_t)c * HW + xs) : 0.0f;
   }
-  store_chunk<T>(dst + i * CH, v);
+  store_chunk<T>(dst + i * ActTraits<T>::pstride(CH), v);
 }
 
 template <typename T>
 __global__ void pack_disp_taps_kernel(const float* __restrict__ disp, T* __restrict__ dst, int N, int h, int w) {
-  constexpr int CH = 128 / sizeof(T);
+  constexpr int CH = ActTraits<T>::CHUNK;
   const int H = 2 * h, W = 2 * w;
   const size_t HW = (size_t)H * W;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,7 +106,7 @@ __global__ void pack_disp_taps_kernel(const float* __restrict__ disp, T* __restr
       if (yy >= 0 && yy < H && xx >= 0 && xx < W)
         v[3 * r + s] = __ldg(disp + ((size_t)n * h + (yy >> 1)) * w + (xx >> 1));  // nearest x2
     }
-  store_chunk<T>(dst + i * CH, v);
+  store_chunk<T>(dst + i * ActTraits<T>::pstride(CH), v);
 }
 
 // ---- refine-input aggregation ------------------------------------------------------------------
@@ -121,7 +121,7 @@ __device__ __forceinline__ float group_mean_at(const float* __restrict__ idepth,
 template <typename T>
 __global__ void refine_taps_kernel(const float* __restrict__ idepth, T* __restrict__ taps, float* __restrict__ id_out,
                                    int B, int H, int W, int group) {
-  constexpr int CH = 128 / sizeof(T);
+  constexpr int CH = ActTraits<T>::CHUNK;
   const size_t HW = (size_t)H * W, BHW = (size_t)B * HW;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= BHW) return;
@@ -145,7 +145,7 @@ __global__ void refine_taps_kernel(const float* __restrict__ idepth, T* __restri
         if (r == 1 && s == 1 && id_out) { id_out[off] = a; id_out[BHW + off] = c; }
       }
     }
-  store_chunk<T>(taps + i * CH, v);
+  store_chunk<T>(taps + i * ActTraits<T>::pstride(CH), v);
 }
 
 // sum_act = mean_0(iconv) + mean_1(iconv) on act tensors [V*B,H,W,64]; one 16-byte vector per thread
@@ -157,10 +157,11 @@ __global__ void refine_sum_act_kernel(const T* __restrict__ iconv, T* __restrict
   float m[2][VN];
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    Vec16<T>::load(iconv + (size_t)g * per_view + i, m[g]);
+    // one pixel = one 64-channel logical chunk, so the flat logical index maps to the physical one like a channel
+    Vec16<T>::load(iconv + ActTraits<T>::phys((size_t)g * per_view + i), m[g]);
     for (int k = 1; k < group; ++k) {
       float t[VN];
-      Vec16<T>::load(iconv + (size_t)(g + 2 * k) * per_view + i, t);
+      Vec16<T>::load(iconv + ActTraits<T>::phys((size_t)(g + 2 * k) * per_view + i), t);
 #pragma unroll
       for (int j = 0; j < VN; ++j) m[g][j] += t[j];
     }
@@ -170,7 +171,7 @@ __global__ void refine_sum_act_kernel(const T* __restrict__ iconv, T* __restrict
   }
 #pragma unroll
   for (int j = 0; j < VN; ++j) m[0][j] += m[1][j];
-  Vec16<T>::store(out + i, m[0]);
+  Vec16<T>::store(out + ActTraits<T>::phys(i), m[0]);
 }
 
 // public-boundary variant: iconv NCHW fp32 [2,B,64,H,W] -> sum act [B,H,W,64]
@@ -190,7 +191,7 @@ __global__ void refine_sum_nchw_kernel(const float* __restrict__ iconv, T* __res
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const size_t p = p0 + j;
-    if (p < HW) out[((size_t)b * HW + p) * 64 + c0 + threadIdx.x] = from_f<T>(tile[threadIdx.x][j]);
+    if (p < HW) store_scalar<T>(out + ((size_t)b * HW + p) * ActTraits<T>::pstride(64), c0 + threadIdx.x, tile[threadIdx.x][j]);
   }
 }
 
@@ -210,16 +211,17 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ s
   const int y = (int)(t % h);
   const int n = (int)(t / h);
   const int xm = max(x - 1, 0), xp = min(x + 1, w - 1), ym = max(y - 1, 0), yp = min(y + 1, h - 1);
-  const T* base = src + (size_t)n * h * w * C + c;
+  const size_t PC = ActTraits<T>::pstride(C), pc = ActTraits<T>::phys(c);
+  const T* base = src + (size_t)n * h * w * PC + pc;
   float v[3][3][VN];
   const int ys[3] = {ym, y, yp}, xs[3] = {xm, x, xp};
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int b = 0; b < 3; ++b) Vec16<T>::load(base + ((size_t)ys[a] * w + xs[b]) * C, v[a][b]);
+    for (int b = 0; b < 3; ++b) Vec16<T>::load(base + ((size_t)ys[a] * w + xs[b]) * PC, v[a][b]);
   // output (2y+dy, 2x+dx): source coordinate y - 0.25 (dy=0) or y + 0.25 (dy=1): rows (y-1,y) w (.25,.75) or (y,y+1) w (.75,.25)
   const int W2 = 2 * w;
-  T* out = dst + (((size_t)n * 2 * h + 2 * y) * W2 + 2 * x) * C + c;
+  T* out = dst + (((size_t)n * 2 * h + 2 * y) * W2 + 2 * x) * PC + pc;
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ s
         const float a00 = v[dy][dx][j], a01 = v[dy][dx + 1][j], a10 = v[dy + 1][dx][j], a11 = v[dy + 1][dx + 1][j];
         o[j] = a00 * ((1.f - fx) * (1.f - fy)) + a01 * (fx * (1.f - fy)) + a10 * ((1.f - fx) * fy) + a11 * (fx * fy);
       }
-      Vec16<T>::store(out + ((size_t)dy * W2 + dx) * C, o);
+      Vec16<T>::store(out + ((size_t)dy * W2 + dx) * PC, o);
     }
 }
 
@@ -249,14 +251,16 @@ __global__ void __launch_bounds__(256, 2)
   T* tile = reinterpret_cast<T*>(hsm + (size_t)9 * C * 4);   // [(TR+2)][34][C]
   const int n = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * TR;
   for (int i = threadIdx.x; i < 9 * C; i += 256) ws[i] = __ldg(w + i);
-  const int cv = C / VN, npix = (TR + 2) * 34;
+  const int PC = (int)ActTraits<T>::pstride(C);  // physical channels per pixel (raw 16-byte vectors are staged as stored)
+  constexpr int RAWN = 16 / sizeof(T);
+  const int cv = PC / RAWN, npix = (TR + 2) * 34;
   for (int i = threadIdx.x; i < npix * cv; i += 256) {
-    const int pi = i / cv, c = (i % cv) * VN;
+    const int pi = i / cv, c = (i % cv) * RAWN;
     const int yy = y0 + pi / 34 - 1, xx = x0 + pi % 34 - 1;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-      v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * C + c));
-    *reinterpret_cast<uint4*>(tile + (size_t)pi * C + c) = v;
+      v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * PC + c));
+    *reinterpret_cast<uint4*>(tile + (size_t)pi * PC + c) = v;
   }
   __syncthreads();
   const int sub = threadIdx.x % LPP, grp = threadIdx.x / LPP;
@@ -275,11 +279,11 @@ __global__ void __launch_bounds__(256, 2)
     const int ty = pi / 32, tx = pi % 32;
     float acc = 0.0f;
     if (wreg) {
-      const T* tp = tile + ((size_t)ty * 34 + tx) * C + sub * VN;
+      const T* tp = tile + ((size_t)ty * 34 + tx) * PC + ActTraits<T>::phys(sub * VN);
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         float v[VN];
-        Vec16<T>::load(tp + ((t / 3) * 34 + t % 3) * C, v);
+        Vec16<T>::load(tp + ((t / 3) * 34 + t % 3) * PC, v);
 #pragma unroll
         for (int j = 0; j < VN; ++j) acc = fmaf(v[j], wr[t][j], acc);
       }
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           float v[VN];
-          Vec16<T>::load(tile + ((size_t)(ty + t / 3) * 34 + tx + t % 3) * C + c, v);
+          Vec16<T>::load(tile + ((size_t)(ty + t / 3) * 34 + tx + t % 3) * PC + ActTraits<T>::phys(c), v);
           const float* wp = ws + t * C + c;
 #pragma unroll
           for (int j = 0; j < VN; j += 4) {
@@ -332,9 +336,9 @@ static int launch_head(const T* x, const float* w, float bias, float scale, floa
   const int lanes = C / Vec16<T>::N;  // one 16-byte vector per lane
   const int lpp = lanes >= 32 ? 32 : (lanes >= 16 ? 16 : 8);
   // rows per CTA: keep the staged halo tile around 100 KB (two CTAs per SM)
-  int TR = (int)(100 * 1024 / ((size_t)34 * C * sizeof(T))) - 2;
+  int TR = (int)(100 * 1024 / ((size_t)34 * ActTraits<T>::pstride(C) * sizeof(T))) - 2;
   TR = TR >= 8 ? 8 : (TR >= 4 ? 4 : (TR >= 2 ? 2 : 1));
-  const size_t smem = (size_t)9 * C * 4 + (size_t)(TR + 2) * 34 * C * sizeof(T);
+  const size_t smem = (size_t)9 * C * 4 + (size_t)(TR + 2) * 34 * ActTraits<T>::pstride(C) * sizeof(T);
   dim3 grid((W + 31) / 32, (H + TR - 1) / TR, N);
   if (N > 65535 || grid.y > 65535) return fail(CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head3x3: grid too large");
   if (lpp == 32) return launch_head_lpp<T, 32>(x, w, bias, scale, out, logits, H, W, C, TR, grid, smem, s);
@@ -349,6 +353,7 @@ using namespace cnm;
 #define DISPATCH_DTYPE(dtype, ...)                                   \
   if ((dtype) == CNM_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
   else if ((dtype) == CNM_TF32) { using T = float; __VA_ARGS__; }    \
+  else if ((dtype) == CNM_BF16X3) { using T = bf16s; __VA_ARGS__; }  \
   else return fail(CNM_ERR_INVALID_ARGUMENT, "%s: dtype %d", __func__, (int)(dtype));
 
 extern "C" int cnm_nchw_to_act(const float* src, void* dst, int N, int C, int H, int W, int c_dst_total,

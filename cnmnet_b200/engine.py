@@ -14,18 +14,29 @@ from collections import namedtuple
 import torch
 
 from . import _lib
-from ._lib import CNM_BF16, CNM_TF32
+from ._lib import CNM_BF16, CNM_BF16X3, CNM_TF32
 
 BN_EPS = 1e-5
 # which stride-1 layers use the row-halo kernel: "auto" (enough tiles for a wave), "force" (every eligible layer,
 # used by tests), "off" (per-tap kernel everywhere)
 HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
-TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32}
+TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32, CNM_BF16X3: torch.bfloat16}
 
 
 def chunk_channels(dtype):
-    return 64 if dtype == CNM_BF16 else 32
+    """Channels per K-chunk (one 128-byte operand row)."""
+    return 32 if dtype == CNM_TF32 else 64
+
+
+def phys_factor(dtype):
+    """Physical channels per logical channel: CNM_BF16X3 stores every value as a (hi, lo) bf16 pair, laid out as a
+    128-byte hi row followed by a 128-byte lo row per 64-channel logical chunk (see csrc/common.cuh: bf16s)."""
+    return 2 if dtype == CNM_BF16X3 else 1
+
+
+# (activation part, weight part) passes of one logical K-chunk: x*w ~ hi*Whi + lo*Whi + hi*Wlo for split bf16
+SPLIT_PASSES = (("hi", "hi"), ("lo", "hi"), ("hi", "lo"))
 
 
 def parse_dtype(d):
@@ -33,7 +44,9 @@ def parse_dtype(d):
         return CNM_BF16
     if d in (CNM_TF32, "tf32", torch.float32):
         return CNM_TF32
-    raise ValueError("precision must be 'bf16' or 'tf32', got %r" % (d,))
+    if d in (CNM_BF16X3, "bf16x3"):
+        return CNM_BF16X3
+    raise ValueError("precision must be 'bf16', 'tf32' or 'bf16x3', got %r" % (d,))
 
 
 def round_tf32(t):
@@ -59,12 +72,22 @@ def fold_bn(sd, prefix, ci):
 Src = namedtuple("Src", "buf kind wch C coff nreal")
 
 
-def act_src(buf, wch, C=None, coff=0):
-    return Src(buf, "act", wch, buf.shape[3] if C is None else C, coff, 0)
+def act_src(buf, wch, C=None, coff=0, phys=1):
+    """Full act tensor as an operand source; C / coff are LOGICAL channels (`phys` physical channels each)."""
+    return Src(buf, "act", wch, buf.shape[3] // phys if C is None else C, coff, 0)
 
 
-def make_steps(srcs, k, stride, ch):
-    """-> (steps [(src, sub, dx, dy, c0)], cols [packing recipe per step]).  See include/cnmnet_b200.h."""
+def _chunk_passes(split):
+    return SPLIT_PASSES if split else ((None, None),)
+
+
+def _pc0(c_logical, apart, split):
+    """Physical first channel of the logical chunk starting at c_logical (hi row, or lo row 64 further)."""
+    return (2 * c_logical + (64 if apart == "lo" else 0)) if split else c_logical
+
+
+def make_steps(srcs, k, stride, ch, split=False):
+    """-> (steps [(src, sub, dx, dy, c0 physical)], cols [packing recipe per step]).  See include/cnmnet_b200.h."""
     pad = (k - 1) // 2
     steps, cols = [], []
     for si, s in enumerate(srcs):
@@ -80,24 +103,27 @@ def make_steps(srcs, k, stride, ch):
                         dy, dx = (ty - py) // 2, (tx - px) // 2
                         sub = py * 2 + px
                     for c0 in range(0, s.C, ch):
-                        steps.append((si, sub, dx, dy, s.coff + c0))
-                        cols.append(("act", s.wch + c0, r, t))
+                        for ap, wp_ in _chunk_passes(split):
+                            steps.append((si, sub, dx, dy, _pc0(s.coff + c0, ap, split)))
+                            cols.append(("act", s.wch + c0, r, t, wp_))
         elif s.kind == "rowtaps":
             assert stride == 1 and k * s.nreal <= ch
             for r in range(k):
-                steps.append((si, 0, 0, r - pad, 0))
-                cols.append(("rowtaps", s.wch, s.nreal, r))
+                for ap, wp_ in _chunk_passes(split):
+                    steps.append((si, 0, 0, r - pad, _pc0(0, ap, split)))
+                    cols.append(("rowtaps", s.wch, s.nreal, r, wp_))
         elif s.kind == "taps3x3":
             assert stride == 1 and k == 3 and 9 * s.nreal <= ch
-            steps.append((si, 0, 0, 0, 0))
-            cols.append(("taps3x3", s.wch, s.nreal, 0))
+            for ap, wp_ in _chunk_passes(split):
+                steps.append((si, 0, 0, 0, _pc0(0, ap, split)))
+                cols.append(("taps3x3", s.wch, s.nreal, 0, wp_))
         else:
             raise ValueError(s.kind)
     return steps, cols
 
 
-def make_groups(srcs, k, ch, stride=1):
-    """Row-halo K loop (csrc/conv_halo.cu): -> (groups [(map, c0, dx, ntaps)], cols, map_info [12][2]).
+def make_groups(srcs, k, ch, stride=1, split=False):
+    """Row-halo K loop (csrc/conv_halo.cu): -> (groups [(map, c0 physical, dx, ntaps)], cols, map_info [12][2]).
     One group = one slab load serving `ntaps` vertical taps; the weight steps (cols) follow group order.
     map = src*4 + sub; map_info[map] = (rows of the slab above the tile, slab rows)."""
     pad = (k - 1) // 2
@@ -108,8 +134,9 @@ def make_groups(srcs, k, ch, stride=1):
             info[si * 4] = [pad, 16 + 2 * pad]
             for c0 in range(0, s.C, ch):
                 for t in range(k):
-                    groups.append((si * 4, s.coff + c0, t - pad, k))
-                    cols += [("act", s.wch + c0, r, t) for r in range(k)]
+                    for ap, wp_ in _chunk_passes(split):
+                        groups.append((si * 4, _pc0(s.coff + c0, ap, split), t - pad, k))
+                        cols += [("act", s.wch + c0, r, t, wp_) for r in range(k)]
         elif s.kind == "act":  # stride 2: taps grouped by (column tap, row parity) on the parity sub-images
             for c0 in range(0, s.C, ch):
                 for t in range(k):
@@ -123,41 +150,50 @@ def make_groups(srcs, k, ch, stride=1):
                         assert qs == list(range(qs[0], qs[0] + len(qs)))
                         m = si * 4 + py * 2 + px
                         info[m] = [-qs[0], 16 + qs[-1] - qs[0]]
-                        groups.append((m, s.coff + c0, qx, len(rs)))
-                        cols += [("act", s.wch + c0, r, t) for r in rs]
+                        for ap, wp_ in _chunk_passes(split):
+                            groups.append((m, _pc0(s.coff + c0, ap, split), qx, len(rs)))
+                            cols += [("act", s.wch + c0, r, t, wp_) for r in rs]
         elif s.kind == "rowtaps":
             assert stride == 1 and k * s.nreal <= ch
             info[si * 4] = [pad, 16 + 2 * pad]
-            groups.append((si * 4, 0, 0, k))
-            cols += [("rowtaps", s.wch, s.nreal, r) for r in range(k)]
+            for ap, wp_ in _chunk_passes(split):
+                groups.append((si * 4, _pc0(0, ap, split), 0, k))
+                cols += [("rowtaps", s.wch, s.nreal, r, wp_) for r in range(k)]
         elif s.kind == "taps3x3":
             assert stride == 1 and k == 3 and 9 * s.nreal <= ch
             info[si * 4] = [0, 16]
-            groups.append((si * 4, 0, 0, 1))
-            cols.append(("taps3x3", s.wch, s.nreal, 0))
+            for ap, wp_ in _chunk_passes(split):
+                groups.append((si * 4, _pc0(0, ap, split), 0, 1))
+                cols.append(("taps3x3", s.wch, s.nreal, 0, wp_))
         else:
             raise ValueError(s.kind)
     return groups, cols, info
 
 
 def pack_weights(wf, cols, ch, dtype):
-    """Folded weights [Cout, Cin, k, k] -> K-major operand [Cout, len(cols)*ch] in the act dtype."""
+    """Folded weights [Cout, Cin, k, k] -> K-major operand [Cout, len(cols)*ch] in the act dtype.  For CNM_BF16X3 a
+    column block holds either Whi = bf16(w) or Wlo = bf16(w - Whi), as its recipe says."""
     cout, _, k, _ = wf.shape
+    parts = {None: wf, "hi": wf, "lo": wf}
+    if dtype == CNM_BF16X3:
+        whi = wf.to(torch.bfloat16).float()
+        parts = {"hi": whi, "lo": wf - whi}
     wp = torch.zeros((cout, len(cols) * ch), dtype=torch.float32, device=wf.device)
     for i, col in enumerate(cols):
         base = i * ch
+        w = parts[col[4] if len(col) > 4 else None]
         if col[0] == "act":
-            _, c, r, t = col
-            wp[:, base:base + ch] = wf[:, c:c + ch, r, t]
+            _, c, r, t = col[:4]
+            wp[:, base:base + ch] = w[:, c:c + ch, r, t]
         elif col[0] == "rowtaps":
-            _, wch, n, r = col
-            wp[:, base:base + k * n] = wf[:, wch:wch + n, r, :].permute(0, 2, 1).reshape(cout, k * n)
+            _, wch, n, r = col[:4]
+            wp[:, base:base + k * n] = w[:, wch:wch + n, r, :].permute(0, 2, 1).reshape(cout, k * n)
         else:
-            _, wch, n, _ = col
-            wp[:, base:base + 9 * n] = wf[:, wch:wch + n].reshape(cout, 9 * n)
-    if dtype == CNM_BF16:
-        return wp.to(torch.bfloat16).contiguous()
-    return round_tf32(wp)
+            _, wch, n, _ = col[:4]
+            wp[:, base:base + 9 * n] = w[:, wch:wch + n].reshape(cout, 9 * n)
+    if dtype == CNM_TF32:
+        return round_tf32(wp)
+    return wp.to(torch.bfloat16).contiguous()
 
 
 _TUNE_CACHE = {}
@@ -193,9 +229,11 @@ class ConvOp:
                  backend="tc"):
         self.name, self.k, self.stride, self.dtype = name, k, stride, dtype
         ch = chunk_channels(dtype)
+        split = dtype == CNM_BF16X3
+        pf = phys_factor(dtype)
         self.srcs = srcs
         self.variants = {}
-        steps, cols = make_steps(srcs, k, stride, ch)
+        steps, cols = make_steps(srcs, k, stride, ch, split)
         st = torch.zeros((len(steps), 8), dtype=torch.int32)
         st[:, :5] = torch.tensor(steps, dtype=torch.int32)
         self.variants["tc"] = {"cols": cols, "steps_dev": st.to(device)}
@@ -203,7 +241,7 @@ class ConvOp:
         halo_ok = Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2") and \
             (stride == 1 or all(s.kind == "act" for s in srcs))
         if halo_ok:
-            groups, gcols, info = make_groups(srcs, k, ch, stride)
+            groups, gcols, info = make_groups(srcs, k, ch, stride, split)
             assert len(gcols) == len(cols)
             flat = [v for pr in info for v in pr]
             self.variants["halo"] = {"cols": gcols, "groups_dev": torch.tensor(groups, dtype=torch.int32).to(device),
@@ -213,7 +251,8 @@ class ConvOp:
         elif backend in ("halo", "halo2"):
             raise ValueError("%s: the row-halo kernel needs an output of at least 16x16" % name)
         self.num_steps = len(cols)
-        self.out = out if out is not None else torch.empty((N, Ho, Wo, cout), dtype=TORCH_DTYPE[dtype], device=device)
+        self.out = out if out is not None else torch.empty((N, Ho, Wo, cout * pf), dtype=TORCH_DTYPE[dtype],
+                                                           device=device)
         self.wp = torch.zeros((cout, self.num_steps * ch), dtype=TORCH_DTYPE[dtype], device=device)
         self.bias = torch.zeros((cout,), dtype=torch.float32, device=device)
         self.desc = _lib.ConvDesc(N, Ho, Wo, cout, self.out.shape[3], c_out_offset, stride, 1 if relu else 0,
@@ -306,9 +345,16 @@ class _Plan:
         self.convs = {}    # name -> ConvOp
         self.heads = {}    # name -> dict(w, bias, scale)
         self.ch = chunk_channels(self.dtype)
+        self.pf = phys_factor(self.dtype)
 
     def buf(self, *shape, dtype=None):
+        """Plain buffer (dtype given) or act tensor [N,H,W,C logical] (C * pf physical channels)."""
+        if dtype is None:
+            shape = tuple(shape[:-1]) + (shape[-1] * self.pf,)
         return torch.empty(shape, dtype=TORCH_DTYPE[self.dtype] if dtype is None else dtype, device=self.device)
+
+    def src(self, buf, wch):
+        return act_src(buf, wch, phys=self.pf)
 
     def conv(self, name, srcs, k, stride, cout, N, Ho, Wo, relu=True):
         op = ConvOp(name, srcs, k, stride, cout, N, Ho, Wo, self.dtype, self.device, relu, backend=self.backend)
@@ -318,6 +364,7 @@ class _Plan:
 
     def upsample(self, x):
         N, h, w, Cc = x.shape
+        Cc //= self.pf
         out = self.buf(N, 2 * h, 2 * w, Cc)
         lib, dt = self.lib, self.dtype
         self.ops.append(lambda s: _lib.check(lib.cnm_upsample2x(x.data_ptr(), out.data_ptr(), N, h, w, Cc, dt, s),
@@ -326,6 +373,7 @@ class _Plan:
 
     def head(self, name, x, scale, want_logits=False):
         N, H, W, Cc = x.shape
+        Cc //= self.pf
         out = self.buf(N, 1, H, W, dtype=torch.float32)
         logits = self.buf(N, 1, H, W, dtype=torch.float32) if want_logits else None
         hw = {"w": torch.zeros((9 * Cc,), dtype=torch.float32, device=self.device), "bias": 0.0, "scale": float(scale)}
@@ -414,35 +462,35 @@ class DepthNetPlan(_Plan):
     def _trunk(self, want_logits):
         N, H, W = self.N, self.H, self.W
         cv = self.conv
-        x = cv("conv1.0", [act_src(self.cost, 3), Src(self.img_taps, "rowtaps", 0, self.ch, 0, 3)], 7, 1, 128, N, H, W)
-        conv1 = cv("conv1.3", [act_src(x, 0)], 7, 2, 128, N, H // 2, W // 2)
-        x = cv("conv2.0", [act_src(conv1, 0)], 5, 1, 256, N, H // 2, W // 2)
-        conv2 = cv("conv2.3", [act_src(x, 0)], 5, 2, 256, N, H // 4, W // 4)
-        x = cv("conv3.0", [act_src(conv2, 0)], 3, 1, 512, N, H // 4, W // 4)
-        conv3 = cv("conv3.3", [act_src(x, 0)], 3, 2, 512, N, H // 8, W // 8)
-        x = cv("conv4.0", [act_src(conv3, 0)], 3, 1, 512, N, H // 8, W // 8)
-        conv4 = cv("conv4.3", [act_src(x, 0)], 3, 2, 512, N, H // 16, W // 16)
-        x = cv("conv5.0", [act_src(conv4, 0)], 3, 1, 512, N, H // 16, W // 16)
-        conv5 = cv("conv5.3", [act_src(x, 0)], 3, 2, 512, N, H // 32, W // 32)
+        x = cv("conv1.0", [self.src(self.cost, 3), Src(self.img_taps, "rowtaps", 0, self.ch, 0, 3)], 7, 1, 128, N, H, W)
+        conv1 = cv("conv1.3", [self.src(x, 0)], 7, 2, 128, N, H // 2, W // 2)
+        x = cv("conv2.0", [self.src(conv1, 0)], 5, 1, 256, N, H // 2, W // 2)
+        conv2 = cv("conv2.3", [self.src(x, 0)], 5, 2, 256, N, H // 4, W // 4)
+        x = cv("conv3.0", [self.src(conv2, 0)], 3, 1, 512, N, H // 4, W // 4)
+        conv3 = cv("conv3.3", [self.src(x, 0)], 3, 2, 512, N, H // 8, W // 8)
+        x = cv("conv4.0", [self.src(conv3, 0)], 3, 1, 512, N, H // 8, W // 8)
+        conv4 = cv("conv4.3", [self.src(x, 0)], 3, 2, 512, N, H // 16, W // 16)
+        x = cv("conv5.0", [self.src(conv4, 0)], 3, 1, 512, N, H // 16, W // 16)
+        conv5 = cv("conv5.3", [self.src(x, 0)], 3, 2, 512, N, H // 32, W // 32)
 
-        up5 = cv("upconv5.1", [act_src(self.upsample(conv5), 0)], 3, 1, 512, N, H // 16, W // 16)
-        iconv5 = cv("iconv5.0", [act_src(up5, 0), act_src(conv4, 512)], 3, 1, 512, N, H // 16, W // 16)
-        up4 = cv("upconv4.1", [act_src(self.upsample(iconv5), 0)], 3, 1, 512, N, H // 8, W // 8)
-        iconv4 = cv("iconv4.0", [act_src(up4, 0), act_src(conv3, 512)], 3, 1, 512, N, H // 8, W // 8)
+        up5 = cv("upconv5.1", [self.src(self.upsample(conv5), 0)], 3, 1, 512, N, H // 16, W // 16)
+        iconv5 = cv("iconv5.0", [self.src(up5, 0), self.src(conv4, 512)], 3, 1, 512, N, H // 16, W // 16)
+        up4 = cv("upconv4.1", [self.src(self.upsample(iconv5), 0)], 3, 1, 512, N, H // 8, W // 8)
+        iconv4 = cv("iconv4.0", [self.src(up4, 0), self.src(conv3, 512)], 3, 1, 512, N, H // 8, W // 8)
         self.disp4, l4 = self.head("disp4", iconv4, self.scale, want_logits)
         t4 = self.disp_taps(self.disp4)
-        up3 = cv("upconv3.1", [act_src(self.upsample(iconv4), 0)], 3, 1, 256, N, H // 4, W // 4)
-        iconv3 = cv("iconv3.0", [act_src(up3, 0), act_src(conv2, 256), Src(t4, "taps3x3", 512, self.ch, 0, 1)], 3, 1,
+        up3 = cv("upconv3.1", [self.src(self.upsample(iconv4), 0)], 3, 1, 256, N, H // 4, W // 4)
+        iconv3 = cv("iconv3.0", [self.src(up3, 0), self.src(conv2, 256), Src(t4, "taps3x3", 512, self.ch, 0, 1)], 3, 1,
                     256, N, H // 4, W // 4)
         self.disp3, l3 = self.head("disp3", iconv3, self.scale, want_logits)
         t3 = self.disp_taps(self.disp3)
-        up2 = cv("upconv2.1", [act_src(self.upsample(iconv3), 0)], 3, 1, 128, N, H // 2, W // 2)
-        iconv2 = cv("iconv2.0", [act_src(up2, 0), act_src(conv1, 128), Src(t3, "taps3x3", 256, self.ch, 0, 1)], 3, 1,
+        up2 = cv("upconv2.1", [self.src(self.upsample(iconv3), 0)], 3, 1, 128, N, H // 2, W // 2)
+        iconv2 = cv("iconv2.0", [self.src(up2, 0), self.src(conv1, 128), Src(t3, "taps3x3", 256, self.ch, 0, 1)], 3, 1,
                     128, N, H // 2, W // 2)
         self.disp2, l2 = self.head("disp2", iconv2, self.scale, want_logits)
         t2 = self.disp_taps(self.disp2)
-        up1 = cv("upconv1.1", [act_src(self.upsample(iconv2), 0)], 3, 1, 64, N, H, W)
-        self.iconv1 = cv("iconv1.0", [act_src(up1, 0), Src(t2, "taps3x3", 64, self.ch, 0, 1)], 3, 1, 64, N, H, W)
+        up1 = cv("upconv1.1", [self.src(self.upsample(iconv2), 0)], 3, 1, 64, N, H, W)
+        self.iconv1 = cv("iconv1.0", [self.src(up1, 0), Src(t2, "taps3x3", 64, self.ch, 0, 1)], 3, 1, 64, N, H, W)
         self.disp1, l1 = self.head("disp1", self.iconv1, self.scale, want_logits)
         self.logits = [l1, l2, l3, l4]
         self.tune()
@@ -465,6 +513,7 @@ class DepthNetPlan(_Plan):
 
     def iconv1_nchw(self, stream=None):
         N, H, W, Cc = self.iconv1.shape
+        Cc //= self.pf
         out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=self.device)
         s = _lib.stream_ptr() if stream is None else stream
         _lib.check(self.lib.cnm_act_to_nchw(self.iconv1.data_ptr(), out.data_ptr(), N, Cc, H, W, Cc, 0, self.dtype, s),
@@ -502,21 +551,21 @@ class RefinePlan(_Plan):
 
         self.ops.append(front)
         cv = self.conv
-        x = cv("conv1.0", [act_src(self.sum_act, 3), Src(self.taps, "taps3x3", 0, ch, 0, 3)], 3, 1, 128, B, H, W)
-        conv1 = cv("conv1.3", [act_src(x, 0)], 3, 2, 128, B, H // 2, W // 2)
-        x = cv("conv2.0", [act_src(conv1, 0)], 3, 1, 256, B, H // 2, W // 2)
-        conv2 = cv("conv2.3", [act_src(x, 0)], 3, 2, 256, B, H // 4, W // 4)
-        x = cv("conv3.0", [act_src(conv2, 0)], 3, 1, 512, B, H // 4, W // 4)
-        conv3 = cv("conv3.3", [act_src(x, 0)], 3, 2, 512, B, H // 8, W // 8)
+        x = cv("conv1.0", [self.src(self.sum_act, 3), Src(self.taps, "taps3x3", 0, ch, 0, 3)], 3, 1, 128, B, H, W)
+        conv1 = cv("conv1.3", [self.src(x, 0)], 3, 2, 128, B, H // 2, W // 2)
+        x = cv("conv2.0", [self.src(conv1, 0)], 3, 1, 256, B, H // 2, W // 2)
+        conv2 = cv("conv2.3", [self.src(x, 0)], 3, 2, 256, B, H // 4, W // 4)
+        x = cv("conv3.0", [self.src(conv2, 0)], 3, 1, 512, B, H // 4, W // 4)
+        conv3 = cv("conv3.3", [self.src(x, 0)], 3, 2, 512, B, H // 8, W // 8)
         up_conv3 = self.upsample(conv3)  # shared by both decoders
         self.out, self.logits, self.iconv1 = {}, {}, {}
         for br, head, sc in (("depth", "disp_refine", self.scale), ("prob", "prob", 1.0)):
-            u3 = cv("upconv3_%s.1" % br, [act_src(up_conv3, 0)], 3, 1, 256, B, H // 4, W // 4)
-            i3 = cv("iconv3_%s.0" % br, [act_src(u3, 0), act_src(conv2, 256)], 3, 1, 256, B, H // 4, W // 4)
-            u2 = cv("upconv2_%s.1" % br, [act_src(self.upsample(i3), 0)], 3, 1, 128, B, H // 2, W // 2)
-            i2 = cv("iconv2_%s.0" % br, [act_src(u2, 0), act_src(conv1, 128)], 3, 1, 128, B, H // 2, W // 2)
-            u1 = cv("upconv1_%s.1" % br, [act_src(self.upsample(i2), 0)], 3, 1, 64, B, H, W)
-            i1 = cv("iconv1_%s.0" % br, [act_src(u1, 0)], 3, 1, 64, B, H, W)
+            u3 = cv("upconv3_%s.1" % br, [self.src(up_conv3, 0)], 3, 1, 256, B, H // 4, W // 4)
+            i3 = cv("iconv3_%s.0" % br, [self.src(u3, 0), self.src(conv2, 256)], 3, 1, 256, B, H // 4, W // 4)
+            u2 = cv("upconv2_%s.1" % br, [self.src(self.upsample(i3), 0)], 3, 1, 128, B, H // 2, W // 2)
+            i2 = cv("iconv2_%s.0" % br, [self.src(u2, 0), self.src(conv1, 128)], 3, 1, 128, B, H // 2, W // 2)
+            u1 = cv("upconv1_%s.1" % br, [self.src(self.upsample(i2), 0)], 3, 1, 64, B, H, W)
+            i1 = cv("iconv1_%s.0" % br, [self.src(u1, 0)], 3, 1, 64, B, H, W)
             self.iconv1[br] = i1
             self.out[br], self.logits[br] = self.head(head, i1, sc, want_logits)
         self.tune()
@@ -530,6 +579,7 @@ class RefinePlan(_Plan):
     def iconv1_depth_nchw(self, stream=None):
         x = self.iconv1["depth"]
         N, H, W, Cc = x.shape
+        Cc //= self.pf
         out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=self.device)
         s = _lib.stream_ptr() if stream is None else stream
         _lib.check(self.lib.cnm_act_to_nchw(x.data_ptr(), out.data_ptr(), N, Cc, H, W, Cc, 0, self.dtype, s),

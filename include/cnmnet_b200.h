@@ -39,7 +39,11 @@ typedef enum cnm_status {
 /* element type of private activation tensors and packed conv weights */
 typedef enum cnm_dtype {
   CNM_BF16 = 0, /* bf16 storage, tcgen05 kind::f16, fp32 accumulate; K-chunk = 64 channels */
-  CNM_TF32 = 1  /* fp32 storage, tcgen05 kind::tf32, fp32 accumulate; K-chunk = 32 channels */
+  CNM_TF32 = 1, /* fp32 storage, tcgen05 kind::tf32, fp32 accumulate; K-chunk = 32 channels */
+  CNM_BF16X3 = 2 /* split bf16: every value stored as hi + lo bf16 (16 mantissa bits); a convolution runs as three
+                    kind::f16 passes hi*Whi + lo*Whi + hi*Wlo.  Physical layout: logical channel c of a pixel at
+                    physical channel (c/64)*128 + c%64 (hi) and 64 further (lo); act tensors have 2*C physical
+                    channels.  Conv descriptors / sources / steps are in PHYSICAL channels; desc.Cout is logical. */
 } cnm_dtype;
 
 /* cost-volume output layouts */

@@ -19,7 +19,7 @@ def to_act(x_nchw, dtype):
     lib = _lib.load()
     x = x_nchw.float().contiguous().to(dev())
     N, C, H, W = x.shape
-    out = torch.empty((N, H, W, C), dtype=engine.TORCH_DTYPE[dtype], device=dev())
+    out = torch.empty((N, H, W, C * engine.phys_factor(dtype)), dtype=engine.TORCH_DTYPE[dtype], device=dev())
     _lib.check(lib.cnm_nchw_to_act(x.data_ptr(), out.data_ptr(), N, C, H, W, C, 0, dtype, _lib.stream_ptr()))
     return out
 
@@ -27,6 +27,7 @@ def to_act(x_nchw, dtype):
 def from_act(a, dtype):
     lib = _lib.load()
     N, H, W, C = a.shape
+    C //= engine.phys_factor(dtype)
     out = torch.empty((N, C, H, W), dtype=torch.float32, device=a.device)
     _lib.check(lib.cnm_act_to_nchw(a.data_ptr(), out.data_ptr(), N, C, H, W, C, 0, dtype, _lib.stream_ptr()))
     torch.cuda.synchronize()
@@ -37,4 +38,13 @@ def quantize(x, dtype):
     """What storing x in an act tensor does to it."""
     if dtype == _lib.CNM_BF16:
         return x.to(torch.bfloat16).float()
+    if dtype == _lib.CNM_BF16X3:
+        hi = x.float().to(torch.bfloat16).float()
+        return hi + (x.float() - hi).to(torch.bfloat16).float()
     return engine.round_tf32(x.float())
+
+
+def act_empty(shape, dtype):
+    """Uninitialised act tensor for a LOGICAL [N,H,W,C] shape (physical channels per the mode)."""
+    N, H, W, C = shape
+    return torch.empty((N, H, W, C * engine.phys_factor(dtype)), dtype=engine.TORCH_DTYPE[dtype], device=dev())

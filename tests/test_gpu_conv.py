@@ -10,14 +10,17 @@ from gpu_util import dev, from_act, quantize, rel_l2, to_act
 
 pytestmark = pytest.mark.gpu
 
-DTYPES = [_lib.CNM_BF16, _lib.CNM_TF32]
+DTYPES = [_lib.CNM_BF16, _lib.CNM_TF32, _lib.CNM_BF16X3]
+# operands identical to the oracle's; what differs is fp32 accumulation order and the output rounding of the mode
+MAX_TOL = {_lib.CNM_BF16: 6e-3, _lib.CNM_TF32: 1e-3, _lib.CNM_BF16X3: 5e-5}
+L2_TOL = {_lib.CNM_BF16: 3e-3, _lib.CNM_TF32: 3e-4, _lib.CNM_BF16X3: 2e-5}
 
 
 def run_conv(backend, dtype, xs, wchs, w, b, k, stride, relu=True):
     N, _, H, W = xs[0].shape
     Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
     acts = [to_act(x, dtype) for x in xs]
-    srcs = [engine.act_src(a, wch) for a, wch in zip(acts, wchs)]
+    srcs = [engine.act_src(a, wch, phys=engine.phys_factor(dtype)) for a, wch in zip(acts, wchs)]
     op = engine.ConvOp("t", srcs, k, stride, w.shape[0], N, Ho, Wo, dtype, dev(), relu, backend=backend)
     op.load(w, b)
     op(_lib.stream_ptr())
@@ -64,10 +67,9 @@ def test_conv_matches_oracle(backend, dtype, case):
     want = oracle_conv(dtype, xs, w, b, k, stride)
     assert got.shape == want.shape
     # operands are identical; only fp32 accumulation order and the output rounding differ
-    tol = 6e-3 if dtype == _lib.CNM_BF16 else 1e-3
     err = (got - quantize(want, dtype)).abs().max().item()
-    assert err < tol * max(1.0, want.abs().max().item()), (err, rel_l2(got, want))
-    assert rel_l2(got, want) < (3e-3 if dtype == _lib.CNM_BF16 else 3e-4)
+    assert err < MAX_TOL[dtype] * max(1.0, want.abs().max().item()), (err, rel_l2(got, want))
+    assert rel_l2(got, want) < L2_TOL[dtype]
 
 
 HALO_CASES = [
@@ -100,10 +102,9 @@ def test_halo_conv_matches_oracle(backend, dtype, case):
     wchs = [sum(cins[:i]) for i in range(len(cins))]
     got = run_conv(backend, dtype, xs, wchs, w, b, k, stride)
     want = oracle_conv(dtype, xs, w, b, k, stride)
-    tol = 6e-3 if dtype == _lib.CNM_BF16 else 1e-3
     err = (got - quantize(want, dtype)).abs().max().item()
-    assert err < tol * max(1.0, want.abs().max().item()), (err, rel_l2(got, want))
-    assert rel_l2(got, want) < (3e-3 if dtype == _lib.CNM_BF16 else 3e-4)
+    assert err < MAX_TOL[dtype] * max(1.0, want.abs().max().item()), (err, rel_l2(got, want))
+    assert rel_l2(got, want) < L2_TOL[dtype]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -114,7 +115,7 @@ def test_conv_no_relu_negative_outputs(dtype):
     b = torch.randn(64, generator=g)
     got = run_conv("tc", dtype, [x], [0], w, b, 3, 1, relu=False)
     want = oracle_conv(dtype, [x], w, b, 3, 1, relu=False)
-    assert (want < 0).any() and rel_l2(got, want) < 3e-3
+    assert (want < 0).any() and rel_l2(got, want) < L2_TOL[dtype]
 
 
 def test_conv_rejects_bad_arguments():

@@ -21,7 +21,10 @@ pytestmark = pytest.mark.gpu
 # max 1.1-1.6e-3, mean 2-3e-4; bf16 p99 ~1e-2, max 1.5e-2, mean 3.7e-3.  The tensor-core kernel and its fp32-FMA
 # SIMT twin give the same numbers, i.e. the error is the operand rounding (10 / 7 mantissa bits) of the mode.
 TOL = {("tf32", "tc"): (1.5e-3, 1e-3, 2.5e-3, 4e-4), ("tf32", "simt"): (1.5e-3, 1e-3, 2.5e-3, 4e-4),
-       ("bf16", "tc"): (1.5e-2, 1.5e-2, 3e-2, 5e-3), ("bf16", "simt"): (1.5e-2, 1.5e-2, 3e-2, 5e-3)}
+       ("bf16", "tc"): (1.5e-2, 1.5e-2, 3e-2, 5e-3), ("bf16", "simt"): (1.5e-2, 1.5e-2, 3e-2, 5e-3),
+       # split bf16 (hi + lo, three tensor-core passes): 16 operand mantissa bits -- the mode that meets the north-star
+       # 1e-3 on the final depth with two orders of magnitude to spare
+       ("bf16x3", "tc"): (5e-5, 1e-4, 1e-3, 5e-5), ("bf16x3", "simt"): (5e-5, 1e-4, 1e-3, 5e-5)}
 MODES = list(TOL.keys())
 
 
@@ -91,7 +94,7 @@ def _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, scale, k_size):
     return depth.numpy(), normal, prob.numpy()
 
 
-@pytest.mark.parametrize("precision,V", [("tf32", 2), ("bf16", 2), ("tf32", 4)])
+@pytest.mark.parametrize("precision,V", [("tf32", 2), ("bf16", 2), ("tf32", 4), ("bf16x3", 2)])
 def test_pipeline_matches_oracle(precision, V):
     B, H, W = 2, 64, 96
     ref, srcs, ref_cam, src_cams = synth.frame_tuples(4321 + V, B, H, W, V)
@@ -121,7 +124,7 @@ def test_pipeline_matches_oracle(precision, V):
     # normals amplify depth noise (9x9 plane fit on a ~1e-3 perturbed surface): compare by angle
     cos = np.clip((n * want_n).sum(1), -1, 1)
     ang = np.degrees(np.arccos(cos))
-    assert np.median(ang) < (1.0 if precision == "tf32" else 8.0), np.median(ang)
+    assert np.median(ang) < {"tf32": 1.0, "bf16": 8.0, "bf16x3": 0.1}[precision], np.median(ang)
 
 
 def test_pipeline_with_halo_kernel_forced(monkeypatch):

@@ -148,6 +148,47 @@ def test_halo_groups_stride2_reproduce_conv(k):
     assert torch.allclose(got, want, atol=1e-9)
 
 
+def _split_phys(x_nhwc):
+    """Logical NHWC float tensor -> CNM_BF16X3 physical layout [.., (hi 64 | lo 64) per 64-channel chunk]."""
+    hi = x_nhwc.to(torch.bfloat16).float()
+    lo = (x_nhwc - hi).to(torch.bfloat16).float()
+    N, H, W, C = x_nhwc.shape
+    return torch.stack((hi.view(N, H, W, C // 64, 64), lo.view(N, H, W, C // 64, 64)), 4).reshape(N, H, W, 2 * C)
+
+
+@pytest.mark.parametrize("halo", [False, True])
+def test_split_bf16_programs_reproduce_conv(halo):
+    """bf16x3: three bf16 passes per logical chunk (hi*Whi + lo*Whi + hi*Wlo) on the hi/lo physical layout."""
+    torch.manual_seed(21)
+    ch, N, H, W, k = 64, 1, 7, 9, 3
+    x, disp = torch.randn(N, 128, H, W), torch.randn(N, 1, H, W)
+    wt, b = torch.randn(8, 129, k, k) / 30, torch.randn(8)
+    want = nhwc(F.conv2d(torch.cat((x, disp), 1).double(), wt.double(), b.double(), padding=1))
+    taps = torch.zeros(N, H, W, ch)
+    pd = F.pad(disp, (1, 1, 1, 1))
+    for r in range(3):
+        for s_ in range(3):
+            taps[..., 3 * r + s_] = pd[:, 0, r:r + H, s_:s_ + W]
+    xp, tp = _split_phys(nhwc(x)), _split_phys(taps)
+    srcs = [engine.act_src(xp, 0, phys=2), engine.Src(tp, "taps3x3", 128, ch, 0, 1)]
+    if halo:
+        groups, cols, info = engine.make_groups(srcs, k, ch, 1, split=True)
+        steps = [(m // 4, 0, dx, t - info[m][0], c0) for (m, c0, dx, nt) in groups for t in range(nt)]
+    else:
+        steps, cols = engine.make_steps(srcs, k, 1, ch, split=True)
+    assert len(steps) == len(cols) == 3 * (9 * 2 + 1)
+    wp = engine.pack_weights(wt, cols, ch, _lib.CNM_BF16X3).float()
+    got = emulate_steps([xp, tp], steps, wp, b, 1, ch, False)
+    # 16 mantissa bits per operand, the lo*lo term dropped: ~1e-5 relative
+    assert (got - want).abs().max() < 3e-5 * want.abs().max()
+    bf = emulate_steps([nhwc(x).to(torch.bfloat16).float(), taps.to(torch.bfloat16).float()],
+                       *engine.make_steps([engine.act_src(nhwc(x), 0), engine.Src(taps, "taps3x3", 128, ch, 0, 1)], k, 1, ch)[:1],
+                       engine.pack_weights(wt, engine.make_steps([engine.act_src(nhwc(x), 0),
+                                                                  engine.Src(taps, "taps3x3", 128, ch, 0, 1)], k, 1, ch)[1],
+                                           ch, _lib.CNM_BF16).float(), b, 1, ch, False)
+    assert (bf - want).abs().max() > 50 * (got - want).abs().max()   # plain bf16 is >50x worse on the same layer
+
+
 def test_fold_bn_matches_batchnorm():
     sd = synth.kaiming_state(nets.state_shapes([("c", "conv", 8, 4, 3)]), seed=5)
     x = torch.randn(2, 8, 6, 6)
