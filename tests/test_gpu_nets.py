@@ -128,6 +128,26 @@ def test_pipeline_matches_oracle(precision, V):
     assert np.median(ang) < {"tf32": 1.0, "bf16": 8.0, "bf16x3": 0.5}[precision], np.median(ang)
 
 
+@pytest.mark.parametrize("H,W,B", [(96, 160, 3), (480, 640, 1)])
+def test_pipeline_odd_pyramid_sizes(H, W, B):
+    """Image sizes whose pyramid levels are not multiples of the 16x16 / 16x8 pixel tiles (96x160 -> 48x80 ... 3x5;
+    640x480 = BASELINE config 5's resolution -> 240x320 ... 15x20): partial tiles, TMA clipping, odd batch."""
+    V = 2
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(500 + H, B, H, W, V)
+    dsd = synth.kaiming_state(onets.state_shapes(onets.DEPTHNET_LAYERS), 51, 0.02)
+    rsd = synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), 52, 0.02)
+    dnet = cnmnet_b200.depthNet(idepth_scale=3.0, precision="bf16x3")
+    rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0, precision="bf16x3")
+    dnet.load_state_dict(dsd)
+    rnet.load_state_dict(rsd)
+    pipe = cnmnet_b200.CNMPipeline(dnet.to(dev()), rnet.to(dev()), k_size=9)
+    d, n, p = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))
+    want_d, want_n, want_p = _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, 9)
+    rel = np.abs(d.cpu().numpy() - want_d) / np.abs(want_d)
+    assert rel.max() < 1e-3 and rel.mean() < 5e-5, (rel.max(), rel.mean())
+    assert np.abs(p.cpu().numpy() - want_p).max() < 1e-3
+
+
 def test_pipeline_with_halo_kernel_forced(monkeypatch):
     """Every eligible stride-1 layer through csrc/conv_halo.cu (incl. the side-tensor sources) vs the per-tap kernel."""
     from cnmnet_b200 import engine
