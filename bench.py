@@ -37,9 +37,10 @@ C2_COST_VOLUME_BYTES = 5 * (2 * 4 * D * H * W + 3 * 4 * 3 * H * W)  # 134 676 48
 # final-depth error of each tensor-core mode vs the fp32 reference restatement, as measured by tests/test_gpu_nets.py and
 # __graft_entry__.smoke() on B200 (round 1); the north-star tolerance is 1e-3 relative
 PRECISION_NOTES = {
-    "bf16": "bf16 operands, fp32 accumulate (speed mode): final depth mean rel err 3.7e-3, p99 1e-2",
-    "tf32": "tf32 operands, fp32 accumulate: final depth mean rel err 2-4e-4, p99 6e-4..1.8e-3 depending on weights",
-    "bf16x3": "split bf16 (hi+lo, 3 tensor-core passes), fp32 accumulate (accuracy mode): final depth max rel err 2.4e-4",
+    "bf16": "bf16 operands, fp32 accumulate (speed mode): final depth mean rel err 4e-3 or more, p99 >= 1e-2",
+    "tf32": "tf32 operands, fp32 accumulate: final depth mean rel err 2e-4..2e-3, p99 6e-4..7e-3 depending on weights",
+    "bf16x3": "split bf16 (hi+lo operands, 3 bf16 tensor-core passes, fp32 accumulate): final depth max rel err 2e-4..7e-4 "
+              "over all weights tried -- the mode that meets the 1e-3 tolerance",
 }
 
 
@@ -206,7 +207,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cnmnet_b200", choices=["cnmnet_b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CNM_PRECISION", "bf16"), choices=["bf16", "tf32", "bf16x3"])
+    ap.add_argument("--precision", default=os.environ.get("CNM_PRECISION", "bf16x3"),
+                    choices=["bf16", "tf32", "bf16x3"],
+                    help="tensor-core mode; the default bf16x3 is the one that meets the 1e-3 final-depth tolerance")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer timing table on stderr")
@@ -346,8 +349,12 @@ def main():
         issued_flop = sum(r[2] for r in conv_rows)
         tf = alg_flop / (conv_ms * 1e-3) / 1e12
         tf32 = args.precision == "tf32"
+        fp32_equiv_tf = tf
         if args.precision == "bf16x3":
-            alg_flop *= 3.0  # three bf16 tensor-core passes per logical product
+            # the arithmetic of this mode is three bf16 tensor-core products per fp32-grade product (hi*Whi + lo*Whi +
+            # hi*Wlo, none redundant): the roofline counts them; fp32_equivalent_tflops is the 1x figure
+            alg_flop *= 3.0
+            tf *= 3.0
         peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
         line["roofline"] = {
             "kernel": "conv_tc / conv_halo / conv_halo2 kernels (tcgen05 implicit GEMM, all %d conv launches of one step)"
@@ -355,7 +362,7 @@ def main():
             "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
             "traffic": traffic.get("conv_bytes_per_step") if not tf32 else None,
             "traffic_note": "DRAM read+write bytes of all conv launches of one step, ncu (profiles/r01_launches_step.md)",
-            "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step,
+            "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step, "fp32_equivalent_tflops": fp32_equiv_tf,
             "peak_source": "%s bf16 sustained%s" % (peaks["source"], " x 0.5 for tf32" if tf32 else ""),
             "issued_tflops_incl_padding": issued_flop / (conv_ms * 1e-3) / 1e12,
         }
