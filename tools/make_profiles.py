@@ -29,7 +29,7 @@ if os.path.exists(bp):
 out = ["# %s launch list of one pipeline step" % tag, "",
        "Command: `CNM_TUNE_CACHE=gpurun_out/tune_cache.json ncu --profile-from-start off --metrics "
        "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv python tools/profile_step.py`",
-       "(one un-graphed C4 step, bf16 mode, B=5 x 2 source views, 256x192x64, after one warm-up step; conv kernel / tile choices",
+       "(one un-graphed C4 step, %s mode, B=5 x 2 source views, 256x192x64, after one warm-up step; conv kernel / tile choices" % bench.get("dtype", "bf16x3"),
        "come from the autotuner cache written by the preceding `bench.py` run; the last `cost_volume_kernel<16,0>` launch is the C2",
        "NCHW fp32 micro-benchmark).  Times are cold-cache and serialised by ncu: compare SHARES, not absolutes (the same step",
        "replayed as a CUDA graph takes %.2f ms in bench.py)." % bench.get("ms_per_step", float("nan")), "",
@@ -55,7 +55,7 @@ out += ["", "Convolution kernels (`conv_tc_kernel`, `conv_halo_kernel`, `conv_ha
         "%.1f MB of DRAM traffic per step." % (cu, 100 * cu / s, cm)]
 open(os.path.join(P, "%s_launches_step.md" % tag), "w").write("\n".join(out) + "\n")
 cv = [d for d in L.values() if d["name"].startswith("cost_volume_kernel<16, 0>")]
-json.dump({"source": "profiles/%s_launches_step.md (ncu dram__bytes_read.sum + dram__bytes_write.sum, one C4 step, bf16)" % tag,
+json.dump({"source": "profiles/%s_launches_step.md (ncu dram__bytes_read.sum + dram__bytes_write.sum, one C4 step, %s)" % (tag, bench.get("dtype", "bf16x3")),
            "conv_bytes_per_step": cm * 1e6, "conv_launches": sum(v[0] for k, v in tot.items() if k.startswith("conv_")),
            "cost_volume_c2_bytes": (cv[0]["dram__bytes_read.sum"] + cv[0]["dram__bytes_write.sum"]) if cv else None},
           open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
@@ -87,12 +87,14 @@ def dump(rep, outname, title, note):
     open(os.path.join(P, outname), "w").write("\n".join(lines))
 
 
-dump("prof_halo.ncu-rep", "%s_conv_halo_ncu.md" % tag,
+if "--full" in sys.argv:
+  dump("prof_halo.ncu-rep", "%s_conv_halo_ncu.md" % tag,
      "%s ncu --set full: conv_halo_kernel / conv_halo2_kernel (row-halo tcgen05 conv, 1-SM and CTA-pair)" % tag,
      "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k "
      "regex:\"conv_halo2_kernel|conv_halo_kernel\" -c 6 python tools/profile_step.py` (bf16, C4 step, first six halo launches of "
      "the DepthNet pass: conv1.0, conv1.3, conv2.0, conv3.0, ... in launch order; see the launch list for grids).")
-dump("prof_tc.ncu-rep", "%s_conv_tc_final_ncu.md" % tag,
+if "--full" in sys.argv:
+  dump("prof_tc.ncu-rep", "%s_conv_tc_final_ncu.md" % tag,
      "%s ncu --set full: conv_tc_kernel (per-tap tcgen05 conv) after the warp-uniform issue loop" % tag,
      "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 "
      "python tools/profile_step.py` (bf16, C4 step; the layers the autotuner leaves on the per-tap kernel: stride-2 and <= 48x64 layers).")
