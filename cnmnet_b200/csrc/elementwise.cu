@@ -254,13 +254,26 @@ __global__ void __launch_bounds__(256, 2)
   const int PC = (int)ActTraits<T>::pstride(C);  // physical channels per pixel (raw 16-byte vectors are staged as stored)
   constexpr int RAWN = 16 / sizeof(T);
   const int cv = PC / RAWN, npix = (TR + 2) * 34;
-  for (int i = threadIdx.x; i < npix * cv; i += 256) {
-    const int pi = i / cv, c = (i % cv) * RAWN;
-    const int yy = y0 + pi / 34 - 1, xx = x0 + pi % 34 - 1;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-      v = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * PC + c));
-    *reinterpret_cast<uint4*>(tile + (size_t)pi * PC + c) = v;
+  // four independent 16-byte loads in flight per thread before the first store (the staging phase is latency-bound)
+  for (int i0 = threadIdx.x; i0 < npix * cv; i0 += 4 * 256) {
+    uint4 v[4];
+    int dsti[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      dsti[u] = -1;
+      if (i < npix * cv) {
+        const int pi = i / cv, c = (i % cv) * RAWN;
+        const int yy = y0 + pi / 34 - 1, xx = x0 + pi % 34 - 1;
+        dsti[u] = pi * PC + c;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v[u] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * PC + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (dsti[u] >= 0) *reinterpret_cast<uint4*>(tile + dsti[u]) = v[u];
   }
   __syncthreads();
   const int sub = threadIdx.x % LPP, grp = threadIdx.x / LPP;
@@ -335,9 +348,9 @@ static int launch_head(const T* x, const float* w, float bias, float scale, floa
                        int W, int C, cudaStream_t s) {
   const int lanes = C / Vec16<T>::N;  // one 16-byte vector per lane
   const int lpp = lanes >= 32 ? 32 : (lanes >= 16 ? 16 : 8);
-  // rows per CTA: keep the staged halo tile around 100 KB (two CTAs per SM)
-  int TR = (int)(100 * 1024 / ((size_t)34 * ActTraits<T>::pstride(C) * sizeof(T))) - 2;
-  TR = TR >= 8 ? 8 : (TR >= 4 ? 4 : (TR >= 2 ? 2 : 1));
+  // rows per CTA: keep the staged halo tile around 50 KB (four CTAs per SM hide the staging latency)
+  int TR = (int)(50 * 1024 / ((size_t)34 * ActTraits<T>::pstride(C) * sizeof(T))) - 2;
+  TR = TR > 8 ? 8 : (TR < 1 ? 1 : TR);
   const size_t smem = (size_t)9 * C * 4 + (size_t)(TR + 2) * 34 * ActTraits<T>::pstride(C) * sizeof(T);
   dim3 grid((W + 31) / 32, (H + TR - 1) / TR, N);
   if (N > 65535 || grid.y > 65535) return fail(CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head3x3: grid too large");
