@@ -280,7 +280,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box) {
+               const uint32_t* box, bool swizzle128) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(CNM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gd[5];
@@ -290,7 +290,8 @@ int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const uin
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(map, dtype == CNM_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                    (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CNM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return CNM_OK;
 }

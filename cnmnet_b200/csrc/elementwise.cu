@@ -4,7 +4,9 @@
 // Reference semantics: depthnet/depthNet_model.py:82-84 (depth_layer), :94,105 (nn.Upsample),
 // :233,247-258 (torch.cat / F.upsample of the inputs), :332-333 (refine input), eval.py:659-663,
 // 920-929 (view-group means).
-#include "common.cuh"
+#include <cstring>
+
+#include "tc_common.cuh"
 
 namespace cnm {
 
@@ -238,48 +240,51 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ s
 }
 
 // ---- 1-channel 3x3 head --------------------------------------------------------------------------------------
-// CTA = 32 x TR output pixels; the (TR+2) x 34 halo of the input (all C channels) is staged once in shared memory
-// (zero outside the image = conv padding), so each input pixel crosses L2 -> SM 1.3-1.6x instead of 3.2x.  LPP lanes
-// per pixel, one 16-byte vector per lane and tap; fp32 accumulate, shuffle reduce, bias + scale * sigmoid epilogue.
+// CTA = 32 x TR output pixels.  The (TR+2) x 34 halo of the input (all channels) is staged in shared memory by TMA
+// (one or two 4-D boxes {<=256 ch, 34, TR+2, 1}; pixels outside the image are zero-filled = conv padding), so the
+// staging costs one instruction and each input pixel crosses L2 -> SM ~1.3x.  LPP lanes per pixel, one 16-byte
+// vector per lane and tap, the lane's 9 x VN weights in registers when one vector per lane covers all channels;
+// fp32 accumulate, shuffle reduce, bias + scale * sigmoid epilogue.
+struct alignas(64) HeadParams {
+  CUtensorMap x_map;
+  const float* w;
+  float* out;
+  float* logits;
+  float bias, scale;
+  int H, W, C, TR, PC, boxc, nbox;
+};
+
 template <typename T, int LPP>
-__global__ void __launch_bounds__(256, 2)
-    head3x3_kernel(const T* __restrict__ x, const float* __restrict__ w, float bias, float scale,
-                   float* __restrict__ out, float* __restrict__ logits, int H, int W, int C, int TR) {
-  extern __shared__ __align__(16) uint8_t hsm[];
+__global__ void __launch_bounds__(256, 2) head3x3_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ uint8_t hsm_raw[];
   constexpr int VN = Vec16<T>::N;
-  float* ws = reinterpret_cast<float*>(hsm);                 // [9*C] in (r, s, c) order
-  T* tile = reinterpret_cast<T*>(hsm + (size_t)9 * C * 4);   // [(TR+2)][34][C]
+  const int C = p.C, PC = p.PC, TR = p.TR, npix = (TR + 2) * 34;
+  const uint32_t base = (smem_u32(hsm_raw) + 127u) & ~127u;
+  uint8_t* hsm = hsm_raw + (base - smem_u32(hsm_raw));
+  T* tile = reinterpret_cast<T*>(hsm);                                   // [nbox][(TR+2)][34][boxc]
+  const size_t tile_bytes = (size_t)npix * PC * sizeof(T);
+  float* ws = reinterpret_cast<float*>(hsm + tile_bytes);                 // [9*C] in (r, s, c) order
+  const uint32_t bar = base + (uint32_t)tile_bytes + (uint32_t)(9 * C * 4);
   const int n = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * TR;
-  for (int i = threadIdx.x; i < 9 * C; i += 256) ws[i] = __ldg(w + i);
-  const int PC = (int)ActTraits<T>::pstride(C);  // physical channels per pixel (raw 16-byte vectors are staged as stored)
-  constexpr int RAWN = 16 / sizeof(T);
-  const int cv = PC / RAWN, npix = (TR + 2) * 34;
-  // four independent 16-byte loads in flight per thread before the first store (the staging phase is latency-bound)
-  for (int i0 = threadIdx.x; i0 < npix * cv; i0 += 4 * 256) {
-    uint4 v[4];
-    int dsti[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 256;
-      v[u] = make_uint4(0u, 0u, 0u, 0u);
-      dsti[u] = -1;
-      if (i < npix * cv) {
-        const int pi = i / cv, c = (i % cv) * RAWN;
-        const int yy = y0 + pi / 34 - 1, xx = x0 + pi % 34 - 1;
-        dsti[u] = pi * PC + c;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-          v[u] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)n * H + yy) * W + xx) * PC + c));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (dsti[u] >= 0) *reinterpret_cast<uint4*>(tile + dsti[u]) = v[u];
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)tile_bytes);
+    for (int b = 0; b < p.nbox; ++b)
+      tma_load_4d(base + (uint32_t)((size_t)b * npix * p.boxc * sizeof(T)), &p.x_map, bar, b * p.boxc, x0 - 1, y0 - 1, n);
+  }
+  for (int i = threadIdx.x; i < 9 * C; i += 256) ws[i] = __ldg(p.w + i);
+  __syncthreads();
+  mbar_wait(bar, 0);
+  // physical channel q of halo pixel pi
+  const int boxc = p.boxc;
+  auto toff = [&](int pi, size_t q) { return (q / boxc) * ((size_t)npix * boxc) + (size_t)pi * boxc + (q % boxc); };
+
   const int sub = threadIdx.x % LPP, grp = threadIdx.x / LPP;
   constexpr int GROUPS = 256 / LPP;
-  // When one 16-byte vector per lane covers all channels (C == LPP*VN) a lane needs the same 9*VN weights for every
-  // pixel: keep them in registers.  Otherwise (C = 512) they are read from shared memory per pixel.
   const bool wreg = (C == LPP * VN);
   float wr[9][VN];
   if (wreg) {
@@ -292,20 +297,21 @@ __global__ void __launch_bounds__(256, 2)
     const int ty = pi / 32, tx = pi % 32;
     float acc = 0.0f;
     if (wreg) {
-      const T* tp = tile + ((size_t)ty * 34 + tx) * PC + ActTraits<T>::phys(sub * VN);
+      const size_t q = ActTraits<T>::phys(sub * VN);
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         float v[VN];
-        Vec16<T>::load(tp + ((t / 3) * 34 + t % 3) * PC, v);
+        Vec16<T>::load(tile + toff((ty + t / 3) * 34 + tx + t % 3, q), v);
 #pragma unroll
         for (int j = 0; j < VN; ++j) acc = fmaf(v[j], wr[t][j], acc);
       }
     } else {
       for (int c = sub * VN; c < C; c += LPP * VN) {
+        const size_t q = ActTraits<T>::phys(c);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           float v[VN];
-          Vec16<T>::load(tile + ((size_t)(ty + t / 3) * 34 + tx + t % 3) * PC + ActTraits<T>::phys(c), v);
+          Vec16<T>::load(tile + toff((ty + t / 3) * 34 + tx + t % 3, q), v);
           const float* wp = ws + t * C + c;
 #pragma unroll
           for (int j = 0; j < VN; j += 4) {
@@ -321,42 +327,55 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
     for (int o = 1; o < LPP; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     const int yy = y0 + ty, xx = x0 + tx;
-    if (sub == 0 && yy < H && xx < W) {
-      const size_t pix = ((size_t)n * H + yy) * W + xx;
-      const float l = acc + bias;
-      if (logits) logits[pix] = l;
-      out[pix] = scale / (1.0f + expf(-l));
+    if (sub == 0 && yy < p.H && xx < p.W) {
+      const size_t pix = ((size_t)n * p.H + yy) * p.W + xx;
+      const float l = acc + p.bias;
+      if (p.logits) p.logits[pix] = l;
+      p.out[pix] = p.scale / (1.0f + expf(-l));
     }
   }
 }
 
 template <typename T, int LPP>
-static int launch_head_lpp(const T* x, const float* w, float bias, float scale, float* out, float* logits, int H, int W,
-                           int C, int TR, dim3 grid, size_t smem, cudaStream_t s) {
+static int launch_head_lpp(const HeadParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(head3x3_kernel<T, LPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_head3x3: smem attribute: %s", cudaGetErrorString(e));
     configured = smem;
   }
-  head3x3_kernel<T, LPP><<<grid, 256, smem, s>>>(x, w, bias, scale, out, logits, H, W, C, TR);
+  head3x3_kernel<T, LPP><<<grid, 256, smem, s>>>(p);
   return CNM_OK;
 }
 
 template <typename T>
 static int launch_head(const T* x, const float* w, float bias, float scale, float* out, float* logits, int N, int H,
-                       int W, int C, cudaStream_t s) {
+                       int W, int C, int dtype, cudaStream_t s) {
   const int lanes = C / Vec16<T>::N;  // one 16-byte vector per lane
   const int lpp = lanes >= 32 ? 32 : (lanes >= 16 ? 16 : 8);
-  // rows per CTA: keep the staged halo tile around 50 KB (four CTAs per SM hide the staging latency)
-  int TR = (int)(50 * 1024 / ((size_t)34 * ActTraits<T>::pstride(C) * sizeof(T))) - 2;
+  HeadParams p;
+  memset(&p, 0, sizeof(p));
+  p.w = w; p.out = out; p.logits = logits; p.bias = bias; p.scale = scale;
+  p.H = H; p.W = W; p.C = C;
+  p.PC = (int)ActTraits<T>::pstride(C);
+  p.boxc = p.PC < 256 ? p.PC : 256;
+  p.nbox = p.PC / p.boxc;
+  // rows per CTA: keep the staged halo tile around 50 KB (four CTAs per SM)
+  int TR = (int)(50 * 1024 / ((size_t)34 * p.PC * sizeof(T))) - 2;
   TR = TR > 8 ? 8 : (TR < 1 ? 1 : TR);
-  const size_t smem = (size_t)9 * C * 4 + (size_t)(TR + 2) * 34 * ActTraits<T>::pstride(C) * sizeof(T);
+  p.TR = TR;
+  const uint64_t pix = (uint64_t)p.PC * sizeof(T);
+  const uint64_t dims[4] = {(uint64_t)p.PC, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  const uint64_t str[3] = {pix, pix * W, pix * W * H};
+  const uint32_t box[4] = {(uint32_t)p.boxc, 34u, (uint32_t)(TR + 2), 1u};
+  int rc = encode_map(&p.x_map, dtype, 4, x, dims, str, box, /*swizzle128=*/false);
+  if (rc) return rc;
+  const size_t smem = 128 + (size_t)(TR + 2) * 34 * p.PC * sizeof(T) + (size_t)9 * C * 4 + 16;
   dim3 grid((W + 31) / 32, (H + TR - 1) / TR, N);
   if (N > 65535 || grid.y > 65535) return fail(CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head3x3: grid too large");
-  if (lpp == 32) return launch_head_lpp<T, 32>(x, w, bias, scale, out, logits, H, W, C, TR, grid, smem, s);
-  if (lpp == 16) return launch_head_lpp<T, 16>(x, w, bias, scale, out, logits, H, W, C, TR, grid, smem, s);
-  return launch_head_lpp<T, 8>(x, w, bias, scale, out, logits, H, W, C, TR, grid, smem, s);
+  if (lpp == 32) return launch_head_lpp<T, 32>(p, grid, smem, s);
+  if (lpp == 16) return launch_head_lpp<T, 16>(p, grid, smem, s);
+  return launch_head_lpp<T, 8>(p, grid, smem, s);
 }
 
 }  // namespace cnm
@@ -460,7 +479,7 @@ extern "C" int cnm_head3x3(const void* x, const float* w, float bias, float scal
   CNM_REQUIRE(x && w && out && N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_head3x3: bad argument");
   CNM_REQUIRE(C % 64 == 0 && C <= 1024, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head3x3: C=%d must be a multiple of 64", C);
   DISPATCH_DTYPE(dtype, {
-    int rc = launch_head<T>((const T*)x, w, bias, scale, out, logits, N, H, W, C, (cudaStream_t)stream);
+    int rc = launch_head<T>((const T*)x, w, bias, scale, out, logits, N, H, W, C, dtype, (cudaStream_t)stream);
     if (rc) return rc;
   });
   return after_launch("cnm_head3x3");

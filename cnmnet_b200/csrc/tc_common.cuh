@@ -97,7 +97,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
 int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
-               const uint32_t* box);
+               const uint32_t* box, bool swizzle128 = true);
 int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* srcs, const void* steps, const void* wp,
                     const void* out);
 
