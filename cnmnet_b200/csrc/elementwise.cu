@@ -360,8 +360,10 @@ static int launch_head(const T* x, const float* w, float bias, float scale, floa
   p.PC = (int)ActTraits<T>::pstride(C);
   p.boxc = p.PC < 256 ? p.PC : 256;
   p.nbox = p.PC / p.boxc;
-  // rows per CTA: keep the staged halo tile around 50 KB (four CTAs per SM)
-  int TR = (int)(50 * 1024 / ((size_t)34 * p.PC * sizeof(T))) - 2;
+  // rows per CTA: staged halo tile of ~50 KB (four CTAs per SM), ~100 KB when a pixel is wider than 128 B so that
+  // the two halo rows stay a small fraction of the tile
+  const size_t px_bytes = (size_t)p.PC * sizeof(T);
+  int TR = (int)((px_bytes > 128 ? 100 : 50) * 1024 / (34 * px_bytes)) - 2;
   TR = TR > 8 ? 8 : (TR < 1 ? 1 : TR);
   p.TR = TR;
   const uint64_t pix = (uint64_t)p.PC * sizeof(T);
