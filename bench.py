@@ -210,10 +210,20 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("CNM_PRECISION", "bf16x3"),
                     choices=["bf16", "tf32", "bf16x3"],
                     help="tensor-core mode; the default bf16x3 is the one that meets the 1e-3 final-depth tolerance")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c4 = BASELINE configs[3] (default, the metric's config); c5 = configs[4] at the reference's 64 "
+                         "planes: 640x480, batch 32 per GPU (128 planes would need a 131-channel conv1 the reference "
+                         "network does not have)")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer timing table on stderr")
     args = ap.parse_args()
+    global H, W, B_PER_GPU, WORKLOAD, DEPTHNET_GFLOP, REFINE_GFLOP
+    if args.workload == "c5":
+        H, W, B_PER_GPU = 480, 640, 32
+        WORKLOAD = "C5 at 64 planes: full refine model, 1 ref + 2 src views, 640x480, 64 planes, k_size 9, batch 32 per GPU"
+        DEPTHNET_GFLOP, REFINE_GFLOP = 1008.94, 704.96
+        args.no_cpu_baseline = True
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
