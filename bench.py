@@ -40,7 +40,10 @@ PRECISION_NOTES = {
     "bf16": "bf16 operands, fp32 accumulate (speed mode): final depth mean rel err 4e-3 or more, p99 >= 1e-2",
     "tf32": "tf32 operands, fp32 accumulate: final depth mean rel err 2e-4..2e-3, p99 6e-4..7e-3 depending on weights",
     "bf16x3": "split bf16 (hi+lo operands, 3 bf16 tensor-core passes, fp32 accumulate): final depth max rel err 2e-4..7e-4 "
-              "over all weights tried -- the mode that meets the 1e-3 tolerance",
+              "over all weights tried -- meets the 1e-3 tolerance",
+    "f16f8": "fp16 operands + fp8 (e4m3) first-order corrections: one kind::f16 pass hi*W16 and one kind::f8f6f4 pass "
+             "[lo8|hi8]*[Whi8|Wlo8] into the same fp32 accumulator (2 bf16-pass-equivalents of tensor time instead of 3); "
+             "operand error ~2^-17 like bf16x3 -- meets the 1e-3 tolerance",
 }
 
 
@@ -207,9 +210,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cnmnet_b200", choices=["cnmnet_b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CNM_PRECISION", "bf16x3"),
-                    choices=["bf16", "tf32", "bf16x3"],
-                    help="tensor-core mode; the default bf16x3 is the one that meets the 1e-3 final-depth tolerance")
+    ap.add_argument("--precision", default=os.environ.get("CNM_PRECISION", "f16f8"),
+                    choices=["bf16", "tf32", "bf16x3", "f16f8"],
+                    help="tensor-core mode; f16f8 (default) and bf16x3 meet the 1e-3 final-depth tolerance")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
                     help="c4 = BASELINE configs[3] (default, the metric's config); c5 = configs[4] at the reference's 64 "
                          "planes: 640x480, batch 32 per GPU (128 planes would need a 131-channel conv1 the reference "
@@ -354,7 +357,7 @@ def main():
             for name, op in plan.convs.items():
                 ms, _ = time_events(lambda: op(s), 5, flush)
                 conv_ms += ms
-                conv_rows.append(("%s.%s [%s/%d]" % (tag, name, op.backend, op.desc.reserved), ms, op.flops))
+                conv_rows.append(("%s.%s [%s/%d]" % (tag, name, op.backend, op.desc.reserved), ms, op.flops_bf16_time))
         alg_flop = B * (V * DEPTHNET_GFLOP + REFINE_GFLOP) * 1e9  # real channels only (no padding)
         issued_flop = sum(r[2] for r in conv_rows)
         tf = alg_flop / (conv_ms * 1e-3) / 1e12
@@ -365,6 +368,12 @@ def main():
             # hi*Wlo, none redundant): the roofline counts them; fp32_equivalent_tflops is the 1x figure
             alg_flop *= 3.0
             tf *= 3.0
+        if args.precision == "f16f8":
+            # one fp16 product plus two fp8 products (K-concatenated into one kind::f8f6f4 pass at twice the f16 rate)
+            # per fp32-grade product: 2 bf16-pass-equivalents of tensor-pipe time.  `achieved` is that bf16-time-
+            # equivalent rate, comparable with the measured bf16 peak; the raw issued rate is 1.5x higher.
+            alg_flop *= 2.0
+            tf *= 2.0
         peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
         line["roofline"] = {
             "kernel": "conv_tc / conv_halo / conv_halo2 kernels (tcgen05 implicit GEMM, all %d conv launches of one step)"
@@ -375,6 +384,9 @@ def main():
             "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step, "fp32_equivalent_tflops": fp32_equiv_tf,
             "peak_source": "%s bf16 sustained%s" % (peaks["source"], " x 0.5 for tf32" if tf32 else ""),
             "issued_tflops_incl_padding": issued_flop / (conv_ms * 1e-3) / 1e12,
+            "achieved_note": {"bf16x3": "3 bf16 passes per product counted", "f16f8": "bf16-time-equivalent: fp16 pass + "
+                              "fp8 pass (2 products at 2x rate) = 2 units per product; raw issued FLOP/s = 1.5 x achieved",
+                              }.get(args.precision, "1 pass per product"),
         }
         # cost volume at BASELINE config 2: NCHW fp32, batch 5, 2 views
         refd, srcd = st["ref"], st["src"].view(V * B, 3, H, W)
@@ -412,7 +424,7 @@ def main():
                                     "algorithmic_bytes": nb}
         # the other tensor-core modes, same workload, same timing method (kept out of the headline value)
         line["other_modes"] = []
-        others = [m for m in ("bf16", "tf32", "bf16x3") if m != args.precision]
+        others = [m for m in ("bf16", "tf32", "bf16x3", "f16f8") if m != args.precision]
         if args.workload != "c4":
             others = []   # one mode at a time at 640x480 x 32: a plan holds ~60-120 GB of activations
         for other in others:

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcnmnet_b200.so")
 
-CNM_BF16, CNM_TF32, CNM_BF16X3 = 0, 1, 2
+CNM_BF16, CNM_TF32, CNM_BF16X3, CNM_F16F8 = 0, 1, 2, 3
 VOLUME_NCHW_F32, VOLUME_ACT = 0, 1
 
 
@@ -25,7 +25,8 @@ class ConvStep(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
                 ("c_out_total", C.c_int32), ("c_out_offset", C.c_int32), ("stride", C.c_int32), ("relu", C.c_int32),
-                ("num_srcs", C.c_int32), ("num_steps", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32)]
+                ("num_srcs", C.c_int32), ("num_steps", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
+                ("acc_exp", C.c_int32), ("reserved2", C.c_int32 * 3)]
 
 
 _P, _I, _D, _F, _L = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int64

@@ -1,6 +1,8 @@
 // Shared helpers for the cnmnet_b200 CUDA sources (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,8 +40,9 @@ inline int after_launch(const char* what) {
 // K-chunk in PHYSICAL channels (one 128-byte operand row) and bytes per physical element
 inline int chunk_channels(int dtype) { return dtype == CNM_TF32 ? 32 : 64; }
 inline int elem_bytes(int dtype) { return dtype == CNM_TF32 ? 4 : 2; }
-// physical channels per logical channel: CNM_BF16X3 stores every value as a (hi, lo) pair of bf16
-inline int phys_factor(int dtype) { return dtype == CNM_BF16X3 ? 2 : 1; }
+// physical channels per logical channel: CNM_BF16X3 stores every value as a (hi, lo) pair of bf16, CNM_F16F8 as
+// fp16 hi + two fp8 bytes
+inline int phys_factor(int dtype) { return (dtype == CNM_BF16X3 || dtype == CNM_F16F8) ? 2 : 1; }
 
 // ---- act element access (T = __nv_bfloat16 or float) ----
 template <typename T>
@@ -91,6 +94,37 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// Element of a CNM_F16F8 act tensor (include/cnmnet_b200.h): hi = fp16(v) in the chunk's 128-byte fp16 row; the next
+// 128-byte row holds lo8 = e4m3((v - hi) * 2^7) for the 64 channels, then hi8 = e4m3(hi * 2^-4).  Readers other than
+// the tensor cores reconstruct v = hi + lo8 * 2^-7.  Chunk rows start on 128-byte boundaries.
+struct h16f8 {
+  __half v;
+};
+template <>
+struct ActTraits<h16f8> {
+  static constexpr bool SPLIT = true;
+  static constexpr int CHUNK = 64;
+  __host__ __device__ static constexpr size_t phys(size_t c) { return ((c >> 6) << 7) + (c & 63); }
+  __host__ __device__ static constexpr size_t pstride(size_t C) { return 2 * C; }
+};
+constexpr float F8_LO_SCALE = 128.0f, F8_HI_SCALE = 0.0625f;
+
+__device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
+__device__ __forceinline__ uint32_t e4m3x2(float a, float b) {  // a -> low byte, b -> high byte
+  return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t v) {
+  const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)v, __NV_E4M3);
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+// the three stored parts of one value
+__device__ __forceinline__ void split_f16f8(float v, __half& hi, float& lo_scaled, float& hi_scaled) {
+  hi = __float2half_rn(sat_f16(v));
+  const float h = __half2float(hi);
+  lo_scaled = (v - h) * F8_LO_SCALE;
+  hi_scaled = h * F8_HI_SCALE;
+}
+
 // scalar access to logical channel c of the pixel starting at `px`
 template <typename T>
 __device__ __forceinline__ float load_scalar(const T* px, size_t c) { return to_f<T>(px[c]); }
@@ -99,8 +133,24 @@ __device__ __forceinline__ float load_scalar<bf16s>(const bf16s* px, size_t c) {
   const size_t q = ActTraits<bf16s>::phys(c);
   return __bfloat162float(px[q].v) + __bfloat162float(px[q + 64].v);
 }
+template <>
+__device__ __forceinline__ float load_scalar<h16f8>(const h16f8* px, size_t c) {
+  const size_t q = ActTraits<h16f8>::phys(c);
+  const uint8_t* row8 = reinterpret_cast<const uint8_t*>(px + (q & ~(size_t)63) + 64);
+  return __half2float(px[q].v) + e4m3x2_to_float2(row8[c & 63]).x * (1.0f / F8_LO_SCALE);
+}
 template <typename T>
 __device__ __forceinline__ void store_scalar(T* px, size_t c, float v) { px[c] = from_f<T>(v); }
+template <>
+__device__ __forceinline__ void store_scalar<h16f8>(h16f8* px, size_t c, float v) {
+  const size_t q = ActTraits<h16f8>::phys(c);
+  uint8_t* row8 = reinterpret_cast<uint8_t*>(px + (q & ~(size_t)63) + 64);
+  float lo, hs;
+  split_f16f8(v, px[q].v, lo, hs);
+  const uint32_t pr = e4m3x2(lo, hs);
+  row8[c & 63] = (uint8_t)(pr & 0xff);
+  row8[64 + (c & 63)] = (uint8_t)(pr >> 8);
+}
 template <>
 __device__ __forceinline__ void store_scalar<bf16s>(bf16s* px, size_t c, float v) {
   const size_t q = ActTraits<bf16s>::phys(c);
@@ -164,6 +214,50 @@ struct Vec16<bf16s> {
     }
     Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(p), hi);
     Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(p) + 64, lo);
+  }
+};
+
+// fp16 + fp8: p points at the 8-channel hi vector (16 B); the matching 8 lo8 bytes sit in the fp8 row that follows the
+// chunk's fp16 row, the 8 hi8 bytes 64 further.  The channel offset inside the chunk comes from the address (chunk rows
+// are 128-byte aligned).
+template <>
+struct Vec16<h16f8> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ const uint8_t* row8(const h16f8* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uintptr_t j = (a & 127) >> 1;  // channel offset of the vector inside its 64-channel chunk
+    return reinterpret_cast<const uint8_t*>(a - 2 * j + 128 + j);
+  }
+  __device__ static __forceinline__ void load(const h16f8* p, float* f) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint2 l = *reinterpret_cast<const uint2*>(row8(p));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t lw[4] = {l.x & 0xffffu, l.x >> 16, l.y & 0xffffu, l.y >> 16};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      const float2 lo = e4m3x2_to_float2(lw[i]);
+      f[2 * i] = h.x + lo.x * (1.0f / F8_LO_SCALE);
+      f[2 * i + 1] = h.y + lo.y * (1.0f / F8_LO_SCALE);
+    }
+  }
+  __device__ static __forceinline__ void store(h16f8* p, const float* f) {
+    uint32_t w[4], lo[4], hs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half h0, h1;
+      float l0, l1, s0, s1;
+      split_f16f8(f[2 * i], h0, l0, s0);
+      split_f16f8(f[2 * i + 1], h1, l1, s1);
+      const __half2 h = __halves2half2(h0, h1);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[i] = e4m3x2(l0, l1);
+      hs[i] = e4m3x2(s0, s1);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    uint8_t* r8 = const_cast<uint8_t*>(row8(p));
+    *reinterpret_cast<uint2*>(r8) = make_uint2(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16));
+    *reinterpret_cast<uint2*>(r8 + 64) = make_uint2(hs[0] | (hs[1] << 16), hs[2] | (hs[3] << 16));
   }
 };
 

@@ -38,7 +38,8 @@ struct alignas(64) HaloParams {
   int map_rows[HL_MAX_SRCS * 4];  // slab height (16 + vertical tap span), per map
   int relu;
   int c_out_offset;
-  int split;  // CNM_BF16X3: every 64-column chunk is stored as a hi row and a lo row (2 x 128 B per pixel)
+  int mode;         // EPI_PLAIN / EPI_BF16X3 / EPI_F16F8: the split modes store two 128-byte rows per 64-column chunk
+  float acc_scale;  // 2^-acc_exp
 };
 
 template <int BN, bool TF32>
@@ -49,8 +50,11 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   constexpr int ACC_STAGES = (4 * BN <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (2 * BN * ACC_STAGES) < 32 ? 32 : 2 * BN * ACC_STAGES;
   constexpr int B_BYTES = BN * 128;
-  constexpr uint32_t IDESC = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t IDESC = IDESC_SHAPE | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10);
+  // CNM_F16F8: operand formats 0 = fp16 (kind::f16) on even groups and 0 = e4m3 (kind::f8f6f4) on odd ones
+  const bool mixed = !TF32 && p.mode == EPI_F16F8;
+  const uint32_t idesc = mixed ? IDESC_SHAPE : IDESC;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -168,9 +172,15 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
             if (elect_one()) {
               const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
               const uint64_t adesc = adesc0 + (uint64_t)(t * (2048 >> 4));
+              if (mixed && (g & 1)) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (first && k == 0) ? 0u : 1u);
+                for (int k = 0; k < 4; ++k)
+                  tc_mma_f8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+              }
               tc_commit(emptyB(sb));
               if (t == ntaps - 1) tc_commit(emptyA(sa));
             }
@@ -217,48 +227,17 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
           tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
           if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
           tmem_ld_wait();
-          for (int part = 0; part < (p.split ? 2 : 1); ++part) {
-          // one staging buffer (smem goes to deeper operand rings): the previous TMA store must have finished
+          for (int part = 0; part < (p.mode ? 2 : 1); ++part) {
+            // one staging buffer (smem goes to deeper operand rings): the previous TMA store must have finished
             // reading it; the epilogue runs under the next tile's main loop, so this wait is off the critical path
             uint8_t* stg = base_ptr + off_out;
             if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             epi_bar();
-            const float* bs = bias_s + ch * COLS_PER_CHUNK;
-            uint8_t* rowp = stg + row * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              uint4 o;
-              if (TF32) {
-                float f[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
-                  if (p.relu) t = fmaxf(t, 0.0f);
-                  f[e] = round_tf32(t);
-                }
-                o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-              } else {
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
-                  float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
-                  if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
-                  if (part) {  // lo pass of the split-bf16 output: what the hi pass rounded away
-                  t0 -= __bfloat162float(__float2bfloat16_rn(t0));
-                  t1 -= __bfloat162float(__float2bfloat16_rn(t1));
-                }
-                __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
-                  w[e] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                o = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-              *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
-            }
+            epi_store_row<TF32>(v, bias_s + ch * COLS_PER_CHUNK, stg + row * 128, row, p.relu, p.mode, part, p.acc_scale);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             epi_bar();
             if (leader) {
-              tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.split ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
+              tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.mode ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
                                    x0, y0 + 8 * half, n0);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
@@ -349,7 +328,8 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   p.num_steps = d->num_steps;
   p.relu = d->relu;
   p.c_out_offset = d->c_out_offset;
-  p.split = d->dtype == CNM_BF16X3;
+  p.mode = d->dtype == CNM_BF16X3 ? EPI_BF16X3 : (d->dtype == CNM_F16F8 ? EPI_F16F8 : EPI_PLAIN);
+  p.acc_scale = ldexpf(1.0f, -d->acc_exp);
   // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
   // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
   // lasts ntaps B tiles.
@@ -415,7 +395,7 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   const int total = m_tiles * p.tiles_n;
   const int grid = total < 148 ? total : 148;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool tf32 = d->dtype == CNM_TF32;  // CNM_BF16 and CNM_BF16X3 both run the kind::f16 kernels
+  const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
   if (BN == 256) return tf32 ? launch_halo<256, true>(p, grid, smem, s) : launch_halo<256, false>(p, grid, smem, s);
   if (BN == 128) return tf32 ? launch_halo<128, true>(p, grid, smem, s) : launch_halo<128, false>(p, grid, smem, s);
   return tf32 ? launch_halo<64, true>(p, grid, smem, s) : launch_halo<64, false>(p, grid, smem, s);

@@ -13,6 +13,7 @@ struct SimtSrc {
 struct SimtParams {
   SimtSrc srcs[4];
   int N, Ho, Wo, Cout, c_out_total, c_out_offset, stride, relu, num_steps, split;
+  float acc_scale;
 };
 
 constexpr int SM_TM = 64, SM_TN = 64;
@@ -87,11 +88,89 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// CNM_F16F8 twin: even K-steps are fp16 rows (64 channels) against fp16 weight columns, odd K-steps are fp8 rows
+// (128 e4m3 bytes: lo8 x 64 | hi8 x 64) against 128 e4m3 weight bytes; everything accumulates in fp32 and is scaled by
+// 2^-acc_exp, exactly the arithmetic the two tensor-core passes perform.
+__global__ void __launch_bounds__(256)
+    conv_simt_f16f8_kernel(SimtParams p, const cnm_conv_step* __restrict__ steps, const uint8_t* __restrict__ wp,
+                           const float* __restrict__ bias, h16f8* __restrict__ out) {
+  constexpr int CH = 64;
+  __shared__ float As[SM_TM][CH + 1];
+  __shared__ float Bs[SM_TN][CH + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const size_t M = (size_t)p.N * p.Ho * p.Wo;
+  const size_t m0 = (size_t)blockIdx.x * SM_TM;
+  const int n0 = blockIdx.y * SM_TN;
+  const size_t Kbytes = (size_t)p.num_steps * 128;
+  float acc[4][4] = {};
+  for (int st = 0; st < p.num_steps; ++st) {
+    const cnm_conv_step s = steps[st];
+    const SimtSrc src = p.srcs[s.src];
+    const int py = (s.sub >> 1) & 1, px = s.sub & 1;
+    const bool f8 = st & 1;
+    for (int sub = 0; sub < (f8 ? 2 : 1); ++sub) {
+      for (int i = threadIdx.x; i < SM_TM * CH; i += 256) {
+        const int r = i / CH, c = i % CH;
+        const size_t m = m0 + r;
+        float v = 0.0f;
+        if (m < M) {
+          const int ox = (int)(m % p.Wo), oy = (int)((m / p.Wo) % p.Ho), n = (int)(m / ((size_t)p.Wo * p.Ho));
+          int iy = oy + s.dy, ix = ox + s.dx;
+          if (p.stride == 2) { iy = 2 * iy + py; ix = 2 * ix + px; }
+          if (iy >= 0 && iy < src.H && ix >= 0 && ix < src.W) {
+            const uint8_t* row = reinterpret_cast<const uint8_t*>(src.ptr) +
+                                 ((((size_t)n * src.H + iy) * src.W + ix) * src.C + s.c0) * 2;
+            v = f8 ? e4m3x2_to_float2(row[sub * 64 + c]).x : __half2float(reinterpret_cast<const __half*>(row)[c]);
+          }
+        }
+        As[r][c] = v;
+      }
+      for (int i = threadIdx.x; i < SM_TN * CH; i += 256) {
+        const int r = i / CH, c = i % CH;
+        float v = 0.0f;
+        if (n0 + r < p.Cout) {
+          const uint8_t* row = wp + (size_t)(n0 + r) * Kbytes + (size_t)st * 128;
+          v = f8 ? e4m3x2_to_float2(row[sub * 64 + c]).x : __half2float(reinterpret_cast<const __half*>(row)[c]);
+        }
+        Bs[r][c] = v;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < CH; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = As[ty * 4 + i][k]; b[i] = Bs[tx * 4 + i][k]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= p.Cout) continue;
+      float v = fmaf(acc[i][j], p.acc_scale, bias ? __ldg(bias + co) : 0.0f);
+      if (p.relu) v = fmaxf(v, 0.0f);
+      store_scalar<h16f8>(out + m * p.c_out_total + p.c_out_offset, co, v);
+    }
+  }
+}
+
 int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* srcs, const void* steps, const void* wp,
                     const void* out) {
   CNM_REQUIRE(d && srcs && steps && wp && out, CNM_ERR_INVALID_ARGUMENT, "%s: null pointer", fn);
-  CNM_REQUIRE(d->dtype == CNM_BF16 || d->dtype == CNM_TF32 || d->dtype == CNM_BF16X3, CNM_ERR_INVALID_ARGUMENT,
-              "%s: dtype %d", fn, d->dtype);
+  CNM_REQUIRE(d->dtype == CNM_BF16 || d->dtype == CNM_TF32 || d->dtype == CNM_BF16X3 || d->dtype == CNM_F16F8,
+              CNM_ERR_INVALID_ARGUMENT, "%s: dtype %d", fn, d->dtype);
+  CNM_REQUIRE(d->dtype == CNM_F16F8 ? (d->acc_exp >= -60 && d->acc_exp <= 60 && d->num_steps % 2 == 0) : d->acc_exp == 0,
+              CNM_ERR_INVALID_ARGUMENT, "%s: acc_exp %d / num_steps %d do not fit dtype %d", fn, d->acc_exp, d->num_steps,
+              d->dtype);
   CNM_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->Cout > 0, CNM_ERR_INVALID_ARGUMENT, "%s: bad output shape", fn);
   CNM_REQUIRE(d->stride == 1 || d->stride == 2, CNM_ERR_UNSUPPORTED_SHAPE, "%s: stride %d", fn, d->stride);
   CNM_REQUIRE(d->num_srcs >= 1 && d->num_srcs <= 3, CNM_ERR_UNSUPPORTED_SHAPE, "%s: num_srcs %d (max 3)", fn, d->num_srcs);
@@ -131,9 +210,12 @@ extern "C" int cnm_conv2d_simt(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   p.c_out_total = d->c_out_total; p.c_out_offset = d->c_out_offset;
   p.stride = d->stride; p.relu = d->relu; p.num_steps = d->num_steps;
   p.split = d->dtype == CNM_BF16X3;
+  p.acc_scale = ldexpf(1.0f, -d->acc_exp);
   const size_t M = (size_t)d->N * d->Ho * d->Wo;
   dim3 grid((unsigned)((M + SM_TM - 1) / SM_TM), (d->Cout + SM_TN - 1) / SM_TN);
-  if (d->dtype != CNM_TF32)
+  if (d->dtype == CNM_F16F8)
+    conv_simt_f16f8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, steps, (const uint8_t*)wp, bias, (h16f8*)out);
+  else if (d->dtype != CNM_TF32)
     conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p, steps, (const __nv_bfloat16*)wp, bias,
                                                                            (__nv_bfloat16*)out);
   else

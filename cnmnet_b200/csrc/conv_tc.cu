@@ -40,7 +40,8 @@ struct alignas(64) TcParams {
   int TW, TH, NB;
   int relu;
   int c_out_offset;
-  int split;  // CNM_BF16X3: every 64-column chunk is stored as a hi row and a lo row (2 x 128 B per pixel)
+  int mode;         // EPI_PLAIN / EPI_BF16X3 / EPI_F16F8: the split modes store two 128-byte rows per 64-column chunk
+  float acc_scale;  // 2^-acc_exp
 };
 
 template <int BN, int STAGES, bool TF32>
@@ -63,8 +64,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr int CHUNK_CH = TF32 ? 32 : 64;        // channels per K-step
   constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
   constexpr uint32_t TMEM_COLS = 2 * BN;          // 128 / 256 / 512: powers of two >= 32
-  constexpr uint32_t IDESC = (1u << 4) | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t IDESC = IDESC_SHAPE | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10);
+  // CNM_F16F8: operand formats 0 = fp16 (kind::f16) on even K-steps and 0 = e4m3 (kind::f8f6f4) on odd ones
+  const bool mixed = !TF32 && p.mode == EPI_F16F8;
+  const uint32_t idesc = mixed ? IDESC_SHAPE : IDESC;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -153,9 +157,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (elect_one()) {
             const uint32_t sa = base + stage * L::STAGE_BYTES;
             const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + TC_A_BYTES);
+            if (mixed && (ks & 1)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // 4 x 32 B along K inside the 128 B swizzle row
-              tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (ks | k) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                tc_mma_f8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // 4 x 32 B along K inside the 128 B swizzle row
+                tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
+            }
             tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
             if (ks == p.num_steps - 1) tc_commit(tfull_bar(as));  // accumulator complete
           }
@@ -197,50 +207,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
         if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
         tmem_ld_wait();
-        for (int part = 0; part < (p.split ? 2 : 1); ++part) {
+        for (int part = 0; part < (p.mode ? 2 : 1); ++part) {
           const uint32_t buf = chunk_counter & 1;
           uint8_t* stg = base_ptr + L::OFF_OUT + buf * TC_A_BYTES;
           // the TMA store that last read this staging buffer (two stores ago) must have finished reading
           if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           epi_bar();
-          const float* bs = bias_s + ch * COLS_PER_CHUNK;
-          uint8_t* rowp = stg + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {  // 8 x 16 B per output row, 128B-swizzled like the TMA box
-            uint4 o;
-            if (TF32) {
-              float f[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float t = __uint_as_float(v[4 * j + e]) + bs[4 * j + e];
-                if (p.relu) t = fmaxf(t, 0.0f);
-                uint32_t r;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(t));  // store tf32-rounded activations
-                f[e] = __uint_as_float(r);
-              }
-              o = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-            } else {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float t0 = __uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e];
-                float t1 = __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1];
-                if (p.relu) { t0 = fmaxf(t0, 0.0f); t1 = fmaxf(t1, 0.0f); }
-                if (part) {  // lo pass of the split-bf16 output: what the hi pass rounded away
-                  t0 -= __bfloat162float(__float2bfloat16_rn(t0));
-                  t1 -= __bfloat162float(__float2bfloat16_rn(t1));
-                }
-                __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
-                w[e] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              o = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
-          }
+          epi_store_row<TF32>(v, bias_s + ch * COLS_PER_CHUNK, stg + row * 128, row, p.relu, p.mode, part, p.acc_scale);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
           epi_bar();
           if (leader) {
-            tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.split ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
+            tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.mode ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
                                  x0, y0, n0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -361,7 +338,8 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.num_steps = d->num_steps;
   p.relu = d->relu;
   p.c_out_offset = d->c_out_offset;
-  p.split = d->dtype == CNM_BF16X3;
+  p.mode = d->dtype == CNM_BF16X3 ? EPI_BF16X3 : (d->dtype == CNM_F16F8 ? EPI_F16F8 : EPI_PLAIN);
+  p.acc_scale = ldexpf(1.0f, -d->acc_exp);
 
   const uint32_t box[4] = {(uint32_t)ch, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.NB};
   for (int i = 0; i < d->num_srcs; ++i) {
@@ -403,7 +381,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   const int total = m_tiles * p.tiles_n;
   const int grid = total < 148 ? total : 148;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool tf32 = d->dtype == CNM_TF32;  // CNM_BF16 and CNM_BF16X3 both run the kind::f16 kernels
+  const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
   if (BN == 256) return tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
   if (BN == 128) return tf32 ? launch_tc<128, 6, true>(p, grid, s) : launch_tc<128, 6, false>(p, grid, s);
   return tf32 ? launch_tc<64, 8, true>(p, grid, s) : launch_tc<64, 8, false>(p, grid, s);

@@ -122,7 +122,7 @@ __global__ void pack_source_kernel(const float* __restrict__ src, float4* __rest
 // ---------------------------------------------------------------------------------------------
 constexpr int CV_TX = 32, CV_TY = 8;
 
-template <int DPB, int LAYOUT>  // LAYOUT: 0 = NCHW fp32, 1 = act bf16, 2 = act fp32 (tf32), 3 = act split bf16
+template <int DPB, int LAYOUT>  // LAYOUT: 0 = NCHW fp32, 1 = act bf16, 2 = act fp32 (tf32), 3 = act split bf16, 4 = act fp16 + fp8
 __global__ void __launch_bounds__(CV_TX* CV_TY)
     cost_volume_kernel(const float* __restrict__ ref, const float4* __restrict__ tex, const float* __restrict__ hk,
                        void* __restrict__ out, int B, int H, int W, int D, double idmin, double idstep) {
@@ -192,11 +192,16 @@ __global__ void __launch_bounds__(CV_TX* CV_TY)
     float* o = reinterpret_cast<float*>(out) + ((size_t)p * HW + (size_t)y * W + x) * D + d0;
 #pragma unroll
     for (int i = 0; i < DPB; i += 4) Vec16<float>::store(o + i, res + i);
-  } else {  // split bf16: planes [d0, d0+DPB) of the pixel's hi row, the lo row 64 physical channels further
+  } else if (LAYOUT == 3) {  // split bf16: planes [d0, d0+DPB) of the pixel's hi row, the lo row 64 physical channels further
     bf16s* o = reinterpret_cast<bf16s*>(out) + ((size_t)p * HW + (size_t)y * W + x) * ActTraits<bf16s>::pstride(D) +
                ActTraits<bf16s>::phys(d0);
 #pragma unroll
     for (int i = 0; i < DPB; i += 8) Vec16<bf16s>::store(o + i, res + i);
+  } else {  // fp16 + fp8: fp16 row, then the lo8 / hi8 bytes of the chunk's fp8 row
+    h16f8* o = reinterpret_cast<h16f8*>(out) + ((size_t)p * HW + (size_t)y * W + x) * ActTraits<h16f8>::pstride(D) +
+               ActTraits<h16f8>::phys(d0);
+#pragma unroll
+    for (int i = 0; i < DPB; i += 8) Vec16<h16f8>::store(o + i, res + i);
   }
 }
 
@@ -254,6 +259,8 @@ extern "C" int cnm_cost_volume(const float* ref, const void* packed_src, const f
     cost_volume_kernel<DPB, 2><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else if (dtype == CNM_BF16X3)
     cost_volume_kernel<DPB, 3><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+  else if (dtype == CNM_F16F8)
+    cost_volume_kernel<DPB, 4><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else
     return fail(CNM_ERR_INVALID_ARGUMENT, "cnm_cost_volume: dtype %d", dtype);
   return after_launch("cnm_cost_volume");

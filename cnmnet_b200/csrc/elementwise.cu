@@ -388,6 +388,7 @@ using namespace cnm;
   if ((dtype) == CNM_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
   else if ((dtype) == CNM_TF32) { using T = float; __VA_ARGS__; }    \
   else if ((dtype) == CNM_BF16X3) { using T = bf16s; __VA_ARGS__; }  \
+  else if ((dtype) == CNM_F16F8) { using T = h16f8; __VA_ARGS__; }   \
   else return fail(CNM_ERR_INVALID_ARGUMENT, "%s: dtype %d", __func__, (int)(dtype));
 
 extern "C" int cnm_nchw_to_act(const float* src, void* dst, int N, int C, int H, int W, int c_dst_total,

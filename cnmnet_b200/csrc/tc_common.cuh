@@ -71,6 +71,12 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
                  : "memory");
 }
+// kind::f8f6f4 (e4m3 x e4m3 here): K = 32 elements = 32 bytes per instruction, twice the kind::f16 rate
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+               : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets row (lane base + t)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -94,6 +100,69 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
          ((uint64_t)2 << 61) /* SWIZZLE_128B */;
 }
 
+// ---- epilogue: one 128-byte output row of this thread's pixel -> 128B-swizzled staging tile ---------------------
+// v = the chunk's accumulator columns (64, or 32 for tf32), bs = their bias.  value = relu(acc * scale + bias).
+// mode 0: plain bf16 / tf32 row.  mode 1 (CNM_BF16X3): part 0 = bf16 hi row, part 1 = bf16 lo row.
+// mode 2 (CNM_F16F8): part 0 = fp16 row, part 1 = fp8 row [lo8 x 64 | hi8 x 64].
+enum { EPI_PLAIN = 0, EPI_BF16X3 = 1, EPI_F16F8 = 2 };
+
+template <bool TF32>
+__device__ __forceinline__ void epi_store_row(const uint32_t* v, const float* bs, uint8_t* rowp, int row, int relu,
+                                              int mode, int part, float scale) {
+  auto val = [&](int c) {
+    float t = fmaf(__uint_as_float(v[c]), scale, bs[c]);
+    return relu ? fmaxf(t, 0.0f) : t;
+  };
+  if (TF32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) f[e] = round_tf32(val(4 * j + e));  // store tf32-rounded activations
+      *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+          make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+  } else if (mode == EPI_F16F8 && part == 1) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // 16 channels -> 16 lo8 bytes (piece j) and 16 hi8 bytes (piece j + 4)
+      uint32_t lw[4], hw[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo[4], hs[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half h;
+          split_f16f8(val(16 * j + 4 * e + i), h, lo[i], hs[i]);
+        }
+        lw[e] = e4m3x2(lo[0], lo[1]) | (e4m3x2(lo[2], lo[3]) << 16);
+        hw[e] = e4m3x2(hs[0], hs[1]) | (e4m3x2(hs[2], hs[3]) << 16);
+      }
+      *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      *reinterpret_cast<uint4*>(rowp + (((j + 4) ^ (row & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t0 = val(8 * j + 2 * e), t1 = val(8 * j + 2 * e + 1);
+        if (mode == EPI_F16F8) {
+          const __half2 h = __floats2half2_rn(sat_f16(t0), sat_f16(t1));
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        } else {
+          if (part) {  // lo row of the split-bf16 output: what the hi row rounded away
+            t0 -= __bfloat162float(__float2bfloat16_rn(t0));
+            t1 -= __bfloat162float(__float2bfloat16_rn(t1));
+          }
+          const __nv_bfloat162 h = __floats2bfloat162_rn(t0, t1);
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      }
+      *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
 int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,

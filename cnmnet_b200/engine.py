@@ -14,14 +14,15 @@ from collections import namedtuple
 import torch
 
 from . import _lib
-from ._lib import CNM_BF16, CNM_BF16X3, CNM_TF32
+from ._lib import CNM_BF16, CNM_BF16X3, CNM_F16F8, CNM_TF32
 
 BN_EPS = 1e-5
 # which stride-1 layers use the row-halo kernel: "auto" (enough tiles for a wave), "force" (every eligible layer,
 # used by tests), "off" (per-tap kernel everywhere)
 HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
-TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32, CNM_BF16X3: torch.bfloat16}
+TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32, CNM_BF16X3: torch.bfloat16, CNM_F16F8: torch.float16}
+F8_LO_SCALE, F8_HI_SCALE = 128.0, 0.0625   # csrc/common.cuh: lo8 = e4m3((v - hi) * 2^7), hi8 = e4m3(hi * 2^-4)
 
 
 def chunk_channels(dtype):
@@ -32,11 +33,19 @@ def chunk_channels(dtype):
 def phys_factor(dtype):
     """Physical channels per logical channel: CNM_BF16X3 stores every value as a (hi, lo) bf16 pair, laid out as a
     128-byte hi row followed by a 128-byte lo row per 64-channel logical chunk (see csrc/common.cuh: bf16s)."""
-    return 2 if dtype == CNM_BF16X3 else 1
+    return 2 if dtype in (CNM_BF16X3, CNM_F16F8) else 1
 
 
-# (activation part, weight part) passes of one logical K-chunk: x*w ~ hi*Whi + lo*Whi + hi*Wlo for split bf16
+# (activation part, weight part) passes of one logical K-chunk: x*w ~ hi*Whi + lo*Whi + hi*Wlo for split bf16;
+# fp16 row x fp16 weights, then fp8 row [lo8 | hi8] x fp8 weights [Whi8 | Wlo8] for CNM_F16F8 (both rows 64 physical
+# channels apart, like the hi / lo rows of split bf16)
 SPLIT_PASSES = (("hi", "hi"), ("lo", "hi"), ("hi", "lo"))
+F16F8_PASSES = (("hi", "h16"), ("lo", "f8"))
+
+
+def split_passes(dtype):
+    """False for the one-row dtypes, else the pass list of the two-row (split) act layouts."""
+    return SPLIT_PASSES if dtype == CNM_BF16X3 else (F16F8_PASSES if dtype == CNM_F16F8 else False)
 
 
 def parse_dtype(d):
@@ -46,7 +55,9 @@ def parse_dtype(d):
         return CNM_TF32
     if d in (CNM_BF16X3, "bf16x3"):
         return CNM_BF16X3
-    raise ValueError("precision must be 'bf16', 'tf32' or 'bf16x3', got %r" % (d,))
+    if d in (CNM_F16F8, "f16f8"):
+        return CNM_F16F8
+    raise ValueError("precision must be 'bf16', 'tf32', 'bf16x3' or 'f16f8', got %r" % (d,))
 
 
 def round_tf32(t):
@@ -78,7 +89,8 @@ def act_src(buf, wch, C=None, coff=0, phys=1):
 
 
 def _chunk_passes(split):
-    return SPLIT_PASSES if split else ((None, None),)
+    """`split` is False or a pass list (split_passes); True means split bf16."""
+    return (SPLIT_PASSES if split is True else split) if split else ((None, None),)
 
 
 def _pc0(c_logical, apart, split):
@@ -170,18 +182,15 @@ def make_groups(srcs, k, ch, stride=1, split=False):
     return groups, cols, info
 
 
-def pack_weights(wf, cols, ch, dtype):
-    """Folded weights [Cout, Cin, k, k] -> K-major operand [Cout, len(cols)*ch] in the act dtype.  For CNM_BF16X3 a
-    column block holds either Whi = bf16(w) or Wlo = bf16(w - Whi), as its recipe says."""
-    cout, _, k, _ = wf.shape
-    parts = {None: wf, "hi": wf, "lo": wf}
-    if dtype == CNM_BF16X3:
-        whi = wf.to(torch.bfloat16).float()
-        parts = {"hi": whi, "lo": wf - whi}
-    wp = torch.zeros((cout, len(cols) * ch), dtype=torch.float32, device=wf.device)
+def _gather_cols(w, cols, ch, want=None):
+    """[Cout, Cin, k, k] -> [Cout, len(cols)*ch] fp32 by the per-step recipes; with `want`, only the column blocks whose
+    weight part is in `want` are filled."""
+    cout, _, k, _ = w.shape
+    wp = torch.zeros((cout, len(cols) * ch), dtype=torch.float32, device=w.device)
     for i, col in enumerate(cols):
+        if want is not None and (col[4] if len(col) > 4 else None) not in want:
+            continue
         base = i * ch
-        w = parts[col[4] if len(col) > 4 else None]
         if col[0] == "act":
             _, c, r, t = col[:4]
             wp[:, base:base + ch] = w[:, c:c + ch, r, t]
@@ -191,6 +200,52 @@ def pack_weights(wf, cols, ch, dtype):
         else:
             _, wch, n, _ = col[:4]
             wp[:, base:base + 9 * n] = w[:, wch:wch + n].reshape(cout, 9 * n)
+    return wp
+
+
+def _e4m3(t):
+    return t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+
+
+def f16f8_weight_exp(wf):
+    """acc_exp e of CNM_F16F8 weights: the largest power of two with max|w| * 2^(e-7) <= 448 (e4m3 range), which also
+    keeps w * 2^e <= 57344 inside fp16."""
+    m = float(wf.abs().max())
+    if m == 0.0:
+        return 0
+    import math
+    return int(math.floor(math.log2(448.0 / m))) + 7
+
+
+def pack_weights(wf, cols, ch, dtype, acc_exp=None):
+    """Folded weights [Cout, Cin, k, k] -> K-major operand [Cout, len(cols)*ch] in the act dtype.  For CNM_BF16X3 a
+    column block holds either Whi = bf16(w) or Wlo = bf16(w - Whi), as its recipe says.  For CNM_F16F8 (include/
+    cnmnet_b200.h) an 'h16' block is W16 = fp16(w * 2^e) and an 'f8' block is 128 bytes [e4m3(w * 2^(e-7)) x 64 |
+    e4m3((w * 2^e - W16) * 2^4) x 64]; e = acc_exp (default f16f8_weight_exp(wf))."""
+    if dtype == CNM_F16F8:
+        e = f16f8_weight_exp(wf) if acc_exp is None else acc_exp
+        ws = wf * (2.0 ** e)
+        w16 = ws.clamp(-65504.0, 65504.0).to(torch.float16)
+        cout = wf.shape[0]
+        out = torch.zeros((cout, len(cols), 128), dtype=torch.uint8, device=wf.device)
+        h16 = _gather_cols(w16.float(), cols, ch, ("h16",)).to(torch.float16).view(cout, len(cols), ch)
+        hi8 = _e4m3(_gather_cols(ws / F8_LO_SCALE, cols, ch, ("f8",))).view(cout, len(cols), ch)
+        lo8 = _e4m3(_gather_cols((ws - w16.float()) / F8_HI_SCALE, cols, ch, ("f8",))).view(cout, len(cols), ch)
+        for i, col in enumerate(cols):
+            if col[4] == "h16":
+                out[:, i] = h16[:, i].contiguous().view(torch.uint8)
+            else:
+                out[:, i, :64] = hi8[:, i].contiguous().view(torch.uint8)
+                out[:, i, 64:] = lo8[:, i].contiguous().view(torch.uint8)
+        return out.view(cout, len(cols) * 128).view(torch.float16)
+    parts = {None: wf, "hi": wf, "lo": wf}
+    if dtype == CNM_BF16X3:
+        whi = wf.to(torch.bfloat16).float()
+        parts = {"hi": whi, "lo": wf - whi}
+    wp = None
+    for part, w in parts.items():
+        blk = _gather_cols(w, cols, ch, (part,))
+        wp = blk if wp is None else wp + blk
     if dtype == CNM_TF32:
         return round_tf32(wp)
     return wp.to(torch.bfloat16).contiguous()
@@ -229,7 +284,7 @@ class ConvOp:
                  backend="tc"):
         self.name, self.k, self.stride, self.dtype = name, k, stride, dtype
         ch = chunk_channels(dtype)
-        split = dtype == CNM_BF16X3
+        split = split_passes(dtype)
         pf = phys_factor(dtype)
         self.srcs = srcs
         self.variants = {}
@@ -261,7 +316,11 @@ class ConvOp:
         for i, s in enumerate(srcs):
             arr[i] = _lib.ConvSrc(_lib.ptr(s.buf), s.buf.shape[1], s.buf.shape[2], s.buf.shape[3], 0)
         self.srcs_arr = arr
-        self.flops = 2.0 * N * Ho * Wo * cout * self.num_steps * ch
+        # issued MACs x 2, padding channels included.  CNM_F16F8: every second K-step is an fp8 row (K = 128);
+        # `flops_bf16_time` weighs those at half (kind::f8f6f4 runs at twice the kind::f16 rate), i.e. it is the
+        # tensor-pipe time of the layer expressed in bf16 FLOPs
+        self.flops = 2.0 * N * Ho * Wo * cout * self.num_steps * ch * (1.5 if dtype == CNM_F16F8 else 1.0)
+        self.flops_bf16_time = 2.0 * N * Ho * Wo * cout * self.num_steps * ch
         self._weights = None
         self.tuned = None
         self.key = repr((dtype, N, Ho, Wo, cout, k, stride, tuple((s.kind, s.C, s.buf.shape[3]) for s in srcs)))
@@ -318,6 +377,8 @@ class ConvOp:
 
     def load(self, wf, bf):
         self._weights = (wf, bf)
+        if self.dtype == CNM_F16F8:
+            self.desc.acc_exp = f16f8_weight_exp(wf)
         self.wp.copy_(pack_weights(wf.to(self.wp.device), self.cols, chunk_channels(self.dtype), self.dtype))
         self.bias.copy_(bf.to(self.bias.device))
 

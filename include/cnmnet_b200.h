@@ -40,10 +40,20 @@ typedef enum cnm_status {
 typedef enum cnm_dtype {
   CNM_BF16 = 0, /* bf16 storage, tcgen05 kind::f16, fp32 accumulate; K-chunk = 64 channels */
   CNM_TF32 = 1, /* fp32 storage, tcgen05 kind::tf32, fp32 accumulate; K-chunk = 32 channels */
-  CNM_BF16X3 = 2 /* split bf16: every value stored as hi + lo bf16 (16 mantissa bits); a convolution runs as three
+  CNM_BF16X3 = 2, /* split bf16: every value stored as hi + lo bf16 (16 mantissa bits); a convolution runs as three
                     kind::f16 passes hi*Whi + lo*Whi + hi*Wlo.  Physical layout: logical channel c of a pixel at
                     physical channel (c/64)*128 + c%64 (hi) and 64 further (lo); act tensors have 2*C physical
                     channels.  Conv descriptors / sources / steps are in PHYSICAL channels; desc.Cout is logical. */
+  CNM_F16F8 = 3   /* fp16 + fp8 corrections: a value v is stored as hi = fp16(v) plus two e4m3 bytes,
+                    lo8 = e4m3((v - hi) * 2^7) and hi8 = e4m3(hi * 2^-4).  Same physical layout as CNM_BF16X3 in
+                    2-byte units: per 64-channel logical chunk a 128-byte fp16 row, then a 128-byte fp8 row
+                    [lo8 x 64 | hi8 x 64].  A convolution runs as TWO passes into one accumulator: kind::f16
+                    hi * W16 and kind::f8f6f4 [lo8 | hi8] * [Whi8 | Wlo8] (K = 128 fp8 elements per 128-byte row,
+                    twice the bf16 rate), with the power-of-two scales folded into the packed weights:
+                    W16 = fp16(w * 2^e), Whi8 = e4m3(w * 2^(e-7)), Wlo8 = e4m3((w * 2^e - W16) * 2^4); the
+                    accumulator is multiplied by 2^-e (desc.acc_exp = e) before bias / ReLU.  K-steps (groups)
+                    alternate fp16 row, fp8 row.  ~22 significand bits for the leading term, corrections good to
+                    ~2^-17 relative: same accuracy class as CNM_BF16X3 at 2/3 of its tensor time. */
 } cnm_dtype;
 
 /* cost-volume output layouts */
@@ -172,6 +182,8 @@ typedef struct cnm_conv_desc {
   int32_t num_srcs, num_steps;
   int32_t dtype; /* cnm_dtype */
   int32_t reserved; /* 0 = library picks the output-channel tile; 64 / 128 / 256 = caller-selected (autotuner) */
+  int32_t acc_exp;  /* the accumulator is scaled by 2^-acc_exp before bias / ReLU (CNM_F16F8 weight scale; else 0) */
+  int32_t reserved2[3];
 } cnm_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM (the product path).  `steps` is a DEVICE array of

@@ -41,7 +41,21 @@ def quantize(x, dtype):
     if dtype == _lib.CNM_BF16X3:
         hi = x.float().to(torch.bfloat16).float()
         return hi + (x.float() - hi).to(torch.bfloat16).float()
+    if dtype == _lib.CNM_F16F8:
+        hi, lo8, _ = f16f8_parts(x)
+        return hi + lo8 / engine.F8_LO_SCALE
     return engine.round_tf32(x.float())
+
+
+def e4m3(t):
+    return t.float().clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+
+
+def f16f8_parts(x):
+    """CNM_F16F8 storage of x (include/cnmnet_b200.h): fp16 hi, e4m3 lo8 = (x - hi) * 2^7, e4m3 hi8 = hi * 2^-4."""
+    x = x.float()
+    hi = x.clamp(-65504.0, 65504.0).to(torch.float16).float()
+    return hi, e4m3((x - hi) * engine.F8_LO_SCALE), e4m3(hi * engine.F8_HI_SCALE)
 
 
 def act_empty(shape, dtype):

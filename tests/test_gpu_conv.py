@@ -6,14 +6,14 @@ import torch
 import torch.nn.functional as F
 
 from cnmnet_b200 import _lib, engine
-from gpu_util import dev, from_act, quantize, rel_l2, to_act
+from gpu_util import dev, e4m3, f16f8_parts, from_act, quantize, rel_l2, to_act
 
 pytestmark = pytest.mark.gpu
 
-DTYPES = [_lib.CNM_BF16, _lib.CNM_TF32, _lib.CNM_BF16X3]
+DTYPES = [_lib.CNM_BF16, _lib.CNM_TF32, _lib.CNM_BF16X3, _lib.CNM_F16F8]
 # operands identical to the oracle's; what differs is fp32 accumulation order and the output rounding of the mode
-MAX_TOL = {_lib.CNM_BF16: 6e-3, _lib.CNM_TF32: 1e-3, _lib.CNM_BF16X3: 5e-5}
-L2_TOL = {_lib.CNM_BF16: 3e-3, _lib.CNM_TF32: 3e-4, _lib.CNM_BF16X3: 2e-5}
+MAX_TOL = {_lib.CNM_BF16: 6e-3, _lib.CNM_TF32: 1e-3, _lib.CNM_BF16X3: 5e-5, _lib.CNM_F16F8: 6e-5}
+L2_TOL = {_lib.CNM_BF16: 3e-3, _lib.CNM_TF32: 3e-4, _lib.CNM_BF16X3: 2e-5, _lib.CNM_F16F8: 2e-5}
 
 
 def run_conv(backend, dtype, xs, wchs, w, b, k, stride, relu=True):
@@ -29,6 +29,16 @@ def run_conv(backend, dtype, xs, wchs, w, b, k, stride, relu=True):
 
 
 def oracle_conv(dtype, xs, w, b, k, stride, relu=True):
+    if dtype == _lib.CNM_F16F8:
+        # the two tensor-core passes on the stored parts: hi * W16 + [lo8 | hi8] * [Whi8 | Wlo8], scaled by 2^-e
+        hi, lo8, hi8 = (t.double() for t in f16f8_parts(torch.cat(xs, 1)))
+        e = engine.f16f8_weight_exp(w)
+        ws = w * (2.0 ** e)
+        w16 = ws.to(torch.float16).float()
+        whi8, wlo8 = e4m3(ws / engine.F8_LO_SCALE), e4m3((ws - w16) / engine.F8_HI_SCALE)
+        conv = lambda a, ww: F.conv2d(a, ww.double(), None, stride=stride, padding=(k - 1) // 2)  # noqa: E731
+        y = (conv(hi, w16) + conv(lo8, whi8) + conv(hi8, wlo8)) * (2.0 ** -e) + b.double().view(1, -1, 1, 1)
+        return (F.relu(y) if relu else y).float()
     x = torch.cat([quantize(t, dtype) for t in xs], 1).double()
     wq = quantize(w, dtype).double()
     y = F.conv2d(x, wq, b.double(), stride=stride, padding=(k - 1) // 2)
@@ -116,6 +126,21 @@ def test_conv_no_relu_negative_outputs(dtype):
     got = run_conv("tc", dtype, [x], [0], w, b, 3, 1, relu=False)
     want = oracle_conv(dtype, [x], w, b, 3, 1, relu=False)
     assert (want < 0).any() and rel_l2(got, want) < L2_TOL[dtype]
+
+
+@pytest.mark.parametrize("backend", ["tc", "halo2"])
+def test_f16f8_accuracy_class(backend):
+    """CNM_F16F8 against the UNQUANTISED fp64 convolution: the fp16 + fp8-correction scheme must stay in the accuracy
+    class of CNM_BF16X3 (operand error ~2^-17), two orders below single-pass bf16."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 128, 32, 32, generator=g).abs()
+    w = torch.randn(128, 128, 3, 3, generator=g) / np.sqrt(128 * 9)
+    b = torch.randn(128, generator=g)
+    want = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float()
+    errs = {}
+    for dtype in (_lib.CNM_F16F8, _lib.CNM_BF16X3, _lib.CNM_BF16):
+        errs[dtype] = rel_l2(run_conv(backend, dtype, [x], [0], w, b, 3, 1), want)
+    assert errs[_lib.CNM_F16F8] < 3e-5 and errs[_lib.CNM_F16F8] < errs[_lib.CNM_BF16] / 50, errs
 
 
 def test_conv_rejects_bad_arguments():

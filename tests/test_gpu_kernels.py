@@ -12,7 +12,7 @@ import cnmnet_b200
 from cnmnet_b200 import _lib, engine, synth
 from gpu_util import act_empty, dev, from_act, quantize, rel_l2, to_act
 
-ALL_DTYPES = [_lib.CNM_BF16, _lib.CNM_TF32, _lib.CNM_BF16X3]
+ALL_DTYPES = [_lib.CNM_BF16, _lib.CNM_TF32, _lib.CNM_BF16X3, _lib.CNM_F16F8]
 from oracle import cost_volume as ocv
 from oracle import nets as onets
 from oracle import normals as onrm
@@ -194,7 +194,7 @@ def test_upsample_head_packers(dtype):
     up = act_empty((2, 12, 20, 64), dtype)
     _lib.check(lib.cnm_upsample2x(xa.data_ptr(), up.data_ptr(), 2, 6, 10, 64, dtype, st))
     want = F.interpolate(quantize(x, dtype), scale_factor=2, mode="bilinear", align_corners=False)
-    tol = {_lib.CNM_BF16: 2e-2, _lib.CNM_TF32: 2e-3, _lib.CNM_BF16X3: 1e-4}[dtype]   # one output rounding
+    tol = {_lib.CNM_BF16: 2e-2, _lib.CNM_TF32: 2e-3, _lib.CNM_BF16X3: 1e-4, _lib.CNM_F16F8: 1e-4}[dtype]   # one output rounding
     assert (from_act(up, dtype) - want).abs().max() < tol
     # head: conv3x3(C->1)+bias -> scale*sigmoid
     w = torch.randn(1, 64, 3, 3, generator=g) * 0.05

@@ -189,6 +189,76 @@ def test_split_bf16_programs_reproduce_conv(halo):
     assert (bf - want).abs().max() > 50 * (got - want).abs().max()   # plain bf16 is >50x worse on the same layer
 
 
+def _f16f8_phys(x_nhwc):
+    """Logical NHWC float tensor -> CNM_F16F8 physical BYTES [.., 256 per 64-channel chunk]: 128 B of fp16 hi, then
+    64 B of e4m3 lo8 = (x - hi) * 2^7 and 64 B of e4m3 hi8 = hi * 2^-4 (include/cnmnet_b200.h)."""
+    N, H, W, C = x_nhwc.shape
+    hi = x_nhwc.to(torch.float16)
+    lo8 = ((x_nhwc - hi.float()) * engine.F8_LO_SCALE).clamp(-448, 448).to(torch.float8_e4m3fn)
+    hi8 = (hi.float() * engine.F8_HI_SCALE).clamp(-448, 448).to(torch.float8_e4m3fn)
+    parts = (hi.view(N, H, W, C // 64, 64).contiguous().view(torch.uint8),
+             lo8.view(N, H, W, C // 64, 64).contiguous().view(torch.uint8),
+             hi8.view(N, H, W, C // 64, 64).contiguous().view(torch.uint8))
+    return torch.cat(parts, 4).reshape(N, H, W, C * 4)
+
+
+def emulate_f16f8_steps(srcs_bytes, steps, wp_bytes, bias, acc_exp):
+    """The CNM_F16F8 K loop: even steps multiply a 128-byte fp16 row (64 ch) with 64 fp16 weight columns, odd steps a
+    128-byte e4m3 row with 128 e4m3 weight columns; one accumulator, scaled by 2^-acc_exp before the bias."""
+    N, H, W, _ = srcs_bytes[0].shape
+    out = torch.zeros((N, H, W, wp_bytes.shape[0]), dtype=torch.float64)
+    for i, (si, sub, dx, dy, c0) in enumerate(steps):
+        assert sub == 0 and (c0 % 128 == 64) == bool(i & 1)          # rows alternate fp16, fp8
+        x = srcs_bytes[si]
+        a = torch.zeros((N, H, W, 128), dtype=torch.uint8)
+        ys, xs = torch.arange(H) + dy, torch.arange(W) + dx
+        vy, vx = (ys >= 0) & (ys < H), (xs >= 0) & (xs < W)
+        a[:, vy.nonzero().flatten()[:, None], vx.nonzero().flatten()[None, :]] = \
+            x[:, ys[vy][:, None], xs[vx][None, :], 2 * c0:2 * c0 + 128]
+        wrow = wp_bytes[:, i * 128:(i + 1) * 128].contiguous()
+        if i & 1:
+            out += a.view(torch.float8_e4m3fn).double() @ wrow.view(torch.float8_e4m3fn).double().T
+        else:
+            out += a.view(torch.float16).double() @ wrow.view(torch.float16).double().T
+    return out * 2.0 ** -acc_exp + bias.double()
+
+
+@pytest.mark.parametrize("halo", [False, True])
+def test_f16f8_programs_reproduce_conv(halo):
+    """f16f8: an fp16 pass and one fp8 correction pass per logical chunk on the fp16-row / fp8-row physical layout."""
+    torch.manual_seed(22)
+    ch, N, H, W, k = 64, 1, 7, 9, 3
+    x, disp = torch.randn(N, 128, H, W), torch.randn(N, 1, H, W)
+    wt, b = torch.randn(8, 129, k, k) / 30, torch.randn(8)
+    want = nhwc(F.conv2d(torch.cat((x, disp), 1).double(), wt.double(), b.double(), padding=1))
+    taps = torch.zeros(N, H, W, ch)
+    pd = F.pad(disp, (1, 1, 1, 1))
+    for r in range(3):
+        for s_ in range(3):
+            taps[..., 3 * r + s_] = pd[:, 0, r:r + H, s_:s_ + W]
+    xb, tb = _f16f8_phys(nhwc(x)), _f16f8_phys(taps)
+    # shapes seen by the program builder: 2-byte physical channels
+    xp, tp = torch.empty(N, H, W, 256, dtype=torch.float16), torch.empty(N, H, W, 128, dtype=torch.float16)
+    srcs = [engine.act_src(xp, 0, phys=2), engine.Src(tp, "taps3x3", 128, ch, 0, 1)]
+    passes = engine.split_passes(_lib.CNM_F16F8)
+    if halo:
+        groups, cols, info = engine.make_groups(srcs, k, ch, 1, split=passes)
+        assert all((c0 % 128 == 64) == bool(i & 1) for i, (m, c0, dx, nt) in enumerate(groups))
+        steps = [(m // 4, 0, dx, t - info[m][0], c0) for (m, c0, dx, nt) in groups for t in range(nt)]
+        # weight steps follow the groups; re-sort both into the alternating order the byte emulator checks
+        order = sorted(range(len(steps)), key=lambda i: (i // 6 * 6 + (i % 3) * 2 + (i % 6) // 3) if i < 36 else i)
+        steps, gcols = [steps[i] for i in order], [cols[i] for i in order]
+    else:
+        steps, gcols = engine.make_steps(srcs, k, 1, ch, split=passes)
+    assert len(steps) == len(gcols) == 2 * (9 * 2 + 1)
+    e = engine.f16f8_weight_exp(wt)
+    assert 224.0 < float(wt.abs().max()) * 2.0 ** (e - 7) <= 448.0
+    wp = engine.pack_weights(wt, gcols, ch, _lib.CNM_F16F8)
+    assert wp.dtype == torch.float16 and wp.shape == (8, len(gcols) * 64)
+    got = emulate_f16f8_steps([xb, tb], steps, wp.view(torch.uint8), b, e)
+    assert (got - want).abs().max() < 3e-5 * want.abs().max()     # same accuracy class as split bf16
+
+
 def test_fold_bn_matches_batchnorm():
     sd = synth.kaiming_state(nets.state_shapes([("c", "conv", 8, 4, 3)]), seed=5)
     x = torch.randn(2, 8, 6, 6)
@@ -259,7 +329,7 @@ def test_cabi_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.ConvSrc) == 24 and ctypes.sizeof(_lib.ConvStep) == 32 and ctypes.sizeof(_lib.ConvDesc) == 48
+    assert ctypes.sizeof(_lib.ConvSrc) == 24 and ctypes.sizeof(_lib.ConvStep) == 32 and ctypes.sizeof(_lib.ConvDesc) == 64
 
 
 def test_shard_range_partitions():

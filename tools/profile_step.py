@@ -12,7 +12,7 @@ import bench  # noqa: E402
 import cnmnet_b200  # noqa: E402
 from cnmnet_b200 import _lib, synth  # noqa: E402
 
-precision = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+precision = sys.argv[1] if len(sys.argv) > 1 else "f16f8"
 dev = torch.device("cuda", 0)
 B, V, H, W = bench.B_PER_GPU, bench.V, bench.H, bench.W
 dnet, rnet = bench.make_weights(0)
