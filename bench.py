@@ -116,7 +116,7 @@ def make_weights(seed=0):
     """Reference random init (kaiming_normal fan_out, BN 1/0) under torch.manual_seed(seed)."""
     import cnmnet_b200
     torch.manual_seed(seed)
-    d = cnmnet_b200.depthNet(idepth_scale=3.0)
+    d = cnmnet_b200.depthNet(idepth_scale=3.0, planes=D)
     r = cnmnet_b200.DepthRefineNet(idepth_scale=3.0)
     return d, r
 
@@ -213,19 +213,23 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("CNM_PRECISION", "f16f8"),
                     choices=["bf16", "tf32", "bf16x3", "f16f8"],
                     help="tensor-core mode; f16f8 (default) and bf16x3 meet the 1e-3 final-depth tolerance")
-    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
-                    help="c4 = BASELINE configs[3] (default, the metric's config); c5 = configs[4] at the reference's 64 "
-                         "planes: 640x480, batch 32 per GPU (128 planes would need a 131-channel conv1 the reference "
-                         "network does not have)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5", "c5-64"],
+                    help="c4 = BASELINE configs[3] (default, the metric's config); c5 = configs[4]: 640x480, 128 planes "
+                         "(depthNet(planes=128): conv1 widened to 131 inputs, an extension -- the reference hard-codes "
+                         "64), batch 32 per GPU; c5-64 = the same at the reference's 64 planes")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer timing table on stderr")
     args = ap.parse_args()
-    global H, W, B_PER_GPU, WORKLOAD, DEPTHNET_GFLOP, REFINE_GFLOP
-    if args.workload == "c5":
+    global H, W, D, B_PER_GPU, WORKLOAD, DEPTHNET_GFLOP, REFINE_GFLOP, METRIC
+    if args.workload in ("c5", "c5-64"):
         H, W, B_PER_GPU = 480, 640, 32
-        WORKLOAD = "C5 at 64 planes: full refine model, 1 ref + 2 src views, 640x480, 64 planes, k_size 9, batch 32 per GPU"
-        DEPTHNET_GFLOP, REFINE_GFLOP = 1008.94, 704.96
+        D = 128 if args.workload == "c5" else 64
+        WORKLOAD = "C5%s: full refine model, 1 ref + 2 src views, 640x480, %d planes, k_size 9, batch 32 per GPU" % (
+            "" if D == 128 else " at 64 planes", D)
+        METRIC = "depth frames/s @640x480x%d planes" % D
+        # 1008.94 GFLOP at 64 planes; conv1.0 grows from 67 to 131 input channels at 128
+        DEPTHNET_GFLOP, REFINE_GFLOP = (1255.5 if D == 128 else 1008.94), 704.96
         args.no_cpu_baseline = True
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -405,12 +409,14 @@ def main():
         cv()
         ms_cv, _ = time_events(cv, 20, flush)
         ms_cvk, _ = time_events(cv_only, 20, flush)
-        gbs = C2_COST_VOLUME_BYTES / (ms_cvk * 1e-3) / 1e9
+        cv_bytes = B * (V * 4 * D * H * W + (V + 1) * 4 * 3 * H * W)   # = C2_COST_VOLUME_BYTES on the default workload
+        gbs = cv_bytes / (ms_cvk * 1e-3) / 1e9
         line["roofline_cost_volume"] = {
-            "kernel": "cost_volume_kernel (C2: 256x192x64, 2 views, batch 5, fp32 NCHW)", "bound": "hbm",
+            "kernel": "cost_volume_kernel (%s: %dx%dx%d, %d views, batch %d, fp32 NCHW)" % (
+                "C2" if args.workload == "c4" else "C5 size", W, H, D, V, B), "bound": "hbm",
             "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-            "traffic": traffic.get("cost_volume_c2_bytes"),
-            "us_per_launch": ms_cvk * 1e3, "us_with_source_repack": ms_cv * 1e3, "algorithmic_bytes": C2_COST_VOLUME_BYTES,
+            "traffic": traffic.get("cost_volume_c2_bytes") if args.workload == "c4" else None,
+            "us_per_launch": ms_cvk * 1e3, "us_with_source_repack": ms_cv * 1e3, "algorithmic_bytes": cv_bytes,
             "peak_source": peaks["source"],
         }
         # depth -> normal at C3 and the aggregation at C4

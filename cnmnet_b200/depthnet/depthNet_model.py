@@ -95,25 +95,31 @@ def _check_image_pair(left_image, right_image):
 class depthNet(_KernelNet):
     """Reference: depthnet/depthNet_model.py:124 -- ``depthNet(idepth_scale=3)``.
 
-    Extra keyword arguments (not in the reference): ``precision`` 'bf16' | 'tf32' selects the tensor-core
-    operand type, ``backend`` 'tc' (tcgen05, product) | 'simt' (CUDA-core validation twin)."""
+    Extra keyword arguments (not in the reference): ``precision`` 'bf16' | 'tf32' | 'bf16x3' | 'f16f8' selects the
+    tensor-core operand type, ``backend`` 'tc' (tcgen05, product) | 'simt' (CUDA-core validation twin), ``planes`` the
+    number of inverse-depth hypotheses.  The reference hard-codes 64 planes (getVolume loops ``range(64)``,
+    conv1 takes 3 + 64 channels, depthNet_model.py:129,193); ``planes=128`` is the variant BASELINE config 5 names:
+    the same sweep sampled at 128 planes over the same inverse-depth range, conv1.0 widened to 3 + 128 inputs."""
 
-    def __init__(self, idepth_scale=3, precision="bf16", backend="tc"):
+    def __init__(self, idepth_scale=3, precision="bf16", backend="tc", planes=64):
         super().__init__()
+        if planes < 64 or planes % 64:
+            raise ValueError("planes must be a positive multiple of 64 (one 128-byte operand row per 64 planes)")
         self.idepth_scale = idepth_scale
         self.precision = parse_dtype(precision)
         self.backend = backend
-        self._build(_DEPTHNET)
+        self.planes = int(planes)
+        self._build([("conv1", "down", 3 + self.planes, 128, 7)] + _DEPTHNET[1:])
         super().train(False)
 
     def plan(self, N, Bref, H, W, want_logits=False):
         dev = next(self.parameters()).device
         key = (N, Bref, H, W, self.precision, self.backend, str(dev), want_logits)
         return self._get_plan(key, lambda: DepthNetPlan(N, Bref, H, W, float(self.idepth_scale), self.precision, dev,
-                                                        self.backend, want_logits=want_logits))
+                                                        self.backend, planes=self.planes, want_logits=want_logits))
 
     def getVolume(self, left_image, right_image, KRKiUV_T, KT_T):
-        """[B,3,H,W] x2, KRKiUV_T [B,3,W*H] (x-major), KT_T [B,3,1] -> cost volume [B,64,H,W] fp32
+        """[B,3,H,W] x2, KRKiUV_T [B,3,W*H] (x-major), KT_T [B,3,1] -> cost volume [B,planes (64),H,W] fp32
         (depthNet_model.py:185-224).  The 3x3 homography is recovered from three columns of KRKiUV_T."""
         _check_image_pair(left_image, right_image)
         B, _, H, W = left_image.shape
@@ -133,9 +139,9 @@ class depthNet(_KernelNet):
         left = left_image.float().contiguous()
         right = right_image.float().contiguous()
         tex = torch.empty((lib.cnm_packed_source_bytes(B, H, W),), dtype=torch.uint8, device=left.device)
-        out = torch.empty((B, 64, H, W), dtype=torch.float32, device=left.device)
+        out = torch.empty((B, self.planes, H, W), dtype=torch.float32, device=left.device)
         _lib.check(lib.cnm_pack_source(_lib.ptr(right), tex.data_ptr(), B, H, W, st), "pack_source")
-        _lib.check(lib.cnm_cost_volume(_lib.ptr(left), tex.data_ptr(), hk.data_ptr(), out.data_ptr(), B, 1, H, W, 64, idmin,
+        _lib.check(lib.cnm_cost_volume(_lib.ptr(left), tex.data_ptr(), hk.data_ptr(), out.data_ptr(), B, 1, H, W, self.planes, idmin,
                                        idmax, _lib.VOLUME_NCHW_F32, 0, st), "cost_volume")
         return out
 

@@ -497,8 +497,8 @@ class DepthNetPlan(_Plan):
             self.idmin, self.idmax = 0.1, 3.0
         else:  # the reference raises UnboundLocalError here (depthNet_model.py:186-191)
             raise ValueError("idepth_scale must be 2.0 or 3.0 (the reference defines no other plane range)")
-        if planes != 64:
-            raise ValueError("the reference network has 67 input channels = 3 + 64 planes")
+        if planes < 64 or planes % 64:
+            raise ValueError("planes must be a positive multiple of 64 (the reference network: 64)")
         self.N, self.Bref, self.H, self.W, self.D, self.scale = N, Bref, H, W, planes, float(idepth_scale)
         lib, dt, ch = self.lib, self.dtype, self.ch
         self.hk = self.buf(N, 12, dtype=torch.float32)

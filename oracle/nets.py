@@ -47,6 +47,13 @@ REFINENET_LAYERS = [
 ]
 
 
+def depthnet_layers(planes=64):
+    """DEPTHNET_LAYERS with conv1 widened to 3 + planes inputs.  planes = 64 is the reference (depthNet_model.py:129);
+    other values are the extension BASELINE config 5 names (128 planes) -- no reference implementation exists for them,
+    the wiring below is unchanged."""
+    return [("conv1", "down", 3 + planes, 128, 7)] + DEPTHNET_LAYERS[1:]
+
+
 def state_shapes(layers):
     """state_dict key -> shape, with the reference's nn.Sequential indices."""
     shapes = OrderedDict()
@@ -124,13 +131,13 @@ def depthnet_trunk(sd, x, idepth_scale=3.0, return_logits=False):
 
 
 def depthnet_forward(sd, left_image, right_image, left_cam, right_cam, idepth_scale=3.0,
-                     dtype=torch.float32, return_logits=False, volume=None):
+                     dtype=torch.float32, return_logits=False, volume=None, num_planes=64):
     """depthNet.forward (depthNet_model.py:226-263): cost volume (fp64 oracle, cast) + trunk."""
     if volume is None:
         idmin, idmax = _cv.idepth_range(float(idepth_scale))
         np_dt = np.float64 if dtype == torch.float64 else np.float32
         vol = _cv.cost_volume(left_image.numpy(), right_image.numpy(), left_cam.numpy(), right_cam.numpy(),
-                              64, idmin, idmax, dtype=np.float64).astype(np_dt)
+                              num_planes, idmin, idmax, dtype=np.float64).astype(np_dt)
         volume = torch.from_numpy(vol)
     x = torch.cat((left_image.to(dtype), volume.to(dtype)), 1)
     return depthnet_trunk(sd, x, idepth_scale, return_logits)
@@ -287,14 +294,14 @@ def depth2normal_torch(depth, intrinsic_inv, k_size=9):
     return n.view(b, h, w, 3).permute(0, 3, 1, 2), points
 
 
-def reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, idepth_scale=3.0, k_size=9):
+def reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, idepth_scale=3.0, k_size=9, num_planes=64):
     """The reference's eval_refine call sequence (eval.py:440-455) on the fp32 torch-CPU ports above:
     V x depthNet (with its own cost volume), refine, 1/idepth, Depth2normal.  -> depth, normal, prob."""
     V = srcs.shape[1]
     ids, ics = [], []
     with torch.no_grad():
         for v in range(V):
-            vol = cost_volume_torch(ref, srcs[:, v], ref_cam, src_cams[:, v], idepth_scale)
+            vol = cost_volume_torch(ref, srcs[:, v], ref_cam, src_cams[:, v], idepth_scale, num_planes)
             d, ic = depthnet_trunk(dsd, torch.cat((ref, vol), 1), idepth_scale)
             ids.append(d[0])
             ics.append(ic)

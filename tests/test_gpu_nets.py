@@ -81,12 +81,12 @@ def test_refinenet_forward_golden(golden_dir, precision, backend):
     assert torch.equal(dr2, dr) and torch.equal(pm2, pm)     # deterministic, and the 2-tuple return form
 
 
-def _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, scale, k_size):
+def _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, scale, k_size, planes=64):
     B, V = srcs.shape[:2]
     ids, ics = [], []
     with torch.no_grad():
         for v in range(V):
-            d, ic = onets.depthnet_forward(dsd, ref, srcs[:, v], ref_cam, src_cams[:, v], scale)
+            d, ic = onets.depthnet_forward(dsd, ref, srcs[:, v], ref_cam, src_cams[:, v], scale, num_planes=planes)
             ids.append(d[0])
             ics.append(ic)
         id1, id2 = onets.group_mean(ids[0::2]), onets.group_mean(ids[1::2])
@@ -154,6 +154,36 @@ def test_pipeline_odd_pyramid_sizes(H, W, B, precision):
     assert np.abs(p.cpu().numpy() - want_p).max() < 2e-3
 
 
+@pytest.mark.parametrize("precision", ["f16f8", "tf32"])
+def test_pipeline_128_planes(precision):
+    """BASELINE config 5's plane count: depthNet(planes=128) = the same sweep at 128 hypotheses, conv1.0 with 3 + 128
+    input channels (an extension: the reference hard-codes 64).  Checked against the oracle wiring with the same
+    widened conv1 and the fp64 cost volume at 128 planes; the NCHW getVolume() result is checked too."""
+    B, H, W, V, D = 1, 64, 96, 2, 128
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(777, B, H, W, V)
+    dsd = synth.kaiming_state(onets.state_shapes(onets.depthnet_layers(D)), 61, 0.02)
+    rsd = synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), 62, 0.02)
+    assert tuple(dsd["conv1.0.weight"].shape) == (128, 3 + D, 7, 7)
+    dnet = cnmnet_b200.depthNet(idepth_scale=3.0, precision=precision, planes=D)
+    rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0, precision=precision)
+    dnet.load_state_dict(dsd)
+    rnet.load_state_dict(rsd)
+    dnet, rnet = dnet.to(dev()), rnet.to(dev())
+    pix = cnmnet_b200.get_pixel_coordinates(H, W)
+    KRKiUV, KT = cnmnet_b200.process_camera_parameters(ref_cam.to(dev()), src_cams[:, 0].to(dev()), pix)
+    vol = dnet.getVolume(ref.to(dev()), srcs[:, 0].to(dev()), KRKiUV, KT).cpu().numpy()
+    from oracle import cost_volume as ocv
+    exact = ocv.cost_volume(ref.numpy(), srcs[:, 0].numpy(), ref_cam.numpy(), src_cams[:, 0].numpy(), D, 0.1, 3.0)
+    assert vol.shape == (B, D, H, W) and rel_l2(vol, exact) < 2e-5
+    pipe = cnmnet_b200.CNMPipeline(dnet, rnet, k_size=9)
+    d, n, p = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))
+    want_d, want_n, want_p = _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, 9, planes=D)
+    rel = np.abs(d.cpu().numpy() - want_d) / np.abs(want_d)
+    _, t_p99, t_max, t_mean = TOL[(precision, "tc")]
+    assert np.percentile(rel, 99) < t_p99 and rel.max() < t_max and rel.mean() < t_mean, \
+        (np.percentile(rel, 99), rel.max(), rel.mean())
+
+
 def test_pipeline_with_halo_kernel_forced(monkeypatch):
     """Every eligible stride-1 layer through csrc/conv_halo.cu (incl. the side-tensor sources) vs the per-tap kernel."""
     from cnmnet_b200 import engine
@@ -196,6 +226,25 @@ def test_infer_stream_matches_single_calls():
     for g, w in zip(got, want):
         for a, b in zip(g, w):
             assert torch.equal(a, b)
+
+
+def test_video_stream_matches_single_calls():
+    """VideoDepthStream (sliding reference tuples, padded last batch) returns per frame what a direct call returns."""
+    T, H, W, B = 30, 32, 64, 2
+    rng = np.random.default_rng(5)
+    frames = torch.from_numpy(synth.smooth_images(rng, T, H, W))
+    cams = torch.from_numpy(synth.cameras(rng, T, H, W)[0])
+    dnet = cnmnet_b200.depthNet(idepth_scale=3.0, precision="f16f8").to(dev())
+    rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0, precision="f16f8").to(dev())
+    pipe = cnmnet_b200.CNMPipeline(dnet, rnet, use_graph=True)
+    got = list(cnmnet_b200.VideoDepthStream(pipe, batch=B, views=3).run(frames, cams))
+    assert [g[0] for g in got] == [12, 15, 18]                                   # 3 frames: one full batch + a padded one
+    for i, depth, normal, prob in got:
+        d, n, p = pipe(frames[i:i + 1].expand(B, -1, -1, -1).contiguous().to(dev()),
+                       torch.stack((frames[i + 10], frames[i - 10])).unsqueeze(0).expand(B, -1, -1, -1, -1).contiguous().to(dev()),
+                       cams[i:i + 1].expand(B, -1, -1, -1).contiguous().to(dev()),
+                       torch.stack((cams[i + 10], cams[i - 10])).unsqueeze(0).expand(B, -1, -1, -1, -1).contiguous().to(dev()))
+        assert torch.equal(depth, d[0].cpu()) and torch.equal(normal, n[0].cpu()) and torch.equal(prob, p[0].cpu())
 
 
 def test_weight_updates_are_picked_up():

@@ -340,3 +340,39 @@ def test_shard_range_partitions():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_video_reference_tuples_follow_the_eval_loops():
+    """eval.py:408-415 (3 views), 581-592 (5 views), 817-830 (7 views): source offsets, order and frame stride."""
+    from cnmnet_b200 import video
+    t3 = video.reference_tuples(100, 3)
+    assert t3[0] == (12, (22, 2)) and t3[-1] == (87, (97, 77)) and all(i % 3 == 0 for i, _ in t3)
+    assert [i for i, _ in t3] == [i for i in range(10, 90) if i % 3 == 0]          # the reference's own index list
+    t5 = video.reference_tuples(100, 5)
+    assert t5[0] == (12, (22, 2, 17, 7))
+    t7 = video.reference_tuples(100, 7)
+    assert t7[0] == (27, (37, 17, 32, 22, 47, 7)) and all(i % 9 == 0 for i, _ in t7)
+    assert all(0 <= s < 100 for _, srcs in t5 + t7 for s in srcs)                   # no wrap-around (unlike eval.py:581)
+    assert video.reference_tuples(15, 3) == []
+    with pytest.raises(ValueError):
+        video.reference_tuples(50, offsets=(5,))
+
+
+def test_video_batches_gather_and_pad():
+    from cnmnet_b200 import video
+    T, H, W = 40, 4, 6
+    frames = torch.arange(T, dtype=torch.float32).view(T, 1, 1, 1).expand(T, 3, H, W).contiguous()
+    cams = torch.arange(T, dtype=torch.float32).view(T, 1, 1, 1).expand(T, 2, 4, 4).contiguous() * 10
+    vs = video.VideoDepthStream(None, batch=4, views=3)
+    idx, gen = vs.batches(frames, cams)
+    want = [i for i in range(10, 30) if i % 3 == 0]                                  # 12, 15, ..., 27
+    assert [i for g in idx for i in g] == want and [len(g) for g in idx] == [4, 2]
+    got = [tuple(t.clone() for t in b) for b in gen]
+    assert len(got) == 2
+    ref, srcs, rc, sc = got[0]
+    assert ref.shape == (4, 3, H, W) and srcs.shape == (4, 2, 3, H, W) and sc.shape == (4, 2, 2, 4, 4)
+    assert ref[:, 0, 0, 0].tolist() == [12, 15, 18, 21]
+    assert srcs[:, 0, 0, 0, 0].tolist() == [22, 25, 28, 31] and srcs[:, 1, 0, 0, 0].tolist() == [2, 5, 8, 11]
+    assert rc[:, 0, 0, 0].tolist() == [120, 150, 180, 210] and sc[:, 1, 0, 0, 0].tolist() == [20, 50, 80, 110]
+    ref, srcs, _, _ = got[1]
+    assert ref[:, 0, 0, 0].tolist() == [24, 27, 27, 27]                              # padded with the last tuple

@@ -91,11 +91,11 @@ if "--full" in sys.argv:
   dump("prof_halo.ncu-rep", "%s_conv_halo_ncu.md" % tag,
      "%s ncu --set full: conv_halo_kernel / conv_halo2_kernel (row-halo tcgen05 conv, 1-SM and CTA-pair)" % tag,
      "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k "
-     "regex:\"conv_halo2_kernel|conv_halo_kernel\" -c 6 python tools/profile_step.py` (bf16, C4 step, first six halo launches of "
+     "regex:\"conv_halo2_kernel|conv_halo_kernel\" -c 6 python tools/profile_step.py` (%s mode, C4 step, first six halo launches of " % bench.get("dtype", "f16f8") +
      "the DepthNet pass: conv1.0, conv1.3, conv2.0, conv3.0, ... in launch order; see the launch list for grids).")
 if "--full" in sys.argv:
   dump("prof_tc.ncu-rep", "%s_conv_tc_final_ncu.md" % tag,
      "%s ncu --set full: conv_tc_kernel (per-tap tcgen05 conv) after the warp-uniform issue loop" % tag,
      "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 "
-     "python tools/profile_step.py` (bf16, C4 step; the layers the autotuner leaves on the per-tap kernel: stride-2 and <= 48x64 layers).")
+     "python tools/profile_step.py` (%s mode, C4 step; the layers the autotuner leaves on the per-tap kernel: small and <= 48x64 layers)." % bench.get("dtype", "f16f8"))
 print("ok", cu, cm, s)
