@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
                 ("c_out_total", C.c_int32), ("c_out_offset", C.c_int32), ("stride", C.c_int32), ("relu", C.c_int32),
                 ("num_srcs", C.c_int32), ("num_steps", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
-                ("acc_exp", C.c_int32), ("reserved2", C.c_int32 * 3)]
+                ("acc_exp", C.c_int32), ("reserved2", C.c_int32 * 3), ("head_w", C.c_void_p), ("head_partial", C.c_void_p)]
 
 
 _P, _I, _D, _F, _L = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int64
@@ -52,6 +52,7 @@ SIGNATURES = {
     "cnm_refine_aggregate_nchw": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cnm_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "cnm_head3x3": (_I, [_P, _P, _F, _F, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "cnm_head_finish": (_I, [_P, _F, _F, _P, _P, _I, _I, _I, _P]),
     "cnm_conv2d_tc": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
     "cnm_conv2d_simt": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
     "cnm_conv2d_halo": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P, _P]),

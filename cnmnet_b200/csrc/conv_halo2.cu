@@ -37,6 +37,9 @@ struct alignas(64) Halo2Params {
   int c_out_offset;
   int mode;         // EPI_PLAIN / EPI_BF16X3 / EPI_F16F8: the split modes store two 128-byte rows per 64-column chunk
   float acc_scale;  // 2^-acc_exp
+  const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
+  float* head_partial;   // [N, Ho, Wo, 12] per-pixel tap dot products
+  int Ho, Wo;
 };
 
 // ---- 2-CTA PTX wrappers --------------------------------------------------------------------------------------
@@ -112,7 +115,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   const uint32_t off_b = (uint32_t)p.a_stages * p.slab_bytes;
   const uint32_t off_out = off_b + (uint32_t)p.b_stages * B_BYTES;
   const uint32_t off_bias = off_out + H2_TILE_BYTES;
-  const uint32_t off_bar = off_bias + BN * 4;
+  const uint32_t off_head = off_bias + BN * 4;  // fused-head weights (BN == 64 only)
+  const uint32_t off_bar = off_head + (BN == 64 ? 9 * 64 * 4 : 0);
   const uint32_t bar0 = base + off_bar;
   auto fullA = [&](int s) { return bar0 + 8u * s; };
   auto emptyA = [&](int s) { return bar0 + 8u * (H2_MAX_A + s); };
@@ -123,6 +127,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   const uint32_t off_tmem = off_bar + 8u * (2 * H2_MAX_A + 2 * H2_MAX_B + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
   float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
+  float* head_s = reinterpret_cast<float*>(base_ptr + off_head);
+  const bool fused_head = !TF32 && BN == 64 && p.head_partial != nullptr;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -252,6 +258,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
     const bool storer = (et == 0);
     int it = 0;
     int bias_tile = -1;
+    if (fused_head) {
+      for (int i = et; i < 9 * 64; i += 128) head_s[i] = __ldg(p.head_w + i);
+      epi_bar();
+    }
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
       const int nt = tile % p.tiles_n;
       int m = 2 * (tile / p.tiles_n) + (int)rank;
@@ -277,13 +287,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
           tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
           if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
           tmem_ld_wait();
+          epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale);
+          if (!TF32 && BN == 64 && fused_head) {
+            const int px = x0 + (row & 15), py = y0 + 8 * half + (row >> 4);
+            if (px < p.Wo && py < p.Ho)
+              epi_head_partial(v, head_s, p.head_partial + (((size_t)n0 * p.Ho + py) * p.Wo + px) * HEAD_PARTIAL_STRIDE);
+          }
           for (int part = 0; part < (p.mode ? 2 : 1); ++part) {
             // one staging buffer (smem goes to deeper operand rings): the previous TMA store must have finished
             // reading it; the epilogue runs under the next tile's main loop, so this wait is off the critical path
             uint8_t* stg = base_ptr + off_out;
             if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             epi_bar();
-            epi_store_row<TF32>(v, bias_s + ch * COLS_PER_CHUNK, stg + row * 128, row, p.relu, p.mode, part, p.acc_scale);
+            epi_store_row<TF32>(v, stg + row * 128, row, p.mode, part);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             epi_bar();
             if (storer) {
@@ -373,6 +389,7 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
                 d->reserved, d->Cout);
     BN = d->reserved;
   }
+  if (d->head_partial) BN = 64;  // the fused head needs all 64 output channels of a pixel in one thread
   p.tiles_n = d->Cout / BN;
   p.groups = groups;
   p.bias = bias;
@@ -382,10 +399,13 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
   p.c_out_offset = d->c_out_offset;
   p.mode = d->dtype == CNM_BF16X3 ? EPI_BF16X3 : (d->dtype == CNM_F16F8 ? EPI_F16F8 : EPI_PLAIN);
   p.acc_scale = ldexpf(1.0f, -d->acc_exp);
+  p.head_w = d->head_w;
+  p.head_partial = d->head_partial;
+  p.Ho = d->Ho; p.Wo = d->Wo;
   // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
   // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
   // lasts ntaps B tiles.
-  const int fixed = 1024 + H2_TILE_BYTES + BN * 4 + 8 * (2 * H2_MAX_A + 2 * H2_MAX_B + 4) + 16;
+  const int fixed = 1024 + H2_TILE_BYTES + BN * 4 + (BN == 64 ? 9 * 64 * 4 : 0) + 8 * (2 * H2_MAX_A + 2 * H2_MAX_B + 4) + 16;
   const int budget = 232448 - fixed;
   const int want_b = 8;
   p.a_stages = (pmax >= 3 || BN == 256) ? 2 : (BN == 64 ? 4 : 3);

@@ -175,6 +175,10 @@ int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* 
   CNM_REQUIRE(d->stride == 1 || d->stride == 2, CNM_ERR_UNSUPPORTED_SHAPE, "%s: stride %d", fn, d->stride);
   CNM_REQUIRE(d->num_srcs >= 1 && d->num_srcs <= 3, CNM_ERR_UNSUPPORTED_SHAPE, "%s: num_srcs %d (max 3)", fn, d->num_srcs);
   CNM_REQUIRE(d->num_steps >= 1, CNM_ERR_INVALID_ARGUMENT, "%s: num_steps %d", fn, d->num_steps);
+  CNM_REQUIRE((d->head_w == nullptr) == (d->head_partial == nullptr), CNM_ERR_INVALID_ARGUMENT,
+              "%s: head_w and head_partial go together", fn);
+  CNM_REQUIRE(!d->head_partial || (d->Cout == 64 && d->dtype != CNM_TF32 && ((uintptr_t)d->head_partial & 15) == 0),
+              CNM_ERR_UNSUPPORTED_SHAPE, "%s: the fused head needs Cout == 64, a 2-byte dtype and a 16B-aligned buffer", fn);
   const int ch = chunk_channels(d->dtype);
   CNM_REQUIRE(d->Cout % ch == 0 && d->c_out_total % ch == 0 && d->c_out_offset % ch == 0 &&
                   d->c_out_offset + phys_factor(d->dtype) * d->Cout <= d->c_out_total,
@@ -204,6 +208,7 @@ extern "C" int cnm_conv2d_simt(const cnm_conv_desc* d, const cnm_conv_src* srcs,
                                const void* wp, const float* bias, void* out, void* stream) {
   int rc = check_conv_args("cnm_conv2d_simt", d, srcs, steps, wp, out);
   if (rc) return rc;
+  CNM_REQUIRE(!d->head_partial, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_simt: no fused head in the validation twin");
   SimtParams p{};
   for (int i = 0; i < d->num_srcs; ++i) p.srcs[i] = SimtSrc{srcs[i].ptr, srcs[i].H, srcs[i].W, srcs[i].C};
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;

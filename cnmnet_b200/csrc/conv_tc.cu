@@ -42,6 +42,9 @@ struct alignas(64) TcParams {
   int c_out_offset;
   int mode;         // EPI_PLAIN / EPI_BF16X3 / EPI_F16F8: the split modes store two 128-byte rows per 64-column chunk
   float acc_scale;  // 2^-acc_exp
+  const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
+  float* head_partial;   // [N, Ho, Wo, 12] per-pixel tap dot products
+  int N, Ho, Wo;
 };
 
 template <int BN, int STAGES, bool TF32>
@@ -51,7 +54,8 @@ struct TcSmem {
   static constexpr int OUT_BYTES = 2 * TC_A_BYTES;  // double-buffered 128 x 128 B staging
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
   static constexpr int OFF_BIAS = OFF_OUT + OUT_BYTES;
-  static constexpr int OFF_BAR = OFF_BIAS + BN * 4;
+  static constexpr int OFF_HEAD = OFF_BIAS + BN * 4;                     // fused-head weights (BN == 64 only)
+  static constexpr int OFF_BAR = OFF_HEAD + (BN == 64 ? 9 * 64 * 4 : 0);
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + slack for manual 1024 B alignment
@@ -80,6 +84,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TMEM);
   float* bias_s = reinterpret_cast<float*>(base_ptr + L::OFF_BIAS);
+  float* head_s = reinterpret_cast<float*>(base_ptr + L::OFF_HEAD);
+  const bool fused_head = !TF32 && BN == 64 && p.head_partial != nullptr;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -183,6 +189,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     int it = 0;
     uint32_t chunk_counter = 0;
     int bias_tile = -1;
+    if (fused_head) {
+      for (int i = et; i < 9 * 64; i += 128) head_s[i] = __ldg(p.head_w + i);
+      epi_bar();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.tiles_n;
       int m = tile / p.tiles_n;
@@ -207,13 +217,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
         if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
         tmem_ld_wait();
+        epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale);
+        if (!TF32 && BN == 64 && fused_head) {
+          const int px = x0 + row % p.TW, py = y0 + (row / p.TW) % p.TH, pn = n0 + row / (p.TW * p.TH);
+          if (px < p.Wo && py < p.Ho && pn < p.N)
+            epi_head_partial(v, head_s, p.head_partial + (((size_t)pn * p.Ho + py) * p.Wo + px) * HEAD_PARTIAL_STRIDE);
+        }
         for (int part = 0; part < (p.mode ? 2 : 1); ++part) {
           const uint32_t buf = chunk_counter & 1;
           uint8_t* stg = base_ptr + L::OFF_OUT + buf * TC_A_BYTES;
           // the TMA store that last read this staging buffer (two stores ago) must have finished reading
           if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           epi_bar();
-          epi_store_row<TF32>(v, bias_s + ch * COLS_PER_CHUNK, stg + row * 128, row, p.relu, p.mode, part, p.acc_scale);
+          epi_store_row<TF32>(v, stg + row * 128, row, p.mode, part);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
           epi_bar();
           if (leader) {
@@ -332,6 +348,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
                 d->reserved, d->Cout);
     BN = d->reserved;
   }
+  if (d->head_partial) BN = 64;  // the fused head needs all 64 output channels of a pixel in one thread
   p.tiles_n = d->Cout / BN;
   p.steps = steps;
   p.bias = bias;
@@ -340,6 +357,9 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.c_out_offset = d->c_out_offset;
   p.mode = d->dtype == CNM_BF16X3 ? EPI_BF16X3 : (d->dtype == CNM_F16F8 ? EPI_F16F8 : EPI_PLAIN);
   p.acc_scale = ldexpf(1.0f, -d->acc_exp);
+  p.head_w = d->head_w;
+  p.head_partial = d->head_partial;
+  p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
 
   const uint32_t box[4] = {(uint32_t)ch, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.NB};
   for (int i = 0; i < d->num_srcs; ++i) {
@@ -384,5 +404,5 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
   if (BN == 256) return tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
   if (BN == 128) return tf32 ? launch_tc<128, 6, true>(p, grid, s) : launch_tc<128, 6, false>(p, grid, s);
-  return tf32 ? launch_tc<64, 8, true>(p, grid, s) : launch_tc<64, 8, false>(p, grid, s);
+  return tf32 ? launch_tc<64, 7, true>(p, grid, s) : launch_tc<64, 7, false>(p, grid, s);
 }

@@ -55,60 +55,150 @@ __global__ void act_to_nchw_kernel(const T* __restrict__ src, float* __restrict_
 }
 
 // ---- tap packers -----------------------------------------------------------------------------
-// one thread per pixel writes one 128-byte chunk row (64 bf16 or 32 fp32 channels)
+// One thread per pixel computes one K-chunk row (64 logical channels, 32 for tf32; only the first few are non-zero).
+// The rows of a 128-thread block are contiguous in memory, so they are packed into shared memory (16-byte pieces,
+// XOR-swizzled by pixel so that both phases are bank-conflict free) and written out as one coalesced stream; a thread
+// storing its own 128 / 256 bytes directly would touch 32 different 256-byte segments per instruction.
 template <typename T>
-__device__ __forceinline__ void store_chunk(T* dst, const float* v) {
-  constexpr int CH = ActTraits<T>::CHUNK;
+struct RowPack;
+template <>
+struct RowPack<__nv_bfloat16> {  // 8 pieces of 8 channels
+  static constexpr int PIECES = 8;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < CH; i += Vec16<T>::N) Vec16<T>::store(dst + i, v + i);  // split bf16: + the lo row 64 further
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <>
+struct RowPack<float> {  // 8 pieces of 4 channels, tf32-rounded
+  static constexpr int PIECES = 8;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    return make_uint4(__float_as_uint(round_tf32(v[4 * j])), __float_as_uint(round_tf32(v[4 * j + 1])),
+                      __float_as_uint(round_tf32(v[4 * j + 2])), __float_as_uint(round_tf32(v[4 * j + 3])));
+  }
+};
+template <>
+struct RowPack<bf16s> {  // 8 hi pieces, then 8 lo pieces
+  static constexpr int PIECES = 16;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a = v[8 * (j & 7) + 2 * e], b = v[8 * (j & 7) + 2 * e + 1];
+      if (j >= 8) {
+        a -= __bfloat162float(__float2bfloat16_rn(a));
+        b -= __bfloat162float(__float2bfloat16_rn(b));
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <>
+struct RowPack<h16f8> {  // 8 fp16 pieces (8 channels), 4 lo8 pieces (16 channels), 4 hi8 pieces
+  static constexpr int PIECES = 16;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    uint32_t w[4];
+    if (j < 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 h = __floats2half2_rn(sat_f16(v[8 * j + 2 * e]), sat_f16(v[8 * j + 2 * e + 1]));
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    } else {
+      const int c0 = 16 * (j & 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float part[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half h;
+          float lo, hs;
+          split_f16f8(v[c0 + 4 * e + i], h, lo, hs);
+          part[i] = j < 12 ? lo : hs;
+        }
+        w[e] = e4m3x2(part[0], part[1]) | (e4m3x2(part[2], part[3]) << 16);
+      }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+constexpr int PACK_THREADS = 128;
+
+// dst_block = first row of this block; `valid` rows exist (the last block of the grid may be partial)
+template <typename T>
+__device__ __forceinline__ void emit_rows(void* dst_block, const float* v, int valid) {
+  constexpr int NP = RowPack<T>::PIECES;
+  __shared__ uint4 stage[PACK_THREADS * NP];
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) stage[t * NP + (j ^ (t & (NP - 1)))] = RowPack<T>::piece(v, j);
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(dst_block);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int l = i * PACK_THREADS + t, p = l / NP, j = (l % NP) ^ (p & (NP - 1));
+    if (p < valid) out[p * NP + j] = stage[l];
+  }
 }
 
 template <typename T, int KW, int CX>
-__global__ void pack_row_taps_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int H, int W) {
+__global__ void __launch_bounds__(PACK_THREADS)
+    pack_row_taps_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int H, int W) {
   constexpr int CH = ActTraits<T>::CHUNK;
   static_assert(KW * CX <= CH, "taps must fit one chunk");
-  const size_t HW = (size_t)H * W;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * HW) return;
-  const int n = (int)(i / HW) % Nsrc;
-  const size_t p = i % HW;
-  const int y = (int)(p / W), xx = (int)(p % W);
+  const size_t HW = (size_t)H * W, total = (size_t)N * HW;
+  const size_t i0 = (size_t)blockIdx.x * PACK_THREADS, i = i0 + threadIdx.x;
   float v[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) v[j] = 0.0f;
-  const float* row = x + (size_t)n * CX * HW + (size_t)y * W;
+  if (i < total) {
+    const int n = (int)(i / HW) % Nsrc;
+    const size_t p = i % HW;
+    const int y = (int)(p / W), xx = (int)(p % W);
+    const float* row = x + (size_t)n * CX * HW + (size_t)y * W;
 #pragma unroll
-  for (int s = 0; s < KW; ++s) {
-    const int xs = xx + s - KW / 2;
-    const bool ok = xs >= 0 && xs < W;
+    for (int s = 0; s < KW; ++s) {
+      const int xs = xx + s - KW / 2;
+      const bool ok = xs >= 0 && xs < W;
 #pragma unroll
-    for (int c = 0; c < CX; ++c) v[s * CX + c] = ok ? __ldg(row + (size_t)c * HW + xs) : 0.0f;
+      for (int c = 0; c < CX; ++c) v[s * CX + c] = ok ? __ldg(row + (size_t)c * HW + xs) : 0.0f;
+    }
   }
-  store_chunk<T>(dst + i * ActTraits<T>::pstride(CH), v);
+  emit_rows<T>(dst + i0 * ActTraits<T>::pstride(CH), v, (int)(total - i0 < (size_t)PACK_THREADS ? total - i0 : (size_t)PACK_THREADS));
 }
 
 template <typename T>
-__global__ void pack_disp_taps_kernel(const float* __restrict__ disp, T* __restrict__ dst, int N, int h, int w) {
+__global__ void __launch_bounds__(PACK_THREADS)
+    pack_disp_taps_kernel(const float* __restrict__ disp, T* __restrict__ dst, int N, int h, int w) {
   constexpr int CH = ActTraits<T>::CHUNK;
   const int H = 2 * h, W = 2 * w;
-  const size_t HW = (size_t)H * W;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * HW) return;
-  const int n = (int)(i / HW);
-  const size_t p = i % HW;
-  const int y = (int)(p / W), x = (int)(p % W);
+  const size_t HW = (size_t)H * W, total = (size_t)N * HW;
+  const size_t i0 = (size_t)blockIdx.x * PACK_THREADS, i = i0 + threadIdx.x;
   float v[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) v[j] = 0.0f;
+  if (i < total) {
+    const int n = (int)(i / HW);
+    const size_t p = i % HW;
+    const int y = (int)(p / W), x = (int)(p % W);
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int yy = y + r - 1, xx = x + s - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        v[3 * r + s] = __ldg(disp + ((size_t)n * h + (yy >> 1)) * w + (xx >> 1));  // nearest x2
-    }
-  store_chunk<T>(dst + i * ActTraits<T>::pstride(CH), v);
+      for (int s = 0; s < 3; ++s) {
+        const int yy = y + r - 1, xx = x + s - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v[3 * r + s] = __ldg(disp + ((size_t)n * h + (yy >> 1)) * w + (xx >> 1));  // nearest x2
+      }
+  }
+  emit_rows<T>(dst + i0 * ActTraits<T>::pstride(CH), v, (int)(total - i0 < (size_t)PACK_THREADS ? total - i0 : (size_t)PACK_THREADS));
 }
 
 // ---- refine-input aggregation ------------------------------------------------------------------
@@ -121,33 +211,35 @@ __device__ __forceinline__ float group_mean_at(const float* __restrict__ idepth,
 }
 
 template <typename T>
-__global__ void refine_taps_kernel(const float* __restrict__ idepth, T* __restrict__ taps, float* __restrict__ id_out,
-                                   int B, int H, int W, int group) {
+__global__ void __launch_bounds__(PACK_THREADS)
+    refine_taps_kernel(const float* __restrict__ idepth, T* __restrict__ taps, float* __restrict__ id_out, int B, int H,
+                       int W, int group) {
   constexpr int CH = ActTraits<T>::CHUNK;
   const size_t HW = (size_t)H * W, BHW = (size_t)B * HW;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BHW) return;
-  const int b = (int)(i / HW);
-  const size_t p = i % HW;
-  const int y = (int)(p / W), x = (int)(p % W);
+  const size_t i0 = (size_t)blockIdx.x * PACK_THREADS, i = i0 + threadIdx.x;
   float v[CH];
 #pragma unroll
   for (int j = 0; j < CH; ++j) v[j] = 0.0f;
+  if (i < BHW) {
+    const int b = (int)(i / HW);
+    const size_t p = i % HW;
+    const int y = (int)(p / W), x = (int)(p % W);
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int yy = y + r - 1, xx = x + s - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const size_t off = (size_t)b * HW + (size_t)yy * W + xx;
-        const float a = group_mean_at(idepth, 0, group, BHW, off), c = group_mean_at(idepth, 1, group, BHW, off);
-        v[3 * r + s] = a;
-        v[9 + 3 * r + s] = c;
-        v[18 + 3 * r + s] = fabsf(a - c);
-        if (r == 1 && s == 1 && id_out) { id_out[off] = a; id_out[BHW + off] = c; }
+      for (int s = 0; s < 3; ++s) {
+        const int yy = y + r - 1, xx = x + s - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const size_t off = (size_t)b * HW + (size_t)yy * W + xx;
+          const float a = group_mean_at(idepth, 0, group, BHW, off), c = group_mean_at(idepth, 1, group, BHW, off);
+          v[3 * r + s] = a;
+          v[9 + 3 * r + s] = c;
+          v[18 + 3 * r + s] = fabsf(a - c);
+          if (r == 1 && s == 1 && id_out) { id_out[off] = a; id_out[BHW + off] = c; }
+        }
       }
-    }
-  store_chunk<T>(taps + i * ActTraits<T>::pstride(CH), v);
+  }
+  emit_rows<T>(taps + i0 * ActTraits<T>::pstride(CH), v, (int)(BHW - i0 < (size_t)PACK_THREADS ? BHW - i0 : (size_t)PACK_THREADS));
 }
 
 // sum_act = mean_0(iconv) + mean_1(iconv) on act tensors [V*B,H,W,64]; one 16-byte vector per thread
@@ -336,6 +428,27 @@ __global__ void __launch_bounds__(256, 2) head3x3_kernel(const __grid_constant__
   }
 }
 
+// second half of a head fused into the producing convolution's epilogue (tc_common.cuh: epi_head_partial)
+__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ partial, float bias, float scale,
+                                                          float* __restrict__ out, float* __restrict__ logits, int N,
+                                                          int H, int W) {
+  const size_t total = (size_t)N * H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H);
+  float acc = bias;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int yy = y + r - 1, xx = x + s - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        acc += __ldg(partial + (i + (size_t)((r - 1) * W + (s - 1))) * HEAD_PARTIAL_STRIDE + 3 * r + s);
+    }
+  if (logits) logits[i] = acc;
+  out[i] = scale / (1.0f + expf(-acc));
+}
+
 template <typename T, int LPP>
 static int launch_head_lpp(const HeadParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static size_t configured = 0;
@@ -475,6 +588,15 @@ extern "C" int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, i
     upsample2x_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, N, h, w, C);
   });
   return after_launch("cnm_upsample2x");
+}
+
+extern "C" int cnm_head_finish(const float* partial, float bias, float scale, float* out, float* logits, int N, int H,
+                               int W, void* stream) {
+  CNM_REQUIRE(partial && out && N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_head_finish: bad argument");
+  const size_t total = (size_t)N * H * W;
+  head_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, bias, scale, out, logits, N,
+                                                                                       H, W);
+  return after_launch("cnm_head_finish");
 }
 
 extern "C" int cnm_head3x3(const void* x, const float* w, float bias, float scale, float* out, float* logits, int N,

@@ -100,19 +100,25 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
          ((uint64_t)2 << 61) /* SWIZZLE_128B */;
 }
 
-// ---- epilogue: one 128-byte output row of this thread's pixel -> 128B-swizzled staging tile ---------------------
-// v = the chunk's accumulator columns (64, or 32 for tf32), bs = their bias.  value = relu(acc * scale + bias).
+// ---- epilogue helpers ---------------------------------------------------------------------------------------------
+// epi_finalize: accumulator columns of this thread's pixel -> value = relu(acc * scale + bias), in place (fp32 bits).
+template <int COLS>
+__device__ __forceinline__ void epi_finalize(uint32_t* v, const float* bs, int relu, float scale) {
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    float t = fmaf(__uint_as_float(v[c]), scale, bs[c]);
+    v[c] = __float_as_uint(relu ? fmaxf(t, 0.0f) : t);
+  }
+}
+
+// epi_store_row: the finalised values of one chunk -> one 128-byte row of the 128B-swizzled staging tile.
 // mode 0: plain bf16 / tf32 row.  mode 1 (CNM_BF16X3): part 0 = bf16 hi row, part 1 = bf16 lo row.
 // mode 2 (CNM_F16F8): part 0 = fp16 row, part 1 = fp8 row [lo8 x 64 | hi8 x 64].
 enum { EPI_PLAIN = 0, EPI_BF16X3 = 1, EPI_F16F8 = 2 };
 
 template <bool TF32>
-__device__ __forceinline__ void epi_store_row(const uint32_t* v, const float* bs, uint8_t* rowp, int row, int relu,
-                                              int mode, int part, float scale) {
-  auto val = [&](int c) {
-    float t = fmaf(__uint_as_float(v[c]), scale, bs[c]);
-    return relu ? fmaxf(t, 0.0f) : t;
-  };
+__device__ __forceinline__ void epi_store_row(const uint32_t* v, uint8_t* rowp, int row, int mode, int part) {
+  auto val = [&](int c) { return __uint_as_float(v[c]); };
   if (TF32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -162,6 +168,31 @@ __device__ __forceinline__ void epi_store_row(const uint32_t* v, const float* bs
       *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
+}
+
+// Fused 1-channel 3x3 head (desc.head_w, Cout == 64): the nine per-tap dot products of this pixel's finalised fp32
+// output vector with the head weights ws [9][64] (shared memory), written as 12 floats (9 used) to dst.  A finishing
+// kernel (cnm_head_finish) adds the nine neighbours' contributions, the bias and the sigmoid.
+constexpr int HEAD_PARTIAL_STRIDE = 12;
+__device__ __forceinline__ void epi_head_partial(const uint32_t* v, const float* ws, float* dst) {
+  float acc[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) acc[t] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float4 w4 = *reinterpret_cast<const float4*>(ws + t * 64 + c);
+      acc[t] = fmaf(__uint_as_float(v[c]), w4.x, acc[t]);
+      acc[t] = fmaf(__uint_as_float(v[c + 1]), w4.y, acc[t]);
+      acc[t] = fmaf(__uint_as_float(v[c + 2]), w4.z, acc[t]);
+      acc[t] = fmaf(__uint_as_float(v[c + 3]), w4.w, acc[t]);
+    }
+  }
+  float4* o = reinterpret_cast<float4*>(dst);
+  o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  o[2] = make_float4(acc[8], 0.0f, 0.0f, 0.0f);
 }
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)

@@ -20,6 +20,7 @@ BN_EPS = 1e-5
 # which stride-1 layers use the row-halo kernel: "auto" (enough tiles for a wave), "force" (every eligible layer,
 # used by tests), "off" (per-tap kernel everywhere)
 HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
+FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
 TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32, CNM_BF16X3: torch.bfloat16, CNM_F16F8: torch.float16}
 F8_LO_SCALE, F8_HI_SCALE = 128.0, 0.0625   # csrc/common.cuh: lo8 = e4m3((v - hi) * 2^7), hi8 = e4m3(hi * 2^-4)
@@ -375,6 +376,12 @@ class ConvOp:
         self.tuned = best
         self.select(best[0], best[1])
 
+    def fuse_head(self, w_tap_major, partial):
+        """Fused 1-channel 3x3 head on this layer's output (cnm_conv_desc.head_w / head_partial); Cout must be 64."""
+        assert self.desc.Cout == 64 and self.dtype != CNM_TF32
+        self._head = (w_tap_major, partial)
+        self.desc.head_w, self.desc.head_partial = w_tap_major.data_ptr(), partial.data_ptr()
+
     def load(self, wf, bf):
         self._weights = (wf, bf)
         if self.dtype == CNM_F16F8:
@@ -441,6 +448,18 @@ class _Plan:
         self.heads[name] = hw
         lib, dt = self.lib, self.dtype
         lp = logits.data_ptr() if logits is not None else None
+        producer = [op for op in self.convs.values() if op.out is x]
+        if FUSE_HEADS and Cc == 64 and dt != CNM_TF32 and self.backend != "simt" and producer:
+            # 64-channel heads ride in the producing convolution's epilogue (nine per-tap dot products per pixel from
+            # the fp32 accumulators); what is left is a 3x3 gather of scalars + bias + sigmoid
+            op = producer[0]
+            partial = self.buf(N, H, W, 12, dtype=torch.float32)
+            hw["w_tap_major"] = torch.zeros((9, 64), dtype=torch.float32, device=self.device)
+            hw["partial"] = partial
+            op.fuse_head(hw["w_tap_major"], partial)
+            self.ops.append(lambda s: _lib.check(
+                lib.cnm_head_finish(partial.data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s), name))
+            return out, logits
         self.ops.append(lambda s: _lib.check(
             lib.cnm_head3x3(x.data_ptr(), hw["w"].data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, Cc,
                             dt, s), name))
@@ -458,6 +477,8 @@ class _Plan:
         hw = self.heads[name]
         w = sd[name + ".0.weight"].to(self.device, torch.float32)  # [1, C, 3, 3] -> (r, s, c)
         hw["w"].copy_(w[0].permute(1, 2, 0).reshape(-1))
+        if "w_tap_major" in hw:
+            hw["w_tap_major"].copy_(w[0].permute(1, 2, 0).reshape(9, -1))
         hw["bias"] = float(sd[name + ".0.bias"].reshape(-1)[0])
 
     def tune(self):

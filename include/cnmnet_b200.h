@@ -150,6 +150,11 @@ int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, int C, int d
 int cnm_head3x3(const void* x, const float* w, float bias, float scale, float* out, float* logits, int N, int H,
                 int W, int C, int dtype, void* stream);
 
+/* second half of a fused head (cnm_conv_desc.head_partial): out(y,x) = scale * sigmoid(bias + sum over the 3x3
+ * neighbourhood of partial[y+r-1][x+s-1][3r+s]), zero outside the image; logits (may be NULL) gets the pre-sigmoid sum */
+int cnm_head_finish(const float* partial, float bias, float scale, float* out, float* logits, int N, int H, int W,
+                    void* stream);
+
 /* ---- convolution as implicit GEMM --------------------------------------------------------
  * replaces nn.Conv2d + BatchNorm2d(eval) + ReLU and the torch.cat of its inputs
  * (depthnet/depthNet_model.py:19-112, 235-261, 335-365).
@@ -184,6 +189,13 @@ typedef struct cnm_conv_desc {
   int32_t reserved; /* 0 = library picks the output-channel tile; 64 / 128 / 256 = caller-selected (autotuner) */
   int32_t acc_exp;  /* the accumulator is scaled by 2^-acc_exp before bias / ReLU (CNM_F16F8 weight scale; else 0) */
   int32_t reserved2[3];
+  /* Optional fused 1-channel 3x3 head on this layer's output (depth_layer, depthnet/depthNet_model.py:82-84), for
+   * Cout == 64 and the 2-byte dtypes (tensor-core kernels only): head_w = [9][64] fp32 tap-major weights (device),
+   * head_partial = [N, Ho, Wo, 12] fp32 (device, 16B aligned) receiving, per pixel, the nine per-tap dot products of
+   * the fp32 output vector (entries 9..11 are zero).  cnm_head_finish() turns them into the head's output.  Both
+   * NULL = no fused head.                                                                                          */
+  const float* head_w;
+  float* head_partial;
 } cnm_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM (the product path).  `steps` is a DEVICE array of

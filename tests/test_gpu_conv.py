@@ -143,6 +143,39 @@ def test_f16f8_accuracy_class(backend):
     assert errs[_lib.CNM_F16F8] < 3e-5 and errs[_lib.CNM_F16F8] < errs[_lib.CNM_BF16] / 50, errs
 
 
+@pytest.mark.parametrize("dtype", [_lib.CNM_BF16, _lib.CNM_BF16X3, _lib.CNM_F16F8])
+@pytest.mark.parametrize("backend", ["tc", "halo", "halo2"])
+def test_fused_head_matches_separate_head(backend, dtype):
+    """cnm_conv_desc.head_w / head_partial + cnm_head_finish: the 1-channel 3x3 head computed from the fp32 accumulators in
+    the convolution epilogue equals conv3x3(+bias) -> scale * sigmoid on the (unrounded) layer output; partial tiles."""
+    N, H, W, cin, k = 2, 24, 40, 64, 3
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(64, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    b = torch.randn(64, generator=g)
+    hw = torch.randn(1, 64, 3, 3, generator=g) * 0.05
+    act = to_act(x, dtype)
+    op = engine.ConvOp("t", [engine.act_src(act, 0, phys=engine.phys_factor(dtype))], k, 1, 64, N, H, W, dtype, dev(), True,
+                       backend=backend)
+    wt = hw[0].permute(1, 2, 0).reshape(9, 64).contiguous().to(dev())
+    partial = torch.full((N, H, W, 12), float("nan"), device=dev())
+    op.fuse_head(wt, partial)
+    op.load(w, b)
+    op(_lib.stream_ptr())
+    out = torch.empty((N, 1, H, W), device=dev())
+    logits = torch.empty((N, 1, H, W), device=dev())
+    lib = _lib.load()
+    _lib.check(lib.cnm_head_finish(partial.data_ptr(), 0.25, 3.0, out.data_ptr(), logits.data_ptr(), N, H, W,
+                                   _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    want_act = oracle_conv(dtype, [x], w, b, k, 1)                         # fp32 layer output before storage rounding
+    assert rel_l2(from_act(op.out, dtype), quantize(want_act, dtype)) < L2_TOL[dtype]   # the act output is still written
+    wl = F.conv2d(want_act.double(), hw.double(), torch.tensor([0.25], dtype=torch.float64), padding=1)
+    assert not torch.isnan(partial).any()
+    assert (logits.cpu() - wl.float()).abs().max() < 2e-5 * max(1.0, wl.abs().max().item())
+    assert (out.cpu() - 3.0 * torch.sigmoid(wl).float()).abs().max() < 1e-5
+
+
 def test_conv_rejects_bad_arguments():
     lib = _lib.load()
     a = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=dev())  # 48 channels: not chunk aligned
