@@ -331,6 +331,82 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ s
     }
 }
 
+// CNM_F16F8 specialisation: the generic kernel is instruction-bound in this layout (address-derived fp8 row pointers,
+// 64-bit index arithmetic per load, saturation clamps); here every offset is a 32-bit byte offset inside the image, the
+// hi8 bytes come from the fp16 pair through the f16x2 -> e4m3x2 conversion, and no clamp is needed (a convex
+// combination of finite fp16 values stays finite).
+__device__ __forceinline__ void load_h16f8_vec(const uint8_t* __restrict__ hi, const uint8_t* __restrict__ lo, float* f) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(hi));
+  const uint2 l = __ldg(reinterpret_cast<const uint2*>(lo));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t lw[4] = {l.x & 0xffffu, l.x >> 16, l.y & 0xffffu, l.y >> 16};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    const float2 q = e4m3x2_to_float2(lw[i]);
+    f[2 * i] = fmaf(q.x, 1.0f / F8_LO_SCALE, h.x);
+    f[2 * i + 1] = fmaf(q.y, 1.0f / F8_LO_SCALE, h.y);
+  }
+}
+__device__ __forceinline__ void store_h16f8_vec(uint8_t* __restrict__ hi, uint8_t* __restrict__ lo, const float* f) {
+  uint32_t w[4], lw[4], hw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    const float2 hf = __half22float2(h);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lw[i] = e4m3x2((f[2 * i] - hf.x) * F8_LO_SCALE, (f[2 * i + 1] - hf.y) * F8_LO_SCALE);
+    const __half2 hs = __hmul2(h, __float2half2_rn(F8_HI_SCALE));  // exact unless far below the e4m3 range
+    hw[i] = (uint32_t)__nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E4M3);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint2*>(lo) = make_uint2(lw[0] | (lw[1] << 16), lw[2] | (lw[3] << 16));
+  *reinterpret_cast<uint2*>(lo + 64) = make_uint2(hw[0] | (hw[1] << 16), hw[2] | (hw[3] << 16));
+}
+
+__global__ void __launch_bounds__(256)
+    upsample2x_h16f8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int N, int h, int w, int C) {
+  const int cv = C >> 3;
+  const unsigned total = (unsigned)(N * h * w * cv);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % cv);
+  unsigned t = i / cv;
+  const int x = (int)(t % w);
+  t /= w;
+  const int y = (int)(t % h);
+  const int n = (int)(t / h);
+  const unsigned PB = 4u * C;                                          // bytes per pixel (2 x 2 bytes per channel)
+  const unsigned hi_off = (unsigned)(c8 >> 3) * 256u + (unsigned)(c8 & 7) * 16u;   // inside the pixel
+  const unsigned lo_off = (unsigned)(c8 >> 3) * 256u + 128u + (unsigned)(c8 & 7) * 8u;
+  const uint8_t* img = src + (size_t)n * h * w * PB;
+  const int xs[3] = {max(x - 1, 0), x, min(x + 1, w - 1)}, ys[3] = {max(y - 1, 0), y, min(y + 1, h - 1)};
+  float v[3][3][8];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const unsigned po = (unsigned)(ys[a] * w + xs[b]) * PB;
+      load_h16f8_vec(img + po + hi_off, img + po + lo_off, v[a][b]);
+    }
+  const unsigned W2 = 2u * w;
+  uint8_t* out = dst + (size_t)n * 4 * h * w * PB;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const float fx = dx ? 0.25f : 0.75f, fy = dy ? 0.25f : 0.75f;  // fraction toward the right / lower tap
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a00 = v[dy][dx][j], a01 = v[dy][dx + 1][j], a10 = v[dy + 1][dx][j], a11 = v[dy + 1][dx + 1][j];
+        o[j] = a00 * ((1.f - fx) * (1.f - fy)) + a01 * (fx * (1.f - fy)) + a10 * ((1.f - fx) * fy) + a11 * (fx * fy);
+      }
+      const unsigned po = ((unsigned)(2 * y + dy) * W2 + (unsigned)(2 * x + dx)) * PB;
+      store_h16f8_vec(out + po + hi_off, out + po + lo_off, o);
+    }
+}
+
 // ---- 1-channel 3x3 head --------------------------------------------------------------------------------------
 // CTA = 32 x TR output pixels.  The (TR+2) x 34 halo of the input (all channels) is staged in shared memory by TMA
 // (one or two 4-D boxes {<=256 ch, 34, TR+2, 1}; pixels outside the image are zero-filled = conv padding), so the
@@ -447,6 +523,68 @@ __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restric
     }
   if (logits) logits[i] = acc;
   out[i] = scale / (1.0f + expf(-acc));
+}
+
+// First half of a head as a stand-alone pass (layers whose head is not fused into the producing convolution): every
+// pixel's C-vector is read and decoded ONCE and dotted with the nine tap weight vectors -> 12 floats per pixel (the
+// layout epi_head_partial writes); head_finish_kernel does the 3x3 gather.  LPP lanes per pixel, 16-byte vectors.
+template <typename T, int LPP>
+__global__ void __launch_bounds__(256) head_partial_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                           float* __restrict__ partial, size_t npix, int C) {
+  extern __shared__ float hp_ws[];  // [9][C]
+  constexpr int VN = Vec16<T>::N, GROUPS = 256 / LPP;
+  for (int i = threadIdx.x; i < 9 * C; i += 256) hp_ws[i] = __ldg(w + i);
+  __syncthreads();
+  const int sub = threadIdx.x % LPP, grp = threadIdx.x / LPP;
+  const size_t PC = ActTraits<T>::pstride(C);
+  for (size_t pix = (size_t)blockIdx.x * GROUPS + grp; pix < npix; pix += (size_t)gridDim.x * GROUPS) {
+    float acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.0f;
+    const T* px = x + pix * PC;
+    for (int c = sub * VN; c < C; c += LPP * VN) {
+      float v[VN];
+      Vec16<T>::load(px + ActTraits<T>::phys(c), v);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float* wp = hp_ws + t * C + c;
+#pragma unroll
+        for (int j = 0; j < VN; j += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wp + j);
+          acc[t] = fmaf(v[j], w4.x, acc[t]);
+          acc[t] = fmaf(v[j + 1], w4.y, acc[t]);
+          acc[t] = fmaf(v[j + 2], w4.z, acc[t]);
+          acc[t] = fmaf(v[j + 3], w4.w, acc[t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int o = 1; o < LPP; o <<= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+    if (sub == 0) {
+      float4* o = reinterpret_cast<float4*>(partial + pix * HEAD_PARTIAL_STRIDE);
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      o[2] = make_float4(acc[8], 0.0f, 0.0f, 0.0f);
+    }
+  }
+}
+
+template <typename T>
+static int launch_head_partial(const T* x, const float* w, float* partial, size_t npix, int C, cudaStream_t s) {
+  const int lanes = C / Vec16<T>::N;
+  const size_t smem = (size_t)9 * C * sizeof(float);
+  long blocks = 148 * 8;
+#define CNM_HP(LPP)                                                                         \
+  {                                                                                         \
+    const long need = (long)((npix + 256 / LPP - 1) / (256 / LPP));                         \
+    if (need < blocks) blocks = need;                                                       \
+    head_partial_kernel<T, LPP><<<(unsigned)blocks, 256, smem, s>>>(x, w, partial, npix, C); \
+  }
+  if (lanes >= 32) CNM_HP(32) else if (lanes >= 16) CNM_HP(16) else CNM_HP(8)
+#undef CNM_HP
+  return CNM_OK;
 }
 
 template <typename T, int LPP>
@@ -583,11 +721,33 @@ extern "C" int cnm_refine_aggregate_nchw(const float* idepth, const float* iconv
 extern "C" int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, int C, int dtype, void* stream) {
   CNM_REQUIRE(src && dst && N > 0 && h > 0 && w > 0 && C > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_upsample2x: bad argument");
   CNM_REQUIRE(C % 8 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_upsample2x: C=%d must be a multiple of 8", C);
+  if (dtype == CNM_F16F8 && C % 64 == 0 && (size_t)N * 4 * h * w * 4 * C < ((size_t)1 << 32) * 64) {
+    // 32-bit offsets inside one image: 4*h*w*4*C bytes per output image must fit 32 bits
+    CNM_REQUIRE((size_t)4 * h * w * 4 * C < ((size_t)1 << 32) && (size_t)N * h * w * (C / 8) < ((size_t)1 << 32),
+                CNM_ERR_UNSUPPORTED_SHAPE, "cnm_upsample2x: image too large for 32-bit offsets");
+    const size_t total = (size_t)N * h * w * (C / 8);
+    upsample2x_h16f8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint8_t*)src, (uint8_t*)dst, N, h, w, C);
+    return after_launch("cnm_upsample2x");
+  }
   DISPATCH_DTYPE(dtype, {
     const size_t total = (size_t)N * h * w * (C / Vec16<T>::N);
     upsample2x_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, N, h, w, C);
   });
   return after_launch("cnm_upsample2x");
+}
+
+extern "C" int cnm_head_partial(const void* x, const float* w_tap_major, float* partial, int N, int H, int W, int C,
+                                int dtype, void* stream) {
+  CNM_REQUIRE(x && w_tap_major && partial && N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_head_partial: bad argument");
+  CNM_REQUIRE(C % 64 == 0 && C <= 1024, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_head_partial: C=%d must be a multiple of 64", C);
+  CNM_REQUIRE(((uintptr_t)partial & 15) == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_head_partial: partial must be 16B aligned");
+  DISPATCH_DTYPE(dtype, {
+    int rc = launch_head_partial<T>((const T*)x, w_tap_major, partial, (size_t)N * H * W, C, (cudaStream_t)stream);
+    if (rc) return rc;
+  });
+  return after_launch("cnm_head_partial");
 }
 
 extern "C" int cnm_head_finish(const float* partial, float bias, float scale, float* out, float* logits, int N, int H,

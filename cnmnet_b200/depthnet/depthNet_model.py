@@ -120,7 +120,9 @@ class depthNet(_KernelNet):
 
     def getVolume(self, left_image, right_image, KRKiUV_T, KT_T):
         """[B,3,H,W] x2, KRKiUV_T [B,3,W*H] (x-major), KT_T [B,3,1] -> cost volume [B,planes (64),H,W] fp32
-        (depthNet_model.py:185-224).  The 3x3 homography is recovered from three columns of KRKiUV_T."""
+        (depthNet_model.py:185-224).  The 3x3 homography is recovered from three columns of KRKiUV_T: the origin and
+        the two FARTHEST pixels along x and y, differenced in fp64, so that the fp32 rounding of the tabulated values
+        is divided by W-1 / H-1 instead of being multiplied by the pixel coordinate."""
         _check_image_pair(left_image, right_image)
         B, _, H, W = left_image.shape
         s = float(self.idepth_scale)
@@ -130,10 +132,11 @@ class depthNet(_KernelNet):
             idmin, idmax = 0.1, 3.0
         else:
             raise ValueError("idepth_scale must be 2.0 or 3.0")
-        a00 = KRKiUV_T[:, :, 0]          # Hm.[0,0,1]
-        col0 = KRKiUV_T[:, :, H] - a00   # flat index x*H + y
-        col1 = KRKiUV_T[:, :, 1] - a00
-        hk = torch.cat([torch.stack([col0, col1, a00], dim=2).reshape(B, 9), KT_T.reshape(B, 3)], 1).float().contiguous()
+        a00 = KRKiUV_T[:, :, 0].double()                                            # Hm.[0,0,1]
+        col0 = (KRKiUV_T[:, :, (W - 1) * H].double() - a00) / max(W - 1, 1)         # flat index x*H + y
+        col1 = (KRKiUV_T[:, :, H - 1].double() - a00) / max(H - 1, 1)
+        hk = torch.cat([torch.stack([col0, col1, a00], dim=2).reshape(B, 9), KT_T.reshape(B, 3).double()],
+                       1).float().contiguous()
         lib = _lib.load()
         st = _lib.stream_ptr()
         left = left_image.float().contiguous()

@@ -460,6 +460,20 @@ class _Plan:
             self.ops.append(lambda s: _lib.check(
                 lib.cnm_head_finish(partial.data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s), name))
             return out, logits
+        if FUSE_HEADS:
+            # two passes: per-pixel tap dot products (each input element read and decoded once), then the 3x3 gather
+            partial = self.buf(N, H, W, 12, dtype=torch.float32)
+            hw["w_tap_major"] = torch.zeros((9, Cc), dtype=torch.float32, device=self.device)
+            hw["partial"] = partial
+
+            def two_pass(s):
+                _lib.check(lib.cnm_head_partial(x.data_ptr(), hw["w_tap_major"].data_ptr(), partial.data_ptr(), N, H, W, Cc,
+                                                dt, s), name)
+                _lib.check(lib.cnm_head_finish(partial.data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s),
+                           name)
+
+            self.ops.append(two_pass)
+            return out, logits
         self.ops.append(lambda s: _lib.check(
             lib.cnm_head3x3(x.data_ptr(), hw["w"].data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, Cc,
                             dt, s), name))

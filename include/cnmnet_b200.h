@@ -150,6 +150,12 @@ int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, int C, int d
 int cnm_head3x3(const void* x, const float* w, float bias, float scale, float* out, float* logits, int N, int H,
                 int W, int C, int dtype, void* stream);
 
+/* The same head in two passes, the form the pipeline uses: cnm_head_partial reads every pixel once and writes the nine
+ * per-tap dot products of its C-vector with w_tap_major [9][C] (fp32, tap t = 3r+s) as 12 floats per pixel
+ * (partial [N,H,W,12], entries 9..11 zero); 64-channel layers get the same partials for free from the producing
+ * convolution's epilogue (cnm_conv_desc.head_partial).  cnm_head_finish gathers the 3x3 neighbourhood.            */
+int cnm_head_partial(const void* x, const float* w_tap_major, float* partial, int N, int H, int W, int C, int dtype,
+                     void* stream);
 /* second half of a fused head (cnm_conv_desc.head_partial): out(y,x) = scale * sigmoid(bias + sum over the 3x3
  * neighbourhood of partial[y+r-1][x+s-1][3r+s]), zero outside the image; logits (may be NULL) gets the pre-sigmoid sum */
 int cnm_head_finish(const float* partial, float bias, float scale, float* out, float* logits, int N, int H, int W,

@@ -89,7 +89,7 @@ def test_cost_volume_ragged_shapes_and_identity_pose(H, W):
     KRKiUV, KT = cnmnet_b200.process_camera_parameters(_cuda(lcam), _cuda(rcam), pix)
     vol = net.getVolume(_cuda(left), _cuda(right), KRKiUV, KT).cpu().numpy()
     exact = ocv.cost_volume(left, right, lcam, rcam, 64, 0.1, 3.0)
-    assert rel_l2(vol, exact) < 2e-5
+    assert rel_l2(vol, exact) < 1e-5
 
 
 # ------------------------------------------------------------------ K3 normals, K3b CNM
@@ -206,6 +206,13 @@ def test_upsample_head_packers(dtype):
     wl = F.conv2d(quantize(x, dtype).double(), w.double(), torch.tensor([0.25], dtype=torch.float64), padding=1)
     assert (logit.cpu() - wl.float()).abs().max() < 1e-4
     assert (out.cpu() - 3.0 * torch.sigmoid(wl).float()).abs().max() < 1e-5
+    # the same head in two passes (per-pixel tap dot products, then the 3x3 gather): what the pipeline runs
+    part = torch.full((2, 6, 10, 12), float("nan"), device=dev())
+    wt = w[0].permute(1, 2, 0).reshape(9, 64).contiguous().to(dev())
+    out2, logit2 = torch.empty_like(out), torch.empty_like(logit)
+    _lib.check(lib.cnm_head_partial(xa.data_ptr(), wt.data_ptr(), part.data_ptr(), 2, 6, 10, 64, dtype, st))
+    _lib.check(lib.cnm_head_finish(part.data_ptr(), 0.25, 3.0, out2.data_ptr(), logit2.data_ptr(), 2, 6, 10, st))
+    assert (logit2.cpu() - wl.float()).abs().max() < 1e-4 and (out2.cpu() - out.cpu()).abs().max() < 1e-5
     # disparity taps: nearest x2 then 3x3 taps
     disp = torch.rand(2, 1, 6, 10, generator=g)
     t = act_empty((2, 12, 20, ch), dtype)
@@ -227,6 +234,28 @@ def test_upsample_head_packers(dtype):
         for s in range(7):
             for c in range(3):
                 assert torch.equal(got[n, s * 3 + c], quantize(pi[n % 2, c, :, s:s + 10], dtype))
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+@pytest.mark.parametrize("C,H,W", [(128, 12, 20), (256, 9, 16), (512, 6, 8)])
+def test_wide_heads_both_forms(dtype, C, H, W):
+    """disp2 / disp3 / disp4-sized heads: the one-kernel form (cnm_head3x3) and the two-pass form agree with torch."""
+    lib, st = _lib.load(), _lib.stream_ptr()
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(3, C, H, W, generator=g).abs()
+    w = torch.randn(1, C, 3, 3, generator=g) * 0.02
+    xa = to_act(x, dtype)
+    wl = F.conv2d(quantize(x, dtype).double(), w.double(), torch.tensor([-0.1], dtype=torch.float64), padding=1).float()
+    wv = w[0].permute(1, 2, 0).reshape(-1).contiguous().to(dev())
+    out, logit = torch.empty((3, 1, H, W), device=dev()), torch.empty((3, 1, H, W), device=dev())
+    _lib.check(lib.cnm_head3x3(xa.data_ptr(), wv.data_ptr(), -0.1, 2.0, out.data_ptr(), logit.data_ptr(), 3, H, W, C, dtype, st))
+    part = torch.empty((3, H, W, 12), device=dev())
+    out2, logit2 = torch.empty_like(out), torch.empty_like(logit)
+    _lib.check(lib.cnm_head_partial(xa.data_ptr(), wv.data_ptr(), part.data_ptr(), 3, H, W, C, dtype, st))
+    _lib.check(lib.cnm_head_finish(part.data_ptr(), -0.1, 2.0, out2.data_ptr(), logit2.data_ptr(), 3, H, W, st))
+    for lg, o in ((logit, out), (logit2, out2)):
+        assert (lg.cpu() - wl).abs().max() < 2e-4
+        assert (o.cpu() - 2.0 * torch.sigmoid(wl)).abs().max() < 5e-5
 
 
 def test_reciprocal_and_inverse_warp(golden_dir):
