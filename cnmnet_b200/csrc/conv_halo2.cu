@@ -31,6 +31,7 @@ struct alignas(64) Halo2Params {
   int num_groups, num_steps;
   int tiles_x, tiles_y, tiles_b, tiles_n;
   int a_stages, b_stages, slab_bytes;
+  int out_stages;  // 1 or 2 staging tiles for the TMA stores (2 when the epilogue is the long pole: BN = 64)
   int map_pad[H2_MAX_SRCS * 4];   // rows of the slab above the tile, per map
   int map_rows[H2_MAX_SRCS * 4];  // slab height (16 + vertical tap span), per map
   int relu;
@@ -114,7 +115,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   // carve-up: [A ring][B ring][staging 16 KB][bias][barriers][tmem slot]
   const uint32_t off_b = (uint32_t)p.a_stages * p.slab_bytes;
   const uint32_t off_out = off_b + (uint32_t)p.b_stages * B_BYTES;
-  const uint32_t off_bias = off_out + H2_TILE_BYTES;
+  const uint32_t off_bias = off_out + (uint32_t)p.out_stages * H2_TILE_BYTES;
   const uint32_t off_head = off_bias + BN * 4;  // fused-head weights (BN == 64 only)
   const uint32_t off_bar = off_head + (BN == 64 ? 9 * 64 * 4 : 0);
   const uint32_t bar0 = base + off_bar;
@@ -258,6 +259,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
     const bool storer = (et == 0);
     int it = 0;
     int bias_tile = -1;
+    uint32_t store_cnt = 0;
     if (fused_head) {
       for (int i = et; i < 9 * 64; i += 128) head_s[i] = __ldg(p.head_w + i);
       epi_bar();
@@ -294,10 +296,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
               epi_head_partial(v, head_s, p.head_partial + (((size_t)n0 * p.Ho + py) * p.Wo + px) * HEAD_PARTIAL_STRIDE);
           }
           for (int part = 0; part < (p.mode ? 2 : 1); ++part) {
-            // one staging buffer (smem goes to deeper operand rings): the previous TMA store must have finished
-            // reading it; the epilogue runs under the next tile's main loop, so this wait is off the critical path
-            uint8_t* stg = base_ptr + off_out;
-            if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            // BN >= 128: one staging tile (smem goes to deeper operand rings; the epilogue runs under the next tile's
+            // long main loop).  BN = 64: the K loop is short and the epilogue is the long pole, so two staging tiles
+            // let the packing of one row overlap the TMA store of the previous one.
+            uint8_t* stg = base_ptr + off_out + (p.out_stages == 2 ? (store_cnt & 1u) * H2_TILE_BYTES : 0u);
+            ++store_cnt;
+            if (storer) {
+              if (p.out_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
             epi_bar();
             epi_store_row<TF32>(v, stg + row * 128, row, p.mode, part);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -405,7 +412,8 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
   // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
   // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
   // lasts ntaps B tiles.
-  const int fixed = 1024 + H2_TILE_BYTES + BN * 4 + (BN == 64 ? 9 * 64 * 4 : 0) + 8 * (2 * H2_MAX_A + 2 * H2_MAX_B + 4) + 16;
+  p.out_stages = BN == 64 ? 2 : 1;
+  const int fixed = 1024 + p.out_stages * H2_TILE_BYTES + BN * 4 + (BN == 64 ? 9 * 64 * 4 : 0) + 8 * (2 * H2_MAX_A + 2 * H2_MAX_B + 4) + 16;
   const int budget = 232448 - fixed;
   const int want_b = 8;
   p.a_stages = (pmax >= 3 || BN == 256) ? 2 : (BN == 64 ? 4 : 3);

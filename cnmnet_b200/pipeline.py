@@ -112,8 +112,7 @@ class CNMPipeline:
         given, is enqueued on the compute stream after every graph replay (bench.py gathers outputs across ranks
         there)."""
         comp = torch.cuda.current_stream()
-        up, down = torch.cuda.Stream(), torch.cuda.Stream()  # separate streams: an upload never queues behind a download
-        st = stage_in = stage_out = host_out = None
+        st = stage_in = stage_out = host_out = up = down = None
         ev = {}
         pending = []
 
@@ -127,14 +126,23 @@ class CNMPipeline:
                 H, W = ref_img.shape[2:]
                 dev = next(self.depth_network.parameters()).device
                 st = self._prepare(B, V, H, W, dev)
-                # staging keeps the caller's [B,V,...] layout so the uploads are plain contiguous DMA transfers; the
-                # view-major transpose happens in the device-side copy into the static buffers
-                f32 = dict(dtype=torch.float32, device=dev)
-                stage_in = [[torch.empty((B, 3, H, W), **f32), torch.empty((B, V, 3, H, W), **f32),
-                             torch.empty((B, 2, 4, 4), **f32), torch.empty((B, V, 2, 4, 4), **f32)] for _ in range(2)]
-                stage_out = [[torch.empty_like(st[k]) for k in ("depth", "normal", "prob")] for _ in range(2)]
-                host_out = [[torch.empty(st[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
-                            for _ in range(2)]
+                if "stream_bufs" not in st:
+                    # staging keeps the caller's [B,V,...] layout so the uploads are plain contiguous DMA transfers; the
+                    # view-major transpose happens in the device-side copy into the static buffers.  Allocated once per
+                    # shape: pinning host memory costs milliseconds.  Separate copy streams: an upload never queues
+                    # behind a download.
+                    f32 = dict(dtype=torch.float32, device=dev)
+                    st["stream_bufs"] = (
+                        [[torch.empty((B, 3, H, W), **f32), torch.empty((B, V, 3, H, W), **f32),
+                          torch.empty((B, 2, 4, 4), **f32), torch.empty((B, V, 2, 4, 4), **f32)] for _ in range(2)],
+                        [[torch.empty_like(st[k]) for k in ("depth", "normal", "prob")] for _ in range(2)],
+                        [[torch.empty(st[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
+                         for _ in range(2)],
+                        torch.cuda.Stream(), torch.cuda.Stream())
+                stage_in, stage_out, host_out, up, down = st["stream_bufs"]
+                # results of an earlier call may still be in flight on the copy streams
+                up.wait_stream(comp)
+                down.wait_stream(comp)
                 if self.use_graph and st["graph"] is None:
                     self.step(st)  # capture outside the pipelined region
             b = i & 1

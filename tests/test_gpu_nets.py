@@ -154,7 +154,7 @@ def test_pipeline_odd_pyramid_sizes(H, W, B, precision):
     assert np.abs(p.cpu().numpy() - want_p).max() < 2e-3
 
 
-@pytest.mark.parametrize("precision", ["f16f8", "tf32"])
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
 def test_pipeline_128_planes(precision):
     """BASELINE config 5's plane count: depthNet(planes=128) = the same sweep at 128 hypotheses, conv1.0 with 3 + 128
     input channels (an extension: the reference hard-codes 64).  Checked against the oracle wiring with the same
@@ -181,8 +181,12 @@ def test_pipeline_128_planes(precision):
     d, n, p = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))
     want_d, want_n, want_p = _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, 9, planes=D)
     rel = np.abs(d.cpu().numpy() - want_d) / np.abs(want_d)
-    _, t_p99, t_max, t_mean = TOL[(precision, "tc")]
-    assert np.percentile(rel, 99) < t_p99 and rel.max() < t_max and rel.mean() < t_mean, \
+    # These weights are the most error-sensitive set in the suite (CPU emulation of the operand roundings,
+    # tools/emulate_modes.py: tf32 mean 1.6e-3 / max 1e-2; f16f8 mean 5.7e-5 / max 2.9e-4, which the fp32-FMA SIMT twin
+    # reproduces on the GPU).  On the tensor cores the floor is the fp32 accumulation inside tcgen05.mma, which grows
+    # with the number of MMA instructions per accumulator (tools/acc_floor.py: f16f8 mean 4.4e-4 / max 1.1e-3, bf16x3
+    # with 1.5x the instructions 6.2e-4 / 1.4e-3): gate at the tf32-class tolerance here.
+    assert np.percentile(rel, 99) < 1.5e-3 and rel.max() < 2.5e-3 and rel.mean() < 8e-4, \
         (np.percentile(rel, 99), rel.max(), rel.mean())
 
 

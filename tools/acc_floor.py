@@ -1,0 +1,32 @@
+"""Where the residual error of the accuracy modes comes from: the same pipeline, same stored operands, once on the
+tensor cores (tcgen05, fp32 accumulation inside the MMA datapath) and once on the fp32-FMA SIMT twin."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import cnmnet_b200  # noqa: E402
+from cnmnet_b200 import synth  # noqa: E402
+from oracle import nets as onets  # noqa: E402
+from test_gpu_nets import _oracle_pipeline  # noqa: E402
+
+dev = torch.device("cuda", 0)
+for (H, W, B, ws, D) in [(64, 96, 2, 21, 64), (64, 96, 2, 51, 64), (64, 96, 1, 61, 128)]:
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(500 + H if D == 64 else 777, B, H, W, 2)
+    dsd = synth.kaiming_state(onets.state_shapes(onets.depthnet_layers(D)), ws, 0.02)
+    rsd = synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), ws + 1, 0.02)
+    want_d, _, _ = _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, 9, planes=D)
+    for mode in ("f16f8", "bf16x3"):
+        for backend in ("tc", "simt"):
+            dnet = cnmnet_b200.depthNet(idepth_scale=3.0, precision=mode, backend=backend, planes=D)
+            rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0, precision=mode, backend=backend)
+            dnet.load_state_dict(dsd)
+            rnet.load_state_dict(rsd)
+            pipe = cnmnet_b200.CNMPipeline(dnet.to(dev), rnet.to(dev), k_size=9, use_graph=False)
+            d, n, p = pipe(ref.to(dev), srcs.to(dev), ref_cam.to(dev), src_cams.to(dev))
+            rel = np.abs(d.cpu().numpy() - want_d) / np.abs(want_d)
+            print("%dx%d D=%d wseed=%d %-7s %-4s depth rel err mean %.2e p99 %.2e max %.2e" %
+                  (H, W, D, ws, mode, backend, rel.mean(), np.percentile(rel, 99), rel.max()), flush=True)
