@@ -372,7 +372,9 @@ def main():
             for name, op in plan.convs.items():
                 ms, _ = time_events(lambda: op(s), 5, flush)
                 conv_ms += ms
-                conv_rows.append(("%s.%s [%s/%d]" % (tag, name, op.backend, op.desc.reserved), ms, op.flops_bf16_time))
+                conv_rows.append(("%s.%s [%s/%d%s]" % (tag, name, op.backend, op.desc.reserved,
+                                                      "/k%d" % op.desc.ksplit if op.desc.ksplit > 1 else ""), ms,
+                                  op.flops_bf16_time))
         alg_flop = B * (V * DEPTHNET_GFLOP + REFINE_GFLOP) * 1e9  # real channels only (no padding)
         issued_flop = sum(r[2] for r in conv_rows)
         tf = alg_flop / (conv_ms * 1e-3) / 1e12

@@ -261,4 +261,77 @@ struct Vec16<h16f8> {
   }
 };
 
+// ---- one K-chunk row (64 logical channels; 32 for tf32) of fp32 values -> its stored 16-byte pieces ----------------
+// PIECES x 16 bytes = 128 (bf16 / tf32) or 256 (the two-row layouts: hi row, then lo / fp8 row) bytes per pixel-chunk.
+template <typename T>
+struct RowPack;
+template <>
+struct RowPack<__nv_bfloat16> {  // 8 pieces of 8 channels
+  static constexpr int PIECES = 8;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <>
+struct RowPack<float> {  // 8 pieces of 4 channels, tf32-rounded
+  static constexpr int PIECES = 8;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    return make_uint4(__float_as_uint(round_tf32(v[4 * j])), __float_as_uint(round_tf32(v[4 * j + 1])),
+                      __float_as_uint(round_tf32(v[4 * j + 2])), __float_as_uint(round_tf32(v[4 * j + 3])));
+  }
+};
+template <>
+struct RowPack<bf16s> {  // 8 hi pieces, then 8 lo pieces
+  static constexpr int PIECES = 16;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float a = v[8 * (j & 7) + 2 * e], b = v[8 * (j & 7) + 2 * e + 1];
+      if (j >= 8) {
+        a -= __bfloat162float(__float2bfloat16_rn(a));
+        b -= __bfloat162float(__float2bfloat16_rn(b));
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <>
+struct RowPack<h16f8> {  // 8 fp16 pieces (8 channels), 4 lo8 pieces (16 channels), 4 hi8 pieces
+  static constexpr int PIECES = 16;
+  __device__ static __forceinline__ uint4 piece(const float* v, int j) {
+    uint32_t w[4];
+    if (j < 8) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __half2 h = __floats2half2_rn(sat_f16(v[8 * j + 2 * e]), sat_f16(v[8 * j + 2 * e + 1]));
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    } else {
+      const int c0 = 16 * (j & 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float part[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half h;
+          float lo, hs;
+          split_f16f8(v[c0 + 4 * e + i], h, lo, hs);
+          part[i] = j < 12 ? lo : hs;
+        }
+        w[e] = e4m3x2(part[0], part[1]) | (e4m3x2(part[2], part[3]) << 16);
+      }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 }  // namespace cnm

@@ -302,6 +302,7 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
                                void* stream) {
   int rc = check_conv_args("cnm_conv2d_halo", d, srcs, groups, wp, out);
   if (rc) return rc;
+  CNM_REQUIRE(d->ksplit <= 1, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: split-K is a cnm_conv2d_tc feature");
   CNM_REQUIRE(map_info && num_groups > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo: bad group list");
   CNM_REQUIRE(d->Ho >= 16 && d->Wo >= 16, CNM_ERR_UNSUPPORTED_SHAPE,
               "cnm_conv2d_halo: output %dx%d smaller than the 16x16 tile (use cnm_conv2d_tc)", d->Ho, d->Wo);

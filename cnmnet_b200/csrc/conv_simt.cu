@@ -208,7 +208,8 @@ extern "C" int cnm_conv2d_simt(const cnm_conv_desc* d, const cnm_conv_src* srcs,
                                const void* wp, const float* bias, void* out, void* stream) {
   int rc = check_conv_args("cnm_conv2d_simt", d, srcs, steps, wp, out);
   if (rc) return rc;
-  CNM_REQUIRE(!d->head_partial, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_simt: no fused head in the validation twin");
+  CNM_REQUIRE(!d->head_partial && d->ksplit <= 1, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_conv2d_simt: no fused head / split-K in the validation twin");
   SimtParams p{};
   for (int i = 0; i < d->num_srcs; ++i) p.srcs[i] = SimtSrc{srcs[i].ptr, srcs[i].H, srcs[i].W, srcs[i].C};
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = d->Cout;

@@ -45,6 +45,9 @@ struct alignas(64) TcParams {
   const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
   float* head_partial;   // [N, Ho, Wo, 12] per-pixel tap dot products
   int N, Ho, Wo;
+  int ksplit;       // > 1: the K loop of every output tile is cut into ksplit ranges run by different CTAs
+  float* ws;        // split-K workspace [ksplit][N*Ho*Wo][Cout] fp32 (raw accumulators; splitk_finish_kernel sums them)
+  int cout;
 };
 
 template <int BN, int STAGES, bool TF32>
@@ -89,7 +92,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n * p.ksplit;
+  // split-K: tile index = ((m * tiles_n) + nt) * ksplit + part; part runs K-steps [kbeg(part), kbeg(part+1)), cut at
+  // even step indices (the fp16 / fp8 steps of CNM_F16F8 alternate and every range must start on an fp16 step)
+  auto kbeg = [&](int part) { return part >= p.ksplit ? p.num_steps : ((p.num_steps / 2) * part / p.ksplit) * 2; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.b_map);
@@ -117,20 +123,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int4 st_next = __ldg(reinterpret_cast<const int4*>(p.steps));
-      int c0_next = __ldg(&p.steps[0].c0);
+      const int k_first = kbeg((int)(blockIdx.x % p.ksplit));
+      int4 st_next = __ldg(reinterpret_cast<const int4*>(p.steps + k_first));
+      int c0_next = __ldg(&p.steps[k_first].c0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        int m = tile / p.tiles_n;
+        const int part = tile % p.ksplit;
+        const int nt = (tile / p.ksplit) % p.tiles_n;
+        int m = tile / (p.ksplit * p.tiles_n);
         const int x0 = (m % p.tiles_x) * p.TW;
         m /= p.tiles_x;
         const int y0 = (m % p.tiles_y) * p.TH;
         const int n0 = (m / p.tiles_y) * p.NB;
-        for (int ks = 0; ks < p.num_steps; ++ks) {
+        const int k_end = kbeg(part + 1);
+        for (int ks = kbeg(part); ks < k_end; ++ks) {
           const int4 st = st_next;  // src, sub, dx, dy
           const int c0 = c0_next;
           {  // prefetch the next step descriptor: its L2 latency overlaps the barrier wait below
-            const int kn = (ks + 1 == p.num_steps) ? 0 : ks + 1;
+            const int kn = (ks + 1 == k_end) ? kbeg((int)((tile + gridDim.x) % p.ksplit)) % p.num_steps : ks + 1;
             st_next = __ldg(reinterpret_cast<const int4*>(p.steps + kn));
             c0_next = __ldg(&p.steps[kn].c0);
           }
@@ -157,7 +166,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int ks = 0; ks < p.num_steps; ++ks) {
+        const int k_begin = kbeg(tile % p.ksplit), k_end = kbeg(tile % p.ksplit + 1);
+        for (int ks = k_begin; ks < k_end; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (elect_one()) {
@@ -170,10 +180,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)  // 4 x 32 B along K inside the 128 B swizzle row
-                tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks | k) ? 1u : 0u);
+                tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                             (ks != k_begin || k) ? 1u : 0u);
             }
             tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
-            if (ks == p.num_steps - 1) tc_commit(tfull_bar(as));  // accumulator complete
+            if (ks == k_end - 1) tc_commit(tfull_bar(as));  // accumulator complete
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -194,14 +205,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       epi_bar();
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int nt = tile % p.tiles_n;
-      int m = tile / p.tiles_n;
+      const int nt = (tile / p.ksplit) % p.tiles_n;
+      int m = tile / (p.ksplit * p.tiles_n);
       const int x0 = (m % p.tiles_x) * p.TW;
       m /= p.tiles_x;
       const int y0 = (m % p.tiles_y) * p.TH;
       const int n0 = (m / p.tiles_y) * p.NB;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      if (p.ksplit > 1) {
+        // split-K: park the raw accumulators of this K range in the workspace; bias / ReLU / packing happen in
+        // splitk_finish_kernel once all ranges are in
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        const int px = x0 + row % p.TW, py = y0 + (row / p.TW) % p.TH, pn = n0 + row / (p.TW * p.TH);
+        const bool inside = px < p.Wo && py < p.Ho && pn < p.N;
+        const size_t mtot = (size_t)p.N * p.Ho * p.Wo;
+        float* wrow = p.ws + ((size_t)(tile % p.ksplit) * mtot + ((size_t)pn * p.Ho + py) * p.Wo + px) * p.cout + nt * BN;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_row + c, v);
+          tmem_ld_wait();
+          if (inside) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(wrow + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
       if (bias_tile != nt) {
         epi_bar();  // previous tile's bias reads are done
         for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
@@ -252,6 +288,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+// Second half of a split-K convolution: sums the ksplit partial accumulators of every output element in a fixed order
+// (deterministic), applies scale / bias / ReLU and writes the act rows.  One thread per (pixel, K-chunk row).
+template <typename T>
+__global__ void __launch_bounds__(128)
+    splitk_finish_kernel(const float* __restrict__ ws, int ksplit, size_t mtot, int cout, const float* __restrict__ bias,
+                         float scale, int relu, uint8_t* __restrict__ out, size_t pix_bytes, size_t off_bytes) {
+  constexpr int CH = ActTraits<T>::CHUNK, NP = RowPack<T>::PIECES;
+  const int nch = cout / CH;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= mtot * nch) return;
+  const int chunk = (int)(idx % nch);
+  const size_t pixel = idx / nch;
+  float v[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) v[c] = 0.0f;
+  for (int s = 0; s < ksplit; ++s) {
+    const float4* src = reinterpret_cast<const float4*>(ws + ((size_t)s * mtot + pixel) * cout + chunk * CH);
+#pragma unroll
+    for (int c = 0; c < CH / 4; ++c) {
+      const float4 t = __ldg(src + c);
+      v[4 * c] += t.x; v[4 * c + 1] += t.y; v[4 * c + 2] += t.z; v[4 * c + 3] += t.w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const float t = fmaf(v[c], scale, bias ? __ldg(bias + chunk * CH + c) : 0.0f);
+    v[c] = relu ? fmaxf(t, 0.0f) : t;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + pixel * pix_bytes + off_bytes + (size_t)chunk * NP * 16);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) dst[j] = RowPack<T>::piece(v, j);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -360,6 +429,15 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.head_w = d->head_w;
   p.head_partial = d->head_partial;
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.ksplit = d->ksplit > 1 ? d->ksplit : 1;
+  p.ws = d->splitk_ws;
+  p.cout = d->Cout;
+  if (p.ksplit > 1) {
+    CNM_REQUIRE(d->splitk_ws && (((uintptr_t)d->splitk_ws) & 15) == 0, CNM_ERR_INVALID_ARGUMENT,
+                "cnm_conv2d_tc: ksplit = %d needs a 16B-aligned splitk_ws", d->ksplit);
+    CNM_REQUIRE(p.ksplit <= 16 && d->num_steps >= 4 * p.ksplit && !d->head_partial, CNM_ERR_UNSUPPORTED_SHAPE,
+                "cnm_conv2d_tc: ksplit = %d does not fit %d K-steps (or a fused head)", d->ksplit, d->num_steps);
+  }
 
   const uint32_t box[4] = {(uint32_t)ch, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.NB};
   for (int i = 0; i < d->num_srcs; ++i) {
@@ -398,11 +476,24 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
     rc = encode_map(&p.out_map, d->dtype, 4, out, dims, str, box);
     if (rc) return rc;
   }
-  const int total = m_tiles * p.tiles_n;
+  const int total = m_tiles * p.tiles_n * p.ksplit;
   const int grid = total < 148 ? total : 148;
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
-  if (BN == 256) return tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
-  if (BN == 128) return tf32 ? launch_tc<128, 6, true>(p, grid, s) : launch_tc<128, 6, false>(p, grid, s);
-  return tf32 ? launch_tc<64, 7, true>(p, grid, s) : launch_tc<64, 7, false>(p, grid, s);
+  if (BN == 256) rc = tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
+  else if (BN == 128) rc = tf32 ? launch_tc<128, 6, true>(p, grid, s) : launch_tc<128, 6, false>(p, grid, s);
+  else rc = tf32 ? launch_tc<64, 7, true>(p, grid, s) : launch_tc<64, 7, false>(p, grid, s);
+  if (rc || p.ksplit == 1) return rc;
+  const size_t mtot = (size_t)d->N * d->Ho * d->Wo;
+  const size_t out_rows = mtot * (d->Cout / ch);
+  const unsigned blocks = (unsigned)((out_rows + 127) / 128);
+  const size_t pix_bytes = (size_t)d->c_out_total * eb, off_bytes = (size_t)d->c_out_offset * eb;
+#define CNM_FINISH(T) \
+  splitk_finish_kernel<T><<<blocks, 128, 0, s>>>(p.ws, p.ksplit, mtot, d->Cout, bias, p.acc_scale, d->relu, (uint8_t*)out, pix_bytes, off_bytes)
+  if (d->dtype == CNM_BF16) CNM_FINISH(__nv_bfloat16);
+  else if (d->dtype == CNM_TF32) CNM_FINISH(float);
+  else if (d->dtype == CNM_BF16X3) CNM_FINISH(bf16s);
+  else CNM_FINISH(h16f8);
+#undef CNM_FINISH
+  return after_launch("cnm_conv2d_tc(split-K finish)");
 }

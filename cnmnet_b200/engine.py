@@ -253,6 +253,16 @@ def pack_weights(wf, cols, ch, dtype, acc_exp=None):
 
 
 _TUNE_CACHE = {}
+SPLITK = os.environ.get("CNM_SPLITK", "1") != "0"   # split-K candidates for layers with fewer tiles than SMs
+_SPLITK_WS = {}   # device -> shared fp32 workspace (layers run one after the other)
+
+
+def splitk_workspace(device, nfloats):
+    ws = _SPLITK_WS.get(str(device))
+    if ws is None or ws.numel() < nfloats:
+        ws = _SPLITK_WS[str(device)] = torch.empty((nfloats,), dtype=torch.float32, device=device)
+    return ws
+
 AUTOTUNE = os.environ.get("CNM_AUTOTUNE", "1") != "0"
 # optional JSON file with earlier decisions ({repr(key): [backend, bn]}): loaded at import, written by save_tune_cache().
 # Needed under profilers, where timing the candidates is meaningless (ncu serialises and replays every launch).
@@ -264,13 +274,13 @@ def _load_tune_cache():
         import json
         with open(TUNE_CACHE_FILE) as f:
             for k, v in json.load(f).items():
-                _TUNE_CACHE[k] = (v[0], int(v[1]), None)
+                _TUNE_CACHE[k] = (v[0], int(v[1]), int(v[2]) if len(v) > 2 else 1, None)
 
 
 def save_tune_cache(path):
     import json
     with open(path, "w") as f:
-        json.dump({k: [v[0], v[1]] for k, v in _TUNE_CACHE.items()}, f, indent=0, sort_keys=True)
+        json.dump({k: [v[0], v[1], v[2]] for k, v in _TUNE_CACHE.items()}, f, indent=0, sort_keys=True)
 
 
 _load_tune_cache()
@@ -336,19 +346,40 @@ class ConvOp:
     def cols(self):
         return self.variants[self.backend]["cols"]
 
-    def select(self, backend, bn):
+    def select(self, backend, bn, ksplit=1):
         repack = getattr(self, "backend", backend) != backend and self._weights is not None
         self.backend = backend
         self.desc.reserved = int(bn)
+        self.desc.ksplit = int(ksplit) if backend == "tc" else 1
+        if self.desc.ksplit > 1:
+            d = self.desc
+            ws = splitk_workspace(self.out.device, d.ksplit * d.N * d.Ho * d.Wo * d.Cout)
+            self._ws = ws
+            d.splitk_ws = ws.data_ptr()
+        else:
+            self.desc.splitk_ws = None
         if repack:
             self.load(*self._weights)
 
     def candidates(self):
-        cout = self.desc.Cout
+        """(kernel, output-channel tile, split-K factor) combinations worth timing for this layer."""
+        d = self.desc
         out = []
         for be in ("tc", "halo", "halo2"):
             if be in self.variants:
-                out += [(be, bn) for bn in (256, 128, 64) if cout % bn == 0]
+                out += [(be, bn, 1) for bn in (256, 128, 64) if d.Cout % bn == 0]
+        if SPLITK and "tc" in self.variants and not getattr(self, "_head", None):
+            tw = 16 if d.Wo >= 16 else 8
+            th = min(128 // tw, 1 << max(d.Ho - 1, 0).bit_length())
+            nb = 128 // (tw * th)
+            m_tiles = -(-d.Wo // tw) * -(-d.Ho // th) * -(-d.N // nb)
+            for bn in (256, 128, 64):
+                if d.Cout % bn:
+                    continue
+                tiles = m_tiles * (d.Cout // bn)
+                for ks in (2, 3, 4, 6, 8):
+                    if tiles < 120 and tiles * ks <= 304 and self.num_steps >= 8 * ks:
+                        out.append(("tc", bn, ks))
         return out
 
     def tune(self, stream, reps=3):
@@ -358,8 +389,8 @@ class ConvOp:
         best = _TUNE_CACHE.get(self.key)
         if best is None:
             results = []
-            for be, bn in self.candidates():
-                self.select(be, bn)
+            for be, bn, ks in self.candidates():
+                self.select(be, bn, ks)
                 for _ in range(2):
                     self(stream)
                 ts = []
@@ -370,11 +401,11 @@ class ConvOp:
                     b.record()
                     b.synchronize()
                     ts.append(a.elapsed_time(b))
-                results.append((min(ts), be, bn))
+                results.append((min(ts), be, bn, ks))
             results.sort()
-            best = _TUNE_CACHE[self.key] = (results[0][1], results[0][2], results)
+            best = _TUNE_CACHE[self.key] = (results[0][1], results[0][2], results[0][3], results)
         self.tuned = best
-        self.select(best[0], best[1])
+        self.select(best[0], best[1], best[2])
 
     def fuse_head(self, w_tap_major, partial):
         """Fused 1-channel 3x3 head on this layer's output (cnm_conv_desc.head_w / head_partial); Cout must be 64."""

@@ -194,7 +194,10 @@ typedef struct cnm_conv_desc {
   int32_t dtype; /* cnm_dtype */
   int32_t reserved; /* 0 = library picks the output-channel tile; 64 / 128 / 256 = caller-selected (autotuner) */
   int32_t acc_exp;  /* the accumulator is scaled by 2^-acc_exp before bias / ReLU (CNM_F16F8 weight scale; else 0) */
-  int32_t reserved2[3];
+  int32_t ksplit;   /* cnm_conv2d_tc only: > 1 cuts the K loop of every output tile into ksplit ranges run by different
+                       CTAs (layers with fewer tiles than SMs); partial accumulators go through splitk_ws and a second
+                       kernel sums them in a fixed order.  0 / 1 = off. */
+  int32_t reserved2[2];
   /* Optional fused 1-channel 3x3 head on this layer's output (depth_layer, depthnet/depthNet_model.py:82-84), for
    * Cout == 64 and the 2-byte dtypes (tensor-core kernels only): head_w = [9][64] fp32 tap-major weights (device),
    * head_partial = [N, Ho, Wo, 12] fp32 (device, 16B aligned) receiving, per pixel, the nine per-tap dot products of
@@ -202,6 +205,7 @@ typedef struct cnm_conv_desc {
    * NULL = no fused head.                                                                                          */
   const float* head_w;
   float* head_partial;
+  float* splitk_ws; /* [ksplit][N*Ho*Wo][Cout] fp32 workspace (device, 16B aligned) when ksplit > 1, else NULL */
 } cnm_conv_desc;
 
 /* tcgen05/TMEM/TMA implicit GEMM (the product path).  `steps` is a DEVICE array of

@@ -176,6 +176,36 @@ def test_fused_head_matches_separate_head(backend, dtype):
     assert (out.cpu() - 3.0 * torch.sigmoid(wl).float()).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case,ksplit", [((3, 6, 8, [128], 512, 3, 1), 4), ((1, 12, 16, [64, 64], 256, 3, 1), 3),
+                                         ((2, 24, 32, [128], 128, 3, 2), 2), ((5, 24, 32, [512], 256, 3, 1), 8)])
+def test_split_k_matches_oracle(dtype, case, ksplit):
+    """cnm_conv_desc.ksplit: K ranges on different CTAs + the fixed-order finishing kernel; deterministic across runs."""
+    N, H, W, cins, cout, k, stride = case
+    g = torch.Generator().manual_seed(cout + ksplit)
+    xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, generator=g) / np.sqrt(sum(cins) * k * k)
+    b = torch.randn(cout, generator=g)
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    acts = [to_act(x, dtype) for x in xs]
+    srcs = [engine.act_src(a, sum(cins[:i]), phys=engine.phys_factor(dtype)) for i, a in enumerate(acts)]
+    op = engine.ConvOp("t", srcs, k, stride, cout, N, Ho, Wo, dtype, dev(), True, backend="tc")
+    op.tunable = False
+    op.load(w, b)
+    op.select("tc", 128 if cout % 128 == 0 else 64, ksplit)
+    outs = []
+    for _ in range(2):
+        op.out.zero_()
+        op(_lib.stream_ptr())
+        torch.cuda.synchronize()
+        outs.append(from_act(op.out, dtype))
+    assert torch.equal(outs[0], outs[1])
+    want = oracle_conv(dtype, xs, w, b, k, stride)
+    err = (outs[0] - quantize(want, dtype)).abs().max().item()
+    assert err < MAX_TOL[dtype] * max(1.0, want.abs().max().item()), (err, rel_l2(outs[0], want))
+    assert rel_l2(outs[0], want) < L2_TOL[dtype]
+
+
 def test_conv_rejects_bad_arguments():
     lib = _lib.load()
     a = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=dev())  # 48 channels: not chunk aligned

@@ -16,6 +16,7 @@ pipe = cnmnet_b200.CNMPipeline(dnet.to(dev), rnet.to(dev), k_size=9, use_graph=F
 st = pipe.static_state(bench.B_PER_GPU, bench.V, bench.H, bench.W, dev)
 for tag, plan in (("depthnet", st["dplan"]), ("refine", st["rplan"])):
     for name, op in plan.convs.items():
-        if op.tuned and op.tuned[2]:
-            row = "  ".join("%s/%d %.1f" % (be, bn, 1e3 * t) for t, be, bn in sorted(op.tuned[2], key=lambda r: (r[1], -r[2])))
-            print("%-9s %-18s best %s/%d | %s" % (tag, name, op.tuned[0], op.tuned[1], row))
+        if op.tuned and op.tuned[3]:
+            row = "  ".join("%s/%d%s %.1f" % (be, bn, "k%d" % ks if ks > 1 else "", 1e3 * t)
+                            for t, be, bn, ks in sorted(op.tuned[3], key=lambda r: (r[1], -r[2], r[3])))
+            print("%-9s %-18s best %s/%d/k%d | %s" % (tag, name, op.tuned[0], op.tuned[1], op.tuned[2], row))
