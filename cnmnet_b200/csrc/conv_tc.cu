@@ -291,36 +291,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 }
 
 // Second half of a split-K convolution: sums the ksplit partial accumulators of every output element in a fixed order
-// (deterministic), applies scale / bias / ReLU and writes the act rows.  One thread per (pixel, K-chunk row).
+// (deterministic), applies scale / bias / ReLU and writes the act tensor.  One thread per (pixel, 8 channels): 32-byte
+// contiguous reads per thread and slice, a warp covers 1 KB.
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     splitk_finish_kernel(const float* __restrict__ ws, int ksplit, size_t mtot, int cout, const float* __restrict__ bias,
                          float scale, int relu, uint8_t* __restrict__ out, size_t pix_bytes, size_t off_bytes) {
-  constexpr int CH = ActTraits<T>::CHUNK, NP = RowPack<T>::PIECES;
-  const int nch = cout / CH;
+  const int groups = cout >> 3;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= mtot * nch) return;
-  const int chunk = (int)(idx % nch);
-  const size_t pixel = idx / nch;
-  float v[CH];
+  if (idx >= mtot * groups) return;
+  const int c = (int)(idx % groups) * 8;
+  const size_t pixel = idx / groups;
+  float v[8];
 #pragma unroll
-  for (int c = 0; c < CH; ++c) v[c] = 0.0f;
+  for (int j = 0; j < 8; ++j) v[j] = 0.0f;
   for (int s = 0; s < ksplit; ++s) {
-    const float4* src = reinterpret_cast<const float4*>(ws + ((size_t)s * mtot + pixel) * cout + chunk * CH);
-#pragma unroll
-    for (int c = 0; c < CH / 4; ++c) {
-      const float4 t = __ldg(src + c);
-      v[4 * c] += t.x; v[4 * c + 1] += t.y; v[4 * c + 2] += t.z; v[4 * c + 3] += t.w;
-    }
+    const float4* src = reinterpret_cast<const float4*>(ws + ((size_t)s * mtot + pixel) * cout + c);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+    v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
   }
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const float t = fmaf(v[c], scale, bias ? __ldg(bias + chunk * CH + c) : 0.0f);
-    v[c] = relu ? fmaxf(t, 0.0f) : t;
+  for (int j = 0; j < 8; ++j) {
+    const float t = fmaf(v[j], scale, bias ? __ldg(bias + c + j) : 0.0f);
+    v[j] = relu ? fmaxf(t, 0.0f) : t;
   }
-  uint4* dst = reinterpret_cast<uint4*>(out + pixel * pix_bytes + off_bytes + (size_t)chunk * NP * 16);
+  T* px = reinterpret_cast<T*>(out + pixel * pix_bytes + off_bytes) + ActTraits<T>::phys(c);
 #pragma unroll
-  for (int j = 0; j < NP; ++j) dst[j] = RowPack<T>::piece(v, j);
+  for (int j = 0; j < 8; j += Vec16<T>::N) Vec16<T>::store(px + j, v + j);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -485,11 +483,11 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   else rc = tf32 ? launch_tc<64, 7, true>(p, grid, s) : launch_tc<64, 7, false>(p, grid, s);
   if (rc || p.ksplit == 1) return rc;
   const size_t mtot = (size_t)d->N * d->Ho * d->Wo;
-  const size_t out_rows = mtot * (d->Cout / ch);
-  const unsigned blocks = (unsigned)((out_rows + 127) / 128);
+  const size_t out_vecs = mtot * (d->Cout / 8);
+  const unsigned blocks = (unsigned)((out_vecs + 255) / 256);
   const size_t pix_bytes = (size_t)d->c_out_total * eb, off_bytes = (size_t)d->c_out_offset * eb;
 #define CNM_FINISH(T) \
-  splitk_finish_kernel<T><<<blocks, 128, 0, s>>>(p.ws, p.ksplit, mtot, d->Cout, bias, p.acc_scale, d->relu, (uint8_t*)out, pix_bytes, off_bytes)
+  splitk_finish_kernel<T><<<blocks, 256, 0, s>>>(p.ws, p.ksplit, mtot, d->Cout, bias, p.acc_scale, d->relu, (uint8_t*)out, pix_bytes, off_bytes)
   if (d->dtype == CNM_BF16) CNM_FINISH(__nv_bfloat16);
   else if (d->dtype == CNM_TF32) CNM_FINISH(float);
   else if (d->dtype == CNM_BF16X3) CNM_FINISH(bf16s);

@@ -98,4 +98,10 @@ if "--full" in sys.argv:
      "%s ncu --set full: conv_tc_kernel (per-tap tcgen05 conv) after the warp-uniform issue loop" % tag,
      "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 "
      "python tools/profile_step.py` (%s mode, C4 step; the layers the autotuner leaves on the per-tap kernel: small and <= 48x64 layers)." % bench.get("dtype", "f16f8"))
+if "--full" in sys.argv:
+  dump("prof_small.ncu-rep", "%s_small_kernels_ncu.md" % tag,
+     "%s ncu --set full: the kernels around the convolutions (cost volume, tap packers, upsample, heads, refine aggregation)" % tag,
+     "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k "
+     "regex:\"upsample2x|head_partial|head_finish|pack_|refine_|cost_volume\" -c 12 python tools/profile_step.py` "
+     "(%s mode, C4 step, first twelve matching launches in launch order)." % bench.get("dtype", "f16f8"))
 print("ok", cu, cm, s)
