@@ -396,7 +396,7 @@ def main():
             "kernel": "conv_tc / conv_halo / conv_halo2 kernels (tcgen05 implicit GEMM, all %d conv launches of one step)"
                       % len(conv_rows),
             "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-            "traffic": traffic.get("conv_bytes_per_step") if not tf32 else None,
+            "traffic": traffic.get("conv_bytes_per_step") if (args.precision == "f16f8" and args.workload == "c4") else None,
             "traffic_note": "DRAM read+write bytes of all conv launches of one step, ncu (profiles/r01_launches_step.md)",
             "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step, "fp32_equivalent_tflops": fp32_equiv_tf,
             "peak_source": "%s bf16 sustained%s" % (peaks["source"], " x 0.5 for tf32" if tf32 else ""),
