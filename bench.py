@@ -441,6 +441,32 @@ def main():
                                     "achieved": nb / (ms_n * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": nb / (ms_n * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_launch": ms_n * 1e3,
                                     "algorithmic_bytes": nb}
+        # Combined Normal Map (K3b) on the same normals: synthetic disjoint plane masks, reference semantics
+        segs_np, pn_np = synth.plane_segments(np.random.default_rng(3), B, H, W)
+        segs = torch.from_numpy(segs_np).to(dev)
+        pn = torch.tensor([int(v) for v in pn_np], dtype=torch.int32, device=dev)
+        P = segs.shape[1]
+        cws = torch.empty((lib.cnm_plane_regularize_workspace_bytes(B, P, H, W),), dtype=torch.uint8, device=dev)
+        ms_c, _ = time_events(lambda: _lib.check(lib.cnm_plane_regularize(nrm.data_ptr(), segs.data_ptr(), pn.data_ptr(), None,
+                                                                          cws.data_ptr(), B, P, H, W, s)), 20, flush)
+        cb = B * (2 * 12 * H * W + P * H * W)   # normals read + written, P mask bytes per pixel
+        line["roofline_cnm"] = {"kernel": "cnm_accumulate / solve / apply kernels (C3: 256x192, batch 5, %d mask slots, %.1f planes per image)"
+                                          % (P, float(pn.float().mean())), "bound": "hbm",
+                                "achieved": cb / (ms_c * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": cb / (ms_c * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_launch": ms_c * 1e3,
+                                "algorithmic_bytes": cb}
+        # refine-input aggregation (K4) as the pipeline runs it: act-format iconv1 of both views in, refine conv1.0 operands out
+        rpl = st["rplan"]
+        ms_a, _ = time_events(lambda: rpl.ops[0](s), 20, flush)
+        ab_fp32 = B * (2 * 65 * 4 * H * W + 67 * 4 * H * W)             # SURVEY 8d figure (fp32 NCHW tensors)
+        esz = dplan.iconv1.element_size() * dplan.iconv1.shape[3]      # stored bytes per pixel of a 64-channel act tensor
+        ab_moved = B * H * W * (V * esz + V * 4 + esz + rpl.taps.element_size() * rpl.taps.shape[3] + 8)
+        line["roofline_refine_aggregate"] = {
+            "kernel": "refine_taps_kernel + refine_sum_act_kernel (C4: batch 5, 2 views)", "bound": "hbm",
+            "achieved": ab_moved / (ms_a * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ab_moved / (ms_a * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_step": ms_a * 1e3,
+            "algorithmic_bytes": ab_moved, "algorithmic_bytes_fp32_reference_layout": ab_fp32,
+            "note": "bytes of the stored formats actually read and written (act tensors of this mode)"}
         # the other tensor-core modes, same workload, same timing method (kept out of the headline value)
         line["other_modes"] = []
         others = [m for m in ("bf16", "tf32", "bf16x3", "f16f8") if m != args.precision]

@@ -43,7 +43,8 @@ SIGNATURES = {
     "cnm_cost_volume": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _D, _D, _I, _I, _P]),
     "cnm_depth2normal": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cnm_intrinsics_inverse": (_I, [_P, _P, _I, _P]),
-    "cnm_plane_regularize": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "cnm_plane_regularize_workspace_bytes": (_L, [_I, _I, _I, _I]),
+    "cnm_plane_regularize": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cnm_reciprocal": (_I, [_P, _P, _L, _P]),
     "cnm_nchw_to_act": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cnm_act_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -102,66 +102,204 @@ __global__ void __launch_bounds__(NT_X* NT_Y)
 }
 
 // ---------------------------------------------------------------------------------------------
-// CNM: sequential replace-by-plane-mean; one 1024-thread CTA per batch item
+// CNM (K3b): replace-by-plane-mean with the reference's SEQUENTIAL semantics (depth_util.py:205-238: plane i averages the
+// normals as left by planes 0..i-1), computed in parallel over pixels.
+//
+// For a pixel, let its planes be i1 < i2 < ... (its bits in the mask stack).  Plane i sees that pixel's ORIGINAL normal
+// if i is its first plane, otherwise the (float-rounded) mean of its previous plane.  Hence
+//     mean_i = ( S_i + sum_{k<i} C(i,k) * float(mean_k) ) / count_i
+// with S_i = sum of original normals over pixels whose first plane is i, C(i,k) = number of pixels of plane i whose
+// previous plane is k.  Pass A accumulates S (fp64, fixed reduction order), count and C (integers) over all pixels,
+// pass B solves the P <= 32 means in order, pass C walks every pixel's plane list once more: loss terms
+// 1 - cos(mean_i, value seen by plane i) and the final value (mean of its last plane).  Disjoint masks (what the
+// reference's loader produces, scannet/dataloader_batch.py:180-194) are the special case C = 0.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
+constexpr int CNM_THREADS = 256, CNM_MAX_P = 32;
+
+struct CnmWorkspace {
+  double* partS;   // [B][NB][P][3]
+  double* means;   // [B][P][3]
+  double* lossp;   // [B][NB]
+  unsigned* cnt;   // [B][P]
+  unsigned* cm;    // [B][P][P]
+};
+
+__host__ __device__ inline int cnm_blocks_per_image(int H, int W) {
+  const int nb = (H * W + CNM_THREADS * 4 - 1) / (CNM_THREADS * 4);
+  return nb < 1 ? 1 : (nb > 64 ? 64 : nb);
+}
+static size_t cnm_align(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t cnm_carve(void* base, int B, int P, int NB, CnmWorkspace* ws) {
+  size_t off = 0;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  auto take = [&](size_t bytes) { uint8_t* r = p ? p + off : nullptr; off += cnm_align(bytes); return r; };
+  double* partS = reinterpret_cast<double*>(take((size_t)B * NB * P * 3 * sizeof(double)));
+  double* means = reinterpret_cast<double*>(take((size_t)B * P * 3 * sizeof(double)));
+  double* lossp = reinterpret_cast<double*>(take((size_t)B * NB * sizeof(double)));
+  unsigned* cnt = reinterpret_cast<unsigned*>(take(((size_t)B * P + (size_t)B * P * P) * sizeof(unsigned)));
+  if (ws) { ws->partS = partS; ws->means = means; ws->lossp = lossp; ws->cnt = cnt; ws->cm = cnt + (size_t)B * P; }
+  return off;
+}
+
+__device__ __forceinline__ unsigned cnm_plane_bits(const uint8_t* __restrict__ segs, size_t HW, size_t j, int np) {
+  unsigned bits = 0;
+  for (int i = 0; i < np; ++i) bits |= (segs[(size_t)i * HW + j] != 0 ? 1u : 0u) << i;
+  return bits;
+}
+__device__ __forceinline__ double warp_sum_ordered(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) scratch[w] = v;
-  __syncthreads();
-  double t = (threadIdx.x < (blockDim.x >> 5)) ? scratch[threadIdx.x] : 0.0;
-  if (w == 0) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (l == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
+  return v;
 }
 
-__global__ void __launch_bounds__(1024)
-    plane_regularize_kernel(float* __restrict__ normals, const uint8_t* __restrict__ segs,
-                            const int32_t* __restrict__ planes_num, double* __restrict__ loss, int P, int H, int W) {
-  __shared__ double scratch[33];
-  const int b = blockIdx.x;
+__global__ void __launch_bounds__(CNM_THREADS)
+    cnm_accumulate_kernel(const float* __restrict__ normals, const uint8_t* __restrict__ segs,
+                          const int32_t* __restrict__ planes_num, CnmWorkspace ws, int P, int H, int W) {
+  __shared__ double s_S[CNM_THREADS / 32][CNM_MAX_P][3];
+  __shared__ unsigned s_cnt[CNM_MAX_P], s_cm[CNM_MAX_P * CNM_MAX_P];
+  const int b = blockIdx.y, NB = gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t HW = (size_t)H * W;
-  float* n = normals + (size_t)b * 3 * HW;
-  int np = planes_num[b];
-  if (np > P) np = P;
-  double loss_b = 0.0;
-  for (int i = 0; i < np; ++i) {
-    const uint8_t* m = segs + ((size_t)b * P + i) * HW;
-    double s0 = 0, s1 = 0, s2 = 0, c = 0;
-    for (size_t j = threadIdx.x; j < HW; j += blockDim.x)
-      if (m[j]) { s0 += n[j]; s1 += n[HW + j]; s2 += n[2 * HW + j]; c += 1.0; }
-    s0 = block_sum(s0, scratch); s1 = block_sum(s1, scratch); s2 = block_sum(s2, scratch);
-    c = block_sum(c, scratch);
-    const double m0 = s0 / c, m1 = s1 / c, m2 = s2 / c;  // 0/0 -> NaN like the reference; NOT renormalised
-    if (loss) {
-      // mean over ALL H*W pixels of 1 - cos(mean, n*mask); off-mask pixels contribute exactly 1
-      const double nm = fmax(sqrt(m0 * m0 + m1 * m1 + m2 * m2), 1e-8);
-      double acc = 0.0;
-      for (size_t j = threadIdx.x; j < HW; j += blockDim.x) {
-        double cs = 0.0;
-        if (m[j]) {
-          const double a0 = n[j], a1 = n[HW + j], a2 = n[2 * HW + j];
-          cs = (a0 * m0 + a1 * m1 + a2 * m2) / (nm * fmax(sqrt(a0 * a0 + a1 * a1 + a2 * a2), 1e-8));
-        }
-        acc += 1.0 - cs;
+  const int np = min(planes_num[b], P);
+  for (int i = threadIdx.x; i < (CNM_THREADS / 32) * CNM_MAX_P * 3; i += CNM_THREADS) (&s_S[0][0][0])[i] = 0.0;
+  for (int i = threadIdx.x; i < CNM_MAX_P; i += CNM_THREADS) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < CNM_MAX_P * CNM_MAX_P; i += CNM_THREADS) s_cm[i] = 0;
+  __syncthreads();
+  const float* n = normals + (size_t)b * 3 * HW;
+  const uint8_t* m = segs + (size_t)b * P * HW;
+  const size_t stride = (size_t)NB * CNM_THREADS;
+  const size_t iters = (HW + stride - 1) / stride;
+  for (size_t it = 0; it < iters; ++it) {  // uniform trip count: every lane takes part in the ballots
+    const size_t j = it * stride + (size_t)blockIdx.x * CNM_THREADS + threadIdx.x;
+    const unsigned bits = j < HW ? cnm_plane_bits(m, HW, j, np) : 0u;
+    unsigned any = __ballot_sync(0xffffffffu, bits != 0);
+    if (!any) continue;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    if (bits) { n0 = n[j]; n1 = n[HW + j]; n2 = n[2 * HW + j]; }
+    unsigned warp_bits = bits;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_bits |= __shfl_xor_sync(0xffffffffu, warp_bits, o);
+    while (warp_bits) {  // planes present in this warp, ascending
+      const int i = __ffs(warp_bits) - 1;
+      warp_bits &= warp_bits - 1;
+      const bool in = (bits >> i) & 1u;
+      const unsigned earlier = bits & ((1u << i) - 1u);
+      if (in) {
+        atomicAdd(&s_cnt[i], 1u);
+        if (earlier) atomicAdd(&s_cm[i * CNM_MAX_P + (31 - __clz(earlier))], 1u);
       }
-      loss_b += block_sum(acc, scratch) / (double)HW;
+      const bool first = in && !earlier;
+      if (__ballot_sync(0xffffffffu, first)) {
+        const double a0 = warp_sum_ordered(first ? (double)n0 : 0.0), a1 = warp_sum_ordered(first ? (double)n1 : 0.0),
+                     a2 = warp_sum_ordered(first ? (double)n2 : 0.0);
+        if (lane == 0) { s_S[warp][i][0] += a0; s_S[warp][i][1] += a1; s_S[warp][i][2] += a2; }
+      }
     }
-    __syncthreads();
-    for (size_t j = threadIdx.x; j < HW; j += blockDim.x)
-      if (m[j]) { n[j] = (float)m0; n[HW + j] = (float)m1; n[2 * HW + j] = (float)m2; }
-    __syncthreads();
   }
-  if (loss && threadIdx.x == 0) atomicAdd(loss, loss_b);
+  __syncthreads();
+  for (int t = threadIdx.x; t < P * 3; t += CNM_THREADS) {
+    double acc = 0.0;
+    for (int w = 0; w < CNM_THREADS / 32; ++w) acc += s_S[w][t / 3][t % 3];
+    ws.partS[(((size_t)b * NB + blockIdx.x) * P) * 3 + t] = acc;
+  }
+  for (int t = threadIdx.x; t < P; t += CNM_THREADS)
+    if (s_cnt[t]) atomicAdd(&ws.cnt[(size_t)b * P + t], s_cnt[t]);
+  for (int t = threadIdx.x; t < P * P; t += CNM_THREADS) {
+    const unsigned v = s_cm[(t / P) * CNM_MAX_P + t % P];
+    if (v) atomicAdd(&ws.cm[(size_t)b * P * P + t], v);
+  }
 }
 
-__global__ void zero_double_kernel(double* p) { *p = 0.0; }
+__global__ void __launch_bounds__(128)
+    cnm_solve_kernel(const int32_t* __restrict__ planes_num, CnmWorkspace ws, int P, int NB) {
+  __shared__ double S[CNM_MAX_P * 3];
+  const int b = blockIdx.x;
+  const int np = min(planes_num[b], P);
+  for (int t = threadIdx.x; t < P * 3; t += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < NB; ++k) acc += ws.partS[(((size_t)b * NB + k) * P) * 3 + t];  // fixed order
+    S[t] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* mean = ws.means + (size_t)b * P * 3;
+    for (int i = 0; i < np; ++i) {
+      double a0 = S[3 * i], a1 = S[3 * i + 1], a2 = S[3 * i + 2];
+      for (int k = 0; k < i; ++k) {
+        const unsigned c = ws.cm[((size_t)b * P + i) * P + k];
+        if (c) {  // pixels of plane i that plane k rewrote: they hold float(mean_k)
+          a0 += (double)c * (double)(float)mean[3 * k];
+          a1 += (double)c * (double)(float)mean[3 * k + 1];
+          a2 += (double)c * (double)(float)mean[3 * k + 2];
+        }
+      }
+      const double cnt = (double)ws.cnt[(size_t)b * P + i];
+      mean[3 * i] = a0 / cnt;  // 0/0 -> NaN like the reference; NOT renormalised
+      mean[3 * i + 1] = a1 / cnt;
+      mean[3 * i + 2] = a2 / cnt;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CNM_THREADS)
+    cnm_apply_kernel(float* __restrict__ normals, const uint8_t* __restrict__ segs, const int32_t* __restrict__ planes_num,
+                     CnmWorkspace ws, int want_loss, int P, int H, int W) {
+  __shared__ double s_mean[CNM_MAX_P * 3], s_nm[CNM_MAX_P], scratch[33];
+  const int b = blockIdx.y, NB = gridDim.x;
+  const size_t HW = (size_t)H * W;
+  const int np = min(planes_num[b], P);
+  for (int t = threadIdx.x; t < np * 3; t += CNM_THREADS) s_mean[t] = ws.means[(size_t)b * P * 3 + t];
+  __syncthreads();
+  for (int t = threadIdx.x; t < np; t += CNM_THREADS)
+    s_nm[t] = fmax(sqrt(s_mean[3 * t] * s_mean[3 * t] + s_mean[3 * t + 1] * s_mean[3 * t + 1] +
+                        s_mean[3 * t + 2] * s_mean[3 * t + 2]), 1e-8);
+  __syncthreads();
+  float* n = normals + (size_t)b * 3 * HW;
+  const uint8_t* m = segs + (size_t)b * P * HW;
+  double lacc = 0.0;
+  for (size_t j = (size_t)blockIdx.x * CNM_THREADS + threadIdx.x; j < HW; j += (size_t)NB * CNM_THREADS) {
+    unsigned bits = cnm_plane_bits(m, HW, j, np);
+    if (!bits) continue;
+    float c0 = n[j], c1 = n[HW + j], c2 = n[2 * HW + j];
+    while (bits) {
+      const int i = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const double m0 = s_mean[3 * i], m1 = s_mean[3 * i + 1], m2 = s_mean[3 * i + 2];
+      if (want_loss) {  // 1 - cos(mean_i, the value plane i saw at this pixel)
+        const double a0 = c0, a1 = c1, a2 = c2;
+        lacc += 1.0 - (a0 * m0 + a1 * m1 + a2 * m2) / (s_nm[i] * fmax(sqrt(a0 * a0 + a1 * a1 + a2 * a2), 1e-8));
+      }
+      c0 = (float)m0; c1 = (float)m1; c2 = (float)m2;
+    }
+    n[j] = c0; n[HW + j] = c1; n[2 * HW + j] = c2;
+  }
+  if (want_loss) {
+    // block sum in a fixed order
+    double v = warp_sum_ordered(lacc);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) scratch[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int k = 0; k < CNM_THREADS / 32; ++k) t += scratch[k];
+      ws.lossp[(size_t)b * NB + blockIdx.x] = t;
+    }
+  }
+}
+
+// loss = sum_b sum_i mean over ALL H*W pixels of (1 - cos): off-mask pixels contribute exactly 1 each
+__global__ void cnm_loss_kernel(const int32_t* __restrict__ planes_num, CnmWorkspace ws, double* __restrict__ loss, int B,
+                                int P, int NB, double HW) {
+  if (threadIdx.x || blockIdx.x) return;
+  double total = 0.0;
+  for (int b = 0; b < B; ++b) {
+    double acc = 0.0;
+    for (int k = 0; k < NB; ++k) acc += ws.lossp[(size_t)b * NB + k];
+    const int np = min(planes_num[b], P);
+    for (int i = 0; i < np; ++i) acc += HW - (double)ws.cnt[(size_t)b * P + i];
+    total += acc / HW;
+  }
+  *loss = total;
+}
 
 __global__ void intrinsics_inverse_kernel(const float* __restrict__ cam, float* __restrict__ Kinv, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,18 +395,34 @@ extern "C" int cnm_depth2normal(const float* depth, const float* Kinv, float* no
   return after_launch("cnm_depth2normal");
 }
 
+extern "C" int64_t cnm_plane_regularize_workspace_bytes(int B, int P, int H, int W) {
+  if (B <= 0 || P <= 0 || P > CNM_MAX_P || H <= 0 || W <= 0) return 0;
+  return (int64_t)cnm_carve(nullptr, B, P, cnm_blocks_per_image(H, W), nullptr);
+}
+
 extern "C" int cnm_plane_regularize(float* normals, const uint8_t* segs, const int32_t* planes_num, double* loss,
-                                    int B, int P, int H, int W, void* stream) {
-  CNM_REQUIRE(normals && segs && planes_num, CNM_ERR_INVALID_ARGUMENT, "cnm_plane_regularize: null pointer");
+                                    void* workspace, int B, int P, int H, int W, void* stream) {
+  CNM_REQUIRE(normals && segs && planes_num && workspace, CNM_ERR_INVALID_ARGUMENT, "cnm_plane_regularize: null pointer");
   CNM_REQUIRE(B > 0 && P > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_plane_regularize: bad shape");
+  CNM_REQUIRE(P <= CNM_MAX_P, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_plane_regularize: at most %d mask slots (got %d)", CNM_MAX_P, P);
+  CNM_REQUIRE(((uintptr_t)workspace & 255) == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_plane_regularize: workspace must be 256B aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  if (loss) {
-    zero_double_kernel<<<1, 1, 0, s>>>(loss);
-    int rc = after_launch("cnm_plane_regularize(zero)");
-    if (rc) return rc;
-  }
-  plane_regularize_kernel<<<B, 1024, 0, s>>>(normals, segs, planes_num, loss, P, H, W);
-  return after_launch("cnm_plane_regularize");
+  const int NB = cnm_blocks_per_image(H, W);
+  CnmWorkspace ws;
+  cnm_carve(workspace, B, P, NB, &ws);
+  cudaError_t e = cudaMemsetAsync(ws.cnt, 0, ((size_t)B * P + (size_t)B * P * P) * sizeof(unsigned), s);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_plane_regularize: memset: %s", cudaGetErrorString(e));
+  cnm_accumulate_kernel<<<dim3(NB, B), CNM_THREADS, 0, s>>>(normals, segs, planes_num, ws, P, H, W);
+  int rc = after_launch("cnm_plane_regularize(accumulate)");
+  if (rc) return rc;
+  cnm_solve_kernel<<<B, 128, 0, s>>>(planes_num, ws, P, NB);
+  rc = after_launch("cnm_plane_regularize(solve)");
+  if (rc) return rc;
+  cnm_apply_kernel<<<dim3(NB, B), CNM_THREADS, 0, s>>>(normals, segs, planes_num, ws, loss ? 1 : 0, P, H, W);
+  rc = after_launch("cnm_plane_regularize(apply)");
+  if (rc || !loss) return rc;
+  cnm_loss_kernel<<<1, 32, 0, s>>>(planes_num, ws, loss, B, P, NB, (double)H * W);
+  return after_launch("cnm_plane_regularize(loss)");
 }
 
 extern "C" int cnm_intrinsics_inverse(const float* cam, float* Kinv, int B, void* stream) {

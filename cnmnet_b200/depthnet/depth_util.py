@@ -63,9 +63,17 @@ class Depth2normal(nn.Module):
         segs = instance_segs.to(torch.uint8).contiguous()
         pn = _planes_num_tensor(planes_num, d.device)
         loss = torch.zeros((), dtype=torch.float64, device=d.device)
-        _lib.check(lib.cnm_plane_regularize(normals.data_ptr(), segs.data_ptr(), pn.data_ptr(), loss.data_ptr(), B,
-                                            segs.shape[1], H, W, st), "plane_regularize")
+        ws = _cnm_workspace(lib, B, segs.shape[1], H, W, d.device)
+        _lib.check(lib.cnm_plane_regularize(normals.data_ptr(), segs.data_ptr(), pn.data_ptr(), loss.data_ptr(),
+                                            ws.data_ptr(), B, segs.shape[1], H, W, st), "plane_regularize")
         return normals, loss.float(), points
+
+
+def _cnm_workspace(lib, B, P, H, W, device):
+    nbytes = lib.cnm_plane_regularize_workspace_bytes(B, P, H, W)
+    if nbytes <= 0:
+        raise ValueError("cnm_plane_regularize supports 1..32 plane slots, got %d" % P)
+    return torch.empty((nbytes,), dtype=torch.uint8, device=device)
 
 
 def get_normal_by_planes(gt_normal, instance_segs, planes_num):
@@ -77,6 +85,7 @@ def get_normal_by_planes(gt_normal, instance_segs, planes_num):
     segs = instance_segs.to(torch.uint8).contiguous()
     pn = _planes_num_tensor(planes_num, out.device)
     lib = _lib.load()
-    _lib.check(lib.cnm_plane_regularize(out.data_ptr(), segs.data_ptr(), pn.data_ptr(), None, B, segs.shape[1], H, W,
-                                        _lib.stream_ptr()), "plane_regularize")
+    ws = _cnm_workspace(lib, B, segs.shape[1], H, W, out.device)
+    _lib.check(lib.cnm_plane_regularize(out.data_ptr(), segs.data_ptr(), pn.data_ptr(), None, ws.data_ptr(), B,
+                                        segs.shape[1], H, W, _lib.stream_ptr()), "plane_regularize")
     return out

@@ -99,9 +99,13 @@ int cnm_intrinsics_inverse(const float* cam, float* Kinv, int B, void* stream);
  * replaces the planes branch of Depth2normal.forward (depthnet/depth_util.py:205-238) and
  * get_normal_by_planes (:243-278).  normals [B,3,H,W] updated IN PLACE (the one exception to
  * the no-mutation rule: callers pass a private copy); segs [B,P,H,W] uint8; planes_num [B]
- * int32 on device; loss (device double, may be NULL) receives sum_b sum_i mean_hw(1-cos).  */
-int cnm_plane_regularize(float* normals, const uint8_t* segs, const int32_t* planes_num, double* loss, int B, int P,
-                         int H, int W, void* stream);
+ * int32 on device; loss (device double, may be NULL) receives sum_b sum_i mean_hw(1-cos).
+ * Planes are applied with the reference's sequential semantics (overlapping masks included) but
+ * computed in parallel over pixels; P <= 32.  workspace: cnm_plane_regularize_workspace_bytes()
+ * bytes of device memory, 256B aligned, contents irrelevant.                                  */
+int64_t cnm_plane_regularize_workspace_bytes(int B, int P, int H, int W);
+int cnm_plane_regularize(float* normals, const uint8_t* segs, const int32_t* planes_num, double* loss, void* workspace,
+                         int B, int P, int H, int W, void* stream);
 
 /* ---- idepth -> depth -------------------------------------------------------------------
  * replaces torch.div(1.0, idepth)  (eval.py:269,452,934).  n elements.                      */

@@ -153,6 +153,37 @@ def test_cnm_golden_and_oracle(golden_dir):
     assert rel_l2(got, onrm.get_normal_by_planes(x, segs, [2])) < 1e-6
 
 
+def test_cnm_overlapping_chains_and_loss(golden_dir):
+    """Masks that overlap in chains (plane i sees what planes < i wrote): the parallel accumulate / solve / apply
+    formulation must reproduce the reference's sequential loop, loss term included."""
+    g = _g(golden_dir, "normals_k9.npz")
+    depth, Kinv = g["depth"], g["Kinv"]
+    B, H, W = depth.shape
+    rng = np.random.default_rng(17)
+
+    def boxes(counts):
+        segs = np.zeros((len(counts), 20, H, W), np.uint8)
+        for b, n in enumerate(counts):
+            for i in range(n):
+                y0, x0 = int(rng.integers(0, H // 2)), int(rng.integers(0, W // 2))
+                segs[b, i, y0:y0 + H // 2, x0:x0 + W // 2] = 1       # half-image boxes: heavy overlap
+        return segs
+
+    counts = [5, 3][:B] + [2] * max(0, B - 2)
+    segs, pn = boxes(counts), np.array(counts)
+    n, loss, _ = cnmnet_b200.Depth2normal(9)(_cuda(depth), _cuda(Kinv), _cuda(segs), torch.from_numpy(pn))
+    n64, loss64, _ = onrm.depth2normal_cnm(depth, Kinv, segs, pn)
+    ok = np.isfinite(n64)
+    assert np.abs(n.cpu().numpy() - n64)[ok].max() < 1e-5
+    assert abs(float(loss) - float(loss64)) < 1e-5 * max(1.0, abs(float(loss64)))
+    counts3 = [6, 3, 0]
+    segs3 = boxes(counts3)
+    x = rng.standard_normal((3, 3, H, W)).astype(np.float32)
+    got = cnmnet_b200.get_normal_by_planes(_cuda(x), _cuda(segs3), counts3).cpu().numpy()
+    assert rel_l2(got, onrm.get_normal_by_planes(x, segs3, np.array(counts3))) < 1e-6
+    assert np.array_equal(got[2], x[2])                               # no planes: untouched
+
+
 # ------------------------------------------------------------------ K4 aggregation and the small kernels
 @pytest.mark.parametrize("dtype", ALL_DTYPES)
 @pytest.mark.parametrize("group", [1, 2, 3])
