@@ -217,6 +217,9 @@ def main():
                     help="c4 = BASELINE configs[3] (default, the metric's config); c5 = configs[4]: 640x480, 128 planes "
                          "(depthNet(planes=128): conv1 widened to 131 inputs, an extension -- the reference hard-codes "
                          "64), batch 32 per GPU; c5-64 = the same at the reference's 64 planes")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="concurrent pipeline lanes of the streaming API in the e2e measurement (0 = 2 at C4, 1 at C5 "
+                         "where a second buffer set does not fit)")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer timing table on stderr")
@@ -323,12 +326,13 @@ def main():
             for _ in range(n):
                 yield tuple(host)
 
-        for _ in pipe.infer_stream(host_batches(3), after_step=gather):
+        lanes = args.lanes or (2 if args.workload == "c4" else 1)
+        for _ in pipe.infer_stream(host_batches(4), after_step=gather, lanes=lanes):
             pass
         barrier()
         e0 = time.perf_counter()
         n_out = 0
-        for outs in pipe.infer_stream(host_batches(args.steps), after_step=gather):
+        for outs in pipe.infer_stream(host_batches(args.steps), after_step=gather, lanes=lanes):
             n_out += 1
         torch.cuda.synchronize()
         assert n_out == args.steps
@@ -354,7 +358,8 @@ def main():
                    "l2": "flushed between timed steps (256 MiB memset, outside the event pair)",
                    "cuda_graph": True, "precision_note": PRECISION_NOTES[args.precision]},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "lanes": lanes},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
         "wall_ms_per_step_incl_flush": wall_ms / args.steps,

@@ -112,11 +112,13 @@ class depthNet(_KernelNet):
         self._build([("conv1", "down", 3 + self.planes, 128, 7)] + _DEPTHNET[1:])
         super().train(False)
 
-    def plan(self, N, Bref, H, W, want_logits=False):
+    def plan(self, N, Bref, H, W, want_logits=False, lane=0):
+        """`lane` distinguishes independent buffer sets of the same shape (plans that run concurrently on two streams)."""
         dev = next(self.parameters()).device
-        key = (N, Bref, H, W, self.precision, self.backend, str(dev), want_logits)
+        key = (N, Bref, H, W, self.precision, self.backend, str(dev), want_logits, lane)
         return self._get_plan(key, lambda: DepthNetPlan(N, Bref, H, W, float(self.idepth_scale), self.precision, dev,
-                                                        self.backend, planes=self.planes, want_logits=want_logits))
+                                                        self.backend, planes=self.planes, want_logits=want_logits,
+                                                        lane=lane))
 
     def getVolume(self, left_image, right_image, KRKiUV_T, KT_T):
         """[B,3,H,W] x2, KRKiUV_T [B,3,W*H] (x-major), KT_T [B,3,1] -> cost volume [B,planes (64),H,W] fp32
@@ -173,11 +175,11 @@ class DepthRefineNet(_KernelNet):
         self._build(_REFINE)
         super().train(False)
 
-    def plan(self, B, H, W, group=1, nchw_input=False, want_logits=False):
+    def plan(self, B, H, W, group=1, nchw_input=False, want_logits=False, lane=0):
         dev = next(self.parameters()).device
-        key = (B, H, W, group, nchw_input, self.precision, self.backend, str(dev), want_logits)
+        key = (B, H, W, group, nchw_input, self.precision, self.backend, str(dev), want_logits, lane)
         return self._get_plan(key, lambda: RefinePlan(B, H, W, float(self.idepth_scale), self.precision, dev,
-                                                      self.backend, group, nchw_input, want_logits))
+                                                      self.backend, group, nchw_input, want_logits, lane=lane))
 
     def forward(self, idepth01, idepth02, iconv01, iconv02, ReturnVolume=False):
         """-> (disp_refined, prob_map[, iconv1_depth])   (depthNet_model.py:331-370)."""

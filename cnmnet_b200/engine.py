@@ -257,10 +257,12 @@ SPLITK = os.environ.get("CNM_SPLITK", "1") != "0"   # split-K candidates for lay
 _SPLITK_WS = {}   # device -> shared fp32 workspace (layers run one after the other)
 
 
-def splitk_workspace(device, nfloats):
-    ws = _SPLITK_WS.get(str(device))
+def splitk_workspace(device, nfloats, lane=0):
+    """One workspace per (device, lane): plans of different lanes may run concurrently on different streams."""
+    key = (str(device), lane)
+    ws = _SPLITK_WS.get(key)
     if ws is None or ws.numel() < nfloats:
-        ws = _SPLITK_WS[str(device)] = torch.empty((nfloats,), dtype=torch.float32, device=device)
+        ws = _SPLITK_WS[key] = torch.empty((nfloats,), dtype=torch.float32, device=device)
     return ws
 
 AUTOTUNE = os.environ.get("CNM_AUTOTUNE", "1") != "0"
@@ -292,8 +294,8 @@ class ConvOp:
     (kernel x output-channel tile) on the device once per layer shape and keeps the fastest."""
 
     def __init__(self, name, srcs, k, stride, cout, N, Ho, Wo, dtype, device, relu=True, out=None, c_out_offset=0,
-                 backend="tc"):
-        self.name, self.k, self.stride, self.dtype = name, k, stride, dtype
+                 backend="tc", lane=0):
+        self.name, self.k, self.stride, self.dtype, self.lane = name, k, stride, dtype, lane
         ch = chunk_channels(dtype)
         split = split_passes(dtype)
         pf = phys_factor(dtype)
@@ -353,7 +355,7 @@ class ConvOp:
         self.desc.ksplit = int(ksplit) if backend == "tc" else 1
         if self.desc.ksplit > 1:
             d = self.desc
-            ws = splitk_workspace(self.out.device, d.ksplit * d.N * d.Ho * d.Wo * d.Cout)
+            ws = splitk_workspace(self.out.device, d.ksplit * d.N * d.Ho * d.Wo * d.Cout, self.lane)
             self._ws = ws
             d.splitk_ws = ws.data_ptr()
         else:
@@ -435,8 +437,8 @@ class ConvOp:
 
 
 class _Plan:
-    def __init__(self, dtype, device, backend):
-        self.dtype, self.device, self.backend = parse_dtype(dtype), torch.device(device), backend
+    def __init__(self, dtype, device, backend, lane=0):
+        self.dtype, self.device, self.backend, self.lane = parse_dtype(dtype), torch.device(device), backend, lane
         if self.device.type != "cuda":
             raise RuntimeError("cnmnet_b200 runs on CUDA devices only (no CPU path); got %s" % (self.device,))
         self.lib = _lib.load()
@@ -456,7 +458,8 @@ class _Plan:
         return act_src(buf, wch, phys=self.pf)
 
     def conv(self, name, srcs, k, stride, cout, N, Ho, Wo, relu=True):
-        op = ConvOp(name, srcs, k, stride, cout, N, Ho, Wo, self.dtype, self.device, relu, backend=self.backend)
+        op = ConvOp(name, srcs, k, stride, cout, N, Ho, Wo, self.dtype, self.device, relu, backend=self.backend,
+                    lane=self.lane)
         self.convs[name] = op
         self.ops.append(op)
         return op.out
@@ -551,8 +554,8 @@ class DepthNetPlan(_Plan):
     iconv1 act [N,H,W,64]."""
 
     def __init__(self, N, Bref, H, W, idepth_scale=3.0, dtype="bf16", device="cuda", backend="tc", planes=64,
-                 want_logits=False):
-        super().__init__(dtype, device, backend)
+                 want_logits=False, lane=0):
+        super().__init__(dtype, device, backend, lane)
         if H % 32 or W % 32:
             raise ValueError("DepthNet needs H and W divisible by 32 (five stride-2 stages); got %dx%d" % (H, W))
         if N % Bref:
@@ -655,8 +658,8 @@ class RefinePlan(_Plan):
     the public boundary, NCHW fp32 [2,B,64,H,W].  V = 2*group source views (eval.py:659-663, 920-929)."""
 
     def __init__(self, B, H, W, idepth_scale=2.0, dtype="bf16", device="cuda", backend="tc", group=1,
-                 nchw_input=False, want_logits=False):
-        super().__init__(dtype, device, backend)
+                 nchw_input=False, want_logits=False, lane=0):
+        super().__init__(dtype, device, backend, lane)
         if H % 8 or W % 8:
             raise ValueError("DepthRefineNet needs H and W divisible by 8; got %dx%d" % (H, W))
         self.B, self.H, self.W, self.group, self.scale = B, H, W, group, float(idepth_scale)

@@ -26,13 +26,13 @@ class CNMPipeline:
         self._state = {}
 
     # -- static state for one shape -----------------------------------------------------------
-    def _prepare(self, B, V, H, W, device):
-        key = (B, V, H, W, str(device))
+    def _prepare(self, B, V, H, W, device, lane=0):
+        key = (B, V, H, W, str(device), lane)
         st = self._state.get(key)
         if st is not None:
             # weights may have changed since the plan was packed
-            self.depth_network.plan(V * B, B, H, W)
-            self.refine_network.plan(B, H, W, V // 2, False)
+            self.depth_network.plan(V * B, B, H, W, lane=lane)
+            self.refine_network.plan(B, H, W, V // 2, False, lane=lane)
             return st
         if V < 2 or V % 2:
             raise ValueError("the refine network takes two view groups: V must be even and >= 2 (got %d)" % V)
@@ -43,8 +43,8 @@ class CNMPipeline:
             "Kinv": torch.empty((B, 3, 3), **f32), "depth": torch.empty((B, H, W), **f32),
             "normal": torch.empty((B, 3, H, W), **f32), "graph": None,
         }
-        dplan = self.depth_network.plan(V * B, B, H, W)
-        rplan = self.refine_network.plan(B, H, W, V // 2, False)
+        dplan = self.depth_network.plan(V * B, B, H, W, lane=lane)
+        rplan = self.refine_network.plan(B, H, W, V // 2, False, lane=lane)
         dplan.bind(st["ref"], st["src"].view(V * B, 3, H, W), st["ref_cam"], st["src_cam"].view(V * B, 2, 4, 4))
         rplan.bind(dplan.disp1.view(V, B, H, W), dplan.iconv1)
         st["dplan"], st["rplan"] = dplan, rplan
@@ -101,72 +101,82 @@ class CNMPipeline:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         return self._prepare(B, V, H, W, dev)
 
-    def infer_stream(self, batches, after_step=None):
+    def infer_stream(self, batches, after_step=None, lanes=2):
         """Streams host batches through the pipeline with transfers overlapped with compute.
 
         `batches` yields (ref_img [B,3,H,W], src_imgs [B,V,3,H,W], ref_cam [B,2,4,4], src_cams [B,V,2,4,4]) CPU tensors
         (pinned memory gives asynchronous copies); yields (depth, normal, prob) as pinned CPU tensors, one tuple per
-        batch, in order (the tensors of a tuple are reused two batches later).  A copy stream uploads batch i+1 and
-        downloads batch i-1 while batch i computes: double-buffered device staging on both sides, CUDA events
-        between the streams, no host synchronisation except when a result is handed out.  `after_step(st)`, if
-        given, is enqueued on the compute stream after every graph replay (bench.py gathers outputs across ranks
-        there)."""
-        comp = torch.cuda.current_stream()
-        st = stage_in = stage_out = host_out = up = down = None
+        batch, in order (the tensors of a tuple are reused 2*lanes batches later).
+
+        Batch i runs on lane i % lanes: every lane owns a complete buffer set + CUDA graph and its own compute
+        stream, so consecutive batches overlap on the GPU -- the second lane fills what one step leaves idle (the
+        partial last wave of every convolution, the launch gaps between the 75 kernels of a step, the layers with
+        fewer tiles than SMs).  A copy stream uploads batch i+lanes and another downloads batch i-1 meanwhile; CUDA
+        events order the streams, the host only blocks when a result is handed out.  `after_step(st)`, if given, is
+        enqueued on the lane's compute stream after every graph replay (bench.py gathers outputs across ranks
+        there).  lanes=1 reproduces the strictly sequential schedule."""
+        caller = torch.cuda.current_stream()
+        states = stage_in = stage_out = host_out = comp = up = down = None
         ev = {}
         pending = []
+        nslots = 2 * lanes
 
         def new_event(name, i):
             ev[(name, i)] = torch.cuda.Event()
             return ev[(name, i)]
 
         for i, (ref_img, src_imgs, ref_cam, src_cams) in enumerate(batches):
-            if st is None:
+            if states is None:
                 B, V = src_imgs.shape[:2]
                 H, W = ref_img.shape[2:]
                 dev = next(self.depth_network.parameters()).device
-                st = self._prepare(B, V, H, W, dev)
-                if "stream_bufs" not in st:
+                states = [self._prepare(B, V, H, W, dev, lane) for lane in range(lanes)]
+                st0 = states[0]
+                key = ("stream_bufs", lanes)
+                if key not in st0:
                     # staging keeps the caller's [B,V,...] layout so the uploads are plain contiguous DMA transfers; the
                     # view-major transpose happens in the device-side copy into the static buffers.  Allocated once per
                     # shape: pinning host memory costs milliseconds.  Separate copy streams: an upload never queues
                     # behind a download.
                     f32 = dict(dtype=torch.float32, device=dev)
-                    st["stream_bufs"] = (
+                    st0[key] = (
                         [[torch.empty((B, 3, H, W), **f32), torch.empty((B, V, 3, H, W), **f32),
-                          torch.empty((B, 2, 4, 4), **f32), torch.empty((B, V, 2, 4, 4), **f32)] for _ in range(2)],
-                        [[torch.empty_like(st[k]) for k in ("depth", "normal", "prob")] for _ in range(2)],
-                        [[torch.empty(st[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
-                         for _ in range(2)],
-                        torch.cuda.Stream(), torch.cuda.Stream())
-                stage_in, stage_out, host_out, up, down = st["stream_bufs"]
-                # results of an earlier call may still be in flight on the copy streams
-                up.wait_stream(comp)
-                down.wait_stream(comp)
-                if self.use_graph and st["graph"] is None:
-                    self.step(st)  # capture outside the pipelined region
-            b = i & 1
-            with torch.cuda.stream(up):  # upload batch i (after compute consumed this staging slot two batches ago)
-                if ("in_free", i - 2) in ev:
-                    up.wait_event(ev.pop(("in_free", i - 2)))
+                          torch.empty((B, 2, 4, 4), **f32), torch.empty((B, V, 2, 4, 4), **f32)] for _ in range(nslots)],
+                        [[torch.empty_like(st0[k]) for k in ("depth", "normal", "prob")] for _ in range(nslots)],
+                        [[torch.empty(st0[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
+                         for _ in range(nslots)],
+                        [torch.cuda.Stream() for _ in range(lanes)], torch.cuda.Stream(), torch.cuda.Stream())
+                stage_in, stage_out, host_out, comp, up, down = st0[key]
+                for st in states:
+                    if self.use_graph and st["graph"] is None:
+                        self.step(st)  # capture outside the pipelined region
+                # work the caller enqueued earlier (and results of an earlier call still in flight) comes first
+                for s_ in comp + [up, down]:
+                    s_.wait_stream(caller)
+            lane, b = i % lanes, i % nslots
+            st, cs = states[lane], comp[lane]
+            with torch.cuda.stream(up):  # upload batch i (after compute consumed this staging slot nslots batches ago)
+                if ("in_free", i - nslots) in ev:
+                    up.wait_event(ev.pop(("in_free", i - nslots)))
                 for dst, src in zip(stage_in[b], (ref_img, src_imgs, ref_cam, src_cams)):
                     dst.copy_(src, non_blocking=True)
                 new_event("in", i).record(up)
-            comp.wait_event(ev.pop(("in", i)))
-            st["ref"].copy_(stage_in[b][0], non_blocking=True)
-            st["src"].copy_(stage_in[b][1].transpose(0, 1), non_blocking=True)
-            st["ref_cam"].copy_(stage_in[b][2], non_blocking=True)
-            st["src_cam"].copy_(stage_in[b][3].transpose(0, 1), non_blocking=True)
-            new_event("in_free", i).record(comp)
-            self.step(st)
-            if after_step is not None:
-                after_step(st)
-            if ("out_free", i - 2) in ev:
-                comp.wait_event(ev.pop(("out_free", i - 2)))
-            for dst, k in zip(stage_out[b], ("depth", "normal", "prob")):
-                dst.copy_(st[k], non_blocking=True)
-            new_event("out", i).record(comp)
-            with torch.cuda.stream(down):  # download batch i while batch i+1 computes
+            with torch.cuda.stream(cs):
+                cs.wait_event(ev.pop(("in", i)))
+                st["ref"].copy_(stage_in[b][0], non_blocking=True)
+                st["src"].copy_(stage_in[b][1].transpose(0, 1), non_blocking=True)
+                st["ref_cam"].copy_(stage_in[b][2], non_blocking=True)
+                st["src_cam"].copy_(stage_in[b][3].transpose(0, 1), non_blocking=True)
+                new_event("in_free", i).record(cs)
+                self.step(st)
+                if after_step is not None:
+                    after_step(st)
+                if ("out_free", i - nslots) in ev:
+                    cs.wait_event(ev.pop(("out_free", i - nslots)))
+                for dst, k in zip(stage_out[b], ("depth", "normal", "prob")):
+                    dst.copy_(st[k], non_blocking=True)
+                new_event("out", i).record(cs)
+            with torch.cuda.stream(down):  # download batch i while later batches compute
                 down.wait_event(ev.pop(("out", i)))
                 for dst, src in zip(host_out[b], stage_out[b]):
                     dst.copy_(src, non_blocking=True)
@@ -174,13 +184,16 @@ class CNMPipeline:
                 done = torch.cuda.Event()
                 done.record(down)
             pending.append((done, host_out[b]))
-            if len(pending) > 1:  # hand out batch i-1 (its download overlapped the launch of batch i)
+            if len(pending) > lanes:  # hand out the oldest batch; `lanes` batches stay in flight
                 d, outs = pending.pop(0)
                 d.synchronize()
                 yield tuple(outs)
         for d, outs in pending:
             d.synchronize()
             yield tuple(outs)
+        if comp is not None:
+            for s_ in comp + [up, down]:
+                caller.wait_stream(s_)
 
     def __call__(self, ref_img, src_imgs, ref_cam, src_cams):
         if ref_img.dim() != 4 or src_imgs.dim() != 5 or src_imgs.shape[0] != ref_img.shape[0]:

@@ -53,15 +53,16 @@ class VideoDepthStream:
         def gen():
             T, _, H, W = frames.shape
             V = len(tuples[0][1]) if tuples else 0
-            # two rotating pinned staging sets: infer_stream has at most two uploads in flight
+            # rotating pinned staging sets: infer_stream (two lanes) hands a result out -- and asks for the next batch --
+            # only after the batch three positions earlier has been consumed; one more set for margin
             pin = [[torch.empty(s, dtype=torch.float32).pin_memory() if torch.cuda.is_available() else
                     torch.empty(s, dtype=torch.float32)
-                    for s in ((B, 3, H, W), (B, V, 3, H, W), (B, 2, 4, 4), (B, V, 2, 4, 4))] for _ in range(3)]
+                    for s in ((B, 3, H, W), (B, V, 3, H, W), (B, 2, 4, 4), (B, V, 2, 4, 4))] for _ in range(4)]
             for n, g in enumerate(groups):
                 g = list(g) + [g[-1]] * (B - len(g))
                 ref_idx = torch.tensor([t[0] for t in g])
                 src_idx = torch.tensor([t[1] for t in g])
-                bufs = pin[n % 3]
+                bufs = pin[n % 4]
                 torch.index_select(frames, 0, ref_idx, out=bufs[0])
                 bufs[1].copy_(frames[src_idx.reshape(-1)].view(B, V, 3, H, W))
                 torch.index_select(cams, 0, ref_idx, out=bufs[2])

@@ -227,11 +227,12 @@ def test_infer_stream_matches_single_calls():
     pipe = cnmnet_b200.CNMPipeline(dnet, rnet, use_graph=True)
     batches = [tuple(t.pin_memory() for t in synth.frame_tuples(100 + i, B, H, W, V)) for i in range(5)]
     want = [tuple(o.cpu().clone() for o in pipe(*[t.to(dev()) for t in b])) for b in batches]
-    got = [tuple(o.clone() for o in outs) for outs in pipe.infer_stream(iter(batches))]
-    assert len(got) == len(want)
-    for g, w in zip(got, want):
-        for a, b in zip(g, w):
-            assert torch.equal(a, b)
+    for lanes in (2, 1, 3):
+        got = [tuple(o.clone() for o in outs) for outs in pipe.infer_stream(iter(batches), lanes=lanes)]
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            for a, b in zip(g, w):
+                assert torch.equal(a, b)
 
 
 def test_video_stream_matches_single_calls():
