@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   constexpr int B_BYTES = BN * 128;
   constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   constexpr uint32_t IDESC = IDESC_SHAPE | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10);
-  // CNM_F16F8: operand formats 0 = fp16 (kind::f16) on even groups and 0 = e4m3 (kind::f8f6f4) on odd ones
+  // CNM_F16F8: operand formats 0 = e4m3 (kind::f8f6f4) on the first half of the groups (the correction rows, accumulated
+  // while the sum is still tiny) and 0 = fp16 (kind::f16) on the second half
   const bool mixed = !TF32 && p.mode == EPI_F16F8;
   const uint32_t idesc = mixed ? IDESC_SHAPE : IDESC;
 
@@ -179,10 +180,10 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
             if (elect_one()) {
               const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
               const uint64_t adesc = adesc0 + (uint64_t)(t * (2048 >> 4));
-              if (mixed && (g & 1)) {
+              if (mixed && g < (p.num_groups >> 1)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  tc_mma_f8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                  tc_mma_f8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)

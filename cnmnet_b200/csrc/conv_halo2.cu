@@ -105,7 +105,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   constexpr int B_BYTES = (BN / 2) * 128;  // this CTA's half of the weight tile
   constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);  // M = 256 over the CTA pair
   constexpr uint32_t IDESC = IDESC_SHAPE | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10);
-  // CNM_F16F8: operand formats 0 = fp16 (kind::f16) on even groups and 0 = e4m3 (kind::f8f6f4) on odd ones
+  // CNM_F16F8: operand formats 0 = e4m3 (kind::f8f6f4) on the first half of the groups (the correction rows, accumulated
+  // while the sum is still tiny) and 0 = fp16 (kind::f16) on the second half
   const bool mixed = !TF32 && p.mode == EPI_F16F8;
   const uint32_t idesc = mixed ? IDESC_SHAPE : IDESC;  // M = 256 over the CTA pair
 
@@ -225,11 +226,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
             if (elect_one()) {
               const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
               const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
-              if (mixed && (g & 1)) {
+              if (mixed && g < (p.num_groups >> 1)) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  tc2_mma_f8(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                  tc2_mma_f8(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                  tc2_mma_f8(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                  tc2_mma_f8(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
                 }
               } else {
 #pragma unroll

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// CNM_F16F8 twin: even K-steps are fp16 rows (64 channels) against fp16 weight columns, odd K-steps are fp8 rows
+// CNM_F16F8 twin: the first half of the K-steps are fp8 rows, the second half fp16 rows (64 channels) against fp16 weight columns; fp8 rows
 // (128 e4m3 bytes: lo8 x 64 | hi8 x 64) against 128 e4m3 weight bytes; everything accumulates in fp32 and is scaled by
 // 2^-acc_exp, exactly the arithmetic the two tensor-core passes perform.
 __global__ void __launch_bounds__(256)
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256)
     const cnm_conv_step s = steps[st];
     const SimtSrc src = p.srcs[s.src];
     const int py = (s.sub >> 1) & 1, px = s.sub & 1;
-    const bool f8 = st & 1;
+    const bool f8 = st < (p.num_steps >> 1);
     for (int sub = 0; sub < (f8 ? 2 : 1); ++sub) {
       for (int i = threadIdx.x; i < SM_TM * CH; i += 256) {
         const int r = i / CH, c = i % CH;

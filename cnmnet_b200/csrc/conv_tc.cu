@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr uint32_t TMEM_COLS = 2 * BN;          // 128 / 256 / 512: powers of two >= 32
   constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   constexpr uint32_t IDESC = IDESC_SHAPE | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10);
-  // CNM_F16F8: operand formats 0 = fp16 (kind::f16) on even K-steps and 0 = e4m3 (kind::f8f6f4) on odd ones
+  // CNM_F16F8: operand formats 0 = e4m3 (kind::f8f6f4) on the first half of the K-steps (the correction rows, accumulated
+  // while the sum is still tiny) and 0 = fp16 (kind::f16) on the second half
   const bool mixed = !TF32 && p.mode == EPI_F16F8;
   const uint32_t idesc = mixed ? IDESC_SHAPE : IDESC;
 
@@ -93,8 +94,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n * p.ksplit;
-  // split-K: tile index = ((m * tiles_n) + nt) * ksplit + part; part runs K-steps [kbeg(part), kbeg(part+1)), cut at
-  // even step indices (the fp16 / fp8 steps of CNM_F16F8 alternate and every range must start on an fp16 step)
+  // split-K: tile index = ((m * tiles_n) + nt) * ksplit + part; part runs K-steps [kbeg(part), kbeg(part+1))
   auto kbeg = [&](int part) { return part >= p.ksplit ? p.num_steps : ((p.num_steps / 2) * part / p.ksplit) * 2; };
 
   if (warp == 0 && lane == 0) {
@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (elect_one()) {
             const uint32_t sa = base + stage * L::STAGE_BYTES;
             const uint64_t adesc = umma_desc(sa), bdesc = umma_desc(sa + TC_A_BYTES);
-            if (mixed && (ks & 1)) {
+            if (mixed && ks < (p.num_steps >> 1)) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                tc_mma_f8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                tc_mma_f8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (ks != k_begin || k) ? 1u : 0u);
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)  // 4 x 32 B along K inside the 128 B swizzle row

@@ -118,21 +118,40 @@ def make_steps(srcs, k, stride, ch, split=False):
                     for c0 in range(0, s.C, ch):
                         for ap, wp_ in _chunk_passes(split):
                             steps.append((si, sub, dx, dy, _pc0(s.coff + c0, ap, split)))
-                            cols.append(("act", s.wch + c0, r, t, wp_))
+                            cols.append(("act", s.wch + c0, r, t, wp_, ap))
         elif s.kind == "rowtaps":
             assert stride == 1 and k * s.nreal <= ch
             for r in range(k):
                 for ap, wp_ in _chunk_passes(split):
                     steps.append((si, 0, 0, r - pad, _pc0(0, ap, split)))
-                    cols.append(("rowtaps", s.wch, s.nreal, r, wp_))
+                    cols.append(("rowtaps", s.wch, s.nreal, r, wp_, ap))
         elif s.kind == "taps3x3":
             assert stride == 1 and k == 3 and 9 * s.nreal <= ch
             for ap, wp_ in _chunk_passes(split):
                 steps.append((si, 0, 0, 0, _pc0(0, ap, split)))
-                cols.append(("taps3x3", s.wch, s.nreal, 0, wp_))
+                cols.append(("taps3x3", s.wch, s.nreal, 0, wp_, ap))
         else:
             raise ValueError(s.kind)
-    return steps, cols
+    order = _corrections_first(cols)
+    return [steps[i] for i in order], [cols[i] for i in order]
+
+
+def _corrections_first(cols):
+    """Order of the K loop for the two-row (split) modes: every correction step (bf16x3: lo*Whi, hi*Wlo; f16f8: the fp8
+    row) before every leading-term step (hi*Whi / fp16 row).  The fp32 accumulation inside tcgen05.mma loses ~1 ulp of the
+    running sum per MMA instruction (tools/acc_floor.py); the correction terms are 2^-8 ... 2^-12 of the leading ones, so
+    accumulating them while the sum is still tiny costs nothing, and the leading terms then see one third (bf16x3) / one
+    half (f16f8) of the updates at full magnitude.  The kernels only need to know that the fp8 steps of f16f8 are the first
+    half of the list."""
+    main = [i for i, c in enumerate(cols) if len(c) > 4 and c[4] in ("hi", "h16") and _apart(c) == "hi"]
+    if not main or len(main) == len(cols):
+        return list(range(len(cols)))
+    ms = set(main)
+    return [i for i in range(len(cols)) if i not in ms] + main
+
+
+def _apart(col):
+    return col[5] if len(col) > 5 else "hi"
 
 
 def make_groups(srcs, k, ch, stride=1, split=False):
@@ -149,7 +168,7 @@ def make_groups(srcs, k, ch, stride=1, split=False):
                 for t in range(k):
                     for ap, wp_ in _chunk_passes(split):
                         groups.append((si * 4, _pc0(s.coff + c0, ap, split), t - pad, k))
-                        cols += [("act", s.wch + c0, r, t, wp_) for r in range(k)]
+                        cols += [("act", s.wch + c0, r, t, wp_, ap) for r in range(k)]
         elif s.kind == "act":  # stride 2: taps grouped by (column tap, row parity) on the parity sub-images
             for c0 in range(0, s.C, ch):
                 for t in range(k):
@@ -165,22 +184,30 @@ def make_groups(srcs, k, ch, stride=1, split=False):
                         info[m] = [-qs[0], 16 + qs[-1] - qs[0]]
                         for ap, wp_ in _chunk_passes(split):
                             groups.append((m, _pc0(s.coff + c0, ap, split), qx, len(rs)))
-                            cols += [("act", s.wch + c0, r, t, wp_) for r in rs]
+                            cols += [("act", s.wch + c0, r, t, wp_, ap) for r in rs]
         elif s.kind == "rowtaps":
             assert stride == 1 and k * s.nreal <= ch
             info[si * 4] = [pad, 16 + 2 * pad]
             for ap, wp_ in _chunk_passes(split):
                 groups.append((si * 4, _pc0(0, ap, split), 0, k))
-                cols += [("rowtaps", s.wch, s.nreal, r, wp_) for r in range(k)]
+                cols += [("rowtaps", s.wch, s.nreal, r, wp_, ap) for r in range(k)]
         elif s.kind == "taps3x3":
             assert stride == 1 and k == 3 and 9 * s.nreal <= ch
             info[si * 4] = [0, 16]
             for ap, wp_ in _chunk_passes(split):
                 groups.append((si * 4, _pc0(0, ap, split), 0, 1))
-                cols.append(("taps3x3", s.wch, s.nreal, 0, wp_))
+                cols.append(("taps3x3", s.wch, s.nreal, 0, wp_, ap))
         else:
             raise ValueError(s.kind)
-    return groups, cols, info
+    # corrections first, group-wise (a group's weight steps stay together and in order)
+    starts, pos = [], 0
+    for g in groups:
+        starts.append(pos)
+        pos += g[3]
+    gorder = _corrections_first([cols[st] for st in starts])
+    groups2 = [groups[i] for i in gorder]
+    cols2 = [c for i in gorder for c in cols[starts[i]:starts[i] + groups[i][3]]]
+    return groups2, cols2, info
 
 
 def _gather_cols(w, cols, ch, want=None):

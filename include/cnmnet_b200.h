@@ -51,8 +51,9 @@ typedef enum cnm_dtype {
                     hi * W16 and kind::f8f6f4 [lo8 | hi8] * [Whi8 | Wlo8] (K = 128 fp8 elements per 128-byte row,
                     twice the bf16 rate), with the power-of-two scales folded into the packed weights:
                     W16 = fp16(w * 2^e), Whi8 = e4m3(w * 2^(e-7)), Wlo8 = e4m3((w * 2^e - W16) * 2^4); the
-                    accumulator is multiplied by 2^-e (desc.acc_exp = e) before bias / ReLU.  K-steps (groups)
-                    alternate fp16 row, fp8 row.  ~22 significand bits for the leading term, corrections good to
+                    accumulator is multiplied by 2^-e (desc.acc_exp = e) before bias / ReLU.  The FIRST half
+                    of the K-steps (groups) are the fp8 rows, the second half the fp16 rows: the small correction terms
+                    are accumulated while the sum is tiny, which halves the rounding of the tensor core's accumulator.  ~22 significand bits for the leading term, corrections good to
                     ~2^-17 relative: same accuracy class as CNM_BF16X3 at 2/3 of its tensor time. */
 } cnm_dtype;
 

@@ -148,9 +148,9 @@ def test_pipeline_odd_pyramid_sizes(H, W, B, precision):
     d, n, p = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))
     want_d, want_n, want_p = _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, 9)
     rel = np.abs(d.cpu().numpy() - want_d) / np.abs(want_d)
-    # these weights (seed 51/52) are ~8x more sensitive than the others in this file (tools/acc_probe.py: tf32 p99 7e-3,
-    # bf16x3 max 7e-4, independent of the image size): the north-star 1e-3 still holds in the accuracy mode
-    assert rel.max() < 1e-3 and rel.mean() < 3e-4, (rel.max(), rel.mean())
+    # these weights (seed 51/52) are ~8x more sensitive than the others in this file (tools/acc_probe.py: tf32 p99 7e-3):
+    # the north-star 1e-3 holds in the accuracy modes with a 2x margin
+    assert rel.max() < 5e-4 and rel.mean() < 1e-4, (rel.max(), rel.mean())
     assert np.abs(p.cpu().numpy() - want_p).max() < 2e-3
 
 
@@ -183,10 +183,10 @@ def test_pipeline_128_planes(precision):
     rel = np.abs(d.cpu().numpy() - want_d) / np.abs(want_d)
     # These weights are the most error-sensitive set in the suite (CPU emulation of the operand roundings,
     # tools/emulate_modes.py: tf32 mean 1.6e-3 / max 1e-2; f16f8 mean 5.7e-5 / max 2.9e-4, which the fp32-FMA SIMT twin
-    # reproduces on the GPU).  On the tensor cores the floor is the fp32 accumulation inside tcgen05.mma, which grows
-    # with the number of MMA instructions per accumulator (tools/acc_floor.py: f16f8 mean 4.4e-4 / max 1.1e-3, bf16x3
-    # with 1.5x the instructions 6.2e-4 / 1.4e-3): gate at the tf32-class tolerance here.
-    assert np.percentile(rel, 99) < 1.5e-3 and rel.max() < 2.5e-3 and rel.mean() < 8e-4, \
+    # reproduces on the GPU).  With the correction steps accumulated first (engine._corrections_first) the tensor cores
+    # stay close to that: tools/acc_floor.py measures f16f8 mean 9.3e-5 / max 3.9e-4, bf16x3 7.5e-5 / 2.2e-4 (the
+    # interleaved K order gave 4.4e-4 / 1.1e-3 and 6.2e-4 / 1.4e-3).
+    assert np.percentile(rel, 99) < 5e-4 and rel.max() < 1e-3 and rel.mean() < 2e-4, \
         (np.percentile(rel, 99), rel.max(), rel.mean())
 
 

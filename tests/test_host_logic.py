@@ -203,12 +203,14 @@ def _f16f8_phys(x_nhwc):
 
 
 def emulate_f16f8_steps(srcs_bytes, steps, wp_bytes, bias, acc_exp):
-    """The CNM_F16F8 K loop: even steps multiply a 128-byte fp16 row (64 ch) with 64 fp16 weight columns, odd steps a
-    128-byte e4m3 row with 128 e4m3 weight columns; one accumulator, scaled by 2^-acc_exp before the bias."""
+    """The CNM_F16F8 K loop: the first half of the steps multiply a 128-byte e4m3 row with 128 e4m3 weight columns, the
+    second half a 128-byte fp16 row (64 ch) with 64 fp16 weight columns; one accumulator, scaled by 2^-acc_exp before the
+    bias."""
     N, H, W, _ = srcs_bytes[0].shape
     out = torch.zeros((N, H, W, wp_bytes.shape[0]), dtype=torch.float64)
     for i, (si, sub, dx, dy, c0) in enumerate(steps):
-        assert sub == 0 and (c0 % 128 == 64) == bool(i & 1)          # rows alternate fp16, fp8
+        f8 = i < len(steps) // 2                                     # corrections first, then the fp16 rows
+        assert sub == 0 and (c0 % 128 == 64) == f8
         x = srcs_bytes[si]
         a = torch.zeros((N, H, W, 128), dtype=torch.uint8)
         ys, xs = torch.arange(H) + dy, torch.arange(W) + dx
@@ -216,7 +218,7 @@ def emulate_f16f8_steps(srcs_bytes, steps, wp_bytes, bias, acc_exp):
         a[:, vy.nonzero().flatten()[:, None], vx.nonzero().flatten()[None, :]] = \
             x[:, ys[vy][:, None], xs[vx][None, :], 2 * c0:2 * c0 + 128]
         wrow = wp_bytes[:, i * 128:(i + 1) * 128].contiguous()
-        if i & 1:
+        if f8:
             out += a.view(torch.float8_e4m3fn).double() @ wrow.view(torch.float8_e4m3fn).double().T
         else:
             out += a.view(torch.float16).double() @ wrow.view(torch.float16).double().T
@@ -242,12 +244,9 @@ def test_f16f8_programs_reproduce_conv(halo):
     srcs = [engine.act_src(xp, 0, phys=2), engine.Src(tp, "taps3x3", 128, ch, 0, 1)]
     passes = engine.split_passes(_lib.CNM_F16F8)
     if halo:
-        groups, cols, info = engine.make_groups(srcs, k, ch, 1, split=passes)
-        assert all((c0 % 128 == 64) == bool(i & 1) for i, (m, c0, dx, nt) in enumerate(groups))
+        groups, gcols, info = engine.make_groups(srcs, k, ch, 1, split=passes)
+        assert all((c0 % 128 == 64) == (i < len(groups) // 2) for i, (m, c0, dx, nt) in enumerate(groups))
         steps = [(m // 4, 0, dx, t - info[m][0], c0) for (m, c0, dx, nt) in groups for t in range(nt)]
-        # weight steps follow the groups; re-sort both into the alternating order the byte emulator checks
-        order = sorted(range(len(steps)), key=lambda i: (i // 6 * 6 + (i % 3) * 2 + (i % 6) // 3) if i < 36 else i)
-        steps, gcols = [steps[i] for i in order], [cols[i] for i in order]
     else:
         steps, gcols = engine.make_steps(srcs, k, 1, ch, split=passes)
     assert len(steps) == len(gcols) == 2 * (9 * 2 + 1)
