@@ -108,7 +108,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   // CNM_F16F8: operand formats 0 = e4m3 (kind::f8f6f4) on the first half of the groups (the correction rows, accumulated
   // while the sum is still tiny) and 0 = fp16 (kind::f16) on the second half
   const bool mixed = !TF32 && p.mode == EPI_F16F8;
-  const uint32_t idesc = mixed ? IDESC_SHAPE : IDESC;  // M = 256 over the CTA pair
+  const uint32_t idesc = mixed ? IDESC_SHAPE : IDESC;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;

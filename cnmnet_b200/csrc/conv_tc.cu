@@ -12,10 +12,15 @@
 //                  The box lands in smem as 128 rows x 128 B, 128B-swizzled = a K-major UMMA tile.
 // B operand      2-D TMA box {chunk, BN} of the packed weights [Cout, K] (BN folded), same layout.
 // MMA            tcgen05.mma cta_group::1, M = 128, N = BN, K = 32 bytes per instruction
-//                  (kind::f16: 16 x bf16, kind::tf32: 8 x tf32); fp32 accumulators in TMEM, two
-//                  accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
-// Epilogue       4 warps: tcgen05.ld -> + bias -> ReLU -> cast -> swizzled smem -> TMA store into a
-//                  channel slice of the NHWC output (TMA clips partial tiles).
+//                  (kind::f16: 16 x bf16 / fp16, kind::tf32: 8 x tf32, kind::f8f6f4: 32 x e4m3 for the
+//                  correction rows of CNM_F16F8); fp32 accumulators in TMEM, two accumulator stages
+//                  so the epilogue of tile i overlaps the main loop of tile i+1.
+// Epilogue       4 warps: tcgen05.ld -> * 2^-acc_exp + bias -> ReLU -> pack (bf16 / tf32 / hi+lo rows /
+//                  fp16 + fp8 rows) -> swizzled smem -> TMA store into a channel slice of the NHWC
+//                  output (TMA clips partial tiles).  Optional: the nine tap dot products of a fused
+//                  1-channel head (Cout = 64), or raw accumulators to the split-K workspace.
+// Split-K        desc.ksplit > 1: tile index gains a K-range dimension; splitk_finish_kernel sums the
+//                  ranges in a fixed order and does the epilogue work.
 // Warp roles     warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM
 //                  allocator, warp 3 idle, warps 4-7 = epilogue (TMEM lane quarter = warp - 4).
 #include <cstring>

@@ -8,7 +8,7 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 import cnmnet_b200  # noqa: E402
 
-precision = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+precision = sys.argv[1] if len(sys.argv) > 1 else "f16f8"
 dev = torch.device("cuda", 0)
 dnet, rnet = bench.make_weights(0)
 dnet.precision = rnet.precision = cnmnet_b200.engine.parse_dtype(precision)
