@@ -365,6 +365,7 @@ def main():
         "launches_per_step": int(launches_per_step),
         "wall_ms_per_step_incl_flush": wall_ms / args.steps,
         "back_to_back_ms_per_step": b2b_ms,
+        "plan_activation_bytes_per_lane": int(st["dplan"].bytes_allocated + st["rplan"].bytes_allocated),
     }
 
     if rank == 0 and os.environ.get("CNM_SAVE_TUNE_CACHE"):

@@ -20,6 +20,7 @@ BN_EPS = 1e-5
 # which stride-1 layers use the row-halo kernel: "auto" (enough tiles for a wave), "force" (every eligible layer,
 # used by tests), "off" (per-tap kernel everywhere)
 HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
+PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0"   # activation buffers of a plan are recycled after their last reader
 FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
 TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32, CNM_BF16X3: torch.bfloat16, CNM_F16F8: torch.float16}
@@ -474,19 +475,50 @@ class _Plan:
         self.heads = {}    # name -> dict(w, bias, scale)
         self.ch = chunk_channels(self.dtype)
         self.pf = phys_factor(self.dtype)
+        self._storage = {}   # data_ptr of a live buffer -> its uint8 backing tensor
+        self._free = []      # backing tensors whose last reader has been enqueued: reusable by later ops
+        self.bytes_allocated = 0
 
-    def buf(self, *shape, dtype=None):
-        """Plain buffer (dtype given) or act tensor [N,H,W,C logical] (C * pf physical channels)."""
+    def buf(self, *shape, dtype=None, fresh=False):
+        """Plain buffer (dtype given) or act tensor [N,H,W,C logical] (C * pf physical channels).
+
+        Buffers come from a small arena: ops run in creation order on one stream, so a buffer handed back with
+        release() after its last reader was created can back any later tensor (PLAN_REUSE).  A plan then holds the peak
+        live set instead of the sum of all activations (~1.7x less)."""
         if dtype is None:
             shape = tuple(shape[:-1]) + (shape[-1] * self.pf,)
-        return torch.empty(shape, dtype=TORCH_DTYPE[self.dtype] if dtype is None else dtype, device=self.device)
+        dt = TORCH_DTYPE[self.dtype] if dtype is None else dtype
+        n = 1
+        for v in shape:
+            n *= int(v)
+        need = (n * torch.empty((), dtype=dt).element_size() + 511) // 512 * 512
+        best = None
+        if PLAN_REUSE and not fresh:
+            for i, t in enumerate(self._free):
+                if t.numel() >= need and (best is None or t.numel() < self._free[best].numel()):
+                    best = i
+        if best is not None:
+            store = self._free.pop(best)
+        else:
+            store = torch.empty((need,), dtype=torch.uint8, device=self.device)
+            self.bytes_allocated += need
+        out = store[:n * torch.empty((), dtype=dt).element_size()].view(dt).view(shape)
+        self._storage[out.data_ptr()] = store
+        return out
+
+    def release(self, *tensors):
+        """The last op reading these buffers has been created: their memory may back later tensors."""
+        for t in tensors:
+            store = self._storage.pop(t.data_ptr(), None)
+            if store is not None:
+                self._free.append(store)
 
     def src(self, buf, wch):
         return act_src(buf, wch, phys=self.pf)
 
     def conv(self, name, srcs, k, stride, cout, N, Ho, Wo, relu=True):
-        op = ConvOp(name, srcs, k, stride, cout, N, Ho, Wo, self.dtype, self.device, relu, backend=self.backend,
-                    lane=self.lane)
+        op = ConvOp(name, srcs, k, stride, cout, N, Ho, Wo, self.dtype, self.device, relu, out=self.buf(N, Ho, Wo, cout),
+                    backend=self.backend, lane=self.lane)
         self.convs[name] = op
         self.ops.append(op)
         return op.out
@@ -514,12 +546,14 @@ class _Plan:
             # 64-channel heads ride in the producing convolution's epilogue (nine per-tap dot products per pixel from
             # the fp32 accumulators); what is left is a 3x3 gather of scalars + bias + sigmoid
             op = producer[0]
-            partial = self.buf(N, H, W, 12, dtype=torch.float32)
+            # fresh: the producing conv (created earlier) writes it while reading inputs that may already be released
+            partial = self.buf(N, H, W, 12, dtype=torch.float32, fresh=True)
             hw["w_tap_major"] = torch.zeros((9, 64), dtype=torch.float32, device=self.device)
             hw["partial"] = partial
             op.fuse_head(hw["w_tap_major"], partial)
             self.ops.append(lambda s: _lib.check(
                 lib.cnm_head_finish(partial.data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s), name))
+            self.release(partial)
             return out, logits
         if FUSE_HEADS:
             # two passes: per-pixel tap dot products (each input element read and decoded once), then the 3x3 gather
@@ -534,6 +568,7 @@ class _Plan:
                            name)
 
             self.ops.append(two_pass)
+            self.release(partial)
             return out, logits
         self.ops.append(lambda s: _lib.check(
             lib.cnm_head3x3(x.data_ptr(), hw["w"].data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, Cc,
@@ -618,36 +653,62 @@ class DepthNetPlan(_Plan):
 
     def _trunk(self, want_logits):
         N, H, W = self.N, self.H, self.W
-        cv = self.conv
+        cv, rel, up = self.conv, self.release, self.upsample
         x = cv("conv1.0", [self.src(self.cost, 3), Src(self.img_taps, "rowtaps", 0, self.ch, 0, 3)], 7, 1, 128, N, H, W)
+        rel(self.cost, self.img_taps)
         conv1 = cv("conv1.3", [self.src(x, 0)], 7, 2, 128, N, H // 2, W // 2)
+        rel(x)
         x = cv("conv2.0", [self.src(conv1, 0)], 5, 1, 256, N, H // 2, W // 2)
         conv2 = cv("conv2.3", [self.src(x, 0)], 5, 2, 256, N, H // 4, W // 4)
+        rel(x)
         x = cv("conv3.0", [self.src(conv2, 0)], 3, 1, 512, N, H // 4, W // 4)
         conv3 = cv("conv3.3", [self.src(x, 0)], 3, 2, 512, N, H // 8, W // 8)
+        rel(x)
         x = cv("conv4.0", [self.src(conv3, 0)], 3, 1, 512, N, H // 8, W // 8)
         conv4 = cv("conv4.3", [self.src(x, 0)], 3, 2, 512, N, H // 16, W // 16)
+        rel(x)
         x = cv("conv5.0", [self.src(conv4, 0)], 3, 1, 512, N, H // 16, W // 16)
         conv5 = cv("conv5.3", [self.src(x, 0)], 3, 2, 512, N, H // 32, W // 32)
+        rel(x)
 
-        up5 = cv("upconv5.1", [self.src(self.upsample(conv5), 0)], 3, 1, 512, N, H // 16, W // 16)
+        u = up(conv5)
+        rel(conv5)
+        up5 = cv("upconv5.1", [self.src(u, 0)], 3, 1, 512, N, H // 16, W // 16)
+        rel(u)
         iconv5 = cv("iconv5.0", [self.src(up5, 0), self.src(conv4, 512)], 3, 1, 512, N, H // 16, W // 16)
-        up4 = cv("upconv4.1", [self.src(self.upsample(iconv5), 0)], 3, 1, 512, N, H // 8, W // 8)
+        rel(up5, conv4)
+        u = up(iconv5)
+        rel(iconv5)
+        up4 = cv("upconv4.1", [self.src(u, 0)], 3, 1, 512, N, H // 8, W // 8)
+        rel(u)
         iconv4 = cv("iconv4.0", [self.src(up4, 0), self.src(conv3, 512)], 3, 1, 512, N, H // 8, W // 8)
+        rel(up4, conv3)
         self.disp4, l4 = self.head("disp4", iconv4, self.scale, want_logits)
         t4 = self.disp_taps(self.disp4)
-        up3 = cv("upconv3.1", [self.src(self.upsample(iconv4), 0)], 3, 1, 256, N, H // 4, W // 4)
+        u = up(iconv4)
+        rel(iconv4)
+        up3 = cv("upconv3.1", [self.src(u, 0)], 3, 1, 256, N, H // 4, W // 4)
+        rel(u)
         iconv3 = cv("iconv3.0", [self.src(up3, 0), self.src(conv2, 256), Src(t4, "taps3x3", 512, self.ch, 0, 1)], 3, 1,
                     256, N, H // 4, W // 4)
+        rel(up3, conv2, t4)
         self.disp3, l3 = self.head("disp3", iconv3, self.scale, want_logits)
         t3 = self.disp_taps(self.disp3)
-        up2 = cv("upconv2.1", [self.src(self.upsample(iconv3), 0)], 3, 1, 128, N, H // 2, W // 2)
+        u = up(iconv3)
+        rel(iconv3)
+        up2 = cv("upconv2.1", [self.src(u, 0)], 3, 1, 128, N, H // 2, W // 2)
+        rel(u)
         iconv2 = cv("iconv2.0", [self.src(up2, 0), self.src(conv1, 128), Src(t3, "taps3x3", 256, self.ch, 0, 1)], 3, 1,
                     128, N, H // 2, W // 2)
+        rel(up2, conv1, t3)
         self.disp2, l2 = self.head("disp2", iconv2, self.scale, want_logits)
         t2 = self.disp_taps(self.disp2)
-        up1 = cv("upconv1.1", [self.src(self.upsample(iconv2), 0)], 3, 1, 64, N, H, W)
+        u = up(iconv2)
+        rel(iconv2)
+        up1 = cv("upconv1.1", [self.src(u, 0)], 3, 1, 64, N, H, W)
+        rel(u)
         self.iconv1 = cv("iconv1.0", [self.src(up1, 0), Src(t2, "taps3x3", 64, self.ch, 0, 1)], 3, 1, 64, N, H, W)
+        rel(up1, t2)
         self.disp1, l1 = self.head("disp1", self.iconv1, self.scale, want_logits)
         self.logits = [l1, l2, l3, l4]
         self.tune()
@@ -707,24 +768,39 @@ class RefinePlan(_Plan):
                                                     s), "refine_aggregate")
 
         self.ops.append(front)
-        cv = self.conv
+        cv, rel = self.conv, self.release
         x = cv("conv1.0", [self.src(self.sum_act, 3), Src(self.taps, "taps3x3", 0, ch, 0, 3)], 3, 1, 128, B, H, W)
+        rel(self.sum_act, self.taps)
         conv1 = cv("conv1.3", [self.src(x, 0)], 3, 2, 128, B, H // 2, W // 2)
+        rel(x)
         x = cv("conv2.0", [self.src(conv1, 0)], 3, 1, 256, B, H // 2, W // 2)
         conv2 = cv("conv2.3", [self.src(x, 0)], 3, 2, 256, B, H // 4, W // 4)
+        rel(x)
         x = cv("conv3.0", [self.src(conv2, 0)], 3, 1, 512, B, H // 4, W // 4)
         conv3 = cv("conv3.3", [self.src(x, 0)], 3, 2, 512, B, H // 8, W // 8)
+        rel(x)
         up_conv3 = self.upsample(conv3)  # shared by both decoders
+        rel(conv3)
         self.out, self.logits, self.iconv1 = {}, {}, {}
         for br, head, sc in (("depth", "disp_refine", self.scale), ("prob", "prob", 1.0)):
             u3 = cv("upconv3_%s.1" % br, [self.src(up_conv3, 0)], 3, 1, 256, B, H // 4, W // 4)
             i3 = cv("iconv3_%s.0" % br, [self.src(u3, 0), self.src(conv2, 256)], 3, 1, 256, B, H // 4, W // 4)
-            u2 = cv("upconv2_%s.1" % br, [self.src(self.upsample(i3), 0)], 3, 1, 128, B, H // 2, W // 2)
+            rel(u3)
+            u = self.upsample(i3)
+            rel(i3)
+            u2 = cv("upconv2_%s.1" % br, [self.src(u, 0)], 3, 1, 128, B, H // 2, W // 2)
+            rel(u)
             i2 = cv("iconv2_%s.0" % br, [self.src(u2, 0), self.src(conv1, 128)], 3, 1, 128, B, H // 2, W // 2)
-            u1 = cv("upconv1_%s.1" % br, [self.src(self.upsample(i2), 0)], 3, 1, 64, B, H, W)
+            rel(u2)
+            u = self.upsample(i2)
+            rel(i2)
+            u1 = cv("upconv1_%s.1" % br, [self.src(u, 0)], 3, 1, 64, B, H, W)
+            rel(u)
             i1 = cv("iconv1_%s.0" % br, [self.src(u1, 0)], 3, 1, 64, B, H, W)
-            self.iconv1[br] = i1
+            rel(u1)
+            self.iconv1[br] = i1          # kept: ReturnVolume hands iconv1_depth out
             self.out[br], self.logits[br] = self.head(head, i1, sc, want_logits)
+        rel(up_conv3, conv2, conv1)
         self.tune()
 
     load_state = DepthNetPlan.load_state

@@ -1,5 +1,6 @@
 """Layer-by-layer comparison of the per-tap and row-halo tensor-core kernels on one DepthNet + RefineNet pass."""
 import os
+os.environ["CNM_PLAN_REUSE"] = "0"   # intermediate activations are compared: keep every buffer
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
