@@ -315,6 +315,29 @@ def main():
         b.synchronize()
         b2b_ms = a.elapsed_time(b) / args.steps
         barrier()
+        # diagnostic: resident inputs, K steps alternating over two lanes (two buffer sets / graphs / streams): what
+        # the streaming API can reach when transfers are free
+        two_lane_ms = None
+        if (args.lanes or (2 if args.workload == "c4" else 1)) >= 2:
+            st1 = pipe._prepare(B, V, H, W, dev, lane=1)
+            pipe.load_inputs(st1, *host, non_blocking=False)
+            pipe.step(st1)
+            torch.cuda.synchronize()
+            cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            side.wait_stream(cur)
+            for i in range(args.steps):
+                if i & 1:
+                    with torch.cuda.stream(side):
+                        pipe.step(st1)
+                else:
+                    pipe.step(st)
+            cur.wait_stream(side)
+            b.record()
+            b.synchronize()
+            two_lane_ms = a.elapsed_time(b) / args.steps
+            barrier()
         # ---- end to end through the public streaming API (CNMPipeline.infer_stream): every step uploads its inputs
         # from pinned host memory and downloads depth / normal / prob to the host; uploads of step i+1 and
         # downloads of step i-1 overlap the compute of step i on a copy stream ----
@@ -365,6 +388,7 @@ def main():
         "launches_per_step": int(launches_per_step),
         "wall_ms_per_step_incl_flush": wall_ms / args.steps,
         "back_to_back_ms_per_step": b2b_ms,
+        "two_lane_resident_ms_per_step": two_lane_ms,
         "plan_activation_bytes_per_lane": int(st["dplan"].bytes_allocated + st["rplan"].bytes_allocated),
     }
 

@@ -278,6 +278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
         epi_bar();
         for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
         bias_tile = nt;
+        epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
       mbar_wait(tfull(as), aphase);
       tc_fence_after();

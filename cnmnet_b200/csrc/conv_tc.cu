@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         epi_bar();  // previous tile's bias reads are done
         for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
         bias_tile = nt;
-        // visibility is ordered by the epi_bar() inside the chunk loop below
+        epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();

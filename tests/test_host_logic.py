@@ -375,3 +375,30 @@ def test_video_batches_gather_and_pad():
     assert rc[:, 0, 0, 0].tolist() == [120, 150, 180, 210] and sc[:, 1, 0, 0, 0].tolist() == [20, 50, 80, 110]
     ref, srcs, _, _ = got[1]
     assert ref[:, 0, 0, 0].tolist() == [24, 27, 27, 27]                              # padded with the last tuple
+
+
+def test_correction_steps_come_first():
+    """K order of the two-row modes (engine._corrections_first): every correction step before every leading-term step,
+    for the per-tap step list and group-wise for the row-halo list; one-row modes keep their order."""
+    x = torch.empty(1, 8, 8, 256, dtype=torch.float16)
+    t = torch.empty(1, 8, 8, 128, dtype=torch.float16)
+    srcs = [engine.act_src(x, 0, phys=2), engine.Src(t, "taps3x3", 128, 64, 0, 1)]
+    for passes, main in ((engine.split_passes(_lib.CNM_F16F8), ("hi", "h16")), (engine.split_passes(_lib.CNM_BF16X3), ("hi", "hi"))):
+        steps, cols = engine.make_steps(srcs, 3, 1, 64, split=passes)
+        is_main = [(c[5], c[4]) == main for c in cols]
+        n_main = sum(is_main)
+        assert n_main == len(cols) // len(passes) and all(is_main[-n_main:]) and not any(is_main[:-n_main])
+        groups, gcols, _ = engine.make_groups(srcs, 3, 64, 1, split=passes)
+        g_main = []
+        pos = 0
+        for g in groups:
+            kinds = {(c[5], c[4]) == main for c in gcols[pos:pos + g[3]]}
+            assert len(kinds) == 1                                    # a group is all-leading or all-correction
+            g_main.append(kinds.pop())
+            pos += g[3]
+        k = sum(g_main)
+        assert pos == len(gcols) and all(g_main[-k:]) and not any(g_main[:-k])
+        if passes is engine.split_passes(_lib.CNM_F16F8):
+            assert k == len(groups) // 2 and all(c0 % 128 == 64 for (_, c0, _, _) in groups[:k])   # fp8 rows = first half
+    steps, cols = engine.make_steps([engine.act_src(torch.empty(1, 8, 8, 128), 0)], 3, 1, 64)
+    assert [c[2:4] for c in cols[:2]] == [(0, 0), (0, 0)] and len(cols) == 18   # unchanged: tap-major, chunk inner
