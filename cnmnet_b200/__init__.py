@@ -12,3 +12,4 @@ from .depthnet.depth_util import (Depth2normal, get_normal_by_planes, get_pixel_
 from .depthnet.inverse_warp import inverse_warp, pixel2cam  # noqa: F401
 from .pipeline import CNMPipeline  # noqa: F401
 from .video import VideoDepthStream, reference_tuples  # noqa: F401
+from .metrics import depth_metrics  # noqa: F401

@@ -108,6 +108,17 @@ int64_t cnm_plane_regularize_workspace_bytes(int B, int P, int H, int W);
 int cnm_plane_regularize(float* normals, const uint8_t* segs, const int32_t* planes_num, double* loss, void* workspace,
                          int B, int P, int H, int W, void* stream);
 
+/* ---- depth evaluation metrics ------------------------------------------------------------
+ * replaces the per-image body of cal_metrics (eval.py:1030-1047) and the functions it calls in
+ * utils/metric.py:149-362.  pred, gt [B,H,W] fp32 (device); pred is clamped to [min_depth,
+ * max_depth], valid pixels are min_depth < gt < max_depth and finite.  out [B,10] double =
+ * {num_valid, l1, abs_relative, rmse, scale_invariant, sq_relative, rmse_log, a1, a2, a3}
+ * (NaN metrics for an image without valid pixels, like the reference).  workspace:
+ * cnm_depth_metrics_workspace_bytes() bytes, 8B aligned.                                    */
+int64_t cnm_depth_metrics_workspace_bytes(int B, int H, int W);
+int cnm_depth_metrics(const float* pred, const float* gt, double* out, void* workspace, int B, int H, int W,
+                      float min_depth, float max_depth, void* stream);
+
 /* ---- idepth -> depth -------------------------------------------------------------------
  * replaces torch.div(1.0, idepth)  (eval.py:269,452,934).  n elements.                      */
 int cnm_reciprocal(const float* idepth, float* depth, int64_t n, void* stream);

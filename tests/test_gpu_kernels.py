@@ -289,6 +289,29 @@ def test_wide_heads_both_forms(dtype, C, H, W):
         assert (o.cpu() - 2.0 * torch.sigmoid(wl)).abs().max() < 5e-5
 
 
+def test_depth_metrics_golden_and_oracle(golden_dir):
+    """cnm_depth_metrics vs the reference's functions (golden) and vs the oracle on a larger random case."""
+    from oracle import metrics as omet
+    g = _g(golden_dir, "depth_metrics.npz")
+    per, means = cnmnet_b200.depth_metrics(_cuda(g["pred"]), _cuda(g["gt"].astype(np.float32)))
+    per = per.cpu().numpy()
+    want = g["metrics"]
+    assert np.array_equal(per[:, 0], want[:, 0])
+    ok = want[:, 0] > 0
+    assert np.allclose(per[ok, 1:7], want[ok, 1:7], rtol=2e-6)          # gt is fp32 on the device, fp64 in the fixture
+    assert np.abs(per[ok, 7:] - want[ok, 7:]).max() <= 2.0 / want[ok, 0].min()   # threshold counts: +-2 pixels
+    assert np.isnan(per[~ok, 1:]).all() and np.isnan(means["l1"])
+    rng = np.random.default_rng(9)
+    gt = synth.depth_maps(rng, 3, 192, 256).astype(np.float32)
+    pred = (gt * (1 + 0.05 * rng.standard_normal(gt.shape)) + 0.01).astype(np.float32)
+    per, means = cnmnet_b200.depth_metrics(_cuda(pred), _cuda(gt))
+    operi, omeans = omet.sequence_metrics(pred, gt)
+    for k in omet.NAMES[:6]:
+        assert abs(means[k] - omeans[k]) < 1e-6 * max(1.0, abs(omeans[k])), k
+    for k in omet.NAMES[6:]:
+        assert abs(means[k] - omeans[k]) < 1e-4, k
+
+
 def test_reciprocal_and_inverse_warp(golden_dir):
     lib, st = _lib.load(), _lib.stream_ptr()
     x = torch.rand(1000, device=dev()) + 0.1

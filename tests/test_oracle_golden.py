@@ -145,3 +145,19 @@ def test_fast_torch_ports_match_reference(golden_dir):
     n, p = nets.depth2normal_torch(torch.from_numpy(g["depth"]), torch.from_numpy(g["Kinv"]), 9)
     fin = np.isfinite(g["normals"]) & np.isfinite(n.numpy())
     assert fin.mean() > 0.99 and np.abs(n.numpy() - g["normals"])[fin].mean() < 1e-4
+
+
+def test_depth_metrics_oracle_matches_reference_functions(golden_dir):
+    """oracle/metrics.py vs the reference's own utils/metric.py functions called as eval.py:1030-1047 does
+    (fixture written by oracle/make_golden_metrics.py): clamping, invalid / non-finite ground truth, an empty image."""
+    from oracle import metrics as omet
+    g = np.load(os.path.join(golden_dir, "depth_metrics.npz"))
+    per, _ = omet.sequence_metrics(g["pred"], g["gt"])
+    for b, m in enumerate(per):
+        want = g["metrics"][b]
+        assert m["num_valid"] == int(want[0])
+        got = np.array([m[k] for k in omet.NAMES])
+        if want[0] == 0:
+            assert np.isnan(got).all() and np.isnan(want[1:]).all()
+        else:
+            assert np.allclose(got, want[1:], rtol=1e-12, atol=0)
