@@ -43,6 +43,10 @@ SIGNATURES = {
     "cnm_cost_volume": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _D, _D, _I, _I, _P]),
     "cnm_depth2normal": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cnm_intrinsics_inverse": (_I, [_P, _P, _I, _P]),
+    "cnm_loss_workspace_bytes": (_L, []),
+    "cnm_idepth_loss": (_I, [_P, _P, _P, _P, _P, _L, _I, _P]),
+    "cnm_idepth_loss_234": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "cnm_surface_normal_loss": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "cnm_depth_metrics_workspace_bytes": (_L, [_I, _I, _I]),
     "cnm_depth_metrics": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _P]),
     "cnm_plane_regularize_workspace_bytes": (_L, [_I, _I, _I, _I]),

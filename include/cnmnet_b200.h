@@ -119,6 +119,21 @@ int64_t cnm_depth_metrics_workspace_bytes(int B, int H, int W);
 int cnm_depth_metrics(const float* pred, const float* gt, double* out, void* workspace, int B, int H, int W,
                       float min_depth, float max_depth, void* stream);
 
+/* ---- training losses, forward values --------------------------------------------------
+ * replace depthnet/losses.py: IdepthLoss (:31-48) / IdepthwithProbLoss (:51-74) -> cnm_idepth_loss (prob NULL = plain
+ * L1; log_mode: |log10 pred - log10 gt|, times 10 when prob is given); IdepthLoss_234 (:7-28) ->
+ * cnm_idepth_loss_234 (gt [B,1,H,W], disp_k [B,1,H/2^(k-1),W/2^(k-1)]); surface_normal_loss (:77-122) ->
+ * cnm_surface_normal_loss (valid [B,1,H,W] uint8 or NULL, prob [B,1,H,W] or NULL).  out: device doubles --
+ * idepth {loss, masked pixel count}, 234 {loss}, normals {loss, mean angle in degrees, pixel count}.
+ * workspace: cnm_loss_workspace_bytes() bytes, 8B aligned.  No gradients: the package is inference-only.        */
+int64_t cnm_loss_workspace_bytes(void);
+int cnm_idepth_loss(const float* pred, const float* gt, const float* prob, double* out, void* workspace, int64_t n,
+                    int log_mode, void* stream);
+int cnm_idepth_loss_234(const float* disp2, const float* disp3, const float* disp4, const float* gt, double* out,
+                        void* workspace, int B, int H, int W, void* stream);
+int cnm_surface_normal_loss(const float* pred, const float* gt_normal, const uint8_t* valid, const float* prob, double* out,
+                            void* workspace, int B, int H, int W, void* stream);
+
 /* ---- idepth -> depth -------------------------------------------------------------------
  * replaces torch.div(1.0, idepth)  (eval.py:269,452,934).  n elements.                      */
 int cnm_reciprocal(const float* idepth, float* depth, int64_t n, void* stream);

@@ -312,6 +312,31 @@ def test_depth_metrics_golden_and_oracle(golden_dir):
         assert abs(means[k] - omeans[k]) < 1e-4, k
 
 
+def test_losses_golden_and_oracle(golden_dir):
+    """cnmnet_b200.depthnet.losses (forward values) vs the reference module's outputs (golden) and the fp64 oracle."""
+    from cnmnet_b200.depthnet import losses as L
+    from oracle import losses as olos
+    g = _g(golden_dir, "losses.npz")
+    t = {k: _cuda(g[k]) for k in ("gt", "pred", "prob", "disp2", "disp3", "disp4", "gt_pos", "n_pred", "n_gt", "valid")}
+    got = {"idepth": L.IdepthLoss()(t["pred"], t["gt"]), "idepth_log": L.IdepthLoss()(t["pred"], t["gt"], log=True),
+           "idepth_prob": L.IdepthwithProbLoss()(t["pred"], t["gt"], t["prob"]),
+           "idepth_prob_log": L.IdepthwithProbLoss()(t["pred"], t["gt"], t["prob"], log=True),
+           "idepth_234": L.IdepthLoss_234()([t["pred"], t["disp2"], t["disp3"], t["disp4"]], t["gt_pos"])}
+    got["normal"], got["normal_angle"] = L.surface_normal_loss(t["n_pred"], t["n_gt"], t["valid"])
+    got["normal_prob"], got["normal_prob_angle"] = L.surface_normal_loss(t["n_pred"], t["n_gt"], t["valid"], t["prob"])
+    for k, v in got.items():
+        assert abs(float(v) - float(g[k])) < 5e-6 * max(1.0, abs(float(g[k]))), (k, float(v), float(g[k]))
+    # a C4-sized case against the oracle
+    gen = torch.Generator().manual_seed(3)
+    gt = torch.rand(5, 1, 192, 256, generator=gen) * 2 + 0.05
+    pred = gt * (1 + 0.05 * torch.randn(5, 1, 192, 256, generator=gen))
+    prob = torch.rand(5, 1, 192, 256, generator=gen)
+    assert abs(float(L.IdepthwithProbLoss()(pred.to(dev()), gt.to(dev()), prob.to(dev()))) -
+               olos.idepth_prob_loss(pred, gt, prob)) < 1e-6
+    with pytest.raises(RuntimeError):
+        L.IdepthLoss()(pred, gt)                                      # CPU tensors: no CPU path
+
+
 def test_reciprocal_and_inverse_warp(golden_dir):
     lib, st = _lib.load(), _lib.stream_ptr()
     x = torch.rand(1000, device=dev()) + 0.1

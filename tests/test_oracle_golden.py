@@ -161,3 +161,19 @@ def test_depth_metrics_oracle_matches_reference_functions(golden_dir):
             assert np.isnan(got).all() and np.isnan(want[1:]).all()
         else:
             assert np.allclose(got, want[1:], rtol=1e-12, atol=0)
+
+
+def test_losses_oracle_matches_reference_module(golden_dir):
+    """oracle/losses.py vs the reference's own depthnet/losses.py (fixture written by oracle/make_golden_losses.py);
+    the reference evaluates in fp32, the oracle in fp64."""
+    from oracle import losses as olos
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    t = {k: torch.from_numpy(g[k]) for k in ("gt", "pred", "prob", "disp2", "disp3", "disp4", "gt_pos", "n_pred", "n_gt", "valid")}
+    got = {"idepth": olos.idepth_loss(t["pred"], t["gt"]), "idepth_log": olos.idepth_loss(t["pred"], t["gt"], log=True),
+           "idepth_prob": olos.idepth_prob_loss(t["pred"], t["gt"], t["prob"]),
+           "idepth_prob_log": olos.idepth_prob_loss(t["pred"], t["gt"], t["prob"], log=True),
+           "idepth_234": olos.idepth_loss_234([None, t["disp2"], t["disp3"], t["disp4"]], t["gt_pos"])}
+    got["normal"], got["normal_angle"] = olos.surface_normal_loss(t["n_pred"], t["n_gt"], t["valid"])
+    got["normal_prob"], got["normal_prob_angle"] = olos.surface_normal_loss(t["n_pred"], t["n_gt"], t["valid"], t["prob"])
+    for k, v in got.items():
+        assert abs(v - float(g[k])) < 2e-6 * max(1.0, abs(float(g[k]))), (k, v, float(g[k]))
