@@ -115,6 +115,8 @@ class CNMPipeline:
         events order the streams, the host only blocks when a result is handed out.  `after_step(st)`, if given, is
         enqueued on the lane's compute stream after every graph replay (bench.py gathers outputs across ranks
         there).  lanes=1 reproduces the strictly sequential schedule."""
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
         caller = torch.cuda.current_stream()
         states = stage_in = stage_out = host_out = comp = up = down = None
         ev = {}
@@ -153,6 +155,10 @@ class CNMPipeline:
                 # work the caller enqueued earlier (and results of an earlier call still in flight) comes first
                 for s_ in comp + [up, down]:
                     s_.wait_stream(caller)
+            if tuple(ref_img.shape) != tuple(stage_in[0][0].shape) or tuple(src_imgs.shape) != tuple(stage_in[0][1].shape):
+                raise ValueError("infer_stream: every batch of one stream must have the same shape (got %s / %s after %s / %s)"
+                                 % (tuple(ref_img.shape), tuple(src_imgs.shape), tuple(stage_in[0][0].shape),
+                                    tuple(stage_in[0][1].shape)))
             lane, b = i % lanes, i % nslots
             st, cs = states[lane], comp[lane]
             with torch.cuda.stream(up):  # upload batch i (after compute consumed this staging slot nslots batches ago)
