@@ -61,7 +61,7 @@ SIGNATURES = {
     "cnm_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "cnm_head3x3": (_I, [_P, _P, _F, _F, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cnm_head_partial": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "cnm_head_finish": (_I, [_P, _F, _F, _P, _P, _I, _I, _I, _P]),
+    "cnm_head_finish": (_I, [_P, _I, _F, _F, _P, _P, _I, _I, _I, _P]),
     "cnm_conv2d_tc": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
     "cnm_conv2d_simt": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
     "cnm_conv2d_halo": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P, _P]),

@@ -42,8 +42,8 @@ struct alignas(64) HaloParams {
   int mode;         // EPI_PLAIN / EPI_BF16X3 / EPI_F16F8: the split modes store two 128-byte rows per 64-column chunk
   float acc_scale;  // 2^-acc_exp
   const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
-  float* head_partial;   // [N, Ho, Wo, 12] per-pixel tap dot products
-  int Ho, Wo;
+  float* head_partial;   // [Cout/64 slices][N, Ho, Wo, 12] per-pixel tap dot products, one slice per 64-channel chunk
+  int Ho, Wo, cout;
 };
 
 template <int BN, bool TF32>
@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   const uint32_t off_b = (uint32_t)p.a_stages * p.slab_bytes;
   const uint32_t off_out = off_b + (uint32_t)p.b_stages * B_BYTES;
   const uint32_t off_bias = off_out + (uint32_t)p.out_stages * HL_TILE_BYTES;
-  const uint32_t off_head = off_bias + BN * 4;  // fused-head weights (BN == 64 only)
-  const uint32_t off_bar = off_head + (BN == 64 ? 9 * 64 * 4 : 0);
+  const uint32_t off_head = off_bias + BN * 4;  // fused-head weights of the N tile [9][BN]
+  const uint32_t off_bar = off_head + (p.head_partial ? 9 * BN * 4 : 0);
   const uint32_t bar0 = base + off_bar;
   auto fullA = [&](int s) { return bar0 + 8u * s; };
   auto emptyA = [&](int s) { return bar0 + 8u * (HL_MAX_A + s); };
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
   float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
   float* head_s = reinterpret_cast<float*>(base_ptr + off_head);
-  const bool fused_head = !TF32 && BN == 64 && p.head_partial != nullptr;
+  const bool fused_head = !TF32 && p.head_partial != nullptr;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -211,10 +211,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     int it = 0;
     int bias_tile = -1;
     uint32_t store_cnt = 0;
-    if (fused_head) {
-      for (int i = et; i < 9 * 64; i += 128) head_s[i] = __ldg(p.head_w + i);
-      epi_bar();
-    }
+
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % p.tiles_n;
       int m = tile / p.tiles_n;
@@ -227,6 +224,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
       if (bias_tile != nt) {
         epi_bar();
         for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
+        if (fused_head)
+          for (int i = et; i < 9 * BN; i += 128) head_s[i] = __ldg(p.head_w + (i / BN) * p.cout + nt * BN + i % BN);
         bias_tile = nt;
         epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
@@ -242,10 +241,13 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
           if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
           tmem_ld_wait();
           epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale);
-          if (!TF32 && BN == 64 && fused_head) {
+          if (!TF32 && fused_head) {
             const int px = x0 + (row & 15), py = y0 + 8 * half + (row >> 4);
-            if (px < p.Wo && py < p.Ho)
-              epi_head_partial(v, head_s, p.head_partial + (((size_t)n0 * p.Ho + py) * p.Wo + px) * HEAD_PARTIAL_STRIDE);
+            if (px < p.Wo && py < p.Ho) {
+              const size_t slice = (size_t)(nt * NUM_CHUNKS + ch) * p.tiles_b * p.Ho * p.Wo;  // one slice per 64-channel chunk
+              epi_head_partial(v, head_s + ch * 64, BN,
+                               p.head_partial + (slice + ((size_t)n0 * p.Ho + py) * p.Wo + px) * HEAD_PARTIAL_STRIDE);
+            }
           }
           for (int part = 0; part < (p.mode ? 2 : 1); ++part) {
             // BN >= 128: one staging tile (smem goes to deeper operand rings; the epilogue runs under the next tile's
@@ -347,7 +349,6 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
                 d->reserved, d->Cout);
     BN = d->reserved;
   }
-  if (d->head_partial) BN = 64;  // the fused head needs all 64 output channels of a pixel in one thread
   p.tiles_n = d->Cout / BN;
   p.groups = groups;
   p.bias = bias;
@@ -359,12 +360,12 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   p.acc_scale = ldexpf(1.0f, -d->acc_exp);
   p.head_w = d->head_w;
   p.head_partial = d->head_partial;
-  p.Ho = d->Ho; p.Wo = d->Wo;
+  p.Ho = d->Ho; p.Wo = d->Wo; p.cout = d->Cout;
   // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
   // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
   // lasts ntaps B tiles.
   p.out_stages = BN == 64 ? 2 : 1;
-  const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (BN == 64 ? 9 * 64 * 4 : 0) + 8 * (2 * HL_MAX_A + 2 * HL_MAX_B + 4) + 16;
+  const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (d->head_partial ? 9 * BN * 4 : 0) + 8 * (2 * HL_MAX_A + 2 * HL_MAX_B + 4) + 16;
   const int budget = 232448 - fixed;
   const int want_b = BN == 256 ? 4 : (BN == 128 ? 7 : 8);
   p.a_stages = (pmax >= 3 || BN == 256) ? 2 : (BN == 64 ? 4 : 3);

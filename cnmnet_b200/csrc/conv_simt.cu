@@ -177,8 +177,9 @@ int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* 
   CNM_REQUIRE(d->num_steps >= 1, CNM_ERR_INVALID_ARGUMENT, "%s: num_steps %d", fn, d->num_steps);
   CNM_REQUIRE((d->head_w == nullptr) == (d->head_partial == nullptr), CNM_ERR_INVALID_ARGUMENT,
               "%s: head_w and head_partial go together", fn);
-  CNM_REQUIRE(!d->head_partial || (d->Cout == 64 && d->dtype != CNM_TF32 && ((uintptr_t)d->head_partial & 15) == 0),
-              CNM_ERR_UNSUPPORTED_SHAPE, "%s: the fused head needs Cout == 64, a 2-byte dtype and a 16B-aligned buffer", fn);
+  CNM_REQUIRE(!d->head_partial || (d->dtype != CNM_TF32 && ((uintptr_t)d->head_partial & 15) == 0 &&
+                                   ((uintptr_t)d->head_w & 15) == 0),
+              CNM_ERR_UNSUPPORTED_SHAPE, "%s: the fused head needs a 2-byte dtype and 16B-aligned buffers", fn);
   const int ch = chunk_channels(d->dtype);
   CNM_REQUIRE(d->Cout % ch == 0 && d->c_out_total % ch == 0 && d->c_out_offset % ch == 0 &&
                   d->c_out_offset + phys_factor(d->dtype) * d->Cout <= d->c_out_total,

@@ -62,8 +62,9 @@ struct TcSmem {
   static constexpr int OUT_BYTES = 2 * TC_A_BYTES;  // double-buffered 128 x 128 B staging
   static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
   static constexpr int OFF_BIAS = OFF_OUT + OUT_BYTES;
-  static constexpr int OFF_HEAD = OFF_BIAS + BN * 4;                     // fused-head weights (BN == 64 only)
-  static constexpr int OFF_BAR = OFF_HEAD + (BN == 64 ? 9 * 64 * 4 : 0);
+  static constexpr int OFF_HEAD = OFF_BIAS + BN * 4;                     // fused-head weights of the N tile [9][BN]
+  static constexpr bool HEAD_IN_SMEM = BN == 64;                         // wider tiles fill shared memory: weights from L1
+  static constexpr int OFF_BAR = OFF_HEAD + (HEAD_IN_SMEM ? 9 * BN * 4 : 0);
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + slack for manual 1024 B alignment
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TMEM);
   float* bias_s = reinterpret_cast<float*>(base_ptr + L::OFF_BIAS);
   float* head_s = reinterpret_cast<float*>(base_ptr + L::OFF_HEAD);
-  const bool fused_head = !TF32 && BN == 64 && p.head_partial != nullptr;
+  const bool fused_head = !TF32 && p.head_partial != nullptr;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -205,10 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     int it = 0;
     uint32_t chunk_counter = 0;
     int bias_tile = -1;
-    if (fused_head) {
-      for (int i = et; i < 9 * 64; i += 128) head_s[i] = __ldg(p.head_w + i);
-      epi_bar();
-    }
+
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nt = (tile / p.ksplit) % p.tiles_n;
       int m = tile / (p.ksplit * p.tiles_n);
@@ -246,6 +244,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (bias_tile != nt) {
         epi_bar();  // previous tile's bias reads are done
         for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
+        if (fused_head && L::HEAD_IN_SMEM)
+          for (int i = et; i < 9 * BN; i += 128) head_s[i] = __ldg(p.head_w + (i / BN) * p.cout + nt * BN + i % BN);
         bias_tile = nt;
         epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
@@ -259,10 +259,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
         tmem_ld_wait();
         epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale);
-        if (!TF32 && BN == 64 && fused_head) {
+        if (!TF32 && fused_head) {
           const int px = x0 + row % p.TW, py = y0 + (row / p.TW) % p.TH, pn = n0 + row / (p.TW * p.TH);
-          if (px < p.Wo && py < p.Ho && pn < p.N)
-            epi_head_partial(v, head_s, p.head_partial + (((size_t)pn * p.Ho + py) * p.Wo + px) * HEAD_PARTIAL_STRIDE);
+          if (px < p.Wo && py < p.Ho && pn < p.N) {
+            const size_t slice = (size_t)(nt * NUM_CHUNKS + ch) * p.N * p.Ho * p.Wo;  // one slice per 64-channel chunk
+            float* dst = p.head_partial + (slice + ((size_t)pn * p.Ho + py) * p.Wo + px) * HEAD_PARTIAL_STRIDE;
+            if (L::HEAD_IN_SMEM) epi_head_partial(v, head_s + ch * 64, BN, dst);
+            else epi_head_partial(v, p.head_w + nt * BN + ch * 64, p.cout, dst);
+          }
         }
         for (int part = 0; part < (p.mode ? 2 : 1); ++part) {
           const uint32_t buf = chunk_counter & 1;
@@ -420,7 +424,6 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
                 d->reserved, d->Cout);
     BN = d->reserved;
   }
-  if (d->head_partial) BN = 64;  // the fused head needs all 64 output channels of a pixel in one thread
   p.tiles_n = d->Cout / BN;
   p.steps = steps;
   p.bias = bias;

@@ -434,9 +434,9 @@ __global__ void __launch_bounds__(256, 2) head3x3_kernel(const __grid_constant__
 }
 
 // second half of a head fused into the producing convolution's epilogue (tc_common.cuh: epi_head_partial)
-__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ partial, float bias, float scale,
-                                                          float* __restrict__ out, float* __restrict__ logits, int N,
-                                                          int H, int W) {
+__global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ partial, int nslices, float bias,
+                                                          float scale, float* __restrict__ out,
+                                                          float* __restrict__ logits, int N, int H, int W) {
   const size_t total = (size_t)N * H * W;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -447,8 +447,12 @@ __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restric
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       const int yy = y + r - 1, xx = x + s - 1;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-        acc += __ldg(partial + (i + (size_t)((r - 1) * W + (s - 1))) * HEAD_PARTIAL_STRIDE + 3 * r + s);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float* q = partial + (i + (size_t)((r - 1) * W + (s - 1))) * HEAD_PARTIAL_STRIDE + 3 * r + s;
+        float t = 0.0f;
+        for (int k = 0; k < nslices; ++k) t += __ldg(q + (size_t)k * total * HEAD_PARTIAL_STRIDE);  // fixed order
+        acc += t;
+      }
     }
   if (logits) logits[i] = acc;
   out[i] = scale / (1.0f + expf(-acc));
@@ -679,12 +683,13 @@ extern "C" int cnm_head_partial(const void* x, const float* w_tap_major, float* 
   return after_launch("cnm_head_partial");
 }
 
-extern "C" int cnm_head_finish(const float* partial, float bias, float scale, float* out, float* logits, int N, int H,
-                               int W, void* stream) {
-  CNM_REQUIRE(partial && out && N > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_head_finish: bad argument");
+extern "C" int cnm_head_finish(const float* partial, int nslices, float bias, float scale, float* out, float* logits, int N,
+                               int H, int W, void* stream) {
+  CNM_REQUIRE(partial && out && N > 0 && H > 0 && W > 0 && nslices >= 1 && nslices <= 64, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_head_finish: bad argument");
   const size_t total = (size_t)N * H * W;
-  head_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, bias, scale, out, logits, N,
-                                                                                       H, W);
+  head_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, nslices, bias, scale, out,
+                                                                                       logits, N, H, W);
   return after_launch("cnm_head_finish");
 }
 

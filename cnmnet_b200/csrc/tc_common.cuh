@@ -170,19 +170,21 @@ __device__ __forceinline__ void epi_store_row(const uint32_t* v, uint8_t* rowp, 
   }
 }
 
-// Fused 1-channel 3x3 head (desc.head_w, Cout == 64): the nine per-tap dot products of this pixel's finalised fp32
-// output vector with the head weights ws [9][64] (shared memory), written as 12 floats (9 used) to dst.  A finishing
-// kernel (cnm_head_finish) adds the nine neighbours' contributions, the bias and the sigmoid.
+// Fused 1-channel 3x3 head (desc.head_w): the nine per-tap dot products of one 64-channel chunk of this pixel's finalised
+// fp32 output vector with the head weights, written as 12 floats (9 used) to dst.  ws points at the chunk's first weight,
+// `stride` floats between taps (shared memory copy of the N tile, or the global [9][Cout] array).  Every 64-channel chunk
+// of the layer writes its own slice of the partial buffer; cnm_head_finish sums the slices in order, gathers the nine
+// neighbours' contributions, adds the bias and applies the sigmoid.
 constexpr int HEAD_PARTIAL_STRIDE = 12;
-__device__ __forceinline__ void epi_head_partial(const uint32_t* v, const float* ws, float* dst) {
-  float acc[12];
+__device__ __forceinline__ void epi_head_partial(const uint32_t* v, const float* __restrict__ ws, int stride, float* dst) {
+  float acc[9];
 #pragma unroll
-  for (int t = 0; t < 12; ++t) acc[t] = 0.0f;
+  for (int t = 0; t < 9; ++t) acc[t] = 0.0f;
 #pragma unroll
   for (int c = 0; c < 64; c += 4) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      const float4 w4 = *reinterpret_cast<const float4*>(ws + t * 64 + c);
+      const float4 w4 = *reinterpret_cast<const float4*>(ws + t * stride + c);
       acc[t] = fmaf(__uint_as_float(v[c]), w4.x, acc[t]);
       acc[t] = fmaf(__uint_as_float(v[c + 1]), w4.y, acc[t]);
       acc[t] = fmaf(__uint_as_float(v[c + 2]), w4.z, acc[t]);

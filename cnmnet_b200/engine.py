@@ -438,8 +438,8 @@ class ConvOp:
         self.select(best[0], best[1], best[2])
 
     def fuse_head(self, w_tap_major, partial):
-        """Fused 1-channel 3x3 head on this layer's output (cnm_conv_desc.head_w / head_partial); Cout must be 64."""
-        assert self.desc.Cout == 64 and self.dtype != CNM_TF32
+        """Fused 1-channel 3x3 head on this layer's output (cnm_conv_desc.head_w [9][Cout] / head_partial [Cout/64 slices])."""
+        assert self.dtype != CNM_TF32
         self._head = (w_tap_major, partial)
         self.desc.head_w, self.desc.head_partial = w_tap_major.data_ptr(), partial.data_ptr()
 
@@ -542,17 +542,19 @@ class _Plan:
         lib, dt = self.lib, self.dtype
         lp = logits.data_ptr() if logits is not None else None
         producer = [op for op in self.convs.values() if op.out is x]
-        if FUSE_HEADS and Cc == 64 and dt != CNM_TF32 and self.backend != "simt" and producer:
-            # 64-channel heads ride in the producing convolution's epilogue (nine per-tap dot products per pixel from
-            # the fp32 accumulators); what is left is a 3x3 gather of scalars + bias + sigmoid
+        if FUSE_HEADS and dt != CNM_TF32 and self.backend != "simt" and producer:
+            # the head rides in the producing convolution's epilogue: every 64-channel chunk of the fp32 accumulators
+            # leaves nine per-tap dot products per pixel in its own slice; what is left is a 3x3 gather of scalars
+            # (summing the Cc/64 slices in order) + bias + sigmoid
             op = producer[0]
+            S = Cc // 64
             # fresh: the producing conv (created earlier) writes it while reading inputs that may already be released
-            partial = self.buf(N, H, W, 12, dtype=torch.float32, fresh=True)
-            hw["w_tap_major"] = torch.zeros((9, 64), dtype=torch.float32, device=self.device)
+            partial = self.buf(S * N, H, W, 12, dtype=torch.float32, fresh=True)
+            hw["w_tap_major"] = torch.zeros((9, Cc), dtype=torch.float32, device=self.device)
             hw["partial"] = partial
             op.fuse_head(hw["w_tap_major"], partial)
             self.ops.append(lambda s: _lib.check(
-                lib.cnm_head_finish(partial.data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s), name))
+                lib.cnm_head_finish(partial.data_ptr(), S, hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s), name))
             self.release(partial)
             return out, logits
         if FUSE_HEADS:
@@ -564,7 +566,7 @@ class _Plan:
             def two_pass(s):
                 _lib.check(lib.cnm_head_partial(x.data_ptr(), hw["w_tap_major"].data_ptr(), partial.data_ptr(), N, H, W, Cc,
                                                 dt, s), name)
-                _lib.check(lib.cnm_head_finish(partial.data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s),
+                _lib.check(lib.cnm_head_finish(partial.data_ptr(), 1, hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s),
                            name)
 
             self.ops.append(two_pass)

@@ -187,10 +187,11 @@ int cnm_head3x3(const void* x, const float* w, float bias, float scale, float* o
  * convolution's epilogue (cnm_conv_desc.head_partial).  cnm_head_finish gathers the 3x3 neighbourhood.            */
 int cnm_head_partial(const void* x, const float* w_tap_major, float* partial, int N, int H, int W, int C, int dtype,
                      void* stream);
-/* second half of a fused head (cnm_conv_desc.head_partial): out(y,x) = scale * sigmoid(bias + sum over the 3x3
- * neighbourhood of partial[y+r-1][x+s-1][3r+s]), zero outside the image; logits (may be NULL) gets the pre-sigmoid sum */
-int cnm_head_finish(const float* partial, float bias, float scale, float* out, float* logits, int N, int H, int W,
-                    void* stream);
+/* second half of a head: out(y,x) = scale * sigmoid(bias + sum over the 3x3 neighbourhood of
+ * sum_k partial[k][y+r-1][x+s-1][3r+s]), zero outside the image; partial = nslices stacked [N,H,W,12] tables (1 from
+ * cnm_head_partial, Cout/64 from a fused head); logits (may be NULL) gets the pre-sigmoid sum                         */
+int cnm_head_finish(const float* partial, int nslices, float bias, float scale, float* out, float* logits, int N, int H,
+                    int W, void* stream);
 
 /* ---- convolution as implicit GEMM --------------------------------------------------------
  * replaces nn.Conv2d + BatchNorm2d(eval) + ReLU and the torch.cat of its inputs
@@ -229,11 +230,11 @@ typedef struct cnm_conv_desc {
                        CTAs (layers with fewer tiles than SMs); partial accumulators go through splitk_ws and a second
                        kernel sums them in a fixed order.  0 / 1 = off. */
   int32_t reserved2[2];
-  /* Optional fused 1-channel 3x3 head on this layer's output (depth_layer, depthnet/depthNet_model.py:82-84), for
-   * Cout == 64 and the 2-byte dtypes (tensor-core kernels only): head_w = [9][64] fp32 tap-major weights (device),
-   * head_partial = [N, Ho, Wo, 12] fp32 (device, 16B aligned) receiving, per pixel, the nine per-tap dot products of
-   * the fp32 output vector (entries 9..11 are zero).  cnm_head_finish() turns them into the head's output.  Both
-   * NULL = no fused head.                                                                                          */
+  /* Optional fused 1-channel 3x3 head on this layer's output (depth_layer, depthnet/depthNet_model.py:82-84), for the
+   * 2-byte dtypes (tensor-core kernels only): head_w = [9][Cout] fp32 tap-major weights (device, 16B aligned),
+   * head_partial = [Cout/64][N, Ho, Wo, 12] fp32 (device, 16B aligned): every 64-channel chunk of the output writes,
+   * per pixel, the nine per-tap dot products of its part of the fp32 output vector into its own slice (entries 9..11
+   * are zero).  cnm_head_finish(nslices = Cout/64) turns them into the head's output.  Both NULL = no fused head.   */
   const float* head_w;
   float* head_partial;
   float* splitk_ws; /* [ksplit][N*Ho*Wo][Cout] fp32 workspace (device, 16B aligned) when ksplit > 1, else NULL */

@@ -144,28 +144,34 @@ def test_f16f8_accuracy_class(backend):
 
 
 @pytest.mark.parametrize("dtype", [_lib.CNM_BF16, _lib.CNM_BF16X3, _lib.CNM_F16F8])
-@pytest.mark.parametrize("backend", ["tc", "halo", "halo2"])
-def test_fused_head_matches_separate_head(backend, dtype):
+@pytest.mark.parametrize("backend,cout,bn", [("tc", 64, 0), ("halo", 64, 0), ("halo2", 64, 0), ("halo2", 128, 128),
+                                             ("halo", 256, 128), ("halo2", 256, 256), ("tc", 256, 128), ("tc", 512, 256),
+                                             ("tc", 128, 64)])
+def test_fused_head_matches_separate_head(backend, cout, bn, dtype):
     """cnm_conv_desc.head_w / head_partial + cnm_head_finish: the 1-channel 3x3 head computed from the fp32 accumulators in
-    the convolution epilogue equals conv3x3(+bias) -> scale * sigmoid on the (unrounded) layer output; partial tiles."""
+    the convolution epilogue (one partial slice per 64-channel chunk, any output-channel tile) equals conv3x3(+bias) ->
+    scale * sigmoid on the (unrounded) layer output; partial tiles."""
     N, H, W, cin, k = 2, 24, 40, 64, 3
-    g = torch.Generator().manual_seed(5)
+    g = torch.Generator().manual_seed(5 + cout)
     x = torch.randn(N, cin, H, W, generator=g)
-    w = torch.randn(64, cin, k, k, generator=g) / np.sqrt(cin * k * k)
-    b = torch.randn(64, generator=g)
-    hw = torch.randn(1, 64, 3, 3, generator=g) * 0.05
+    w = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g)
+    hw = torch.randn(1, cout, 3, 3, generator=g) * 0.05
     act = to_act(x, dtype)
-    op = engine.ConvOp("t", [engine.act_src(act, 0, phys=engine.phys_factor(dtype))], k, 1, 64, N, H, W, dtype, dev(), True,
+    op = engine.ConvOp("t", [engine.act_src(act, 0, phys=engine.phys_factor(dtype))], k, 1, cout, N, H, W, dtype, dev(), True,
                        backend=backend)
-    wt = hw[0].permute(1, 2, 0).reshape(9, 64).contiguous().to(dev())
-    partial = torch.full((N, H, W, 12), float("nan"), device=dev())
+    op.tunable = False
+    op.select(backend, bn)
+    wt = hw[0].permute(1, 2, 0).reshape(9, cout).contiguous().to(dev())
+    S = cout // 64
+    partial = torch.full((S * N, H, W, 12), float("nan"), device=dev())
     op.fuse_head(wt, partial)
     op.load(w, b)
     op(_lib.stream_ptr())
     out = torch.empty((N, 1, H, W), device=dev())
     logits = torch.empty((N, 1, H, W), device=dev())
     lib = _lib.load()
-    _lib.check(lib.cnm_head_finish(partial.data_ptr(), 0.25, 3.0, out.data_ptr(), logits.data_ptr(), N, H, W,
+    _lib.check(lib.cnm_head_finish(partial.data_ptr(), S, 0.25, 3.0, out.data_ptr(), logits.data_ptr(), N, H, W,
                                    _lib.stream_ptr()))
     torch.cuda.synchronize()
     want_act = oracle_conv(dtype, [x], w, b, k, 1)                         # fp32 layer output before storage rounding
@@ -173,7 +179,7 @@ def test_fused_head_matches_separate_head(backend, dtype):
     wl = F.conv2d(want_act.double(), hw.double(), torch.tensor([0.25], dtype=torch.float64), padding=1)
     assert not torch.isnan(partial).any()
     assert (logits.cpu() - wl.float()).abs().max() < 2e-5 * max(1.0, wl.abs().max().item())
-    assert (out.cpu() - 3.0 * torch.sigmoid(wl).float()).abs().max() < 1e-5
+    assert (out.cpu() - 3.0 * torch.sigmoid(wl).float()).abs().max() < 3e-5   # fp32 sums over up to 8 slices of 576 terms
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

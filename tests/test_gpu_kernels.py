@@ -242,7 +242,7 @@ def test_upsample_head_packers(dtype):
     wt = w[0].permute(1, 2, 0).reshape(9, 64).contiguous().to(dev())
     out2, logit2 = torch.empty_like(out), torch.empty_like(logit)
     _lib.check(lib.cnm_head_partial(xa.data_ptr(), wt.data_ptr(), part.data_ptr(), 2, 6, 10, 64, dtype, st))
-    _lib.check(lib.cnm_head_finish(part.data_ptr(), 0.25, 3.0, out2.data_ptr(), logit2.data_ptr(), 2, 6, 10, st))
+    _lib.check(lib.cnm_head_finish(part.data_ptr(), 1, 0.25, 3.0, out2.data_ptr(), logit2.data_ptr(), 2, 6, 10, st))
     assert (logit2.cpu() - wl.float()).abs().max() < 1e-4 and (out2.cpu() - out.cpu()).abs().max() < 1e-5
     # disparity taps: nearest x2 then 3x3 taps
     disp = torch.rand(2, 1, 6, 10, generator=g)
@@ -283,7 +283,7 @@ def test_wide_heads_both_forms(dtype, C, H, W):
     part = torch.empty((3, H, W, 12), device=dev())
     out2, logit2 = torch.empty_like(out), torch.empty_like(logit)
     _lib.check(lib.cnm_head_partial(xa.data_ptr(), wv.data_ptr(), part.data_ptr(), 3, H, W, C, dtype, st))
-    _lib.check(lib.cnm_head_finish(part.data_ptr(), -0.1, 2.0, out2.data_ptr(), logit2.data_ptr(), 3, H, W, st))
+    _lib.check(lib.cnm_head_finish(part.data_ptr(), 1, -0.1, 2.0, out2.data_ptr(), logit2.data_ptr(), 3, H, W, st))
     for lg, o in ((logit, out), (logit2, out2)):
         assert (lg.cpu() - wl).abs().max() < 2e-4
         assert (o.cpu() - 2.0 * torch.sigmoid(wl)).abs().max() < 5e-5
