@@ -380,6 +380,9 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": B * world, "views": V + 1, "planes": D, "k_size": K_SIZE,
                    "weights": "reference random init, torch.manual_seed(0)", "parallelism": "dp%d" % world,
                    "l2": "flushed between timed steps (256 MiB memset, outside the event pair)",
+                   "timing": "value / ms_per_step: K isolated steps, one batch in flight, device events per step; e2e: the "
+                             "streaming API with host buffers and %d batch(es) in flight (lanes), which is why it can exceed "
+                             "value; two_lane_resident_ms_per_step is the same overlap with resident inputs" % lanes,
                    "cuda_graph": True, "precision_note": PRECISION_NOTES[args.precision]},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
