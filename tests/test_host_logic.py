@@ -402,3 +402,30 @@ def test_correction_steps_come_first():
             assert k == len(groups) // 2 and all(c0 % 128 == 64 for (_, c0, _, _) in groups[:k])   # fp8 rows = first half
     steps, cols = engine.make_steps([engine.act_src(torch.empty(1, 8, 8, 128), 0)], 3, 1, 64)
     assert [c[2:4] for c in cols[:2]] == [(0, 0), (0, 0)] and len(cols) == 18   # unchanged: tap-major, chunk inner
+
+
+def test_plan_arena_recycles_released_buffers(monkeypatch):
+    """_Plan.buf / release: a released buffer backs the next request that fits (best fit), `fresh` never reuses, live
+    buffers never alias, PLAN_REUSE=0 disables recycling."""
+    plan = object.__new__(engine._Plan)
+    plan.dtype, plan.device, plan.pf = _lib.CNM_F16F8, torch.device("cpu"), 2
+    plan._storage, plan._free, plan.bytes_allocated = {}, [], 0
+    a = plan.buf(2, 8, 8, 64)                       # act tensor: 2 physical channels per logical one
+    assert a.shape == (2, 8, 8, 128) and a.dtype == torch.float16 and a.data_ptr() % 128 == 0
+    b = plan.buf(2, 4, 4, 64)
+    first = plan.bytes_allocated
+    assert a.data_ptr() != b.data_ptr()
+    plan.release(a)
+    c = plan.buf(1, 8, 8, 64)                       # fits into a's storage
+    assert c.data_ptr() == a.data_ptr() and plan.bytes_allocated == first
+    d = plan.buf(1, 8, 8, 64, fresh=True)           # never recycled
+    assert d.data_ptr() not in (a.data_ptr(), b.data_ptr()) and plan.bytes_allocated > first
+    plan.release(b, c)
+    e = plan.buf(2, 2, 2, 12, dtype=torch.float32)  # best fit: the smaller free block (b's)
+    assert e.data_ptr() == b.data_ptr() and e.dtype == torch.float32
+    plan.release(e)
+    plan.release(e)                                 # double release is harmless
+    assert len(plan._free) == 2
+    monkeypatch.setattr(engine, "PLAN_REUSE", False)
+    f = plan.buf(1, 2, 2, 64)
+    assert f.data_ptr() not in (a.data_ptr(), b.data_ptr())
