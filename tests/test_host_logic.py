@@ -429,3 +429,29 @@ def test_plan_arena_recycles_released_buffers(monkeypatch):
     monkeypatch.setattr(engine, "PLAN_REUSE", False)
     f = plan.buf(1, 2, 2, 64)
     assert f.data_ptr() not in (a.data_ptr(), b.data_ptr())
+
+
+@pytest.mark.parametrize("halo", [False, True])
+def test_128_plane_conv1_program(halo):
+    """depthNet(planes=128): conv1.0 = 7x7 over cat(image [3], cost volume [128]) -- four cost chunks + the row-tap side
+    tensor of the image, as a per-tap step list and as row-halo groups."""
+    torch.manual_seed(128)
+    ch, N, H, W, k, D = 32, 1, 9, 10, 7, 128
+    img, cost = torch.randn(N, 3, H, W), torch.randn(N, D, H, W)
+    wt, b = torch.randn(8, 3 + D, k, k) / 20, torch.randn(8)
+    want = nhwc(F.conv2d(torch.cat((img, cost), 1).double(), engine.round_tf32(wt).double(), b.double(), padding=3))
+    taps = torch.zeros(N, H, W, ch)
+    pi = F.pad(img, (3, 3, 0, 0))
+    for s in range(k):
+        for c in range(3):
+            taps[..., s * 3 + c] = pi[:, c, :, s:s + W]
+    srcs = [engine.act_src(nhwc(cost), 3), engine.Src(taps, "rowtaps", 0, ch, 0, 3)]
+    if halo:
+        groups, cols, info = engine.make_groups(srcs, k, ch)
+        steps = [(m // 4, 0, dx, t - info[m][0], c0) for (m, c0, dx, nt) in groups for t in range(nt)]
+    else:
+        steps, cols = engine.make_steps(srcs, k, 1, ch)
+    assert len(steps) == len(cols) == 49 * (D // ch) + 7
+    wp = engine.pack_weights(wt, cols, ch, _lib.CNM_TF32)
+    got = emulate_steps([s_.buf for s_ in srcs], steps, wp, b, 1, ch, False)
+    assert torch.allclose(got, want, atol=1e-9)
