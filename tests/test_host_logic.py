@@ -411,7 +411,7 @@ def test_plan_arena_recycles_released_buffers(monkeypatch):
     plan.dtype, plan.device, plan.pf = _lib.CNM_F16F8, torch.device("cpu"), 2
     plan._storage, plan._free, plan.bytes_allocated = {}, [], 0
     a = plan.buf(2, 8, 8, 64)                       # act tensor: 2 physical channels per logical one
-    assert a.shape == (2, 8, 8, 128) and a.dtype == torch.float16 and a.data_ptr() % 128 == 0
+    assert a.shape == (2, 8, 8, 128) and a.dtype == torch.float16   # (CUDA allocations are 512-byte aligned; CPU ones only 64)
     b = plan.buf(2, 4, 4, 64)
     first = plan.bytes_allocated
     assert a.data_ptr() != b.data_ptr()
