@@ -127,79 +127,83 @@ class CNMPipeline:
             ev[(name, i)] = torch.cuda.Event()
             return ev[(name, i)]
 
-        for i, (ref_img, src_imgs, ref_cam, src_cams) in enumerate(batches):
-            if states is None:
-                B, V = src_imgs.shape[:2]
-                H, W = ref_img.shape[2:]
-                dev = next(self.depth_network.parameters()).device
-                states = [self._prepare(B, V, H, W, dev, lane) for lane in range(lanes)]
-                st0 = states[0]
-                key = ("stream_bufs", lanes)
-                if key not in st0:
-                    # staging keeps the caller's [B,V,...] layout so the uploads are plain contiguous DMA transfers; the
-                    # view-major transpose happens in the device-side copy into the static buffers.  Allocated once per
-                    # shape: pinning host memory costs milliseconds.  Separate copy streams: an upload never queues
-                    # behind a download.
-                    f32 = dict(dtype=torch.float32, device=dev)
-                    st0[key] = (
-                        [[torch.empty((B, 3, H, W), **f32), torch.empty((B, V, 3, H, W), **f32),
-                          torch.empty((B, 2, 4, 4), **f32), torch.empty((B, V, 2, 4, 4), **f32)] for _ in range(nslots)],
-                        [[torch.empty_like(st0[k]) for k in ("depth", "normal", "prob")] for _ in range(nslots)],
-                        [[torch.empty(st0[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
-                         for _ in range(nslots)],
-                        [torch.cuda.Stream() for _ in range(lanes)], torch.cuda.Stream(), torch.cuda.Stream())
-                stage_in, stage_out, host_out, comp, up, down = st0[key]
-                for st in states:
-                    if self.use_graph and st["graph"] is None:
-                        self.step(st)  # capture outside the pipelined region
-                # work the caller enqueued earlier (and results of an earlier call still in flight) comes first
-                for s_ in comp + [up, down]:
-                    s_.wait_stream(caller)
-            if tuple(ref_img.shape) != tuple(stage_in[0][0].shape) or tuple(src_imgs.shape) != tuple(stage_in[0][1].shape):
-                raise ValueError("infer_stream: every batch of one stream must have the same shape (got %s / %s after %s / %s)"
-                                 % (tuple(ref_img.shape), tuple(src_imgs.shape), tuple(stage_in[0][0].shape),
-                                    tuple(stage_in[0][1].shape)))
-            lane, b = i % lanes, i % nslots
-            st, cs = states[lane], comp[lane]
-            with torch.cuda.stream(up):  # upload batch i (after compute consumed this staging slot nslots batches ago)
-                if ("in_free", i - nslots) in ev:
-                    up.wait_event(ev.pop(("in_free", i - nslots)))
-                for dst, src in zip(stage_in[b], (ref_img, src_imgs, ref_cam, src_cams)):
-                    dst.copy_(src, non_blocking=True)
-                new_event("in", i).record(up)
-            with torch.cuda.stream(cs):
-                cs.wait_event(ev.pop(("in", i)))
-                st["ref"].copy_(stage_in[b][0], non_blocking=True)
-                st["src"].copy_(stage_in[b][1].transpose(0, 1), non_blocking=True)
-                st["ref_cam"].copy_(stage_in[b][2], non_blocking=True)
-                st["src_cam"].copy_(stage_in[b][3].transpose(0, 1), non_blocking=True)
-                new_event("in_free", i).record(cs)
-                self.step(st)
-                if after_step is not None:
-                    after_step(st)
-                if ("out_free", i - nslots) in ev:
-                    cs.wait_event(ev.pop(("out_free", i - nslots)))
-                for dst, k in zip(stage_out[b], ("depth", "normal", "prob")):
-                    dst.copy_(st[k], non_blocking=True)
-                new_event("out", i).record(cs)
-            with torch.cuda.stream(down):  # download batch i while later batches compute
-                down.wait_event(ev.pop(("out", i)))
-                for dst, src in zip(host_out[b], stage_out[b]):
-                    dst.copy_(src, non_blocking=True)
-                new_event("out_free", i).record(down)
-                done = torch.cuda.Event()
-                done.record(down)
-            pending.append((done, host_out[b]))
-            if len(pending) > lanes:  # hand out the oldest batch; `lanes` batches stay in flight
-                d, outs = pending.pop(0)
+        try:
+            for i, (ref_img, src_imgs, ref_cam, src_cams) in enumerate(batches):
+                if states is None:
+                    B, V = src_imgs.shape[:2]
+                    H, W = ref_img.shape[2:]
+                    dev = next(self.depth_network.parameters()).device
+                    states = [self._prepare(B, V, H, W, dev, lane) for lane in range(lanes)]
+                    st0 = states[0]
+                    key = ("stream_bufs", lanes)
+                    if key not in st0:
+                        # staging keeps the caller's [B,V,...] layout so the uploads are plain contiguous DMA transfers; the
+                        # view-major transpose happens in the device-side copy into the static buffers.  Allocated once per
+                        # shape: pinning host memory costs milliseconds.  Separate copy streams: an upload never queues
+                        # behind a download.
+                        f32 = dict(dtype=torch.float32, device=dev)
+                        st0[key] = (
+                            [[torch.empty((B, 3, H, W), **f32), torch.empty((B, V, 3, H, W), **f32),
+                              torch.empty((B, 2, 4, 4), **f32), torch.empty((B, V, 2, 4, 4), **f32)] for _ in range(nslots)],
+                            [[torch.empty_like(st0[k]) for k in ("depth", "normal", "prob")] for _ in range(nslots)],
+                            [[torch.empty(st0[k].shape, dtype=torch.float32).pin_memory() for k in ("depth", "normal", "prob")]
+                             for _ in range(nslots)],
+                            [torch.cuda.Stream() for _ in range(lanes)], torch.cuda.Stream(), torch.cuda.Stream())
+                    stage_in, stage_out, host_out, comp, up, down = st0[key]
+                    for st in states:
+                        if self.use_graph and st["graph"] is None:
+                            self.step(st)  # capture outside the pipelined region
+                    # work the caller enqueued earlier (and results of an earlier call still in flight) comes first
+                    for s_ in comp + [up, down]:
+                        s_.wait_stream(caller)
+                if tuple(ref_img.shape) != tuple(stage_in[0][0].shape) or tuple(src_imgs.shape) != tuple(stage_in[0][1].shape):
+                    raise ValueError("infer_stream: every batch of one stream must have the same shape (got %s / %s after %s / %s)"
+                                     % (tuple(ref_img.shape), tuple(src_imgs.shape), tuple(stage_in[0][0].shape),
+                                        tuple(stage_in[0][1].shape)))
+                lane, b = i % lanes, i % nslots
+                st, cs = states[lane], comp[lane]
+                with torch.cuda.stream(up):  # upload batch i (after compute consumed this staging slot nslots batches ago)
+                    if ("in_free", i - nslots) in ev:
+                        up.wait_event(ev.pop(("in_free", i - nslots)))
+                    for dst, src in zip(stage_in[b], (ref_img, src_imgs, ref_cam, src_cams)):
+                        dst.copy_(src, non_blocking=True)
+                    new_event("in", i).record(up)
+                with torch.cuda.stream(cs):
+                    cs.wait_event(ev.pop(("in", i)))
+                    st["ref"].copy_(stage_in[b][0], non_blocking=True)
+                    st["src"].copy_(stage_in[b][1].transpose(0, 1), non_blocking=True)
+                    st["ref_cam"].copy_(stage_in[b][2], non_blocking=True)
+                    st["src_cam"].copy_(stage_in[b][3].transpose(0, 1), non_blocking=True)
+                    new_event("in_free", i).record(cs)
+                    self.step(st)
+                    if after_step is not None:
+                        after_step(st)
+                    if ("out_free", i - nslots) in ev:
+                        cs.wait_event(ev.pop(("out_free", i - nslots)))
+                    for dst, k in zip(stage_out[b], ("depth", "normal", "prob")):
+                        dst.copy_(st[k], non_blocking=True)
+                    new_event("out", i).record(cs)
+                with torch.cuda.stream(down):  # download batch i while later batches compute
+                    down.wait_event(ev.pop(("out", i)))
+                    for dst, src in zip(host_out[b], stage_out[b]):
+                        dst.copy_(src, non_blocking=True)
+                    new_event("out_free", i).record(down)
+                    done = torch.cuda.Event()
+                    done.record(down)
+                pending.append((done, host_out[b]))
+                if len(pending) > lanes:  # hand out the oldest batch; `lanes` batches stay in flight
+                    d, outs = pending.pop(0)
+                    d.synchronize()
+                    yield tuple(outs)
+            for d, outs in pending:
                 d.synchronize()
                 yield tuple(outs)
-        for d, outs in pending:
-            d.synchronize()
-            yield tuple(outs)
-        if comp is not None:
-            for s_ in comp + [up, down]:
-                caller.wait_stream(s_)
+        finally:
+            # also when the consumer stops early (generator closed): later work on the caller's stream must not overtake
+            # what is still running on the lane / copy streams
+            if comp is not None:
+                for s_ in comp + [up, down]:
+                    caller.wait_stream(s_)
 
     def __call__(self, ref_img, src_imgs, ref_cam, src_cams):
         if ref_img.dim() != 4 or src_imgs.dim() != 5 or src_imgs.shape[0] != ref_img.shape[0]:

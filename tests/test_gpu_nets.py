@@ -234,6 +234,13 @@ def test_infer_stream_matches_single_calls():
         for g, w in zip(got, want):
             for a, b in zip(g, w):
                 assert torch.equal(a, b)
+    # a consumer that stops early: the generator's cleanup joins the lane streams, a direct call afterwards is correct
+    for k, outs in enumerate(pipe.infer_stream(iter(batches))):
+        if k == 1:
+            break
+    again = tuple(o.cpu() for o in pipe(*[t.to(dev()) for t in batches[3]]))
+    for a, b in zip(again, want[3]):
+        assert torch.equal(a, b)
 
 
 def test_video_stream_matches_single_calls():
