@@ -41,6 +41,7 @@ SIGNATURES = {
     "cnm_packed_source_bytes": (_L, [_I, _I, _I]),
     "cnm_pack_source": (_I, [_P, _P, _I, _I, _I, _P]),
     "cnm_cost_volume": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _D, _D, _I, _I, _P]),
+    "cnm_plane_sweep": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _D, _D, _I, _I, _P]),
     "cnm_depth2normal": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cnm_intrinsics_inverse": (_I, [_P, _P, _I, _P]),
     "cnm_loss_workspace_bytes": (_L, []),

@@ -32,6 +32,22 @@ inline int after_launch(const char* what) {
   return CNM_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: callers keep one `static DynSmemLimit` per kernel
+// instantiation and raise the limit on whichever device is current (a process may drive several GPUs).
+struct DynSmemLimit {
+  int set[64] = {0};
+  template <typename K>
+  cudaError_t ensure(K kernel, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& cur = set[dev & 63];
+    if ((int)smem <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) cur = (int)smem;
+    return e;
+  }
+};
+
 #define CNM_REQUIRE(cond, code, ...) \
   do {                               \
     if (!(cond)) return ::cnm::fail(code, __VA_ARGS__); \

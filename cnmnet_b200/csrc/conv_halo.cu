@@ -287,12 +287,9 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
 
 template <int BN, bool TF32>
 static int launch_halo(const HaloParams& p, int grid, int smem, cudaStream_t s) {
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_halo: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  static DynSmemLimit limit;
+  cudaError_t e = limit.ensure(conv_halo_kernel<BN, TF32>, smem);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_halo: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
   conv_halo_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
   return after_launch("cnm_conv2d_halo");
 }

@@ -337,12 +337,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
 
 template <int BN, bool TF32>
 static int launch_halo2(const Halo2Params& p, int grid, int smem, cudaStream_t s) {
-  static int configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_halo2: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  static DynSmemLimit limit;
+  cudaError_t e = limit.ensure(conv_halo2_kernel<BN, TF32>, smem);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_halo2: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
   conv_halo2_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
   return after_launch("cnm_conv2d_halo2");
 }

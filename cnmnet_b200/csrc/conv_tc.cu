@@ -374,13 +374,9 @@ static int next_pow2(int v) {
 template <int BN, int STAGES, bool TF32>
 static int launch_tc(const TcParams& p, int grid, cudaStream_t s) {
   using L = TcSmem<BN, STAGES, TF32>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL);
-    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static DynSmemLimit limit;
+  cudaError_t e = limit.ensure(conv_tc_kernel<BN, STAGES, TF32>, L::TOTAL);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
   conv_tc_kernel<BN, STAGES, TF32><<<grid, TC_THREADS, L::TOTAL, s>>>(p);
   return after_launch("cnm_conv2d_tc");
 }

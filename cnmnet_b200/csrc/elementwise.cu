@@ -522,12 +522,9 @@ static int launch_head_partial(const T* x, const float* w, float* partial, size_
 
 template <typename T, int LPP>
 static int launch_head_lpp(const HeadParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(head3x3_kernel<T, LPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_head3x3: smem attribute: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static DynSmemLimit limit;
+  cudaError_t e = limit.ensure(head3x3_kernel<T, LPP>, smem);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_head3x3: smem attribute: %s", cudaGetErrorString(e));
   head3x3_kernel<T, LPP><<<grid, 256, smem, s>>>(p);
   return CNM_OK;
 }

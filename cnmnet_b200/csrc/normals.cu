@@ -295,7 +295,12 @@ __global__ void cnm_loss_kernel(const int32_t* __restrict__ planes_num, CnmWorks
     double acc = 0.0;
     for (int k = 0; k < NB; ++k) acc += ws.lossp[(size_t)b * NB + k];
     const int np = min(planes_num[b], P);
-    for (int i = 0; i < np; ++i) acc += HW - (double)ws.cnt[(size_t)b * P + i];
+    for (int i = 0; i < np; ++i) {
+      const double cnt = (double)ws.cnt[(size_t)b * P + i];
+      // an empty mask below planes_num: the reference's mean is 0/0 = NaN, cosine_similarity is NaN at every pixel
+      // and the whole loss becomes NaN (depth_util.py:222-231)
+      acc += cnt > 0.0 ? HW - cnt : __longlong_as_double(0x7ff8000000000000LL);
+    }
     total += acc / HW;
   }
   *loss = total;
@@ -384,12 +389,9 @@ extern "C" int cnm_depth2normal(const float* depth, const float* Kinv, float* no
   CNM_REQUIRE(B <= 65535, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_depth2normal: B too large");
   const int r = k_size / 2;
   const size_t smem = ((size_t)(NT_Y + 2 * r) * (NT_X + 2 * r) * 3 + (size_t)(NT_Y + 2 * r) * NT_X * 9) * sizeof(double);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(depth2normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_depth2normal: smem attr: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static DynSmemLimit limit;
+  cudaError_t e = limit.ensure(depth2normal_kernel, smem);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_depth2normal: smem attr: %s", cudaGetErrorString(e));
   dim3 grid((W + NT_X - 1) / NT_X, (H + NT_Y - 1) / NT_Y, B), block(NT_X, NT_Y);
   depth2normal_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(depth, Kinv, normals, points, H, W, k_size);
   return after_launch("cnm_depth2normal");

@@ -71,6 +71,9 @@ class _KernelNet(nn.Module):
             with torch.no_grad():
                 plan.load_state({k: v.detach() for k, v in self.state_dict().items()})
             self._packed[key] = ver
+            # some packed values are launch ARGUMENTS (head bias, the f16f8 accumulator scale): a CUDA graph captured
+            # before this point has the old ones baked in -- holders of a graph compare this counter (CNMPipeline)
+            plan.weights_epoch = getattr(plan, "weights_epoch", 0) + 1
         return plan
 
     def load_reference_checkpoint(self, state_dict):
@@ -95,13 +98,14 @@ def _check_image_pair(left_image, right_image):
 class depthNet(_KernelNet):
     """Reference: depthnet/depthNet_model.py:124 -- ``depthNet(idepth_scale=3)``.
 
-    Extra keyword arguments (not in the reference): ``precision`` 'bf16' | 'tf32' | 'bf16x3' | 'f16f8' selects the
+    Extra keyword arguments (not in the reference): ``precision`` 'f16f8' (default: the mode that meets the 1e-3
+    final-depth tolerance at the best speed) | 'bf16x3' | 'tf32' | 'bf16' (speed mode, misses the tolerance) selects the
     tensor-core operand type, ``backend`` 'tc' (tcgen05, product) | 'simt' (CUDA-core validation twin), ``planes`` the
     number of inverse-depth hypotheses.  The reference hard-codes 64 planes (getVolume loops ``range(64)``,
     conv1 takes 3 + 64 channels, depthNet_model.py:129,193); ``planes=128`` is the variant BASELINE config 5 names:
     the same sweep sampled at 128 planes over the same inverse-depth range, conv1.0 widened to 3 + 128 inputs."""
 
-    def __init__(self, idepth_scale=3, precision="bf16", backend="tc", planes=64):
+    def __init__(self, idepth_scale=3, precision="f16f8", backend="tc", planes=64):
         super().__init__()
         if planes < 64 or planes % 64:
             raise ValueError("planes must be a positive multiple of 64 (one 128-byte operand row per 64 planes)")
@@ -143,8 +147,14 @@ class depthNet(_KernelNet):
         st = _lib.stream_ptr()
         left = left_image.float().contiguous()
         right = right_image.float().contiguous()
-        tex = torch.empty((lib.cnm_packed_source_bytes(B, H, W),), dtype=torch.uint8, device=left.device)
         out = torch.empty((B, self.planes, H, W), dtype=torch.float32, device=left.device)
+        from .. import engine
+        if engine.PLANE_SWEEP and W % 4 == 0 and self.planes <= 128 and right.data_ptr() % 16 == 0:
+            _lib.check(lib.cnm_plane_sweep(_lib.ptr(left), _lib.ptr(right), hk.data_ptr(), out.data_ptr(), B, 1, H, W,
+                                           self.planes, idmin, idmax, _lib.VOLUME_NCHW_F32, 0, st), "plane_sweep")
+            return out
+        # widths that TMA cannot address (row pitch not a multiple of 16 bytes): repack + L1-gather kernel
+        tex = torch.empty((lib.cnm_packed_source_bytes(B, H, W),), dtype=torch.uint8, device=left.device)
         _lib.check(lib.cnm_pack_source(_lib.ptr(right), tex.data_ptr(), B, H, W, st), "pack_source")
         _lib.check(lib.cnm_cost_volume(_lib.ptr(left), tex.data_ptr(), hk.data_ptr(), out.data_ptr(), B, 1, H, W, self.planes, idmin,
                                        idmax, _lib.VOLUME_NCHW_F32, 0, st), "cost_volume")
@@ -166,7 +176,7 @@ class DepthRefineNet(_KernelNet):
     """Reference: depthnet/depthNet_model.py:268 -- ``DepthRefineNet(base_channels_num=32, idepth_scale=2)``
     (the first positional argument is unused there too)."""
 
-    def __init__(self, base_channels_num=32, idepth_scale=2, precision="bf16", backend="tc"):
+    def __init__(self, base_channels_num=32, idepth_scale=2, precision="f16f8", backend="tc"):
         super().__init__()
         self.base_channels_num = base_channels_num
         self.idepth_scale = idepth_scale

@@ -45,6 +45,10 @@ def inverse_warp(feat, depth, pose, intrinsics, intrinsics_inv, padding_mode="ze
     if not feat.is_cuda:
         raise RuntimeError("cnmnet_b200 runs on CUDA tensors only (no CPU path)")
     B, Cc, H, W = feat.shape
+    if tuple(depth.shape) != (B, H, W):
+        # the reference builds the sampling grid from depth's own size (inverse_warp.py:101-110); the kernel indexes
+        # depth with feat's H and W, so a depth map at another resolution must be resampled by the caller
+        raise ValueError("inverse_warp: depth %s must be [B,H,W] = %s of feat" % (tuple(depth.shape), (B, H, W)))
     out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=feat.device)
     lib = _lib.load()
     args = [t.float().contiguous() for t in (feat, depth, pose, intrinsics, intrinsics_inv)]

@@ -22,6 +22,7 @@ BN_EPS = 1e-5
 HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
 PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0"   # activation buffers of a plan are recycled after their last reader
 FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
+PLANE_SWEEP = os.environ.get("CNM_PLANE_SWEEP", "1") != "0"   # K1 = csrc/plane_sweep.cu (TMA-staged); 0: cost_volume.cu
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
 TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32, CNM_BF16X3: torch.bfloat16, CNM_F16F8: torch.float16}
 F8_LO_SCALE, F8_HI_SCALE = 128.0, 0.0625   # csrc/common.cuh: lo8 = e4m3((v - hi) * 2^7), hi8 = e4m3(hi * 2^-4)
@@ -293,18 +294,26 @@ def splitk_workspace(device, nfloats, lane=0):
         ws = _SPLITK_WS[key] = torch.empty((nfloats,), dtype=torch.float32, device=device)
     return ws
 
-AUTOTUNE = os.environ.get("CNM_AUTOTUNE", "1") != "0"
-# optional JSON file with earlier decisions ({repr(key): [backend, bn]}): loaded at import, written by save_tune_cache().
-# Needed under profilers, where timing the candidates is meaningless (ncu serialises and replays every launch).
+# Kernel-variant choice (which of the three convolution kernels, output-channel tile, split-K factor) per layer shape:
+#   "cache"  (default)  the shipped table cnmnet_b200/tune/b200.json (+ CNM_TUNE_CACHE, a JSON file of the same format that
+#                        overrides it); shapes it does not list run the deterministic default of ConvOp.__init__.  Nothing is
+#                        timed, so two processes -- or two boxes -- run the same kernels in the same K order and produce
+#                        bit-identical outputs.
+#   "auto"   (CNM_AUTOTUNE=1)  shapes missing from the table time their candidates once on the device (how the table is
+#                        made: tools/tune_report.py, bench.py with CNM_SAVE_TUNE_CACHE).  Variants differ in K order, so
+#                        the result of an auto-tuned process is reproducible only through the table it saves.
+#   "off"    (CNM_AUTOTUNE=off)  defaults only (tests cover the untuned variants this way).
+TUNE_MODE = {"1": "auto", "auto": "auto", "off": "off", "none": "off"}.get(os.environ.get("CNM_AUTOTUNE", "0"), "cache")
+SHIPPED_TUNE_CACHE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tune", "b200.json")
 TUNE_CACHE_FILE = os.environ.get("CNM_TUNE_CACHE", "")
 
 
-def _load_tune_cache():
-    if TUNE_CACHE_FILE and os.path.exists(TUNE_CACHE_FILE):
-        import json
-        with open(TUNE_CACHE_FILE) as f:
-            for k, v in json.load(f).items():
-                _TUNE_CACHE[k] = (v[0], int(v[1]), int(v[2]) if len(v) > 2 else 1, None)
+def load_tune_cache(path):
+    """Merges a saved table ({repr(key): [kernel, tile, ksplit]}) into the process's table."""
+    import json
+    with open(path) as f:
+        for k, v in json.load(f).items():
+            _TUNE_CACHE[k] = (v[0], int(v[1]), int(v[2]) if len(v) > 2 else 1, None)
 
 
 def save_tune_cache(path):
@@ -313,7 +322,9 @@ def save_tune_cache(path):
         json.dump({k: [v[0], v[1], v[2]] for k, v in _TUNE_CACHE.items()}, f, indent=0, sort_keys=True)
 
 
-_load_tune_cache()
+for _p in (SHIPPED_TUNE_CACHE, TUNE_CACHE_FILE):
+    if _p and os.path.exists(_p):
+        load_tune_cache(_p)
 
 
 class ConvOp:
@@ -369,7 +380,7 @@ class ConvOp:
         halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
         if backend == "tc" and halo_ok and HALO_MODE != "off" and (halo_tiles >= 120 or HALO_MODE == "force"):
             backend = "halo"
-        self.tunable = backend in ("tc", "halo", "halo2") and HALO_MODE == "auto" and AUTOTUNE
+        self.tunable = backend in ("tc", "halo", "halo2") and HALO_MODE == "auto"
         self.select(backend, 0)
 
     @property
@@ -413,11 +424,16 @@ class ConvOp:
         return out
 
     def tune(self, stream, reps=3):
-        """Times every (kernel, tile) candidate with CUDA events and keeps the fastest (cached per layer shape)."""
-        if not self.tunable:
+        """Applies the table's choice for this layer shape; in "auto" mode a missing shape times every (kernel, tile,
+        split-K) candidate with CUDA events once and enters the fastest into the table."""
+        if not self.tunable or TUNE_MODE == "off":
             return
         best = _TUNE_CACHE.get(self.key)
+        if best is not None and best[0] not in self.variants:
+            best = None
         if best is None:
+            if TUNE_MODE != "auto":
+                return   # not in the table: the deterministic default stays
             results = []
             for be, bn, ks in self.candidates():
                 self.select(be, bn, ks)
@@ -594,7 +610,7 @@ class _Plan:
         hw["bias"] = float(sd[name + ".0.bias"].reshape(-1)[0])
 
     def tune(self):
-        """Autotune every convolution of the plan (kernel x tile) on its real buffers; weights are still zero."""
+        """Kernel-variant choice for every convolution of the plan (see TUNE_MODE); weights are still zero."""
         s = _lib.stream_ptr()
         for op in self.convs.values():
             op.tune(s)
@@ -635,7 +651,11 @@ class DepthNetPlan(_Plan):
         self.N, self.Bref, self.H, self.W, self.D, self.scale = N, Bref, H, W, planes, float(idepth_scale)
         lib, dt, ch = self.lib, self.dtype, self.ch
         self.hk = self.buf(N, 12, dtype=torch.float32)
-        self.tex = torch.empty((lib.cnm_packed_source_bytes(N, H, W),), dtype=torch.uint8, device=self.device)
+        # K1: the TMA-staged plane sweep reads the source views in place; the first-generation pair (repack + L1 gather,
+        # CNM_PLANE_SWEEP=0) stays as its twin
+        self.use_sweep = PLANE_SWEEP and W % 4 == 0 and planes <= 128
+        self.tex = None if self.use_sweep else torch.empty((lib.cnm_packed_source_bytes(N, H, W),), dtype=torch.uint8,
+                                                           device=self.device)
         self.cost = self.buf(N, H, W, planes)
         self.img_taps = self.buf(N, H, W, ch)
         self.inputs = {}
@@ -643,10 +663,15 @@ class DepthNetPlan(_Plan):
         def front(s):
             i = self.inputs
             _lib.check(lib.cnm_camera_setup(i["ref_cam"], i["src_cam"], self.hk.data_ptr(), Bref, N // Bref, s), "camera")
-            _lib.check(lib.cnm_pack_source(i["src"], self.tex.data_ptr(), N, H, W, s), "pack_source")
-            _lib.check(lib.cnm_cost_volume(i["ref"], self.tex.data_ptr(), self.hk.data_ptr(), self.cost.data_ptr(), Bref,
-                                           N // Bref, H, W, planes, self.idmin, self.idmax, _lib.VOLUME_ACT, dt, s),
-                       "cost_volume")
+            if self.use_sweep:
+                _lib.check(lib.cnm_plane_sweep(i["ref"], i["src"], self.hk.data_ptr(), self.cost.data_ptr(), Bref,
+                                               N // Bref, H, W, planes, self.idmin, self.idmax, _lib.VOLUME_ACT, dt, s),
+                           "plane_sweep")
+            else:
+                _lib.check(lib.cnm_pack_source(i["src"], self.tex.data_ptr(), N, H, W, s), "pack_source")
+                _lib.check(lib.cnm_cost_volume(i["ref"], self.tex.data_ptr(), self.hk.data_ptr(), self.cost.data_ptr(),
+                                               Bref, N // Bref, H, W, planes, self.idmin, self.idmax, _lib.VOLUME_ACT,
+                                               dt, s), "cost_volume")
             _lib.check(lib.cnm_pack_row_taps(i["ref"], self.img_taps.data_ptr(), N, Bref, 3, H, W, 7, dt, s),
                        "pack_row_taps")
 

@@ -30,9 +30,13 @@ class CNMPipeline:
         key = (B, V, H, W, str(device), lane)
         st = self._state.get(key)
         if st is not None:
-            # weights may have changed since the plan was packed
-            self.depth_network.plan(V * B, B, H, W, lane=lane)
-            self.refine_network.plan(B, H, W, V // 2, False, lane=lane)
+            # weights may have changed since the plan was packed: repack, and drop a graph captured with the old ones
+            # (head biases and the f16f8 accumulator scales are launch arguments, frozen at capture)
+            dplan = self.depth_network.plan(V * B, B, H, W, lane=lane)
+            rplan = self.refine_network.plan(B, H, W, V // 2, False, lane=lane)
+            epochs = (dplan.weights_epoch, rplan.weights_epoch)
+            if st["epochs"] != epochs:
+                st["graph"], st["epochs"] = None, epochs
             return st
         if V < 2 or V % 2:
             raise ValueError("the refine network takes two view groups: V must be even and >= 2 (got %d)" % V)
@@ -48,6 +52,7 @@ class CNMPipeline:
         dplan.bind(st["ref"], st["src"].view(V * B, 3, H, W), st["ref_cam"], st["src_cam"].view(V * B, 2, 4, 4))
         rplan.bind(dplan.disp1.view(V, B, H, W), dplan.iconv1)
         st["dplan"], st["rplan"] = dplan, rplan
+        st["epochs"] = (dplan.weights_epoch, rplan.weights_epoch)
         st["prob"] = rplan.out["prob"]
         st["idepth"] = rplan.out["depth"]
         self._state[key] = st
@@ -106,7 +111,8 @@ class CNMPipeline:
 
         `batches` yields (ref_img [B,3,H,W], src_imgs [B,V,3,H,W], ref_cam [B,2,4,4], src_cams [B,V,2,4,4]) CPU tensors
         (pinned memory gives asynchronous copies); yields (depth, normal, prob) as pinned CPU tensors, one tuple per
-        batch, in order (the tensors of a tuple are reused 2*lanes batches later).
+        batch, in order.  A yielded tuple is valid until `lanes` more results have been requested (its pinned buffers are then
+        overwritten asynchronously by a later batch; with lanes=1 at the very next one): clone what must be kept.
 
         Batch i runs on lane i % lanes: every lane owns a complete buffer set + CUDA graph and its own compute
         stream, so consecutive batches overlap on the GPU -- the second lane fills what one step leaves idle (the

@@ -86,6 +86,15 @@ int cnm_pack_source(const float* src, void* packed, int N, int H, int W, void* s
 int cnm_cost_volume(const float* ref, const void* packed_src, const float* hk, void* out, int B, int V, int H,
                     int W, int D, double idepth_min, double idepth_max, int layout, int dtype, void* stream);
 
+/* cnm_plane_sweep: the same cost volume, second-generation kernel (csrc/plane_sweep.cu).  Reads the source views IN
+ *   PLACE: src [V*B,3,H,W] fp32 planar, pair p = v*B + b -- no cnm_pack_source pass.  Per (32x8 pixel tile, 8 planes)
+ *   the source footprint is staged in shared memory by TMA (zero fill outside the image = grid_sample's zeros
+ *   padding) and every bilinear tap is a shared-memory load; footprints that do not fit a 64 x 40 box are sampled from
+ *   global memory.  Same arguments and outputs otherwise.  Needs W % 4 == 0, D % 8 == 0, D <= 128, src 16B aligned
+ *   (CNM_ERR_UNSUPPORTED_SHAPE otherwise: use the cnm_pack_source + cnm_cost_volume pair).                        */
+int cnm_plane_sweep(const float* ref, const float* src, const float* hk, void* out, int B, int V, int H, int W, int D,
+                    double idepth_min, double idepth_max, int layout, int dtype, void* stream);
+
 /* ---- depth -> normal -------------------------------------------------------------------
  * replaces pixel2cam (depthnet/inverse_warp.py:27-43) + Depth2normal.forward without planes
  * (depthnet/depth_util.py:149-203,240).  depth [B,H,W], Kinv [B,3,3] -> normals [B,3,H,W],

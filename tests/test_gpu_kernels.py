@@ -46,7 +46,23 @@ def test_cost_volume_golden(golden_dir, tag):
     assert rel_l2(vol, g["volume"]) < 2e-5
 
 
-def test_cost_volume_c2_size_vs_oracle():
+def _volume(kernel, refd, src_vm, hk, out, B, V, H, W, D, layout, dtype, idmin=0.1, idmax=3.0):
+    """One cost-volume launch through the C ABI: 'sweep' = cnm_plane_sweep (TMA-staged, reads the sources in place),
+    'gather' = cnm_pack_source + cnm_cost_volume (first-generation kernel, taps through L1)."""
+    lib, st = _lib.load(), _lib.stream_ptr()
+    if kernel == "sweep":
+        _lib.check(lib.cnm_plane_sweep(refd.data_ptr(), src_vm.data_ptr(), hk.data_ptr(), out.data_ptr(), B, V, H, W, D,
+                                       idmin, idmax, layout, dtype, st))
+    else:
+        tex = torch.empty((lib.cnm_packed_source_bytes(V * B, H, W),), dtype=torch.uint8, device=dev())
+        _lib.check(lib.cnm_pack_source(src_vm.data_ptr(), tex.data_ptr(), V * B, H, W, st))
+        _lib.check(lib.cnm_cost_volume(refd.data_ptr(), tex.data_ptr(), hk.data_ptr(), out.data_ptr(), B, V, H, W, D,
+                                       idmin, idmax, layout, dtype, st))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("kernel", ["sweep", "gather"])
+def test_cost_volume_c2_size_vs_oracle(kernel):
     """BASELINE config 2: 256x192, 64 planes, 2 source views, batch 5, fp32."""
     B, V, H, W = 5, 2, 192, 256
     ref, srcs, ref_cam, src_cams = synth.frame_tuples(1234, B, H, W, V)
@@ -55,13 +71,9 @@ def test_cost_volume_c2_size_vs_oracle():
     cam_vm = src_cams.transpose(0, 1).contiguous().to(dev())
     refd, rcd = ref.to(dev()), ref_cam.to(dev())
     hk = torch.empty((V * B, 12), dtype=torch.float32, device=dev())
-    tex = torch.empty((lib.cnm_packed_source_bytes(V * B, H, W),), dtype=torch.uint8, device=dev())
     out = torch.empty((V * B, 64, H, W), dtype=torch.float32, device=dev())
     _lib.check(lib.cnm_camera_setup(rcd.data_ptr(), cam_vm.data_ptr(), hk.data_ptr(), B, V, st))
-    _lib.check(lib.cnm_pack_source(src_vm.data_ptr(), tex.data_ptr(), V * B, H, W, st))
-    _lib.check(lib.cnm_cost_volume(refd.data_ptr(), tex.data_ptr(), hk.data_ptr(), out.data_ptr(), B, V, H, W, 64, 0.1, 3.0,
-                                   _lib.VOLUME_NCHW_F32, 0, st))
-    torch.cuda.synchronize()
+    _volume(kernel, refd, src_vm, hk, out, B, V, H, W, 64, _lib.VOLUME_NCHW_F32, 0)
     got = out.cpu().numpy().reshape(V, B, 64, H, W)
     for v in range(V):
         exact = ocv.cost_volume(ref.numpy(), srcs[:, v].numpy(), ref_cam.numpy(), src_cams[:, v].numpy(), 64, 0.1, 3.0)
@@ -71,11 +83,52 @@ def test_cost_volume_c2_size_vs_oracle():
     # the act layouts carry the same numbers (bf16-rounded / exact fp32)
     for dtype in ALL_DTYPES:
         act = act_empty((V * B, H, W, 64), dtype)
-        _lib.check(lib.cnm_cost_volume(refd.data_ptr(), tex.data_ptr(), hk.data_ptr(), act.data_ptr(), B, V, H, W, 64, 0.1,
-                                       3.0, _lib.VOLUME_ACT, dtype, st))
+        _volume(kernel, refd, src_vm, hk, act, B, V, H, W, 64, _lib.VOLUME_ACT, dtype)
         back = from_act(act, dtype)
         want = out.cpu()
         assert torch.equal(back, quantize(want, dtype))
+
+
+@pytest.mark.parametrize("case", ["wide_baseline", "behind_camera", "rotation", "planes128", "partial_tiles", "scale2"])
+def test_plane_sweep_footprint_cases(case):
+    """The TMA-staged kernel against the fp64 oracle where its box logic is exercised: footprints that move too fast
+    for 8 planes per box (finer levels), sample rays that cross the source camera plane (p_z changes sign: no box, the
+    global-memory path), strong rotation (boxes much taller than the tile), 128 planes (16 groups), image sizes that
+    leave partial tiles, and idepth_scale 2 (planes out to 50 m)."""
+    rng = np.random.default_rng(len(case))
+    B, V, H, W, D, idr = 2, 1, 64, 96, 64, (0.1, 3.0)
+    rot, trans = 0.05, 0.15
+    if case == "wide_baseline":
+        trans = 1.0
+    elif case == "behind_camera":
+        trans = 3.0
+    elif case == "rotation":
+        rot = 0.6
+    elif case == "planes128":
+        D = 128
+    elif case == "partial_tiles":
+        H, W = 44, 84
+    elif case == "scale2":
+        idr = (0.02, 2.0)
+    left, right = synth.smooth_images(rng, B, H, W), synth.smooth_images(rng, B, H, W)
+    lcam, rcam = synth.cameras(rng, B, H, W, rot_sigma=rot, trans_sigma=trans)
+    lib, st = _lib.load(), _lib.stream_ptr()
+    hk = torch.empty((B, 12), dtype=torch.float32, device=dev())
+    _lib.check(lib.cnm_camera_setup(_cuda(lcam).data_ptr(), _cuda(rcam).data_ptr(), hk.data_ptr(), B, 1, st))
+    outs = {}
+    for kernel in ("sweep", "gather"):
+        out = torch.full((B, D, H, W), float("nan"), dtype=torch.float32, device=dev())
+        _volume(kernel, _cuda(left), _cuda(right), hk, out, B, 1, H, W, D, _lib.VOLUME_NCHW_F32, 0, *idr)
+        outs[kernel] = out.cpu().numpy()
+    exact = ocv.cost_volume(left, right, lcam, rcam, D, idr[0], idr[1])
+    assert np.isfinite(outs["sweep"]).all()
+    # Sample positions are amplified where p_z is small (wide baselines, rays near the source camera plane): both
+    # kernels are gated by what the first-generation kernel -- the round-1 parity reference -- scores on the same inputs
+    err_s, err_g = rel_l2(outs["sweep"], exact), rel_l2(outs["gather"], exact)
+    assert err_s < max(1e-5, 2.0 * err_g), (case, err_s, err_g)
+    big = np.abs(outs["sweep"] - exact) > 1e-3 * np.maximum(np.abs(exact), 1.0)
+    big_g = np.abs(outs["gather"] - exact) > 1e-3 * np.maximum(np.abs(exact), 1.0)
+    assert big.mean() <= max(1e-4, 2.0 * big_g.mean()), (case, big.mean(), big_g.mean())
 
 
 @pytest.mark.parametrize("H,W", [(24, 40), (33, 70), (8, 8)])
@@ -182,6 +235,23 @@ def test_cnm_overlapping_chains_and_loss(golden_dir):
     got = cnmnet_b200.get_normal_by_planes(_cuda(x), _cuda(segs3), counts3).cpu().numpy()
     assert rel_l2(got, onrm.get_normal_by_planes(x, segs3, np.array(counts3))) < 1e-6
     assert np.array_equal(got[2], x[2])                               # no planes: untouched
+
+
+def test_cnm_empty_mask_below_planes_num_gives_nan_loss(golden_dir):
+    """A plane slot below planes_num with an empty mask: the reference's mean is 0/0, cosine_similarity is NaN at every
+    pixel and the loss is NaN (depth_util.py:222-231); the oracle's sequential loop reproduces that."""
+    g = _g(golden_dir, "normals_k9.npz")
+    depth, Kinv = g["depth"][:1], g["Kinv"][:1]
+    _, H, W = depth.shape
+    segs = np.zeros((1, 20, H, W), np.uint8)
+    segs[0, 0, : H // 2] = 1                     # slot 1 stays empty, slot 2 is used
+    segs[0, 2, H // 2:] = 1
+    pn = np.array([3])
+    n, loss, _ = cnmnet_b200.Depth2normal(9)(_cuda(depth), _cuda(Kinv), _cuda(segs), torch.from_numpy(pn))
+    n64, loss64, _ = onrm.depth2normal_cnm(depth, Kinv, segs, pn)
+    assert np.isnan(float(loss64)) and np.isnan(float(loss))
+    ok = np.isfinite(n64)
+    assert np.abs(n.cpu().numpy() - n64)[ok].max() < 1e-5
 
 
 # ------------------------------------------------------------------ K4 aggregation and the small kernels
