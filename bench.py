@@ -9,7 +9,7 @@ on): full refine model, 1 ref + 2 source views, 256x192, 64 planes, k_size 9, ba
 GPU, random-init weights (reference init under torch.manual_seed(0)), synthetic frames.  A step is one
 pass of the whole pipeline over one batch: 2 cost volumes -> 2 x DepthNet -> aggregation -> DepthRefineNet
 -> 1/idepth -> depth->normal, replayed as one CUDA graph.  Multi-GPU = weak scaling: every rank runs its
-own batch, then one NCCL all-gather of the outputs.
+own batch, then ONE NCCL all-gather of the packed outputs on a side stream (overlapping the next step).
 """
 import argparse
 import json
@@ -122,51 +122,157 @@ def make_weights(seed=0):
     return d, r
 
 
-def cpu_pipeline_fps(reps, batch=1):
-    """The reference's algorithm (fp32 torch-CPU ports in oracle/nets.py) on the host cores, bounded sample."""
-    from cnmnet_b200 import synth
-    from oracle import nets as onets
-    torch.set_num_threads(os.cpu_count() or 1)
+def reference_modules(device):
+    """The UNMODIFIED reference modules through the import shim (oracle/ref_shim.py; baseline/_ref on the GPU box), with
+    the reference's own random init under torch.manual_seed(0).  None when the reference files are not present."""
+    from oracle import ref_shim
+    if not ref_shim.reference_available():
+        return None
+    ns = ref_shim.load_reference()
     torch.manual_seed(0)
-    dsd = onets.reference_init_state(onets.DEPTHNET_LAYERS, 0)
-    rsd = onets.reference_init_state(onets.REFINENET_LAYERS, 0)
+    d = ns.depthNet(idepth_scale=3.0).eval().to(device)
+    r = ns.DepthRefineNet(idepth_scale=3.0).eval().to(device)
+    return ns, d, r, ns.Depth2normal(K_SIZE)
+
+
+def reference_step(mods, ref, srcs, ref_cam, src_cams):
+    """One batch through the reference's own modules in the order of eval_refine (eval.py:440-455)."""
+    ns, d, r, d2n = mods
+    from oracle import ref_shim
+    ref_shim.reset_pixel_cache(ns)
+    with torch.no_grad():
+        p1, ic1 = d(ref, srcs[:, 0].contiguous(), ref_cam, src_cams[:, 0].contiguous())
+        p2, ic2 = d(ref, srcs[:, 1].contiguous(), ref_cam, src_cams[:, 1].contiguous())
+        idr, prob = r(idepth01=p1[0], idepth02=p2[0], iconv01=ic1, iconv02=ic2)
+        depth = torch.div(1.0, idr.squeeze(1))
+        normal, _ = d2n(depth, torch.inverse(ref_cam[:, 1, 0:3, 0:3]))
+    return depth, normal, prob
+
+
+def cpu_reference_fps(steps, warmup, batch):
+    """The reference on the host cores: its own modules when baseline/_ref (or /root/reference) is present
+    (kind "reference"), else the op-for-op torch-CPU port in oracle/nets.py (kind "port").  Bounded sample: `steps`
+    batches of `batch` frame tuples.  -> (frames/s, per-step seconds, kind)"""
+    from cnmnet_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
     ref, srcs, ref_cam, src_cams = synth.frame_tuples(1234, batch, H, W, V)
-    onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)  # warm-up
+    mods = reference_modules(torch.device("cpu"))
+    if mods is not None:
+        kind = "reference"
+
+        def run():
+            reference_step(mods, ref, srcs, ref_cam, src_cams)
+    else:
+        from oracle import nets as onets
+        kind = "port"
+        dsd = onets.reference_init_state(onets.DEPTHNET_LAYERS, 0)
+        rsd = onets.reference_init_state(onets.REFINENET_LAYERS, 0)
+
+        def run():
+            onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)
+    for _ in range(warmup):
+        run()
     ts = []
-    for _ in range(reps):
+    for _ in range(steps):
         t0 = time.perf_counter()
-        onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)
+        run()
         ts.append(time.perf_counter() - t0)
-    return batch / statistics.median(ts), ts
+    return batch * len(ts) / sum(ts), ts, kind
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, same workload
+    (batch of B_PER_GPU tuples per step), a bounded number of steps."""
     if rank != 0:
         return
-    from cnmnet_b200 import synth
-    from oracle import nets as onets
-    torch.set_num_threads(os.cpu_count() or 1)
-    dsd = onets.reference_init_state(onets.DEPTHNET_LAYERS, 0)
-    rsd = onets.reference_init_state(onets.REFINENET_LAYERS, 0)
-    ref, srcs, ref_cam, src_cams = synth.frame_tuples(1234, 1, H, W, V)
-    for _ in range(max(1, min(args.warmup, 2))):
-        onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)
-    steps = max(1, min(args.steps, 12))  # bounded: ~1.5 s of CPU work per step
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        onets.reference_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, K_SIZE)
-    dt = time.perf_counter() - t0
-    fps = steps / dt
-    sample = "%d steps of 1 frame tuple (of the batch of %d) at 256x192x64" % (steps, B_PER_GPU)
+    steps = max(1, min(args.steps, 4))      # ~5-8 s of CPU work per batch-5 step
+    warmup = max(1, min(args.warmup, 1))
+    fps, ts, kind = cpu_reference_fps(steps, warmup, B_PER_GPU)
+    sample = "%d timed steps (+%d warm-up) of one batch of %d frame tuples at 256x192x64, all host threads" % (
+        steps, warmup, B_PER_GPU)
     emit({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "host": "torch %s CPU" % torch.__version__},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+        "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "views": V + 1, "planes": D, "k_size": K_SIZE,
+                   "weights": "reference random init, torch.manual_seed(0)", "sample": sample,
+                   "host": "torch %s CPU, %d threads" % (torch.__version__, torch.get_num_threads()),
+                   "what": "the reference's own depthNet / DepthRefineNet / Depth2normal modules (unmodified files in "
+                           "baseline/_ref behind oracle/ref_shim.py), call order of eval.py:440-455" if kind == "reference"
+                           else "op-for-op torch-CPU port of the reference pipeline (oracle/nets.py): baseline/_ref absent"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
+
+
+def reference_gpu_block(dev, host, reps=5):
+    """Informational: the reference's own modules on THIS GPU through stock PyTorch (cuDNN / ATen library kernels) -- the
+    bar SURVEY.md section 2.1 names ("the reference does have a Blackwell path -- the stock library kernels").  Call sites:
+    depthNet_model.py:208-223 (~1000 ATen launches per getVolume), :235-261 and :335-365 (cuDNN convolutions, TF32 by
+    default on this torch).  Same batch, same inputs, device-resident, CUDA events; plus the same modules in
+    channels_last under bf16 autocast (what a user would try first to make the reference fast)."""
+    mods = reference_modules(dev)
+    if mods is None:
+        return {"unavailable": "baseline/_ref not present (the reference files are vendored by __graft_entry__.build() in "
+                               "the build container)"}
+    ns, d, r, d2n = mods
+    ref, srcs, ref_cam, src_cams = [t.to(dev) for t in host]
+    B = ref.shape[0]
+
+    def ev(fn, n=reps):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    out = {"what": "reference modules (baseline/_ref, unmodified) on this GPU, stock torch %s / cuDNN %s, batch %d, inputs "
+                   "resident, median of %d" % (torch.__version__, torch.backends.cudnn.version(), B, reps),
+           "allow_tf32_conv": bool(torch.backends.cudnn.allow_tf32), "unit": "frames/s"}
+    try:
+        with torch.no_grad():
+            ms_all = ev(lambda: reference_step(mods, ref, srcs, ref_cam, src_cams))
+            pix = ns.get_pixel_coordinates(H, W)
+            s0, c0 = srcs[:, 0].contiguous(), src_cams[:, 0].contiguous()
+            krk, kt = ns.process_camera_parameters(ref_cam, c0, pix)
+            ms_vol = ev(lambda: d.getVolume(ref, s0, krk, kt))
+            ms_net = ev(lambda: d(ref, s0, ref_cam, c0))
+            p1, ic1 = d(ref, s0, ref_cam, c0)
+            ms_ref = ev(lambda: r(idepth01=p1[0], idepth02=p1[0], iconv01=ic1, iconv02=ic1))
+            depth = torch.div(1.0, p1[0].squeeze(1))
+            Kinv = torch.inverse(ref_cam[:, 1, 0:3, 0:3])
+            ms_nrm = ev(lambda: d2n(depth, Kinv))
+        out["fp32_tf32"] = {"value": B / (ms_all * 1e-3), "ms_per_step": ms_all,
+                            "stages_ms": {"getVolume (one source view)": ms_vol,
+                                          "depthNet.forward (one source view, incl. getVolume)": ms_net,
+                                          "DepthRefineNet.forward": ms_ref, "Depth2normal": ms_nrm}}
+        # channels_last + bf16 autocast on the two networks
+        d2 = d.to(memory_format=torch.channels_last)
+        r2 = r.to(memory_format=torch.channels_last)
+        mods2 = (ns, d2, r2, d2n)
+
+        def fast():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                dep, nrm, prob = reference_step(mods2, ref, srcs, ref_cam, src_cams)
+            return dep
+
+        try:
+            ms_fast = ev(fast)
+            out["channels_last_bf16_autocast"] = {"value": B / (ms_fast * 1e-3), "ms_per_step": ms_fast}
+        except Exception as e:  # the reference mixes dtypes in places autocast does not cover
+            out["channels_last_bf16_autocast"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    except Exception as e:
+        out["unavailable"] = "%s: %s" % (type(e).__name__, str(e)[:300])
+    del mods
+    torch.cuda.empty_cache()
+    return out
 
 
 def time_events(fn, reps, flush):
@@ -221,7 +327,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=0,
                     help="concurrent pipeline lanes of the streaming API in the e2e measurement (0 = 2 at C4, 1 at C5 "
                          "where a second buffer set does not fit)")
-    ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--cpu-reps", type=int, default=2)
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the informational run of the reference's own modules on this GPU (stock PyTorch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer timing table on stderr")
     args = ap.parse_args()
@@ -253,7 +361,7 @@ def main():
 
     import cnmnet_b200
     from cnmnet_b200 import _lib, synth
-    from cnmnet_b200.dist import gather_outputs
+    from cnmnet_b200.dist import OutputGatherer
     lib = _lib.load()
     peaks = load_peaks()
     traffic = load_traffic()
@@ -272,13 +380,14 @@ def main():
     def flush():
         flush_buf.zero_()
 
-    gathered = {}
+    # the only collective: ONE all-gather per step of the packed output block (depth, normal, prob), on a side stream so
+    # that it overlaps the next step
+    gatherer = OutputGatherer(st["packed"].numel(), dev) if world > 1 else None
 
     def step():
         pipe.step(st)
-        if world > 1:  # the only collective: gather the outputs (depth, normal, prob) of all ranks
-            for k in ("depth", "normal", "prob"):
-                gathered[k] = gather_outputs(st[k], B * world)
+        if gatherer is not None:
+            gatherer.submit(st["packed"])
 
     def barrier():
         if world > 1:
@@ -295,11 +404,13 @@ def main():
         barrier()
         wall0 = time.perf_counter()
         total_ms = 0.0
-        for _ in range(args.steps):
+        for i in range(args.steps):
             flush()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step()
+            if gatherer is not None and i == args.steps - 1:
+                gatherer.join()   # every gather of the timed region completes inside it
             b.record()
             b.synchronize()
             total_ms += a.elapsed_time(b)
@@ -311,6 +422,8 @@ def main():
         a.record()
         for _ in range(args.steps):
             step()
+        if gatherer is not None:
+            gatherer.join()
         b.record()
         b.synchronize()
         b2b_ms = a.elapsed_time(b) / args.steps
@@ -342,9 +455,8 @@ def main():
         # from pinned host memory and downloads depth / normal / prob to the host; uploads of step i+1 and
         # downloads of step i-1 overlap the compute of step i on a copy stream ----
         def gather(_st):
-            if world > 1:
-                for k in ("depth", "normal", "prob"):
-                    gathered[k] = gather_outputs(_st[k], B * world)
+            if gatherer is not None:
+                gatherer.submit(_st["packed"])
 
         def host_batches(n):
             for _ in range(n):
@@ -358,6 +470,8 @@ def main():
         n_out = 0
         for outs in pipe.infer_stream(host_batches(args.steps), after_step=gather, lanes=lanes):
             n_out += 1
+        if gatherer is not None:
+            gatherer.join()
         torch.cuda.synchronize()
         assert n_out == args.steps
         barrier()
@@ -409,63 +523,60 @@ def main():
                 conv_rows.append(("%s.%s [%s/%d%s]" % (tag, name, op.backend, op.desc.reserved,
                                                       "/k%d" % op.desc.ksplit if op.desc.ksplit > 1 else ""), ms,
                                   op.flops_bf16_time))
-        alg_flop = B * (V * DEPTHNET_GFLOP + REFINE_GFLOP) * 1e9  # real channels only (no padding)
-        issued_flop = sum(r[2] for r in conv_rows)
+        alg_flop = B * (V * DEPTHNET_GFLOP + REFINE_GFLOP) * 1e9  # real channels only (no padding), SURVEY 8d
+        issued_bf16_time = sum(r[2] for r in conv_rows)             # bf16-pass-equivalents issued, padding included
         tf = alg_flop / (conv_ms * 1e-3) / 1e12
-        tf32 = args.precision == "tf32"
-        fp32_equiv_tf = tf
-        if args.precision == "bf16x3":
-            # the arithmetic of this mode is three bf16 tensor-core products per fp32-grade product (hi*Whi + lo*Whi +
-            # hi*Wlo, none redundant): the roofline counts them; fp32_equivalent_tflops is the 1x figure
-            alg_flop *= 3.0
-            tf *= 3.0
-        if args.precision == "f16f8":
-            # one fp16 product plus two fp8 products (K-concatenated into one kind::f8f6f4 pass at twice the f16 rate)
-            # per fp32-grade product: 2 bf16-pass-equivalents of tensor-pipe time.  `achieved` is that bf16-time-
-            # equivalent rate, comparable with the measured bf16 peak; the raw issued rate is 1.5x higher.
-            alg_flop *= 2.0
-            tf *= 2.0
-        peak = peaks["bf16_tflops_sustained"] * (0.5 if tf32 else 1.0)
+        # every convolution is timed alone (5 launches of 50-250 us with an L2 flush in between): the burst peak is
+        # the denominator; the sustained one is given beside it
+        peak = peaks["bf16_tflops"]
+        passes = {"bf16": 1.0, "tf32": 2.0, "bf16x3": 3.0, "f16f8": 2.0}[args.precision]
         line["roofline"] = {
             "kernel": "conv_tc / conv_halo / conv_halo2 kernels (tcgen05 implicit GEMM, all %d conv launches of one step)"
                       % len(conv_rows),
             "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+            "achieved_note": "ALGORITHMIC FLOPs (SURVEY 8d: 2*Cout*Cin*k*k*Ho*Wo over real channels, %.3f TFLOP per step) / "
+                             "summed conv kernel time" % (alg_flop / 1e12),
+            "peak_source": "%s bf16 burst (kernels timed in isolation); sustained %.1f -> frac %.3f" % (
+                peaks["source"], peaks["bf16_tflops_sustained"], tf / peaks["bf16_tflops_sustained"]),
             "traffic": traffic.get("conv_bytes_per_step") if (args.precision == "f16f8" and args.workload == "c4") else None,
-            "traffic_note": "DRAM read+write bytes of all conv launches of one step, ncu (profiles/r01_launches_step.md)",
-            "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step, "fp32_equivalent_tflops": fp32_equiv_tf,
-            "peak_source": "%s bf16 sustained%s" % (peaks["source"], " x 0.5 for tf32" if tf32 else ""),
-            "issued_tflops_incl_padding": issued_flop / (conv_ms * 1e-3) / 1e12,
-            "achieved_note": {"bf16x3": "3 bf16 passes per product counted", "f16f8": "bf16-time-equivalent: fp16 pass + "
-                              "fp8 pass (2 products at 2x rate) = 2 units per product; raw issued FLOP/s = 1.5 x achieved",
-                              }.get(args.precision, "1 pass per product"),
+            "traffic_note": "DRAM read+write bytes of all conv launches of one step, ncu (profiles/)",
+            "ms_per_step": conv_ms, "share_of_step": conv_ms / ms_per_step,
+            # what the tensor pipe is actually asked to do: this precision mode spends `passes` bf16-pass-equivalents per
+            # algorithmic MAC (f16f8: one fp16 pass + one fp8 pass of twice the K at twice the rate)
+            "tensor_pipe_equiv": {"bf16_pass_equivalents_per_mac": passes, "achieved": tf * passes,
+                                  "frac_of_burst": tf * passes / peak,
+                                  "frac_of_sustained": tf * passes / peaks["bf16_tflops_sustained"],
+                                  "issued_incl_padding": issued_bf16_time / (conv_ms * 1e-3) / 1e12},
         }
         # cost volume at BASELINE config 2: NCHW fp32, batch 5, 2 views
         refd, srcd = st["ref"], st["src"].view(V * B, 3, H, W)
         hk = dplan.hk
         vol = torch.empty((V * B, D, H, W), dtype=torch.float32, device=dev)
+        tex = torch.empty((lib.cnm_packed_source_bytes(V * B, H, W),), dtype=torch.uint8, device=dev)
 
-        def cv():
-            _lib.check(lib.cnm_pack_source(srcd.data_ptr(), dplan.tex.data_ptr(), V * B, H, W, s))
-            _lib.check(lib.cnm_cost_volume(refd.data_ptr(), dplan.tex.data_ptr(), hk.data_ptr(), vol.data_ptr(), B, V, H,
-                                           W, D, 0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
+        def cv_sweep():
+            _lib.check(lib.cnm_plane_sweep(refd.data_ptr(), srcd.data_ptr(), hk.data_ptr(), vol.data_ptr(), B, V, H, W, D,
+                                           0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
 
-        def cv_only():
-            _lib.check(lib.cnm_cost_volume(refd.data_ptr(), dplan.tex.data_ptr(), hk.data_ptr(), vol.data_ptr(), B, V, H,
-                                           W, D, 0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
+        def cv_gather():
+            _lib.check(lib.cnm_cost_volume(refd.data_ptr(), tex.data_ptr(), hk.data_ptr(), vol.data_ptr(), B, V, H, W, D,
+                                           0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
 
-        cv()
-        ms_cv, _ = time_events(cv, 20, flush)
-        ms_cvk, _ = time_events(cv_only, 20, flush)
+        _lib.check(lib.cnm_pack_source(srcd.data_ptr(), tex.data_ptr(), V * B, H, W, s))
+        cv_sweep()
+        ms_cvk, _ = time_events(cv_sweep, 20, flush)
+        ms_cvg, _ = time_events(cv_gather, 20, flush)
         cv_bytes = B * (V * 4 * D * H * W + (V + 1) * 4 * 3 * H * W)   # = C2_COST_VOLUME_BYTES on the default workload
         gbs = cv_bytes / (ms_cvk * 1e-3) / 1e9
         line["roofline_cost_volume"] = {
-            "kernel": "cost_volume_kernel (%s: %dx%dx%d, %d views, batch %d, fp32 NCHW)" % (
+            "kernel": "plane_sweep_kernel (%s: %dx%dx%d, %d views, batch %d, fp32 NCHW; TMA-staged source boxes)" % (
                 "C2" if args.workload == "c4" else "C5 size", W, H, D, V, B), "bound": "hbm",
             "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
             "traffic": traffic.get("cost_volume_c2_bytes") if args.workload == "c4" else None,
-            "us_per_launch": ms_cvk * 1e3, "us_with_source_repack": ms_cv * 1e3, "algorithmic_bytes": cv_bytes,
-            "peak_source": peaks["source"],
+            "us_per_launch": ms_cvk * 1e3, "algorithmic_bytes": cv_bytes, "peak_source": peaks["source"],
+            "first_generation_kernel_us": ms_cvg * 1e3,
         }
+        del vol, tex
         # depth -> normal at C3 and the aggregation at C4
         nrm = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
         ms_n, _ = time_events(lambda: _lib.check(lib.cnm_depth2normal(st["depth"].data_ptr(), st["Kinv"].data_ptr(),
@@ -475,6 +586,20 @@ def main():
                                     "achieved": nb / (ms_n * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": nb / (ms_n * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_launch": ms_n * 1e3,
                                     "algorithmic_bytes": nb}
+        if args.workload == "c4":
+            # the same kernel at C5 size (640x480, batch 32: 157 MB), where it leaves the launch-latency regime
+            B5, H5, W5 = 32, 480, 640
+            d5 = torch.rand((B5, H5, W5), dtype=torch.float32, device=dev) * 4.0 + 0.5
+            k5 = st["Kinv"][:1].expand(B5, 3, 3).contiguous()
+            n5 = torch.empty((B5, 3, H5, W5), dtype=torch.float32, device=dev)
+            ms_n5, _ = time_events(lambda: _lib.check(lib.cnm_depth2normal(d5.data_ptr(), k5.data_ptr(), n5.data_ptr(), None,
+                                                                           B5, H5, W5, K_SIZE, s)), 10, flush)
+            nb5 = B5 * 16 * H5 * W5
+            line["roofline_normals_c5"] = {"kernel": "depth2normal_kernel (C5 size: 640x480, batch 32, k=9)", "bound": "hbm",
+                                           "achieved": nb5 / (ms_n5 * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                           "frac": nb5 / (ms_n5 * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "us_per_launch": ms_n5 * 1e3, "algorithmic_bytes": nb5}
+            del d5, n5
         # Combined Normal Map (K3b) on the same normals: synthetic disjoint plane masks, reference semantics
         segs_np, pn_np = synth.plane_segments(np.random.default_rng(3), B, H, W)
         segs = torch.from_numpy(segs_np).to(dev)
@@ -497,10 +622,11 @@ def main():
         ab_moved = B * H * W * (V * esz + V * 4 + esz + rpl.taps.element_size() * rpl.taps.shape[3] + 8)
         line["roofline_refine_aggregate"] = {
             "kernel": "refine_taps_kernel + refine_sum_act_kernel (C4: batch 5, 2 views)", "bound": "hbm",
-            "achieved": ab_moved / (ms_a * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ab_moved / (ms_a * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_step": ms_a * 1e3,
-            "algorithmic_bytes": ab_moved, "algorithmic_bytes_fp32_reference_layout": ab_fp32,
-            "note": "bytes of the stored formats actually read and written (act tensors of this mode)"}
+            "achieved": ab_fp32 / (ms_a * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ab_fp32 / (ms_a * 1e-3) / 1e9 / peaks["hbm_gbs"], "us_per_step": ms_a * 1e3,
+            "algorithmic_bytes": ab_fp32,
+            "note": "algorithmic bytes = SURVEY 8d (fp32 NCHW tensors of the reference: read 2*(1+64)*4*HW, write 67*4*HW "
+                    "per sample); the kernels move %d bytes of the stored act formats" % ab_moved}
         # the other tensor-core modes, same workload, same timing method (kept out of the headline value)
         line["other_modes"] = []
         others = [m for m in ("bf16", "tf32", "bf16x3", "f16f8") if m != args.precision]
@@ -522,11 +648,14 @@ def main():
         if args.layers:
             for name, ms, fl in sorted(conv_rows, key=lambda r: -r[1]):
                 sys.stderr.write("%-40s %8.3f ms  %7.1f TFLOP/s issued\n" % (name, ms, fl / ms / 1e9))
+        if world == 1 and args.workload == "c4" and not args.no_reference_gpu:
+            line["reference_gpu"] = reference_gpu_block(dev, host)
         if not args.no_cpu_baseline and world == 1:
-            fps_cpu, ts = cpu_pipeline_fps(args.cpu_reps)
-            line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "%d timed runs of 1 frame tuple at 256x192x64 (median), fp32 torch-CPU port "
-                                              "of the reference pipeline" % len(ts)}
+            fps_cpu, ts, kind = cpu_reference_fps(max(1, args.cpu_reps), 1, B_PER_GPU)
+            line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": kind,
+                                    "sample": "%d timed steps (+1 warm-up) of one batch of %d frame tuples at 256x192x64: %s"
+                                              % (len(ts), B_PER_GPU, "the reference's own modules (baseline/_ref)"
+                                                 if kind == "reference" else "fp32 torch-CPU port of the reference")}
         emit(line)
     if world > 1:
         dist.barrier()

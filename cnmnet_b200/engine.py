@@ -553,7 +553,8 @@ class _Plan:
         Cc //= self.pf
         out = self.buf(N, 1, H, W, dtype=torch.float32)
         logits = self.buf(N, 1, H, W, dtype=torch.float32) if want_logits else None
-        hw = {"w": torch.zeros((9 * Cc,), dtype=torch.float32, device=self.device), "bias": 0.0, "scale": float(scale)}
+        hw = {"w": torch.zeros((9 * Cc,), dtype=torch.float32, device=self.device), "bias": 0.0, "scale": float(scale),
+              "out": out}
         self.heads[name] = hw
         lib, dt = self.lib, self.dtype
         lp = logits.data_ptr() if logits is not None else None
@@ -570,7 +571,7 @@ class _Plan:
             hw["partial"] = partial
             op.fuse_head(hw["w_tap_major"], partial)
             self.ops.append(lambda s: _lib.check(
-                lib.cnm_head_finish(partial.data_ptr(), S, hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s), name))
+                lib.cnm_head_finish(partial.data_ptr(), S, hw["bias"], hw["scale"], hw["out"].data_ptr(), lp, N, H, W, s), name))
             self.release(partial)
             return out, logits
         if FUSE_HEADS:
@@ -582,16 +583,24 @@ class _Plan:
             def two_pass(s):
                 _lib.check(lib.cnm_head_partial(x.data_ptr(), hw["w_tap_major"].data_ptr(), partial.data_ptr(), N, H, W, Cc,
                                                 dt, s), name)
-                _lib.check(lib.cnm_head_finish(partial.data_ptr(), 1, hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, s),
+                _lib.check(lib.cnm_head_finish(partial.data_ptr(), 1, hw["bias"], hw["scale"], hw["out"].data_ptr(), lp, N, H, W, s),
                            name)
 
             self.ops.append(two_pass)
             self.release(partial)
             return out, logits
         self.ops.append(lambda s: _lib.check(
-            lib.cnm_head3x3(x.data_ptr(), hw["w"].data_ptr(), hw["bias"], hw["scale"], out.data_ptr(), lp, N, H, W, Cc,
+            lib.cnm_head3x3(x.data_ptr(), hw["w"].data_ptr(), hw["bias"], hw["scale"], hw["out"].data_ptr(), lp, N, H, W, Cc,
                             dt, s), name))
         return out, logits
+
+    def bind_head_output(self, name, out):
+        """Redirects a head's output [N,1,H,W] fp32 to a caller-owned buffer (CNMPipeline's packed output block).  The
+        owner of the plan must do this before capturing a graph."""
+        hw = self.heads[name]
+        if tuple(out.shape) != tuple(hw["out"].shape) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("head output must be a contiguous fp32 tensor of shape %s" % (tuple(hw["out"].shape),))
+        hw["out"] = out
 
     def disp_taps(self, disp):
         N, _, h, w = disp.shape

@@ -44,16 +44,22 @@ class CNMPipeline:
         st = {
             "ref": torch.empty((B, 3, H, W), **f32), "src": torch.empty((V, B, 3, H, W), **f32),
             "ref_cam": torch.empty((B, 2, 4, 4), **f32), "src_cam": torch.empty((V, B, 2, 4, 4), **f32),
-            "Kinv": torch.empty((B, 3, 3), **f32), "depth": torch.empty((B, H, W), **f32),
-            "normal": torch.empty((B, 3, H, W), **f32), "graph": None,
+            "Kinv": torch.empty((B, 3, 3), **f32), "graph": None,
+            # the three outputs of a step live in ONE buffer [depth B*HW | normal 3*B*HW | prob B*HW]: a multi-GPU run
+            # gathers it with a single collective (cnmnet_b200.dist.OutputGatherer)
+            "packed": torch.empty((5 * B * H * W,), **f32),
         }
+        n = B * H * W
+        st["depth"] = st["packed"][:n].view(B, H, W)
+        st["normal"] = st["packed"][n:4 * n].view(B, 3, H, W)
+        st["prob"] = st["packed"][4 * n:].view(B, 1, H, W)
         dplan = self.depth_network.plan(V * B, B, H, W, lane=lane)
         rplan = self.refine_network.plan(B, H, W, V // 2, False, lane=lane)
         dplan.bind(st["ref"], st["src"].view(V * B, 3, H, W), st["ref_cam"], st["src_cam"].view(V * B, 2, 4, 4))
         rplan.bind(dplan.disp1.view(V, B, H, W), dplan.iconv1)
         st["dplan"], st["rplan"] = dplan, rplan
         st["epochs"] = (dplan.weights_epoch, rplan.weights_epoch)
-        st["prob"] = rplan.out["prob"]
+        rplan.bind_head_output("prob", st["prob"])     # the prob head writes straight into the packed block
         st["idepth"] = rplan.out["depth"]
         self._state[key] = st
         return st

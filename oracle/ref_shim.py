@@ -1,19 +1,48 @@
-"""Import shim for the UNMODIFIED reference at /root/reference (build container only).
+"""Import shim for the UNMODIFIED reference (test / benchmark infrastructure, never used by the product).
 
-Recipe: SURVEY.md Appendix D.  The reference imports tensorflow (unused on the hot
-path), hard-codes torch.cuda.FloatTensor and uses Tensor.get_device() as a device;
-on a CPU-only box those three are patched and nothing else.  Never used at run time
-on the GPU box (``/root/reference`` does not exist there) and never by the product.
+Recipe: SURVEY.md Appendix D.  The reference imports tensorflow (unused on the hot path), hard-codes
+torch.cuda.FloatTensor and uses Tensor.get_device() as a device; on a CPU-only box those three are patched and nothing
+else.  Where it is found, in this order: $CNM_REFERENCE_ROOT, /root/reference (the build container), baseline/_ref
+(git-ignored copy of the six files the import chain needs, made by __graft_entry__.build() in the build container so
+that bench.py can time the reference itself on the GPU box's host cores and on its GPU -- BASELINE.md section 4.2).
 """
 import os
+import shutil
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CNM_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VENDORED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+VENDORED_FILES = ("depthnet/__init__.py", "depthnet/depthNet_model.py", "depthnet/depth_util.py",
+                  "depthnet/inverse_warp.py", "scannet/__init__.py", "scannet/preprocess.py")
+
+
+def _find_root():
+    for root in (os.environ.get("CNM_REFERENCE_ROOT", ""), "/root/reference", VENDORED_ROOT):
+        if root and os.path.isfile(os.path.join(root, "depthnet", "depthNet_model.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
+
+
+def vendor_reference(src_root="/root/reference"):
+    """Copies the reference files of the import chain, unmodified, to the git-ignored baseline/_ref (build container
+    only; a no-op where the reference tree is absent).  Returns True if baseline/_ref is populated afterwards."""
+    global REFERENCE_ROOT
+    if os.path.isfile(os.path.join(src_root, "depthnet", "depthNet_model.py")):
+        for rel in VENDORED_FILES:
+            dst = os.path.join(VENDORED_ROOT, rel)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(os.path.join(src_root, rel), dst)
+    ok = all(os.path.isfile(os.path.join(VENDORED_ROOT, rel)) for rel in VENDORED_FILES)
+    REFERENCE_ROOT = _find_root()
+    return ok
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "depthnet"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "depthnet", "depthNet_model.py"))
 
 
 def load_reference():

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _worker(rank, world, port, total, q):
     sys.path.insert(0, ROOT)
-    from cnmnet_b200.dist import gather_outputs, reduce_metrics, shard_range
+    from cnmnet_b200.dist import OutputGatherer, gather_outputs, reduce_metrics, shard_range, unpack_outputs
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -21,6 +21,18 @@ def _worker(rank, world, port, total, q):
     got = gather_outputs(full[a:b].clone(), total)
     m = reduce_metrics(torch.tensor([float(b - a), 1.0]))
     ok = torch.equal(got, full) and m.tolist() == [float(total), float(world)]
+    # one packed all-gather per step (depth | normal | prob of B frames per rank), two steps through the two slots
+    B, H, W = 2, 3, 4
+    g = OutputGatherer(5 * B * H * W, "cpu")
+    for step in range(3):
+        packed = torch.arange(5 * B * H * W, dtype=torch.float32) + 1000.0 * rank + 7.0 * step
+        depth, normal, prob = unpack_outputs(g.result(g.submit(packed)), B, H, W)
+        ok = ok and depth.shape == (world * B, H, W) and normal.shape == (world * B, 3, H, W) and prob.shape == (world * B, 1, H, W)
+        for r in range(world):
+            want = torch.arange(5 * B * H * W, dtype=torch.float32) + 1000.0 * r + 7.0 * step
+            ok = ok and torch.equal(depth[r * B:(r + 1) * B].reshape(-1), want[:B * H * W])
+            ok = ok and torch.equal(normal[r * B:(r + 1) * B].reshape(-1), want[B * H * W:4 * B * H * W])
+            ok = ok and torch.equal(prob[r * B:(r + 1) * B].reshape(-1), want[4 * B * H * W:])
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
