@@ -37,6 +37,8 @@ SIGNATURES = {
     "cnm_last_error": (C.c_char_p, []),
     "cnm_version": (C.c_char_p, []),
     "cnm_launch_count": (_L, []),
+    "cnm_set_range_check": (None, [_I]),
+    "cnm_range_overflow_count": (_L, [_I]),
     "cnm_camera_setup": (_I, [_P, _P, _P, _I, _I, _P]),
     "cnm_packed_source_bytes": (_L, [_I, _I, _I]),
     "cnm_pack_source": (_I, [_P, _P, _I, _I, _I, _P]),

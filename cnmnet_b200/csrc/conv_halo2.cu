@@ -38,6 +38,7 @@ struct alignas(64) Halo2Params {
   int c_out_offset;
   int mode;         // EPI_PLAIN / EPI_BF16X3 / EPI_F16F8: the split modes store two 128-byte rows per 64-column chunk
   float acc_scale;  // 2^-acc_exp
+  unsigned long long* range_ctr;  // debug counter of out-of-fp16-range outputs (NULL: off)
   const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
   float* head_partial;   // [Cout/64 slices][N, Ho, Wo, 12] per-pixel tap dot products, one slice per 64-channel chunk
   int Ho, Wo, cout;
@@ -290,7 +291,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
           tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
           if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
           tmem_ld_wait();
-          epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale);
+          epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr);
           if (!TF32 && fused_head) {
             const int px = x0 + (row & 15), py = y0 + 8 * half + (row >> 4);
             if (px < p.Wo && py < p.Ho) {
@@ -407,6 +408,7 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
   p.c_out_offset = d->c_out_offset;
   p.mode = d->dtype == CNM_BF16X3 ? EPI_BF16X3 : (d->dtype == CNM_F16F8 ? EPI_F16F8 : EPI_PLAIN);
   p.acc_scale = ldexpf(1.0f, -d->acc_exp);
+  p.range_ctr = d->dtype == CNM_F16F8 ? range_counter() : nullptr;
   p.head_w = d->head_w;
   p.head_partial = d->head_partial;
   p.Ho = d->Ho; p.Wo = d->Wo; p.cout = d->Cout;

@@ -47,6 +47,7 @@ struct alignas(64) TcParams {
   int c_out_offset;
   int mode;         // EPI_PLAIN / EPI_BF16X3 / EPI_F16F8: the split modes store two 128-byte rows per 64-column chunk
   float acc_scale;  // 2^-acc_exp
+  unsigned long long* range_ctr;  // debug counter of out-of-fp16-range outputs (NULL: off)
   const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
   float* head_partial;   // [N, Ho, Wo, 12] per-pixel tap dot products
   int N, Ho, Wo;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
         if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
         tmem_ld_wait();
-        epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale);
+        epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr);
         if (!TF32 && fused_head) {
           const int px = x0 + row % p.TW, py = y0 + (row / p.TW) % p.TH, pn = n0 + row / (p.TW * p.TH);
           if (px < p.Wo && py < p.Ho && pn < p.N) {
@@ -305,13 +306,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 template <typename T>
 __global__ void __launch_bounds__(256)
     splitk_finish_kernel(const float* __restrict__ ws, int ksplit, size_t mtot, int cout, const float* __restrict__ bias,
-                         float scale, int relu, uint8_t* __restrict__ out, size_t pix_bytes, size_t off_bytes) {
+                         float scale, int relu, uint8_t* __restrict__ out, size_t pix_bytes, size_t off_bytes,
+                         unsigned long long* range_ctr) {
   const int groups = cout >> 3;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= mtot * groups) return;
   const int c = (int)(idx % groups) * 8;
   const size_t pixel = idx / groups;
   float v[8];
+  bool over = false;
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.0f;
   for (int s = 0; s < ksplit; ++s) {
@@ -324,7 +327,9 @@ __global__ void __launch_bounds__(256)
   for (int j = 0; j < 8; ++j) {
     const float t = fmaf(v[j], scale, bias ? __ldg(bias + c + j) : 0.0f);
     v[j] = relu ? fmaxf(t, 0.0f) : t;
+    over |= !(fabsf(v[j]) <= 65504.0f);
   }
+  if (range_ctr && over) atomicAdd(range_ctr, 1ULL);
   T* px = reinterpret_cast<T*>(out + pixel * pix_bytes + off_bytes) + ActTraits<T>::phys(c);
 #pragma unroll
   for (int j = 0; j < 8; j += Vec16<T>::N) Vec16<T>::store(px + j, v + j);
@@ -428,6 +433,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.c_out_offset = d->c_out_offset;
   p.mode = d->dtype == CNM_BF16X3 ? EPI_BF16X3 : (d->dtype == CNM_F16F8 ? EPI_F16F8 : EPI_PLAIN);
   p.acc_scale = ldexpf(1.0f, -d->acc_exp);
+  p.range_ctr = d->dtype == CNM_F16F8 ? range_counter() : nullptr;
   p.head_w = d->head_w;
   p.head_partial = d->head_partial;
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
@@ -491,7 +497,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   const unsigned blocks = (unsigned)((out_vecs + 255) / 256);
   const size_t pix_bytes = (size_t)d->c_out_total * eb, off_bytes = (size_t)d->c_out_offset * eb;
 #define CNM_FINISH(T) \
-  splitk_finish_kernel<T><<<blocks, 256, 0, s>>>(p.ws, p.ksplit, mtot, d->Cout, bias, p.acc_scale, d->relu, (uint8_t*)out, pix_bytes, off_bytes)
+  splitk_finish_kernel<T><<<blocks, 256, 0, s>>>(p.ws, p.ksplit, mtot, d->Cout, bias, p.acc_scale, d->relu, (uint8_t*)out, pix_bytes, off_bytes, p.range_ctr)
   if (d->dtype == CNM_BF16) CNM_FINISH(__nv_bfloat16);
   else if (d->dtype == CNM_TF32) CNM_FINISH(float);
   else if (d->dtype == CNM_BF16X3) CNM_FINISH(bf16s);

@@ -102,13 +102,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 
 // ---- epilogue helpers ---------------------------------------------------------------------------------------------
 // epi_finalize: accumulator columns of this thread's pixel -> value = relu(acc * scale + bias), in place (fp32 bits).
+// range_ctr (debug, CNM_CHECK_RANGE=1 / cnm_set_range_check): counts (pixel, chunk) pairs holding a value beyond the fp16
+// range, which CNM_F16F8 storage saturates silently otherwise.
 template <int COLS>
-__device__ __forceinline__ void epi_finalize(uint32_t* v, const float* bs, int relu, float scale) {
+__device__ __forceinline__ void epi_finalize(uint32_t* v, const float* bs, int relu, float scale,
+                                             unsigned long long* range_ctr = nullptr) {
+  bool over = false;
 #pragma unroll
   for (int c = 0; c < COLS; ++c) {
     float t = fmaf(__uint_as_float(v[c]), scale, bs[c]);
-    v[c] = __float_as_uint(relu ? fmaxf(t, 0.0f) : t);
+    t = relu ? fmaxf(t, 0.0f) : t;
+    over |= !(fabsf(t) <= 65504.0f);
+    v[c] = __float_as_uint(t);
   }
+  if (range_ctr && over) atomicAdd(range_ctr, 1ULL);
 }
 
 // epi_store_row: the finalised values of one chunk -> one 128-byte row of the 128B-swizzled staging tile.
@@ -200,6 +207,7 @@ __device__ __forceinline__ void epi_head_partial(const uint32_t* v, const float*
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)
 int encode_map(CUtensorMap* map, int dtype, int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, bool swizzle128 = true);
+unsigned long long* range_counter();  // device counter of the current device, or nullptr when range checking is off
 int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* srcs, const void* steps, const void* wp,
                     const void* out);
 

@@ -69,6 +69,14 @@ const char* cnm_version(void);
 /* number of kernels launched by this library since load (all threads); used for gpu_launches */
 int64_t cnm_launch_count(void);
 
+/* Debug range check of CNM_F16F8 (activations are stored as fp16 and saturate at 65504 silently): when enabled -- by
+ * cnm_set_range_check(1) or CNM_CHECK_RANGE=1 in the environment at first use -- every convolution epilogue counts the
+ * (pixel, 64-channel chunk) pairs holding a value beyond the fp16 range in a per-device counter.
+ * cnm_range_overflow_count synchronises the device and returns the count (-1 when the check is off); reset != 0
+ * clears it.  Enable before the first step of a pipeline (the counter is allocated on first use, outside graphs). */
+void cnm_set_range_check(int enable);
+int64_t cnm_range_overflow_count(int reset);
+
 /* ---- camera pre-processing -------------------------------------------------------------
  * replaces process_camera_parameters + get_pixel_coordinates  (depthnet/depth_util.py:13-56)
  * ref_cam [B,2,4,4], src_cam [V,B,2,4,4]  ->  hk [V*B, 12] = (Hm row-major 3x3, kt 3)

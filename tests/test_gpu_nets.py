@@ -384,3 +384,29 @@ def test_outputs_are_bit_identical_across_processes():
         assert out.returncode == 0, out.stderr[-2000:]
         hashes.append([ln for ln in out.stdout.splitlines() if ln.startswith("HASH")][-1])
     assert hashes[0] == hashes[1]
+
+
+def test_range_check_counts_fp16_overflow():
+    """CNM_F16F8 stores activations as fp16 (saturating at 65504); the debug range check counts convolution outputs
+    beyond that range: zero on ordinary weights, non-zero when a layer is scaled out of range."""
+    from cnmnet_b200 import _lib
+    lib = _lib.load()
+    B, H, W = 1, 32, 64
+    ref, srcs, ref_cam, src_cams = [t.to(dev()) for t in synth.frame_tuples(12, B, H, W, 2)]
+    sd = synth.kaiming_state(onets.state_shapes(onets.DEPTHNET_LAYERS), 91, 0.02)
+    lib.cnm_set_range_check(1)
+    try:
+        assert lib.cnm_range_overflow_count(1) >= 0
+        net = cnmnet_b200.depthNet(idepth_scale=3.0, precision="f16f8")
+        net.load_state_dict(sd)
+        net.to(dev())(ref, srcs[:, 0].contiguous(), ref_cam, src_cams[:, 0].contiguous())
+        assert lib.cnm_range_overflow_count(1) == 0
+        hot = dict(sd)
+        hot["conv1.1.weight"] = sd["conv1.1.weight"] * 1.0e5      # BatchNorm gamma of conv1.0: activations ~1e5
+        net2 = cnmnet_b200.depthNet(idepth_scale=3.0, precision="f16f8")
+        net2.load_state_dict(hot)
+        net2.to(dev())(ref, srcs[:, 0].contiguous(), ref_cam, src_cams[:, 0].contiguous())
+        assert lib.cnm_range_overflow_count(1) > 0
+    finally:
+        lib.cnm_set_range_check(0)
+    assert lib.cnm_range_overflow_count(0) == -1
