@@ -13,3 +13,4 @@ from .depthnet.inverse_warp import inverse_warp, pixel2cam  # noqa: F401
 from .pipeline import CNMPipeline  # noqa: F401
 from .video import VideoDepthStream, reference_tuples  # noqa: F401
 from .metrics import depth_metrics  # noqa: F401
+from . import sevenscenes  # noqa: F401

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcnmnet_b200.so")
-SOURCES = ["api.cu", "cost_volume.cu", "plane_sweep.cu", "normals.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "conv_halo2.cu",
+SOURCES = ["api.cu", "cost_volume.cu", "plane_sweep.cu", "normals.cu", "elementwise.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu",
            "metrics.cu", "losses.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]

@@ -15,6 +15,18 @@
 // Accumulators    2 x BN TMEM columns per tile pair; double-buffered when 4*BN <= 512.
 // Warp roles      warp 0 A-slab TMA producer, warp 3 B-tile TMA producer, warps 1-2 MMA issuers (one per pixel tile;
 //                   warp 2 also allocates TMEM), warps 4-7 epilogue.
+//
+// CTA-pair variant (conv_halo2_kernel, CG = 2): tcgen05.mma.cta_group::2 with M = 256 across the two SMs of a cluster.
+// With both operands in shared memory a single-SM UMMA at N <= 128 is bound by the 128 B/clk shared-memory port
+// (profiles/r01_conv_halo_ncu.md: 4 KB of A + 4 KB of B per 64-cycle MMA plus the TMA fill).  In cta_group::2 each SM
+// supplies the 128 A rows of its own pixel block but only HALF of the weight tile (BN/2 rows), so B reads and B fill per
+// SM halve.  Differences to the single-CTA instantiation (all under `if constexpr (CG == 2)` in ONE kernel body):
+//   * cluster of 2 CTAs, both walk the same (N-tile, group, tap) sequence on two neighbouring 16x16 pixel blocks;
+//   * every CTA TMA-loads its own A slabs and its half of each B tile; the loads signal the LEADER CTA's "full"
+//     barriers (cp.async.bulk.tensor ... .cta_group::2 with the peer bit of the barrier address cleared);
+//   * only the leader's warp 1 issues MMAs (D = 128 rows x BN columns in EACH CTA's TMEM); tcgen05.commit is
+//     multicast to both CTAs' "empty" and "accumulator full" barriers;
+//   * both CTAs run the epilogue on their own TMEM half; "accumulator empty" arrivals go to the leader's barrier.
 #include <cstring>
 
 #include "tc_common.cuh"
@@ -47,15 +59,69 @@ struct alignas(64) HaloParams {
   int Ho, Wo, cout;
 };
 
-template <int BN, bool TF32>
-__global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+// ---- 2-CTA PTX wrappers --------------------------------------------------------------------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: -> leader CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA's smem, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// tcgen05.commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (TF32)
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+  else
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void tc2_mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+               : "memory");
+}
+// arrive on the barrier at this offset in the leader CTA (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+
+// CG = 1: one CTA per 16x16 pixel block, two MMA-issuing warps (one per half of the block).  CG = 2: a CTA pair on two
+// neighbouring blocks, one M = 256 MMA per half issued by the leader.
+template <int BN, bool TF32, int CG>
+__device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;
   constexpr int CHUNK_CH = TF32 ? 32 : 64;
   constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
   constexpr int ACC_STAGES = (4 * BN <= 512) ? 2 : 1;
   constexpr uint32_t TMEM_COLS = (2 * BN * ACC_STAGES) < 32 ? 32 : 2 * BN * ACC_STAGES;
-  constexpr int B_BYTES = BN * 128;
-  constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int B_BYTES = (BN / CG) * 128;  // CG = 2: this CTA's half of the weight tile
+  constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);  // M = 128 per CTA
   constexpr uint32_t IDESC = IDESC_SHAPE | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10);
   // CNM_F16F8: operand formats 0 = e4m3 (kind::f8f6f4) on the first half of the groups (the correction rows, accumulated
   // while the sum is still tiny) and 0 = fp16 (kind::f16) on the second half
@@ -86,7 +152,11 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n;
+  // CG = 2: a super-tile = the same N tile on two neighbouring pixel blocks (m = 2*mm + rank), one per CTA of the pair
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  const int total_tiles = (p.tiles_x * p.tiles_y * p.tiles_b / CG) * p.tiles_n;
+  const int first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.b_map);
@@ -94,18 +164,27 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     tma_prefetch_desc(&p.a_maps[0]);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 2); }
-    for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 2); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 2); mbar_init(tempty(a), 128); }
+    // CG = 1: two issuing warps commit to every barrier the MMAs release; CG = 2: one issuer, 2 x 128 epilogue threads
+    constexpr uint32_t ISSUERS = CG == 1 ? 2u : 1u;
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), ISSUERS); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), ISSUERS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), ISSUERS); mbar_init(tempty(a), 128u * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + off_tmem), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + off_tmem), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + off_tmem), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // both CTAs' barriers are initialised and TMEM is allocated before any remote signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -116,8 +195,8 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
       int sa = 0;
       uint32_t pa = 0;
       int4 g_next = __ldg(reinterpret_cast<const int4*>(p.groups));
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int m = tile / p.tiles_n;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        int m = CG * (tile / p.tiles_n) + (int)rank;
         const int x0 = (m % p.tiles_x) * 16;
         m /= p.tiles_x;
         const int y0 = (m % p.tiles_y) * 16;
@@ -128,8 +207,9 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
           const int pad = p.map_pad[gr.x];
           const uint32_t slab_tx = (uint32_t)p.map_rows[gr.x] * 2048u;
           mbar_wait(emptyA(sa), pa ^ 1);
-          mbar_expect_tx(fullA(sa), slab_tx);
-          tma_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
+          if (leader) mbar_expect_tx(fullA(sa), (uint32_t)CG * slab_tx);  // CG = 2: both CTAs' slabs
+          if (CG == 2) tma2_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
+          else tma_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
       }
@@ -140,31 +220,33 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
       int sb = 0;
       uint32_t pb = 0;
       const int num_steps = p.num_steps;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int nt = tile % p.tiles_n;
         for (int kstep = 0; kstep < num_steps; ++kstep) {
           mbar_wait(emptyB(sb), pb ^ 1);
-          mbar_expect_tx(fullB(sb), B_BYTES);
-          tma_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN);
+          if (leader) mbar_expect_tx(fullB(sb), (uint32_t)CG * B_BYTES);  // CG = 2: both halves
+          if (CG == 2) tma2_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN + (int)rank * (BN / 2));
+          else tma_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN);
           if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp == 1 || (CG == 1 && warp == 2)) {
     // ================= MMA issuers =================
-    // Two issuing lanes, one per pixel tile of the pair (warp 1 -> rows 0-7 / accumulator columns [0,BN), warp 2 -> rows
-    // 8-15 / [BN,2BN)): a single lane needs ~100 instructions per weight step (barrier wait, descriptors, 8 MMAs,
-    // commit), which at BN <= 128 is as long as the MMAs themselves take (profiles/r01_conv_halo_ncu.md).  Each
-    // barrier that the MMAs release therefore expects two commits.
-    // The whole warp walks the loop (all lanes poll the barriers) and one elected lane issues: this keeps the control
-    // flow warp-uniform, so the compiler holds descriptors in uniform registers instead of wrapping every tcgen05
+    // CG = 1: two issuing warps, one per half of the pixel block (warp 1 -> rows 0-7 / accumulator columns [0,BN),
+    // warp 2 -> rows 8-15 / [BN,2BN)): a single lane needs ~100 instructions per weight step (barrier wait,
+    // descriptors, 8 MMAs, commit), which at BN <= 128 is as long as the MMAs themselves take
+    // (profiles/r01_conv_halo_ncu.md); every barrier the MMAs release therefore expects two commits.
+    // CG = 2: the leader CTA's warp 1 issues one M = 256 MMA per half, spanning both CTAs.
+    // The whole warp walks the loop (all lanes poll the barriers) and one elected lane issues: the control flow stays
+    // warp-uniform, so the compiler holds descriptors in uniform registers instead of wrapping every tcgen05
     // instruction in a per-lane election loop.
-    {
-      const int half = warp - 1;
+    if (leader) {
+      const int half = CG == 1 ? warp - 1 : 0;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
         const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
         const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(tempty(as), aphase ^ 1);
@@ -174,24 +256,37 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
         for (int g = 0; g < p.num_groups; ++g) {
           const int ntaps = __ldg(&p.groups[g].ntaps);
           mbar_wait(fullA(sa), pa);
-          const uint64_t adesc0 = umma_desc(base + sa * p.slab_bytes + half * 8 * 2048);
+          const uint32_t slab = base + sa * p.slab_bytes + half * 8 * 2048;
           for (int t = 0; t < ntaps; ++t) {
             mbar_wait(fullB(sb), pb);
             tc_fence_after();
             if (elect_one()) {
               const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
-              const uint64_t adesc = adesc0 + (uint64_t)(t * (2048 >> 4));
-              if (mixed && g < (p.num_groups >> 1)) {
+              const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
+              const bool f8 = mixed && g < (p.num_groups >> 1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc_mma_f8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
-              } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                if (CG == 2) {
+                  if (f8) {
+                    tc2_mma_f8(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                    tc2_mma_f8(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                  } else {
+                    tc2_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                    tc2_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                  }
+                } else {
+                  if (f8) tc_mma_f8(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                  else tc_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                }
               }
-              tc_commit(emptyB(sb));
-              if (t == ntaps - 1) tc_commit(emptyA(sa));
+              if (CG == 2) {
+                tc2_commit(emptyB(sb));
+                if (t == ntaps - 1) tc2_commit(emptyA(sa));
+              } else {
+                tc_commit(emptyB(sb));
+                if (t == ntaps - 1) tc_commit(emptyA(sa));
+              }
             }
             __syncwarp();
             first = 0;
@@ -199,7 +294,10 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
           }
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
-        if (elect_one()) tc_commit(tfull(as));
+        if (elect_one()) {
+          if (CG == 2) tc2_commit(tfull(as));
+          else tc_commit(tfull(as));
+        }
         __syncwarp();
       }
     }
@@ -208,14 +306,14 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
     const int q = warp - 4;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;
-    const bool leader = (et == 0);
+    const bool storer = (et == 0);
     int it = 0;
     int bias_tile = -1;
     uint32_t store_cnt = 0;
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
       const int nt = tile % p.tiles_n;
-      int m = tile / p.tiles_n;
+      int m = CG * (tile / p.tiles_n) + (int)rank;
       const int x0 = (m % p.tiles_x) * 16;
       m /= p.tiles_x;
       const int y0 = (m % p.tiles_y) * 16;
@@ -256,7 +354,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
             // let the packing of one row overlap the TMA store of the previous one.
             uint8_t* stg = base_ptr + off_out + (p.out_stages == 2 ? (store_cnt & 1u) * HL_TILE_BYTES : 0u);
             ++store_cnt;
-            if (leader) {
+            if (storer) {
               if (p.out_stages == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
               else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
@@ -264,7 +362,7 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
             epi_store_row<TF32>(v, stg + row * 128, row, p.mode, part);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             epi_bar();
-            if (leader) {
+            if (storer) {
               tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.mode ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
                                    x0, y0 + 8 * half, n0);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -273,42 +371,61 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty(as));
+      if (CG == 2) mbar_arrive_leader(tempty(as));  // 2 x 128 arrivals on the leader's barrier release the accumulator stage
+      else mbar_arrive(tempty(as));
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its operands
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
 template <int BN, bool TF32>
+__global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, TF32, 1>(p);
+}
+template <int BN, bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, TF32, 2>(p);
+}
+
+template <int BN, bool TF32, int CG>
 static int launch_halo(const HaloParams& p, int grid, int smem, cudaStream_t s) {
   static DynSmemLimit limit;
-  cudaError_t e = limit.ensure(conv_halo_kernel<BN, TF32>, smem);
-  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_halo: smem attribute (%d B): %s", smem, cudaGetErrorString(e));
-  conv_halo_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
-  return after_launch("cnm_conv2d_halo");
+  const char* fn = CG == 2 ? "cnm_conv2d_halo2" : "cnm_conv2d_halo";
+  cudaError_t e = CG == 2 ? limit.ensure(conv_halo2_kernel<BN, TF32>, smem) : limit.ensure(conv_halo_kernel<BN, TF32>, smem);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
+  if (CG == 2) conv_halo2_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
+  else conv_halo_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
+  return after_launch(fn);
 }
 
 }  // namespace cnm
 
 using namespace cnm;
 
-extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* map_info,
-                               const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
-                               void* stream) {
-  int rc = check_conv_args("cnm_conv2d_halo", d, srcs, groups, wp, out);
+// Shared host side of cnm_conv2d_halo (CG = 1) and cnm_conv2d_halo2 (CG = 2)
+template <int CG>
+static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* map_info,
+                       const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                       void* stream) {
+  const char* fn = CG == 2 ? "cnm_conv2d_halo2" : "cnm_conv2d_halo";
+  int rc = check_conv_args(fn, d, srcs, groups, wp, out);
   if (rc) return rc;
-  CNM_REQUIRE(d->ksplit <= 1, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: split-K is a cnm_conv2d_tc feature");
-  CNM_REQUIRE(map_info && num_groups > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo: bad group list");
+  CNM_REQUIRE(d->ksplit <= 1, CNM_ERR_UNSUPPORTED_SHAPE, "%s: split-K is a cnm_conv2d_tc feature", fn);
+  CNM_REQUIRE(map_info && num_groups > 0, CNM_ERR_INVALID_ARGUMENT, "%s: bad group list", fn);
   CNM_REQUIRE(d->Ho >= 16 && d->Wo >= 16, CNM_ERR_UNSUPPORTED_SHAPE,
-              "cnm_conv2d_halo: output %dx%d smaller than the 16x16 tile (use cnm_conv2d_tc)", d->Ho, d->Wo);
-  CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_halo: Cout=%d must be a multiple of 64", d->Cout);
+              "%s: output %dx%d smaller than the 16x16 tile (use cnm_conv2d_tc)", fn, d->Ho, d->Wo);
+  CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "%s: Cout=%d must be a multiple of 64", fn, d->Cout);
+  CNM_REQUIRE(CG == 1 || (((d->Wo + 15) / 16) * ((d->Ho + 15) / 16) * d->N) % 2 == 0, CNM_ERR_UNSUPPORTED_SHAPE,
+              "%s: needs an even number of 16x16 pixel blocks (CTA pairs)", fn);
   const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
   HaloParams p;
   memset(&p, 0, sizeof(p));
@@ -320,12 +437,12 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
       const int m = i * 4 + sub, pad = map_info[2 * m], rows = map_info[2 * m + 1];
       if (rows == 0) continue;  // sub-image not used by any group
       CNM_REQUIRE(pad >= 0 && pad <= 4 && rows >= 16 && rows <= 24, CNM_ERR_UNSUPPORTED_SHAPE,
-                  "cnm_conv2d_halo: map %d has pad %d / %d slab rows", m, pad, rows);
+                  "%s: map %d has pad %d / %d slab rows", fn, m, pad, rows);
       p.map_pad[m] = pad;
       p.map_rows[m] = rows;
       if (rows > rows_max) rows_max = rows;
     }
-  CNM_REQUIRE(rows_max > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo: no operand maps");
+  CNM_REQUIRE(rows_max > 0, CNM_ERR_INVALID_ARGUMENT, "%s: no operand maps", fn);
   const int pmax = (rows_max - 16 + 1) / 2;
   p.slab_bytes = rows_max * 2048;
   p.tiles_x = (d->Wo + 15) / 16;
@@ -343,7 +460,7 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
     }
   }
   if (d->reserved == 64 || d->reserved == 128 || d->reserved == 256) {  // caller-selected tile (host autotuner)
-    CNM_REQUIRE(d->Cout % d->reserved == 0, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo: BN=%d does not divide Cout=%d",
+    CNM_REQUIRE(d->Cout % d->reserved == 0, CNM_ERR_INVALID_ARGUMENT, "%s: BN=%d does not divide Cout=%d", fn,
                 d->reserved, d->Cout);
     BN = d->reserved;
   }
@@ -366,24 +483,25 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
   p.out_stages = BN == 64 ? 2 : 1;
   const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (d->head_partial ? 9 * BN * 4 : 0) + 8 * (2 * HL_MAX_A + 2 * HL_MAX_B + 4) + 16;
   const int budget = 232448 - fixed;
-  const int want_b = BN == 256 ? 4 : (BN == 128 ? 7 : 8);
+  const int want_b = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 7 : 8));
+  const int b_tile = BN * 128 / CG;   // bytes of one weight tile (CG = 2: this CTA's half)
   p.a_stages = (pmax >= 3 || BN == 256) ? 2 : (BN == 64 ? 4 : 3);
-  p.b_stages = (budget - p.a_stages * p.slab_bytes) / (BN * 128);
+  p.b_stages = (budget - p.a_stages * p.slab_bytes) / b_tile;
   if (p.b_stages > want_b) p.b_stages = want_b;
   if (p.b_stages > HL_MAX_B) p.b_stages = HL_MAX_B;
   while (p.b_stages < 3 && p.a_stages > 2) {
     p.a_stages -= 1;
-    p.b_stages = (budget - p.a_stages * p.slab_bytes) / (BN * 128);
+    p.b_stages = (budget - p.a_stages * p.slab_bytes) / b_tile;
   }
   CNM_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, CNM_ERR_UNSUPPORTED_SHAPE,
-              "cnm_conv2d_halo: slab of %d B does not fit", p.slab_bytes);
+              "%s: slab of %d B does not fit", fn, p.slab_bytes);
   {  // spend what is left on more slabs
-    const int left = budget - p.a_stages * p.slab_bytes - p.b_stages * BN * 128;
+    const int left = budget - p.a_stages * p.slab_bytes - p.b_stages * b_tile;
     const int extra = left / p.slab_bytes;
     p.a_stages += extra;
     if (p.a_stages > HL_MAX_A) p.a_stages = HL_MAX_A;
   }
-  const int smem = fixed + p.a_stages * p.slab_bytes + p.b_stages * BN * 128;
+  const int smem = fixed + p.a_stages * p.slab_bytes + p.b_stages * b_tile;
 
   for (int i = 0; i < d->num_srcs; ++i) {
     const cnm_conv_src& s = srcs[i];
@@ -411,7 +529,7 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
     const uint64_t K = (uint64_t)d->num_steps * ch;
     const uint64_t dims[2] = {K, (uint64_t)d->Cout};
     const uint64_t str[1] = {K * eb};
-    const uint32_t bbox[2] = {(uint32_t)ch, (uint32_t)BN};
+    const uint32_t bbox[2] = {(uint32_t)ch, (uint32_t)(BN / CG)};
     rc = encode_map(&p.b_map, d->dtype, 2, wp, dims, str, bbox);
     if (rc) return rc;
   }
@@ -423,11 +541,23 @@ extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs,
     rc = encode_map(&p.out_map, d->dtype, 4, out, dims, str, box);
     if (rc) return rc;
   }
-  const int total = m_tiles * p.tiles_n;
-  const int grid = total < 148 ? total : 148;
+  const int total = (m_tiles / CG) * p.tiles_n;  // CG = 2: super-tiles, one per CTA pair
+  const int grid = CG * (total < 148 / CG ? total : 148 / CG);
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
-  if (BN == 256) return tf32 ? launch_halo<256, true>(p, grid, smem, s) : launch_halo<256, false>(p, grid, smem, s);
-  if (BN == 128) return tf32 ? launch_halo<128, true>(p, grid, smem, s) : launch_halo<128, false>(p, grid, smem, s);
-  return tf32 ? launch_halo<64, true>(p, grid, smem, s) : launch_halo<64, false>(p, grid, smem, s);
+  if (BN == 256) return tf32 ? launch_halo<256, true, CG>(p, grid, smem, s) : launch_halo<256, false, CG>(p, grid, smem, s);
+  if (BN == 128) return tf32 ? launch_halo<128, true, CG>(p, grid, smem, s) : launch_halo<128, false, CG>(p, grid, smem, s);
+  return tf32 ? launch_halo<64, true, CG>(p, grid, smem, s) : launch_halo<64, false, CG>(p, grid, smem, s);
+}
+
+extern "C" int cnm_conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* map_info,
+                               const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                               void* stream) {
+  return conv2d_halo<1>(d, srcs, map_info, groups, num_groups, wp, bias, out, stream);
+}
+
+extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* map_info,
+                                const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                                void* stream) {
+  return conv2d_halo<2>(d, srcs, map_info, groups, num_groups, wp, bias, out, stream);
 }

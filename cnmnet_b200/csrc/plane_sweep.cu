@@ -11,7 +11,9 @@
 //
 // Structure
 //   CTA            32 x 8 pixels of one (view, batch) pair, ALL D planes (per-pixel invariants a = Hm.[x,y,1] and the
-//                  reference pixel are computed once), 256 threads, one pixel per thread.
+//                  reference pixel are computed once): 8 consumer warps, one pixel per thread, + 1 producer warp that
+//                  only issues TMA.  No CTA-wide barrier in the plane loop: consumers wait on a stage's "full"
+//                  mbarrier (TMA transaction count) and release it on its "empty" mbarrier, one arrival per warp.
 //   plane group    8 consecutive planes share one source BOX: for a fixed pixel the sample point moves along the
 //                  epipolar line as the plane changes, so the union of the footprints of the tile over 8 planes is a
 //                  slightly larger rectangle than the tile itself.  Warp 0 finds it at kernel start: the homography is
@@ -42,11 +44,14 @@ constexpr int PS_CH_WORDS = PS_BW * PS_BH_MAX;       // one colour channel of a 
 constexpr int PS_STAGE_BYTES = 3 * PS_CH_WORDS * 4;  // 30 720
 constexpr int PS_MAX_D = 128;
 constexpr int PS_MAX_GROUPS = PS_MAX_D / PS_DP;
-constexpr int PS_OFF_GSTATE = 2 * PS_STAGE_BYTES + 16;
+constexpr int PS_STAGES = 2;
+constexpr int PS_CONSUMER_WARPS = PS_TY, PS_THREADS = PS_TX * (PS_TY + 1);  // + the producer warp
+constexpr int PS_OFF_GSTATE = PS_STAGES * PS_STAGE_BYTES + 64;
 constexpr int PS_OFF_GBASE = PS_OFF_GSTATE + PS_MAX_GROUPS * 16;
 constexpr int PS_OFF_NODES = PS_OFF_GBASE + 80;
 constexpr int PS_OFF_FLAT = PS_OFF_NODES + 15 * PS_MAX_GROUPS * 16;
 constexpr int PS_SMEM = PS_OFF_FLAT + 8 * PS_MAX_GROUPS * 16 + 1024;
+static_assert(2 * PS_STAGES * 8 <= 64, "barrier block");
 constexpr float PS_MAGIC = 12582912.0f;  // 1.5 * 2^23: (v + MAGIC) has integer spacing, low mantissa bits = round(v)
 constexpr uint32_t PS_MAGIC_BITS = 0x4B400000u;
 
@@ -89,7 +94,7 @@ __device__ __forceinline__ void sweep_position(float a0, float a1, float a2, flo
 }
 
 // one output from global memory with per-tap predicates (groups whose footprint does not fit a box)
-__device__ __forceinline__ float sweep_gather_global(const float* __restrict__ sp, int H, int W, float ix, float iy,
+__device__ __noinline__ float sweep_gather_global(const float* __restrict__ sp, int H, int W, float ix, float iy,
                                                      float r0, float r1, float r2) {
   ix = fminf(fmaxf(ix, -1.0f), (float)W);  // NaN -> -1: all four taps outside
   iy = fminf(fmaxf(iy, -1.0f), (float)H);
@@ -142,57 +147,54 @@ struct SweepPixel {  // per-thread invariants of the plane loop
 
 template <int LAYOUT>  // 0 = NCHW fp32, 1 = act bf16, 2 = act fp32 (tf32), 3 = act split bf16, 4 = act fp16 + fp8
 __device__ __forceinline__ void sweep_store8(const SweepParams& p, const SweepPixel& px, int d0, const float* res) {
-  const size_t HW = (size_t)p.H * p.W, pixel = (size_t)px.pair * HW + (size_t)px.y * p.W + px.x;
+  const size_t HW = (size_t)p.H * p.W;
+  const uint32_t pix = (uint32_t)(px.y * p.W + px.x);   // inside one image plane: 32 bits
   const int D = p.D;
   if (LAYOUT == 0) {
-    float* o = reinterpret_cast<float*>(p.out) + ((size_t)px.pair * D + d0) * HW + (size_t)px.y * p.W + px.x;
+    // one byte pointer, advanced by the (uniform) plane stride: two integer instructions per store
+    char* o = reinterpret_cast<char*>(p.out) + (((size_t)px.pair * D + d0) * HW + pix) * sizeof(float);
+    const size_t plane_bytes = HW * sizeof(float);
+    asm volatile("" : "+l"(o));  // one opaque per-thread pointer: keeps the compiler from re-deriving it per plane
 #pragma unroll
-    for (int i = 0; i < PS_DP; ++i) __stcs(o + (size_t)i * HW, res[i]);
-  } else if (LAYOUT == 1) {
-    Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(p.out) + pixel * D + d0, res);
-  } else if (LAYOUT == 2) {
-    float* o = reinterpret_cast<float*>(p.out) + pixel * D + d0;
-    Vec16<float>::store(o, res);
-    Vec16<float>::store(o + 4, res + 4);
-  } else if (LAYOUT == 3) {
-    Vec16<bf16s>::store(reinterpret_cast<bf16s*>(p.out) + pixel * ActTraits<bf16s>::pstride(D) + ActTraits<bf16s>::phys(d0), res);
+    for (int i = 0; i < PS_DP; ++i) {
+      __stcs(reinterpret_cast<float*>(o), res[i]);
+      o += plane_bytes;
+    }
   } else {
-    Vec16<h16f8>::store(reinterpret_cast<h16f8*>(p.out) + pixel * ActTraits<h16f8>::pstride(D) + ActTraits<h16f8>::phys(d0), res);
+    const size_t pixel = (size_t)px.pair * HW + pix;
+    if (LAYOUT == 1) {
+      Vec16<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(p.out) + pixel * D + d0, res);
+    } else if (LAYOUT == 2) {
+      float* o = reinterpret_cast<float*>(p.out) + pixel * D + d0;
+      Vec16<float>::store(o, res);
+      Vec16<float>::store(o + 4, res + 4);
+    } else if (LAYOUT == 3) {
+      Vec16<bf16s>::store(reinterpret_cast<bf16s*>(p.out) + pixel * ActTraits<bf16s>::pstride(D) + ActTraits<bf16s>::phys(d0), res);
+    } else {
+      Vec16<h16f8>::store(reinterpret_cast<h16f8*>(p.out) + pixel * ActTraits<h16f8>::pstride(D) + ActTraits<h16f8>::phys(d0), res);
+    }
   }
 }
 
 struct SweepCtx {  // CTA-uniform state of the plane loop
   const int4* flat;   // segments in plane order: box origin x, y, BH index (-1: no box), first plane
   int nflat;
-  uint32_t base, bar0;
-  uint32_t phases;    // bit st = parity of stage st's barrier
+  uint32_t base, bar0;  // stage s: "full" barrier at bar0 + 8 s, "empty" barrier at bar0 + 8 (PS_STAGES + s)
 };
 
-// thread 0: TMA of segment n's box into stage n & 1
-__device__ __forceinline__ void sweep_issue(const SweepParams& p, const SweepCtx& c, int pair, int n) {
-  const int4 bi = c.flat[n];
-  if (bi.z < 0) return;
-  const int st = n & 1;
-  mbar_expect_tx(c.bar0 + 8u * st, 3u * (uint32_t)(PS_BW * ps_bh(bi.z) * 4));
-#pragma unroll
-  for (int ch = 0; ch < 3; ++ch)
-    tma_load_3d(c.base + st * PS_STAGE_BYTES + ch * PS_CH_WORDS * 4, &p.maps[bi.z], c.bar0 + 8u * st, bi.x, bi.y, 3 * pair + ch);
-}
-
-// One group of 8 planes as 8 / S segments of S planes per box, starting at flat segment n0.
+// One group of 8 planes as 8 / S segments of S planes per box, starting at flat segment n0 (consumer warps).
 template <int S>
-__device__ __forceinline__ void sweep_group(const SweepParams& p, const SweepPixel& px, SweepCtx& c, int n0, int tid,
+__device__ __forceinline__ void sweep_group(const SweepParams& p, const SweepPixel& px, const SweepCtx& c, int n0, int lane,
                                             float* res) {
   const int H = p.H, W = p.W;
   const float* sp = p.src + (size_t)px.pair * 3 * H * W;
 #pragma unroll
   for (int sub = 0; sub < PS_DP / S; ++sub) {
     const int n = n0 + sub;
-    const int st = n & 1;
+    const int st = n % PS_STAGES;
     const int4 bi = c.flat[n];
+    mbar_wait(c.bar0 + 8u * st, (uint32_t)(n / PS_STAGES) & 1u);  // the box has landed (or the segment has none)
     if (bi.z >= 0) {
-      mbar_wait(c.bar0 + 8u * st, (c.phases >> st) & 1u);
-      c.phases ^= 1u << st;
       // x0 in [floor(ix) - 1, floor(ix)], taps x0 and x0 + 1: ix in [ox + 1, ox + BW - 2) keeps them inside the box
       const float cx_lo = fmaxf(-1.0f, (float)(bi.x + 1)), cx_hi = fminf((float)W, (float)(bi.x + PS_BW - 3));
       const float cy_lo = fmaxf(-1.0f, (float)(bi.y + 1)), cy_hi = fminf((float)H, (float)(bi.y + ps_bh(bi.z) - 3));
@@ -214,24 +216,45 @@ __device__ __forceinline__ void sweep_group(const SweepParams& p, const SweepPix
         res[sub * S + i] = px.active ? sweep_gather_global(sp, H, W, ix, iy, px.r0, px.r1, px.r2) : 0.0f;
       }
     }
-    __syncthreads();  // every thread is done with stage st: its next box may land
-    if (tid == 0 && n + 2 < c.nflat) sweep_issue(p, c, px.pair, n + 2);
+    __syncwarp();  // every lane's loads of this stage have returned (their values feed the arithmetic above)
+    if (lane == 0) mbar_arrive(c.bar0 + 8u * (PS_STAGES + st));  // this warp is done with stage st
+  }
+}
+
+// The producer warp's lane 0: fills stage n % PS_STAGES with segment n's box as soon as all consumer warps have
+// released what it held before.  Segments without a box complete the "full" barrier with a plain arrival, so that the
+// consumers' phase arithmetic does not depend on which segments have one.
+__device__ __forceinline__ void sweep_produce(const SweepParams& p, const SweepCtx& c, int pair) {
+  for (int n = 0; n < c.nflat; ++n) {
+    const int st = n % PS_STAGES;
+    if (n >= PS_STAGES) mbar_wait(c.bar0 + 8u * (PS_STAGES + st), (uint32_t)(n / PS_STAGES - 1) & 1u);
+    const int4 bi = c.flat[n];
+    const uint32_t full = c.bar0 + 8u * st;
+    if (bi.z < 0) {
+      mbar_arrive(full);
+      continue;
+    }
+    mbar_expect_tx(full, 3u * (uint32_t)(PS_BW * ps_bh(bi.z) * 4));
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      tma_load_3d(c.base + st * PS_STAGE_BYTES + ch * PS_CH_WORDS * 4, &p.maps[bi.z], full, bi.x, bi.y, 3 * pair + ch);
   }
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(PS_TX* PS_TY, 3) plane_sweep_kernel(const __grid_constant__ SweepParams p) {
+__global__ void __launch_bounds__(PS_THREADS, 3) plane_sweep_kernel(const __grid_constant__ SweepParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar0 = base + 2 * PS_STAGE_BYTES;
-  // after the two stages: barriers [16 B], per-group state [16 groups x 16 B: fit[3], level], group -> first flat segment
+  const uint32_t bar0 = base + PS_STAGES * PS_STAGE_BYTES;
+  // after the stages: barriers [64 B], per-group state [16 groups x 16 B: fit[3], level], group -> first flat segment
   // [17 ints], node table [15 G x 16 B], flat segment list [8 G x 16 B]
   int4* gstate = reinterpret_cast<int4*>(base_ptr + PS_OFF_GSTATE);
   int* gbase = reinterpret_cast<int*>(base_ptr + PS_OFF_GBASE);
   int4* seg = reinterpret_cast<int4*>(base_ptr + PS_OFF_NODES);
   int4* flat = reinterpret_cast<int4*>(base_ptr + PS_OFF_FLAT);
-  const int tid = threadIdx.y * PS_TX + threadIdx.x;
+  const int tid = threadIdx.y * PS_TX + threadIdx.x;   // consumers: 0..255 (one pixel each); producer warp: 256..287
+  const bool consumer = threadIdx.y < PS_TY;
   const int H = p.H, W = p.W;
   const int G = p.D / PS_DP;
   const size_t HW = (size_t)H * W;
@@ -239,7 +262,7 @@ __global__ void __launch_bounds__(PS_TX* PS_TY, 3) plane_sweep_kernel(const __gr
   px.pair = blockIdx.z;
   px.x = blockIdx.x * PS_TX + threadIdx.x;
   px.y = blockIdx.y * PS_TY + threadIdx.y;
-  px.active = px.x < W && px.y < H;
+  px.active = consumer && px.x < W && px.y < H;
 
   const float* h = p.hk + (size_t)px.pair * 12;
   const float h0 = __ldg(h + 0), h1 = __ldg(h + 1), h2 = __ldg(h + 2), h3 = __ldg(h + 3), h4 = __ldg(h + 4),
@@ -247,8 +270,10 @@ __global__ void __launch_bounds__(PS_TX* PS_TY, 3) plane_sweep_kernel(const __gr
   px.k0 = __ldg(h + 9); px.k1 = __ldg(h + 10); px.k2e = __ldg(h + 11) + 1e-6f;
 
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    for (int st = 0; st < PS_STAGES; ++st) {
+      mbar_init(bar0 + 8u * st, 1);                                   // full: the producer's arrival (+ TMA bytes)
+      mbar_init(bar0 + 8u * (PS_STAGES + st), PS_CONSUMER_WARPS);     // empty: one arrival per consumer warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = 0; i < PS_NUM_BH; ++i) tma_prefetch_desc(&p.maps[i]);
   }
@@ -266,7 +291,7 @@ __global__ void __launch_bounds__(PS_TX* PS_TY, 3) plane_sweep_kernel(const __gr
     const float cx = (float)((corner & 1) ? min(x_lo + PS_TX - 1, W - 1) : x_lo);
     const float cy = (float)((corner & 2) ? min(y_lo + PS_TY - 1, H - 1) : y_lo);
     const float a0 = fmaf(h0, cx, fmaf(h1, cy, h2)), a1 = fmaf(h3, cx, fmaf(h4, cy, h5)), a2 = fmaf(h6, cx, fmaf(h7, cy, h8));
-    for (int n0 = node_begin; n0 < node_end; n0 += (PS_TX * PS_TY) / 4) {  // warp-uniform trip count
+    for (int n0 = node_begin; n0 < node_end; n0 += (PS_TX * PS_TY) / 4) {  // warp-uniform trip count (consumer threads)
       const int node = n0 + (tid >> 2);
       const bool live = node < node_end;
       const int nn = live ? node : node_end - 1;
@@ -297,8 +322,10 @@ __global__ void __launch_bounds__(PS_TX* PS_TY, 3) plane_sweep_kernel(const __gr
       if (corner == 0 && live) {
         // the taps of a sample at ix touch columns floor(ix) - 1 .. floor(ix) + 1; one more column on each side absorbs
         // the fp32 rounding of the corner positions
-        const int ox = (int)floorf(mnx) - 2, oy = (int)floorf(mny) - 2;
-        const int wneed = (int)floorf(mxx) - (int)floorf(mnx) + 6, hneed = (int)floorf(mxy) - (int)floorf(mny) + 6;
+        // ... and the box starts on a multiple of 4 texels: TMA traps (illegal instruction) when the innermost start
+        // coordinate is not 16-byte aligned
+        const int ox = ((int)floorf(mnx) - 2) & ~3, oy = (int)floorf(mny) - 2;
+        const int wneed = (int)floorf(mxx) + 4 - ox, hneed = (int)floorf(mxy) - (int)floorf(mny) + 6;
         int idx = -1;
         if (oki && wneed <= PS_BW) idx = hneed <= ps_bh(0) ? 0 : (hneed <= ps_bh(1) ? 1 : (hneed <= ps_bh(2) ? 2 : -1));
         seg[node] = make_int4(ox, oy, idx, j * S);
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(PS_TX* PS_TY, 3) plane_sweep_kernel(const __gr
   }
   __syncthreads();
   if (gbase[PS_MAX_GROUPS]) {  // CTA-uniform
-    box_tasks(G, 15 * G);
+    if (consumer) box_tasks(G, 15 * G);
     __syncthreads();
   }
   // flat segment list: group g runs at the coarsest level whose segments all have a box (level 3 = one plane per box;
@@ -349,18 +376,18 @@ __global__ void __launch_bounds__(PS_TX* PS_TY, 3) plane_sweep_kernel(const __gr
   c.nflat = gbase[PS_MAX_GROUPS];
   c.base = base;
   c.bar0 = bar0;
-  c.phases = 0u;
-  if (tid == 0) {
-    sweep_issue(p, c, px.pair, 0);
-    if (c.nflat > 1) sweep_issue(p, c, px.pair, 1);
+  if (!consumer) {
+    if (threadIdx.x == 0) sweep_produce(p, c, px.pair);
+    return;
   }
+  const int lane = threadIdx.x;
   for (int g = 0; g < G; ++g) {
     float res[PS_DP];
     const int lv = gstate[g].w, n0 = gbase[g];
-    if (lv == 0) sweep_group<8>(p, px, c, n0, tid, res);
-    else if (lv == 1) sweep_group<4>(p, px, c, n0, tid, res);
-    else if (lv == 2) sweep_group<2>(p, px, c, n0, tid, res);
-    else sweep_group<1>(p, px, c, n0, tid, res);
+    if (lv == 0) sweep_group<8>(p, px, c, n0, lane, res);
+    else if (lv == 1) sweep_group<4>(p, px, c, n0, lane, res);
+    else if (lv == 2) sweep_group<2>(p, px, c, n0, lane, res);
+    else sweep_group<1>(p, px, c, n0, lane, res);
     if (px.active) sweep_store8<LAYOUT>(p, px, g * PS_DP, res);
   }
 }
@@ -370,7 +397,7 @@ static int launch_sweep(const SweepParams& p, dim3 grid, cudaStream_t s) {
   static DynSmemLimit limit;
   cudaError_t e = limit.ensure(plane_sweep_kernel<LAYOUT>, PS_SMEM);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_plane_sweep: smem attribute: %s", cudaGetErrorString(e));
-  plane_sweep_kernel<LAYOUT><<<grid, dim3(PS_TX, PS_TY), PS_SMEM, s>>>(p);
+  plane_sweep_kernel<LAYOUT><<<grid, dim3(PS_TX, PS_TY + 1), PS_SMEM, s>>>(p);
   return after_launch("cnm_plane_sweep");
 }
 

@@ -1,0 +1,81 @@
+"""7-Scenes front end: the loader against outputs of the reference's own LoadSevenScenes on the same synthetic files
+(tests/golden/sevenscenes_loader.npz, made by oracle/make_golden_sevenscenes.py), and the evaluation driver end to end."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+from cnmnet_b200 import sevenscenes  # noqa: E402
+from make_golden_sevenscenes import write_sequence  # noqa: E402
+
+
+def test_loader_matches_reference_class(tmp_path, golden_dir):
+    g = np.load(os.path.join(golden_dir, "sevenscenes_loader.npz"))
+    write_sequence(str(tmp_path))                                   # same seed -> the same files the fixture was made from
+    loader = sevenscenes.LoadSevenScenes(str(tmp_path))
+    assert ["%s/%s" % t for t in loader.test_seqs_list] == list(g["test_seqs"])
+    assert np.array_equal(loader.intrinsics, g["intrinsics"])
+    paths = loader.get_filepaths("chess", "seq-03")
+    assert len(paths) == int(g["num_frames"]) and [p["pred_depth_name"] for p in paths] == list(g["names"])
+    for i, sp in enumerate(paths):
+        rgb, depth, cam, name = loader.load_sample(sp, 24, 32)
+        assert rgb.dtype == torch.float32 and tuple(rgb.shape) == (3, 24, 32) and tuple(depth.shape) == (48, 64)
+        assert np.array_equal(rgb.numpy(), g["rgb%d" % i])
+        assert np.array_equal(depth.numpy(), g["depth%d" % i])
+        assert np.array_equal(cam.numpy(), g["cam%d" % i])
+    frames, gts, cams, names = loader.load_sequence("chess", "seq-03", 24, 32)
+    assert tuple(frames.shape) == (4, 3, 24, 32) and tuple(cams.shape) == (4, 2, 4, 4) and len(gts) == 4
+
+
+def test_stored_depth_matches_eval():
+    """eval.py:493-494: np.reciprocal(idepth + 1e-4), values above 100 zeroed."""
+    idepth = np.array([2.5, 0.5, 1e-3, 5e-3, 1e-5], dtype=np.float32)
+    want = np.reciprocal(idepth + 1e-4)
+    want[want > 100] = 0
+    got = sevenscenes.stored_depth(torch.from_numpy(1.0 / idepth)).numpy()
+    assert np.allclose(got, want, rtol=1e-5)
+
+
+def test_missing_file_raises(tmp_path):
+    loader = sevenscenes.LoadSevenScenes(str(tmp_path))
+    with pytest.raises(FileNotFoundError):
+        loader.load_sample({"rgb": str(tmp_path / "nope.color.png"), "depth": "", "pose": "", "pred_depth_name": ""}, 24, 32)
+
+
+@pytest.mark.gpu
+def test_evaluate_runs_the_pipeline_and_scores_like_cal_metrics(tmp_path):
+    """A 36-frame synthetic sequence through evaluate(): frame selection of eval_refine, stored-depth formula, resize to
+    the ground-truth size and the GPU metrics -- against the same steps done by hand with the numpy oracle of the metrics."""
+    import cv2
+    import cnmnet_b200
+    from cnmnet_b200 import synth
+    from oracle import metrics as omet
+    from oracle import nets as onets
+    dev = torch.device("cuda", 0)
+    write_sequence(str(tmp_path), frames=36, h=96, w=128, seed=3)
+    dnet = cnmnet_b200.depthNet(idepth_scale=3.0)
+    rnet = cnmnet_b200.DepthRefineNet(idepth_scale=3.0)
+    dnet.load_state_dict(synth.kaiming_state(onets.state_shapes(onets.DEPTHNET_LAYERS), 5, 0.02))
+    rnet.load_state_dict(synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), 6, 0.02))
+    pipe = cnmnet_b200.CNMPipeline(dnet.to(dev), rnet.to(dev))
+    means, rows = sevenscenes.evaluate(pipe, str(tmp_path), sequences=[("chess", "seq-03")], image_height=64,
+                                       image_width=96, batch=2)
+    assert [r[2] for r in rows] == [12, 15, 18, 21, 24]          # every 3rd frame of [10, 26)
+    loader = sevenscenes.LoadSevenScenes(str(tmp_path))
+    frames, gts, cams, _ = loader.load_sequence("chess", "seq-03", 64, 96)
+    i = 15
+    rep = lambda t: t.expand(2, *t.shape[1:]).contiguous().to(dev)      # the batch shape evaluate() ran (same plan)
+    d, _, _ = pipe(rep(frames[i:i + 1]), rep(torch.stack((frames[i + 10], frames[i - 10]))[None]),
+                   rep(cams[i:i + 1]), rep(torch.stack((cams[i + 10], cams[i - 10]))[None]))
+    pred = cv2.resize(sevenscenes.stored_depth(d[0].cpu()).numpy(), (128, 96), interpolation=cv2.INTER_LINEAR)
+    want = omet.image_metrics(pred, gts[i].numpy())
+    got = dict(zip(cnmnet_b200.metrics.NAMES, rows[1][3:]))
+    for k, v in want.items():
+        if k in got:
+            assert abs(got[k] - v) <= 1e-5 * max(1.0, abs(v)), (k, got[k], v)
+    assert set(means) == set(cnmnet_b200.metrics.NAMES)
