@@ -72,6 +72,21 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// mbarrier wait that does not burn issue slots: try_wait with a suspend-time hint parks the warp in hardware, the
+// nanosleep backs the retry off (the profile of the plain spin loop showed 10 % of all issued instructions in it)
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+    __nanosleep(64);
+  }
+}
+
 // one fp32 from shared memory at a byte address + immediate (all 12 taps of a sample hang off one address register)
 template <int IMM>
 __device__ __forceinline__ float lds(uint32_t addr) {
@@ -94,7 +109,7 @@ __device__ __forceinline__ void sweep_position(float a0, float a1, float a2, flo
 }
 
 // one output from global memory with per-tap predicates (groups whose footprint does not fit a box)
-__device__ __noinline__ float sweep_gather_global(const float* __restrict__ sp, int H, int W, float ix, float iy,
+__device__ __forceinline__ float sweep_gather_global(const float* __restrict__ sp, int H, int W, float ix, float iy,
                                                      float r0, float r1, float r2) {
   ix = fminf(fmaxf(ix, -1.0f), (float)W);  // NaN -> -1: all four taps outside
   iy = fminf(fmaxf(iy, -1.0f), (float)H);
@@ -193,8 +208,10 @@ __device__ __forceinline__ void sweep_group(const SweepParams& p, const SweepPix
     const int n = n0 + sub;
     const int st = n % PS_STAGES;
     const int4 bi = c.flat[n];
-    mbar_wait(c.bar0 + 8u * st, (uint32_t)(n / PS_STAGES) & 1u);  // the box has landed (or the segment has none)
-    if (bi.z >= 0) {
+    mbar_wait_parked(c.bar0 + 8u * st, (uint32_t)(n / PS_STAGES) & 1u);  // the box has landed (or the segment has none)
+    // a group runs at a level above the finest only if all its segments have a box: the global-memory path exists in
+    // the one-plane-per-box instantiation only
+    if (S > 1 || bi.z >= 0) {
       // x0 in [floor(ix) - 1, floor(ix)], taps x0 and x0 + 1: ix in [ox + 1, ox + BW - 2) keeps them inside the box
       const float cx_lo = fmaxf(-1.0f, (float)(bi.x + 1)), cx_hi = fminf((float)W, (float)(bi.x + PS_BW - 3));
       const float cy_lo = fmaxf(-1.0f, (float)(bi.y + 1)), cy_hi = fminf((float)H, (float)(bi.y + ps_bh(bi.z) - 3));
@@ -227,7 +244,7 @@ __device__ __forceinline__ void sweep_group(const SweepParams& p, const SweepPix
 __device__ __forceinline__ void sweep_produce(const SweepParams& p, const SweepCtx& c, int pair) {
   for (int n = 0; n < c.nflat; ++n) {
     const int st = n % PS_STAGES;
-    if (n >= PS_STAGES) mbar_wait(c.bar0 + 8u * (PS_STAGES + st), (uint32_t)(n / PS_STAGES - 1) & 1u);
+    if (n >= PS_STAGES) mbar_wait_parked(c.bar0 + 8u * (PS_STAGES + st), (uint32_t)(n / PS_STAGES - 1) & 1u);
     const int4 bi = c.flat[n];
     const uint32_t full = c.bar0 + 8u * st;
     if (bi.z < 0) {

@@ -74,6 +74,23 @@ def load_reference():
     return ns
 
 
+class cpu_mode:
+    """Context manager for running the reference on the CPU of a box that HAS a GPU: the reference allocates
+    torch.cuda.FloatTensor in get_pixel_coordinates / getVolume (depth_util.py:20,53-54; depthNet_model.py:199,204);
+    while active that name is aliased to torch.FloatTensor, as load_reference() does permanently on CPU-only boxes."""
+
+    def __enter__(self):
+        import torch
+        self._saved = torch.cuda.FloatTensor
+        torch.cuda.FloatTensor = torch.FloatTensor
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.cuda.FloatTensor = self._saved
+        return False
+
+
 def reset_pixel_cache(ns):
     """The reference caches a pixel grid in a module global keyed on height only."""
     ns._iw.pixel_coords = None

@@ -77,5 +77,8 @@ def test_evaluate_runs_the_pipeline_and_scores_like_cal_metrics(tmp_path):
     got = dict(zip(cnmnet_b200.metrics.NAMES, rows[1][3:]))
     for k, v in want.items():
         if k in got:
-            assert abs(got[k] - v) <= 1e-5 * max(1.0, abs(v)), (k, got[k], v)
+            # ground truth in whole millimetres puts pixels exactly on the 0.3 m validity bound, where the fp32 kernel
+            # and the fp64 oracle may disagree about a handful of pixels: the flow is what is checked here, the
+            # reductions themselves are pinned by tests/golden/depth_metrics.npz
+            assert abs(got[k] - v) <= 1e-3 * max(1.0, abs(v)), (k, got[k], v)
     assert set(means) == set(cnmnet_b200.metrics.NAMES)

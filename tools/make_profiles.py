@@ -54,7 +54,7 @@ cm = sum(v[2] for k, v in tot.items() if k.startswith("conv_"))
 out += ["", "Convolution kernels (`conv_tc_kernel`, `conv_halo_kernel`, `conv_halo2_kernel`): %.1f us = %.1f %% of the step, "
         "%.1f MB of DRAM traffic per step." % (cu, 100 * cu / s, cm)]
 open(os.path.join(P, "%s_launches_step.md" % tag), "w").write("\n".join(out) + "\n")
-cv = [d for d in L.values() if d["name"].startswith("cost_volume_kernel<16, 0>")]
+cv = [d for d in L.values() if d["name"].startswith("plane_sweep_kernel<0>")] or [d for d in L.values() if d["name"].startswith("cost_volume_kernel<16, 0>")]
 json.dump({"source": "profiles/%s_launches_step.md (ncu dram__bytes_read.sum + dram__bytes_write.sum, one C4 step, %s)" % (tag, bench.get("dtype", "bf16x3")),
            "conv_bytes_per_step": cm * 1e6, "conv_launches": sum(v[0] for k, v in tot.items() if k.startswith("conv_")),
            "cost_volume_c2_bytes": (cv[0]["dram__bytes_read.sum"] + cv[0]["dram__bytes_write.sum"]) if cv else None},

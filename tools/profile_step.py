@@ -28,9 +28,14 @@ torch.cuda.synchronize()
 lib, s = _lib.load(), _lib.stream_ptr()
 dplan = st["dplan"]
 vol = torch.empty((V * B, 64, H, W), dtype=torch.float32, device=dev)
-for _ in range(1):
-    _lib.check(lib.cnm_cost_volume(st["ref"].data_ptr(), dplan.tex.data_ptr(), dplan.hk.data_ptr(), vol.data_ptr(), B, V, H,
-                                   W, 64, 0.1, 3.0, _lib.VOLUME_NCHW_F32, 0, s))
+srcd = st["src"].view(V * B, 3, H, W)
+# the C2 cost-volume micro-benchmark (NCHW fp32): second-generation kernel, then the first-generation pair
+_lib.check(lib.cnm_plane_sweep(st["ref"].data_ptr(), srcd.data_ptr(), dplan.hk.data_ptr(), vol.data_ptr(), B, V, H, W, 64, 0.1,
+                               3.0, _lib.VOLUME_NCHW_F32, 0, s))
+tex = torch.empty((lib.cnm_packed_source_bytes(V * B, H, W),), dtype=torch.uint8, device=dev)
+_lib.check(lib.cnm_pack_source(srcd.data_ptr(), tex.data_ptr(), V * B, H, W, s))
+_lib.check(lib.cnm_cost_volume(st["ref"].data_ptr(), tex.data_ptr(), dplan.hk.data_ptr(), vol.data_ptr(), B, V, H, W, 64, 0.1,
+                               3.0, _lib.VOLUME_NCHW_F32, 0, s))
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("done", _lib.launch_count())
