@@ -261,9 +261,17 @@ def reference_gpu_block(dev, host, reps=5):
         mods2 = (ns, d2, r2, d2n)
 
         def fast():
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                dep, nrm, prob = reference_step(mods2, ref, srcs, ref_cam, src_cams)
-            return dep
+            # autocast around the two networks only: Depth2normal's batched LU has no bf16 kernel in torch
+            from oracle import ref_shim
+            ref_shim.reset_pixel_cache(ns)
+            with torch.no_grad():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    p1, ic1 = d2(ref, srcs[:, 0].contiguous(), ref_cam, src_cams[:, 0].contiguous())
+                    p2, ic2 = d2(ref, srcs[:, 1].contiguous(), ref_cam, src_cams[:, 1].contiguous())
+                    idr, prob = r2(idepth01=p1[0], idepth02=p2[0], iconv01=ic1, iconv02=ic2)
+                depth = torch.div(1.0, idr.float().squeeze(1))
+                normal, _ = d2n(depth, torch.inverse(ref_cam[:, 1, 0:3, 0:3]))
+            return depth
 
         try:
             ms_fast = ev(fast)

@@ -25,8 +25,10 @@
 //                  the box of group g+1 lands while group g is being sampled.
 //   sampling       per plane: 3 FMA (p = a z + kt), rcp + Newton, clamp into the box, integer / fraction split by
 //                  adding 1.5 * 2^23, 12 x LDS.32 at immediate offsets from one address, 14 FMA/ADD.
-//   fallback       a group whose box does not fit (large baselines, p_z changing sign, D > 128 ...) is sampled straight
-//                  from global memory with per-tap predicates -- same arithmetic, CTA-uniform branch.
+//   levels         a group whose 8-plane footprint does not fit the largest box (fast-moving footprints: wide baselines)
+//                  is cut into 2 x 4 or 4 x 2 planes per box; one that does not fit even then (extreme zoom, p_z
+//                  changing sign) is sampled straight from global memory with per-tap predicates -- same arithmetic,
+//                  CTA-uniform branch.
 //
 // Data layout   ref, src [.,3,H,W] fp32 planar (public NCHW);  z_d in kernel parameters (constant bank), evaluated in
 //               fp64 on the host like the reference's Python double;  out as in cost_volume.cu.
@@ -49,8 +51,8 @@ constexpr int PS_CONSUMER_WARPS = PS_TY, PS_THREADS = PS_TX * (PS_TY + 1);  // +
 constexpr int PS_OFF_GSTATE = PS_STAGES * PS_STAGE_BYTES + 64;
 constexpr int PS_OFF_GBASE = PS_OFF_GSTATE + PS_MAX_GROUPS * 16;
 constexpr int PS_OFF_NODES = PS_OFF_GBASE + 80;
-constexpr int PS_OFF_FLAT = PS_OFF_NODES + 15 * PS_MAX_GROUPS * 16;
-constexpr int PS_SMEM = PS_OFF_FLAT + 8 * PS_MAX_GROUPS * 16 + 1024;
+constexpr int PS_OFF_FLAT = PS_OFF_NODES + 7 * PS_MAX_GROUPS * 16;
+constexpr int PS_SMEM = PS_OFF_FLAT + 4 * PS_MAX_GROUPS * 16 + 1024;
 static_assert(2 * PS_STAGES * 8 <= 64, "barrier block");
 constexpr float PS_MAGIC = 12582912.0f;  // 1.5 * 2^23: (v + MAGIC) has integer spacing, low mantissa bits = round(v)
 constexpr uint32_t PS_MAGIC_BITS = 0x4B400000u;
@@ -209,9 +211,9 @@ __device__ __forceinline__ void sweep_group(const SweepParams& p, const SweepPix
     const int st = n % PS_STAGES;
     const int4 bi = c.flat[n];
     mbar_wait_parked(c.bar0 + 8u * st, (uint32_t)(n / PS_STAGES) & 1u);  // the box has landed (or the segment has none)
-    // a group runs at a level above the finest only if all its segments have a box: the global-memory path exists in
-    // the one-plane-per-box instantiation only
-    if (S > 1 || bi.z >= 0) {
+    // a group whose footprint does not fit a box even at 2 planes per box (extreme zoom, p_z changing sign) is ONE
+    // 8-plane segment without a box, sampled from global memory: only the S = 8 instantiation carries that path
+    if (S < 8 || bi.z >= 0) {
       // x0 in [floor(ix) - 1, floor(ix)], taps x0 and x0 + 1: ix in [ox + 1, ox + BW - 2) keeps them inside the box
       const float cx_lo = fmaxf(-1.0f, (float)(bi.x + 1)), cx_hi = fminf((float)W, (float)(bi.x + PS_BW - 3));
       const float cy_lo = fmaxf(-1.0f, (float)(bi.y + 1)), cy_hi = fminf((float)H, (float)(bi.y + ps_bh(bi.z) - 3));
@@ -298,10 +300,10 @@ __global__ void __launch_bounds__(PS_THREADS, 3) plane_sweep_kernel(const __grid
   if (tid == 0) gbase[PS_MAX_GROUPS] = 0;                        // "some group needs a finer level"
   __syncthreads();
 
-  // ---- source boxes.  Level L cuts the D planes into segments of S = 8 >> L planes; segment nodes are numbered level
-  // by level (G, 2G, 4G, 8G of them).  One task = (node, tile corner): the corner's sample position at the segment's
-  // first and last plane; four neighbouring lanes reduce to the bounding box.  Level 0 first (one warp); the finer
-  // levels are only evaluated for tiles whose 8-plane footprints do not fit (large baselines).
+  // ---- source boxes.  Level L (0, 1, 2) cuts the D planes into segments of S = 8 >> L planes; segment nodes are
+  // numbered level by level (G, 2G, 4G of them).  One task = (node, tile corner): the corner's sample position at the
+  // segment's first and last plane; four neighbouring lanes reduce to the bounding box.  Level 0 first (two warps); the
+  // finer levels are only evaluated for tiles with a group whose 8-plane footprint does not fit (large baselines).
   auto box_tasks = [&](int node_begin, int node_end) {
     const int x_lo = blockIdx.x * PS_TX, y_lo = blockIdx.y * PS_TY;
     const int corner = tid & 3;
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(PS_THREADS, 3) plane_sweep_kernel(const __grid
       const int node = n0 + (tid >> 2);
       const bool live = node < node_end;
       const int nn = live ? node : node_end - 1;
-      const int level = (nn >= G) + (nn >= 3 * G) + (nn >= 7 * G);
+      const int level = (nn >= G) + (nn >= 3 * G);
       const int j = nn - G * ((1 << level) - 1), S = PS_DP >> level;
       const float z0 = p.z[j * S], z1 = p.z[j * S + S - 1];
       const float d0 = fmaf(a2, z0, px.k2e), d1 = fmaf(a2, z1, px.k2e);
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(PS_THREADS, 3) plane_sweep_kernel(const __grid
         int idx = -1;
         if (oki && wneed <= PS_BW) idx = hneed <= ps_bh(0) ? 0 : (hneed <= ps_bh(1) ? 1 : (hneed <= ps_bh(2) ? 2 : -1));
         seg[node] = make_int4(ox, oy, idx, j * S);
-        if (idx < 0 && level < 3) {
+        if (idx < 0) {
           reinterpret_cast<int*>(&gstate[j >> level])[level] = 0;  // group of 8 planes this segment belongs to
           if (level == 0) gbase[PS_MAX_GROUPS] = 1;
         }
@@ -366,23 +368,28 @@ __global__ void __launch_bounds__(PS_THREADS, 3) plane_sweep_kernel(const __grid
   }
   __syncthreads();
   if (gbase[PS_MAX_GROUPS]) {  // CTA-uniform
-    if (consumer) box_tasks(G, 15 * G);
+    if (consumer) box_tasks(G, 7 * G);
     __syncthreads();
   }
-  // flat segment list: group g runs at the coarsest level whose segments all have a box (level 3 = one plane per box;
-  // what still has none there is sampled from global memory)
+  // flat segment list: group g runs at the coarsest level (8, 4 or 2 planes per box) whose segments all have a box; a
+  // group that has none even at 2 planes per box becomes one box-less segment of 8 planes (global-memory path)
   if (tid < G) {
     int first = 0;
     for (int hgrp = 0; hgrp <= tid; ++hgrp) {
       const int4 gs = gstate[hgrp];
       const int lv = gs.x ? 0 : (gs.y ? 1 : (gs.z ? 2 : 3));
+      const int cnt = lv == 3 ? 1 : (1 << lv);
       if (hgrp == tid) {
         gstate[tid].w = lv;
         gbase[tid] = first;
-        const int4* src_nodes = seg + G * ((1 << lv) - 1) + (tid << lv);
-        for (int k = 0; k < (1 << lv); ++k) flat[first + k] = src_nodes[k];
+        if (lv == 3) {
+          flat[first] = make_int4(0, 0, -1, tid * PS_DP);
+        } else {
+          const int4* src_nodes = seg + G * ((1 << lv) - 1) + (tid << lv);
+          for (int k = 0; k < cnt; ++k) flat[first + k] = src_nodes[k];
+        }
       }
-      first += 1 << lv;
+      first += cnt;
     }
     if (tid == G - 1) gbase[PS_MAX_GROUPS] = first;  // number of flat segments
   }
@@ -401,10 +408,9 @@ __global__ void __launch_bounds__(PS_THREADS, 3) plane_sweep_kernel(const __grid
   for (int g = 0; g < G; ++g) {
     float res[PS_DP];
     const int lv = gstate[g].w, n0 = gbase[g];
-    if (lv == 0) sweep_group<8>(p, px, c, n0, lane, res);
+    if (lv == 0 || lv == 3) sweep_group<8>(p, px, c, n0, lane, res);
     else if (lv == 1) sweep_group<4>(p, px, c, n0, lane, res);
-    else if (lv == 2) sweep_group<2>(p, px, c, n0, lane, res);
-    else sweep_group<1>(p, px, c, n0, lane, res);
+    else sweep_group<2>(p, px, c, n0, lane, res);
     if (px.active) sweep_store8<LAYOUT>(p, px, g * PS_DP, res);
   }
 }

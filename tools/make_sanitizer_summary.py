@@ -1,0 +1,28 @@
+"""profiles/<tag>_sanitizer.md from the logs tools/sanitize.sh left in gpurun_out/."""
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+G = os.path.join(ROOT, "gpurun_out")
+out = ["# %s compute-sanitizer runs (tools/sanitize.sh)" % tag, ""]
+head = os.path.join(G, "sanitize_head.txt")
+if os.path.exists(head):
+    out += ["Build under test:", "", "```"] + open(head).read().strip().splitlines() + ["```", ""]
+out += ["| pass | tests | pytest result | sanitizer summary |", "|---|---|---|---|"]
+for name, what in (("memcheck_conv.log", "memcheck: tests/test_gpu_conv.py + tests/test_gpu_kernels.py"),
+                   ("memcheck_nets.log", "memcheck: tests/test_gpu_nets.py (without the full-size headline cases)"),
+                   ("initcheck.log", "initcheck: __graft_entry__.smoke()"),
+                   ("racecheck.log", "racecheck: non-TMA shared-memory kernels (normals, CNM, packers, upsample, ...)")):
+    p = os.path.join(G, name)
+    if not os.path.exists(p):
+        out.append("| %s | %s | (log missing) | |" % (name, what))
+        continue
+    txt = open(p, errors="replace").read()
+    res = re.findall(r"^(?:=+ )?(\d+ (?:passed|failed).*?)(?: =+)?$", txt, re.M)
+    smoke = re.findall(r"^smoke: .*$", txt, re.M)
+    summ = re.findall(r"^========= (ERROR SUMMARY.*|RACECHECK SUMMARY.*|Error: .*)$", txt, re.M)
+    out.append("| %s | %s | %s | %s |" % (name, what, "; ".join(res + smoke) or "-", "; ".join(summ) or "-"))
+open(os.path.join(ROOT, "profiles", "%s_sanitizer.md" % tag), "w").write("\n".join(out) + "\n")
+print("\n".join(out))

@@ -1,15 +1,30 @@
 #!/bin/bash
-# compute-sanitizer passes over the GPU parity tests (run on a B200 box, e.g. through gpurun).  memcheck changes kernel
-# timing enough to expose ordering bugs that the plain runs hide: round 1 found a missing barrier between staging the
-# bias in shared memory and the epilogue's first read of it this way (test_fused_head failed only under memcheck).
+# compute-sanitizer passes over the GPU parity tests (run on a B200 box through gpurun; ~12 GPU-minutes).  Logs go to
+# gpurun_out/ and their summaries are committed as profiles/<tag>_sanitizer.md by tools/make_sanitizer_summary.py.
+#   memcheck   all convolution / kernel tests and the network tests (minus the full-size headline cases, whose CPU
+#              oracle dominates; their kernels and plans are the ones the smaller cases run)
+#   initcheck  smoke()
+#   racecheck  the shared-memory kernels WITHOUT TMA / tcgen05 (normals, CNM, packers, upsample, heads, metrics,
+#              losses): racecheck does not model the async proxy (TMA writes, tcgen05 reads of shared memory), so the
+#              tensor-core convolutions, the TMA-staged head kernel and the plane sweep are outside what it can check
+# memcheck changes kernel timing enough to expose ordering bugs that the plain runs hide: round 1 found a missing
+# barrier between staging the bias in shared memory and the epilogue's first read of it this way.
 set -u
 mkdir -p gpurun_out
-timeout 1500 compute-sanitizer --tool memcheck --print-limit 10 \
+git rev-parse HEAD > gpurun_out/sanitize_head.txt 2>/dev/null || echo "snapshot (no .git on the box)" > gpurun_out/sanitize_head.txt
+date -u +%Y-%m-%dT%H:%M:%SZ >> gpurun_out/sanitize_head.txt
+sha256sum cnmnet_b200/libcnmnet_b200.so >> gpurun_out/sanitize_head.txt
+timeout 1200 compute-sanitizer --tool memcheck --print-limit 10 \
     python -m pytest tests/test_gpu_conv.py tests/test_gpu_kernels.py -m gpu -q > gpurun_out/memcheck_conv.log 2>&1
 tail -3 gpurun_out/memcheck_conv.log
-CNM_AUTOTUNE=0 timeout 2400 compute-sanitizer --tool memcheck --print-limit 10 \
-    python -m pytest tests/test_gpu_nets.py -m gpu -q > gpurun_out/memcheck_nets.log 2>&1
+timeout 1800 compute-sanitizer --tool memcheck --print-limit 10 \
+    python -m pytest tests/test_gpu_nets.py -m gpu -q -k "not headline and not bit_identical" > gpurun_out/memcheck_nets.log 2>&1
 tail -3 gpurun_out/memcheck_nets.log
 timeout 600 compute-sanitizer --tool initcheck --print-limit 10 \
     python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/initcheck.log 2>&1
 tail -2 gpurun_out/initcheck.log
+timeout 900 compute-sanitizer --tool racecheck --print-limit 10 \
+    python -m pytest tests/test_gpu_kernels.py -m gpu -q \
+    -k "normals or cnm or refine_aggregate or upsample or pack or metrics or losses or reciprocal or inverse_warp" \
+    > gpurun_out/racecheck.log 2>&1
+tail -3 gpurun_out/racecheck.log
