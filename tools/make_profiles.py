@@ -27,11 +27,11 @@ bp = os.path.join(G, "bench.json")
 if os.path.exists(bp):
     bench = json.load(open(bp))
 out = ["# %s launch list of one pipeline step" % tag, "",
-       "Command: `CNM_TUNE_CACHE=gpurun_out/tune_cache.json ncu --profile-from-start off --metrics "
+       "Command: `ncu --profile-from-start off --metrics "
        "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv python tools/profile_step.py`",
        "(one un-graphed C4 step, %s mode, B=5 x 2 source views, 256x192x64, after one warm-up step; conv kernel / tile choices" % bench.get("dtype", "bf16x3"),
-       "come from the autotuner cache written by the preceding `bench.py` run; the last `cost_volume_kernel<16,0>` launch is the C2",
-       "NCHW fp32 micro-benchmark).  Times are cold-cache and serialised by ncu: compare SHARES, not absolutes (the same step",
+       "come from the shipped table cnmnet_b200/tune/b200.json; the last `plane_sweep_kernel<0>` and `cost_volume_kernel<16,0>` launches are",
+       "the C2 NCHW fp32 micro-benchmark of K1, second and first generation).  Times are cold-cache and serialised by ncu: compare SHARES, not absolutes (the same step",
        "replayed as a CUDA graph takes %.2f ms in bench.py)." % bench.get("ms_per_step", float("nan")), "",
        "| # | kernel | grid | us | DRAM read+write MB |", "|---|---|---|---|---|"]
 tot = collections.OrderedDict()
@@ -61,7 +61,7 @@ json.dump({"source": "profiles/%s_launches_step.md (ncu dram__bytes_read.sum + d
           open(os.path.join(P, "%s_traffic.json" % tag), "w"), indent=1)
 
 # ---- full-set captures ----
-PICKS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+PICKS = ["gpu__time_duration.sum", "launch__grid_size", "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
          "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
          "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum",
          "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed",
@@ -87,6 +87,21 @@ def dump(rep, outname, title, note):
     open(os.path.join(P, outname), "w").write("\n".join(lines))
 
 
+if "--full" in sys.argv:
+  dump("prof_k1.ncu-rep", "%s_plane_sweep_ncu.md" % tag,
+     "%s ncu --set full: plane_sweep_kernel (K1, TMA-staged plane sweep)" % tag,
+     "Capture: `ncu --set full --clock-control none --import-source on -k regex:plane_sweep -o gpurun_out/prof_k1 python "
+     "tools/k1_profile.py`: C2 (256x192x64, 2 views, batch 5, fp32 NCHW, 134 676 480 algorithmic bytes), first launch with the "
+     "bench cameras (seed 1234), second with seed 77.  Reading: issue slots 65-73 % active and l1tex LSU wavefronts (shared-memory "
+     "taps, 1.5x the conflict-free count when the local zoom of the homography exceeds 1) 66-71 % of peak are the co-limiters; "
+     "DRAM 12 %, L2 20 %.")
+  dump("prof_c64.ncu-rep", "%s_conv_cout64_ncu.md" % tag,
+     "%s ncu --set full: the Cout = 64 full-resolution layers (conv_halo2_kernel<64> / conv_halo_kernel<64>)" % tag,
+     "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled -k "
+     "\"regex:conv_halo2?_kernel<\\(int\\)64\" -c 4 python tools/profile_step.py` (DepthNet upconv1.1, iconv1.0 with the fused "
+     "disp1 head, RefineNet upconv1_depth.1, iconv1_depth.0).  Reading: tensor pipe 33-49 % active -- with N = 64 an MMA step "
+     "reads 32 KB of A for 256 cycles of math (M = 256 pair), so the 128 B/clk shared-memory port (A reads + slab fills + "
+     "staging) bounds these layers, not the tensor pipe; see DESIGN.md section 3.")
 if "--full" in sys.argv:
   dump("prof_halo.ncu-rep", "%s_conv_halo_ncu.md" % tag,
      "%s ncu --set full: conv_halo_kernel / conv_halo2_kernel (row-halo tcgen05 conv, 1-SM and CTA-pair)" % tag,
