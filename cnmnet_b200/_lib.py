@@ -30,6 +30,12 @@ class ConvDesc(C.Structure):
                 ("head_partial", C.c_void_p), ("splitk_ws", C.c_void_p)]
 
 
+class SweepFuse(C.Structure):
+    _fields_ = [("ref", C.c_void_p), ("packed_src", C.c_void_p), ("hk", C.c_void_p), ("scratch", C.c_void_p),
+                ("scratch_bytes", C.c_int64), ("B", C.c_int32), ("D", C.c_int32), ("vol_src", C.c_int32),
+                ("reserved", C.c_int32), ("idepth_min", C.c_double), ("idepth_max", C.c_double)]
+
+
 _P, _I, _D, _F, _L = C.c_void_p, C.c_int, C.c_double, C.c_float, C.c_int64
 
 # name -> (restype, argtypes); must list every function declared in include/cnmnet_b200.h
@@ -69,6 +75,9 @@ SIGNATURES = {
     "cnm_conv2d_simt": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
     "cnm_conv2d_halo": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P, _P]),
     "cnm_conv2d_halo2": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P, _P]),
+    "cnm_sweep_scratch_bytes": (_L, [_I, _I]),
+    "cnm_conv2d_halo2_sweep": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P,
+                                    C.POINTER(SweepFuse), _P]),
     "cnm_inverse_warp": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
 }
 

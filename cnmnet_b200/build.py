@@ -26,7 +26,7 @@ def _stale(obj, deps):
 
 
 def build(force=False, verbose=False):
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "cnmnet_b200.h")]
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "sweep_l1.cuh"), os.path.join(os.path.dirname(HERE), "include", "cnmnet_b200.h")]
     objs = []
     procs = []
     for src in SOURCES:

@@ -29,6 +29,7 @@
 //   * both CTAs run the epilogue on their own TMEM half; "accumulator empty" arrivals go to the leader's barrier.
 #include <cstring>
 
+#include "sweep_l1.cuh"
 #include "tc_common.cuh"
 
 namespace cnm {
@@ -36,6 +37,30 @@ namespace cnm {
 constexpr int HL_MAX_SRCS = 3;
 constexpr int HL_TILE_BYTES = 128 * 128;
 constexpr int HL_MAX_A = 4, HL_MAX_B = 8;
+constexpr int HL_NUM_BARS = 2 * HL_MAX_A + 2 * HL_MAX_B + 4 + 2;  // A / B rings, accumulator full / empty, volume slots
+constexpr int HL_SWEEP_MAX_D = 128;
+constexpr int HL_SWEEP_THREADS = 256;  // volume-producer warps of the fused conv1.0 kernel (warps 8-15)
+// registers per thread of the three roles once the fused kernel has re-balanced its 64 K (x 128 threads each: control
+// warps 0-3, epilogue warps 4-7, two producer warpgroups).  ptxas allocates each role's code against its own limit.
+constexpr int HL_SWEEP_REGS_CTRL = 104, HL_SWEEP_REGS_EPI = 200, HL_SWEEP_REGS_PROD = 104;
+static_assert(HL_SWEEP_REGS_CTRL + HL_SWEEP_REGS_EPI + 2 * HL_SWEEP_REGS_PROD <= 512, "register file");
+constexpr int HL_SWEEP_PLANES = 16;  // planes per pass of a producer thread over its pixel
+
+// Fused plane sweep (SWEEP instantiations, cnm_conv2d_halo2_sweep): the cost-volume operand of conv1.0 never exists as a
+// tensor.  Producer warps compute, per 16x16 output tile, the (16+2p)^2 halo region of the volume straight in the act
+// layout into a per-CTA scratch slot (two slots per CTA, re-used every other tile: the lines stay in L2), and the A-slab
+// TMA producer boxes its slabs out of that slot instead of out of a [P,H,W,D] tensor.
+struct SweepFuseParams {
+  CUtensorMap map;       // scratch as [2 * gridDim.x slots][R][R][2 D physical channels], box {64, 16, R, 1}
+  const float* ref;      // [B,3,H,W] fp32
+  const float4* tex;     // packed source views (cnm_pack_source)
+  const float* hk;       // [P,12]
+  uint8_t* scratch;
+  double idmin, idstep;
+  int B, D, H, W;
+  int vol_map;           // the a_maps index (source * 4) the scratch stands in for
+  int pad;               // rows / columns of the region above / left of the tile ((k - 1) / 2)
+};
 
 struct alignas(64) HaloParams {
   CUtensorMap a_maps[HL_MAX_SRCS * 4];  // [source][parity sub-image]
@@ -57,6 +82,7 @@ struct alignas(64) HaloParams {
   const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
   float* head_partial;   // [Cout/64 slices][N, Ho, Wo, 12] per-pixel tap dot products, one slice per 64-channel chunk
   int Ho, Wo, cout;
+  SweepFuseParams sw;    // SWEEP instantiations only
 };
 
 // ---- 2-CTA PTX wrappers --------------------------------------------------------------------------------------
@@ -113,8 +139,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 
 // CG = 1: one CTA per 16x16 pixel block, two MMA-issuing warps (one per half of the block).  CG = 2: a CTA pair on two
 // neighbouring blocks, one M = 256 MMA per half issued by the leader.
-template <int BN, bool TF32, int CG>
+template <int BN, bool TF32, int CG, bool SWEEP = false>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
+  static_assert(!SWEEP || (!TF32 && 4 * BN <= 512), "the fused plane sweep needs two accumulator stages (BN <= 128)");
   constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;
   constexpr int CHUNK_CH = TF32 ? 32 : 64;
   constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
@@ -144,11 +171,13 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   auto emptyB = [&](int s) { return bar0 + 8u * (2 * HL_MAX_A + HL_MAX_B + s); };
   auto tfull = [&](int a) { return bar0 + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + a); };
   auto tempty = [&](int a) { return bar0 + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + 2 + a); };
-  const uint32_t off_tmem = off_bar + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + 4);
+  auto vfull = [&](int s) { return bar0 + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + 4 + s); };  // SWEEP: volume slot s is written
+  const uint32_t off_tmem = off_bar + 8u * HL_NUM_BARS;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
+  float* zs = reinterpret_cast<float*>(base_ptr + off_tmem + 16);  // SWEEP: z_d of the D planes
   float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
   float* head_s = reinterpret_cast<float*>(base_ptr + off_head);
-  const bool fused_head = !TF32 && p.head_partial != nullptr;
+  const bool fused_head = !TF32 && !SWEEP && p.head_partial != nullptr;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -169,6 +198,8 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), ISSUERS); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), ISSUERS); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), ISSUERS); mbar_init(tempty(a), 128u * CG); }
+    if (SWEEP)
+      for (int a = 0; a < 2; ++a) mbar_init(vfull(a), HL_SWEEP_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -188,6 +219,14 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (SWEEP) {
+    // 512 threads share the register file at 128 each; the epilogue warpgroup needs ~200 (64 accumulator columns in
+    // flight per thread), the TMA / MMA warps and the volume producers less: re-balance per warpgroup
+    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HL_SWEEP_REGS_CTRL));
+    else if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HL_SWEEP_REGS_EPI));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HL_SWEEP_REGS_PROD));
+  }
+
   if (warp == 0) {
     // ================= TMA producer, A slabs =================
     // (separate from the B producer so that slab requests run a_stages groups ahead regardless of the B ring depth)
@@ -195,12 +234,14 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       int sa = 0;
       uint32_t pa = 0;
       int4 g_next = __ldg(reinterpret_cast<const int4*>(p.groups));
-      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+      int it = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
         int m = CG * (tile / p.tiles_n) + (int)rank;
         const int x0 = (m % p.tiles_x) * 16;
         m /= p.tiles_x;
         const int y0 = (m % p.tiles_y) * 16;
         const int n0 = m / p.tiles_y;
+        bool vol_ready = false;
         for (int g = 0; g < p.num_groups; ++g) {
           const int4 gr = g_next;  // src, c0, dx, ntaps
           g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == p.num_groups) ? 0 : g + 1)));
@@ -208,8 +249,20 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
           const uint32_t slab_tx = (uint32_t)p.map_rows[gr.x] * 2048u;
           mbar_wait(emptyA(sa), pa ^ 1);
           if (leader) mbar_expect_tx(fullA(sa), (uint32_t)CG * slab_tx);  // CG = 2: both CTAs' slabs
-          if (CG == 2) tma2_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
-          else tma_load_4d(base + sa * p.slab_bytes, &p.a_maps[gr.x], fullA(sa), gr.y, x0 + gr.z, y0 - pad, n0);
+          const CUtensorMap* map = &p.a_maps[gr.x];
+          int c1 = x0 + gr.z, c2 = y0 - pad, c3 = n0;
+          if (SWEEP && gr.x == p.sw.vol_map) {
+            // the tile's region of the volume sits in this CTA's scratch slot (written by warps 8-15): columns
+            // dx + pad ... of the region, all rows
+            if (!vol_ready) {
+              mbar_wait(vfull(it & 1), (uint32_t)(it >> 1) & 1u);
+              vol_ready = true;
+            }
+            map = &p.sw.map;
+            c1 = gr.z + p.sw.pad; c2 = 0; c3 = (int)blockIdx.x * 2 + (it & 1);
+          }
+          if (CG == 2) tma2_load_4d(base + sa * p.slab_bytes, map, fullA(sa), gr.y, c1, c2, c3);
+          else tma_load_4d(base + sa * p.slab_bytes, map, fullA(sa), gr.y, c1, c2, c3);
           if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         }
       }
@@ -301,7 +354,66 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
+  } else if (SWEEP && warp >= 8) {
+    // ================= fused plane sweep: volume producers =================
+    // Per tile: the (16 + 2 pad)^2 region of the cost volume around it, one pixel per thread and pass, all D planes, in
+    // the act layout (CNM_F16F8 rows: fp16 | lo8 | hi8), zeros outside the image (= the convolution's padding).  Slot
+    // it & 1 is free again when the MMAs of tile it - 2 have completed (their commit on the accumulator-full barrier of
+    // stage it & 1 also covers the TMA reads of that slot).
+    const int pt = (int)threadIdx.x - 256;
+    const SweepFuseParams& sw = p.sw;
+    const int D = sw.D, H = sw.H, W = sw.W;
+    const int R = 16 + 2 * sw.pad, npx = R * R;
+    const size_t px_bytes = (size_t)D * 4;  // 2 D physical 2-byte channels
+    const size_t HW = (size_t)H * W;
+    for (int i = pt; i < D; i += HL_SWEEP_THREADS) zs[i] = sweep_plane_z(sw.idmin, sw.idstep, i);
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    int it = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+      int m = CG * (tile / p.tiles_n) + (int)rank;
+      const int x0 = (m % p.tiles_x) * 16;
+      m /= p.tiles_x;
+      const int y0 = (m % p.tiles_y) * 16;
+      const int n0 = m / p.tiles_y;
+      const int slot = it & 1;
+      if (it >= 2) {
+        if (lane == 0) mbar_wait(tfull(slot), (uint32_t)((it - 2) >> 1) & 1u);
+        __syncwarp();
+      }
+      uint8_t* sc = sw.scratch + ((size_t)((int)blockIdx.x * 2 + slot) * npx) * px_bytes;
+      const float* h = sw.hk + (size_t)n0 * 12;
+      const float* rimg = sw.ref + (size_t)(n0 % sw.B) * 3 * HW;
+      SweepPixelL1 sp;
+      sp.pitch = W + 4;
+      sp.tp = sw.tex + (size_t)n0 * (H + 3) * sp.pitch + sp.pitch + 1;  // texel (0,0)
+      sp.xmax = (float)W; sp.ymax = (float)H;
+      for (int idx = pt; idx < npx; idx += HL_SWEEP_THREADS) {
+        const int ry = idx / R, rx = idx - ry * R;
+        const int x = x0 - sw.pad + rx, y = y0 - sw.pad + ry;
+        h16f8* row = reinterpret_cast<h16f8*>(sc + (size_t)idx * px_bytes);
+        if (x < 0 || x >= W || y < 0 || y >= H) {
+          uint4* z4 = reinterpret_cast<uint4*>(row);
+          for (int i = 0; i < (int)(px_bytes / 16); ++i) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+          continue;
+        }
+        sweep_l1_setup(sp, h, x, y);
+        const float* rp = rimg + (size_t)y * W + x;
+        sp.r0 = __ldg(rp); sp.r1 = __ldg(rp + HW); sp.r2 = __ldg(rp + 2 * HW);
+#pragma unroll 1
+        for (int d0 = 0; d0 < D; d0 += HL_SWEEP_PLANES) {
+          float res[HL_SWEEP_PLANES];
+#pragma unroll
+          for (int i = 0; i < HL_SWEEP_PLANES; ++i) res[i] = sweep_l1_sample(sp, zs[d0 + i]);
+          h16f8* o = row + ActTraits<h16f8>::phys(d0);
+#pragma unroll
+          for (int i = 0; i < HL_SWEEP_PLANES; i += 8) Vec16<h16f8>::store(o + i, res + i);
+        }
+      }
+      // generic-proxy writes -> visible to the TMA (async proxy) reads the A producer issues after its wait
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_arrive(vfull(slot));
+    }
+  } else if (warp >= 4 && warp < 8) {
     // ================= epilogue =================
     const int q = warp - 4;
     const int row = q * 32 + lane;
@@ -377,6 +489,11 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
+  if (SWEEP) {  // back to the launch allocation before the roles join
+    if (warp < 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    else if (warp < 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+  }
   tc_fence_before();
   if (CG == 2) cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its operands
   else __syncthreads();
@@ -396,6 +513,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   conv_halo_body<BN, TF32, 2>(p);
 }
 
+// conv1.0 with the plane sweep fused in: CTA pairs + eight volume-producer warps per CTA
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) conv_halo2_sweep_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, false, 2, true>(p);
+}
+
 template <int BN, bool TF32, int CG>
 static int launch_halo(const HaloParams& p, int grid, int smem, cudaStream_t s) {
   static DynSmemLimit limit;
@@ -412,11 +535,16 @@ static int launch_halo(const HaloParams& p, int grid, int smem, cudaStream_t s) 
 using namespace cnm;
 
 // Shared host side of cnm_conv2d_halo (CG = 1) and cnm_conv2d_halo2 (CG = 2)
+static int64_t sweep_scratch_bytes(int D, int k) {
+  const int64_t R = 16 + (k - 1);
+  return (int64_t)2 * 148 * R * R * 4 * D;  // two slots per CTA, a full grid of CTAs, 4 D bytes per pixel (CNM_F16F8)
+}
+
 template <int CG>
 static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* map_info,
                        const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
-                       void* stream) {
-  const char* fn = CG == 2 ? "cnm_conv2d_halo2" : "cnm_conv2d_halo";
+                       void* stream, const cnm_sweep_fuse* sweep = nullptr) {
+  const char* fn = sweep ? "cnm_conv2d_halo2_sweep" : (CG == 2 ? "cnm_conv2d_halo2" : "cnm_conv2d_halo");
   int rc = check_conv_args(fn, d, srcs, groups, wp, out);
   if (rc) return rc;
   CNM_REQUIRE(d->ksplit <= 1, CNM_ERR_UNSUPPORTED_SHAPE, "%s: split-K is a cnm_conv2d_tc feature", fn);
@@ -481,7 +609,39 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
   // lasts ntaps B tiles.
   p.out_stages = BN == 64 ? 2 : 1;
-  const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (d->head_partial ? 9 * BN * 4 : 0) + 8 * (2 * HL_MAX_A + 2 * HL_MAX_B + 4) + 16;
+  if (sweep) {
+    // the fused plane sweep: see SweepFuseParams.  One N tile (every tile computes its region of the volume once), two
+    // accumulator stages (the producers pace themselves on the accumulator-full barriers), CNM_F16F8 rows.
+    const int vs = sweep->vol_src;
+    CNM_REQUIRE(CG == 2 && d->stride == 1 && d->dtype == CNM_F16F8, CNM_ERR_UNSUPPORTED_SHAPE,
+                "%s: stride-1 CNM_F16F8 layers on CTA pairs only", fn);
+    CNM_REQUIRE(BN == d->Cout && BN <= 128, CNM_ERR_UNSUPPORTED_SHAPE, "%s: Cout=%d must be one tile of at most 128", fn, d->Cout);
+    CNM_REQUIRE(!d->head_partial, CNM_ERR_UNSUPPORTED_SHAPE, "%s: no fused head on this layer", fn);
+    CNM_REQUIRE(vs >= 0 && vs < d->num_srcs && p.map_rows[vs * 4] > 16, CNM_ERR_INVALID_ARGUMENT, "%s: vol_src %d", fn, vs);
+    CNM_REQUIRE(sweep->ref && sweep->packed_src && sweep->hk && sweep->scratch, CNM_ERR_INVALID_ARGUMENT, "%s: null pointer", fn);
+    CNM_REQUIRE(sweep->D >= 64 && sweep->D % 64 == 0 && sweep->D <= HL_SWEEP_MAX_D && srcs[vs].C == 2 * sweep->D,
+                CNM_ERR_UNSUPPORTED_SHAPE, "%s: D=%d planes (64 or 128) against %d physical channels", fn, sweep->D, srcs[vs].C);
+    CNM_REQUIRE(sweep->B > 0 && d->N % sweep->B == 0, CNM_ERR_INVALID_ARGUMENT, "%s: N=%d pairs, B=%d reference frames", fn, d->N, sweep->B);
+    const int pad = p.map_pad[vs * 4], R = 16 + 2 * pad;
+    CNM_REQUIRE(p.map_rows[vs * 4] == R, CNM_ERR_UNSUPPORTED_SHAPE, "%s: slab of %d rows for pad %d", fn, p.map_rows[vs * 4], pad);
+    CNM_REQUIRE(((uintptr_t)sweep->scratch & 127) == 0 && sweep->scratch_bytes >= sweep_scratch_bytes(sweep->D, 2 * pad + 1),
+                CNM_ERR_INVALID_ARGUMENT, "%s: scratch must be 128B aligned and hold cnm_sweep_scratch_bytes() = %lld bytes", fn,
+                (long long)sweep_scratch_bytes(sweep->D, 2 * pad + 1));
+    SweepFuseParams& sw = p.sw;
+    sw.ref = sweep->ref; sw.tex = (const float4*)sweep->packed_src; sw.hk = sweep->hk; sw.scratch = (uint8_t*)sweep->scratch;
+    sw.idmin = sweep->idepth_min;
+    sw.idstep = (sweep->idepth_max - sweep->idepth_min) / (double)(sweep->D - 1);
+    sw.B = sweep->B; sw.D = sweep->D; sw.H = d->Ho; sw.W = d->Wo;
+    sw.vol_map = vs * 4; sw.pad = pad;
+    const uint64_t pix = (uint64_t)sweep->D * 4;
+    const uint64_t dims[4] = {(uint64_t)2 * sweep->D, (uint64_t)R, (uint64_t)R, (uint64_t)2 * 148};
+    const uint64_t str[3] = {pix, pix * R, pix * R * R};
+    const uint32_t box[4] = {(uint32_t)ch, 16u, (uint32_t)R, 1u};
+    rc = encode_map(&sw.map, d->dtype, 4, sweep->scratch, dims, str, box);
+    if (rc) return rc;
+  }
+  const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (d->head_partial ? 9 * BN * 4 : 0) + 8 * HL_NUM_BARS + 16 +
+                    (sweep ? HL_SWEEP_MAX_D * 4 : 0);
   const int budget = 232448 - fixed;
   const int want_b = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 7 : 8));
   const int b_tile = BN * 128 / CG;   // bytes of one weight tile (CG = 2: this CTA's half)
@@ -509,6 +669,7 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     for (int sub = 0; sub < nsub; ++sub) {
       const int m = i * 4 + sub;
       if (p.map_rows[m] == 0) continue;
+      if (sweep && m == p.sw.vol_map) continue;  // the scratch map stands in for it
       const uint32_t box[4] = {(uint32_t)ch, 16u, (uint32_t)p.map_rows[m], 1u};
       if (d->stride == 1) {
         const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)d->N};
@@ -545,6 +706,14 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   const int grid = CG * (total < 148 / CG ? total : 148 / CG);
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
+  if (sweep) {
+    static DynSmemLimit limit64, limit128;
+    cudaError_t e = BN == 128 ? limit128.ensure(conv_halo2_sweep_kernel<128>, smem) : limit64.ensure(conv_halo2_sweep_kernel<64>, smem);
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
+    if (BN == 128) conv_halo2_sweep_kernel<128><<<grid, 512, smem, s>>>(p);
+    else conv_halo2_sweep_kernel<64><<<grid, 512, smem, s>>>(p);
+    return after_launch(fn);
+  }
   if (BN == 256) return tf32 ? launch_halo<256, true, CG>(p, grid, smem, s) : launch_halo<256, false, CG>(p, grid, smem, s);
   if (BN == 128) return tf32 ? launch_halo<128, true, CG>(p, grid, smem, s) : launch_halo<128, false, CG>(p, grid, smem, s);
   return tf32 ? launch_halo<64, true, CG>(p, grid, smem, s) : launch_halo<64, false, CG>(p, grid, smem, s);
@@ -560,4 +729,16 @@ extern "C" int cnm_conv2d_halo2(const cnm_conv_desc* d, const cnm_conv_src* srcs
                                 const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
                                 void* stream) {
   return conv2d_halo<2>(d, srcs, map_info, groups, num_groups, wp, bias, out, stream);
+}
+
+extern "C" int64_t cnm_sweep_scratch_bytes(int D, int k) {
+  if (D <= 0 || k < 1 || k > 9 || !(k & 1)) return 0;
+  return sweep_scratch_bytes(D, k);
+}
+
+extern "C" int cnm_conv2d_halo2_sweep(const cnm_conv_desc* d, const cnm_conv_src* srcs, const int32_t* map_info,
+                                      const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias,
+                                      void* out, const cnm_sweep_fuse* sweep, void* stream) {
+  CNM_REQUIRE(sweep, CNM_ERR_INVALID_ARGUMENT, "cnm_conv2d_halo2_sweep: null sweep descriptor");
+  return conv2d_halo<2>(d, srcs, map_info, groups, num_groups, wp, bias, out, stream, sweep);
 }

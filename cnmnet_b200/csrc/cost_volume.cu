@@ -20,6 +20,7 @@
 //                                                                                  expected anchor, 80 regs
 // The kernel is bound by L1 data-pipe wavefronts (a 32-lane x 16 B tap request spans 4-6 lines), not by HBM.
 #include "common.cuh"
+#include "sweep_l1.cuh"
 
 namespace cnm {
 
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(CV_TX* CV_TY)
   const int p = blockIdx.z / groups;
   const int d0 = (blockIdx.z % groups) * DPB;
   const int tid = threadIdx.y * CV_TX + threadIdx.x;
-  if (tid < DPB) zs[tid] = (float)(1.0 / (idmin + (double)(d0 + tid) * idstep));  // fp64 like the Python double
+  if (tid < DPB) zs[tid] = sweep_plane_z(idmin, idstep, d0 + tid);
   __syncthreads();
 
   const int x = blockIdx.x * CV_TX + threadIdx.x;
@@ -140,45 +141,17 @@ __global__ void __launch_bounds__(CV_TX* CV_TY)
   const int b = p % B;
   const size_t HW = (size_t)H * W;
 
-  const float* h = hk + (size_t)p * 12;
-  const float fx = (float)x, fy = (float)y;
-  // a = Hm . [x, y, 1]^T   (KRKiUV)
-  const float a0 = fmaf(__ldg(h + 0), fx, fmaf(__ldg(h + 1), fy, __ldg(h + 2)));
-  const float a1 = fmaf(__ldg(h + 3), fx, fmaf(__ldg(h + 4), fy, __ldg(h + 5)));
-  const float a2 = fmaf(__ldg(h + 6), fx, fmaf(__ldg(h + 7), fy, __ldg(h + 8)));
-  const float k0 = __ldg(h + 9), k1 = __ldg(h + 10), k2 = __ldg(h + 11) + 1e-6f;
-
+  SweepPixelL1 sp;
+  sweep_l1_setup(sp, hk + (size_t)p * 12, x, y);
   const float* rp = ref + (size_t)b * 3 * HW + (size_t)y * W + x;
-  const float r0 = __ldg(rp), r1 = __ldg(rp + HW), r2 = __ldg(rp + 2 * HW);
-
-  const int pitch = W + 4;
-  const float4* tp = tex + (size_t)p * (H + 3) * pitch + pitch + 1;  // texel (0,0)
-  const float xmax = (float)W, ymax = (float)H;
+  sp.r0 = __ldg(rp); sp.r1 = __ldg(rp + HW); sp.r2 = __ldg(rp + 2 * HW);
+  sp.pitch = W + 4;
+  sp.tp = tex + (size_t)p * (H + 3) * sp.pitch + sp.pitch + 1;  // texel (0,0)
+  sp.xmax = (float)W; sp.ymax = (float)H;
 
   float res[DPB];
 #pragma unroll
-  for (int i = 0; i < DPB; ++i) {
-    const float z = zs[i];
-    const float px = fmaf(a0, z, k0), py = fmaf(a1, z, k1);
-    const float den = fmaf(a2, z, k2);  // p_z + 1e-6
-    float rcp;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(den));
-    rcp = fmaf(fmaf(-den, rcp, 1.0f), rcp, rcp);  // one Newton step: ~0.5 ulp
-    // grid_sample un-normalisation with align_corners=False: ix = u - 0.5
-    float ix = fmaf(px, rcp, -0.5f), iy = fmaf(py, rcp, -0.5f);
-    ix = fminf(fmaxf(ix, -1.0f), xmax);  // NaN -> -1 (zero border)
-    iy = fminf(fmaxf(iy, -1.0f), ymax);
-    const float x0f = floorf(ix), y0f = floorf(iy);
-    const float wx1 = ix - x0f, wy1 = iy - y0f;
-    const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-    const float4* t = tp + (int)y0f * pitch + (int)x0f;
-    const float4 t00 = __ldg(t), t10 = __ldg(t + 1), t01 = __ldg(t + pitch), t11 = __ldg(t + pitch + 1);
-    const float w00 = wx0 * wy0, w10 = wx1 * wy0, w01 = wx0 * wy1, w11 = wx1 * wy1;
-    const float c0 = fmaf(t11.x, w11, fmaf(t01.x, w01, fmaf(t10.x, w10, fmaf(t00.x, w00, -r0))));
-    const float c1 = fmaf(t11.y, w11, fmaf(t01.y, w01, fmaf(t10.y, w10, fmaf(t00.y, w00, -r1))));
-    const float c2 = fmaf(t11.z, w11, fmaf(t01.z, w01, fmaf(t10.z, w10, fmaf(t00.z, w00, -r2))));
-    res[i] = fabsf(c0) + fabsf(c1) + fabsf(c2);
-  }
+  for (int i = 0; i < DPB; ++i) res[i] = sweep_l1_sample(sp, zs[i]);
 
   if (LAYOUT == 0) {
     float* o = reinterpret_cast<float*>(out) + ((size_t)p * D + d0) * HW + (size_t)y * W + x;

@@ -24,6 +24,9 @@ PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0"   # activation buffers
 FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
 PLANE_SWEEP = os.environ.get("CNM_PLANE_SWEEP", "1") != "0"   # K1 = csrc/plane_sweep.cu (TMA-staged); 0: cost_volume.cu
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
+# conv1.0 with the plane sweep fused in (cnm_conv2d_halo2_sweep, kernel name "halo2s"): "1" = available to the variant
+# table / autotuner, "force" = used wherever it applies, "0" = off
+FUSE_SWEEP = os.environ.get("CNM_FUSE_SWEEP", "1")
 TORCH_DTYPE = {CNM_BF16: torch.bfloat16, CNM_TF32: torch.float32, CNM_BF16X3: torch.bfloat16, CNM_F16F8: torch.float16}
 F8_LO_SCALE, F8_HI_SCALE = 128.0, 0.0625   # csrc/common.cuh: lo8 = e4m3((v - hi) * 2^7), hi8 = e4m3(hi * 2^-4)
 
@@ -375,6 +378,7 @@ class ConvOp:
         self.flops_bf16_time = 2.0 * N * Ho * Wo * cout * self.num_steps * ch
         self._weights = None
         self.tuned = None
+        self.sweep = None
         self.key = repr((dtype, N, Ho, Wo, cout, k, stride, tuple((s.kind, s.C, s.buf.shape[3]) for s in srcs)))
         # default choice without tuning
         halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
@@ -409,6 +413,8 @@ class ConvOp:
         for be in ("tc", "halo", "halo2"):
             if be in self.variants:
                 out += [(be, bn, 1) for bn in (256, 128, 64) if d.Cout % bn == 0]
+        if "halo2s" in self.variants:
+            out.append(("halo2s", d.Cout, 1))
         if SPLITK and "tc" in self.variants and not getattr(self, "_head", None):
             tw = 16 if d.Wo >= 16 else 8
             th = min(128 // tw, 1 << max(d.Ho - 1, 0).bit_length())
@@ -426,7 +432,7 @@ class ConvOp:
     def tune(self, stream, reps=3):
         """Applies the table's choice for this layer shape; in "auto" mode a missing shape times every (kernel, tile,
         split-K) candidate with CUDA events once and enters the fastest into the table."""
-        if not self.tunable or TUNE_MODE == "off":
+        if not self.tunable or TUNE_MODE == "off" or (FUSE_SWEEP == "force" and "halo2s" in self.variants):
             return
         best = _TUNE_CACHE.get(self.key)
         if best is not None and best[0] not in self.variants:
@@ -453,6 +459,25 @@ class ConvOp:
         self.tuned = best
         self.select(best[0], best[1], best[2])
 
+    def attach_sweep(self, vol_src, Bref, planes, idmin, idmax, tex, hk):
+        """Makes the fused plane-sweep kernel ("halo2s": csrc/conv_halo.cu, SWEEP instantiation) a variant of this layer:
+        source `vol_src` is then computed inside the convolution from the packed source views `tex`, the homographies
+        `hk` and the reference frames (pointer bound per call through `self.sweep.ref`) instead of being read."""
+        d = self.desc
+        if FUSE_SWEEP == "0" or "halo2" not in self.variants or self.dtype != CNM_F16F8 or self.stride != 1 or \
+                d.Cout > 128 or getattr(self, "_head", None):
+            return False
+        lib = _lib.load()
+        nbytes = int(lib.cnm_sweep_scratch_bytes(planes, self.k))
+        self._sweep_scratch = torch.empty((nbytes,), dtype=torch.uint8, device=self.out.device)
+        self._sweep_keep = (tex, hk)
+        self.sweep = _lib.SweepFuse(None, tex.data_ptr(), hk.data_ptr(), self._sweep_scratch.data_ptr(), nbytes, Bref,
+                                    planes, vol_src, 0, idmin, idmax)
+        self.variants["halo2s"] = self.variants["halo2"]   # same program; the volume's slabs come from the scratch
+        if FUSE_SWEEP == "force":
+            self.select("halo2s", d.Cout)
+        return True
+
     def fuse_head(self, w_tap_major, partial):
         """Fused 1-channel 3x3 head on this layer's output (cnm_conv_desc.head_w [9][Cout] / head_partial [Cout/64 slices])."""
         assert self.dtype != CNM_TF32
@@ -469,6 +494,13 @@ class ConvOp:
     def __call__(self, stream):
         lib = _lib.load()
         v = self.variants[self.backend]
+        if self.backend == "halo2s":
+            if not self.sweep.ref:
+                raise RuntimeError("%s: the fused plane sweep has no reference frames bound" % self.name)
+            _lib.check(lib.cnm_conv2d_halo2_sweep(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(),
+                                                  v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),
+                                                  self.out.data_ptr(), C.byref(self.sweep), stream), self.name)
+            return
         if self.backend in ("halo", "halo2"):
             fn = lib.cnm_conv2d_halo if self.backend == "halo" else lib.cnm_conv2d_halo2
             _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(),
@@ -663,8 +695,9 @@ class DepthNetPlan(_Plan):
         # K1: the TMA-staged plane sweep reads the source views in place; the first-generation pair (repack + L1 gather,
         # CNM_PLANE_SWEEP=0) stays as its twin
         self.use_sweep = PLANE_SWEEP and W % 4 == 0 and planes <= 128
-        self.tex = None if self.use_sweep else torch.empty((lib.cnm_packed_source_bytes(N, H, W),), dtype=torch.uint8,
-                                                           device=self.device)
+        self.may_fuse = FUSE_SWEEP != "0" and self.dtype == CNM_F16F8 and planes <= 128
+        self.tex = None if (self.use_sweep and not self.may_fuse) else \
+            torch.empty((lib.cnm_packed_source_bytes(N, H, W),), dtype=torch.uint8, device=self.device)
         self.cost = self.buf(N, H, W, planes)
         self.img_taps = self.buf(N, H, W, ch)
         self.inputs = {}
@@ -672,7 +705,10 @@ class DepthNetPlan(_Plan):
         def front(s):
             i = self.inputs
             _lib.check(lib.cnm_camera_setup(i["ref_cam"], i["src_cam"], self.hk.data_ptr(), Bref, N // Bref, s), "camera")
-            if self.use_sweep:
+            if self.convs["conv1.0"].backend == "halo2s":
+                # (f)-1: conv1.0 computes the volume itself; it only needs the source views as zero-bordered texels
+                _lib.check(lib.cnm_pack_source(i["src"], self.tex.data_ptr(), N, H, W, s), "pack_source")
+            elif self.use_sweep:
                 _lib.check(lib.cnm_plane_sweep(i["ref"], i["src"], self.hk.data_ptr(), self.cost.data_ptr(), Bref,
                                                N // Bref, H, W, planes, self.idmin, self.idmax, _lib.VOLUME_ACT, dt, s),
                            "plane_sweep")
@@ -691,6 +727,8 @@ class DepthNetPlan(_Plan):
         N, H, W = self.N, self.H, self.W
         cv, rel, up = self.conv, self.release, self.upsample
         x = cv("conv1.0", [self.src(self.cost, 3), Src(self.img_taps, "rowtaps", 0, self.ch, 0, 3)], 7, 1, 128, N, H, W)
+        if self.may_fuse:
+            self.convs["conv1.0"].attach_sweep(0, self.Bref, self.D, self.idmin, self.idmax, self.tex, self.hk)
         rel(self.cost, self.img_taps)
         conv1 = cv("conv1.3", [self.src(x, 0)], 7, 2, 128, N, H // 2, W // 2)
         rel(x)
@@ -763,6 +801,9 @@ class DepthNetPlan(_Plan):
                 raise ValueError("expected fp32 tensor of shape %s, got %s %s" % (shape, tuple(t.shape), t.dtype))
         self.inputs = {"ref": _lib.ptr(ref), "src": _lib.ptr(src), "ref_cam": _lib.ptr(ref_cam),
                        "src_cam": _lib.ptr(src_cam)}
+        sweep = self.convs["conv1.0"].sweep
+        if sweep is not None:
+            sweep.ref = self.inputs["ref"]
         self._keep = (ref, src, ref_cam, src_cam)
 
     def iconv1_nchw(self, stream=None):

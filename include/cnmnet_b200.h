@@ -284,6 +284,32 @@ int cnm_conv2d_halo2(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const 
                      const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
                      void* stream);
 
+/* ---- conv1.0 with the plane sweep fused in -----------------------------------------
+ * replaces getVolume + torch.cat + conv1[0]  (depthnet/depthNet_model.py:185-224, 231-235) in ONE kernel: the cost
+ * volume never exists as a tensor.  Same contract as cnm_conv2d_halo2 for a stride-1 CNM_F16F8 layer whose source
+ * `vol_src` is the [N, H, W, D] volume (Cout one tile of <= 128, no fused head); srcs[vol_src].ptr is NOT read (pass
+ * any 128B-aligned device pointer).  Eight extra warps per CTA compute, for every 16x16 output tile, the
+ * (16 + k - 1)^2 region of the volume around it -- exactly the arithmetic of cnm_cost_volume on the packed source
+ * views, zeros outside the image -- into one of the CTA's two scratch slots in the act layout, and the TMA producer
+ * boxes the operand slabs out of that slot.  A slot is rewritten every other tile, so the scratch (37 MB at 64
+ * planes) lives in L2.  The output is bit-identical to cnm_pack_source + cnm_cost_volume(CNM_VOLUME_ACT) +
+ * cnm_conv2d_halo2 with the same tile.                                                                             */
+typedef struct cnm_sweep_fuse {
+  const float* ref;        /* [B,3,H,W] fp32 reference frames */
+  const void* packed_src;  /* cnm_pack_source of the N = V*B source views (pair p = v*B + b) */
+  const float* hk;         /* [N,12] from cnm_camera_setup */
+  void* scratch;           /* device, 128B aligned */
+  int64_t scratch_bytes;   /* >= cnm_sweep_scratch_bytes(D, k) */
+  int32_t B, D;            /* reference frames; planes (64 or 128) */
+  int32_t vol_src;         /* index of the volume among the layer's sources */
+  int32_t reserved;
+  double idepth_min, idepth_max;
+} cnm_sweep_fuse;
+int64_t cnm_sweep_scratch_bytes(int D, int k);
+int cnm_conv2d_halo2_sweep(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* map_info,
+                           const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
+                           const cnm_sweep_fuse* sweep, void* stream);
+
 /* ---- depth-driven inverse warp ("next") ----------------------------
  * replaces inverse_warp + cam2pixel  (depthnet/inverse_warp.py:46-118).
  * feat [B,C,H,W], depth [B,H,W], pose [B,3,4], K [B,3,3], Kinv [B,3,3] -> out [B,C,H,W];
