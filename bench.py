@@ -341,6 +341,7 @@ def main():
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the informational run of the reference's own modules on this GPU (stock PyTorch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the bf16 / tf32 / bf16x3 lines (A/B experiments)")
     ap.add_argument("--layers", action="store_true", help="also print a per-layer timing table on stderr")
     args = ap.parse_args()
     global H, W, D, B_PER_GPU, WORKLOAD, DEPTHNET_GFLOP, REFINE_GFLOP, METRIC
@@ -638,7 +639,7 @@ def main():
         # the other tensor-core modes, same workload, same timing method (kept out of the headline value)
         line["other_modes"] = []
         others = [m for m in ("bf16", "tf32", "bf16x3", "f16f8") if m != args.precision]
-        if args.workload != "c4":
+        if args.workload != "c4" or args.no_other_modes:
             others = []   # one mode at a time at 640x480 x 32: a plan holds ~60-120 GB of activations
         for other in others:
             d2, r2 = make_weights(0)

@@ -27,6 +27,7 @@
 //   * only the leader's warp 1 issues MMAs (D = 128 rows x BN columns in EACH CTA's TMEM); tcgen05.commit is
 //     multicast to both CTAs' "empty" and "accumulator full" barriers;
 //   * both CTAs run the epilogue on their own TMEM half; "accumulator empty" arrivals go to the leader's barrier.
+#include <climits>
 #include <cstring>
 
 #include "sweep_l1.cuh"
@@ -44,7 +45,9 @@ constexpr int HL_SWEEP_THREADS = 256;  // volume-producer warps of the fused con
 // warps 0-3, epilogue warps 4-7, two producer warpgroups).  ptxas allocates each role's code against its own limit.
 constexpr int HL_SWEEP_REGS_CTRL = 104, HL_SWEEP_REGS_EPI = 200, HL_SWEEP_REGS_PROD = 104;
 static_assert(HL_SWEEP_REGS_CTRL + HL_SWEEP_REGS_EPI + 2 * HL_SWEEP_REGS_PROD <= 512, "register file");
-constexpr int HL_SWEEP_PLANES = 16;  // planes per pass of a producer thread over its pixel
+constexpr int HL_SWEEP_PLANES = 8;          // planes per staged box
+constexpr int HL_SWEEP_BOX_TEXELS = 3072;  // float4 texels of the staged source box (48 KB)
+constexpr int HL_SWEEP_SMEM = HL_SWEEP_MAX_D * 4 + 32 + HL_SWEEP_BOX_TEXELS * 16;  // z table, min / max records, box
 
 // Fused plane sweep (SWEEP instantiations, cnm_conv2d_halo2_sweep): the cost-volume operand of conv1.0 never exists as a
 // tensor.  Producer warps compute, per 16x16 output tile, the (16+2p)^2 halo region of the volume straight in the act
@@ -60,6 +63,7 @@ struct SweepFuseParams {
   int B, D, H, W;
   int vol_map;           // the a_maps index (source * 4) the scratch stands in for
   int pad;               // rows / columns of the region above / left of the tile ((k - 1) / 2)
+  int park;              // waiting TMA / epilogue warps back off with nanosleep
 };
 
 struct alignas(64) HaloParams {
@@ -137,6 +141,21 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
 }
 
+// mbarrier wait that leaves the issue slots to other warps while it waits (SWEEP kernels: the volume producers share the
+// schedulers with the waiting TMA / epilogue warps)
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000u)
+        : "memory");
+    if (ok) return;
+    __nanosleep(ns);
+  }
+}
+
 // CG = 1: one CTA per 16x16 pixel block, two MMA-issuing warps (one per half of the block).  CG = 2: a CTA pair on two
 // neighbouring blocks, one M = 256 MMA per half issued by the leader.
 template <int BN, bool TF32, int CG, bool SWEEP = false>
@@ -174,7 +193,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   auto vfull = [&](int s) { return bar0 + 8u * (2 * HL_MAX_A + 2 * HL_MAX_B + 4 + s); };  // SWEEP: volume slot s is written
   const uint32_t off_tmem = off_bar + 8u * HL_NUM_BARS;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + off_tmem);
-  float* zs = reinterpret_cast<float*>(base_ptr + off_tmem + 16);  // SWEEP: z_d of the D planes
+  float* zs = reinterpret_cast<float*>(base_ptr + ((off_tmem + 16 + 15) & ~15u));  // SWEEP: z_d of the D planes (16B aligned)
   float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
   float* head_s = reinterpret_cast<float*>(base_ptr + off_head);
   const bool fused_head = !TF32 && !SWEEP && p.head_partial != nullptr;
@@ -247,7 +266,8 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
           g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == p.num_groups) ? 0 : g + 1)));
           const int pad = p.map_pad[gr.x];
           const uint32_t slab_tx = (uint32_t)p.map_rows[gr.x] * 2048u;
-          mbar_wait(emptyA(sa), pa ^ 1);
+          if (SWEEP && p.sw.park) mbar_wait_backoff(emptyA(sa), pa ^ 1, 200);
+          else mbar_wait(emptyA(sa), pa ^ 1);
           if (leader) mbar_expect_tx(fullA(sa), (uint32_t)CG * slab_tx);  // CG = 2: both CTAs' slabs
           const CUtensorMap* map = &p.a_maps[gr.x];
           int c1 = x0 + gr.z, c2 = y0 - pad, c3 = n0;
@@ -255,7 +275,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
             // the tile's region of the volume sits in this CTA's scratch slot (written by warps 8-15): columns
             // dx + pad ... of the region, all rows
             if (!vol_ready) {
-              mbar_wait(vfull(it & 1), (uint32_t)(it >> 1) & 1u);
+              mbar_wait_backoff(vfull(it & 1), (uint32_t)(it >> 1) & 1u, 200);
               vol_ready = true;
             }
             map = &p.sw.map;
@@ -276,7 +296,8 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int nt = tile % p.tiles_n;
         for (int kstep = 0; kstep < num_steps; ++kstep) {
-          mbar_wait(emptyB(sb), pb ^ 1);
+          if (SWEEP && p.sw.park) mbar_wait_backoff(emptyB(sb), pb ^ 1, 100);
+          else mbar_wait(emptyB(sb), pb ^ 1);
           if (leader) mbar_expect_tx(fullB(sb), (uint32_t)CG * B_BYTES);  // CG = 2: both halves
           if (CG == 2) tma2_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN + (int)rank * (BN / 2));
           else tma_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN);
@@ -356,19 +377,29 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     }
   } else if (SWEEP && warp >= 8) {
     // ================= fused plane sweep: volume producers =================
-    // Per tile: the (16 + 2 pad)^2 region of the cost volume around it, one pixel per thread and pass, all D planes, in
-    // the act layout (CNM_F16F8 rows: fp16 | lo8 | hi8), zeros outside the image (= the convolution's padding).  Slot
-    // it & 1 is free again when the MMAs of tile it - 2 have completed (their commit on the accumulator-full barrier of
-    // stage it & 1 also covers the TMA reads of that slot).
-    const int pt = (int)threadIdx.x - 256;
+    // Per tile: the (16 + 2 pad)^2 region of the cost volume around it, all D planes, in the act layout (CNM_F16F8 rows:
+    // fp16 | lo8 | hi8), zeros outside the image (= the convolution's padding).  A thread owns up to two pixels of the
+    // region.  Eight planes at a time: (A) every thread computes its sample positions and the warps reduce their
+    // bounding box; (L) the box of source texels is copied to shared memory with coalesced loads; (S) the samples are
+    // blended from the staged copy -- two producer warps per scheduler cannot hide L2 latency behind four dependent
+    // gathers per sample (ncu on the direct version: 0.3 instructions per cycle and scheduler, half of the stalls on
+    // L1TEX), but a shared-memory tap returns in ~30 cycles.  A box that does not fit (extreme zoom) is sampled through
+    // L1 instead; both paths return the same texels, so the rows equal cnm_cost_volume's bit for bit.
+    // Slot it & 1 of the scratch is free again when the MMAs of tile it - 2 have completed (their commit on the
+    // accumulator-full barrier of stage it & 1 also covers the TMA reads of that slot).
+    const int pt = (int)threadIdx.x - 256, pw = warp - 8;
     const SweepFuseParams& sw = p.sw;
     const int D = sw.D, H = sw.H, W = sw.W;
     const int R = 16 + 2 * sw.pad, npx = R * R;
     const size_t px_bytes = (size_t)D * 4;  // 2 D physical 2-byte channels
     const size_t HW = (size_t)H * W;
+    int* mm = reinterpret_cast<int*>(zs + HL_SWEEP_MAX_D);      // [2][4]: min x0, min y0, max x0, max y0 (group parity)
+    float4* box = reinterpret_cast<float4*>(mm + 8);
     for (int i = pt; i < D; i += HL_SWEEP_THREADS) zs[i] = sweep_plane_z(sw.idmin, sw.idstep, i);
+    if (pt < 8) mm[pt] = (pt & 2) ? INT_MIN : INT_MAX;
     asm volatile("bar.sync 2, 256;" ::: "memory");
     int it = 0;
+    uint32_t grp = 0;  // running group count: parity selects the min / max record
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
       int m = CG * (tile / p.tiles_n) + (int)rank;
       const int x0 = (m % p.tiles_x) * 16;
@@ -377,37 +408,94 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       const int n0 = m / p.tiles_y;
       const int slot = it & 1;
       if (it >= 2) {
-        if (lane == 0) mbar_wait(tfull(slot), (uint32_t)((it - 2) >> 1) & 1u);
+        if (lane == 0) mbar_wait_backoff(tfull(slot), (uint32_t)((it - 2) >> 1) & 1u, 200);
         __syncwarp();
       }
       uint8_t* sc = sw.scratch + ((size_t)((int)blockIdx.x * 2 + slot) * npx) * px_bytes;
       const float* h = sw.hk + (size_t)n0 * 12;
       const float* rimg = sw.ref + (size_t)(n0 % sw.B) * 3 * HW;
-      SweepPixelL1 sp;
-      sp.pitch = W + 4;
-      sp.tp = sw.tex + (size_t)n0 * (H + 3) * sp.pitch + sp.pitch + 1;  // texel (0,0)
-      sp.xmax = (float)W; sp.ymax = (float)H;
-      for (int idx = pt; idx < npx; idx += HL_SWEEP_THREADS) {
+      const int pitch = W + 4;
+      const float4* tp = sw.tex + (size_t)n0 * (H + 3) * pitch + pitch + 1;  // texel (0,0)
+      SweepPixelL1 sp[2];
+      h16f8* row[2];
+      bool live[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int idx = pt + k * HL_SWEEP_THREADS;
         const int ry = idx / R, rx = idx - ry * R;
         const int x = x0 - sw.pad + rx, y = y0 - sw.pad + ry;
-        h16f8* row = reinterpret_cast<h16f8*>(sc + (size_t)idx * px_bytes);
-        if (x < 0 || x >= W || y < 0 || y >= H) {
-          uint4* z4 = reinterpret_cast<uint4*>(row);
+        row[k] = reinterpret_cast<h16f8*>(sc + (size_t)idx * px_bytes);
+        live[k] = idx < npx && x >= 0 && x < W && y >= 0 && y < H;
+        sp[k].pitch = pitch; sp[k].tp = tp;
+        sp[k].xmax = (float)W; sp[k].ymax = (float)H;
+        if (live[k]) {
+          sweep_l1_setup(sp[k], h, x, y);
+          const float* rp = rimg + (size_t)y * W + x;
+          sp[k].r0 = __ldg(rp); sp[k].r1 = __ldg(rp + HW); sp[k].r2 = __ldg(rp + 2 * HW);
+        } else if (idx < npx) {
+          uint4* z4 = reinterpret_cast<uint4*>(row[k]);
           for (int i = 0; i < (int)(px_bytes / 16); ++i) z4[i] = make_uint4(0u, 0u, 0u, 0u);
-          continue;
         }
-        sweep_l1_setup(sp, h, x, y);
-        const float* rp = rimg + (size_t)y * W + x;
-        sp.r0 = __ldg(rp); sp.r1 = __ldg(rp + HW); sp.r2 = __ldg(rp + 2 * HW);
+      }
 #pragma unroll 1
-        for (int d0 = 0; d0 < D; d0 += HL_SWEEP_PLANES) {
-          float res[HL_SWEEP_PLANES];
+      for (int d0 = 0; d0 < D; d0 += HL_SWEEP_PLANES, ++grp) {
+        // ---- (A) positions of this thread's samples, bounding box of their upper-left taps
+        float ix[2][HL_SWEEP_PLANES], iy[2][HL_SWEEP_PLANES];
+        int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
 #pragma unroll
-          for (int i = 0; i < HL_SWEEP_PLANES; ++i) res[i] = sweep_l1_sample(sp, zs[d0 + i]);
-          h16f8* o = row + ActTraits<h16f8>::phys(d0);
+        for (int k = 0; k < 2; ++k)
+          if (live[k]) {
 #pragma unroll
-          for (int i = 0; i < HL_SWEEP_PLANES; i += 8) Vec16<h16f8>::store(o + i, res + i);
+            for (int i = 0; i < HL_SWEEP_PLANES; ++i) {
+              sweep_l1_position(sp[k], zs[d0 + i], ix[k][i], iy[k][i]);
+              const int tx = (int)floorf(ix[k][i]), ty = (int)floorf(iy[k][i]);
+              mnx = min(mnx, tx); mxx = max(mxx, tx);
+              mny = min(mny, ty); mxy = max(mxy, ty);
+            }
+          }
+        int* rec = mm + 4 * (grp & 1u);
+        mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+        mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+        if (lane == 0 && mnx <= mxx) {
+          atomicMin(rec + 0, mnx); atomicMin(rec + 1, mny);
+          atomicMax(rec + 2, mxx); atomicMax(rec + 3, mxy);
         }
+        asm volatile("bar.sync 2, 256;" ::: "memory");   // also: every thread is done sampling the previous box
+        const int bx = rec[0], by = rec[1];
+        const int bw = rec[2] - bx + 2, bh = rec[3] - by + 2;   // taps x0, x0 + 1 / y0, y0 + 1
+        const bool staged = bw * bh <= HL_SWEEP_BOX_TEXELS;      // CTA-uniform
+        // ---- (L) the box, one row per warp and pass, 32 texels per load instruction
+        if (staged) {
+          for (int r = pw; r < bh; r += HL_SWEEP_THREADS / 32) {
+            const float4* srow = tp + (by + r) * pitch + bx;
+            for (int c = lane; c < bw; c += 32) box[r * bw + c] = __ldg(srow + c);
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (pt == 0) { rec[0] = INT_MAX; rec[1] = INT_MAX; rec[2] = INT_MIN; rec[3] = INT_MIN; }   // next use: group grp + 2
+        // ---- (S) blend and store
+        const float4* bo = box - (by * bw + bx);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (live[k]) {
+            float res[HL_SWEEP_PLANES];
+            if (staged) {
+#pragma unroll
+              for (int i = 0; i < HL_SWEEP_PLANES; ++i)
+                res[i] = sweep_l1_blend(sp[k], ix[k][i], iy[k][i],
+                                        [&](int tx, int ty, float4& t00, float4& t10, float4& t01, float4& t11) {
+                                          const float4* t = bo + ty * bw + tx;
+                                          t00 = t[0]; t10 = t[1]; t01 = t[bw]; t11 = t[bw + 1];
+                                        });
+            } else {
+#pragma unroll
+              for (int i = 0; i < HL_SWEEP_PLANES; ++i)
+                res[i] = sweep_l1_blend(sp[k], ix[k][i], iy[k][i], SweepFetchGlobal{tp, pitch});
+            }
+            h16f8* o = row[k] + ActTraits<h16f8>::phys(d0);
+#pragma unroll
+            for (int i = 0; i < HL_SWEEP_PLANES; i += 8) Vec16<h16f8>::store(o + i, res + i);
+          }
       }
       // generic-proxy writes -> visible to the TMA (async proxy) reads the A producer issues after its wait
       asm volatile("fence.proxy.async;" ::: "memory");
@@ -440,7 +528,8 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         bias_tile = nt;
         epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
-      mbar_wait(tfull(as), aphase);
+      if (SWEEP && p.sw.park) mbar_wait_backoff(tfull(as), aphase, 500);
+      else mbar_wait(tfull(as), aphase);
       tc_fence_after();
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
@@ -633,6 +722,7 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     sw.idstep = (sweep->idepth_max - sweep->idepth_min) / (double)(sweep->D - 1);
     sw.B = sweep->B; sw.D = sweep->D; sw.H = d->Ho; sw.W = d->Wo;
     sw.vol_map = vs * 4; sw.pad = pad;
+    sw.park = 1;
     const uint64_t pix = (uint64_t)sweep->D * 4;
     const uint64_t dims[4] = {(uint64_t)2 * sweep->D, (uint64_t)R, (uint64_t)R, (uint64_t)2 * 148};
     const uint64_t str[3] = {pix, pix * R, pix * R * R};
@@ -641,7 +731,7 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     if (rc) return rc;
   }
   const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (d->head_partial ? 9 * BN * 4 : 0) + 8 * HL_NUM_BARS + 16 +
-                    (sweep ? HL_SWEEP_MAX_D * 4 : 0);
+                    (sweep ? HL_SWEEP_SMEM + 16 : 0);
   const int budget = 232448 - fixed;
   const int want_b = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 7 : 8));
   const int b_tile = BN * 128 / CG;   // bytes of one weight tile (CG = 2: this CTA's half)

@@ -394,6 +394,10 @@ class ConvOp:
     def select(self, backend, bn, ksplit=1):
         repack = getattr(self, "backend", backend) != backend and self._weights is not None
         self.backend = backend
+        if backend == "halo2s" and not self.sweep.scratch:
+            nbytes = int(_lib.load().cnm_sweep_scratch_bytes(self.sweep.D, self.k))
+            self._sweep_scratch = torch.empty((nbytes,), dtype=torch.uint8, device=self.out.device)
+            self.sweep.scratch, self.sweep.scratch_bytes = self._sweep_scratch.data_ptr(), nbytes
         self.desc.reserved = int(bn)
         self.desc.ksplit = int(ksplit) if backend == "tc" else 1
         if self.desc.ksplit > 1:
@@ -467,12 +471,9 @@ class ConvOp:
         if FUSE_SWEEP == "0" or "halo2" not in self.variants or self.dtype != CNM_F16F8 or self.stride != 1 or \
                 d.Cout > 128 or getattr(self, "_head", None):
             return False
-        lib = _lib.load()
-        nbytes = int(lib.cnm_sweep_scratch_bytes(planes, self.k))
-        self._sweep_scratch = torch.empty((nbytes,), dtype=torch.uint8, device=self.out.device)
         self._sweep_keep = (tex, hk)
-        self.sweep = _lib.SweepFuse(None, tex.data_ptr(), hk.data_ptr(), self._sweep_scratch.data_ptr(), nbytes, Bref,
-                                    planes, vol_src, 0, idmin, idmax)
+        # the scratch (37 MB at 64 planes) is allocated when the variant is first selected
+        self.sweep = _lib.SweepFuse(None, tex.data_ptr(), hk.data_ptr(), None, 0, Bref, planes, vol_src, 0, idmin, idmax)
         self.variants["halo2s"] = self.variants["halo2"]   # same program; the volume's slabs come from the scratch
         if FUSE_SWEEP == "force":
             self.select("halo2s", d.Cout)
