@@ -92,14 +92,6 @@ struct alignas(64) HaloParams {
 // ---- 2-CTA PTX wrappers --------------------------------------------------------------------------------------
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: -> leader CTA
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // TMA loads of a CTA pair: data lands in the executing CTA's smem, the transaction bytes are counted on the LEADER's barrier
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                              int c3) {

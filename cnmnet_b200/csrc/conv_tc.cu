@@ -21,6 +21,10 @@
 //                  1-channel head (Cout = 64), or raw accumulators to the split-K workspace.
 // Split-K        desc.ksplit > 1: tile index gains a K-range dimension; splitk_finish_kernel sums the
 //                  ranges in a fixed order and does the epilogue work.
+// Multicast       CL = 2 / 4 (cnm_conv_desc.cluster): a cluster of CL CTAs works on CL pixel tiles of the SAME column
+//                  tile and K range; every CTA loads 1/CL of each weight tile and multicasts it to all of them, so the
+//                  L2 -> SM bytes per K-step drop from 16 + BN/8 KB to 16 + BN/(8 CL) KB.  These layers are bound by
+//                  operand delivery (bytes in flight / loaded L2 latency), not by MMA time.
 // Warp roles     warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM
 //                  allocator, warp 3 idle, warps 4-7 = epilogue (TMEM lane quarter = warp - 4).
 #include <cstring>
@@ -71,9 +75,15 @@ struct TcSmem {
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + slack for manual 1024 B alignment
 };
 
-template <int BN, int STAGES, bool TF32>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+template <int BN, int STAGES, bool TF32, int CL>
+__device__ __forceinline__ void conv_tc_body(const TcParams& p) {
   using L = TcSmem<BN, STAGES, TF32>;
+  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  // work item q of a cluster = (pixel-tile group, column tile, K range); CTA `rank` takes pixel tile CL * group + rank
+  // (a tile index beyond the last one is a dummy: its TMA boxes lie outside the tensors -- zero-filled loads, clipped
+  // stores -- but it walks the same K-steps, because the cluster shares the weight ring)
+  const int first_q = (int)blockIdx.x / CL, q_stride = (int)gridDim.x / CL;
   constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;  // accumulator columns per 128-byte output row
   constexpr int CHUNK_CH = TF32 ? 32 : 64;        // channels per K-step
   constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
@@ -100,8 +110,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_n * p.ksplit;
-  // split-K: tile index = ((m * tiles_n) + nt) * ksplit + part; part runs K-steps [kbeg(part), kbeg(part+1))
+  const int m_groups = (p.tiles_x * p.tiles_y * p.tiles_b + CL - 1) / CL;
+  const int total_tiles = m_groups * p.tiles_n * p.ksplit;
+  // split-K: item index = ((group * tiles_n) + nt) * ksplit + part; part runs K-steps [kbeg(part), kbeg(part+1))
   auto kbeg = [&](int part) { return part >= p.ksplit ? p.num_steps : ((p.num_steps / 2) * part / p.ksplit) * 2; };
 
   if (warp == 0 && lane == 0) {
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     tma_prefetch_desc(&p.a_maps[0]);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -121,7 +132,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer's multicast / commit can reach them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -130,13 +142,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int k_first = kbeg((int)(blockIdx.x % p.ksplit));
+      const int k_first = kbeg(first_q % p.ksplit);
       int4 st_next = __ldg(reinterpret_cast<const int4*>(p.steps + k_first));
       int c0_next = __ldg(&p.steps[k_first].c0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_q; tile < total_tiles; tile += q_stride) {
         const int part = tile % p.ksplit;
         const int nt = (tile / p.ksplit) % p.tiles_n;
-        int m = tile / (p.ksplit * p.tiles_n);
+        int m = (tile / (p.ksplit * p.tiles_n)) * CL + (int)rank;
         const int x0 = (m % p.tiles_x) * p.TW;
         m /= p.tiles_x;
         const int y0 = (m % p.tiles_y) * p.TH;
@@ -146,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int4 st = st_next;  // src, sub, dx, dy
           const int c0 = c0_next;
           {  // prefetch the next step descriptor: its L2 latency overlaps the barrier wait below
-            const int kn = (ks + 1 == k_end) ? kbeg((int)((tile + gridDim.x) % p.ksplit)) % p.num_steps : ks + 1;
+            const int kn = (ks + 1 == k_end) ? kbeg((tile + q_stride) % p.ksplit) % p.num_steps : ks + 1;
             st_next = __ldg(reinterpret_cast<const int4*>(p.steps + kn));
             c0_next = __ldg(&p.steps[kn].c0);
           }
@@ -154,7 +166,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
           const uint32_t sa = base + stage * L::STAGE_BYTES;
           tma_load_4d(sa, &p.a_maps[st.x * 4 + st.y], full_bar(stage), c0, x0 + st.z, y0 + st.w, n0);
-          tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), ks * CHUNK_CH, nt * BN);
+          if (CL > 1)  // this CTA's 1/CL of the weight rows, to every CTA of the cluster
+            tma_load_2d_mc(sa + TC_A_BYTES + rank * (uint32_t)(L::B_BYTES / CL), &p.b_map, full_bar(stage), ks * CHUNK_CH,
+                           nt * BN + (int)rank * (BN / CL), CL_MASK);
+          else
+            tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), ks * CHUNK_CH, nt * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -167,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_q; tile < total_tiles; tile += q_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
@@ -190,7 +206,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 tc_mma<TF32>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                              (ks != k_begin || k) ? 1u : 0u);
             }
-            tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+            // frees the smem stage when these MMAs retire (CL > 1: in every CTA -- the peers write into it)
+            if (CL > 1) tc_commit_mc(empty_bar(stage), CL_MASK);
+            else tc_commit(empty_bar(stage));
             if (ks == k_end - 1) tc_commit(tfull_bar(as));  // accumulator complete
           }
           __syncwarp();
@@ -208,9 +226,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t chunk_counter = 0;
     int bias_tile = -1;
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_q; tile < total_tiles; tile += q_stride, ++it) {
       const int nt = (tile / p.ksplit) % p.tiles_n;
-      int m = tile / (p.ksplit * p.tiles_n);
+      int m = (tile / (p.ksplit * p.tiles_n)) * CL + (int)rank;
       const int x0 = (m % p.tiles_x) * p.TW;
       m /= p.tiles_x;
       const int y0 = (m % p.tiles_y) * p.TH;
@@ -293,11 +311,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // a peer may still be writing this CTA's ring or arriving on its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+template <int BN, int STAGES, bool TF32>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  conv_tc_body<BN, STAGES, TF32, 1>(p);
+}
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc_mc2_kernel(const __grid_constant__ TcParams p) {
+  conv_tc_body<BN, STAGES, false, 2>(p);
+}
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc_mc4_kernel(const __grid_constant__ TcParams p) {
+  conv_tc_body<BN, STAGES, false, 4>(p);
 }
 
 // Second half of a split-K convolution: sums the ksplit partial accumulators of every output element in a fixed order
@@ -383,6 +415,38 @@ static int launch_tc(const TcParams& p, int grid, cudaStream_t s) {
   cudaError_t e = limit.ensure(conv_tc_kernel<BN, STAGES, TF32>, L::TOTAL);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
   conv_tc_kernel<BN, STAGES, TF32><<<grid, TC_THREADS, L::TOTAL, s>>>(p);
+  return after_launch("cnm_conv2d_tc");
+}
+
+// multicast variant: grid = CL x (as many clusters as the device keeps resident, at most one per work item)
+template <int BN, int STAGES, int CL>
+static int launch_tc_mc(const TcParams& p, int total_q, cudaStream_t s) {
+  using L = TcSmem<BN, STAGES, false>;
+  static DynSmemLimit limit;
+  static int max_clusters[64] = {0};
+  auto kernel = CL == 2 ? conv_tc_mc2_kernel<BN, STAGES> : conv_tc_mc4_kernel<BN, STAGES>;
+  cudaError_t e = limit.ensure(kernel, L::TOTAL);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& mc = max_clusters[dev & 63];
+  if (mc == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148 / CL * CL);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+    if (e != cudaSuccess || n <= 0) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: cluster occupancy query: %s", cudaGetErrorString(e));
+    mc = n;
+  }
+  const int clusters = total_q < mc ? total_q : mc;
+  kernel<<<clusters * CL, TC_THREADS, L::TOTAL, s>>>(p);
   return after_launch("cnm_conv2d_tc");
 }
 
@@ -473,7 +537,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
     const uint64_t K = (uint64_t)d->num_steps * ch;
     const uint64_t dims[2] = {K, (uint64_t)d->Cout};
     const uint64_t str[1] = {K * eb};
-    const uint32_t bbox[2] = {(uint32_t)ch, (uint32_t)BN};
+    const uint32_t bbox[2] = {(uint32_t)ch, (uint32_t)(BN / (d->cluster > 1 ? d->cluster : 1))};
     rc = encode_map(&p.b_map, d->dtype, 2, wp, dims, str, bbox);
     if (rc) return rc;
   }
@@ -488,7 +552,14 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   const int grid = total < 148 ? total : 148;
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
-  if (BN == 256) rc = tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
+  const int CL = d->cluster > 1 ? d->cluster : 1;
+  if (CL > 1) {
+    CNM_REQUIRE((CL == 2 || CL == 4) && !tf32 && BN >= 128, CNM_ERR_UNSUPPORTED_SHAPE,
+                "cnm_conv2d_tc: cluster = %d needs a 2-byte dtype and a column tile of 128 or 256 (got %d)", d->cluster, BN);
+    const int total_q = ((m_tiles + CL - 1) / CL) * p.tiles_n * p.ksplit;
+    if (BN == 256) rc = CL == 2 ? launch_tc_mc<256, 4, 2>(p, total_q, s) : launch_tc_mc<256, 4, 4>(p, total_q, s);
+    else rc = CL == 2 ? launch_tc_mc<128, 6, 2>(p, total_q, s) : launch_tc_mc<128, 6, 4>(p, total_q, s);
+  } else if (BN == 256) rc = tf32 ? launch_tc<256, 4, true>(p, grid, s) : launch_tc<256, 4, false>(p, grid, s);
   else if (BN == 128) rc = tf32 ? launch_tc<128, 6, true>(p, grid, s) : launch_tc<128, 6, false>(p, grid, s);
   else rc = tf32 ? launch_tc<64, 7, true>(p, grid, s) : launch_tc<64, 7, false>(p, grid, s);
   if (rc || p.ksplit == 1) return rc;

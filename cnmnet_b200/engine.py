@@ -24,6 +24,7 @@ PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0"   # activation buffers
 FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
 PLANE_SWEEP = os.environ.get("CNM_PLANE_SWEEP", "1") != "0"   # K1 = csrc/plane_sweep.cu (TMA-staged); 0: cost_volume.cu
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
+TC_MULTICAST = os.environ.get("CNM_TC_MULTICAST", "1") != "0"   # per-tap kernel on clusters sharing the weight tiles (tcm2 / tcm4)
 # conv1.0 with the plane sweep fused in (cnm_conv2d_halo2_sweep, kernel name "halo2s"): "1" = available to the variant
 # table / autotuner, "force" = used wherever it applies, "0" = off
 FUSE_SWEEP = os.environ.get("CNM_FUSE_SWEEP", "1")
@@ -326,6 +327,8 @@ def save_tune_cache(path):
 
 
 for _p in (SHIPPED_TUNE_CACHE, TUNE_CACHE_FILE):
+    if _p == SHIPPED_TUNE_CACHE and os.environ.get("CNM_NO_SHIPPED_TUNE", "0") == "1":
+        continue   # re-making the table: every shape is timed afresh
     if _p and os.path.exists(_p):
         load_tune_cache(_p)
 
@@ -348,6 +351,9 @@ class ConvOp:
         st[:, :5] = torch.tensor(steps, dtype=torch.int32)
         self.variants["tc"] = {"cols": cols, "steps_dev": st.to(device)}
         self.variants["simt"] = self.variants["tc"]
+        if dtype != CNM_TF32 and cout % 128 == 0 and backend != "simt" and TC_MULTICAST:
+            # same program on clusters of 2 / 4 CTAs sharing every weight tile by TMA multicast (cnm_conv_desc.cluster)
+            self.variants["tcm2"] = self.variants["tcm4"] = self.variants["tc"]
         halo_ok = Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2") and \
             (stride == 1 or all(s.kind == "act" for s in srcs))
         if halo_ok:
@@ -399,7 +405,8 @@ class ConvOp:
             self._sweep_scratch = torch.empty((nbytes,), dtype=torch.uint8, device=self.out.device)
             self.sweep.scratch, self.sweep.scratch_bytes = self._sweep_scratch.data_ptr(), nbytes
         self.desc.reserved = int(bn)
-        self.desc.ksplit = int(ksplit) if backend == "tc" else 1
+        self.desc.cluster = {"tcm2": 2, "tcm4": 4}.get(backend, 0)
+        self.desc.ksplit = int(ksplit) if backend in ("tc", "tcm2", "tcm4") else 1
         if self.desc.ksplit > 1:
             d = self.desc
             ws = splitk_workspace(self.out.device, d.ksplit * d.N * d.Ho * d.Wo * d.Cout, self.lane)
@@ -417,8 +424,10 @@ class ConvOp:
         for be in ("tc", "halo", "halo2"):
             if be in self.variants:
                 out += [(be, bn, 1) for bn in (256, 128, 64) if d.Cout % bn == 0]
-        if "halo2s" in self.variants:
-            out.append(("halo2s", d.Cout, 1))
+        # "halo2s" (fused plane sweep) is not timed here: it replaces the cost-volume launch as well, so it is compared
+        # at step level (bench.py, CNM_FUSE_SWEEP=force) and entered into the table by hand if it wins
+        mc = [be for be in ("tcm2", "tcm4") if be in self.variants]
+        out += [(be, bn, 1) for be in mc for bn in (256, 128) if d.Cout % bn == 0]
         if SPLITK and "tc" in self.variants and not getattr(self, "_head", None):
             tw = 16 if d.Wo >= 16 else 8
             th = min(128 // tw, 1 << max(d.Ho - 1, 0).bit_length())
@@ -431,6 +440,7 @@ class ConvOp:
                 for ks in (2, 3, 4, 6, 8):
                     if tiles < 120 and tiles * ks <= 304 and self.num_steps >= 8 * ks:
                         out.append(("tc", bn, ks))
+                        out += [(be, bn, ks) for be in mc if bn >= 128]
         return out
 
     def tune(self, stream, reps=3):
@@ -508,7 +518,7 @@ class ConvOp:
                                            v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),
                                            self.out.data_ptr(), stream), self.name)
             return
-        fn = lib.cnm_conv2d_tc if self.backend == "tc" else lib.cnm_conv2d_simt
+        fn = lib.cnm_conv2d_simt if self.backend == "simt" else lib.cnm_conv2d_tc
         _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["steps_dev"].data_ptr(), self.wp.data_ptr(),
                       self.bias.data_ptr(), self.out.data_ptr(), stream), self.name)
 

@@ -246,7 +246,10 @@ typedef struct cnm_conv_desc {
   int32_t ksplit;   /* cnm_conv2d_tc only: > 1 cuts the K loop of every output tile into ksplit ranges run by different
                        CTAs (layers with fewer tiles than SMs); partial accumulators go through splitk_ws and a second
                        kernel sums them in a fixed order.  0 / 1 = off. */
-  int32_t reserved2[2];
+  int32_t cluster;  /* cnm_conv2d_tc only, 2-byte dtypes, column tile >= 128: 2 or 4 = thread-block clusters of that many
+                       CTAs share every weight tile through TMA multicast (each CTA loads 1/cluster of it).  Same
+                       results as 0 / 1 (off): the K order of a tile does not change. */
+  int32_t reserved2;
   /* Optional fused 1-channel 3x3 head on this layer's output (depth_layer, depthnet/depthNet_model.py:82-84), for the
    * 2-byte dtypes (tensor-core kernels only): head_w = [9][Cout] fp32 tap-major weights (device, 16B aligned),
    * head_partial = [Cout/64][N, Ho, Wo, 12] fp32 (device, 16B aligned): every 64-channel chunk of the output writes,

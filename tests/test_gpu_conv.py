@@ -212,6 +212,48 @@ def test_split_k_matches_oracle(dtype, case, ksplit):
     assert rel_l2(outs[0], want) < L2_TOL[dtype]
 
 
+MC_DTYPES = [d for d in DTYPES if d != _lib.CNM_TF32]
+
+
+@pytest.mark.parametrize("dtype", MC_DTYPES)
+@pytest.mark.parametrize("case,bn,ksplit", [
+    ((5, 24, 32, [256], 512, 3, 1), 256, 1),      # the 24x32 level: 30 pixel tiles x 2 column tiles
+    ((5, 48, 64, [128], 256, 3, 1), 256, 1),      # the 48x64 level of the refine network: 120 tiles
+    ((3, 24, 32, [128], 256, 3, 2), 128, 1),      # stride 2 (parity sub-images), 5 pixel tiles: dummy tiles in the cluster
+    ((5, 12, 16, [64, 64], 256, 3, 1), 128, 2),   # ragged batch tile + split-K
+    ((2, 96, 128, [64], 128, 3, 1), 128, 1),      # more work items than clusters: several per CTA
+    ((1, 8, 16, [64], 128, 1, 1), 128, 1),        # one pixel tile: three of four CTAs of a cluster are dummies
+])
+def test_multicast_clusters_are_bit_identical_to_single_ctas(dtype, case, bn, ksplit):
+    """cnm_conv_desc.cluster = 2 / 4: the weight tiles arrive by TMA multicast from the cluster's CTAs; every tile still
+    accumulates its K-steps in the same order, so the output bits are those of the single-CTA launch."""
+    N, H, W, cins, cout, k, stride = case
+    g = torch.Generator().manual_seed(cout + bn + ksplit)
+    xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, generator=g) / np.sqrt(sum(cins) * k * k)
+    b = torch.randn(cout, generator=g)
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    acts = [to_act(x, dtype) for x in xs]
+    srcs = [engine.act_src(a, sum(cins[:i]), phys=engine.phys_factor(dtype)) for i, a in enumerate(acts)]
+    op = engine.ConvOp("t", srcs, k, stride, cout, N, Ho, Wo, dtype, dev(), True, backend="tc")
+    op.tunable = False
+    op.load(w, b)
+    outs = {}
+    for be in ("tc", "tcm2", "tcm4"):
+        assert be in op.variants
+        op.select(be, bn, ksplit)
+        assert op.desc.cluster == {"tc": 0, "tcm2": 2, "tcm4": 4}[be]
+        op.out.fill_(7)
+        op(_lib.stream_ptr())
+        torch.cuda.synchronize()
+        outs[be] = op.out.clone().view(torch.uint8)
+    want = oracle_conv(dtype, xs, w, b, k, stride)
+    assert rel_l2(from_act(op.out, dtype), want) < L2_TOL[dtype]
+    for be in ("tcm2", "tcm4"):
+        diff = int((outs[be] != outs["tc"]).sum())
+        assert diff == 0, "%s: %d of %d output bytes differ from the single-CTA kernel" % (be, diff, outs["tc"].numel())
+
+
 def test_conv_rejects_bad_arguments():
     lib = _lib.load()
     a = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=dev())  # 48 channels: not chunk aligned
