@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
                 ("c_out_total", C.c_int32), ("c_out_offset", C.c_int32), ("stride", C.c_int32), ("relu", C.c_int32),
                 ("num_srcs", C.c_int32), ("num_steps", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
-                ("acc_exp", C.c_int32), ("ksplit", C.c_int32), ("cluster", C.c_int32), ("reserved2", C.c_int32), ("head_w", C.c_void_p),
+                ("acc_exp", C.c_int32), ("ksplit", C.c_int32), ("cluster", C.c_int32), ("tile_h", C.c_int32), ("head_w", C.c_void_p),
                 ("head_partial", C.c_void_p), ("splitk_ws", C.c_void_p)]
 
 

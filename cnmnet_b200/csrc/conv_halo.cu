@@ -150,14 +150,19 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
 
 // CG = 1: one CTA per 16x16 pixel block, two MMA-issuing warps (one per half of the block).  CG = 2: a CTA pair on two
 // neighbouring blocks, one M = 256 MMA per half issued by the leader.
-template <int BN, bool TF32, int CG, bool SWEEP = false>
+// TH = 16: the CTA's pixel block is 16x16 (two M = 128 halves sharing every weight tile).  TH = 8 (CTA pairs only): one
+// 16x8 half per CTA -- twice the work items for maps with few blocks (the 48x64 / 24x32 levels), BN = 256 with two
+// accumulator stages, and still a slab per (chunk, dx) instead of a pixel tile per tap.
+template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
-  static_assert(!SWEEP || (!TF32 && 4 * BN <= 512), "the fused plane sweep needs two accumulator stages (BN <= 128)");
+  constexpr int HALVES = TH / 8;
+  static_assert(TH == 16 || (TH == 8 && CG == 2 && !SWEEP), "16x8 blocks: CTA-pair instantiations");
+  static_assert(!SWEEP || (!TF32 && 4 * BN <= 512 && TH == 16), "the fused plane sweep needs two accumulator stages (BN <= 128)");
   constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;
   constexpr int CHUNK_CH = TF32 ? 32 : 64;
   constexpr int NUM_CHUNKS = BN / COLS_PER_CHUNK;
-  constexpr int ACC_STAGES = (4 * BN <= 512) ? 2 : 1;
-  constexpr uint32_t TMEM_COLS = (2 * BN * ACC_STAGES) < 32 ? 32 : 2 * BN * ACC_STAGES;
+  constexpr int ACC_STAGES = (2 * HALVES * BN <= 512) ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = (HALVES * BN * ACC_STAGES) < 32 ? 32 : HALVES * BN * ACC_STAGES;
   constexpr int B_BYTES = (BN / CG) * 128;  // CG = 2: this CTA's half of the weight tile
   constexpr uint32_t IDESC_SHAPE = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);  // M = 128 per CTA
   constexpr uint32_t IDESC = IDESC_SHAPE | ((TF32 ? 2u : 1u) << 7) | ((TF32 ? 2u : 1u) << 10);
@@ -250,7 +255,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         int m = CG * (tile / p.tiles_n) + (int)rank;
         const int x0 = (m % p.tiles_x) * 16;
         m /= p.tiles_x;
-        const int y0 = (m % p.tiles_y) * 16;
+        const int y0 = (m % p.tiles_y) * TH;
         const int n0 = m / p.tiles_y;
         bool vol_ready = false;
         for (int g = 0; g < p.num_groups; ++g) {
@@ -317,7 +322,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(tempty(as), aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 2 * BN + half * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * HALVES * BN + half * BN);
         uint32_t first = 1;
         for (int g = 0; g < p.num_groups; ++g) {
           const int ntaps = __ldg(&p.groups[g].ntaps);
@@ -336,10 +341,10 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
                 if (CG == 2) {
                   if (f8) {
                     tc2_mma_f8(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
-                    tc2_mma_f8(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                    if (HALVES == 2) tc2_mma_f8(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
                   } else {
                     tc2_mma<TF32>(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
-                    tc2_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
+                    if (HALVES == 2) tc2_mma<TF32>(tmem_d + BN, a1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
                   }
                 } else {
                   if (f8) tc_mma_f8(tmem_d, a0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc);
@@ -396,7 +401,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       int m = CG * (tile / p.tiles_n) + (int)rank;
       const int x0 = (m % p.tiles_x) * 16;
       m /= p.tiles_x;
-      const int y0 = (m % p.tiles_y) * 16;
+      const int y0 = (m % p.tiles_y) * TH;
       const int n0 = m / p.tiles_y;
       const int slot = it & 1;
       if (it >= 2) {
@@ -508,7 +513,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       int m = CG * (tile / p.tiles_n) + (int)rank;
       const int x0 = (m % p.tiles_x) * 16;
       m /= p.tiles_x;
-      const int y0 = (m % p.tiles_y) * 16;
+      const int y0 = (m % p.tiles_y) * TH;
       const int n0 = m / p.tiles_y;
       const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
       const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
@@ -524,8 +529,8 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       else mbar_wait(tfull(as), aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * BN + half * BN);
+      for (int half = 0; half < HALVES; ++half) {
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * HALVES * BN + half * BN);
 #pragma unroll 1
         for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
           uint32_t v[COLS_PER_CHUNK];
@@ -594,6 +599,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_k
   conv_halo_body<BN, TF32, 2>(p);
 }
 
+// 16x8 pixel blocks on CTA pairs (maps with few 16x16 blocks)
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2h_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, false, 2, false, 8>(p);
+}
+
 // conv1.0 with the plane sweep fused in: CTA pairs + eight volume-producer warps per CTA
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) conv_halo2_sweep_kernel(const __grid_constant__ HaloParams p) {
@@ -633,8 +644,11 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   CNM_REQUIRE(d->Ho >= 16 && d->Wo >= 16, CNM_ERR_UNSUPPORTED_SHAPE,
               "%s: output %dx%d smaller than the 16x16 tile (use cnm_conv2d_tc)", fn, d->Ho, d->Wo);
   CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "%s: Cout=%d must be a multiple of 64", fn, d->Cout);
-  CNM_REQUIRE(CG == 1 || (((d->Wo + 15) / 16) * ((d->Ho + 15) / 16) * d->N) % 2 == 0, CNM_ERR_UNSUPPORTED_SHAPE,
-              "%s: needs an even number of 16x16 pixel blocks (CTA pairs)", fn);
+  CNM_REQUIRE(d->tile_h == 0 || d->tile_h == 16 || (d->tile_h == 8 && CG == 2 && !sweep && d->dtype != CNM_TF32),
+              CNM_ERR_UNSUPPORTED_SHAPE, "%s: tile_h = %d (8 = 16x8 blocks: cnm_conv2d_halo2, 2-byte dtypes)", fn, d->tile_h);
+  const int TH = d->tile_h == 8 ? 8 : 16;
+  CNM_REQUIRE(CG == 1 || (((d->Wo + 15) / 16) * ((d->Ho + TH - 1) / TH) * d->N) % 2 == 0, CNM_ERR_UNSUPPORTED_SHAPE,
+              "%s: needs an even number of 16x%d pixel blocks (CTA pairs)", fn, TH);
   const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
   HaloParams p;
   memset(&p, 0, sizeof(p));
@@ -648,14 +662,14 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
       CNM_REQUIRE(pad >= 0 && pad <= 4 && rows >= 16 && rows <= 24, CNM_ERR_UNSUPPORTED_SHAPE,
                   "%s: map %d has pad %d / %d slab rows", fn, m, pad, rows);
       p.map_pad[m] = pad;
-      p.map_rows[m] = rows;
-      if (rows > rows_max) rows_max = rows;
+      p.map_rows[m] = rows - (16 - TH);   // map_info counts a 16-row block; a 16x8 block needs 8 rows less
+      if (p.map_rows[m] > rows_max) rows_max = p.map_rows[m];
     }
   CNM_REQUIRE(rows_max > 0, CNM_ERR_INVALID_ARGUMENT, "%s: no operand maps", fn);
-  const int pmax = (rows_max - 16 + 1) / 2;
+  const int pmax = (rows_max - TH + 1) / 2;
   p.slab_bytes = rows_max * 2048;
   p.tiles_x = (d->Wo + 15) / 16;
-  p.tiles_y = (d->Ho + 15) / 16;
+  p.tiles_y = (d->Ho + TH - 1) / TH;
   p.tiles_b = d->N;
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
   // column tile: minimise waves x relative tile time.  BN=256 holds 2 x 256 accumulator columns = all of TMEM, so its
@@ -794,6 +808,16 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
     if (BN == 128) conv_halo2_sweep_kernel<128><<<grid, 512, smem, s>>>(p);
     else conv_halo2_sweep_kernel<64><<<grid, 512, smem, s>>>(p);
+    return after_launch(fn);
+  }
+  if (TH == 8) {
+    static DynSmemLimit l64, l128, l256;
+    cudaError_t e = BN == 256 ? l256.ensure(conv_halo2h_kernel<256>, smem)
+                              : (BN == 128 ? l128.ensure(conv_halo2h_kernel<128>, smem) : l64.ensure(conv_halo2h_kernel<64>, smem));
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
+    if (BN == 256) conv_halo2h_kernel<256><<<grid, 256, smem, s>>>(p);
+    else if (BN == 128) conv_halo2h_kernel<128><<<grid, 256, smem, s>>>(p);
+    else conv_halo2h_kernel<64><<<grid, 256, smem, s>>>(p);
     return after_launch(fn);
   }
   if (BN == 256) return tf32 ? launch_halo<256, true, CG>(p, grid, smem, s) : launch_halo<256, false, CG>(p, grid, smem, s);

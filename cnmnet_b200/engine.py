@@ -354,7 +354,7 @@ class ConvOp:
         if dtype != CNM_TF32 and cout % 128 == 0 and backend != "simt" and TC_MULTICAST:
             # same program on clusters of 2 / 4 CTAs sharing every weight tile by TMA multicast (cnm_conv_desc.cluster)
             self.variants["tcm2"] = self.variants["tcm4"] = self.variants["tc"]
-        halo_ok = Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2") and \
+        halo_ok = Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2", "halo2h") and \
             (stride == 1 or all(s.kind == "act" for s in srcs))
         if halo_ok:
             groups, gcols, info = make_groups(srcs, k, ch, stride, split)
@@ -364,7 +364,9 @@ class ConvOp:
                                      "ngroups": len(groups), "pads": (C.c_int32 * len(flat))(*flat)}
             if (N * ((Ho + 15) // 16) * ((Wo + 15) // 16)) % 2 == 0 and HALO2_ENABLED:
                 self.variants["halo2"] = self.variants["halo"]   # same program, CTA-pair kernel
-        elif backend in ("halo", "halo2"):
+            if (N * ((Ho + 7) // 8) * ((Wo + 15) // 16)) % 2 == 0 and HALO2_ENABLED and dtype != CNM_TF32:
+                self.variants["halo2h"] = self.variants["halo"]  # same program, CTA pairs on 16x8 blocks (tile_h = 8)
+        elif backend in ("halo", "halo2", "halo2h"):
             raise ValueError("%s: the row-halo kernel needs an output of at least 16x16" % name)
         self.num_steps = len(cols)
         self.out = out if out is not None else torch.empty((N, Ho, Wo, cout * pf), dtype=TORCH_DTYPE[dtype],
@@ -390,7 +392,7 @@ class ConvOp:
         halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
         if backend == "tc" and halo_ok and HALO_MODE != "off" and (halo_tiles >= 120 or HALO_MODE == "force"):
             backend = "halo"
-        self.tunable = backend in ("tc", "halo", "halo2") and HALO_MODE == "auto"
+        self.tunable = backend in ("tc", "halo", "halo2", "halo2h") and HALO_MODE == "auto"
         self.select(backend, 0)
 
     @property
@@ -406,6 +408,7 @@ class ConvOp:
             self.sweep.scratch, self.sweep.scratch_bytes = self._sweep_scratch.data_ptr(), nbytes
         self.desc.reserved = int(bn)
         self.desc.cluster = {"tcm2": 2, "tcm4": 4}.get(backend, 0)
+        self.desc.tile_h = 8 if backend == "halo2h" else 0
         self.desc.ksplit = int(ksplit) if backend in ("tc", "tcm2", "tcm4") else 1
         if self.desc.ksplit > 1:
             d = self.desc
@@ -421,7 +424,7 @@ class ConvOp:
         """(kernel, output-channel tile, split-K factor) combinations worth timing for this layer."""
         d = self.desc
         out = []
-        for be in ("tc", "halo", "halo2"):
+        for be in ("tc", "halo", "halo2", "halo2h"):
             if be in self.variants:
                 out += [(be, bn, 1) for bn in (256, 128, 64) if d.Cout % bn == 0]
         # "halo2s" (fused plane sweep) is not timed here: it replaces the cost-volume launch as well, so it is compared
@@ -512,7 +515,7 @@ class ConvOp:
                                                   v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),
                                                   self.out.data_ptr(), C.byref(self.sweep), stream), self.name)
             return
-        if self.backend in ("halo", "halo2"):
+        if self.backend in ("halo", "halo2", "halo2h"):
             fn = lib.cnm_conv2d_halo if self.backend == "halo" else lib.cnm_conv2d_halo2
             _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(),
                                            v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),

@@ -249,7 +249,8 @@ typedef struct cnm_conv_desc {
   int32_t cluster;  /* cnm_conv2d_tc only, 2-byte dtypes, column tile >= 128: 2 or 4 = thread-block clusters of that many
                        CTAs share every weight tile through TMA multicast (each CTA loads 1/cluster of it).  Same
                        results as 0 / 1 (off): the K order of a tile does not change. */
-  int32_t reserved2;
+  int32_t tile_h;   /* cnm_conv2d_halo2 only, 2-byte dtypes: 8 = 16x8 pixel blocks per CTA instead of 16x16 (maps with few
+                       blocks: twice the work items, two accumulator stages at a column tile of 256).  0 / 16 = 16x16. */
   /* Optional fused 1-channel 3x3 head on this layer's output (depth_layer, depthnet/depthNet_model.py:82-84), for the
    * 2-byte dtypes (tensor-core kernels only): head_w = [9][Cout] fp32 tap-major weights (device, 16B aligned),
    * head_partial = [Cout/64][N, Ho, Wo, 12] fp32 (device, 16B aligned): every 64-channel chunk of the output writes,

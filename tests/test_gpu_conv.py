@@ -99,12 +99,14 @@ HALO_CASES = [
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("case", HALO_CASES)
-@pytest.mark.parametrize("backend", ["halo", "halo2"])
+@pytest.mark.parametrize("backend", ["halo", "halo2", "halo2h"])
 def test_halo_conv_matches_oracle(backend, dtype, case):
     N, H, W, cins, cout, k, stride = case
     Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
     if backend == "halo2" and (N * ((Ho + 15) // 16) * ((Wo + 15) // 16)) % 2:
         pytest.skip("the CTA-pair kernel needs an even number of 16x16 pixel blocks")
+    if backend == "halo2h" and (dtype == _lib.CNM_TF32 or (N * ((Ho + 7) // 8) * ((Wo + 15) // 16)) % 2):
+        pytest.skip("16x8 blocks: 2-byte dtypes, even number of blocks")
     g = torch.Generator().manual_seed(N * 1000 + H * 7 + W + cout + k * 13)
     xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
     w = torch.randn(cout, sum(cins), k, k, generator=g) / np.sqrt(sum(cins) * k * k)
@@ -213,6 +215,41 @@ def test_split_k_matches_oracle(dtype, case, ksplit):
 
 
 MC_DTYPES = [d for d in DTYPES if d != _lib.CNM_TF32]
+
+
+@pytest.mark.parametrize("dtype", MC_DTYPES)
+@pytest.mark.parametrize("case,bn", [((5, 48, 64, [128], 256, 3, 1), 256),    # refine 48x64 level: 60 pairs, one per CTA pair
+                                     ((10, 48, 64, [64], 256, 3, 1), 256),    # 120 pairs: two accumulator stages in use
+                                     ((5, 24, 32, [256], 512, 3, 1), 128),
+                                     ((2, 40, 72, [64], 256, 5, 2), 256),     # stride 2, partial blocks
+                                     ((10, 192, 256, [64], 64, 3, 1), 64)])
+def test_half_block_halo_matches_oracle_and_full_blocks(dtype, case, bn):
+    """cnm_conv_desc.tile_h = 8 (16x8 blocks on CTA pairs) against the oracle, and bit-identical to the 16x16-block
+    CTA-pair kernel where that runs: a pixel's K-steps come in the same order in both."""
+    N, H, W, cins, cout, k, stride = case
+    g = torch.Generator().manual_seed(cout + bn + N)
+    xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, generator=g) / np.sqrt(sum(cins) * k * k)
+    b = torch.randn(cout, generator=g)
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    acts = [to_act(x, dtype) for x in xs]
+    srcs = [engine.act_src(a, sum(cins[:i]), phys=engine.phys_factor(dtype)) for i, a in enumerate(acts)]
+    op = engine.ConvOp("t", srcs, k, stride, cout, N, Ho, Wo, dtype, dev(), True, backend="halo2h")
+    op.tunable = False
+    op.load(w, b)
+    outs = {}
+    for be in ("halo2h", "halo2"):
+        if be not in op.variants:
+            continue
+        op.select(be, bn)
+        op.out.fill_(7)
+        op(_lib.stream_ptr())
+        torch.cuda.synchronize()
+        outs[be] = op.out.clone().view(torch.uint8)
+        assert rel_l2(from_act(op.out, dtype), oracle_conv(dtype, xs, w, b, k, stride)) < L2_TOL[dtype]
+    if "halo2" in outs:
+        diff = int((outs["halo2h"] != outs["halo2"]).sum())
+        assert diff == 0, "%d of %d output bytes differ between 16x8 and 16x16 blocks" % (diff, outs["halo2"].numel())
 
 
 @pytest.mark.parametrize("dtype", MC_DTYPES)
