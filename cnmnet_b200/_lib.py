@@ -44,6 +44,7 @@ SIGNATURES = {
     "cnm_version": (C.c_char_p, []),
     "cnm_launch_count": (_L, []),
     "cnm_set_range_check": (None, [_I]),
+    "cnm_set_pdl": (None, [_I]),
     "cnm_range_overflow_count": (_L, [_I]),
     "cnm_camera_setup": (_I, [_P, _P, _P, _I, _I, _P]),
     "cnm_packed_source_bytes": (_L, [_I, _I, _I]),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "cnm_head_partial": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cnm_head_finish": (_I, [_P, _I, _F, _F, _P, _P, _I, _I, _I, _P]),
     "cnm_conv2d_tc": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
+    "cnm_debug_conv_timeline": (_I, [C.POINTER(C.c_longlong)]),
     "cnm_conv2d_simt": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
     "cnm_conv2d_halo": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P, _P]),
     "cnm_conv2d_halo2": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P, _P]),

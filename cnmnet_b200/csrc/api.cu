@@ -28,6 +28,18 @@ unsigned long long* range_counter() {
 }
 }  // namespace cnm
 
+namespace cnm {
+static int g_pdl = -1;  // -1: environment (CNM_PDL, default on)
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("CNM_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+}  // namespace cnm
+
+extern "C" void cnm_set_pdl(int enable) { cnm::g_pdl = enable ? 1 : 0; }
 extern "C" void cnm_set_range_check(int enable) { cnm::g_range_check = enable ? 1 : 0; }
 extern "C" int64_t cnm_range_overflow_count(int reset) {
   if (cnm::g_range_check != 1) return -1;

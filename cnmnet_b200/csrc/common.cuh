@@ -48,6 +48,33 @@ struct DynSmemLimit {
   }
 };
 
+// ---- programmatic dependent launch -------------------------------------------------------------------------------
+// The kernels of a pipeline step run back to back on one stream (as a CUDA graph).  Launched through launch_pdl they
+// carry cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may be scheduled while this one is
+// still running -- as soon as all of its CTAs have called pdl_trigger() and an SM has room -- and run their prologue
+// (barrier init, TMEM allocation, descriptor prefetch) up to pdl_wait(), which blocks until the previous kernel has
+// completed and its writes are visible.  EVERY global-memory access of a kernel launched this way comes after its
+// pdl_wait().  CNM_PDL=0 turns the attribute off (plain stream order); the device-side calls are no-ops then.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // api.cu
+
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 #define CNM_REQUIRE(cond, code, ...) \
   do {                               \
     if (!(cond)) return ::cnm::fail(code, __VA_ARGS__); \

@@ -155,6 +155,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
 // accumulator stages, and still a slab per (chunk, dx) instead of a pixel tile per tap.
 template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
+  pdl_trigger();
   constexpr int HALVES = TH / 8;
   static_assert(TH == 16 || (TH == 8 && CG == 2 && !SWEEP), "16x8 blocks: CTA-pair instantiations");
   static_assert(!SWEEP || (!TF32 && 4 * BN <= 512 && TH == 16), "the fused plane sweep needs two accumulator stages (BN <= 128)");
@@ -234,6 +235,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (SWEEP) {
     // 512 threads share the register file at 128 each; the epilogue warpgroup needs ~200 (64 accumulator columns in
@@ -617,8 +619,8 @@ static int launch_halo(const HaloParams& p, int grid, int smem, cudaStream_t s) 
   const char* fn = CG == 2 ? "cnm_conv2d_halo2" : "cnm_conv2d_halo";
   cudaError_t e = CG == 2 ? limit.ensure(conv_halo2_kernel<BN, TF32>, smem) : limit.ensure(conv_halo_kernel<BN, TF32>, smem);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
-  if (CG == 2) conv_halo2_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
-  else conv_halo_kernel<BN, TF32><<<grid, 256, smem, s>>>(p);
+  if (CG == 2) launch_pdl(conv_halo2_kernel<BN, TF32>, dim3(grid), dim3(256), smem, s, p);
+  else launch_pdl(conv_halo_kernel<BN, TF32>, dim3(grid), dim3(256), smem, s, p);
   return after_launch(fn);
 }
 
@@ -806,8 +808,8 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     static DynSmemLimit limit64, limit128;
     cudaError_t e = BN == 128 ? limit128.ensure(conv_halo2_sweep_kernel<128>, smem) : limit64.ensure(conv_halo2_sweep_kernel<64>, smem);
     if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
-    if (BN == 128) conv_halo2_sweep_kernel<128><<<grid, 512, smem, s>>>(p);
-    else conv_halo2_sweep_kernel<64><<<grid, 512, smem, s>>>(p);
+    if (BN == 128) launch_pdl(conv_halo2_sweep_kernel<128>, dim3(grid), dim3(512), smem, s, p);
+    else launch_pdl(conv_halo2_sweep_kernel<64>, dim3(grid), dim3(512), smem, s, p);
     return after_launch(fn);
   }
   if (TH == 8) {
@@ -815,9 +817,9 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     cudaError_t e = BN == 256 ? l256.ensure(conv_halo2h_kernel<256>, smem)
                               : (BN == 128 ? l128.ensure(conv_halo2h_kernel<128>, smem) : l64.ensure(conv_halo2h_kernel<64>, smem));
     if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
-    if (BN == 256) conv_halo2h_kernel<256><<<grid, 256, smem, s>>>(p);
-    else if (BN == 128) conv_halo2h_kernel<128><<<grid, 256, smem, s>>>(p);
-    else conv_halo2h_kernel<64><<<grid, 256, smem, s>>>(p);
+    if (BN == 256) launch_pdl(conv_halo2h_kernel<256>, dim3(grid), dim3(256), smem, s, p);
+    else if (BN == 128) launch_pdl(conv_halo2h_kernel<128>, dim3(grid), dim3(256), smem, s, p);
+    else launch_pdl(conv_halo2h_kernel<64>, dim3(grid), dim3(256), smem, s, p);
     return after_launch(fn);
   }
   if (BN == 256) return tf32 ? launch_halo<256, true, CG>(p, grid, smem, s) : launch_halo<256, false, CG>(p, grid, smem, s);

@@ -27,6 +27,7 @@
 //                  operand delivery (bytes in flight / loaded L2 latency), not by MMA time.
 // Warp roles     warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 = TMEM
 //                  allocator, warp 3 idle, warps 4-7 = epilogue (TMEM lane quarter = warp - 4).
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -58,6 +59,7 @@ struct alignas(64) TcParams {
   int ksplit;       // > 1: the K loop of every output tile is cut into ksplit ranges run by different CTAs
   float* ws;        // split-K workspace [ksplit][N*Ho*Wo][Cout] fp32 (raw accumulators; splitk_finish_kernel sums them)
   int cout;
+  long long* dbg;   // CNM_CONV_TIMELINE=1: clock64 stamps of CTA 0 (tools/conv_timeline.py), else NULL
 };
 
 template <int BN, int STAGES, bool TF32>
@@ -78,6 +80,9 @@ struct TcSmem {
 template <int BN, int STAGES, bool TF32, int CL>
 __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
   using L = TcSmem<BN, STAGES, TF32>;
+  const bool stamp = p.dbg != nullptr && blockIdx.x == 0;
+  if (stamp && threadIdx.x == 0) p.dbg[0] = clock64();
+  pdl_trigger();
   constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   // work item q of a cluster = (pixel-tile group, column tile, K range); CTA `rank` takes pixel tile CL * group + rank
@@ -136,6 +141,9 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (stamp && threadIdx.x == 0) p.dbg[1] = clock64();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  if (stamp && threadIdx.x == 0) p.dbg[2] = clock64();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -171,6 +179,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
                            nt * BN + (int)rank * (BN / CL), CL_MASK);
           else
             tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), ks * CHUNK_CH, nt * BN);
+          if (stamp && tile == first_q && ks == kbeg(part)) p.dbg[3] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -192,6 +201,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
         const int k_begin = kbeg(tile % p.ksplit), k_end = kbeg(tile % p.ksplit + 1);
         for (int ks = k_begin; ks < k_end; ++ks) {
           mbar_wait(full_bar(stage), phase);
+          if (stamp && lane == 0 && tile == first_q && ks == k_begin) p.dbg[4] = clock64();
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = base + stage * L::STAGE_BYTES;
@@ -212,6 +222,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
             if (ks == k_end - 1) tc_commit(tfull_bar(as));  // accumulator complete
           }
           __syncwarp();
+          if (stamp && lane == 0 && tile == first_q && ks == k_end - 1) p.dbg[5] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -269,6 +280,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
         epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
       mbar_wait(tfull_bar(as), aphase);
+      if (stamp && et == 0 && tile == first_q) p.dbg[6] = clock64();
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
@@ -308,11 +320,13 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
       mbar_arrive(tempty_bar(as));  // 128 arrivals release the accumulator stage
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (stamp && et == 0) p.dbg[7] = clock64();
   }
 
   tc_fence_before();
   if (CL > 1) cluster_sync_all();  // a peer may still be writing this CTA's ring or arriving on its barriers
   else __syncthreads();
+  if (stamp && threadIdx.x == 0) p.dbg[8] = clock64();
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -340,6 +354,8 @@ __global__ void __launch_bounds__(256)
     splitk_finish_kernel(const float* __restrict__ ws, int ksplit, size_t mtot, int cout, const float* __restrict__ bias,
                          float scale, int relu, uint8_t* __restrict__ out, size_t pix_bytes, size_t off_bytes,
                          unsigned long long* range_ctr) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = cout >> 3;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= mtot * groups) return;
@@ -414,7 +430,7 @@ static int launch_tc(const TcParams& p, int grid, cudaStream_t s) {
   static DynSmemLimit limit;
   cudaError_t e = limit.ensure(conv_tc_kernel<BN, STAGES, TF32>, L::TOTAL);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
-  conv_tc_kernel<BN, STAGES, TF32><<<grid, TC_THREADS, L::TOTAL, s>>>(p);
+  launch_pdl(conv_tc_kernel<BN, STAGES, TF32>, dim3(grid), dim3(TC_THREADS), L::TOTAL, s, p);
   return after_launch("cnm_conv2d_tc");
 }
 
@@ -446,13 +462,16 @@ static int launch_tc_mc(const TcParams& p, int total_q, cudaStream_t s) {
     mc = n;
   }
   const int clusters = total_q < mc ? total_q : mc;
-  kernel<<<clusters * CL, TC_THREADS, L::TOTAL, s>>>(p);
+  launch_pdl(kernel, dim3(clusters * CL), dim3(TC_THREADS), L::TOTAL, s, p);
   return after_launch("cnm_conv2d_tc");
 }
 
 }  // namespace cnm
 
 using namespace cnm;
+
+static long long* g_tc_dbg_buf = nullptr;
+static int g_tc_dbg_on = -1;
 
 extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, const cnm_conv_step* steps,
                              const void* wp, const float* bias, void* out, void* stream) {
@@ -504,6 +523,15 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.ksplit = d->ksplit > 1 ? d->ksplit : 1;
   p.ws = d->splitk_ws;
   p.cout = d->Cout;
+  if (g_tc_dbg_on < 0) {  // debugging aid: per-role time stamps of CTA 0 (cnm_debug_conv_timeline)
+    const char* e = getenv("CNM_CONV_TIMELINE");
+    g_tc_dbg_on = (e && e[0] == '1') ? 1 : 0;
+    if (g_tc_dbg_on && (cudaMalloc(&g_tc_dbg_buf, 16 * sizeof(long long)) != cudaSuccess ||
+                        cudaMemset(g_tc_dbg_buf, 0, 16 * sizeof(long long)) != cudaSuccess)) {
+      g_tc_dbg_on = 0; g_tc_dbg_buf = nullptr; cudaGetLastError();
+    }
+  }
+  p.dbg = g_tc_dbg_on == 1 ? g_tc_dbg_buf : nullptr;
   if (p.ksplit > 1) {
     CNM_REQUIRE(d->splitk_ws && (((uintptr_t)d->splitk_ws) & 15) == 0, CNM_ERR_INVALID_ARGUMENT,
                 "cnm_conv2d_tc: ksplit = %d needs a 16B-aligned splitk_ws", d->ksplit);
@@ -568,11 +596,21 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   const unsigned blocks = (unsigned)((out_vecs + 255) / 256);
   const size_t pix_bytes = (size_t)d->c_out_total * eb, off_bytes = (size_t)d->c_out_offset * eb;
 #define CNM_FINISH(T) \
-  splitk_finish_kernel<T><<<blocks, 256, 0, s>>>(p.ws, p.ksplit, mtot, d->Cout, bias, p.acc_scale, d->relu, (uint8_t*)out, pix_bytes, off_bytes, p.range_ctr)
+  launch_pdl(splitk_finish_kernel<T>, dim3(blocks), dim3(256), 0, s, p.ws, p.ksplit, mtot, d->Cout, bias, p.acc_scale, d->relu, (uint8_t*)out, pix_bytes, off_bytes, p.range_ctr)
   if (d->dtype == CNM_BF16) CNM_FINISH(__nv_bfloat16);
   else if (d->dtype == CNM_TF32) CNM_FINISH(float);
   else if (d->dtype == CNM_BF16X3) CNM_FINISH(bf16s);
   else CNM_FINISH(h16f8);
 #undef CNM_FINISH
   return after_launch("cnm_conv2d_tc(split-K finish)");
+}
+
+// CNM_CONV_TIMELINE=1: the clock64 stamps CTA 0 of the last cnm_conv2d_tc launch left (synchronises the device)
+extern "C" int cnm_debug_conv_timeline(long long* out9) {
+  CNM_REQUIRE(out9, CNM_ERR_INVALID_ARGUMENT, "cnm_debug_conv_timeline: null pointer");
+  CNM_REQUIRE(g_tc_dbg_buf, CNM_ERR_INVALID_ARGUMENT, "cnm_debug_conv_timeline: set CNM_CONV_TIMELINE=1 before the first convolution");
+  cudaError_t e = cudaMemcpy(out9, g_tc_dbg_buf, 9 * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_debug_conv_timeline: %s", cudaGetErrorString(e));
+  cudaMemset(g_tc_dbg_buf, 0, 16 * sizeof(long long));
+  return CNM_OK;
 }

@@ -56,6 +56,8 @@ __device__ bool invert_n(double* a, double* inv, int n) {
 
 __global__ void camera_setup_kernel(const float* __restrict__ ref_cam, const float* __restrict__ src_cam,
                                     float* __restrict__ hk, int B, int V) {
+  pdl_trigger();
+  pdl_wait();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= B * V) return;
   int b = p % B;
@@ -99,6 +101,8 @@ __global__ void camera_setup_kernel(const float* __restrict__ ref_cam, const flo
 // source repack: NCHW planar -> zero-bordered pixel-interleaved float4
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_source_kernel(const float* __restrict__ src, float4* __restrict__ tex, int N, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const int pitch = W + 4, rows = H + 3;
   size_t total = (size_t)N * rows * pitch;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -127,6 +131,8 @@ template <int DPB, int LAYOUT>  // LAYOUT: 0 = NCHW fp32, 1 = act bf16, 2 = act 
 __global__ void __launch_bounds__(CV_TX* CV_TY)
     cost_volume_kernel(const float* __restrict__ ref, const float4* __restrict__ tex, const float* __restrict__ hk,
                        void* __restrict__ out, int B, int H, int W, int D, double idmin, double idstep) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float zs[DPB];
   const int groups = D / DPB;
   const int p = blockIdx.z / groups;
@@ -186,7 +192,7 @@ extern "C" int cnm_camera_setup(const float* ref_cam, const float* src_cam, floa
   CNM_REQUIRE(ref_cam && src_cam && hk, CNM_ERR_INVALID_ARGUMENT, "cnm_camera_setup: null pointer");
   CNM_REQUIRE(B > 0 && V > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_camera_setup: B=%d V=%d", B, V);
   int n = B * V;
-  camera_setup_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(ref_cam, src_cam, hk, B, V);
+  launch_pdl(camera_setup_kernel, dim3((n + 63) / 64), dim3(64), 0, (cudaStream_t)stream, ref_cam, src_cam, hk, B, V);
   return after_launch("cnm_camera_setup");
 }
 
@@ -202,7 +208,7 @@ extern "C" int cnm_pack_source(const float* src, void* packed, int N, int H, int
   size_t total = (size_t)N * (H + 3) * (W + 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_source_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (float4*)packed, N, H, W);
+  launch_pdl(pack_source_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, (float4*)packed, N, H, W);
   return after_launch("cnm_pack_source");
 }
 
@@ -225,15 +231,15 @@ extern "C" int cnm_cost_volume(const float* ref, const void* packed_src, const f
   cudaStream_t s = (cudaStream_t)stream;
   const float4* tex = (const float4*)packed_src;
   if (layout == CNM_VOLUME_NCHW_F32)
-    cost_volume_kernel<DPB, 0><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    launch_pdl(cost_volume_kernel<DPB, 0>, dim3(grid), dim3(block), 0, s, ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else if (dtype == CNM_BF16)
-    cost_volume_kernel<DPB, 1><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    launch_pdl(cost_volume_kernel<DPB, 1>, dim3(grid), dim3(block), 0, s, ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else if (dtype == CNM_TF32)
-    cost_volume_kernel<DPB, 2><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    launch_pdl(cost_volume_kernel<DPB, 2>, dim3(grid), dim3(block), 0, s, ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else if (dtype == CNM_BF16X3)
-    cost_volume_kernel<DPB, 3><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    launch_pdl(cost_volume_kernel<DPB, 3>, dim3(grid), dim3(block), 0, s, ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else if (dtype == CNM_F16F8)
-    cost_volume_kernel<DPB, 4><<<grid, block, 0, s>>>(ref, tex, hk, out, B, H, W, D, idepth_min, step);
+    launch_pdl(cost_volume_kernel<DPB, 4>, dim3(grid), dim3(block), 0, s, ref, tex, hk, out, B, H, W, D, idepth_min, step);
   else
     return fail(CNM_ERR_INVALID_ARGUMENT, "cnm_cost_volume: dtype %d", dtype);
   return after_launch("cnm_cost_volume");

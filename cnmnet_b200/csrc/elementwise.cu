@@ -81,6 +81,8 @@ __device__ __forceinline__ void emit_rows(void* dst_block, const float* v, int v
 template <typename T, int KW, int CX>
 __global__ void __launch_bounds__(PACK_THREADS)
     pack_row_taps_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int CH = ActTraits<T>::CHUNK;
   static_assert(KW * CX <= CH, "taps must fit one chunk");
   const size_t HW = (size_t)H * W, total = (size_t)N * HW;
@@ -107,6 +109,8 @@ __global__ void __launch_bounds__(PACK_THREADS)
 template <typename T>
 __global__ void __launch_bounds__(PACK_THREADS)
     pack_disp_taps_kernel(const float* __restrict__ disp, T* __restrict__ dst, int N, int h, int w) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int CH = ActTraits<T>::CHUNK;
   const int H = 2 * h, W = 2 * w;
   const size_t HW = (size_t)H * W, total = (size_t)N * HW;
@@ -143,6 +147,8 @@ template <typename T>
 __global__ void __launch_bounds__(PACK_THREADS)
     refine_taps_kernel(const float* __restrict__ idepth, T* __restrict__ taps, float* __restrict__ id_out, int B, int H,
                        int W, int group) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int CH = ActTraits<T>::CHUNK;
   const size_t HW = (size_t)H * W, BHW = (size_t)B * HW;
   const size_t i0 = (size_t)blockIdx.x * PACK_THREADS, i = i0 + threadIdx.x;
@@ -174,6 +180,8 @@ __global__ void __launch_bounds__(PACK_THREADS)
 // sum_act = mean_0(iconv) + mean_1(iconv) on act tensors [V*B,H,W,64]; one 16-byte vector per thread
 template <typename T>
 __global__ void refine_sum_act_kernel(const T* __restrict__ iconv, T* __restrict__ out, size_t per_view, int group) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * VN;
   if (i >= per_view) return;
@@ -222,6 +230,8 @@ __global__ void refine_sum_nchw_kernel(const float* __restrict__ iconv, T* __res
 // one thread per (low-res pixel, 16-byte channel vector): 9 clamped loads in flight -> the 2x2 output quad
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ src, T* __restrict__ dst, int N, int h, int w, int C) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VN = Vec16<T>::N;
   const int cv = C / VN;
   const size_t total = (size_t)N * h * w * cv;
@@ -295,6 +305,8 @@ __device__ __forceinline__ void store_h16f8_vec(uint8_t* __restrict__ hi, uint8_
 
 __global__ void __launch_bounds__(256)
     upsample2x_h16f8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int N, int h, int w, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int cv = C >> 3;
   const unsigned total = (unsigned)(N * h * w * cv);
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,6 +365,8 @@ struct alignas(64) HeadParams {
 
 template <typename T, int LPP>
 __global__ void __launch_bounds__(256, 2) head3x3_kernel(const __grid_constant__ HeadParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t hsm_raw[];
   constexpr int VN = Vec16<T>::N;
   const int C = p.C, PC = p.PC, TR = p.TR, npix = (TR + 2) * 34;
@@ -437,6 +451,8 @@ __global__ void __launch_bounds__(256, 2) head3x3_kernel(const __grid_constant__
 __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restrict__ partial, int nslices, float bias,
                                                           float scale, float* __restrict__ out,
                                                           float* __restrict__ logits, int N, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = (size_t)N * H * W;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -464,6 +480,8 @@ __global__ void __launch_bounds__(256) head_finish_kernel(const float* __restric
 template <typename T, int LPP>
 __global__ void __launch_bounds__(256) head_partial_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                            float* __restrict__ partial, size_t npix, int C) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float hp_ws[];  // [9][C]
   constexpr int VN = Vec16<T>::N, GROUPS = 256 / LPP;
   for (int i = threadIdx.x; i < 9 * C; i += 256) hp_ws[i] = __ldg(w + i);
@@ -513,7 +531,7 @@ static int launch_head_partial(const T* x, const float* w, float* partial, size_
   {                                                                                         \
     const long need = (long)((npix + 256 / LPP - 1) / (256 / LPP));                         \
     if (need < blocks) blocks = need;                                                       \
-    head_partial_kernel<T, LPP><<<(unsigned)blocks, 256, smem, s>>>(x, w, partial, npix, C); \
+    launch_pdl(head_partial_kernel<T, LPP>, dim3((unsigned)blocks), dim3(256), smem, s, x, w, partial, npix, C); \
   }
   if (lanes >= 32) CNM_HP(32) else if (lanes >= 16) CNM_HP(16) else CNM_HP(8)
 #undef CNM_HP
@@ -525,7 +543,7 @@ static int launch_head_lpp(const HeadParams& p, dim3 grid, size_t smem, cudaStre
   static DynSmemLimit limit;
   cudaError_t e = limit.ensure(head3x3_kernel<T, LPP>, smem);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_head3x3: smem attribute: %s", cudaGetErrorString(e));
-  head3x3_kernel<T, LPP><<<grid, 256, smem, s>>>(p);
+  launch_pdl(head3x3_kernel<T, LPP>, dim3(grid), dim3(256), smem, s, p);
   return CNM_OK;
 }
 
@@ -601,16 +619,14 @@ extern "C" int cnm_pack_row_taps(const float* x, void* dst, int N, int Nsrc, int
   CNM_REQUIRE(kw == 7 && Cx == 3, CNM_ERR_UNSUPPORTED_SHAPE,
               "cnm_pack_row_taps: only kw=7, Cx=3 (conv1.0 of DepthNet) is instantiated, got kw=%d Cx=%d", kw, Cx);
   const size_t total = (size_t)N * H * W;
-  DISPATCH_DTYPE(dtype, (pack_row_taps_kernel<T, 7, 3><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-                            x, (T*)dst, N, Nsrc, H, W)));
+  DISPATCH_DTYPE(dtype, (launch_pdl(pack_row_taps_kernel<T, 7, 3>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, x, (T*)dst, N, Nsrc, H, W)));
   return after_launch("cnm_pack_row_taps");
 }
 
 extern "C" int cnm_pack_disp_taps(const float* disp, void* dst, int N, int h, int w, int dtype, void* stream) {
   CNM_REQUIRE(disp && dst && N > 0 && h > 0 && w > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_pack_disp_taps: bad argument");
   const size_t total = (size_t)N * 4 * h * w;
-  DISPATCH_DTYPE(dtype, (pack_disp_taps_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-                            disp, (T*)dst, N, h, w)));
+  DISPATCH_DTYPE(dtype, (launch_pdl(pack_disp_taps_kernel<T>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, disp, (T*)dst, N, h, w)));
   return after_launch("cnm_pack_disp_taps");
 }
 
@@ -622,11 +638,11 @@ extern "C" int cnm_refine_aggregate(const float* idepth, const void* iconv, void
   const size_t px = (size_t)B * H * W, per_view = px * 64;
   cudaStream_t s = (cudaStream_t)stream;
   DISPATCH_DTYPE(dtype, {
-    refine_taps_kernel<T><<<(unsigned)((px + 127) / 128), 128, 0, s>>>(idepth, (T*)taps_act, id_out, B, H, W, group);
+    launch_pdl(refine_taps_kernel<T>, dim3((unsigned)((px + 127) / 128)), dim3(128), 0, s, idepth, (T*)taps_act, id_out, B, H, W, group);
     int rc = after_launch("cnm_refine_aggregate(taps)");
     if (rc) return rc;
     const size_t nv = per_view / Vec16<T>::N;
-    refine_sum_act_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, s>>>((const T*)iconv, (T*)sum_act, per_view, group);
+    launch_pdl(refine_sum_act_kernel<T>, dim3((unsigned)((nv + 255) / 256)), dim3(256), 0, s, (const T*)iconv, (T*)sum_act, per_view, group);
   });
   return after_launch("cnm_refine_aggregate(sum)");
 }
@@ -639,7 +655,7 @@ extern "C" int cnm_refine_aggregate_nchw(const float* idepth, const float* iconv
   const size_t px = (size_t)B * H * W;
   cudaStream_t s = (cudaStream_t)stream;
   DISPATCH_DTYPE(dtype, {
-    refine_taps_kernel<T><<<(unsigned)((px + 127) / 128), 128, 0, s>>>(idepth, (T*)taps_act, nullptr, B, H, W, 1);
+    launch_pdl(refine_taps_kernel<T>, dim3((unsigned)((px + 127) / 128)), dim3(128), 0, s, idepth, (T*)taps_act, nullptr, B, H, W, 1);
     int rc = after_launch("cnm_refine_aggregate_nchw(taps)");
     if (rc) return rc;
     dim3 grid((unsigned)(((size_t)H * W + 31) / 32), 2, B), block(32, 8);
@@ -656,13 +672,12 @@ extern "C" int cnm_upsample2x(const void* src, void* dst, int N, int h, int w, i
     CNM_REQUIRE((size_t)4 * h * w * 4 * C < ((size_t)1 << 32) && (size_t)N * h * w * (C / 8) < ((size_t)1 << 32),
                 CNM_ERR_UNSUPPORTED_SHAPE, "cnm_upsample2x: image too large for 32-bit offsets");
     const size_t total = (size_t)N * h * w * (C / 8);
-    upsample2x_h16f8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint8_t*)src, (uint8_t*)dst, N, h, w, C);
+    launch_pdl(upsample2x_h16f8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const uint8_t*)src, (uint8_t*)dst, N, h, w, C);
     return after_launch("cnm_upsample2x");
   }
   DISPATCH_DTYPE(dtype, {
     const size_t total = (size_t)N * h * w * (C / Vec16<T>::N);
-    upsample2x_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const T*)src, (T*)dst, N, h, w, C);
+    launch_pdl(upsample2x_kernel<T>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const T*)src, (T*)dst, N, h, w, C);
   });
   return after_launch("cnm_upsample2x");
 }
@@ -685,7 +700,7 @@ extern "C" int cnm_head_finish(const float* partial, int nslices, float bias, fl
   CNM_REQUIRE(partial && out && N > 0 && H > 0 && W > 0 && nslices >= 1 && nslices <= 64, CNM_ERR_INVALID_ARGUMENT,
               "cnm_head_finish: bad argument");
   const size_t total = (size_t)N * H * W;
-  head_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, nslices, bias, scale, out,
+  launch_pdl(head_finish_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, partial, nslices, bias, scale, out,
                                                                                        logits, N, H, W);
   return after_launch("cnm_head_finish");
 }

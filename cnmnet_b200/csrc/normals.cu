@@ -14,6 +14,8 @@ constexpr int NT_X = 32, NT_Y = 16;
 __global__ void __launch_bounds__(NT_X* NT_Y)
     depth2normal_kernel(const float* __restrict__ depth, const float* __restrict__ Kinv, float* __restrict__ normals,
                         float* __restrict__ points, int H, int W, int k) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ double sm[];
   const int r = k / 2;
   const int HX = NT_X + 2 * r, HY = NT_Y + 2 * r;
@@ -307,6 +309,8 @@ __global__ void cnm_loss_kernel(const int32_t* __restrict__ planes_num, CnmWorks
 }
 
 __global__ void intrinsics_inverse_kernel(const float* __restrict__ cam, float* __restrict__ Kinv, int B) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* K = cam + (size_t)b * 32 + 16;  // cam[b,1,:3,:3]
@@ -320,6 +324,8 @@ __global__ void intrinsics_inverse_kernel(const float* __restrict__ cam, float* 
 }
 
 __global__ void reciprocal_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = 1.0f / in[i];
 }
@@ -393,7 +399,7 @@ extern "C" int cnm_depth2normal(const float* depth, const float* Kinv, float* no
   cudaError_t e = limit.ensure(depth2normal_kernel, smem);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_depth2normal: smem attr: %s", cudaGetErrorString(e));
   dim3 grid((W + NT_X - 1) / NT_X, (H + NT_Y - 1) / NT_Y, B), block(NT_X, NT_Y);
-  depth2normal_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(depth, Kinv, normals, points, H, W, k_size);
+  launch_pdl(depth2normal_kernel, dim3(grid), dim3(block), smem, (cudaStream_t)stream, depth, Kinv, normals, points, H, W, k_size);
   return after_launch("cnm_depth2normal");
 }
 
@@ -429,7 +435,7 @@ extern "C" int cnm_plane_regularize(float* normals, const uint8_t* segs, const i
 
 extern "C" int cnm_intrinsics_inverse(const float* cam, float* Kinv, int B, void* stream) {
   CNM_REQUIRE(cam && Kinv && B > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_intrinsics_inverse: bad argument");
-  intrinsics_inverse_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(cam, Kinv, B);
+  launch_pdl(intrinsics_inverse_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)stream, cam, Kinv, B);
   return after_launch("cnm_intrinsics_inverse");
 }
 
@@ -437,7 +443,7 @@ extern "C" int cnm_reciprocal(const float* idepth, float* depth, int64_t n, void
   CNM_REQUIRE(idepth && depth && n > 0, CNM_ERR_INVALID_ARGUMENT, "cnm_reciprocal: bad argument");
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  reciprocal_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(idepth, depth, n);
+  launch_pdl(reciprocal_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, idepth, depth, n);
   return after_launch("cnm_reciprocal");
 }
 

@@ -262,6 +262,8 @@ __device__ __forceinline__ void sweep_produce(const SweepParams& p, const SweepC
 
 template <int LAYOUT>
 __global__ void __launch_bounds__(PS_THREADS, 3) plane_sweep_kernel(const __grid_constant__ SweepParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -420,7 +422,7 @@ static int launch_sweep(const SweepParams& p, dim3 grid, cudaStream_t s) {
   static DynSmemLimit limit;
   cudaError_t e = limit.ensure(plane_sweep_kernel<LAYOUT>, PS_SMEM);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_plane_sweep: smem attribute: %s", cudaGetErrorString(e));
-  plane_sweep_kernel<LAYOUT><<<grid, dim3(PS_TX, PS_TY + 1), PS_SMEM, s>>>(p);
+  launch_pdl(plane_sweep_kernel<LAYOUT>, dim3(grid), dim3(dim3(PS_TX, PS_TY + 1)), PS_SMEM, s, p);
   return after_launch("cnm_plane_sweep");
 }
 

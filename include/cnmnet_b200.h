@@ -75,6 +75,13 @@ int64_t cnm_launch_count(void);
  * cnm_range_overflow_count synchronises the device and returns the count (-1 when the check is off); reset != 0
  * clears it.  Enable before the first step of a pipeline (the counter is allocated on first use, outside graphs). */
 void cnm_set_range_check(int enable);
+
+/* Programmatic dependent launch between the kernels of a pipeline step (on by default; CNM_PDL=0 in the environment
+ * or cnm_set_pdl(0) turns it off): every step kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and waits (griddepcontrol.wait) before its first global-memory
+ * access, so its prologue overlaps the tail of the kernel before it.  Results do not depend on the setting.
+ * Set it before a plan is captured into a CUDA graph. */
+void cnm_set_pdl(int enable);
 int64_t cnm_range_overflow_count(int reset);
 
 /* ---- camera pre-processing -------------------------------------------------------------
@@ -287,6 +294,12 @@ int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const i
 int cnm_conv2d_halo2(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* map_info,
                      const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
                      void* stream);
+
+/* Debugging aid (CNM_CONV_TIMELINE=1 in the environment before the first convolution): CTA 0 of every cnm_conv2d_tc
+ * launch leaves nine clock64 stamps -- kernel entry, prologue done, dependency wait done, first TMA issued, first
+ * operands landed, last MMA of the first tile issued, first accumulator complete, last store drained, exit -- and this
+ * call copies the stamps of the last launch to the host (it synchronises the device).  tools/conv_timeline.py.  */
+int cnm_debug_conv_timeline(long long* out9);
 
 /* ---- conv1.0 with the plane sweep fused in -----------------------------------------
  * replaces getVolume + torch.cat + conv1[0]  (depthnet/depthNet_model.py:185-224, 231-235) in ONE kernel: the cost
