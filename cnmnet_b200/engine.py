@@ -20,7 +20,12 @@ BN_EPS = 1e-5
 # which stride-1 layers use the row-halo kernel: "auto" (enough tiles for a wave), "force" (every eligible layer,
 # used by tests), "off" (per-tap kernel everywhere)
 HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
-PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0"   # activation buffers of a plan are recycled after their last reader
+# CNM_POISON=1 (a test mode, tools/sanitize.sh): every plan buffer starts as 0xFF bytes (NaN in every act format and in
+# fp32) and buffers are not recycled, so a kernel that reads an element nobody wrote turns the outputs into NaN and
+# fails the parity tests.  compute-sanitizer's initcheck cannot do this job here: it does not see TMA bulk stores (the
+# async proxy) as writes, so every consumer of a convolution output is flagged.
+POISON = os.environ.get("CNM_POISON", "0") == "1"
+PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0" and not POISON   # activation buffers of a plan are recycled after their last reader
 FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
 PLANE_SWEEP = os.environ.get("CNM_PLANE_SWEEP", "1") != "0"   # K1 = csrc/plane_sweep.cu (TMA-staged); 0: cost_volume.cu
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
@@ -405,6 +410,8 @@ class ConvOp:
         if backend == "halo2s" and not self.sweep.scratch:
             nbytes = int(_lib.load().cnm_sweep_scratch_bytes(self.sweep.D, self.k))
             self._sweep_scratch = torch.empty((nbytes,), dtype=torch.uint8, device=self.out.device)
+            if POISON:
+                self._sweep_scratch.fill_(0xFF)
             self.sweep.scratch, self.sweep.scratch_bytes = self._sweep_scratch.data_ptr(), nbytes
         self.desc.reserved = int(bn)
         self.desc.cluster = {"tcm2": 2, "tcm4": 4}.get(backend, 0)
@@ -563,6 +570,8 @@ class _Plan:
             store = self._free.pop(best)
         else:
             store = torch.empty((need,), dtype=torch.uint8, device=self.device)
+            if POISON:
+                store.fill_(0xFF)
             self.bytes_allocated += need
         out = store[:n * torch.empty((), dtype=dt).element_size()].view(dt).view(shape)
         self._storage[out.data_ptr()] = store

@@ -13,7 +13,8 @@ if os.path.exists(head):
 out += ["| pass | tests | pytest result | sanitizer summary |", "|---|---|---|---|"]
 for name, what in (("memcheck_conv.log", "memcheck: tests/test_gpu_conv.py + tests/test_gpu_kernels.py"),
                    ("memcheck_nets.log", "memcheck: tests/test_gpu_nets.py (without the full-size headline cases)"),
-                   ("initcheck.log", "initcheck: __graft_entry__.smoke()"),
+                   ("initcheck.log", "initcheck: __graft_entry__.smoke() -- does not see TMA stores as writes; flags their readers"),
+                   ("poison.log", "poison: CNM_POISON=1 (plan buffers start as NaN, no recycling) end-to-end pipeline tests, default and fused-sweep variants"),
                    ("racecheck.log", "racecheck: non-TMA shared-memory kernels (normals, CNM, packers, upsample, ...)")):
     p = os.path.join(G, name)
     if not os.path.exists(p):
@@ -22,7 +23,8 @@ for name, what in (("memcheck_conv.log", "memcheck: tests/test_gpu_conv.py + tes
     txt = open(p, errors="replace").read()
     res = re.findall(r"^(?:=+ )?(\d+ (?:passed|failed).*?)(?: =+)?$", txt, re.M)
     smoke = re.findall(r"^smoke: .*$", txt, re.M)
-    summ = re.findall(r"^========= (ERROR SUMMARY.*|RACECHECK SUMMARY.*|Error: .*)$", txt, re.M)
+    summ = re.findall(r"^=* ?(ERROR SUMMARY.*|RACECHECK SUMMARY.*|Error: .*)$", txt, re.M)
+    summ += [" ".join(l.split()) for l in re.findall(r"^\s*\d+ Host Frame: ?cnm_\w+$", txt, re.M)]
     out.append("| %s | %s | %s | %s |" % (name, what, "; ".join(res + smoke) or "-", "; ".join(summ) or "-"))
 open(os.path.join(ROOT, "profiles", "%s_sanitizer.md" % tag), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
