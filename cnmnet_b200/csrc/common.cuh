@@ -168,6 +168,18 @@ __device__ __forceinline__ void split_f16f8(float v, __half& hi, float& lo_scale
   hi_scaled = h * F8_HI_SCALE;
 }
 
+// Two values -> their stored parts, in as few instructions as the ISA allows: one saturating packed f32 -> f16x2
+// conversion, the lo residuals in fp32, hi8 from the fp16 pair (hi * 2^-4 is exact in fp16 unless far below the e4m3
+// range, where both routes give 0).  Same results as two split_f16f8 calls for every non-NaN input.
+__device__ __forceinline__ void pack2_f16f8(float a, float b, uint32_t& h2, uint32_t& lo2, uint32_t& hi2) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(b), "f"(a));  // a -> low half
+  const __half2 h = *reinterpret_cast<const __half2*>(&h2);
+  const float2 hf = __half22float2(h);
+  lo2 = e4m3x2((a - hf.x) * F8_LO_SCALE, (b - hf.y) * F8_LO_SCALE);
+  const __half2 hs = __hmul2(h, __float2half2_rn(F8_HI_SCALE));
+  hi2 = (uint32_t)__nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&hs), __NV_SATFINITE, __NV_E4M3);
+}
+
 // scalar access to logical channel c of the pixel starting at `px`
 template <typename T>
 __device__ __forceinline__ float load_scalar(const T* px, size_t c) { return to_f<T>(px[c]); }
@@ -287,16 +299,7 @@ struct Vec16<h16f8> {
   __device__ static __forceinline__ void store(h16f8* p, const float* f) {
     uint32_t w[4], lo[4], hs[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __half h0, h1;
-      float l0, l1, s0, s1;
-      split_f16f8(f[2 * i], h0, l0, s0);
-      split_f16f8(f[2 * i + 1], h1, l1, s1);
-      const __half2 h = __halves2half2(h0, h1);
-      w[i] = *reinterpret_cast<const uint32_t*>(&h);
-      lo[i] = e4m3x2(l0, l1);
-      hs[i] = e4m3x2(s0, s1);
-    }
+    for (int i = 0; i < 4; ++i) pack2_f16f8(f[2 * i], f[2 * i + 1], w[i], lo[i], hs[i]);
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
     uint8_t* r8 = const_cast<uint8_t*>(row8(p));
     *reinterpret_cast<uint2*>(r8) = make_uint2(lo[0] | (lo[1] << 16), lo[2] | (lo[3] << 16));
@@ -355,22 +358,17 @@ struct RowPack<h16f8> {  // 8 fp16 pieces (8 channels), 4 lo8 pieces (16 channel
     if (j < 8) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const __half2 h = __floats2half2_rn(sat_f16(v[8 * j + 2 * e]), sat_f16(v[8 * j + 2 * e + 1]));
-        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        uint32_t lo, hs;
+        pack2_f16f8(v[8 * j + 2 * e], v[8 * j + 2 * e + 1], w[e], lo, hs);
       }
     } else {
       const int c0 = 16 * (j & 3);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float part[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half h;
-          float lo, hs;
-          split_f16f8(v[c0 + 4 * e + i], h, lo, hs);
-          part[i] = j < 12 ? lo : hs;
-        }
-        w[e] = e4m3x2(part[0], part[1]) | (e4m3x2(part[2], part[3]) << 16);
+        uint32_t h, lo0, hs0, lo1, hs1;
+        pack2_f16f8(v[c0 + 4 * e], v[c0 + 4 * e + 1], h, lo0, hs0);
+        pack2_f16f8(v[c0 + 4 * e + 2], v[c0 + 4 * e + 3], h, lo1, hs1);
+        w[e] = j < 12 ? (lo0 | (lo1 << 16)) : (hs0 | (hs1 << 16));
       }
     }
     return make_uint4(w[0], w[1], w[2], w[3]);

@@ -165,14 +165,11 @@ __device__ __forceinline__ void epi_store_row(const uint32_t* v, uint8_t* rowp, 
       uint32_t lw[4], hw[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float lo[4], hs[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __half h;
-          split_f16f8(val(16 * j + 4 * e + i), h, lo[i], hs[i]);
-        }
-        lw[e] = e4m3x2(lo[0], lo[1]) | (e4m3x2(lo[2], lo[3]) << 16);
-        hw[e] = e4m3x2(hs[0], hs[1]) | (e4m3x2(hs[2], hs[3]) << 16);
+        uint32_t h, lo0, hs0, lo1, hs1;
+        pack2_f16f8(val(16 * j + 4 * e), val(16 * j + 4 * e + 1), h, lo0, hs0);
+        pack2_f16f8(val(16 * j + 4 * e + 2), val(16 * j + 4 * e + 3), h, lo1, hs1);
+        lw[e] = lo0 | (lo1 << 16);
+        hw[e] = hs0 | (hs1 << 16);
       }
       *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       *reinterpret_cast<uint4*>(rowp + (((j + 4) ^ (row & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -185,8 +182,7 @@ __device__ __forceinline__ void epi_store_row(const uint32_t* v, uint8_t* rowp, 
       for (int e = 0; e < 4; ++e) {
         float t0 = val(8 * j + 2 * e), t1 = val(8 * j + 2 * e + 1);
         if (mode == EPI_F16F8) {
-          const __half2 h = __floats2half2_rn(sat_f16(t0), sat_f16(t1));
-          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[e]) : "f"(t1), "f"(t0));
         } else {
           if (part) {  // lo row of the split-bf16 output: what the hi row rounded away
             t0 -= __bfloat162float(__float2bfloat16_rn(t0));
