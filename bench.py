@@ -654,6 +654,32 @@ def main():
                                         "n_gpus": 1})
             del pipe2, st2, d2, r2
             torch.cuda.empty_cache()
+        if args.workload == "c4" and args.precision == "f16f8" and not args.no_other_modes:
+            # (f)-1 as an A/B at step level: the same step with conv1.0 computing the cost volume itself
+            # (cnm_conv2d_halo2_sweep, engine kernel name "halo2s"); same timing method, kept out of the headline value
+            eng = cnmnet_b200.engine
+            was = eng.FUSE_SWEEP
+            try:
+                eng.FUSE_SWEEP = "force"
+                d2, r2 = make_weights(0)
+                pipe2 = cnmnet_b200.CNMPipeline(d2.to(dev), r2.to(dev), k_size=K_SIZE, use_graph=True)
+                st2 = pipe2.static_state(B, V, H, W, dev)
+                op1 = st2["dplan"].convs["conv1.0"]
+                pipe2.load_inputs(st2, *host, non_blocking=False)
+                for _ in range(3):
+                    pipe2.step(st2)
+                ms2, _ = time_events(lambda: pipe2.step(st2), max(3, min(args.steps, 10)), flush)
+                ms_c, _ = time_events(lambda: op1(s), 10, flush)
+                line["fused_sweep"] = {
+                    "what": "the same step with conv1.0 computing the plane-sweep cost volume itself (SURVEY 8f rank 1: "
+                            "cnm_conv2d_halo2_sweep; the volume never exists as a tensor); bit-identical outputs "
+                            "(tests/test_gpu_fused_sweep.py); opt-in (CNM_FUSE_SWEEP=force), not the default, because it is slower",
+                    "kernel": op1.backend, "value": B / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2,
+                    "conv1_0_ms": ms_c, "default_ms_per_step": line["ms_per_step"]}
+                del pipe2, st2, d2, r2
+                torch.cuda.empty_cache()
+            finally:
+                eng.FUSE_SWEEP = was
         if args.layers:
             for name, ms, fl in sorted(conv_rows, key=lambda r: -r[1]):
                 sys.stderr.write("%-40s %8.3f ms  %7.1f TFLOP/s issued\n" % (name, ms, fl / ms / 1e9))

@@ -119,4 +119,33 @@ if "--full" in sys.argv:
      "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k "
      "regex:\"upsample2x|head_partial|head_finish|pack_|refine_|cost_volume\" -c 12 python tools/profile_step.py` "
      "(%s mode, C4 step, first twelve matching launches in launch order)." % bench.get("dtype", "f16f8"))
+
+def text_profile(logs, outname, title, note, keep=None):
+    """A committed summary made of the text a tool printed (ncu sections without a report file, timeline tools)."""
+    body = []
+    for lg in logs:
+        pth = os.path.join(G, lg)
+        if not os.path.exists(pth):
+            continue
+        lines = [l.rstrip() for l in open(pth, errors="replace") if not l.startswith("==") and l.strip()]
+        if keep:
+            lines = [l for l in lines if keep(l)]
+        body += ["```"] + lines + ["```", ""]
+    if body:
+        open(os.path.join(P, outname), "w").write("\n".join(["# " + title, "", note, ""] + body))
+
+
+text_profile(["prof_fused.log"], "%s_fused_sweep_ncu.md" % tag,
+             "%s ncu (hardware-counter sections): conv_halo2_sweep_kernel<128> -- conv1.0 with the plane sweep fused in" % tag,
+             "Capture: `CNM_FUSE_SWEEP=force ncu --profile-from-start off --section SpeedOfLight --section SchedulerStats --section "
+             "WarpStateStats --section MemoryWorkloadAnalysis --section Occupancy --section LaunchStats --clock-control none -k "
+             "regex:sweep_kernel -c 1 python tools/profile_step.py` (C4 step).  `--set full` is not usable on this kernel: ncu's "
+             "SASS-patching metrics hang on a kernel that re-balances registers with setmaxnreg.  Reading: DESIGN.md section 3, (f)-1.",
+             keep=lambda l: not l.lstrip().startswith(("OPT", "INF", "WRN", "-----")) and "Est." not in l and "done " not in l)
+text_profile(["conv_timeline.log", "conv_scaling.log"], "%s_conv_timeline.md" % tag,
+             "%s where the time of a mid-size convolution launch goes" % tag,
+             "`tools/conv_timeline.py` (clock64 stamps of CTA 0 of the per-tap kernel, CNM_CONV_TIMELINE=1) and "
+             "`tools/conv_scaling.py` (t = t0 + steps x t_step per kernel variant; single launches timed with events, so t0 "
+             "includes ~15 us of host-side launch work that a CUDA-graph replay does not pay) on the refine network's "
+             "5 x 48x64 -> 256 layer.  Reading: DESIGN.md section 3, \"What bounds the 48x64 / 24x32 layers\".")
 print("ok", cu, cm, s)
