@@ -25,10 +25,10 @@ tail -3 gpurun_out/memcheck_conv.log
 timeout 1800 compute-sanitizer --tool memcheck --print-limit 10 \
     python -m pytest tests/test_gpu_nets.py -m gpu -q -k "not headline and not bit_identical" > gpurun_out/memcheck_nets.log 2>&1
 tail -3 gpurun_out/memcheck_nets.log
-timeout 600 compute-sanitizer --tool initcheck --print-limit 4000 \
+timeout 600 compute-sanitizer --tool initcheck --print-limit 300 \
     python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/initcheck_full.log 2>&1
 # keep the log small: the summary lines, smoke()'s own line and a tally of the flagged kernels (Host Frame = the C entry)
-{ grep -E "^smoke:|ERROR SUMMARY" gpurun_out/initcheck_full.log; echo "flagged reads by entry point (first 4000):";
+{ grep -E "^smoke:|ERROR SUMMARY" gpurun_out/initcheck_full.log; echo "flagged reads by entry point (first 300 reports):";
   grep -oE "Host Frame: ?cnm_[a-z0-9_]+" gpurun_out/initcheck_full.log | sort | uniq -c; } > gpurun_out/initcheck.log
 rm -f gpurun_out/initcheck_full.log
 tail -12 gpurun_out/initcheck.log
