@@ -668,14 +668,22 @@ def main():
                 pipe2.load_inputs(st2, *host, non_blocking=False)
                 for _ in range(3):
                     pipe2.step(st2)
-                ms2, _ = time_events(lambda: pipe2.step(st2), max(3, min(args.steps, 10)), flush)
+                # interleaved blocks of both arms: under the power cap the step time drifts by several per cent over a
+                # run, more than the difference that is being measured
+                blocks = {"default": [], "fused": []}
+                for rd in range(6):
+                    for arm in (("default", "fused") if rd % 2 == 0 else ("fused", "default")):
+                        fn = (lambda: pipe.step(st)) if arm == "default" else (lambda: pipe2.step(st2))
+                        blocks[arm].append(time_events(fn, 5, flush)[0])
+                ms2, ms_def = statistics.median(blocks["fused"]), statistics.median(blocks["default"])
                 ms_c, _ = time_events(lambda: op1(s), 10, flush)
                 line["fused_sweep"] = {
                     "what": "the same step with conv1.0 computing the plane-sweep cost volume itself (SURVEY 8f rank 1: "
                             "cnm_conv2d_halo2_sweep; the volume never exists as a tensor); bit-identical outputs "
                             "(tests/test_gpu_fused_sweep.py); opt-in (CNM_FUSE_SWEEP=force), not the default, because it is slower",
                     "kernel": op1.backend, "value": B / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2,
-                    "conv1_0_ms": ms_c, "default_ms_per_step": line["ms_per_step"]}
+                    "conv1_0_ms_single_launch": ms_c, "default_ms_per_step_interleaved": ms_def,
+                    "method": "6 alternating blocks of 5 timed steps per arm in this process, medians"}
                 del pipe2, st2, d2, r2
                 torch.cuda.empty_cache()
             finally:
