@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
                 ("c_out_total", C.c_int32), ("c_out_offset", C.c_int32), ("stride", C.c_int32), ("relu", C.c_int32),
                 ("num_srcs", C.c_int32), ("num_steps", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
-                ("acc_exp", C.c_int32), ("ksplit", C.c_int32), ("cluster", C.c_int32), ("tile_h", C.c_int32), ("head_w", C.c_void_p),
+                ("acc_exp", C.c_int32), ("ksplit", C.c_int32), ("cluster", C.c_int32), ("tile_h", C.c_int32), ("balance", C.c_int32), ("head_w", C.c_void_p),
                 ("head_partial", C.c_void_p), ("splitk_ws", C.c_void_p)]
 
 
@@ -73,6 +73,7 @@ SIGNATURES = {
     "cnm_head_partial": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cnm_head_finish": (_I, [_P, _I, _F, _F, _P, _P, _I, _I, _I, _P]),
     "cnm_conv2d_tc": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
+    "cnm_conv_balance_ws_bytes": (_L, []),
     "cnm_debug_conv_timeline": (_I, [C.POINTER(C.c_longlong)]),
     "cnm_conv2d_simt": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), _P, _P, _P, _P, _P]),
     "cnm_conv2d_halo": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvSrc), C.POINTER(C.c_int32), _P, _I, _P, _P, _P, _P]),

@@ -86,7 +86,49 @@ struct alignas(64) HaloParams {
   const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
   float* head_partial;   // [Cout/64 slices][N, Ho, Wo, 12] per-pixel tap dot products, one slice per 64-channel chunk
   int Ho, Wo, cout;
+  // balanced schedule (cnm_conv_desc.balance, BAL instantiations): see HaloWalk
+  float* bal_slots;      // [gridDim.x][HALVES][128][BN] fp32 raw accumulators of the contributor pieces
+  int* bal_flags;        // [gridDim.x] 1 = the CTA's contributor piece is in its slot (reset by the tile's finishing CTA)
   SweepFuseParams sw;    // SWEEP instantiations only
+};
+
+// Work of one CTA (CG = 1) or CTA pair (CG = 2) as a sequence of segments (tile, groups [g0, g1)).
+//   static (BAL = false): whole tiles first_tile, first_tile + stride, ...
+//   balanced (BAL = true, stream-K): the launch's slab groups -- tiles x num_groups, tile-major -- are cut into one equal
+//     contiguous range per unit.  A unit whose range starts inside a tile runs that CONTRIBUTOR piece first and parks the raw
+//     accumulators in its CTAs' slots; the unit that owns the tile's first group (the HEAD piece, the last segment of its
+//     range) adds the slots of the following units in index order and runs the normal epilogue.  Contributors never wait and
+//     are done before the head unit has finished its own range.  240 tiles then cost 74 pairs 3.24 tile times instead of 4.
+template <bool BAL>
+struct HaloWalk {
+  long long pos, end;
+  int cur, stride, total, NG;
+  int tile, g0, g1;
+  __device__ __forceinline__ static long long cut(long long T, int u, int U) { return T * u / U; }
+  __device__ __forceinline__ HaloWalk(int num_groups, int total_tiles, int unit, int units) {
+    NG = num_groups;
+    if (BAL) {
+      const long long T = (long long)total_tiles * NG;
+      pos = cut(T, unit, units); end = cut(T, unit + 1, units);
+    } else {
+      cur = unit; stride = units; total = total_tiles;
+    }
+  }
+  __device__ __forceinline__ bool next() {
+    if (BAL) {
+      if (pos >= end) return false;
+      tile = (int)(pos / NG);
+      g0 = (int)(pos - (long long)tile * NG);
+      const long long left = end - pos;
+      g1 = (left < (long long)(NG - g0)) ? g0 + (int)left : NG;
+      pos += g1 - g0;
+      return true;
+    }
+    if (cur >= total) return false;
+    tile = cur; g0 = 0; g1 = NG;
+    cur += stride;
+    return true;
+  }
 };
 
 // ---- 2-CTA PTX wrappers --------------------------------------------------------------------------------------
@@ -153,10 +195,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
 // TH = 16: the CTA's pixel block is 16x16 (two M = 128 halves sharing every weight tile).  TH = 8 (CTA pairs only): one
 // 16x8 half per CTA -- twice the work items for maps with few blocks (the 48x64 / 24x32 levels), BN = 256 with two
 // accumulator stages, and still a slab per (chunk, dx) instead of a pixel tile per tap.
-template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16>
+template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16, bool BAL = false>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   pdl_trigger();
   constexpr int HALVES = TH / 8;
+  static_assert(!BAL || (!SWEEP && !TF32 && TH == 16 && 4 * BN <= 512), "balanced schedule: 2-byte dtypes, 16x16 blocks, two accumulator stages");
   static_assert(TH == 16 || (TH == 8 && CG == 2 && !SWEEP), "16x8 blocks: CTA-pair instantiations");
   static_assert(!SWEEP || (!TF32 && 4 * BN <= 512 && TH == 16), "the fused plane sweep needs two accumulator stages (BN <= 128)");
   constexpr int COLS_PER_CHUNK = TF32 ? 32 : 64;
@@ -217,6 +260,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), ISSUERS); mbar_init(tempty(a), 128u * CG); }
     if (SWEEP)
       for (int a = 0; a < 2; ++a) mbar_init(vfull(a), HL_SWEEP_THREADS);
+    if (BAL) mbar_init(vfull(0), 1);   // balanced schedule: the bulk-copy barrier of balance_gather
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -251,18 +295,21 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     if (lane == 0) {
       int sa = 0;
       uint32_t pa = 0;
-      int4 g_next = __ldg(reinterpret_cast<const int4*>(p.groups));
+      HaloWalk<BAL> w(p.num_groups, total_tiles, first_tile, tile_stride);
+      bool more = w.next();
+      int4 g_next = __ldg(reinterpret_cast<const int4*>(p.groups + (more ? w.g0 : 0)));
       int it = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+      for (; more; more = w.next(), ++it) {
+        const int tile = w.tile;
         int m = CG * (tile / p.tiles_n) + (int)rank;
         const int x0 = (m % p.tiles_x) * 16;
         m /= p.tiles_x;
         const int y0 = (m % p.tiles_y) * TH;
         const int n0 = m / p.tiles_y;
         bool vol_ready = false;
-        for (int g = 0; g < p.num_groups; ++g) {
+        for (int g = w.g0; g < w.g1; ++g) {
           const int4 gr = g_next;  // src, c0, dx, ntaps
-          g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == p.num_groups) ? 0 : g + 1)));
+          g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == w.g1) ? 0 : g + 1)));  // later segments start at group 0
           const int pad = p.map_pad[gr.x];
           const uint32_t slab_tx = (uint32_t)p.map_rows[gr.x] * 2048u;
           if (SWEEP && p.sw.park) mbar_wait_backoff(emptyA(sa), pa ^ 1, 200);
@@ -291,10 +338,15 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     if (lane == 0) {
       int sb = 0;
       uint32_t pb = 0;
-      const int num_steps = p.num_steps;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-        const int nt = tile % p.tiles_n;
-        for (int kstep = 0; kstep < num_steps; ++kstep) {
+      HaloWalk<BAL> w(p.num_groups, total_tiles, first_tile, tile_stride);
+      while (w.next()) {
+        const int nt = w.tile % p.tiles_n;
+        int ks0 = 0, ks1 = p.num_steps;
+        if (BAL) {   // weight steps of the piece: bits 8.. of a group's ntaps field = index of its first weight step
+          if (w.g0 > 0) ks0 = __ldg(&p.groups[w.g0].ntaps) >> 8;
+          if (w.g1 < w.NG) ks1 = __ldg(&p.groups[w.g1].ntaps) >> 8;
+        }
+        for (int kstep = ks0; kstep < ks1; ++kstep) {
           if (SWEEP && p.sw.park) mbar_wait_backoff(emptyB(sb), pb ^ 1, 100);
           else mbar_wait(emptyB(sb), pb ^ 1);
           if (leader) mbar_expect_tx(fullB(sb), (uint32_t)CG * B_BYTES);  // CG = 2: both halves
@@ -319,15 +371,16 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+      HaloWalk<BAL> w(p.num_groups, total_tiles, first_tile, tile_stride);
+      for (; w.next(); ++it) {
         const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
         const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(tempty(as), aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * HALVES * BN + half * BN);
         uint32_t first = 1;
-        for (int g = 0; g < p.num_groups; ++g) {
-          const int ntaps = __ldg(&p.groups[g].ntaps);
+        for (int g = w.g0; g < w.g1; ++g) {
+          const int ntaps = __ldg(&p.groups[g].ntaps) & 0xff;
           mbar_wait(fullA(sa), pa);
           const uint32_t slab = base + sa * p.slab_bytes + half * 8 * 2048;
           for (int t = 0; t < ntaps; ++t) {
@@ -509,8 +562,11 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
     int it = 0;
     int bias_tile = -1;
     uint32_t store_cnt = 0;
+    uint32_t gather_phase = 0;
 
-    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++it) {
+    HaloWalk<BAL> w(p.num_groups, total_tiles, first_tile, tile_stride);
+    for (; w.next(); ++it) {
+      const int tile = w.tile;
       const int nt = tile % p.tiles_n;
       int m = CG * (tile / p.tiles_n) + (int)rank;
       const int x0 = (m % p.tiles_x) * 16;
@@ -519,6 +575,23 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       const int n0 = m / p.tiles_y;
       const int as = (ACC_STAGES == 2) ? (it & 1) : 0;
       const uint32_t aphase = (ACC_STAGES == 2) ? ((it >> 1) & 1) : (it & 1);
+      if (BAL && w.g0 > 0) {
+        // contributor piece: raw accumulators of both halves -> this CTA's slot, then the flag
+        mbar_wait(tfull(as), aphase);
+        tc_fence_after();
+        balance_park(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * HALVES * BN), HALVES * BN,
+                     p.bal_slots + (size_t)blockIdx.x * (BALANCE_SLOT_BYTES / 4), row, p.bal_flags + blockIdx.x, storer);
+        tc_fence_before();
+        if (CG == 2) mbar_arrive_leader(tempty(as));
+        else mbar_arrive(tempty(as));
+        continue;
+      }
+      // head piece of a balanced tile: the next `ncontrib` units hold the rest of its groups (same CTA rank in each)
+      int ncontrib = 0;
+      if (BAL && w.g1 < w.NG) {
+        const long long T = (long long)total_tiles * w.NG, tile_end = (long long)(tile + 1) * w.NG;
+        while (HaloWalk<BAL>::cut(T, first_tile + 1 + ncontrib, tile_stride) < tile_end) ++ncontrib;
+      }
       if (bias_tile != nt) {
         epi_bar();
         for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
@@ -530,6 +603,9 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
       if (SWEEP && p.sw.park) mbar_wait_backoff(tfull(as), aphase, 500);
       else mbar_wait(tfull(as), aphase);
       tc_fence_after();
+      if (BAL && ncontrib)   // the tile's other pieces -> added to the accumulator in TMEM (the rings are idle: last segment)
+        balance_gather(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * HALVES * BN), HALVES * BN, p.bal_slots,
+                       p.bal_flags, (int)blockIdx.x + CG, CG, ncontrib, base_ptr, vfull(0), gather_phase, row, storer);
 #pragma unroll 1
       for (int half = 0; half < HALVES; ++half) {
         const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * HALVES * BN + half * BN);
@@ -599,6 +675,16 @@ __global__ void __launch_bounds__(256, 1) conv_halo_kernel(const __grid_constant
 template <int BN, bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_kernel(const __grid_constant__ HaloParams p) {
   conv_halo_body<BN, TF32, 2>(p);
+}
+
+// balanced (stream-K) schedule, 2-byte dtypes, column tile <= 128
+template <int BN>
+__global__ void __launch_bounds__(256, 1) conv_halob_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, false, 1, false, 16, true>(p);
+}
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2b_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, false, 2, false, 16, true>(p);
 }
 
 // 16x8 pixel blocks on CTA pairs (maps with few 16x16 blocks)
@@ -804,6 +890,32 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   const int grid = CG * (total < 148 / CG ? total : 148 / CG);
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
+  if (d->balance) {
+    CNM_REQUIRE(!sweep && !tf32 && TH == 16 && BN <= 128, CNM_ERR_UNSUPPORTED_SHAPE,
+                "%s: balance needs a 2-byte dtype, 16x16 blocks and a column tile of at most 128 (got %d)", fn, BN);
+    CNM_REQUIRE(d->splitk_ws && (((uintptr_t)d->splitk_ws) & 127) == 0, CNM_ERR_INVALID_ARGUMENT,
+                "%s: balance needs a 128B-aligned, zero-initialised splitk_ws of cnm_conv_balance_ws_bytes() bytes", fn);
+    p.bal_flags = reinterpret_cast<int*>(d->splitk_ws);
+    p.bal_slots = d->splitk_ws + BALANCE_FLAG_BYTES / 4;
+    CNM_REQUIRE(p.a_stages * p.slab_bytes + p.b_stages * b_tile >= 2 * 128 * BN * 4, CNM_ERR_UNSUPPORTED_SHAPE,
+                "%s: operand rings of %d B cannot stage a contributor slot", fn, p.a_stages * p.slab_bytes + p.b_stages * b_tile);
+    // one equal range of slab groups per CTA (pair); at least 4 groups each
+    const long long T = (long long)total * num_groups;
+    const int units = T / 4 < 148 / CG ? (int)(T / 4 > 0 ? T / 4 : 1) : 148 / CG;
+    static DynSmemLimit b64, b128, b2_64, b2_128;
+    cudaError_t e;
+    if (CG == 2) e = BN == 128 ? b2_128.ensure(conv_halo2b_kernel<128>, smem) : b2_64.ensure(conv_halo2b_kernel<64>, smem);
+    else e = BN == 128 ? b128.ensure(conv_halob_kernel<128>, smem) : b64.ensure(conv_halob_kernel<64>, smem);
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
+    if (CG == 2) {
+      if (BN == 128) launch_pdl(conv_halo2b_kernel<128>, dim3(CG * units), dim3(256), smem, s, p);
+      else launch_pdl(conv_halo2b_kernel<64>, dim3(CG * units), dim3(256), smem, s, p);
+    } else {
+      if (BN == 128) launch_pdl(conv_halob_kernel<128>, dim3(units), dim3(256), smem, s, p);
+      else launch_pdl(conv_halob_kernel<64>, dim3(units), dim3(256), smem, s, p);
+    }
+    return after_launch(fn);
+  }
   if (sweep) {
     static DynSmemLimit limit64, limit128;
     cudaError_t e = BN == 128 ? limit128.ensure(conv_halo2_sweep_kernel<128>, smem) : limit64.ensure(conv_halo2_sweep_kernel<64>, smem);

@@ -60,6 +60,56 @@ struct alignas(64) TcParams {
   float* ws;        // split-K workspace [ksplit][N*Ho*Wo][Cout] fp32 (raw accumulators; splitk_finish_kernel sums them)
   int cout;
   long long* dbg;   // CNM_CONV_TIMELINE=1: clock64 stamps of CTA 0 (tools/conv_timeline.py), else NULL
+  // balanced mode (cnm_conv_desc.balance, BAL instantiations): see TcWalk
+  float* bal_slots;  // [gridDim.x][128][BN] fp32 raw accumulators of the contributor pieces
+  int* bal_flags;    // [gridDim.x] 1 = the CTA's contributor piece is in its slot (reset by the tile's finishing CTA)
+};
+
+// Work of one CTA as a sequence of segments (tile, K-steps [k0, k1)).
+//   static (BAL = false): work items first_q, first_q + stride, ... of the (pixel-tile group, column tile, split-K part)
+//     index space; a split-K part is a K range whose raw accumulators go to the workspace for splitk_finish_kernel.
+//   balanced (BAL = true): the launch's K-steps -- tiles x num_steps, tile-major -- are cut into gridDim.x equal contiguous
+//     ranges, one per CTA (stream-K).  A CTA whose range starts inside a tile runs that CONTRIBUTOR piece first and parks
+//     the raw accumulators in its slot; the CTA that owns the tile's first K-step (the HEAD piece, the last segment of its
+//     range) adds the slots of the following CTAs in index order and runs the normal epilogue.  Contributors never wait,
+//     and they finish their piece before the head CTA finishes its own, so nobody idles: a layer with 120 tiles keeps all
+//     148 SMs busy for 0.81 tile times instead of 120 SMs for one.  The summation order is fixed, results are
+//     deterministic (but differ in the last bits from the static schedule, which adds the K-steps in one chain).
+template <bool BAL>
+struct TcWalk {
+  long long pos, end;   // balanced: position in the global K-step space
+  int q, stride, total; // static: work item, stride, number of items
+  int S, ksplit;
+  int tile, part, k0, k1;
+  __device__ __forceinline__ int kbeg(int pt) const { return pt >= ksplit ? S : ((S / 2) * pt / ksplit) * 2; }
+  __device__ __forceinline__ static long long cut(long long T, int c, int G) { return T * c / G; }
+  __device__ __forceinline__ TcWalk(const TcParams& p, int tiles, int first_q, int q_stride) {
+    S = p.num_steps; ksplit = p.ksplit;
+    if (BAL) {
+      const long long T = (long long)tiles * S;
+      pos = cut(T, (int)blockIdx.x, (int)gridDim.x); end = cut(T, (int)blockIdx.x + 1, (int)gridDim.x);
+    } else {
+      q = first_q; stride = q_stride; total = tiles * ksplit;
+    }
+  }
+  __device__ __forceinline__ bool next() {
+    if (BAL) {
+      if (pos >= end) return false;
+      tile = (int)(pos / S); part = 0;
+      k0 = (int)(pos - (long long)tile * S);
+      const long long left = end - pos;
+      k1 = (left < (long long)(S - k0)) ? k0 + (int)left : S;
+      pos += k1 - k0;
+      return true;
+    }
+    if (q >= total) return false;
+    part = q % ksplit; tile = q / ksplit;
+    k0 = kbeg(part); k1 = kbeg(part + 1);
+    q += stride;
+    return true;
+  }
+  // first K-step of the segment after the current one (descriptor prefetch; any valid index if there is none)
+  __device__ __forceinline__ int next_first() const { return BAL ? 0 : kbeg(q % ksplit) % S; }
 };
 
 template <int BN, int STAGES, bool TF32>
@@ -72,13 +122,14 @@ struct TcSmem {
   static constexpr int OFF_HEAD = OFF_BIAS + BN * 4;                     // fused-head weights of the N tile [9][BN]
   static constexpr bool HEAD_IN_SMEM = BN == 64;                         // wider tiles fill shared memory: weights from L1
   static constexpr int OFF_BAR = OFF_HEAD + (HEAD_IN_SMEM ? 9 * BN * 4 : 0);
-  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 5;   // + the bulk-copy barrier of the balanced schedule
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + slack for manual 1024 B alignment
 };
 
-template <int BN, int STAGES, bool TF32, int CL>
+template <int BN, int STAGES, bool TF32, int CL, bool BAL = false>
 __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
+  static_assert(!BAL || CL == 1, "balanced schedule: single CTAs");
   using L = TcSmem<BN, STAGES, TF32>;
   const bool stamp = p.dbg != nullptr && blockIdx.x == 0;
   if (stamp && threadIdx.x == 0) p.dbg[0] = clock64();
@@ -108,6 +159,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t gather_bar = bar0 + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::OFF_TMEM);
   float* bias_s = reinterpret_cast<float*>(base_ptr + L::OFF_BIAS);
   float* head_s = reinterpret_cast<float*>(base_ptr + L::OFF_HEAD);
@@ -116,9 +168,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int m_groups = (p.tiles_x * p.tiles_y * p.tiles_b + CL - 1) / CL;
-  const int total_tiles = m_groups * p.tiles_n * p.ksplit;
-  // split-K: item index = ((group * tiles_n) + nt) * ksplit + part; part runs K-steps [kbeg(part), kbeg(part+1))
-  auto kbeg = [&](int part) { return part >= p.ksplit ? p.num_steps : ((p.num_steps / 2) * part / p.ksplit) * 2; };
+  const int num_tiles = m_groups * p.tiles_n;   // (pixel-tile group, column tile) pairs; x ksplit work items (TcWalk)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.b_map);
@@ -128,6 +178,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(gather_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -150,23 +201,23 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int k_first = kbeg(first_q % p.ksplit);
-      int4 st_next = __ldg(reinterpret_cast<const int4*>(p.steps + k_first));
-      int c0_next = __ldg(&p.steps[k_first].c0);
-      for (int tile = first_q; tile < total_tiles; tile += q_stride) {
-        const int part = tile % p.ksplit;
-        const int nt = (tile / p.ksplit) % p.tiles_n;
-        int m = (tile / (p.ksplit * p.tiles_n)) * CL + (int)rank;
+      TcWalk<BAL> w(p, num_tiles, first_q, q_stride);
+      bool more = w.next(), first_seg = true;
+      int4 st_next = __ldg(reinterpret_cast<const int4*>(p.steps + (more ? w.k0 : 0)));
+      int c0_next = __ldg(&p.steps[more ? w.k0 : 0].c0);
+      for (; more; more = w.next(), first_seg = false) {
+        const int nt = w.tile % p.tiles_n;
+        int m = (w.tile / p.tiles_n) * CL + (int)rank;
         const int x0 = (m % p.tiles_x) * p.TW;
         m /= p.tiles_x;
         const int y0 = (m % p.tiles_y) * p.TH;
         const int n0 = (m / p.tiles_y) * p.NB;
-        const int k_end = kbeg(part + 1);
-        for (int ks = kbeg(part); ks < k_end; ++ks) {
+        const int k_begin = w.k0, k_end = w.k1, k_after = w.next_first();
+        for (int ks = k_begin; ks < k_end; ++ks) {
           const int4 st = st_next;  // src, sub, dx, dy
           const int c0 = c0_next;
           {  // prefetch the next step descriptor: its L2 latency overlaps the barrier wait below
-            const int kn = (ks + 1 == k_end) ? kbeg((tile + q_stride) % p.ksplit) % p.num_steps : ks + 1;
+            const int kn = (ks + 1 == k_end) ? k_after : ks + 1;
             st_next = __ldg(reinterpret_cast<const int4*>(p.steps + kn));
             c0_next = __ldg(&p.steps[kn].c0);
           }
@@ -179,7 +230,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
                            nt * BN + (int)rank * (BN / CL), CL_MASK);
           else
             tma_load_2d(sa + TC_A_BYTES, &p.b_map, full_bar(stage), ks * CHUNK_CH, nt * BN);
-          if (stamp && tile == first_q && ks == kbeg(part)) p.dbg[3] = clock64();
+          if (stamp && first_seg && ks == k_begin) p.dbg[3] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -192,16 +243,17 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = first_q; tile < total_tiles; tile += q_stride, ++it) {
+      TcWalk<BAL> w(p, num_tiles, first_q, q_stride);
+      for (; w.next(); ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        const int k_begin = kbeg(tile % p.ksplit), k_end = kbeg(tile % p.ksplit + 1);
+        const int k_begin = w.k0, k_end = w.k1;
         for (int ks = k_begin; ks < k_end; ++ks) {
           mbar_wait(full_bar(stage), phase);
-          if (stamp && lane == 0 && tile == first_q && ks == k_begin) p.dbg[4] = clock64();
+          if (stamp && lane == 0 && it == 0 && ks == k_begin) p.dbg[4] = clock64();
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = base + stage * L::STAGE_BYTES;
@@ -222,7 +274,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
             if (ks == k_end - 1) tc_commit(tfull_bar(as));  // accumulator complete
           }
           __syncwarp();
-          if (stamp && lane == 0 && tile == first_q && ks == k_end - 1) p.dbg[5] = clock64();
+          if (stamp && lane == 0 && it == 0 && ks == k_end - 1) p.dbg[5] = clock64();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -236,17 +288,35 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
     int it = 0;
     uint32_t chunk_counter = 0;
     int bias_tile = -1;
+    uint32_t gather_phase = 0;
 
-    for (int tile = first_q; tile < total_tiles; tile += q_stride, ++it) {
-      const int nt = (tile / p.ksplit) % p.tiles_n;
-      int m = (tile / (p.ksplit * p.tiles_n)) * CL + (int)rank;
+    TcWalk<BAL> w(p, num_tiles, first_q, q_stride);
+    for (; w.next(); ++it) {
+      const int nt = w.tile % p.tiles_n;
+      int m = (w.tile / p.tiles_n) * CL + (int)rank;
       const int x0 = (m % p.tiles_x) * p.TW;
       m /= p.tiles_x;
       const int y0 = (m % p.tiles_y) * p.TH;
       const int n0 = (m / p.tiles_y) * p.NB;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      if (p.ksplit > 1) {
+      if (BAL && w.k0 > 0) {
+        // contributor piece: raw accumulators -> this CTA's slot, then the flag
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        balance_park(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN), BN,
+                     p.bal_slots + (size_t)blockIdx.x * (BALANCE_SLOT_BYTES / 4), row, p.bal_flags + blockIdx.x, leader);
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
+      // head piece of a balanced tile: CTAs blockIdx.x + 1 ... + ncontrib hold the rest of its K range
+      int ncontrib = 0;
+      if (BAL && w.k1 < w.S) {
+        const long long T = (long long)num_tiles * w.S, tile_end = (long long)(w.tile + 1) * w.S;
+        while (TcWalk<BAL>::cut(T, (int)blockIdx.x + 1 + ncontrib, (int)gridDim.x) < tile_end) ++ncontrib;
+      }
+      if (!BAL && p.ksplit > 1) {
         // split-K: park the raw accumulators of this K range in the workspace; bias / ReLU / packing happen in
         // splitk_finish_kernel once all ranges are in
         mbar_wait(tfull_bar(as), aphase);
@@ -254,7 +324,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
         const int px = x0 + row % p.TW, py = y0 + (row / p.TW) % p.TH, pn = n0 + row / (p.TW * p.TH);
         const bool inside = px < p.Wo && py < p.Ho && pn < p.N;
         const size_t mtot = (size_t)p.N * p.Ho * p.Wo;
-        float* wrow = p.ws + ((size_t)(tile % p.ksplit) * mtot + ((size_t)pn * p.Ho + py) * p.Wo + px) * p.cout + nt * BN;
+        float* wrow = p.ws + ((size_t)w.part * mtot + ((size_t)pn * p.Ho + py) * p.Wo + px) * p.cout + nt * BN;
         const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -280,9 +350,13 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
         epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
       mbar_wait(tfull_bar(as), aphase);
-      if (stamp && et == 0 && tile == first_q) p.dbg[6] = clock64();
+      if (stamp && et == 0 && it == 0) p.dbg[6] = clock64();
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if (BAL && ncontrib)   // the tile's other pieces -> added to the accumulator in TMEM (the rings are idle: last segment)
+        balance_gather(tmem_row, BN, p.bal_slots, p.bal_flags, (int)blockIdx.x + 1, 1, ncontrib, base_ptr, gather_bar,
+                       gather_phase, row, leader);
+      if (stamp && et == 0 && it == 0) p.dbg[9] = clock64();
 #pragma unroll 1
       for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
         uint32_t v[COLS_PER_CHUNK];
@@ -336,6 +410,11 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
 template <int BN, int STAGES, bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   conv_tc_body<BN, STAGES, TF32, 1>(p);
+}
+// balanced (stream-K) schedule, 2-byte dtypes
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tcb_kernel(const __grid_constant__ TcParams p) {
+  conv_tc_body<BN, STAGES, false, 1, true>(p);
 }
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) conv_tc_mc2_kernel(const __grid_constant__ TcParams p) {
@@ -431,6 +510,16 @@ static int launch_tc(const TcParams& p, int grid, cudaStream_t s) {
   cudaError_t e = limit.ensure(conv_tc_kernel<BN, STAGES, TF32>, L::TOTAL);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
   launch_pdl(conv_tc_kernel<BN, STAGES, TF32>, dim3(grid), dim3(TC_THREADS), L::TOTAL, s, p);
+  return after_launch("cnm_conv2d_tc");
+}
+
+template <int BN, int STAGES>
+static int launch_tcb(const TcParams& p, int grid, cudaStream_t s) {
+  using L = TcSmem<BN, STAGES, false>;
+  static DynSmemLimit limit;
+  cudaError_t e = limit.ensure(conv_tcb_kernel<BN, STAGES>, L::TOTAL);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+  launch_pdl(conv_tcb_kernel<BN, STAGES>, dim3(grid), dim3(TC_THREADS), L::TOTAL, s, p);
   return after_launch("cnm_conv2d_tc");
 }
 
@@ -532,6 +621,15 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
     }
   }
   p.dbg = g_tc_dbg_on == 1 ? g_tc_dbg_buf : nullptr;
+  const bool balance = d->balance != 0;
+  if (balance) {
+    CNM_REQUIRE(p.ksplit == 1 && d->cluster <= 1 && d->dtype != CNM_TF32, CNM_ERR_UNSUPPORTED_SHAPE,
+                "cnm_conv2d_tc: balance goes with ksplit <= 1, cluster <= 1 and a 2-byte dtype");
+    CNM_REQUIRE(d->splitk_ws && (((uintptr_t)d->splitk_ws) & 127) == 0, CNM_ERR_INVALID_ARGUMENT,
+                "cnm_conv2d_tc: balance needs a 128B-aligned, zero-initialised splitk_ws of cnm_conv_balance_ws_bytes() bytes");
+    p.bal_flags = reinterpret_cast<int*>(d->splitk_ws);
+    p.bal_slots = d->splitk_ws + BALANCE_FLAG_BYTES / 4;
+  }
   if (p.ksplit > 1) {
     CNM_REQUIRE(d->splitk_ws && (((uintptr_t)d->splitk_ws) & 15) == 0, CNM_ERR_INVALID_ARGUMENT,
                 "cnm_conv2d_tc: ksplit = %d needs a 16B-aligned splitk_ws", d->ksplit);
@@ -581,6 +679,14 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
   const int CL = d->cluster > 1 ? d->cluster : 1;
+  if (balance) {
+    // equal K ranges for all SMs; at least 8 K-steps per CTA
+    const long long T = (long long)m_tiles * p.tiles_n * d->num_steps;
+    const int g = T / 8 < 148 ? (int)(T / 8 > 0 ? T / 8 : 1) : 148;
+    if (BN == 256) return launch_tcb<256, 4>(p, g, s);
+    if (BN == 128) return launch_tcb<128, 6>(p, g, s);
+    return launch_tcb<64, 7>(p, g, s);
+  }
   if (CL > 1) {
     CNM_REQUIRE((CL == 2 || CL == 4) && !tf32 && BN >= 128, CNM_ERR_UNSUPPORTED_SHAPE,
                 "cnm_conv2d_tc: cluster = %d needs a 2-byte dtype and a column tile of 128 or 256 (got %d)", d->cluster, BN);
@@ -605,11 +711,14 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   return after_launch("cnm_conv2d_tc(split-K finish)");
 }
 
+extern "C" int64_t cnm_conv_balance_ws_bytes(void) { return BALANCE_WS_BYTES; }
+
 // CNM_CONV_TIMELINE=1: the clock64 stamps CTA 0 of the last cnm_conv2d_tc launch left (synchronises the device)
-extern "C" int cnm_debug_conv_timeline(long long* out9) {
+extern "C" int cnm_debug_conv_timeline(long long* out12) {
+  long long* out9 = out12;
   CNM_REQUIRE(out9, CNM_ERR_INVALID_ARGUMENT, "cnm_debug_conv_timeline: null pointer");
   CNM_REQUIRE(g_tc_dbg_buf, CNM_ERR_INVALID_ARGUMENT, "cnm_debug_conv_timeline: set CNM_CONV_TIMELINE=1 before the first convolution");
-  cudaError_t e = cudaMemcpy(out9, g_tc_dbg_buf, 9 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(out9, g_tc_dbg_buf, 12 * sizeof(long long), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_debug_conv_timeline: %s", cudaGetErrorString(e));
   cudaMemset(g_tc_dbg_buf, 0, 16 * sizeof(long long));
   return CNM_OK;

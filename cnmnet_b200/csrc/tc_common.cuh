@@ -115,6 +115,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the reverse: thread t of the warp writes 32 consecutive fp32 columns of row (lane base + t)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major, 128B-swizzled smem tile: rows of 128 B, 8-row groups 1024 B apart
@@ -222,6 +236,87 @@ __device__ __forceinline__ void epi_head_partial(const uint32_t* v, const float*
   o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   o[2] = make_float4(acc[8], 0.0f, 0.0f, 0.0f);
+}
+
+// Balanced (stream-K) schedules (cnm_conv_desc.balance): the workspace is [flags, one int per CTA][slots, one per CTA];
+// a slot holds the raw fp32 accumulators of one contributor piece: 128 rows x 256 columns (per-tap kernel) or two
+// halves x 128 rows x 128 columns (row-halo kernels).
+constexpr int BALANCE_FLAG_BYTES = 1024;
+constexpr int BALANCE_SLOT_BYTES = 128 * 256 * 4;
+constexpr long long BALANCE_WS_BYTES = BALANCE_FLAG_BYTES + 148LL * BALANCE_SLOT_BYTES;
+
+// ---- balanced (stream-K) schedules: contributor pieces travel through an L2-resident slot -------------------------
+// Slot layout [column][128 rows] fp32: a warp's 32 rows of one column are 128 contiguous bytes (coalesced stores by the
+// contributor, conflict-free shared-memory reads by the finishing CTA).
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// 1-D bulk copy global -> this CTA's shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// Contributor piece (128 epilogue threads): accumulator columns [0, ncols) of this thread's TMEM row -> slot, then the flag.
+// tmem_row = address of column 0 in this warp's lane quarter; row = 0..127.
+__device__ __forceinline__ void balance_park(uint32_t tmem_row, int ncols, float* slot, int row, int* flag, bool leader) {
+#pragma unroll 1
+  for (int c = 0; c < ncols; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_row + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) __stcg(slot + (size_t)(c + j) * 128 + row, __uint_as_float(v[j]));
+  }
+  // generic-proxy stores -> visible to the finishing CTA's bulk copy (async proxy) once it has seen the flag
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __threadfence();
+  epi_bar();
+  if (leader) st_release_gpu(flag, 1);
+}
+// Head piece (128 epilogue threads), after the tile's own MMAs have completed (the operand rings are idle: this is the
+// CTA's last segment): for every contributor, bulk-copy its slot into the ring memory and add it to the accumulator in
+// TMEM, in contributor order.  `stride` = distance between consecutive contributors' CTA indices.
+__device__ __forceinline__ void balance_gather(uint32_t tmem_row, int ncols, const float* slots, int* flags, int first, int stride,
+                                               int ncontrib, uint8_t* ring, uint32_t bar, uint32_t& bar_phase, int row,
+                                               bool leader) {
+  const size_t slot_floats = (size_t)BALANCE_SLOT_BYTES / 4;
+  for (int c = 0; c < ncontrib; ++c) {
+    const int cta = first + c * stride;
+    if (leader) {
+      for (unsigned spins = 0; ld_acquire_gpu(flags + cta) == 0; ++spins) {
+        __nanosleep(100);
+        if (spins > (1u << 24)) __trap();   // ~2 s: the contributor never arrived (corrupt flags / workspace shared by concurrent launches)
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");
+      const uint32_t bytes = (uint32_t)ncols * 128u * 4u;
+      mbar_expect_tx(bar, bytes);
+      for (uint32_t o = 0; o < bytes; o += 32768u)
+        bulk_load(smem_u32(ring) + o, reinterpret_cast<const uint8_t*>(slots + (size_t)cta * slot_floats) + o,
+                  bytes - o < 32768u ? bytes - o : 32768u, bar);
+    }
+    mbar_wait(bar, bar_phase);
+    bar_phase ^= 1u;
+    const float* sm = reinterpret_cast<const float*>(ring);
+#pragma unroll 1
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_row + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + sm[(c0 + j) * 128 + row]);
+      tmem_st32(tmem_row + c0, v);
+    }
+    tmem_st_wait();
+    epi_bar();   // everyone is done with the ring copy before the next contributor's lands (and before flags are reset)
+  }
+  if (leader)
+    for (int c = 0; c < ncontrib; ++c) flags[first + c * stride] = 0;
 }
 
 // host: cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked)

@@ -303,6 +303,21 @@ def splitk_workspace(device, nfloats, lane=0):
         ws = _SPLITK_WS[key] = torch.empty((nfloats,), dtype=torch.float32, device=device)
     return ws
 
+_BALANCE_WS = {}   # (device, lane) -> zero-initialised workspace of the balanced (stream-K) schedules
+BALANCE = os.environ.get("CNM_CONV_BALANCE", "1") != "0"   # "tcb" / "halob" / "halo2b" as variants (cnm_conv_desc.balance)
+
+
+def balance_workspace(device, lane=0):
+    """Flags + one accumulator slot per CTA (include/cnmnet_b200.h: cnm_conv_desc.balance).  Zeroed once; the kernels
+    leave the flags zeroed.  One per (device, lane): launches sharing it must be stream-ordered."""
+    key = (str(device), lane)
+    ws = _BALANCE_WS.get(key)
+    if ws is None:
+        n = int(_lib.load().cnm_conv_balance_ws_bytes())
+        ws = _BALANCE_WS[key] = torch.zeros((n // 4,), dtype=torch.float32, device=device)
+    return ws
+
+
 # Kernel-variant choice (which of the three convolution kernels, output-channel tile, split-K factor) per layer shape:
 #   "cache"  (default)  the shipped table cnmnet_b200/tune/b200.json (+ CNM_TUNE_CACHE, a JSON file of the same format that
 #                        overrides it); shapes it does not list run the deterministic default of ConvOp.__init__.  Nothing is
@@ -359,19 +374,27 @@ class ConvOp:
         if dtype != CNM_TF32 and cout % 128 == 0 and backend != "simt" and TC_MULTICAST:
             # same program on clusters of 2 / 4 CTAs sharing every weight tile by TMA multicast (cnm_conv_desc.cluster)
             self.variants["tcm2"] = self.variants["tcm4"] = self.variants["tc"]
-        halo_ok = Ho >= 16 and Wo >= 16 and backend in ("tc", "halo", "halo2", "halo2h") and \
+        if dtype != CNM_TF32 and backend != "simt" and BALANCE:
+            self.variants["tcb"] = self.variants["tc"]   # same program, balanced (stream-K) schedule
+        halo_ok = Ho >= 16 and Wo >= 16 and backend in ("tc", "tcb", "halo", "halo2", "halo2h", "halob", "halo2b") and \
             (stride == 1 or all(s.kind == "act" for s in srcs))
         if halo_ok:
             groups, gcols, info = make_groups(srcs, k, ch, stride, split)
             assert len(gcols) == len(cols)
             flat = [v for pr in info for v in pr]
-            self.variants["halo"] = {"cols": gcols, "groups_dev": torch.tensor(groups, dtype=torch.int32).to(device),
+            gt = torch.tensor(groups, dtype=torch.int32)
+            gt[:, 3] += (torch.cumsum(gt[:, 3], 0) - gt[:, 3]) << 8   # cnm_conv_group.ntaps: taps | first weight step << 8
+            self.variants["halo"] = {"cols": gcols, "groups_dev": gt.to(device),
                                      "ngroups": len(groups), "pads": (C.c_int32 * len(flat))(*flat)}
             if (N * ((Ho + 15) // 16) * ((Wo + 15) // 16)) % 2 == 0 and HALO2_ENABLED:
                 self.variants["halo2"] = self.variants["halo"]   # same program, CTA-pair kernel
             if (N * ((Ho + 7) // 8) * ((Wo + 15) // 16)) % 2 == 0 and HALO2_ENABLED and dtype != CNM_TF32:
                 self.variants["halo2h"] = self.variants["halo"]  # same program, CTA pairs on 16x8 blocks (tile_h = 8)
-        elif backend in ("halo", "halo2", "halo2h"):
+            if dtype != CNM_TF32 and BALANCE:   # same programs, balanced (stream-K) schedule; column tile <= 128
+                self.variants["halob"] = self.variants["halo"]
+                if "halo2" in self.variants:
+                    self.variants["halo2b"] = self.variants["halo"]
+        elif backend in ("halo", "halo2", "halo2h", "halob", "halo2b"):
             raise ValueError("%s: the row-halo kernel needs an output of at least 16x16" % name)
         self.num_steps = len(cols)
         self.out = out if out is not None else torch.empty((N, Ho, Wo, cout * pf), dtype=TORCH_DTYPE[dtype],
@@ -397,7 +420,7 @@ class ConvOp:
         halo_tiles = N * ((Ho + 15) // 16) * ((Wo + 15) // 16) * max(1, cout // 256)
         if backend == "tc" and halo_ok and HALO_MODE != "off" and (halo_tiles >= 120 or HALO_MODE == "force"):
             backend = "halo"
-        self.tunable = backend in ("tc", "halo", "halo2", "halo2h") and HALO_MODE == "auto"
+        self.tunable = backend in ("tc", "halo", "halo2", "halo2h", "tcb", "halob", "halo2b") and HALO_MODE == "auto"
         self.select(backend, 0)
 
     @property
@@ -417,7 +440,11 @@ class ConvOp:
         self.desc.cluster = {"tcm2": 2, "tcm4": 4}.get(backend, 0)
         self.desc.tile_h = 8 if backend == "halo2h" else 0
         self.desc.ksplit = int(ksplit) if backend in ("tc", "tcm2", "tcm4") else 1
-        if self.desc.ksplit > 1:
+        self.desc.balance = 1 if backend in ("tcb", "halob", "halo2b") else 0
+        if self.desc.balance:
+            self._ws = balance_workspace(self.out.device, self.lane)
+            self.desc.splitk_ws = self._ws.data_ptr()
+        elif self.desc.ksplit > 1:
             d = self.desc
             ws = splitk_workspace(self.out.device, d.ksplit * d.N * d.Ho * d.Wo * d.Cout, self.lane)
             self._ws = ws
@@ -431,9 +458,9 @@ class ConvOp:
         """(kernel, output-channel tile, split-K factor) combinations worth timing for this layer."""
         d = self.desc
         out = []
-        for be in ("tc", "halo", "halo2", "halo2h"):
+        for be in ("tc", "halo", "halo2", "halo2h", "tcb", "halob", "halo2b"):
             if be in self.variants:
-                out += [(be, bn, 1) for bn in (256, 128, 64) if d.Cout % bn == 0]
+                out += [(be, bn, 1) for bn in (256, 128, 64) if d.Cout % bn == 0 and (bn <= 128 or be not in ("halob", "halo2b"))]
         # "halo2s" (fused plane sweep) is not timed here: it replaces the cost-volume launch as well, so it is compared
         # at step level (bench.py, CNM_FUSE_SWEEP=force) and entered into the table by hand if it wins
         mc = [be for be in ("tcm2", "tcm4") if be in self.variants]
@@ -522,8 +549,8 @@ class ConvOp:
                                                   v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),
                                                   self.out.data_ptr(), C.byref(self.sweep), stream), self.name)
             return
-        if self.backend in ("halo", "halo2", "halo2h"):
-            fn = lib.cnm_conv2d_halo if self.backend == "halo" else lib.cnm_conv2d_halo2
+        if self.backend in ("halo", "halo2", "halo2h", "halob", "halo2b"):
+            fn = lib.cnm_conv2d_halo if self.backend in ("halo", "halob") else lib.cnm_conv2d_halo2
             _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(),
                                            v["ngroups"], self.wp.data_ptr(), self.bias.data_ptr(),
                                            self.out.data_ptr(), stream), self.name)
@@ -531,6 +558,20 @@ class ConvOp:
         fn = lib.cnm_conv2d_simt if self.backend == "simt" else lib.cnm_conv2d_tc
         _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["steps_dev"].data_ptr(), self.wp.data_ptr(),
                       self.bias.data_ptr(), self.out.data_ptr(), stream), self.name)
+
+
+class _ShapeOnly:
+    """Stands in for an act tensor that is never materialised (the cost volume under the fused plane sweep): ConvOp
+    reads its shape and passes a valid, aligned device pointer that no kernel dereferences."""
+
+    def __init__(self, shape, anchor):
+        self.shape, self._anchor, self.is_cuda = tuple(shape), anchor, True
+
+    def is_contiguous(self):
+        return True
+
+    def data_ptr(self):
+        return self._anchor.data_ptr()
 
 
 class _Plan:
@@ -721,7 +762,9 @@ class DepthNetPlan(_Plan):
         self.may_fuse = FUSE_SWEEP != "0" and self.dtype == CNM_F16F8 and planes <= 128
         self.tex = None if (self.use_sweep and not self.may_fuse) else \
             torch.empty((lib.cnm_packed_source_bytes(N, H, W),), dtype=torch.uint8, device=self.device)
-        self.cost = self.buf(N, H, W, planes)
+        # with the fused plane sweep forced, the volume never exists: conv1.0 only needs its shape
+        self.cost = _ShapeOnly((N, H, W, planes * self.pf), self.hk) if (self.may_fuse and FUSE_SWEEP == "force") \
+            else self.buf(N, H, W, planes)
         self.img_taps = self.buf(N, H, W, ch)
         self.inputs = {}
 

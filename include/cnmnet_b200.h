@@ -258,6 +258,14 @@ typedef struct cnm_conv_desc {
                        results as 0 / 1 (off): the K order of a tile does not change. */
   int32_t tile_h;   /* cnm_conv2d_halo2 only, 2-byte dtypes: 8 = 16x8 pixel blocks per CTA instead of 16x16 (maps with few
                        blocks: twice the work items, two accumulator stages at a column tile of 256).  0 / 16 = 16x16. */
+  int32_t balance;  /* 1 = balanced (stream-K) schedule, 2-byte dtypes: the launch's K-steps (tiles x steps) are cut into one
+                       equal contiguous range per SM instead of whole tiles per CTA, so layers whose tile count is not a
+                       multiple of the SM count (120 or 240 tiles on 148 SMs) keep every SM busy.  A CTA whose range starts
+                       inside a tile parks that piece's raw fp32 accumulators in splitk_ws; the CTA holding the tile's first
+                       K-step adds the pieces in a fixed order in its epilogue (deterministic; last bits differ from the
+                       one-chain schedule).  cnm_conv2d_tc (ksplit <= 1, cluster <= 1) and cnm_conv2d_halo / _halo2 (column
+                       tile <= 128, 16x16 blocks).  splitk_ws: cnm_conv_balance_ws_bytes() bytes, 128B aligned, ZEROED once
+                       by the caller (the kernels leave it zeroed); launches sharing it must be stream-ordered. */
   /* Optional fused 1-channel 3x3 head on this layer's output (depth_layer, depthnet/depthNet_model.py:82-84), for the
    * 2-byte dtypes (tensor-core kernels only): head_w = [9][Cout] fp32 tap-major weights (device, 16B aligned),
    * head_partial = [Cout/64][N, Ho, Wo, 12] fp32 (device, 16B aligned): every 64-channel chunk of the output writes,
@@ -267,6 +275,8 @@ typedef struct cnm_conv_desc {
   float* head_partial;
   float* splitk_ws; /* [ksplit][N*Ho*Wo][Cout] fp32 workspace (device, 16B aligned) when ksplit > 1, else NULL */
 } cnm_conv_desc;
+
+int64_t cnm_conv_balance_ws_bytes(void);
 
 /* tcgen05/TMEM/TMA implicit GEMM (the product path).  `steps` is a DEVICE array of
  * num_steps entries (uploaded once when the layer plan is built); wp/bias/out are device.   */
@@ -283,7 +293,9 @@ int cnm_conv2d_simt(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const c
  * by t.  desc->num_steps is the total number of weight steps (sum of ntaps); map_info[2*map] = pad and
  * map_info[2*map+1] = rows (16 + vertical tap span; 0 = map unused) is a HOST array of 12 x 2 ints.             */
 typedef struct cnm_conv_group {
-  int32_t map, c0, dx, ntaps;
+  int32_t map, c0, dx;
+  int32_t ntaps; /* bits 0-7: taps of the group; bits 8..: index of the group's first weight step (= sum of the taps of
+                    the groups before it; read by the balanced schedule only) */
 } cnm_conv_group;
 int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* map_info,
                     const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,
@@ -296,10 +308,11 @@ int cnm_conv2d_halo2(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const 
                      void* stream);
 
 /* Debugging aid (CNM_CONV_TIMELINE=1 in the environment before the first convolution): CTA 0 of every cnm_conv2d_tc
- * launch leaves nine clock64 stamps -- kernel entry, prologue done, dependency wait done, first TMA issued, first
- * operands landed, last MMA of the first tile issued, first accumulator complete, last store drained, exit -- and this
- * call copies the stamps of the last launch to the host (it synchronises the device).  tools/conv_timeline.py.  */
-int cnm_debug_conv_timeline(long long* out9);
+ * launch leaves clock64 stamps -- kernel entry, prologue done, dependency wait done, first TMA issued, first
+ * operands landed, last MMA of the first segment issued, first accumulator complete, last store drained, exit, and (balanced
+ * schedule) contributor pieces gathered -- and this call copies the 12 slots (unused ones 0) of the last launch to the
+ * host (it synchronises the device).  tools/conv_timeline.py.  */
+int cnm_debug_conv_timeline(long long* out12);
 
 /* ---- conv1.0 with the plane sweep fused in -----------------------------------------
  * replaces getVolume + torch.cat + conv1[0]  (depthnet/depthNet_model.py:185-224, 231-235) in ONE kernel: the cost

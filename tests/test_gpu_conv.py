@@ -291,6 +291,91 @@ def test_multicast_clusters_are_bit_identical_to_single_ctas(dtype, case, bn, ks
         assert diff == 0, "%s: %d of %d output bytes differ from the single-CTA kernel" % (be, diff, outs["tc"].numel())
 
 
+@pytest.mark.parametrize("dtype", MC_DTYPES)
+@pytest.mark.parametrize("case,bn", [
+    ((5, 48, 64, [128], 256, 3, 1), 256),          # 120 tiles: every CTA holds 0.81 of a tile (head + contributor pieces)
+    ((5, 48, 64, [128, 128], 256, 3, 1), 128),     # 240 tiles on 148 CTAs, two sources
+    ((10, 96, 128, [64], 128, 3, 1), 128),         # 240 pair tiles on 74 pairs: whole tiles between the two pieces
+    ((5, 96, 128, [64, 64], 128, 3, 1), 64),       # column tile 64, two column tiles per pixel block
+    ((2, 40, 72, [64], 128, 5, 2), 128),           # stride 2 (parity sub-images), partial blocks
+    ((10, 12, 16, [128], 256, 3, 1), 256),         # 20 tiles: up to eight contributors per tile
+    ((10, 48, 64, [64, 64], 256, 3, 1), 128),      # + a 1-channel side tensor below: groups of unequal tap counts
+])
+def test_balanced_schedule_matches_static_schedule(dtype, case, bn):
+    """cnm_conv_desc.balance (stream-K): equal K ranges per SM, contributor pieces summed in a fixed order by the tile's
+    head CTA.  Against the oracle, against the static schedule of the same kernel (same products, another summation tree:
+    equal to fp32 rounding of the accumulator), bit-identical across runs, and the flags end up zeroed."""
+    N, H, W, cins, cout, k, stride = case
+    g = torch.Generator().manual_seed(cout + bn + N + H)
+    xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), k, k, generator=g) / np.sqrt(sum(cins) * k * k)
+    b = torch.randn(cout, generator=g)
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    acts = [to_act(x, dtype) for x in xs]
+    srcs = [engine.act_src(a, sum(cins[:i]), phys=engine.phys_factor(dtype)) for i, a in enumerate(acts)]
+    op = engine.ConvOp("t", srcs, k, stride, cout, N, Ho, Wo, dtype, dev(), True, backend="tc")
+    op.tunable = False
+    op.load(w, b)
+    want = oracle_conv(dtype, xs, w, b, k, stride)
+    ran = 0
+    for static, bal in (("tc", "tcb"), ("halo", "halob"), ("halo2", "halo2b")):
+        if bal not in op.variants or (bn > 128 and bal != "tcb"):
+            continue
+        op.select(static, bn)
+        op.out.fill_(7)
+        op(_lib.stream_ptr())
+        torch.cuda.synchronize()
+        ref = from_act(op.out, dtype)
+        outs = []
+        for _ in range(3):
+            op.select(bal, bn)
+            assert op.desc.balance == 1
+            op.out.fill_(7)
+            op(_lib.stream_ptr())
+            torch.cuda.synchronize()
+            outs.append(op.out.clone().view(torch.uint8))
+        ran += 1
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), bal
+        got = from_act(op.out, dtype)
+        assert rel_l2(got, want) < L2_TOL[dtype], bal
+        scale = max(1.0, want.abs().max().item())
+        assert (got - ref).abs().max().item() <= MAX_TOL[dtype] * scale, bal   # one storage-rounding flip at most
+        ws = engine.balance_workspace(dev())
+        assert int(ws[:256].view(torch.int32).abs().sum()) == 0, "%s left flags set" % bal
+    assert ran >= 1
+
+
+def test_balanced_schedule_with_fused_head_and_side_tensor():
+    """The balanced schedule on a layer of the iconv kind: two act sources + a 9-tap side tensor (a group with one tap) and
+    a fused 1-channel head computed from the summed accumulators."""
+    # (the side tensor case is the last one of test_balanced_schedule_matches_static_schedule's list)
+    dtype = _lib.CNM_F16F8
+    N, H, W, cin, cout, k = 5, 48, 64, 64, 64, 3
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / np.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g)
+    hw = torch.randn(1, cout, 3, 3, generator=g) * 0.05
+    act = to_act(x, dtype)
+    wt = hw[0].permute(1, 2, 0).reshape(9, cout).contiguous().to(dev())
+    res = {}
+    for be in ("halo2", "halo2b", "tc", "tcb"):
+        op = engine.ConvOp("t", [engine.act_src(act, 0, phys=engine.phys_factor(dtype))], k, 1, cout, N, H, W, dtype, dev(),
+                           True, backend=be)
+        op.tunable = False
+        op.select(be, 64)
+        partial = torch.full((N, H, W, 12), float("nan"), device=dev())
+        op.fuse_head(wt, partial)
+        op.load(w, b)
+        op(_lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert not torch.isnan(partial).any()
+        res[be] = (from_act(op.out, dtype), partial.clone())
+    for a, bb in (("halo2", "halo2b"), ("tc", "tcb")):
+        assert (res[a][0] - res[bb][0]).abs().max().item() < 3e-4   # a flip of the fp8 residual byte at most
+        assert (res[a][1] - res[bb][1]).abs().max().item() < 1e-5
+
+
 def test_conv_rejects_bad_arguments():
     lib = _lib.load()
     a = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=dev())  # 48 channels: not chunk aligned

@@ -386,6 +386,33 @@ def test_outputs_are_bit_identical_across_processes():
     assert hashes[0] == hashes[1]
 
 
+def test_programmatic_dependent_launch_does_not_change_results():
+    """cnm_set_pdl: with the step kernels chained by programmatic dependent launch (every kernel waits before its first
+    global-memory access) or in plain stream order, eagerly and as a captured graph, the outputs are the same bytes."""
+    from cnmnet_b200 import _lib
+    lib = _lib.load()
+    B, H, W, V = 2, 96, 128, 2
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(21, B, H, W, V)
+    dsd = synth.kaiming_state(onets.state_shapes(onets.DEPTHNET_LAYERS), 41, 0.02)
+    rsd = synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), 42, 0.02)
+    args = [t.to(dev()) for t in (ref, srcs, ref_cam, src_cams)]
+    outs = []
+    try:
+        for pdl in (1, 0):
+            for graph in (False, True):
+                lib.cnm_set_pdl(pdl)
+                pipe = _fresh_pipeline(dsd, rsd, graph=graph)
+                for _ in range(3):   # the third call of a graph pipeline is a replay
+                    d, n, p = pipe(*args)
+                torch.cuda.synchronize()
+                outs.append(torch.cat([d.flatten(), n.flatten(), p.flatten()]).clone())
+    finally:
+        lib.cnm_set_pdl(1)
+    assert torch.isfinite(outs[0]).all()
+    for o in outs[1:]:
+        assert torch.equal(outs[0].view(torch.int32), o.view(torch.int32))
+
+
 def test_range_check_counts_fp16_overflow():
     """CNM_F16F8 stores activations as fp16 (saturating at 65504); the debug range check counts convolution outputs
     beyond that range: zero on ordinary weights, non-zero when a layer is scaled out of range."""

@@ -20,8 +20,8 @@ op.tunable = False
 op.load(torch.randn(cout, cin, 3, 3) * 0.01, torch.zeros(cout))
 flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
 names = ["entry", "prologue done", "dependency wait done", "first TMA issued", "first operands landed",
-         "last MMA of tile 0 issued", "accumulator 0 complete", "stores drained", "exit"]
-for be, bn, cold in (("tc", 256, True), ("tc", 256, False), ("tc", 128, False)):
+         "last MMA of tile 0 issued", "accumulator 0 complete", "stores drained", "exit", "pieces gathered (balanced)"]
+for be, bn, cold in (("tc", 256, True), ("tc", 256, False), ("tc", 128, False), ("tcb", 256, False), ("tcb", 128, False)):
     op.select(be, bn)
     s = _lib.stream_ptr()
     for _ in range(3):
@@ -34,7 +34,7 @@ for be, bn, cold in (("tc", 256, True), ("tc", 256, False), ("tc", 128, False)):
     op(s)
     b.record()
     torch.cuda.synchronize()
-    ts = (C.c_longlong * 9)()
+    ts = (C.c_longlong * 12)()
     _lib.check(lib.cnm_debug_conv_timeline(ts))
     t0 = ts[0]
     print("%s/%d %s: %d K-steps, %.1f us by events; cycles since entry (CTA 0):" % (be, bn, "cold L2" if cold else "warm L2",

@@ -20,3 +20,5 @@ for tag, plan in (("depthnet", st["dplan"]), ("refine", st["rplan"])):
             row = "  ".join("%s/%d%s %.1f" % (be, bn, "k%d" % ks if ks > 1 else "", 1e3 * t)
                             for t, be, bn, ks in sorted(op.tuned[3], key=lambda r: (r[1], -r[2], r[3])))
             print("%-9s %-18s best %s/%d/k%d | %s" % (tag, name, op.tuned[0], op.tuned[1], op.tuned[2], row))
+if os.environ.get("CNM_SAVE_TUNE_CACHE"):
+    cnmnet_b200.engine.save_tune_cache(os.environ["CNM_SAVE_TUNE_CACHE"])
