@@ -14,7 +14,8 @@ VOLUME_NCHW_F32, VOLUME_ACT = 0, 1
 
 
 class ConvSrc(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("ptr", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("reserved", C.c_int32),
+                ("x_off", C.c_int32), ("y_off", C.c_int32), ("pitch_w", C.c_int32), ("pitch_hw", C.c_int32)]
 
 
 class ConvStep(C.Structure):
@@ -26,7 +27,7 @@ class ConvDesc(C.Structure):
     _fields_ = [("N", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32), ("Cout", C.c_int32),
                 ("c_out_total", C.c_int32), ("c_out_offset", C.c_int32), ("stride", C.c_int32), ("relu", C.c_int32),
                 ("num_srcs", C.c_int32), ("num_steps", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
-                ("acc_exp", C.c_int32), ("ksplit", C.c_int32), ("cluster", C.c_int32), ("tile_h", C.c_int32), ("balance", C.c_int32), ("head_w", C.c_void_p),
+                ("acc_exp", C.c_int32), ("ksplit", C.c_int32), ("cluster", C.c_int32), ("tile_h", C.c_int32), ("fold", C.c_int32), ("balance", C.c_int32), ("head_w", C.c_void_p),
                 ("head_partial", C.c_void_p), ("splitk_ws", C.c_void_p)]
 
 

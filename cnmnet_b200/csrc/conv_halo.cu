@@ -87,6 +87,11 @@ struct alignas(64) HaloParams {
   float* head_partial;   // [Cout/64 slices][N, Ho, Wo, 12] per-pixel tap dot products, one slice per 64-channel chunk
   int Ho, Wo, cout;
   // balanced schedule (cnm_conv_desc.balance, BAL instantiations): see HaloWalk
+  // folded bilinear x2 upsampling (cnm_conv_desc.fold, FOLD instantiations): the layer runs on the low-res tensor with
+  // 4 x fold_cout output channels, one block of fold_cout per output phase (a, b); phase maps address out[2y+a][2x+b]
+  CUtensorMap out_phase[4];
+  int fold_cout;
+  int map_xoff[HL_MAX_SRCS * 4], map_yoff[HL_MAX_SRCS * 4];   // window origin of a source view (cnm_conv_src.x_off / y_off)
   float* bal_slots;      // [gridDim.x][HALVES][128][BN] fp32 raw accumulators of the contributor pieces
   int* bal_flags;        // [gridDim.x] 1 = the CTA's contributor piece is in its slot (reset by the tile's finishing CTA)
   SweepFuseParams sw;    // SWEEP instantiations only
@@ -195,10 +200,20 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
 // TH = 16: the CTA's pixel block is 16x16 (two M = 128 halves sharing every weight tile).  TH = 8 (CTA pairs only): one
 // 16x8 half per CTA -- twice the work items for maps with few blocks (the 48x64 / 24x32 levels), BN = 256 with two
 // accumulator stages, and still a slab per (chunk, dx) instead of a pixel tile per tap.
-template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16, bool BAL = false>
+// Border class of a 16x16 pixel block: bit 0 top, 1 bottom, 2 left, 3 right edge of the map.  A group whose ntaps field
+// carries flags in bits 4-7 (FOLD instantiations: the border-correction groups of a folded upsampling) runs only on tiles
+// whose class has all of them; for a CTA pair the class is the union of the two blocks (the block that does not need the
+// group reads zeros through the view's TMA bounds).
+__device__ __forceinline__ int halo_block_class(const HaloParams& p, int m) {
+  const int x0 = (m % p.tiles_x) * 16, y0 = ((m / p.tiles_x) % p.tiles_y) * 16;
+  return (y0 == 0 ? 1 : 0) | (y0 + 16 >= p.Ho ? 2 : 0) | (x0 == 0 ? 4 : 0) | (x0 + 16 >= p.Wo ? 8 : 0);
+}
+
+template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16, bool BAL = false, bool FOLD = false>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   pdl_trigger();
   constexpr int HALVES = TH / 8;
+  static_assert(!FOLD || (!SWEEP && !TF32 && !BAL && TH == 16), "folded upsampling: 2-byte dtypes, 16x16 blocks, static schedule");
   static_assert(!BAL || (!SWEEP && !TF32 && TH == 16 && 4 * BN <= 512), "balanced schedule: 2-byte dtypes, 16x16 blocks, two accumulator stages");
   static_assert(TH == 16 || (TH == 8 && CG == 2 && !SWEEP), "16x8 blocks: CTA-pair instantiations");
   static_assert(!SWEEP || (!TF32 && 4 * BN <= 512 && TH == 16), "the fused plane sweep needs two accumulator stages (BN <= 128)");
@@ -246,6 +261,10 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   const bool leader = (rank == 0);
   const int total_tiles = (p.tiles_x * p.tiles_y * p.tiles_b / CG) * p.tiles_n;
   const int first_tile = blockIdx.x / CG, tile_stride = gridDim.x / CG;
+  auto tile_class = [&](int tile) {   // FOLD: which border groups this tile (pair) runs
+    const int m = CG * (tile / p.tiles_n);
+    return CG == 2 ? (halo_block_class(p, m) | halo_block_class(p, m + 1)) : halo_block_class(p, m);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.b_map);
@@ -307,9 +326,11 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         const int y0 = (m % p.tiles_y) * TH;
         const int n0 = m / p.tiles_y;
         bool vol_ready = false;
+        const int cls = FOLD ? tile_class(tile) : 0;
         for (int g = w.g0; g < w.g1; ++g) {
           const int4 gr = g_next;  // src, c0, dx, ntaps
           g_next = __ldg(reinterpret_cast<const int4*>(p.groups + ((g + 1 == w.g1) ? 0 : g + 1)));  // later segments start at group 0
+          if (FOLD && (((gr.w >> 4) & 15) & ~cls)) continue;   // border group of another tile class
           const int pad = p.map_pad[gr.x];
           const uint32_t slab_tx = (uint32_t)p.map_rows[gr.x] * 2048u;
           if (SWEEP && p.sw.park) mbar_wait_backoff(emptyA(sa), pa ^ 1, 200);
@@ -317,6 +338,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
           if (leader) mbar_expect_tx(fullA(sa), (uint32_t)CG * slab_tx);  // CG = 2: both CTAs' slabs
           const CUtensorMap* map = &p.a_maps[gr.x];
           int c1 = x0 + gr.z, c2 = y0 - pad, c3 = n0;
+          if (FOLD) { c1 -= p.map_xoff[gr.x]; c2 -= p.map_yoff[gr.x]; }
           if (SWEEP && gr.x == p.sw.vol_map) {
             // the tile's region of the volume sits in this CTA's scratch slot (written by warps 8-15): columns
             // dx + pad ... of the region, all rows
@@ -345,6 +367,21 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         if (BAL) {   // weight steps of the piece: bits 8.. of a group's ntaps field = index of its first weight step
           if (w.g0 > 0) ks0 = __ldg(&p.groups[w.g0].ntaps) >> 8;
           if (w.g1 < w.NG) ks1 = __ldg(&p.groups[w.g1].ntaps) >> 8;
+        }
+        if (FOLD) {   // group by group: the border groups of other tile classes are skipped, weight steps with them
+          const int cls = tile_class(w.tile);
+          for (int g = 0; g < w.NG; ++g) {
+            const int nf = __ldg(&p.groups[g].ntaps);
+            if (((nf >> 4) & 15) & ~cls) continue;
+            for (int kstep = nf >> 8; kstep < (nf >> 8) + (nf & 15); ++kstep) {
+              mbar_wait(emptyB(sb), pb ^ 1);
+              if (leader) mbar_expect_tx(fullB(sb), (uint32_t)CG * B_BYTES);
+              if (CG == 2) tma2_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN + (int)rank * (BN / 2));
+              else tma_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            }
+          }
+          continue;
         }
         for (int kstep = ks0; kstep < ks1; ++kstep) {
           if (SWEEP && p.sw.park) mbar_wait_backoff(emptyB(sb), pb ^ 1, 100);
@@ -379,8 +416,11 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * HALVES * BN + half * BN);
         uint32_t first = 1;
+        const int cls = FOLD ? tile_class(w.tile) : 0;
         for (int g = w.g0; g < w.g1; ++g) {
-          const int ntaps = __ldg(&p.groups[g].ntaps) & 0xff;
+          const int nfield = __ldg(&p.groups[g].ntaps);
+          if (FOLD && (((nfield >> 4) & 15) & ~cls)) continue;
+          const int ntaps = nfield & 15;
           mbar_wait(fullA(sa), pa);
           const uint32_t slab = base + sa * p.slab_bytes + half * 8 * 2048;
           for (int t = 0; t < ntaps; ++t) {
@@ -639,8 +679,13 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             epi_bar();
             if (storer) {
-              tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.mode ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
-                                   x0, y0 + 8 * half, n0);
+              if (FOLD) {   // column block -> (output phase, channel inside the phase)
+                const int cg = nt * BN + ch * CHUNK_CH, ph = cg / p.fold_cout, cc = cg - ph * p.fold_cout;
+                tma_store_4d(&p.out_phase[ph], smem_u32(stg), p.c_out_offset + (p.mode ? 2 * cc + part * 64 : cc), x0, y0 + 8 * half, n0);
+              } else {
+                tma_store_4d(&p.out_map, smem_u32(stg), p.c_out_offset + (p.mode ? 2 * (nt * BN + ch * CHUNK_CH) + part * 64 : nt * BN + ch * CHUNK_CH),
+                             x0, y0 + 8 * half, n0);
+              }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
@@ -685,6 +730,14 @@ __global__ void __launch_bounds__(256, 1) conv_halob_kernel(const __grid_constan
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2b_kernel(const __grid_constant__ HaloParams p) {
   conv_halo_body<BN, false, 2, false, 16, true>(p);
+}
+
+// folded bilinear x2 upsampling (cnm_conv_desc.fold), 2-byte dtypes, column tile 128
+__global__ void __launch_bounds__(256, 1) conv_halof_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<128, false, 1, false, 16, false, true>(p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2f_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<128, false, 2, false, 16, false, true>(p);
 }
 
 // 16x8 pixel blocks on CTA pairs (maps with few 16x16 blocks)
@@ -735,6 +788,8 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   CNM_REQUIRE(d->tile_h == 0 || d->tile_h == 16 || (d->tile_h == 8 && CG == 2 && !sweep && d->dtype != CNM_TF32),
               CNM_ERR_UNSUPPORTED_SHAPE, "%s: tile_h = %d (8 = 16x8 blocks: cnm_conv2d_halo2, 2-byte dtypes)", fn, d->tile_h);
   const int TH = d->tile_h == 8 ? 8 : 16;
+  const bool fold = d->fold != 0;
+  CNM_REQUIRE(!fold || (!sweep && TH == 16), CNM_ERR_UNSUPPORTED_SHAPE, "%s: fold goes with 16x16 blocks and no fused sweep", fn);
   CNM_REQUIRE(CG == 1 || (((d->Wo + 15) / 16) * ((d->Ho + TH - 1) / TH) * d->N) % 2 == 0, CNM_ERR_UNSUPPORTED_SHAPE,
               "%s: needs an even number of 16x%d pixel blocks (CTA pairs)", fn, TH);
   const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
@@ -743,9 +798,10 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   // map_info[src*4 + sub] = {rows above the tile, slab rows}; sub = 0 for stride 1, parity py*2+px for stride 2
   int rows_max = 0;
   const int nsub = d->stride == 2 ? 4 : 1;
+  const int mstride = fold ? 1 : 4;   // fold: operand map = source index (up to 12 sources, stride 1)
   for (int i = 0; i < d->num_srcs; ++i)
     for (int sub = 0; sub < nsub; ++sub) {
-      const int m = i * 4 + sub, pad = map_info[2 * m], rows = map_info[2 * m + 1];
+      const int m = i * mstride + sub, pad = map_info[2 * m], rows = map_info[2 * m + 1];
       if (rows == 0) continue;  // sub-image not used by any group
       CNM_REQUIRE(pad >= 0 && pad <= 4 && rows >= 16 && rows <= 24, CNM_ERR_UNSUPPORTED_SHAPE,
                   "%s: map %d has pad %d / %d slab rows", fn, m, pad, rows);
@@ -775,6 +831,7 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
                 d->reserved, d->Cout);
     BN = d->reserved;
   }
+  if (fold) BN = 128;   // the FOLD instantiations: two accumulator stages, a phase block (>= 64 channels) never straddles chunks
   p.tiles_n = d->Cout / BN;
   p.groups = groups;
   p.bias = bias;
@@ -851,13 +908,16 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     const cnm_conv_src& s = srcs[i];
     const uint64_t pix = (uint64_t)s.C * eb;
     for (int sub = 0; sub < nsub; ++sub) {
-      const int m = i * 4 + sub;
+      const int m = i * mstride + sub;
       if (p.map_rows[m] == 0) continue;
       if (sweep && m == p.sw.vol_map) continue;  // the scratch map stands in for it
       const uint32_t box[4] = {(uint32_t)ch, 16u, (uint32_t)p.map_rows[m], 1u};
       if (d->stride == 1) {
+        // a view keeps its parent's pitches; TMA zero-fills everything outside its H x W window
+        const uint64_t pw = s.pitch_w ? (uint64_t)s.pitch_w : (uint64_t)s.W, phw = s.pitch_hw ? (uint64_t)s.pitch_hw : pw * s.H;
         const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)d->N};
-        const uint64_t str[3] = {pix, pix * s.W, pix * s.W * s.H};
+        const uint64_t str[3] = {pix, pix * pw, pix * phw};
+        p.map_xoff[m] = s.x_off; p.map_yoff[m] = s.y_off;
         rc = encode_map(&p.a_maps[m], d->dtype, 4, s.ptr, dims, str, box);
       } else {  // parity sub-image (py, px): every other row / column of the source, doubled strides
         const int py = sub >> 1, px = sub & 1;
@@ -885,11 +945,29 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     const uint32_t box[4] = {(uint32_t)ch, 16u, 8u, 1u};
     rc = encode_map(&p.out_map, d->dtype, 4, out, dims, str, box);
     if (rc) return rc;
+    if (fold) {   // phase (a, b): out[n][2y + a][2x + b], addressed with low-res coordinates through doubled strides
+      p.fold_cout = d->Cout / 4;
+      const uint64_t W2 = 2 * (uint64_t)d->Wo, H2 = 2 * (uint64_t)d->Ho;
+      const uint64_t pstr[3] = {2 * pix, 2 * pix * W2, pix * W2 * H2};
+      for (int ph = 0; ph < 4; ++ph) {
+        const uint8_t* base = (const uint8_t*)out + ((uint64_t)(ph >> 1) * W2 + (ph & 1)) * pix;
+        rc = encode_map(&p.out_phase[ph], d->dtype, 4, base, dims, pstr, box);
+        if (rc) return rc;
+      }
+    }
   }
   const int total = (m_tiles / CG) * p.tiles_n;  // CG = 2: super-tiles, one per CTA pair
   const int grid = CG * (total < 148 / CG ? total : 148 / CG);
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
+  if (fold) {
+    static DynSmemLimit f1, f2;
+    cudaError_t e = CG == 2 ? f2.ensure(conv_halo2f_kernel, smem) : f1.ensure(conv_halof_kernel, smem);
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
+    if (CG == 2) launch_pdl(conv_halo2f_kernel, dim3(grid), dim3(256), smem, s, p);
+    else launch_pdl(conv_halof_kernel, dim3(grid), dim3(256), smem, s, p);
+    return after_launch(fn);
+  }
   if (d->balance) {
     CNM_REQUIRE(!sweep && !tf32 && TH == 16 && BN <= 128, CNM_ERR_UNSUPPORTED_SHAPE,
                 "%s: balance needs a 2-byte dtype, 16x16 blocks and a column tile of at most 128 (got %d)", fn, BN);

@@ -173,7 +173,12 @@ int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* 
               d->dtype);
   CNM_REQUIRE(d->N > 0 && d->Ho > 0 && d->Wo > 0 && d->Cout > 0, CNM_ERR_INVALID_ARGUMENT, "%s: bad output shape", fn);
   CNM_REQUIRE(d->stride == 1 || d->stride == 2, CNM_ERR_UNSUPPORTED_SHAPE, "%s: stride %d", fn, d->stride);
-  CNM_REQUIRE(d->num_srcs >= 1 && d->num_srcs <= 3, CNM_ERR_UNSUPPORTED_SHAPE, "%s: num_srcs %d (max 3)", fn, d->num_srcs);
+  const bool fold = d->fold != 0;   // cnm_conv2d_halo / _halo2 only (they check the rest); up to 12 sources, views allowed
+  CNM_REQUIRE(d->num_srcs >= 1 && d->num_srcs <= (fold ? 12 : 3), CNM_ERR_UNSUPPORTED_SHAPE, "%s: num_srcs %d (max %d)", fn,
+              d->num_srcs, fold ? 12 : 3);
+  CNM_REQUIRE(!fold || (d->Cout % 256 == 0 && d->stride == 1 && !d->head_partial && d->ksplit <= 1 && !d->balance &&
+                        d->dtype != CNM_TF32),
+              CNM_ERR_UNSUPPORTED_SHAPE, "%s: fold needs a stride-1 layer of 4 x (multiple of 64) channels, a 2-byte dtype, no head / split-K / balance", fn);
   CNM_REQUIRE(d->num_steps >= 1, CNM_ERR_INVALID_ARGUMENT, "%s: num_steps %d", fn, d->num_steps);
   CNM_REQUIRE((d->head_w == nullptr) == (d->head_partial == nullptr), CNM_ERR_INVALID_ARGUMENT,
               "%s: head_w and head_partial go together", fn);
@@ -182,14 +187,20 @@ int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* 
               CNM_ERR_UNSUPPORTED_SHAPE, "%s: the fused head needs a 2-byte dtype and 16B-aligned buffers", fn);
   const int ch = chunk_channels(d->dtype);
   CNM_REQUIRE(d->Cout % ch == 0 && d->c_out_total % ch == 0 && d->c_out_offset % ch == 0 &&
-                  d->c_out_offset + phys_factor(d->dtype) * d->Cout <= d->c_out_total,
+                  d->c_out_offset + phys_factor(d->dtype) * (fold ? d->Cout / 4 : d->Cout) <= d->c_out_total,
               CNM_ERR_UNSUPPORTED_SHAPE, "%s: Cout=%d / c_out_total=%d / offset=%d must be chunk (%d) aligned", fn,
               d->Cout, d->c_out_total, d->c_out_offset, ch);
   for (int i = 0; i < d->num_srcs; ++i) {
     CNM_REQUIRE(srcs[i].ptr && srcs[i].C > 0 && srcs[i].C % ch == 0, CNM_ERR_UNSUPPORTED_SHAPE,
                 "%s: source %d channels %d must be a multiple of %d", fn, i, srcs[i].C, ch);
     CNM_REQUIRE(((uintptr_t)srcs[i].ptr & 127) == 0, CNM_ERR_INVALID_ARGUMENT, "%s: source %d must be 128B aligned", fn, i);
-    if (d->stride == 1)
+    const bool view = srcs[i].x_off || srcs[i].y_off || srcs[i].pitch_w || srcs[i].pitch_hw;
+    CNM_REQUIRE(!view || fold, CNM_ERR_UNSUPPORTED_SHAPE, "%s: source %d is a view (fold layers of the row-halo kernels only)", fn, i);
+    if (view)
+      CNM_REQUIRE(srcs[i].x_off >= 0 && srcs[i].y_off >= 0 && srcs[i].W > 0 && srcs[i].H > 0 && srcs[i].x_off + srcs[i].W <= d->Wo &&
+                      srcs[i].y_off + srcs[i].H <= d->Ho && srcs[i].pitch_w >= srcs[i].W && srcs[i].pitch_hw >= srcs[i].pitch_w * srcs[i].H,
+                  CNM_ERR_INVALID_ARGUMENT, "%s: source %d: bad view", fn, i);
+    else if (d->stride == 1)
       CNM_REQUIRE(srcs[i].H == d->Ho && srcs[i].W == d->Wo, CNM_ERR_UNSUPPORTED_SHAPE,
                   "%s: source %d is %dx%d, output %dx%d", fn, i, srcs[i].H, srcs[i].W, d->Ho, d->Wo);
     else

@@ -568,6 +568,7 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   if (rc) return rc;
   const int eb = elem_bytes(d->dtype), ch = chunk_channels(d->dtype);
   CNM_REQUIRE(d->Cout % 64 == 0, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_tc: Cout=%d must be a multiple of 64", d->Cout);
+  CNM_REQUIRE(!d->fold, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_tc: fold is a cnm_conv2d_halo / _halo2 feature");
   TcParams p;
   memset(&p, 0, sizeof(p));
   // pixel tile: TW x TH x NB = 128

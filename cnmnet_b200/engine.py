@@ -560,6 +560,151 @@ class ConvOp:
                       self.bias.data_ptr(), self.out.data_ptr(), stream), self.name)
 
 
+# ---- bilinear x2 upsampling folded into the consuming 3x3 convolution ------------------------------------------------
+# nn.Upsample(scale_factor=2, mode='bilinear') + conv3x3 (depthnet/depthNet_model.py:92-98, `upconv`) is a linear map of
+# the LOW-RES tensor x: with u[2i] = .25 x[i-1] + .75 x[i], u[2i+1] = .75 x[i] + .25 x[i+1] (align_corners=False), output
+# row 2i+a of the convolution reads low-res rows i-1, i, i+1 with the kernel rows combined by _FOLD_A[a] (low-res tap j x
+# kernel row r), and the same along the columns.  So the layer is ONE 3x3 convolution on x with 4 x Cout output channels --
+# a block of Cout per output phase (a, b) -- whose epilogue scatters block (a, b) of pixel (i, j) to out[2i+a][2j+b]
+# (cnm_conv_desc.fold): the upsampled tensor is never written or read, and a 64-channel layer runs at a column tile of 128.
+# At the border the interpolation clamps (x[-1] := x[0]) while the convolution pads u with zeros, and TMA hands the kernel
+# zeros for x[-1]: the difference to the interior operator is, per dimension, a multiple of x[0] (first row / column:
+# _FOLD_T[a]) or x[last] (_FOLD_B[a]) only.  Those corrections enter the same accumulator as extra K groups whose operand is
+# a one-row / one-column / one-pixel VIEW of x (cnm_conv_src.x_off ...; everything outside the view reads as zero) and which
+# run only on the tiles of that border class (bits 4-7 of cnm_conv_group.ntaps): rows need 3 column taps, columns 3 row
+# taps, corners one -- 2-D operator = (A + dR) x (A + dC) = AxA + dRxA + AxdC + dRxdC.
+FOLD_UPSAMPLE = os.environ.get("CNM_FOLD_UPSAMPLE", "1") != "0"
+FOLD_MIN_BLOCKS = int(os.environ.get("CNM_FOLD_MIN_BLOCKS", "6"))   # low-res blocks (16 px) per side from which folding pays
+_FOLD_A = (((.75, .25, 0.), (.25, .75, .75), (0., 0., .25)), ((.25, 0., 0.), (.75, .75, .25), (0., .25, .75)))
+_FOLD_T = ((-.25, .25, 0.), (.25, 0., 0.))
+_FOLD_B = ((0., 0., .25), (0., .25, -.25))
+_FOLD_TOP, _FOLD_BOTTOM, _FOLD_LEFT, _FOLD_RIGHT = 1, 2, 4, 8
+
+
+def fold_upconv_weights(wf):
+    """[Cout, Cin, 3, 3] (BN folded) -> [4 Cout, 9 Cin, 3, 3] fp32: input-channel block s holds the weights of operand s
+    (0 x, 1 top row, 2 bottom row, 3 left column, 4 right column, 5-8 corners TL TR BL BR), output block 2a+b is phase
+    (a, b); kernel position [j, l] = low-res tap (j-1, l-1).  Computed in fp64."""
+    w = wf.double()
+    cout, cin = w.shape[:2]
+    big = torch.zeros((4, cout, 9, cin, 3, 3), dtype=torch.float64, device=w.device)
+    t64 = lambda v: torch.tensor(v, dtype=torch.float64, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            A_a, A_b, T_a, T_b, B_a, B_b = t64(_FOLD_A[a]), t64(_FOLD_A[b]), t64(_FOLD_T[a]), t64(_FOLD_T[b]), t64(_FOLD_B[a]), t64(_FOLD_B[b])
+            o = big[2 * a + b]
+            o[:, 0] = torch.einsum("jr,lt,ocrt->ocjl", A_a, A_b, w)
+            o[:, 1, :, 1, :] = torch.einsum("r,lt,ocrt->ocl", T_a, A_b, w)
+            o[:, 2, :, 1, :] = torch.einsum("r,lt,ocrt->ocl", B_a, A_b, w)
+            o[:, 3, :, :, 1] = torch.einsum("jr,t,ocrt->ocj", A_a, T_b, w)
+            o[:, 4, :, :, 1] = torch.einsum("jr,t,ocrt->ocj", A_a, B_b, w)
+            for s_, (ra, cb) in enumerate(((T_a, T_b), (T_a, B_b), (B_a, T_b), (B_a, B_b))):
+                o[:, 5 + s_, :, 1, 1] = torch.einsum("r,t,ocrt->oc", ra, cb, w)
+    return big.reshape(4 * cout, 9 * cin, 3, 3).float()
+
+
+class FoldedUpconvOp(ConvOp):
+    """`upconv` of the reference (Upsample x2 bilinear + conv3x3 + BN + ReLU) as one convolution on the low-res act tensor
+    `x` [N, h, w, Cin]; writes the [N, 2h, 2w, Cout] output.  See the section comment above; kernels conv_halo2f / conv_halof
+    (csrc/conv_halo.cu, FOLD instantiations)."""
+
+    def __init__(self, name, x, cout, N, h, w, dtype, device, out, relu=True, lane=0):
+        if dtype == CNM_TF32 or cout % 64 or h < 16 or w < 16:
+            raise ValueError("%s: folded upsampling needs a 2-byte dtype, Cout %% 64 == 0 and a low-res map of at least 16x16" % name)
+        self.name, self.k, self.stride, self.dtype, self.lane = name, 3, 1, dtype, lane
+        ch, split, pf = chunk_channels(dtype), split_passes(dtype), phys_factor(dtype)
+        cin = x.shape[3] // pf
+        assert cin % ch == 0 and tuple(x.shape[:3]) == (N, h, w) and tuple(out.shape) == (N, 2 * h, 2 * w, cout * pf)
+        self.x, self.out, self.cin, self.cout_phase = x, out, cin, cout
+        groups, cols = [], []   # group = (map, c0 physical, dx, ntaps, class flags)
+        fl = {1: _FOLD_TOP, 2: _FOLD_BOTTOM, 3: _FOLD_LEFT, 4: _FOLD_RIGHT, 5: _FOLD_TOP | _FOLD_LEFT,
+              6: _FOLD_TOP | _FOLD_RIGHT, 7: _FOLD_BOTTOM | _FOLD_LEFT, 8: _FOLD_BOTTOM | _FOLD_RIGHT}
+        for c0 in range(0, cin, ch):
+            for ap, wp_ in _chunk_passes(split):
+                pc = _pc0(c0, ap, split)
+                for t in range(3):                                    # x: a slab per column tap, three row taps
+                    groups.append((0, pc, t - 1, 3, 0))
+                    cols += [("act", c0, r, t, wp_, ap) for r in range(3)]
+                for s_ in (1, 2):                                     # first / last row: three column taps, row tap 0
+                    for t in range(3):
+                        groups.append((s_, pc, t - 1, 1, fl[s_]))
+                        cols.append(("act", s_ * cin + c0, 1, t, wp_, ap))
+                for s_ in (3, 4):                                     # first / last column: column tap 0, three row taps
+                    groups.append((s_, pc, 0, 3, fl[s_]))
+                    cols += [("act", s_ * cin + c0, r, 1, wp_, ap) for r in range(3)]
+                for s_ in (5, 6, 7, 8):                               # corners
+                    groups.append((s_, pc, 0, 1, fl[s_]))
+                    cols.append(("act", s_ * cin + c0, 1, 1, wp_, ap))
+        starts, pos = [], 0
+        for g in groups:
+            starts.append(pos)
+            pos += g[3]
+        gorder = _corrections_first([cols[st] for st in starts])      # fp8 / lo rows first, group-wise (see make_groups)
+        gcols = [c for i in gorder for c in cols[starts[i]:starts[i] + groups[i][3]]]
+        groups = [groups[i] for i in gorder]
+        first, pos = [], 0
+        for g in groups:
+            first.append(pos)
+            pos += g[3]
+        gt = torch.tensor([[g[0], g[1], g[2], g[3] | (g[4] << 4) | (f << 8)] for g, f in zip(groups, first)], dtype=torch.int32)
+        info = [[0, 0] for _ in range(12)]
+        for m in range(9):
+            info[m] = [1, 18] if m in (0, 3, 4) else [0, 16]
+        flat = [v for pr in info for v in pr]
+        pairs_ok = (N * ((h + 15) // 16) * ((w + 15) // 16)) % 2 == 0 and HALO2_ENABLED
+        self.backend = "halo2f" if pairs_ok else "halof"
+        self.variants = {self.backend: {"cols": gcols, "groups_dev": gt.to(device), "ngroups": len(groups),
+                                        "pads": (C.c_int32 * len(flat))(*flat)}}
+        self.num_steps = len(gcols)
+        self.wp = torch.zeros((4 * cout, self.num_steps * ch), dtype=TORCH_DTYPE[dtype], device=device)
+        self.bias = torch.zeros((4 * cout,), dtype=torch.float32, device=device)
+        self.desc = _lib.ConvDesc(N, h, w, 4 * cout, out.shape[3], 0, 1, 1 if relu else 0, 9, self.num_steps, dtype, 128)
+        self.desc.fold = 1
+        es = x.element_size()
+        pix = x.shape[3] * es
+        arr = (_lib.ConvSrc * 9)()
+        base = x.data_ptr()
+        views = {1: (1, w, 0, 0), 2: (1, w, 0, h - 1), 3: (h, 1, 0, 0), 4: (h, 1, w - 1, 0), 5: (1, 1, 0, 0), 6: (1, 1, w - 1, 0),
+                 7: (1, 1, 0, h - 1), 8: (1, 1, w - 1, h - 1)}   # source -> (H, W, x_off, y_off)
+        arr[0] = _lib.ConvSrc(base, h, w, x.shape[3], 0)
+        for s_, (vh, vw, xo, yo) in views.items():
+            arr[s_] = _lib.ConvSrc(base + (yo * w + xo) * pix, vh, vw, x.shape[3], 0, xo, yo, w, h * w)
+        self.srcs_arr, self.srcs = arr, []
+        # issued MACs x 2 of the interior operator (the border groups add ~3 / 9 on edge tiles, 7 / 9 on corner tiles)
+        main_steps = 9 * (cin // ch) * len(_chunk_passes(split))
+        self.flops = 2.0 * N * h * w * 4 * cout * main_steps * ch * (1.5 if dtype == CNM_F16F8 else 1.0)
+        self.flops_bf16_time = 2.0 * N * h * w * 4 * cout * main_steps * ch
+        self._weights, self.sweep, self.tunable = None, None, False
+        self.tuned = (self.backend, 128, 1, None)
+        self.key = repr(("fold", dtype, N, h, w, cout, cin))
+
+    @property
+    def cols(self):
+        return self.variants[self.backend]["cols"]
+
+    def select(self, backend, bn, ksplit=1):
+        if backend != self.backend:
+            raise ValueError("%s: a folded upsampling layer runs %s only" % (self.name, self.backend))
+
+    def tune(self, stream, reps=3):
+        return
+
+    def load(self, wf, bf):
+        self._weights = (wf, bf)
+        big = fold_upconv_weights(wf.to(self.wp.device))
+        if self.dtype == CNM_F16F8:
+            self.desc.acc_exp = f16f8_weight_exp(big)
+        self.wp.copy_(pack_weights(big, self.cols, chunk_channels(self.dtype), self.dtype))
+        self.bias.copy_(bf.to(self.bias.device).repeat(4))
+
+    def __call__(self, stream):
+        lib = _lib.load()
+        v = self.variants[self.backend]
+        fn = lib.cnm_conv2d_halo2 if self.backend == "halo2f" else lib.cnm_conv2d_halo
+        _lib.check(fn(C.byref(self.desc), self.srcs_arr, v["pads"], v["groups_dev"].data_ptr(), v["ngroups"], self.wp.data_ptr(),
+                      self.bias.data_ptr(), self.out.data_ptr(), stream), self.name)
+
+
 class _ShapeOnly:
     """Stands in for an act tensor that is never materialised (the cost volume under the fused plane sweep): ConvOp
     reads its shape and passes a valid, aligned device pointer that no kernel dereferences."""
@@ -643,6 +788,26 @@ class _Plan:
         self.ops.append(lambda s: _lib.check(lib.cnm_upsample2x(x.data_ptr(), out.data_ptr(), N, h, w, Cc, dt, s),
                                              "upsample2x"))
         return out
+
+    def upconv(self, name, x, cout, N, H, W):
+        """The reference's `upconv` block (Upsample x2 bilinear + conv3x3 + BN + ReLU, depthNet_model.py:92-98) on the
+        low-res act tensor x -> [N, H, W, cout]; x is released.  Maps of at least FOLD_MIN_BLOCKS 16-pixel blocks per side
+        run it as ONE convolution on x (FoldedUpconvOp: the upsampled tensor is never written); smaller ones -- where the
+        border-correction groups would cost more than the upsampling pass -- keep the two kernels."""
+        h, w = H // 2, W // 2
+        if FOLD_UPSAMPLE and self.dtype != CNM_TF32 and self.backend == "tc" and HALO_MODE != "off" and \
+                min(h, w) // 16 >= FOLD_MIN_BLOCKS and cout % 64 == 0:
+            out = self.buf(N, H, W, cout)
+            op = FoldedUpconvOp(name, x, cout, N, h, w, self.dtype, self.device, out, lane=self.lane)
+            self.convs[name] = op
+            self.ops.append(op)
+            self.release(x)
+            return out
+        u = self.upsample(x)
+        self.release(x)
+        y = self.conv(name, [self.src(u, 0)], 3, 1, cout, N, H, W)
+        self.release(u)
+        return y
 
     def head(self, name, x, scale, want_logits=False):
         N, H, W, Cc = x.shape
@@ -791,7 +956,7 @@ class DepthNetPlan(_Plan):
 
     def _trunk(self, want_logits):
         N, H, W = self.N, self.H, self.W
-        cv, rel, up = self.conv, self.release, self.upsample
+        cv, rel = self.conv, self.release
         x = cv("conv1.0", [self.src(self.cost, 3), Src(self.img_taps, "rowtaps", 0, self.ch, 0, 3)], 7, 1, 128, N, H, W)
         if self.may_fuse:
             self.convs["conv1.0"].attach_sweep(0, self.Bref, self.D, self.idmin, self.idmax, self.tex, self.hk)
@@ -811,42 +976,27 @@ class DepthNetPlan(_Plan):
         conv5 = cv("conv5.3", [self.src(x, 0)], 3, 2, 512, N, H // 32, W // 32)
         rel(x)
 
-        u = up(conv5)
-        rel(conv5)
-        up5 = cv("upconv5.1", [self.src(u, 0)], 3, 1, 512, N, H // 16, W // 16)
-        rel(u)
+        up5 = self.upconv("upconv5.1", conv5, 512, N, H // 16, W // 16)
         iconv5 = cv("iconv5.0", [self.src(up5, 0), self.src(conv4, 512)], 3, 1, 512, N, H // 16, W // 16)
         rel(up5, conv4)
-        u = up(iconv5)
-        rel(iconv5)
-        up4 = cv("upconv4.1", [self.src(u, 0)], 3, 1, 512, N, H // 8, W // 8)
-        rel(u)
+        up4 = self.upconv("upconv4.1", iconv5, 512, N, H // 8, W // 8)
         iconv4 = cv("iconv4.0", [self.src(up4, 0), self.src(conv3, 512)], 3, 1, 512, N, H // 8, W // 8)
         rel(up4, conv3)
         self.disp4, l4 = self.head("disp4", iconv4, self.scale, want_logits)
         t4 = self.disp_taps(self.disp4)
-        u = up(iconv4)
-        rel(iconv4)
-        up3 = cv("upconv3.1", [self.src(u, 0)], 3, 1, 256, N, H // 4, W // 4)
-        rel(u)
+        up3 = self.upconv("upconv3.1", iconv4, 256, N, H // 4, W // 4)
         iconv3 = cv("iconv3.0", [self.src(up3, 0), self.src(conv2, 256), Src(t4, "taps3x3", 512, self.ch, 0, 1)], 3, 1,
                     256, N, H // 4, W // 4)
         rel(up3, conv2, t4)
         self.disp3, l3 = self.head("disp3", iconv3, self.scale, want_logits)
         t3 = self.disp_taps(self.disp3)
-        u = up(iconv3)
-        rel(iconv3)
-        up2 = cv("upconv2.1", [self.src(u, 0)], 3, 1, 128, N, H // 2, W // 2)
-        rel(u)
+        up2 = self.upconv("upconv2.1", iconv3, 128, N, H // 2, W // 2)
         iconv2 = cv("iconv2.0", [self.src(up2, 0), self.src(conv1, 128), Src(t3, "taps3x3", 256, self.ch, 0, 1)], 3, 1,
                     128, N, H // 2, W // 2)
         rel(up2, conv1, t3)
         self.disp2, l2 = self.head("disp2", iconv2, self.scale, want_logits)
         t2 = self.disp_taps(self.disp2)
-        u = up(iconv2)
-        rel(iconv2)
-        up1 = cv("upconv1.1", [self.src(u, 0)], 3, 1, 64, N, H, W)
-        rel(u)
+        up1 = self.upconv("upconv1.1", iconv2, 64, N, H, W)
         self.iconv1 = cv("iconv1.0", [self.src(up1, 0), Src(t2, "taps3x3", 64, self.ch, 0, 1)], 3, 1, 64, N, H, W)
         rel(up1, t2)
         self.disp1, l1 = self.head("disp1", self.iconv1, self.scale, want_logits)
@@ -929,16 +1079,10 @@ class RefinePlan(_Plan):
             u3 = cv("upconv3_%s.1" % br, [self.src(up_conv3, 0)], 3, 1, 256, B, H // 4, W // 4)
             i3 = cv("iconv3_%s.0" % br, [self.src(u3, 0), self.src(conv2, 256)], 3, 1, 256, B, H // 4, W // 4)
             rel(u3)
-            u = self.upsample(i3)
-            rel(i3)
-            u2 = cv("upconv2_%s.1" % br, [self.src(u, 0)], 3, 1, 128, B, H // 2, W // 2)
-            rel(u)
+            u2 = self.upconv("upconv2_%s.1" % br, i3, 128, B, H // 2, W // 2)
             i2 = cv("iconv2_%s.0" % br, [self.src(u2, 0), self.src(conv1, 128)], 3, 1, 128, B, H // 2, W // 2)
             rel(u2)
-            u = self.upsample(i2)
-            rel(i2)
-            u1 = cv("upconv1_%s.1" % br, [self.src(u, 0)], 3, 1, 64, B, H, W)
-            rel(u)
+            u1 = self.upconv("upconv1_%s.1" % br, i2, 64, B, H, W)
             i1 = cv("iconv1_%s.0" % br, [self.src(u1, 0)], 3, 1, 64, B, H, W)
             rel(u1)
             self.iconv1[br] = i1          # kept: ReturnVolume hands iconv1_depth out

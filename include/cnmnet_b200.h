@@ -228,9 +228,14 @@ int cnm_head_finish(const float* partial, int nslices, float bias, float scale, 
  * their taps against the four parity sub-images of the source (sub = py*2+px).
  */
 typedef struct cnm_conv_src {
-  const void* ptr; /* act tensor [N, H, W, C] */
+  const void* ptr; /* act tensor [N, H, W, C]; for a view: its first pixel */
   int32_t H, W, C;
   int32_t reserved;
+  /* View (fold layers of cnm_conv2d_halo / _halo2 only; all four 0 = the whole contiguous tensor): the source is the
+   * window rows [y_off, y_off + H) x columns [x_off, x_off + W) of images that are pitch_w pixels wide and pitch_hw pixels
+   * apart; every pixel outside the window reads as zero (TMA bounds).  This is how a border row / column / corner of a
+   * tensor becomes an operand of its own without being copied.                                                      */
+  int32_t x_off, y_off, pitch_w, pitch_hw;
 } cnm_conv_src;
 
 typedef struct cnm_conv_step {
@@ -258,6 +263,15 @@ typedef struct cnm_conv_desc {
                        results as 0 / 1 (off): the K order of a tile does not change. */
   int32_t tile_h;   /* cnm_conv2d_halo2 only, 2-byte dtypes: 8 = 16x8 pixel blocks per CTA instead of 16x16 (maps with few
                        blocks: twice the work items, two accumulator stages at a column tile of 256).  0 / 16 = 16x16. */
+  int32_t fold;     /* cnm_conv2d_halo / _halo2, 2-byte dtypes: 1 = the layer is nn.Upsample(x2, bilinear) + conv3x3 folded into
+                       ONE convolution on the low-res tensor (depthnet/depthNet_model.py:92-98, `upconv`).  Ho x Wo is the
+                       LOW-RES size, Cout = 4 x C channels = one block of C per output phase (a, b), and the epilogue writes
+                       block (a, b) of low-res pixel (y, x) to out[n][2y+a][2x+b] of the [N, 2Ho, 2Wo, c_out_total] output.
+                       The caller supplies the phase-combined weights (bilinear taps 0.75 / 0.25 folded into the 3x3
+                       kernel) and, as extra sources, one-row / one-column / one-pixel VIEWS of the input with the border
+                       corrections (where the interpolation clamps and the convolution pads with zeros, the operator
+                       differs from the interior one); groups carry a border class in bits 4-7 of ntaps and run only on
+                       the tiles of that class.  Up to 12 sources, operand map = source index.  See engine.FoldedUpconvOp. */
   int32_t balance;  /* 1 = balanced (stream-K) schedule, 2-byte dtypes: the launch's K-steps (tiles x steps) are cut into one
                        equal contiguous range per SM instead of whole tiles per CTA, so layers whose tile count is not a
                        multiple of the SM count (120 or 240 tiles on 148 SMs) keep every SM busy.  A CTA whose range starts
@@ -294,8 +308,9 @@ int cnm_conv2d_simt(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const c
  * map_info[2*map+1] = rows (16 + vertical tap span; 0 = map unused) is a HOST array of 12 x 2 ints.             */
 typedef struct cnm_conv_group {
   int32_t map, c0, dx;
-  int32_t ntaps; /* bits 0-7: taps of the group; bits 8..: index of the group's first weight step (= sum of the taps of
-                    the groups before it; read by the balanced schedule only) */
+  int32_t ntaps; /* bits 0-3: taps of the group; bits 4-7: border class the group needs (fold layers: 1 top, 2 bottom,
+                    4 left, 8 right; 0 = every tile); bits 8..: index of the group's first weight step (= sum of the taps
+                    of the groups before it; read by the balanced and the fold schedules) */
 } cnm_conv_group;
 int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* map_info,
                     const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,

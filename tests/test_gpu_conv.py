@@ -376,6 +376,69 @@ def test_balanced_schedule_with_fused_head_and_side_tensor():
         assert (res[a][1] - res[bb][1]).abs().max().item() < 1e-5
 
 
+FOLD_CASES = [
+    # (N, h, w, Cin, Cout) of the LOW-RES input; output [N, 2h, 2w, Cout]
+    (2, 32, 48, 64, 64),      # 2 x 3 blocks: every tile is a border tile, corners included
+    (2, 96, 128, 128, 64),    # the C4 upconv1 shape (fewer images): interior tiles skip the border groups
+    (1, 48, 48, 64, 128),     # 9 blocks: odd count -> single-CTA kernel (halof); two phases per column tile
+    (2, 40, 56, 64, 64),      # partial blocks on the bottom / right edges
+    (1, 16, 16, 64, 64),      # one block holding all four corners
+]
+
+
+def _zero_extended_views(x):
+    """The nine operands of a folded upconv as full-size tensors: x, then its first / last row, first / last column and
+    four corner pixels with zeros everywhere else (what the kernel reads through the views' TMA bounds)."""
+    h, w = x.shape[2:]
+    out = [x]
+    for rows, cols in ((slice(0, 1), slice(None)), (slice(h - 1, h), slice(None)), (slice(None), slice(0, 1)),
+                       (slice(None), slice(w - 1, w)), (slice(0, 1), slice(0, 1)), (slice(0, 1), slice(w - 1, w)),
+                       (slice(h - 1, h), slice(0, 1)), (slice(h - 1, h), slice(w - 1, w))):
+        v = torch.zeros_like(x)
+        v[:, :, rows, cols] = x[:, :, rows, cols]
+        out.append(v)
+    return out
+
+
+@pytest.mark.parametrize("dtype", MC_DTYPES)
+@pytest.mark.parametrize("case", FOLD_CASES)
+def test_folded_upconv_matches_oracle(dtype, case):
+    """cnm_conv_desc.fold (engine.FoldedUpconvOp): Upsample(x2, bilinear) + conv3x3 + bias + ReLU as one convolution on the
+    low-res tensor.  (1) Kernel mechanics -- views, border classes, phase stores -- against the fp64 convolution of the same
+    quantised operands (the nine zero-extended sources x the folded weights), at the tolerance of every other convolution
+    test; (2) the operator itself against F.interpolate + F.conv2d in fp64 with the unrounded weights."""
+    N, h, w, cin, cout = case
+    g = torch.Generator().manual_seed(N + h * 3 + w + cin + cout)
+    x = torch.randn(N, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(cin * 9)
+    b = torch.randn(cout, generator=g)
+    act = to_act(x, dtype)
+    pf = engine.phys_factor(dtype)
+    out = torch.full((N, 2 * h, 2 * w, cout * pf), 7, dtype=engine.TORCH_DTYPE[dtype], device=dev())
+    op = engine.FoldedUpconvOp("t", act, cout, N, h, w, dtype, dev(), out)
+    assert op.backend == ("halo2f" if (N * ((h + 15) // 16) * ((w + 15) // 16)) % 2 == 0 else "halof")
+    op.load(wt, b)
+    op(_lib.stream_ptr())
+    torch.cuda.synchronize()
+    got = from_act(out, dtype)
+    big = engine.fold_upconv_weights(wt)
+    y = oracle_conv(dtype, _zero_extended_views(x), big, b.repeat(4), 3, 1)          # [N, 4 cout, h, w], phase-major
+    want = torch.empty(N, cout, 2 * h, 2 * w)
+    for ph in range(4):
+        want[:, :, (ph >> 1)::2, (ph & 1)::2] = y[:, ph * cout:(ph + 1) * cout]
+    err = (got - quantize(want, dtype)).abs()
+    assert rel_l2(got, want) < L2_TOL[dtype], (rel_l2(got, want), np.unravel_index(int(err.argmax()), err.shape))
+    assert err.max().item() < MAX_TOL[dtype] * max(1.0, want.abs().max().item())
+    xq = quantize(x, dtype).double()
+    exact = F.relu(F.conv2d(F.interpolate(xq, scale_factor=2, mode="bilinear", align_corners=False), wt.double(), b.double(),
+                            padding=1)).float()
+    assert rel_l2(got, exact) < {_lib.CNM_BF16: 6e-3, _lib.CNM_BF16X3: 5e-5, _lib.CNM_F16F8: 5e-5}[dtype]
+    # the border ring and the interior separately (a wrong border class would hide in a global norm)
+    ring = torch.ones(2 * h, 2 * w, dtype=torch.bool)
+    ring[2:-2, 2:-2] = False
+    assert rel_l2(got[..., ring], exact[..., ring]) < {_lib.CNM_BF16: 8e-3, _lib.CNM_BF16X3: 8e-5, _lib.CNM_F16F8: 8e-5}[dtype]
+
+
 def test_conv_rejects_bad_arguments():
     lib = _lib.load()
     a = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=dev())  # 48 channels: not chunk aligned

@@ -328,7 +328,7 @@ def test_cabi_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.ConvSrc) == 24 and ctypes.sizeof(_lib.ConvStep) == 32 and ctypes.sizeof(_lib.ConvDesc) == 96
+    assert ctypes.sizeof(_lib.ConvSrc) == 40 and ctypes.sizeof(_lib.ConvStep) == 32 and ctypes.sizeof(_lib.ConvDesc) == 96
 
 
 def test_shard_range_partitions():
@@ -455,3 +455,28 @@ def test_128_plane_conv1_program(halo):
     wp = engine.pack_weights(wt, cols, ch, _lib.CNM_TF32)
     got = emulate_steps([s_.buf for s_ in srcs], steps, wp, b, 1, ch, False)
     assert torch.allclose(got, want, atol=1e-9)
+
+
+def test_folded_upconv_weights_equal_upsample_then_conv():
+    """engine.fold_upconv_weights: Upsample(x2, bilinear, align_corners=False) + conv3x3(pad 1) == the sum over nine
+    zero-extended operands (x, border rows / columns, corners) of 3x3 convolutions with the folded weights, phase by phase."""
+    import torch.nn.functional as F
+    from cnmnet_b200 import engine
+    torch.manual_seed(0)
+    for h, w in ((5, 6), (2, 2), (3, 7)):
+        cout, cin = 3, 2
+        wt = torch.randn(cout, cin, 3, 3, dtype=torch.float64)
+        x = torch.randn(2, cin, h, w, dtype=torch.float64)
+        want = F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), wt, padding=1)
+        big = engine.fold_upconv_weights(wt).double().reshape(4, cout, 9, cin, 3, 3)
+        srcs = [x]
+        for rows, cols in ((slice(0, 1), slice(None)), (slice(h - 1, h), slice(None)), (slice(None), slice(0, 1)),
+                           (slice(None), slice(w - 1, w)), (slice(0, 1), slice(0, 1)), (slice(0, 1), slice(w - 1, w)),
+                           (slice(h - 1, h), slice(0, 1)), (slice(h - 1, h), slice(w - 1, w))):
+            v = torch.zeros_like(x)
+            v[:, :, rows, cols] = x[:, :, rows, cols]
+            srcs.append(v)
+        got = torch.zeros_like(want)
+        for ph in range(4):
+            got[:, :, (ph >> 1)::2, (ph & 1)::2] = sum(F.conv2d(srcs[s_], big[ph][:, s_], padding=1) for s_ in range(9))
+        assert (got - want).abs().max() < 1e-6 * want.abs().max()
