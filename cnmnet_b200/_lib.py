@@ -14,7 +14,7 @@ VOLUME_NCHW_F32, VOLUME_ACT = 0, 1
 
 
 class ConvSrc(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("ptr", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("apron", C.c_int32),
                 ("x_off", C.c_int32), ("y_off", C.c_int32), ("pitch_w", C.c_int32), ("pitch_hw", C.c_int32)]
 
 
@@ -66,6 +66,7 @@ SIGNATURES = {
     "cnm_nchw_to_act": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cnm_act_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cnm_pack_row_taps": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "cnm_pack_row_taps3": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "cnm_pack_disp_taps": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "cnm_refine_aggregate": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cnm_refine_aggregate_nchw": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

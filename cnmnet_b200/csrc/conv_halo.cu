@@ -365,15 +365,15 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         const int nt = w.tile % p.tiles_n;
         int ks0 = 0, ks1 = p.num_steps;
         if (BAL) {   // weight steps of the piece: bits 8.. of a group's ntaps field = index of its first weight step
-          if (w.g0 > 0) ks0 = __ldg(&p.groups[w.g0].ntaps) >> 8;
-          if (w.g1 < w.NG) ks1 = __ldg(&p.groups[w.g1].ntaps) >> 8;
+          if (w.g0 > 0) ks0 = (__ldg(&p.groups[w.g0].ntaps) >> 8) & 0xFFFFF;
+          if (w.g1 < w.NG) ks1 = (__ldg(&p.groups[w.g1].ntaps) >> 8) & 0xFFFFF;
         }
         if (FOLD) {   // group by group: the border groups of other tile classes are skipped, weight steps with them
           const int cls = tile_class(w.tile);
           for (int g = 0; g < w.NG; ++g) {
             const int nf = __ldg(&p.groups[g].ntaps);
             if (((nf >> 4) & 15) & ~cls) continue;
-            for (int kstep = nf >> 8; kstep < (nf >> 8) + (nf & 15); ++kstep) {
+            for (int kstep = (nf >> 8) & 0xFFFFF; kstep < ((nf >> 8) & 0xFFFFF) + (nf & 15); ++kstep) {
               mbar_wait(emptyB(sb), pb ^ 1);
               if (leader) mbar_expect_tx(fullB(sb), (uint32_t)CG * B_BYTES);
               if (CG == 2) tma2_load_2d(base + off_b + sb * B_BYTES, &p.b_map, fullB(sb), kstep * CHUNK_CH, nt * BN + (int)rank * (BN / 2));
@@ -421,6 +421,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
           const int nfield = __ldg(&p.groups[g].ntaps);
           if (FOLD && (((nfield >> 4) & 15) & ~cls)) continue;
           const int ntaps = nfield & 15;
+          const int trows = (((nfield >> 28) & 7) + 1) * 2048;   // bytes between the row windows of consecutive taps
           mbar_wait(fullA(sa), pa);
           const uint32_t slab = base + sa * p.slab_bytes + half * 8 * 2048;
           for (int t = 0; t < ntaps; ++t) {
@@ -428,7 +429,7 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
             tc_fence_after();
             if (elect_one()) {
               const uint64_t bdesc = umma_desc(base + off_b + sb * B_BYTES);
-              const uint64_t a0 = umma_desc(slab + t * 2048), a1 = umma_desc(slab + (t + 8) * 2048);
+              const uint64_t a0 = umma_desc(slab + t * trows), a1 = umma_desc(slab + t * trows + 8 * 2048);
               const bool f8 = mixed && g < (p.num_groups >> 1);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {

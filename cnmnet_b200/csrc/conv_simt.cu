@@ -201,8 +201,9 @@ int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* 
                       srcs[i].y_off + srcs[i].H <= d->Ho && srcs[i].pitch_w >= srcs[i].W && srcs[i].pitch_hw >= srcs[i].pitch_w * srcs[i].H,
                   CNM_ERR_INVALID_ARGUMENT, "%s: source %d: bad view", fn, i);
     else if (d->stride == 1)
-      CNM_REQUIRE(srcs[i].H == d->Ho && srcs[i].W == d->Wo, CNM_ERR_UNSUPPORTED_SHAPE,
-                  "%s: source %d is %dx%d, output %dx%d", fn, i, srcs[i].H, srcs[i].W, d->Ho, d->Wo);
+      CNM_REQUIRE(srcs[i].apron >= 0 && srcs[i].apron <= 4 && srcs[i].H == d->Ho + 2 * srcs[i].apron && srcs[i].W == d->Wo,
+                  CNM_ERR_UNSUPPORTED_SHAPE, "%s: source %d is %dx%d (apron %d), output %dx%d", fn, i, srcs[i].H, srcs[i].W,
+                  srcs[i].apron, d->Ho, d->Wo);
     else
       CNM_REQUIRE((srcs[i].H + 1) / 2 == d->Ho && (srcs[i].W + 1) / 2 == d->Wo, CNM_ERR_UNSUPPORTED_SHAPE,
                   "%s: stride-2 source %d is %dx%d, output %dx%d", fn, i, srcs[i].H, srcs[i].W, d->Ho, d->Wo);

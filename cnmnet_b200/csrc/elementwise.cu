@@ -106,6 +106,40 @@ __global__ void __launch_bounds__(PACK_THREADS)
   emit_rows<T>(dst + i0 * ActTraits<T>::pstride(CH), v, (int)(total - i0 < (size_t)PACK_THREADS ? total - i0 : (size_t)PACK_THREADS));
 }
 
+// three kernel rows per chunk: dst [N, H+2, W, CH], row j centred on image row j-1 (see include/cnmnet_b200.h)
+template <typename T, int KW, int CX>
+__global__ void __launch_bounds__(PACK_THREADS)
+    pack_row_taps3_kernel(const float* __restrict__ x, T* __restrict__ dst, int N, int Nsrc, int H, int W) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int CH = ActTraits<T>::CHUNK;
+  static_assert(3 * KW * CX <= CH, "three rows of taps must fit one chunk");
+  const size_t HW = (size_t)H * W, H2W = (size_t)(H + 2) * W, total = (size_t)N * H2W;
+  const size_t i0 = (size_t)blockIdx.x * PACK_THREADS, i = i0 + threadIdx.x;
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = 0.0f;
+  if (i < total) {
+    const int n = (int)(i / H2W) % Nsrc;
+    const size_t p = i % H2W;
+    const int j = (int)(p / W), xx = (int)(p % W);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int y = j - 2 + q;
+      if (y < 0 || y >= H) continue;
+      const float* row = x + (size_t)n * CX * HW + (size_t)y * W;
+#pragma unroll
+      for (int s = 0; s < KW; ++s) {
+        const int xs = xx + s - KW / 2;
+        const bool ok = xs >= 0 && xs < W;
+#pragma unroll
+        for (int c = 0; c < CX; ++c) v[(q * KW + s) * CX + c] = ok ? __ldg(row + (size_t)c * HW + xs) : 0.0f;
+      }
+    }
+  }
+  emit_rows<T>(dst + i0 * ActTraits<T>::pstride(CH), v, (int)(total - i0 < (size_t)PACK_THREADS ? total - i0 : (size_t)PACK_THREADS));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(PACK_THREADS)
     pack_disp_taps_kernel(const float* __restrict__ disp, T* __restrict__ dst, int N, int h, int w) {
@@ -621,6 +655,22 @@ extern "C" int cnm_pack_row_taps(const float* x, void* dst, int N, int Nsrc, int
   const size_t total = (size_t)N * H * W;
   DISPATCH_DTYPE(dtype, (launch_pdl(pack_row_taps_kernel<T, 7, 3>, dim3((unsigned)((total + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, x, (T*)dst, N, Nsrc, H, W)));
   return after_launch("cnm_pack_row_taps");
+}
+
+extern "C" int cnm_pack_row_taps3(const float* x, void* dst, int N, int Nsrc, int Cx, int H, int W, int kw, int dtype,
+                                  void* stream) {
+  CNM_REQUIRE(x && dst && N > 0 && Nsrc > 0 && Cx > 0 && H > 0 && W > 0, CNM_ERR_INVALID_ARGUMENT,
+              "cnm_pack_row_taps3: bad argument");
+  CNM_REQUIRE(kw == 7 && Cx == 3 && dtype != CNM_TF32, CNM_ERR_UNSUPPORTED_SHAPE,
+              "cnm_pack_row_taps3: only kw=7, Cx=3 in the 2-byte dtypes (63 of 64 channels), got kw=%d Cx=%d dtype=%d", kw, Cx, dtype);
+  const size_t total = (size_t)N * (H + 2) * W;
+  const dim3 grid((unsigned)((total + 127) / 128)), block(128);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == CNM_BF16) launch_pdl(pack_row_taps3_kernel<__nv_bfloat16, 7, 3>, grid, block, 0, s, x, (__nv_bfloat16*)dst, N, Nsrc, H, W);
+  else if (dtype == CNM_BF16X3) launch_pdl(pack_row_taps3_kernel<bf16s, 7, 3>, grid, block, 0, s, x, (bf16s*)dst, N, Nsrc, H, W);
+  else if (dtype == CNM_F16F8) launch_pdl(pack_row_taps3_kernel<h16f8, 7, 3>, grid, block, 0, s, x, (h16f8*)dst, N, Nsrc, H, W);
+  else return fail(CNM_ERR_INVALID_ARGUMENT, "cnm_pack_row_taps3: dtype %d", dtype);
+  return after_launch("cnm_pack_row_taps3");
 }
 
 extern "C" int cnm_pack_disp_taps(const float* disp, void* dst, int N, int h, int w, int dtype, void* stream) {

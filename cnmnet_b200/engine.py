@@ -27,6 +27,7 @@ HALO_MODE = os.environ.get("CNM_CONV_HALO", "auto")
 POISON = os.environ.get("CNM_POISON", "0") == "1"
 PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0" and not POISON   # activation buffers of a plan are recycled after their last reader
 FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
+DENSE_ROWTAPS = os.environ.get("CNM_DENSE_ROWTAPS", "1") != "0"   # conv1.0's image taps: three kernel rows per K-step
 PLANE_SWEEP = os.environ.get("CNM_PLANE_SWEEP", "1") != "0"   # K1 = csrc/plane_sweep.cu (TMA-staged); 0: cost_volume.cu
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
 TC_MULTICAST = os.environ.get("CNM_TC_MULTICAST", "1") != "0"   # per-tap kernel on clusters sharing the weight tiles (tcm2 / tcm4)
@@ -91,6 +92,10 @@ def fold_bn(sd, prefix, ci):
 # An operand source of a convolution.
 #   kind 'act'      full act tensor, channels [coff, coff+C) <-> weight input channels [wch, wch+C)
 #   kind 'rowtaps'  side tensor whose channel s*nreal+c holds tap s of input channel wch+c (one K-step per kernel row)
+#   kind 'rowtaps3' side tensor [N, H+2, W, chunk] (one apron row above and below the image: row j is centred on image row
+#                   j-1) whose channel (q*k + s)*nreal+c holds tap (row q-1, column s) of input channel wch+c: three kernel
+#                   rows per K-step (2-byte dtypes: 3*k*nreal <= 64), taps 3 rows apart (cnm_pack_row_taps3).  The apron
+#                   keeps the rows that are centred outside the image but reach into it.
 #   kind 'taps3x3'  side tensor whose channel 9c+3r+s holds tap (r,s) of input channel wch+c (a single K-step)
 Src = namedtuple("Src", "buf kind wch C coff nreal")
 
@@ -136,6 +141,12 @@ def make_steps(srcs, k, stride, ch, split=False):
                 for ap, wp_ in _chunk_passes(split):
                     steps.append((si, 0, 0, r - pad, _pc0(0, ap, split)))
                     cols.append(("rowtaps", s.wch, s.nreal, r, wp_, ap))
+        elif s.kind == "rowtaps3":
+            assert stride == 1 and 3 * k * s.nreal <= ch
+            for T in range((k + 2) // 3):   # kernel rows 3T .. 3T+2, read at their middle row (+1: the apron row)
+                for ap, wp_ in _chunk_passes(split):
+                    steps.append((si, 0, 0, 3 * T + 2 - pad, _pc0(0, ap, split)))
+                    cols.append(("rowtaps3", s.wch, s.nreal, T, wp_, ap))
         elif s.kind == "taps3x3":
             assert stride == 1 and k == 3 and 9 * s.nreal <= ch
             for ap, wp_ in _chunk_passes(split):
@@ -165,10 +176,18 @@ def _apart(col):
     return col[5] if len(col) > 5 else "hi"
 
 
+GROUP_TAP_STRIDE_SHIFT = 28   # cnm_conv_group.ntaps bits 28-30: rows between consecutive taps, minus one
+
+
+def group_taps(nt):
+    """(taps, rows between taps) of a group's ntaps entry as make_groups returns it."""
+    return nt & 15, ((nt >> GROUP_TAP_STRIDE_SHIFT) & 7) + 1
+
+
 def make_groups(srcs, k, ch, stride=1, split=False):
     """Row-halo K loop (csrc/conv_halo.cu): -> (groups [(map, c0 physical, dx, ntaps)], cols, map_info [12][2]).
-    One group = one slab load serving `ntaps` vertical taps; the weight steps (cols) follow group order.
-    map = src*4 + sub; map_info[map] = (rows of the slab above the tile, slab rows)."""
+    One group = one slab load serving `ntaps` vertical taps (ntaps may carry a tap stride: group_taps); the weight steps
+    (cols) follow group order.  map = src*4 + sub; map_info[map] = (rows of the slab above the tile, slab rows)."""
     pad = (k - 1) // 2
     groups, cols = [], []
     info = [[0, 0] for _ in range(12)]
@@ -202,6 +221,13 @@ def make_groups(srcs, k, ch, stride=1, split=False):
             for ap, wp_ in _chunk_passes(split):
                 groups.append((si * 4, _pc0(0, ap, split), 0, k))
                 cols += [("rowtaps", s.wch, s.nreal, r, wp_, ap) for r in range(k)]
+        elif s.kind == "rowtaps3":
+            assert stride == 1 and 3 * k * s.nreal <= ch and k >= 5
+            nT = (k + 2) // 3
+            info[si * 4] = [pad - 2, 16 + 3 * (nT - 1)]   # first tap at tensor row 2 - pad (apron included), taps 3 rows apart
+            for ap, wp_ in _chunk_passes(split):
+                groups.append((si * 4, _pc0(0, ap, split), 0, nT | (2 << GROUP_TAP_STRIDE_SHIFT)))
+                cols += [("rowtaps3", s.wch, s.nreal, T, wp_, ap) for T in range(nT)]
         elif s.kind == "taps3x3":
             assert stride == 1 and k == 3 and 9 * s.nreal <= ch
             info[si * 4] = [0, 16]
@@ -214,10 +240,10 @@ def make_groups(srcs, k, ch, stride=1, split=False):
     starts, pos = [], 0
     for g in groups:
         starts.append(pos)
-        pos += g[3]
+        pos += g[3] & 15
     gorder = _corrections_first([cols[st] for st in starts])
     groups2 = [groups[i] for i in gorder]
-    cols2 = [c for i in gorder for c in cols[starts[i]:starts[i] + groups[i][3]]]
+    cols2 = [c for i in gorder for c in cols[starts[i]:starts[i] + (groups[i][3] & 15)]]
     return groups2, cols2, info
 
 
@@ -236,6 +262,12 @@ def _gather_cols(w, cols, ch, want=None):
         elif col[0] == "rowtaps":
             _, wch, n, r = col[:4]
             wp[:, base:base + k * n] = w[:, wch:wch + n, r, :].permute(0, 2, 1).reshape(cout, k * n)
+        elif col[0] == "rowtaps3":
+            _, wch, n, T = col[:4]
+            for q in range(3):
+                if 3 * T + q < k:
+                    wp[:, base + q * k * n:base + (q + 1) * k * n] = \
+                        w[:, wch:wch + n, 3 * T + q, :].permute(0, 2, 1).reshape(cout, k * n)
         else:
             _, wch, n, _ = col[:4]
             wp[:, base:base + 9 * n] = w[:, wch:wch + n].reshape(cout, 9 * n)
@@ -383,7 +415,8 @@ class ConvOp:
             assert len(gcols) == len(cols)
             flat = [v for pr in info for v in pr]
             gt = torch.tensor(groups, dtype=torch.int32)
-            gt[:, 3] += (torch.cumsum(gt[:, 3], 0) - gt[:, 3]) << 8   # cnm_conv_group.ntaps: taps | first weight step << 8
+            taps = gt[:, 3] & 15
+            gt[:, 3] += (torch.cumsum(taps, 0) - taps) << 8   # cnm_conv_group.ntaps: taps | first weight step << 8 (| tap stride)
             self.variants["halo"] = {"cols": gcols, "groups_dev": gt.to(device),
                                      "ngroups": len(groups), "pads": (C.c_int32 * len(flat))(*flat)}
             if (N * ((Ho + 15) // 16) * ((Wo + 15) // 16)) % 2 == 0 and HALO2_ENABLED:
@@ -405,7 +438,7 @@ class ConvOp:
                                   len(srcs), self.num_steps, dtype, 0)
         arr = (_lib.ConvSrc * len(srcs))()
         for i, s in enumerate(srcs):
-            arr[i] = _lib.ConvSrc(_lib.ptr(s.buf), s.buf.shape[1], s.buf.shape[2], s.buf.shape[3], 0)
+            arr[i] = _lib.ConvSrc(_lib.ptr(s.buf), s.buf.shape[1], s.buf.shape[2], s.buf.shape[3], 1 if s.kind == "rowtaps3" else 0)
         self.srcs_arr = arr
         # issued MACs x 2, padding channels included.  CNM_F16F8: every second K-step is an fp8 row (K = 128);
         # `flops_bf16_time` weighs those at half (kind::f8f6f4 runs at twice the kind::f16 rate), i.e. it is the
@@ -930,7 +963,10 @@ class DepthNetPlan(_Plan):
         # with the fused plane sweep forced, the volume never exists: conv1.0 only needs its shape
         self.cost = _ShapeOnly((N, H, W, planes * self.pf), self.hk) if (self.may_fuse and FUSE_SWEEP == "force") \
             else self.buf(N, H, W, planes)
-        self.img_taps = self.buf(N, H, W, ch)
+        # the 3 image channels of conv1.0 as a side tensor: 7 column taps x 3 kernel rows per K-step where a chunk holds them
+        # (63 of 64 channels: 3 K-steps instead of 7), else 7 column taps per kernel row
+        self.dense_taps = DENSE_ROWTAPS and 3 * 7 * 3 <= ch
+        self.img_taps = self.buf(N, H + 2, W, ch) if self.dense_taps else self.buf(N, H, W, ch)
         self.inputs = {}
 
         def front(s):
@@ -948,8 +984,8 @@ class DepthNetPlan(_Plan):
                 _lib.check(lib.cnm_cost_volume(i["ref"], self.tex.data_ptr(), self.hk.data_ptr(), self.cost.data_ptr(),
                                                Bref, N // Bref, H, W, planes, self.idmin, self.idmax, _lib.VOLUME_ACT,
                                                dt, s), "cost_volume")
-            _lib.check(lib.cnm_pack_row_taps(i["ref"], self.img_taps.data_ptr(), N, Bref, 3, H, W, 7, dt, s),
-                       "pack_row_taps")
+            _lib.check((lib.cnm_pack_row_taps3 if self.dense_taps else lib.cnm_pack_row_taps)(
+                i["ref"], self.img_taps.data_ptr(), N, Bref, 3, H, W, 7, dt, s), "pack_row_taps")
 
         self.ops.append(front)
         self._trunk(want_logits)
@@ -957,7 +993,8 @@ class DepthNetPlan(_Plan):
     def _trunk(self, want_logits):
         N, H, W = self.N, self.H, self.W
         cv, rel = self.conv, self.release
-        x = cv("conv1.0", [self.src(self.cost, 3), Src(self.img_taps, "rowtaps", 0, self.ch, 0, 3)], 7, 1, 128, N, H, W)
+        x = cv("conv1.0", [self.src(self.cost, 3), Src(self.img_taps, "rowtaps3" if self.dense_taps else "rowtaps", 0, self.ch, 0, 3)],
+               7, 1, 128, N, H, W)
         if self.may_fuse:
             self.convs["conv1.0"].attach_sweep(0, self.Bref, self.D, self.idmin, self.idmax, self.tex, self.hk)
         rel(self.cost, self.img_taps)

@@ -175,6 +175,10 @@ int cnm_act_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
  *   (torch.cat((left_image, volume),1), depthNet_model.py:233-235).
  * cnm_pack_disp_taps: disp [N,1,h,w] fp32 -> act [N,2h,2w,chunk]; channel 3r+s holds
  *   nearest_up2(disp)[y+r-1][x+s-1] (zero outside): F.upsample + cat (depthNet_model.py:247-258). */
+/* cnm_pack_row_taps3: the denser form for the 2-byte dtypes -- dst [N, H+2, W, 64]: row j (j = 0 .. H+1, one apron row
+ * above and below the image) is centred on image row j-1 and channel (q*kw + s)*Cx + c holds x[c][j-2+q][xx+s-kw/2],
+ * q = 0..2 (zero outside the image): three kernel rows per K-step, a 7x7 layer needs 3 steps instead of 7.           */
+int cnm_pack_row_taps3(const float* x, void* dst, int N, int Nsrc, int Cx, int H, int W, int kw, int dtype, void* stream);
 int cnm_pack_row_taps(const float* x, void* dst, int N, int Nsrc, int Cx, int H, int W, int kw, int dtype,
                       void* stream);
 int cnm_pack_disp_taps(const float* disp, void* dst, int N, int h, int w, int dtype, void* stream);
@@ -230,7 +234,8 @@ int cnm_head_finish(const float* partial, int nslices, float bias, float scale, 
 typedef struct cnm_conv_src {
   const void* ptr; /* act tensor [N, H, W, C]; for a view: its first pixel */
   int32_t H, W, C;
-  int32_t reserved;
+  int32_t apron;   /* stride-1 layers: the tensor has `apron` extra rows above and below the image (H = Ho + 2 apron; row r
+                      is image row r - apron); steps and groups address TENSOR rows.  0 for ordinary sources. */
   /* View (fold layers of cnm_conv2d_halo / _halo2 only; all four 0 = the whole contiguous tensor): the source is the
    * window rows [y_off, y_off + H) x columns [x_off, x_off + W) of images that are pitch_w pixels wide and pitch_hw pixels
    * apart; every pixel outside the window reads as zero (TMA bounds).  This is how a border row / column / corner of a
@@ -309,8 +314,9 @@ int cnm_conv2d_simt(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const c
 typedef struct cnm_conv_group {
   int32_t map, c0, dx;
   int32_t ntaps; /* bits 0-3: taps of the group; bits 4-7: border class the group needs (fold layers: 1 top, 2 bottom,
-                    4 left, 8 right; 0 = every tile); bits 8..: index of the group's first weight step (= sum of the taps
-                    of the groups before it; read by the balanced and the fold schedules) */
+                    4 left, 8 right; 0 = every tile); bits 8-27: index of the group's first weight step (= sum of the taps
+                    of the groups before it; read by the balanced and the fold schedules); bits 28-30: slab rows between
+                    consecutive taps, minus one (0 = taps on consecutive rows) */
 } cnm_conv_group;
 int cnm_conv2d_halo(const cnm_conv_desc* desc, const cnm_conv_src* srcs, const int32_t* map_info,
                     const cnm_conv_group* groups, int num_groups, const void* wp, const float* bias, void* out,

@@ -335,6 +335,20 @@ def test_upsample_head_packers(dtype):
         for s in range(7):
             for c in range(3):
                 assert torch.equal(got[n, s * 3 + c], quantize(pi[n % 2, c, :, s:s + 10], dtype))
+    if dtype != _lib.CNM_TF32:
+        # the denser form: three kernel rows per chunk, one apron row above and below (row j centred on image row j - 1)
+        t3 = act_empty((4, 8, 10, ch), dtype)
+        _lib.check(lib.cnm_pack_row_taps3(im.data_ptr(), t3.data_ptr(), 4, 2, 3, 6, 10, 7, dtype, st))
+        pi3 = F.pad(img, (3, 3, 3, 3))
+        got = from_act(t3, dtype)
+        assert got.shape == (4, ch, 8, 10)
+        for n in range(4):
+            for j in range(8):
+                for q in range(3):
+                    for s in range(7):
+                        for c in range(3):
+                            assert torch.equal(got[n, (q * 7 + s) * 3 + c, j], quantize(pi3[n % 2, c, j - 2 + q + 3, s:s + 10], dtype))
+        assert float(got[:, 63].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("dtype", ALL_DTYPES)

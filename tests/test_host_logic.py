@@ -480,3 +480,35 @@ def test_folded_upconv_weights_equal_upsample_then_conv():
         for ph in range(4):
             got[:, :, (ph >> 1)::2, (ph & 1)::2] = sum(F.conv2d(srcs[s_], big[ph][:, s_], padding=1) for s_ in range(9))
         assert (got - want).abs().max() < 1e-6 * want.abs().max()
+
+
+def test_dense_rowtaps_source_reproduces_conv1():
+    """conv1.0 with the image taps packed three kernel rows per K-step (kind 'rowtaps3': side tensor with one apron row above
+    and below, what cnm_pack_row_taps3 writes): per-tap steps and row-halo groups (taps 3 rows apart) == conv2d."""
+    torch.manual_seed(14)
+    ch, N, H, W, k = 64, 1, 9, 11, 7
+    img, cost = torch.randn(N, 3, H, W), torch.randn(N, 64, H, W)
+    wt, b = torch.randn(8, 67, k, k), torch.randn(8)
+    want = nhwc(F.conv2d(torch.cat((img, cost), 1).double(), engine.round_tf32(wt).double(), b.double(), padding=3))
+    taps = torch.zeros(N, H + 2, W, ch)
+    pi = F.pad(img, (3, 3, 3, 3))            # image row y at padded row y + 3
+    for j in range(H + 2):                   # tensor row j is centred on image row j - 1
+        for q in range(3):
+            for s in range(k):
+                for c in range(3):
+                    taps[:, j, :, (q * k + s) * 3 + c] = pi[:, c, j - 2 + q + 3, s:s + W]
+    srcs = [engine.act_src(nhwc(cost), 3), engine.Src(taps, "rowtaps3", 0, ch, 0, 3)]
+    steps, cols = engine.make_steps(srcs, k, 1, ch)
+    assert len(steps) == 49 + 3
+    wp = engine.pack_weights(wt, cols, ch, _lib.CNM_TF32)
+    got = emulate_steps([s.buf for s in srcs], steps, wp, b, 1, ch, False)
+    assert torch.allclose(got, want, atol=1e-9)
+    groups, gcols, info = engine.make_groups(srcs, k, ch)
+    gsteps = []
+    for (m, c0, dx, nt) in groups:
+        taps_n, tstride = engine.group_taps(nt)
+        gsteps += [(m // 4, 0, dx, t * tstride - info[m][0], c0) for t in range(taps_n)]
+    assert len(gsteps) == len(gcols) == 52 and info[4] == [1, 22]
+    wp = engine.pack_weights(wt, gcols, ch, _lib.CNM_TF32)
+    got = emulate_steps([s.buf for s in srcs], gsteps, wp, b, 1, ch, False)
+    assert torch.allclose(got, want, atol=1e-9)
