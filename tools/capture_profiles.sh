@@ -12,6 +12,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:plan
 timeout 300 $N $F -k "regex:conv_halo2?_kernel<\(int\)64" -c 4 -f -o gpurun_out/prof_c64 python tools/profile_step.py > gpurun_out/prof_c64.log 2>&1
 timeout 300 $N $F -k "regex:conv_halo2_kernel|conv_halo_kernel" -c 6 -f -o gpurun_out/prof_halo python tools/profile_step.py > gpurun_out/ph.log 2>&1
 timeout 300 $N $F -k regex:conv_tc_kernel -c 4 -f -o gpurun_out/prof_tc python tools/profile_step.py > gpurun_out/pt.log 2>&1
+# folded upsampling (conv_halo2f: DepthNet upconv1.1, RefineNet upconv1_depth.1) and the balanced CTA-pair kernel (conv1.3, conv2.3)
+timeout 300 $N $F -k "regex:conv_halo2?f_kernel" -c 2 -f -o gpurun_out/prof_fold python tools/profile_step.py > gpurun_out/pfold.log 2>&1
+timeout 300 $N $F -k "regex:conv_halo2?b_kernel|conv_tcb_kernel" -c 2 -f -o gpurun_out/prof_bal python tools/profile_step.py > gpurun_out/pbal.log 2>&1
 timeout 300 $N $F -k "regex:upsample2x|head_partial|head_finish|pack_|refine_|plane_sweep" -c 12 -f -o gpurun_out/prof_small \
     python tools/profile_step.py > gpurun_out/psm.log 2>&1
 # the fused conv1.0 (hardware-counter sections only: ncu's SASS-patching metrics hang on a kernel that uses setmaxnreg)

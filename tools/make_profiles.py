@@ -51,7 +51,7 @@ for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
 out.append("| total | %d | %.1f | 100 %% | %.1f |" % (n, s, sum(v[2] for v in tot.values())))
 cu = sum(v[1] for k, v in tot.items() if k.startswith("conv_"))
 cm = sum(v[2] for k, v in tot.items() if k.startswith("conv_"))
-out += ["", "Convolution kernels (`conv_tc_kernel`, `conv_halo_kernel`, `conv_halo2_kernel`): %.1f us = %.1f %% of the step, "
+out += ["", "Convolution kernels (every `conv_*` kernel: per-tap, row-halo, CTA-pair, balanced `...b`, folded upsampling `...f`): %.1f us = %.1f %% of the step, "
         "%.1f MB of DRAM traffic per step." % (cu, 100 * cu / s, cm)]
 open(os.path.join(P, "%s_launches_step.md" % tag), "w").write("\n".join(out) + "\n")
 cv = [d for d in L.values() if d["name"].startswith("plane_sweep_kernel<0>")] or [d for d in L.values() if d["name"].startswith("cost_volume_kernel<16, 0>")]
@@ -113,6 +113,19 @@ if "--full" in sys.argv:
      "%s ncu --set full: conv_tc_kernel (per-tap tcgen05 conv) after the warp-uniform issue loop" % tag,
      "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 "
      "python tools/profile_step.py` (%s mode, C4 step; the layers the autotuner leaves on the per-tap kernel: small and <= 48x64 layers)." % bench.get("dtype", "f16f8"))
+if "--full" in sys.argv:
+  dump("prof_fold.ncu-rep", "%s_conv_fold_ncu.md" % tag,
+     "%s ncu --set full: conv_halo2f_kernel (bilinear x2 upsampling folded into the 3x3 convolution, cnm_conv_desc.fold)" % tag,
+     "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k \"regex:conv_halo2?f_kernel\" -c 2 "
+     "python tools/profile_step.py` (DepthNet upconv1.1: 10 x 96x128x128 -> 10 x 192x256x64 as a 256-column convolution on the "
+     "low-res tensor, and RefineNet upconv1_depth.1 at batch 5).  Compare with %s_conv_cout64_ncu.md / r02 history: the same layers as "
+     "64-column convolutions on the upsampled tensor ran the tensor pipe at 47-50 %% and moved 348 / 160 MB of DRAM traffic "
+     "each, after upsample2x launches of 253 / 96 MB." % tag)
+  dump("prof_bal.ncu-rep", "%s_conv_balanced_ncu.md" % tag,
+     "%s ncu --set full: conv_halo2b_kernel (balanced / stream-K schedule of the CTA-pair row-halo kernel)" % tag,
+     "Capture: `ncu --profile-from-start off --set full --clock-control none --import-source on -k "
+     "\"regex:conv_halo2?b_kernel|conv_tcb_kernel\" -c 2 python tools/profile_step.py` (DepthNet conv1.3 and conv2.3, the two "
+     "layers the table runs on the balanced schedule).")
 if "--full" in sys.argv:
   dump("prof_small.ncu-rep", "%s_small_kernels_ncu.md" % tag,
      "%s ncu --set full: the kernels around the convolutions (cost volume, tap packers, upsample, heads, refine aggregation)" % tag,
