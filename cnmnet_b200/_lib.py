@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
                 ("c_out_total", C.c_int32), ("c_out_offset", C.c_int32), ("stride", C.c_int32), ("relu", C.c_int32),
                 ("num_srcs", C.c_int32), ("num_steps", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32),
                 ("acc_exp", C.c_int32), ("ksplit", C.c_int32), ("cluster", C.c_int32), ("tile_h", C.c_int32), ("fold", C.c_int32), ("balance", C.c_int32), ("head_w", C.c_void_p),
-                ("head_partial", C.c_void_p), ("splitk_ws", C.c_void_p)]
+                ("head_partial", C.c_void_p), ("splitk_ws", C.c_void_p), ("side_disp", C.c_void_p), ("side_w", C.c_void_p)]
 
 
 class SweepFuse(C.Structure):

@@ -86,6 +86,8 @@ struct alignas(64) HaloParams {
   const float* head_w;   // fused 1-channel 3x3 head (BN == Cout == 64 only): [9][64] weights, or NULL
   float* head_partial;   // [Cout/64 slices][N, Ho, Wo, 12] per-pixel tap dot products, one slice per 64-channel chunk
   int Ho, Wo, cout;
+  const float* side_disp;   // 1-channel side input added in the epilogue (cnm_conv_desc.side_disp / side_w), or NULL
+  const float* side_w;      // [9][Cout]
   // balanced schedule (cnm_conv_desc.balance, BAL instantiations): see HaloWalk
   // folded bilinear x2 upsampling (cnm_conv_desc.fold, FOLD instantiations): the layer runs on the low-res tensor with
   // 4 x fold_cout output channels, one block of fold_cout per output phase (a, b); phase maps address out[2y+a][2x+b]
@@ -209,8 +211,9 @@ __device__ __forceinline__ int halo_block_class(const HaloParams& p, int m) {
   return (y0 == 0 ? 1 : 0) | (y0 + 16 >= p.Ho ? 2 : 0) | (x0 == 0 ? 4 : 0) | (x0 + 16 >= p.Wo ? 8 : 0);
 }
 
-template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16, bool BAL = false, bool FOLD = false>
+template <int BN, bool TF32, int CG, bool SWEEP = false, int TH = 16, bool BAL = false, bool FOLD = false, bool SIDE = false>
 __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
+  static_assert(!SIDE || (!TF32 && !SWEEP && !BAL && !FOLD && TH == 16), "side disparity input: plain 2-byte instantiations");
   pdl_trigger();
   constexpr int HALVES = TH / 8;
   static_assert(!FOLD || (!SWEEP && !TF32 && !BAL && TH == 16), "folded upsampling: 2-byte dtypes, 16x16 blocks, static schedule");
@@ -238,7 +241,8 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   const uint32_t off_out = off_b + (uint32_t)p.b_stages * B_BYTES;
   const uint32_t off_bias = off_out + (uint32_t)p.out_stages * HL_TILE_BYTES;
   const uint32_t off_head = off_bias + BN * 4;  // fused-head weights of the N tile [9][BN]
-  const uint32_t off_bar = off_head + (p.head_partial ? 9 * BN * 4 : 0);
+  const uint32_t off_side = off_head + (p.head_partial ? 9 * BN * 4 : 0);  // side-disparity weights of the N tile [9][BN]
+  const uint32_t off_bar = off_side + (SIDE ? 9 * BN * 4 : 0);
   const uint32_t bar0 = base + off_bar;
   auto fullA = [&](int s) { return bar0 + 8u * s; };
   auto emptyA = [&](int s) { return bar0 + 8u * (HL_MAX_A + s); };
@@ -252,7 +256,9 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
   float* zs = reinterpret_cast<float*>(base_ptr + ((off_tmem + 16 + 15) & ~15u));  // SWEEP: z_d of the D planes (16B aligned)
   float* bias_s = reinterpret_cast<float*>(base_ptr + off_bias);
   float* head_s = reinterpret_cast<float*>(base_ptr + off_head);
+  float* side_s = reinterpret_cast<float*>(base_ptr + off_side);
   const bool fused_head = !TF32 && !SWEEP && p.head_partial != nullptr;
+  constexpr bool side = SIDE;   // own instantiations: the extra epilogue state costs the others registers
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -638,6 +644,8 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
         for (int i = et; i < BN; i += 128) bias_s[i] = p.bias ? __ldg(p.bias + nt * BN + i) : 0.0f;
         if (fused_head)
           for (int i = et; i < 9 * BN; i += 128) head_s[i] = __ldg(p.head_w + (i / BN) * p.cout + nt * BN + i % BN);
+        if (side)
+          for (int i = et; i < 9 * BN; i += 128) side_s[i] = __ldg(p.side_w + (i / BN) * p.cout + nt * BN + i % BN);
         bias_tile = nt;
         epi_bar();  // epi_finalize reads bias_s right after the TMEM load, before any other barrier
       }
@@ -650,13 +658,17 @@ __device__ __forceinline__ void conv_halo_body(const HaloParams& p) {
 #pragma unroll 1
       for (int half = 0; half < HALVES; ++half) {
         const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * HALVES * BN + half * BN);
+        float sd[9];
+        if (side) side_disp_taps(p.side_disp, n0, y0 + 8 * half + (row >> 4), x0 + (row & 15), p.Ho, p.Wo, sd);
 #pragma unroll 1
         for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
           uint32_t v[COLS_PER_CHUNK];
           tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
           if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
           tmem_ld_wait();
-          epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr);
+          if (side) epi_finalize_side<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr, sd,
+                                                      side_s + ch * COLS_PER_CHUNK, BN);
+          else epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr);
           if (!TF32 && fused_head) {
             const int px = x0 + (row & 15), py = y0 + 8 * half + (row >> 4);
             if (px < p.Wo && py < p.Ho) {
@@ -731,6 +743,16 @@ __global__ void __launch_bounds__(256, 1) conv_halob_kernel(const __grid_constan
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2b_kernel(const __grid_constant__ HaloParams p) {
   conv_halo_body<BN, false, 2, false, 16, true>(p);
+}
+
+// side disparity input in the epilogue (cnm_conv_desc.side_disp), 2-byte dtypes, column tile <= 128
+template <int BN>
+__global__ void __launch_bounds__(256, 1) conv_halo_side_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, false, 1, false, 16, false, false, true>(p);
+}
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv_halo2_side_kernel(const __grid_constant__ HaloParams p) {
+  conv_halo_body<BN, false, 2, false, 16, false, false, true>(p);
 }
 
 // folded bilinear x2 upsampling (cnm_conv_desc.fold), 2-byte dtypes, column tile 128
@@ -832,6 +854,7 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
                 d->reserved, d->Cout);
     BN = d->reserved;
   }
+  if (d->side_disp && BN == 256) BN = 128;   // the SIDE instantiations: column tile <= 128
   if (fold) BN = 128;   // the FOLD instantiations: two accumulator stages, a phase block (>= 64 channels) never straddles chunks
   p.tiles_n = d->Cout / BN;
   p.groups = groups;
@@ -845,6 +868,10 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   p.range_ctr = d->dtype == CNM_F16F8 ? range_counter() : nullptr;
   p.head_w = d->head_w;
   p.head_partial = d->head_partial;
+  p.side_disp = d->side_disp;
+  p.side_w = d->side_w;
+  CNM_REQUIRE(!d->side_disp || (!sweep && !fold && !d->balance && TH == 16), CNM_ERR_UNSUPPORTED_SHAPE,
+              "%s: no side disparity input on fused-sweep / fold / balanced / 16x8-block layers", fn);
   p.Ho = d->Ho; p.Wo = d->Wo; p.cout = d->Cout;
   // smem budget: 227 KB - alignment slack - staging - bias - barriers.  Ring depths are sized to cover the loaded
   // L2 latency (~3-4k cycles): a B tile lasts 2 x 4 MMAs (1024 / 512 / 384 cycles at BN = 256 / 128 / 64), a slab
@@ -882,7 +909,8 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
     rc = encode_map(&sw.map, d->dtype, 4, sweep->scratch, dims, str, box);
     if (rc) return rc;
   }
-  const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (d->head_partial ? 9 * BN * 4 : 0) + 8 * HL_NUM_BARS + 16 +
+  const int fixed = 1024 + p.out_stages * HL_TILE_BYTES + BN * 4 + (d->head_partial ? 9 * BN * 4 : 0) + (d->side_disp ? 9 * BN * 4 : 0) +
+                    8 * HL_NUM_BARS + 16 +
                     (sweep ? HL_SWEEP_SMEM + 16 : 0);
   const int budget = 232448 - fixed;
   const int want_b = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 7 : 8));
@@ -961,6 +989,21 @@ static int conv2d_halo(const cnm_conv_desc* d, const cnm_conv_src* srcs, const i
   const int grid = CG * (total < 148 / CG ? total : 148 / CG);
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
+  if (d->side_disp) {
+    static DynSmemLimit s64, s128, s2_64, s2_128;
+    cudaError_t e;
+    if (CG == 2) e = BN == 128 ? s2_128.ensure(conv_halo2_side_kernel<128>, smem) : s2_64.ensure(conv_halo2_side_kernel<64>, smem);
+    else e = BN == 128 ? s128.ensure(conv_halo_side_kernel<128>, smem) : s64.ensure(conv_halo_side_kernel<64>, smem);
+    if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "%s: smem attribute (%d B): %s", fn, smem, cudaGetErrorString(e));
+    if (CG == 2) {
+      if (BN == 128) launch_pdl(conv_halo2_side_kernel<128>, dim3(grid), dim3(256), smem, s, p);
+      else launch_pdl(conv_halo2_side_kernel<64>, dim3(grid), dim3(256), smem, s, p);
+    } else {
+      if (BN == 128) launch_pdl(conv_halo_side_kernel<128>, dim3(grid), dim3(256), smem, s, p);
+      else launch_pdl(conv_halo_side_kernel<64>, dim3(grid), dim3(256), smem, s, p);
+    }
+    return after_launch(fn);
+  }
   if (fold) {
     static DynSmemLimit f1, f2;
     cudaError_t e = CG == 2 ? f2.ensure(conv_halo2f_kernel, smem) : f1.ensure(conv_halof_kernel, smem);

@@ -185,6 +185,9 @@ int check_conv_args(const char* fn, const cnm_conv_desc* d, const cnm_conv_src* 
   CNM_REQUIRE(!d->head_partial || (d->dtype != CNM_TF32 && ((uintptr_t)d->head_partial & 15) == 0 &&
                                    ((uintptr_t)d->head_w & 15) == 0),
               CNM_ERR_UNSUPPORTED_SHAPE, "%s: the fused head needs a 2-byte dtype and 16B-aligned buffers", fn);
+  CNM_REQUIRE((d->side_disp == nullptr) == (d->side_w == nullptr), CNM_ERR_INVALID_ARGUMENT, "%s: side_disp and side_w go together", fn);
+  CNM_REQUIRE(!d->side_disp || (d->dtype != CNM_TF32 && d->ksplit <= 1 && d->Ho % 2 == 0 && d->Wo % 2 == 0 && ((uintptr_t)d->side_w & 15) == 0),
+              CNM_ERR_UNSUPPORTED_SHAPE, "%s: the side disparity input needs a 2-byte dtype, no split-K, an even output size and 16B-aligned weights", fn);
   const int ch = chunk_channels(d->dtype);
   CNM_REQUIRE(d->Cout % ch == 0 && d->c_out_total % ch == 0 && d->c_out_offset % ch == 0 &&
                   d->c_out_offset + phys_factor(d->dtype) * (fold ? d->Cout / 4 : d->Cout) <= d->c_out_total,
@@ -221,6 +224,7 @@ extern "C" int cnm_conv2d_simt(const cnm_conv_desc* d, const cnm_conv_src* srcs,
                                const void* wp, const float* bias, void* out, void* stream) {
   int rc = check_conv_args("cnm_conv2d_simt", d, srcs, steps, wp, out);
   if (rc) return rc;
+  CNM_REQUIRE(!d->side_disp, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_simt: no side disparity input (list it as a taps source instead)");
   CNM_REQUIRE(!d->head_partial && d->ksplit <= 1, CNM_ERR_UNSUPPORTED_SHAPE,
               "cnm_conv2d_simt: no fused head / split-K in the validation twin");
   SimtParams p{};

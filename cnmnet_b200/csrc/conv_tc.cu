@@ -61,6 +61,8 @@ struct alignas(64) TcParams {
   int cout;
   long long* dbg;   // CNM_CONV_TIMELINE=1: clock64 stamps of CTA 0 (tools/conv_timeline.py), else NULL
   // balanced mode (cnm_conv_desc.balance, BAL instantiations): see TcWalk
+  const float* side_disp;   // 1-channel side input added in the epilogue (cnm_conv_desc.side_disp / side_w), or NULL
+  const float* side_w;      // [9][Cout]; read through L1 (the layers that matter run the row-halo kernels)
   float* bal_slots;  // [gridDim.x][128][BN] fp32 raw accumulators of the contributor pieces
   int* bal_flags;    // [gridDim.x] 1 = the CTA's contributor piece is in its slot (reset by the tile's finishing CTA)
 };
@@ -127,8 +129,9 @@ struct TcSmem {
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;  // + slack for manual 1024 B alignment
 };
 
-template <int BN, int STAGES, bool TF32, int CL, bool BAL = false>
+template <int BN, int STAGES, bool TF32, int CL, bool BAL = false, bool SIDE = false>
 __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
+  static_assert(!SIDE || (!TF32 && CL == 1 && !BAL), "side disparity input: plain 2-byte instantiations");
   static_assert(!BAL || CL == 1, "balanced schedule: single CTAs");
   using L = TcSmem<BN, STAGES, TF32>;
   const bool stamp = p.dbg != nullptr && blockIdx.x == 0;
@@ -164,6 +167,7 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
   float* bias_s = reinterpret_cast<float*>(base_ptr + L::OFF_BIAS);
   float* head_s = reinterpret_cast<float*>(base_ptr + L::OFF_HEAD);
   const bool fused_head = !TF32 && p.head_partial != nullptr;
+  constexpr bool side = SIDE;   // own instantiations: the extra epilogue state costs the others registers
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -357,13 +361,20 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
         balance_gather(tmem_row, BN, p.bal_slots, p.bal_flags, (int)blockIdx.x + 1, 1, ncontrib, base_ptr, gather_bar,
                        gather_phase, row, leader);
       if (stamp && et == 0 && it == 0) p.dbg[9] = clock64();
+      float sd[9];
+      if (side) {
+        const int px = x0 + row % p.TW, py = y0 + (row / p.TW) % p.TH, pn = n0 + row / (p.TW * p.TH);
+        side_disp_taps(p.side_disp, pn < p.N ? pn : p.N - 1, py, px, p.Ho, p.Wo, sd);
+      }
 #pragma unroll 1
       for (int ch = 0; ch < NUM_CHUNKS; ++ch) {
         uint32_t v[COLS_PER_CHUNK];
         tmem_ld32(tmem_row + ch * COLS_PER_CHUNK, v);
         if (!TF32) tmem_ld32(tmem_row + ch * COLS_PER_CHUNK + 32, v + 32);
         tmem_ld_wait();
-        epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr);
+        if (side) epi_finalize_side<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr, sd,
+                                                    p.side_w + nt * BN + ch * COLS_PER_CHUNK, p.cout);
+        else epi_finalize<COLS_PER_CHUNK>(v, bias_s + ch * COLS_PER_CHUNK, p.relu, p.acc_scale, p.range_ctr);
         if (!TF32 && fused_head) {
           const int px = x0 + row % p.TW, py = y0 + (row / p.TW) % p.TH, pn = n0 + row / (p.TW * p.TH);
           if (px < p.Wo && py < p.Ho && pn < p.N) {
@@ -410,6 +421,11 @@ __device__ __forceinline__ void conv_tc_body(const TcParams& p) {
 template <int BN, int STAGES, bool TF32>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   conv_tc_body<BN, STAGES, TF32, 1>(p);
+}
+// side disparity input in the epilogue (cnm_conv_desc.side_disp), 2-byte dtypes
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_side_kernel(const __grid_constant__ TcParams p) {
+  conv_tc_body<BN, STAGES, false, 1, false, true>(p);
 }
 // balanced (stream-K) schedule, 2-byte dtypes
 template <int BN, int STAGES>
@@ -514,6 +530,16 @@ static int launch_tc(const TcParams& p, int grid, cudaStream_t s) {
 }
 
 template <int BN, int STAGES>
+static int launch_tc_side(const TcParams& p, int grid, cudaStream_t s) {
+  using L = TcSmem<BN, STAGES, false>;
+  static DynSmemLimit limit;
+  cudaError_t e = limit.ensure(conv_tc_side_kernel<BN, STAGES>, L::TOTAL);
+  if (e != cudaSuccess) return fail(CNM_ERR_CUDA, "cnm_conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+  launch_pdl(conv_tc_side_kernel<BN, STAGES>, dim3(grid), dim3(TC_THREADS), L::TOTAL, s, p);
+  return after_launch("cnm_conv2d_tc");
+}
+
+template <int BN, int STAGES>
 static int launch_tcb(const TcParams& p, int grid, cudaStream_t s) {
   using L = TcSmem<BN, STAGES, false>;
   static DynSmemLimit limit;
@@ -609,6 +635,8 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   p.range_ctr = d->dtype == CNM_F16F8 ? range_counter() : nullptr;
   p.head_w = d->head_w;
   p.head_partial = d->head_partial;
+  p.side_disp = d->side_disp;
+  p.side_w = d->side_w;
   p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo;
   p.ksplit = d->ksplit > 1 ? d->ksplit : 1;
   p.ws = d->splitk_ws;
@@ -680,6 +708,12 @@ extern "C" int cnm_conv2d_tc(const cnm_conv_desc* d, const cnm_conv_src* srcs, c
   cudaStream_t s = (cudaStream_t)stream;
   const bool tf32 = d->dtype == CNM_TF32;  // the 2-byte modes share the kind::f16 instantiations
   const int CL = d->cluster > 1 ? d->cluster : 1;
+  if (d->side_disp) {
+    CNM_REQUIRE(!balance && CL == 1, CNM_ERR_UNSUPPORTED_SHAPE, "cnm_conv2d_tc: no side disparity input on balanced / cluster launches");
+    if (BN == 256) return launch_tc_side<256, 4>(p, grid, s);
+    if (BN == 128) return launch_tc_side<128, 6>(p, grid, s);
+    return launch_tc_side<64, 7>(p, grid, s);
+  }
   if (balance) {
     // equal K ranges for all SMs; at least 8 K-steps per CTA
     const long long T = (long long)m_tiles * p.tiles_n * d->num_steps;

@@ -156,6 +156,42 @@ __device__ __forceinline__ void epi_finalize(uint32_t* v, const float* bs, int r
   if (range_ctr && over) atomicAdd(range_ctr, 1ULL);
 }
 
+// Side disparity input (cnm_conv_desc.side_disp / side_w): the nine taps of the nearest-upsampled disparity around this
+// thread's pixel (zero outside the image), then value = relu(acc * scale + bias + sum_t d[t] * w[t][c]).
+__device__ __forceinline__ void side_disp_taps(const float* __restrict__ disp, int n, int py, int px, int Ho, int Wo, float* d) {
+  const int h = Ho >> 1, w = Wo >> 1;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int yy = py + r - 1, xx = px + s - 1;
+      d[3 * r + s] = (yy >= 0 && yy < Ho && xx >= 0 && xx < Wo) ? __ldg(disp + ((size_t)n * h + (yy >> 1)) * w + (xx >> 1)) : 0.0f;
+    }
+}
+template <int COLS>
+__device__ __forceinline__ void epi_finalize_side(uint32_t* v, const float* bs, int relu, float scale, unsigned long long* range_ctr,
+                                                  const float* d, const float* w, int wstride) {
+  bool over = false;
+#pragma unroll
+  for (int c = 0; c < COLS; c += 4) {
+    float t[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) t[e] = fmaf(__uint_as_float(v[c + e]), scale, bs[c + e]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w + k * wstride + c);
+      t[0] = fmaf(d[k], w4.x, t[0]); t[1] = fmaf(d[k], w4.y, t[1]); t[2] = fmaf(d[k], w4.z, t[2]); t[3] = fmaf(d[k], w4.w, t[3]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float u = relu ? fmaxf(t[e], 0.0f) : t[e];
+      over |= !(fabsf(u) <= 65504.0f);
+      v[c + e] = __float_as_uint(u);
+    }
+  }
+  if (range_ctr && over) atomicAdd(range_ctr, 1ULL);
+}
+
 // epi_store_row: the finalised values of one chunk -> one 128-byte row of the 128B-swizzled staging tile.
 // mode 0: plain bf16 / tf32 row.  mode 1 (CNM_BF16X3): part 0 = bf16 hi row, part 1 = bf16 lo row.
 // mode 2 (CNM_F16F8): part 0 = fp16 row, part 1 = fp8 row [lo8 x 64 | hi8 x 64].

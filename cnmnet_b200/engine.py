@@ -28,6 +28,12 @@ POISON = os.environ.get("CNM_POISON", "0") == "1"
 PLAN_REUSE = os.environ.get("CNM_PLAN_REUSE", "1") != "0" and not POISON   # activation buffers of a plan are recycled after their last reader
 FUSE_HEADS = os.environ.get("CNM_FUSE_HEADS", "1") != "0"   # 64-channel heads in the producing conv's epilogue
 DENSE_ROWTAPS = os.environ.get("CNM_DENSE_ROWTAPS", "1") != "0"   # conv1.0's image taps: three kernel rows per K-step
+# iconv3 / iconv2 / iconv1: the upsampled disparity enters in the epilogue, in fp32 on unrounded values (cnm_conv_desc.side_disp),
+# instead of as a 64-channel side tensor + K-step.  Exact and tested, saves 165 MB of buffers per lane at C4 -- and is NOT
+# faster (tools/ab_step.py: +1.6 % step time on all three layers, +-0 on iconv3 / iconv2 only: 576 extra FMAs per pixel and 64
+# output channels in an epilogue that the Cout = 64 layer cannot hide), so it is opt-in: CNM_SIDE_DISP=1.
+SIDE_DISP = os.environ.get("CNM_SIDE_DISP", "0") == "1"
+SIDE_DISP_MIN_CIN = int(os.environ.get("CNM_SIDE_DISP_MIN_CIN", "64"))   # layers with at least this many input channels
 PLANE_SWEEP = os.environ.get("CNM_PLANE_SWEEP", "1") != "0"   # K1 = csrc/plane_sweep.cu (TMA-staged); 0: cost_volume.cu
 HALO2_ENABLED = os.environ.get("CNM_CONV_HALO2", "1") != "0"   # CTA-pair (cta_group::2) variant as a tuning candidate
 TC_MULTICAST = os.environ.get("CNM_TC_MULTICAST", "1") != "0"   # per-tap kernel on clusters sharing the weight tiles (tcm2 / tcm4)
@@ -498,7 +504,7 @@ class ConvOp:
         # at step level (bench.py, CNM_FUSE_SWEEP=force) and entered into the table by hand if it wins
         mc = [be for be in ("tcm2", "tcm4") if be in self.variants]
         out += [(be, bn, 1) for be in mc for bn in (256, 128) if d.Cout % bn == 0]
-        if SPLITK and "tc" in self.variants and not getattr(self, "_head", None):
+        if SPLITK and "tc" in self.variants and not getattr(self, "_head", None) and not getattr(self, "_side", None):
             tw = 16 if d.Wo >= 16 else 8
             th = min(128 // tw, 1 << max(d.Ho - 1, 0).bit_length())
             nb = 128 // (tw * th)
@@ -559,6 +565,20 @@ class ConvOp:
             self.select("halo2s", d.Cout)
         return True
 
+    def attach_side_disp(self, disp, wch):
+        """Input channel `wch` of the layer is the nearest-upsampled 1-channel disparity `disp` [N, 1, Ho/2, Wo/2] fp32
+        (depthNet_model.py:247-258): it is not among the operand sources; the kernels add its nine taps to the fp32
+        accumulator in the epilogue (cnm_conv_desc.side_disp / side_w).  2-byte dtypes, tensor-core kernels."""
+        d = self.desc
+        assert self.dtype != CNM_TF32 and tuple(disp.shape) == (d.N, 1, d.Ho // 2, d.Wo // 2) and disp.dtype == torch.float32
+        self._side = (disp, wch)
+        self.side_w = torch.zeros((9, d.Cout), dtype=torch.float32, device=self.out.device)
+        d.side_disp, d.side_w = disp.data_ptr(), self.side_w.data_ptr()
+        # variants that cannot take it: balanced schedules, 16x8 blocks, multicast clusters
+        for be in ("tcb", "halob", "halo2b", "halo2h", "tcm2", "tcm4"):
+            self.variants.pop(be, None)
+        self.key = self.key[:-1] + ", 'side')"   # its own rows in the variant table
+
     def fuse_head(self, w_tap_major, partial):
         """Fused 1-channel 3x3 head on this layer's output (cnm_conv_desc.head_w [9][Cout] / head_partial [Cout/64 slices])."""
         assert self.dtype != CNM_TF32
@@ -571,6 +591,9 @@ class ConvOp:
             self.desc.acc_exp = f16f8_weight_exp(wf)
         self.wp.copy_(pack_weights(wf.to(self.wp.device), self.cols, chunk_channels(self.dtype), self.dtype))
         self.bias.copy_(bf.to(self.bias.device))
+        if getattr(self, "_side", None):
+            cout = wf.shape[0]
+            self.side_w.copy_(wf[:, self._side[1]].reshape(cout, 9).t().to(self.side_w.device))
 
     def __call__(self, stream):
         lib = _lib.load()
@@ -896,6 +919,20 @@ class _Plan:
             raise ValueError("head output must be a contiguous fp32 tensor of shape %s" % (tuple(hw["out"].shape),))
         hw["out"] = out
 
+    def iconv(self, name, srcs, disp, wch, cout, N, Ho, Wo):
+        """iconv3 / iconv2 / iconv1 of DepthNet (depthNet_model.py:247-260): conv3x3 over cat(srcs, nearest-upsampled
+        disparity `disp`); the disparity is input channel `wch`.  Tensor-core plans in the 2-byte modes add its nine taps in
+        the epilogue, in fp32 (ConvOp.attach_side_disp); the others list them as a 64-channel side tensor."""
+        cin = sum(s.C for s in srcs)
+        if SIDE_DISP and self.dtype != CNM_TF32 and self.backend != "simt" and cin >= SIDE_DISP_MIN_CIN:
+            y = self.conv(name, srcs, 3, 1, cout, N, Ho, Wo)
+            self.convs[name].attach_side_disp(disp, wch)
+            return y
+        t = self.disp_taps(disp)
+        y = self.conv(name, srcs + [Src(t, "taps3x3", wch, self.ch, 0, 1)], 3, 1, cout, N, Ho, Wo)
+        self.release(t)
+        return y
+
     def disp_taps(self, disp):
         N, _, h, w = disp.shape
         out = self.buf(N, 2 * h, 2 * w, self.ch)
@@ -1020,22 +1057,17 @@ class DepthNetPlan(_Plan):
         iconv4 = cv("iconv4.0", [self.src(up4, 0), self.src(conv3, 512)], 3, 1, 512, N, H // 8, W // 8)
         rel(up4, conv3)
         self.disp4, l4 = self.head("disp4", iconv4, self.scale, want_logits)
-        t4 = self.disp_taps(self.disp4)
         up3 = self.upconv("upconv3.1", iconv4, 256, N, H // 4, W // 4)
-        iconv3 = cv("iconv3.0", [self.src(up3, 0), self.src(conv2, 256), Src(t4, "taps3x3", 512, self.ch, 0, 1)], 3, 1,
-                    256, N, H // 4, W // 4)
-        rel(up3, conv2, t4)
+        iconv3 = self.iconv("iconv3.0", [self.src(up3, 0), self.src(conv2, 256)], self.disp4, 512, 256, N, H // 4, W // 4)
+        rel(up3, conv2)
         self.disp3, l3 = self.head("disp3", iconv3, self.scale, want_logits)
-        t3 = self.disp_taps(self.disp3)
         up2 = self.upconv("upconv2.1", iconv3, 128, N, H // 2, W // 2)
-        iconv2 = cv("iconv2.0", [self.src(up2, 0), self.src(conv1, 128), Src(t3, "taps3x3", 256, self.ch, 0, 1)], 3, 1,
-                    128, N, H // 2, W // 2)
-        rel(up2, conv1, t3)
+        iconv2 = self.iconv("iconv2.0", [self.src(up2, 0), self.src(conv1, 128)], self.disp3, 256, 128, N, H // 2, W // 2)
+        rel(up2, conv1)
         self.disp2, l2 = self.head("disp2", iconv2, self.scale, want_logits)
-        t2 = self.disp_taps(self.disp2)
         up1 = self.upconv("upconv1.1", iconv2, 64, N, H, W)
-        self.iconv1 = cv("iconv1.0", [self.src(up1, 0), Src(t2, "taps3x3", 64, self.ch, 0, 1)], 3, 1, 64, N, H, W)
-        rel(up1, t2)
+        self.iconv1 = self.iconv("iconv1.0", [self.src(up1, 0)], self.disp2, 64, 64, N, H, W)
+        rel(up1)
         self.disp1, l1 = self.head("disp1", self.iconv1, self.scale, want_logits)
         self.logits = [l1, l2, l3, l4]
         self.tune()

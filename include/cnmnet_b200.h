@@ -293,6 +293,14 @@ typedef struct cnm_conv_desc {
   const float* head_w;
   float* head_partial;
   float* splitk_ws; /* [ksplit][N*Ho*Wo][Cout] fp32 workspace (device, 16B aligned) when ksplit > 1, else NULL */
+  /* Optional 1-channel side input added in the epilogue: the nearest-upsampled disparity that depthNet_model.py:247-258
+   * concatenates to the inputs of iconv3 / iconv2 / iconv1.  side_disp = [N, 1, Ho/2, Wo/2] fp32 (Ho, Wo even), side_w =
+   * [9][Cout] fp32 tap-major = the BN-folded 3x3 weights of that input channel (16B aligned).  Before bias-ReLU the layer
+   * adds sum_{r,s} side_w[3r+s][c] * up(side_disp)(y+r-1, x+s-1), up = nearest x2, zero outside the image -- in fp32, on
+   * unrounded disparities, instead of spending a 64-channel K-step (and a 64-channel side tensor) on nine scalars per
+   * pixel.  Tensor-core kernels, 2-byte dtypes, ksplit <= 1.  Both NULL = none.                                       */
+  const float* side_disp;
+  const float* side_w;
 } cnm_conv_desc;
 
 int64_t cnm_conv_balance_ws_bytes(void);

@@ -439,6 +439,50 @@ def test_folded_upconv_matches_oracle(dtype, case):
     assert rel_l2(got[..., ring], exact[..., ring]) < {_lib.CNM_BF16: 8e-3, _lib.CNM_BF16X3: 8e-5, _lib.CNM_F16F8: 8e-5}[dtype]
 
 
+@pytest.mark.parametrize("dtype", MC_DTYPES)
+@pytest.mark.parametrize("backend,case,bn", [
+    ("halo", (2, 32, 48, [64], 64), 64),            # iconv1 kind: one source
+    ("halo2", (2, 32, 48, [64, 64], 128), 128),     # iconv2 kind: two sources, CTA pairs
+    ("halo2", (2, 32, 48, [64], 64), 64),
+    ("halo", (1, 40, 56, [64, 64], 256), 0),        # library-chosen tile (256 -> 128 for side layers), partial blocks
+    ("tc", (3, 8, 12, [64], 128), 128),             # small map: per-tap kernel, images packed into one tile
+    ("tc", (2, 32, 48, [64], 256), 256),
+])
+def test_side_disparity_input_matches_oracle(dtype, backend, case, bn):
+    """cnm_conv_desc.side_disp / side_w (ConvOp.attach_side_disp): the nearest-upsampled 1-channel disparity as an input
+    channel of a 3x3 layer, added in the epilogue in fp32 -- against the fp64 convolution of the quantised operands plus the
+    fp64 convolution of the unrounded upsampled disparity, before bias-ReLU."""
+    N, H, W, cins, cout = case
+    g = torch.Generator().manual_seed(N + H + W + cout + sum(cins))
+    xs = [torch.randn(N, c, H, W, generator=g) for c in cins]
+    disp = torch.rand(N, 1, H // 2, W // 2, generator=g) * 3.0
+    ctot = sum(cins)
+    w = torch.randn(cout, ctot + 1, 3, 3, generator=g) / np.sqrt((ctot + 1) * 9)
+    w[:, ctot] *= 0.5                                     # the largest weight (-> f16f8 scale) stays among the act channels
+    b = torch.randn(cout, generator=g)
+    acts = [to_act(x, dtype) for x in xs]
+    srcs = [engine.act_src(a, sum(cins[:i]), phys=engine.phys_factor(dtype)) for i, a in enumerate(acts)]
+    op = engine.ConvOp("t", srcs, 3, 1, cout, N, H, W, dtype, dev(), True, backend=backend)
+    op.tunable = False
+    dd = disp.to(dev())
+    op.attach_side_disp(dd, ctot)
+    op.select(backend, bn)
+    op.load(w, b)
+    op.out.fill_(7)
+    op(_lib.stream_ptr())
+    torch.cuda.synchronize()
+    got = from_act(op.out, dtype)
+    # oracle: the layer without the disparity channel, pre-activation, on the quantised operands of the mode ...
+    wmain = w.clone()
+    wmain[:, ctot] = 0                                    # keeps the mode's weight scale (acc_exp) identical
+    pre = oracle_conv(dtype, xs + [torch.zeros(N, 1, H, W)], wmain, b, 3, 1, relu=False).double()
+    # ... plus the disparity channel exactly
+    ud = F.interpolate(disp.double(), scale_factor=2, mode="nearest")
+    want = F.relu(pre + F.conv2d(ud, w[:, ctot:ctot + 1].double(), padding=1)).float()
+    assert rel_l2(got, want) < L2_TOL[dtype], rel_l2(got, want)
+    assert (got - quantize(want, dtype)).abs().max().item() < MAX_TOL[dtype] * max(1.0, want.abs().max().item())
+
+
 def test_conv_rejects_bad_arguments():
     lib = _lib.load()
     a = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=dev())  # 48 channels: not chunk aligned

@@ -437,3 +437,29 @@ def test_range_check_counts_fp16_overflow():
     finally:
         lib.cnm_set_range_check(0)
     assert lib.cnm_range_overflow_count(0) == -1
+
+
+@pytest.mark.parametrize("switch,value", [("SIDE_DISP", True), ("FOLD_UPSAMPLE", False), ("DENSE_ROWTAPS", False),
+                                           ("FOLD_MIN_BLOCKS", 2)])
+def test_pipeline_matches_oracle_with_layer_program_switches(monkeypatch, switch, value):
+    """The alternative layer programs behind engine switches -- disparity input in the epilogue (CNM_SIDE_DISP=1), upsample2x
+    + conv3x3 instead of the folded upconv, one kernel row of image taps per K-step, folded upconv on small maps (every
+    tile a border tile) -- give the same depth as the oracle, within the tolerance of the default program."""
+    from cnmnet_b200 import engine
+    monkeypatch.setattr(engine, switch, value)
+    B, H, W, V = 2, 96, 160, 2
+    ref, srcs, ref_cam, src_cams = synth.frame_tuples(77, B, H, W, V)
+    dsd = synth.kaiming_state(onets.state_shapes(onets.DEPTHNET_LAYERS), 51, 0.02)
+    rsd = synth.kaiming_state(onets.state_shapes(onets.REFINENET_LAYERS), 52, 0.02)
+    pipe = _fresh_pipeline(dsd, rsd, graph=False)
+    d, n, p = pipe(ref.to(dev()), srcs.to(dev()), ref_cam.to(dev()), src_cams.to(dev()))
+    st = pipe.static_state(B, V, H, W, dev())
+    kinds = {op.backend for op in list(st["dplan"].convs.values()) + list(st["rplan"].convs.values())}
+    if switch == "FOLD_MIN_BLOCKS":
+        assert "halo2f" in kinds or "halof" in kinds
+    if switch == "SIDE_DISP":
+        assert st["dplan"].convs["iconv1.0"].desc.side_disp
+    want_d, want_n, want_p = _oracle_pipeline(dsd, rsd, ref, srcs, ref_cam, src_cams, 3.0, 9)
+    rel = np.abs(d.cpu().numpy() - want_d) / np.abs(want_d)
+    assert rel.max() < 1e-3 and np.percentile(rel, 99) < 3e-4 and rel.mean() < 1e-4, (rel.max(), np.percentile(rel, 99), rel.mean())
+    assert np.abs(p.cpu().numpy() - want_p).max() < 2e-3

@@ -328,7 +328,7 @@ def test_cabi_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.ConvSrc) == 40 and ctypes.sizeof(_lib.ConvStep) == 32 and ctypes.sizeof(_lib.ConvDesc) == 96
+    assert ctypes.sizeof(_lib.ConvSrc) == 40 and ctypes.sizeof(_lib.ConvStep) == 32 and ctypes.sizeof(_lib.ConvDesc) == 112
 
 
 def test_shard_range_partitions():
