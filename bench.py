@@ -285,6 +285,15 @@ def reference_gpu_block(dev, host, reps=5):
     return out
 
 
+def _kernel_census(st):
+    """Which convolution kernel variant runs how many layers of the step (engine.ConvOp names: tc per-tap, halo / halo2 row-halo
+    on one CTA / a CTA pair, ...b balanced (stream-K) schedule, halo2f / halof bilinear x2 upsampling folded in)."""
+    kinds = {}
+    for op in list(st["dplan"].convs.values()) + list(st["rplan"].convs.values()):
+        kinds[op.backend] = kinds.get(op.backend, 0) + 1
+    return kinds
+
+
 def time_events(fn, reps, flush):
     """Average device time of fn() over reps, CUDA events on the current stream, L2 flushed between reps."""
     ts = []
@@ -508,7 +517,8 @@ def main():
                    "timing": "value / ms_per_step: K isolated steps, one batch in flight, device events per step; e2e: the "
                              "streaming API with host buffers and %d batch(es) in flight (lanes), which is why it can exceed "
                              "value; two_lane_resident_ms_per_step is the same overlap with resident inputs" % lanes,
-                   "cuda_graph": True, "precision_note": PRECISION_NOTES[args.precision]},
+                   "cuda_graph": True, "precision_note": PRECISION_NOTES[args.precision],
+                   "conv_kernels": _kernel_census(st)},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "lanes": lanes},

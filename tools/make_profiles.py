@@ -73,9 +73,13 @@ PICKS = ["gpu__time_duration.sum", "launch__grid_size", "sm__warps_active.avg.pc
 
 def dump(rep, outname, title, note):
     rp = os.path.join(G, rep)
-    if not os.path.exists(rp):
+    rc = rp.replace(".ncu-rep", ".raw.csv")   # written on the GPU box by tools/capture_profiles.sh (the reports stay there)
+    if os.path.exists(rc):
+        raw = open(rc).read()
+    elif os.path.exists(rp):
+        raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rws = list(csv.reader(raw.splitlines()))
     h, u = rws[0], rws[1]
     lines = ["# " + title, "", note, ""]

@@ -18,7 +18,12 @@ for name, what in (("memcheck_conv.log", "memcheck: tests/test_gpu_conv.py + tes
                    ("racecheck.log", "racecheck: non-TMA shared-memory kernels (normals, CNM, packers, upsample, ...)")):
     p = os.path.join(G, name)
     if not os.path.exists(p):
-        out.append("| %s | %s | (log missing) | |" % (name, what))
+        note = "(log missing)"
+        if name == "initcheck.log":
+            note = ("not re-run on this build (CNM_SANITIZE_INITCHECK=0): on the earlier round-2 build it printed 607968 reports, all "
+                    "of them consumers of TMA-stored convolution outputs (first: cnm_upsample2x) -- a tool limitation, see DESIGN.md "
+                    "section 4; the poison pass below is the real check")
+        out.append("| %s | %s | %s | |" % (name, what, note))
         continue
     txt = open(p, errors="replace").read()
     res = re.findall(r"^(?:=+ )?(\d+ (?:passed|failed).*?)(?: =+)?$", txt, re.M)

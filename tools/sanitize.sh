@@ -25,6 +25,8 @@ tail -3 gpurun_out/memcheck_conv.log
 timeout 1800 compute-sanitizer --tool memcheck --print-limit 10 \
     python -m pytest tests/test_gpu_nets.py -m gpu -q -k "not headline and not bit_identical" > gpurun_out/memcheck_nets.log 2>&1
 tail -3 gpurun_out/memcheck_nets.log
+rm -f gpurun_out/initcheck.log
+if [ "${CNM_SANITIZE_INITCHECK:-1}" = "1" ]; then   # ~10 GPU-minutes for a report that only restates the tool's blind spot
 timeout 600 compute-sanitizer --tool initcheck --print-limit 300 \
     python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/initcheck_full.log 2>&1
 # keep the log small: the summary lines, smoke()'s own line and a tally of the flagged kernels (Host Frame = the C entry)
@@ -32,8 +34,9 @@ timeout 600 compute-sanitizer --tool initcheck --print-limit 300 \
   grep -oE "Host Frame: ?cnm_[a-z0-9_]+" gpurun_out/initcheck_full.log | sort | uniq -c; } > gpurun_out/initcheck.log
 rm -f gpurun_out/initcheck_full.log
 tail -12 gpurun_out/initcheck.log
+fi
 CNM_POISON=1 timeout 900 python -m pytest tests/test_gpu_nets.py tests/test_gpu_fused_sweep.py -m gpu -q \
-    -k "pipeline_matches_oracle or odd_pyramid or 128_planes or fused or C1" > gpurun_out/poison.log 2>&1
+    -k "pipeline_matches_oracle or odd_pyramid or 128_planes or fused or C1 or layer_program_switches" > gpurun_out/poison.log 2>&1
 CNM_POISON=1 CNM_FUSE_SWEEP=force timeout 600 python -m pytest tests/test_gpu_nets.py -m gpu -q \
     -k "pipeline_matches_oracle and f16f8" >> gpurun_out/poison.log 2>&1
 tail -4 gpurun_out/poison.log
