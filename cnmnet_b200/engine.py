@@ -631,6 +631,7 @@ class ConvOp:
 # taps, corners one -- 2-D operator = (A + dR) x (A + dC) = AxA + dRxA + AxdC + dRxdC.
 FOLD_UPSAMPLE = os.environ.get("CNM_FOLD_UPSAMPLE", "1") != "0"
 FOLD_MIN_BLOCKS = int(os.environ.get("CNM_FOLD_MIN_BLOCKS", "6"))   # low-res blocks (16 px) per side from which folding pays
+FOLD_PAIRS = os.environ.get("CNM_FOLD_PAIRS", "1") != "0"   # CTA pairs (halo2f) where the block count is even, else single CTAs (halof)
 _FOLD_A = (((.75, .25, 0.), (.25, .75, .75), (0., 0., .25)), ((.25, 0., 0.), (.75, .75, .25), (0., .25, .75)))
 _FOLD_T = ((-.25, .25, 0.), (.25, 0., 0.))
 _FOLD_B = ((0., 0., .25), (0., .25, -.25))
@@ -707,7 +708,7 @@ class FoldedUpconvOp(ConvOp):
         for m in range(9):
             info[m] = [1, 18] if m in (0, 3, 4) else [0, 16]
         flat = [v for pr in info for v in pr]
-        pairs_ok = (N * ((h + 15) // 16) * ((w + 15) // 16)) % 2 == 0 and HALO2_ENABLED
+        pairs_ok = (N * ((h + 15) // 16) * ((w + 15) // 16)) % 2 == 0 and HALO2_ENABLED and FOLD_PAIRS
         self.backend = "halo2f" if pairs_ok else "halof"
         self.variants = {self.backend: {"cols": gcols, "groups_dev": gt.to(device), "ngroups": len(groups),
                                         "pads": (C.c_int32 * len(flat))(*flat)}}
