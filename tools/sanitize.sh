@@ -19,6 +19,8 @@ mkdir -p gpurun_out
 git rev-parse HEAD > gpurun_out/sanitize_head.txt 2>/dev/null || echo "snapshot (no .git on the box)" > gpurun_out/sanitize_head.txt
 date -u +%Y-%m-%dT%H:%M:%SZ >> gpurun_out/sanitize_head.txt
 sha256sum cnmnet_b200/libcnmnet_b200.so >> gpurun_out/sanitize_head.txt
+# the library is not bit-reproducible across builds; the sources are what ties the logs to a commit
+echo "$(cat cnmnet_b200/csrc/*.cu cnmnet_b200/csrc/*.cuh include/*.h | sha256sum | cut -d' ' -f1)  cnmnet_b200/csrc/*.cu *.cuh include/*.h (concatenated)" >> gpurun_out/sanitize_head.txt
 timeout 1200 compute-sanitizer --tool memcheck --print-limit 10 \
     python -m pytest tests/test_gpu_conv.py tests/test_gpu_kernels.py -m gpu -q > gpurun_out/memcheck_conv.log 2>&1
 tail -3 gpurun_out/memcheck_conv.log
