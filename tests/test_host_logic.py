@@ -512,3 +512,135 @@ def test_dense_rowtaps_source_reproduces_conv1():
     wp = engine.pack_weights(wt, gcols, ch, _lib.CNM_TF32)
     got = emulate_steps([s.buf for s in srcs], gsteps, wp, b, 1, ch, False)
     assert torch.allclose(got, want, atol=1e-9)
+
+
+def test_folded_upconv_program_reproduces_operator():
+    """engine.FoldedUpconvOp's device program, emulated on the CPU exactly as csrc/conv_halo.cu (FOLD) walks it: per 16x16
+    block (pairs: the union class of two blocks), every group whose border class the tile has, its slab = a window of the
+    source VIEW (zeros outside the view's extent), `taps` row windows against consecutive weight steps, phase scatter.
+    Must equal Upsample(x2, bilinear) + conv3x3 with the (bf16-rounded) folded weights."""
+    torch.manual_seed(21)
+    N, h, w, cin, cout = 2, 40, 48, 64, 64
+    dt = _lib.CNM_BF16
+    x = torch.randn(N, h, w, cin).to(torch.bfloat16)
+    out = torch.zeros(N, 2 * h, 2 * w, cout, dtype=torch.bfloat16)
+    op = engine.FoldedUpconvOp("t", x, cout, N, h, w, dt, "cpu", out)
+    wt, b = torch.randn(cout, cin, 3, 3) / 24.0, torch.randn(cout)
+    op.load(wt, b)
+    v = op.variants[op.backend]
+    groups = v["groups_dev"].tolist()
+    pads = list(v["pads"])
+    wp = op.wp.double()                                  # [4 cout, steps * 64]
+    xs = x.double()
+    srcs = op.srcs_arr
+    pix = x.shape[3] * x.element_size()
+
+    def view_window(m, n, y_lo, x_lo, rows, cols):
+        """rows x cols window of source m starting at full-image coordinates (y_lo, x_lo); zeros outside the view."""
+        s = srcs[m]
+        off = (s.ptr - x.data_ptr()) // pix                # first pixel of the view inside image 0
+        vy0, vx0 = off // w, off % w
+        assert (vx0, vy0) == (s.x_off, s.y_off) and (m == 0 or (s.pitch_w, s.pitch_hw) == (w, h * w))
+        o = torch.zeros(rows, cols, cin, dtype=torch.float64)
+        for r in range(rows):
+            for c in range(cols):
+                vy, vx = y_lo + r - s.y_off, x_lo + c - s.x_off    # coordinates inside the view
+                if 0 <= vy < s.H and 0 <= vx < s.W:
+                    o[r, c] = xs[n, vy + vy0, vx + vx0]
+        return o
+
+    def block_class(ty, tx):
+        return (1 if ty == 0 else 0) | (2 if ty * 16 + 16 >= h else 0) | (4 if tx == 0 else 0) | (8 if tx * 16 + 16 >= w else 0)
+
+    tiles_x, tiles_y = (w + 15) // 16, (h + 15) // 16
+    got = torch.zeros(N, 2 * h, 2 * w, cout, dtype=torch.float64)
+    pairs = op.backend == "halo2f"
+    blocks = [(n, ty, tx) for n in range(N) for ty in range(tiles_y) for tx in range(tiles_x)]
+    executed = set()
+    for bi, (n, ty, tx) in enumerate(blocks):
+        cls = block_class(ty, tx)
+        if pairs:
+            pn, pty, ptx = blocks[bi ^ 1]
+            cls |= block_class(pty, ptx)
+        y0, x0 = ty * 16, tx * 16
+        acc = torch.zeros(16, 16, 4 * cout, dtype=torch.float64)
+        for m, c0, dx, nf in groups:
+            taps, flags, first = nf & 15, (nf >> 4) & 15, (nf >> 8) & 0xFFFFF
+            if flags & ~cls:
+                continue
+            executed.add(flags)
+            pad, rows = pads[2 * m], pads[2 * m + 1]
+            slab = view_window(m, n, y0 - pad, x0 + dx, rows, 16)          # one TMA box {64, 16, rows}
+            for t in range(taps):
+                a = slab[t:t + 16, :, c0:c0 + 64]
+                acc += a @ wp[:, (first + t) * 64:(first + t + 1) * 64].T
+        for ph in range(4):
+            blk = acc[:, :, ph * cout:(ph + 1) * cout] + b.double()
+            ys = [2 * (y0 + r) + (ph >> 1) for r in range(16) if y0 + r < h]
+            xs_ = [2 * (x0 + c) + (ph & 1) for c in range(16) if x0 + c < w]
+            got[n][ys[0]:ys[-1] + 1:2, xs_[0]:xs_[-1] + 1:2] = blk[:len(ys), :len(xs_)]
+    assert executed == {0, 1, 2, 4, 8, 5, 9, 6, 10}          # every border class ran somewhere
+    big = engine.fold_upconv_weights(wt).to(torch.bfloat16).double()       # what pack_weights stored
+    xn = xs.permute(0, 3, 1, 2)
+    want = torch.zeros(N, cout, 2 * h, 2 * w, dtype=torch.float64)
+    zs = [xn]
+    for rows, cols in ((slice(0, 1), slice(None)), (slice(h - 1, h), slice(None)), (slice(None), slice(0, 1)),
+                       (slice(None), slice(w - 1, w)), (slice(0, 1), slice(0, 1)), (slice(0, 1), slice(w - 1, w)),
+                       (slice(h - 1, h), slice(0, 1)), (slice(h - 1, h), slice(w - 1, w))):
+        z = torch.zeros_like(xn)
+        z[:, :, rows, cols] = xn[:, :, rows, cols]
+        zs.append(z)
+    for ph in range(4):
+        y = sum(F.conv2d(zs[s_], big[ph * cout:(ph + 1) * cout, s_ * cin:(s_ + 1) * cin], padding=1) for s_ in range(9))
+        want[:, :, (ph >> 1)::2, (ph & 1)::2] = y + b.double().view(1, -1, 1, 1)
+    assert torch.allclose(got.permute(0, 3, 1, 2), want, atol=1e-9)
+    # ... and that is the operator: Upsample + conv3x3 with the unrounded weights, to bf16 weight rounding
+    exact = F.conv2d(F.interpolate(xn, scale_factor=2, mode="bilinear", align_corners=False), wt.double(), b.double(), padding=1)
+    assert (want - exact).abs().max() < 2e-2 * exact.abs().max()
+
+
+def _balanced_segments(tiles, S, G):
+    """Python mirror of TcWalk / HaloWalk (csrc/conv_tc.cu, conv_halo.cu) in balanced mode: CTA c -> [(tile, k0, k1)]."""
+    T = tiles * S
+    out = []
+    for c in range(G):
+        pos, end, segs = T * c // G, T * (c + 1) // G, []
+        while pos < end:
+            tile = pos // S
+            k0 = pos - tile * S
+            k1 = min(S, k0 + end - pos)
+            segs.append((tile, k0, k1))
+            pos += k1 - k0
+        out.append(segs)
+    return out
+
+
+@pytest.mark.parametrize("tiles,S,G", [(120, 144, 148), (240, 72, 74), (960, 98, 74), (20, 144, 148), (74, 36, 74), (1, 300, 148)])
+def test_balanced_schedule_partition(tiles, S, G):
+    """The stream-K partition the balanced kernels walk: every (tile, K-step) exactly once; a CTA has at most one contributor
+    piece (k0 > 0) and it comes first, at most one head piece (k0 == 0, k1 < S) and it comes last; the contributors of a
+    tile are the CTAs right after its head CTA, in order -- what the head CTA's epilogue assumes when it gathers."""
+    segs = _balanced_segments(tiles, S, G)
+    cover = {}
+    for c, ss in enumerate(segs):
+        kinds = ["contrib" if k0 > 0 else ("head" if k1 < S else "whole") for (_, k0, k1) in ss]
+        assert kinds.count("contrib") <= 1 and kinds.count("head") <= 1
+        if "contrib" in kinds:
+            assert kinds[0] == "contrib"
+        if "head" in kinds:
+            assert kinds[-1] == "head"
+        for (t, k0, k1) in ss:
+            assert 0 <= k0 < k1 <= S
+            cover.setdefault(t, []).append((k0, k1, c))
+    assert sorted(cover) == list(range(tiles))
+    T = tiles * S
+    for t, pieces in cover.items():
+        pieces.sort()
+        assert pieces[0][0] == 0 and pieces[-1][1] == S and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        head = pieces[0][2]
+        assert [p_[2] for p_ in pieces] == list(range(head, head + len(pieces)))
+        # the kernel's contributor count: CTAs after the head whose range starts before the tile ends
+        n = 0
+        while T * (head + 1 + n) // G < (t + 1) * S:
+            n += 1
+        assert n == len(pieces) - 1
